@@ -1,0 +1,130 @@
+"""Generate the golden vectors under tests/golden/ by RUNNING THE UNMODIFIED REFERENCE.
+
+Run in the build container (where /root/reference is mounted):
+
+    python tests/golden/make_golden.py
+
+It calls the reference's own ``FSAGRUScorer.compute_beta_per_sample`` (scorers.py:692-751),
+``compute_beta_parallel`` (:753-856) and ``Estimators.iwae`` (estimatros.py:32-44, with
+``WFSTScorer`` scorers.py:1663-1687 as the model and ``Sampler`` samplers.py:137-335 as the
+proposal) through ``oracle/ref_harness.py`` and stores inputs + outputs as small ``.npz``
+fixtures.  The fixtures are committed; the GPU box never needs the reference.
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+
+from oracle import ref_harness as rh  # noqa: E402
+from tests.lattice_gen import PAD, chain_with_skips, random_mark_lattice  # noqa: E402
+
+OUT = os.path.dirname(os.path.abspath(__file__))
+V, H = 24, 8
+
+
+def params_of(m):
+    return dict(
+        emb=m.embeddings.weight.detach().double().numpy(),
+        Wx=m.Wx.detach().double().numpy(),
+        Wh=m.Wh.detach().double().numpy(),
+        W=m.W.detach().double().numpy(),
+        bias=m.beta_bias.detach().double().numpy(),
+    )
+
+
+def gen_per_sample():
+    """float64 runs of compute_beta_per_sample: Wh=0 (log-semiring bridge) and Wh!=0."""
+    rng = np.random.default_rng(20260101)
+    cases = []
+    for i, n_inner in enumerate([1, 2, 3, 5, 8, 12, 17, 25, 40]):
+        cases.append(random_mark_lattice(rng, n_inner, V, parallel_arcs=False)[1])
+    for n_inner in [6, 15, 30]:
+        cases.append(random_mark_lattice(rng, n_inner, V, parallel_arcs=True)[1])
+    cases.append(chain_with_skips(60, V)[1])
+    out = {"n_cases": np.int64(len(cases)), "vocab": np.int64(V), "hid": np.int64(H)}
+    m0 = rh.make_scorer(H, V, seed=11, zero_wh=True, double=True)
+    m1 = rh.make_scorer(H, V, seed=12, zero_wh=False, double=True)
+    out["theta0"] = rh.arc_theta(m0).numpy()
+    for k, v in params_of(m1).items():
+        out["p1_" + k] = v
+    with rh.default_dtype(torch.float64), torch.no_grad():
+        for i, tr in enumerate(cases):
+            t = torch.from_numpy(tr).int()
+            out[f"tr_{i}"] = tr
+            out[f"beta0_{i}"] = m0.compute_beta_per_sample(t).numpy()  # real space, float64
+            out[f"beta1_{i}"] = m1.compute_beta_per_sample(t).numpy()
+    np.savez_compressed(os.path.join(OUT, "beta_per_sample.npz"), **out)
+    print("beta_per_sample.npz:", len(cases), "cases")
+
+
+def gen_parallel():
+    """float32 runs of the batched compute_beta_parallel on collate-padded batches (Q5),
+    lattices without parallel arcs (Q4); k=2 exercises repeat_interleave (:854)."""
+    from oracle.lattice_oracle import collate_pad
+
+    rng = np.random.default_rng(20260202)
+    out = {"vocab": np.int64(V), "hid": np.int64(H), "k": np.int64(2)}
+    m0 = rh.make_scorer(H, V, seed=21, zero_wh=True, double=False)
+    out["theta0"] = rh.arc_theta(m0).double().numpy()
+    batches = [[4, 9, 6], [7, 7, 2, 11]]
+    out["n_batches"] = np.int64(len(batches))
+    for bi, sizes in enumerate(batches):
+        tabs = [random_mark_lattice(rng, n, V, parallel_arcs=False)[1] for n in sizes]
+        tr = collate_pad(tabs, PAD)
+        em = collate_pad([t != 0 for t in tabs], PAD)  # bool array padded with pad id -> True
+        with torch.no_grad():
+            m0.set_masks(emission=torch.from_numpy(em), transition=torch.from_numpy(tr))
+            m0.set_k(2)
+            beta = m0.compute_beta()  # [B*k, S] float32 real space
+        out[f"tr_{bi}"] = tr
+        out[f"n_states_{bi}"] = np.array([t.shape[0] for t in tabs], dtype=np.int64)
+        out[f"beta_{bi}"] = beta.numpy()
+    np.savez_compressed(os.path.join(OUT, "beta_parallel.npz"), **out)
+    print("beta_parallel.npz:", len(batches), "batches")
+
+
+def gen_iwae():
+    """The reference's importance-sampling estimate of the log-marginal with an
+    arc-factored model (WFSTScorer) -- a statistical pin for the exact logZ.  The sampler
+    consumes bos as its initial input (scorers.py:230-231), so the estimate targets
+    logZ - theta[bos]."""
+    ns = rh.load()
+    rng = np.random.default_rng(20260303)
+    out = {"vocab": np.int64(V)}
+    m = rh.make_scorer(H, V, seed=31, zero_wh=True, double=False)
+    theta = rh.arc_theta(m).double().numpy()
+    out["theta"] = theta
+    th_t = torch.from_numpy(theta).float()
+    model = ns.WFSTScorer(ns.pad, ns.bos, ns.eos, scorer=lambda t: th_t[t])
+    sampler = ns.Sampler(m)
+    sizes = [5, 10]
+    out["n_cases"] = np.int64(len(sizes))
+    k, reps = 512, 12
+    for i, n in enumerate(sizes):
+        em, tr = random_mark_lattice(rng, n, V, parallel_arcs=False)
+        sampler.set_masks(transition=torch.from_numpy(tr)[None], emission=torch.from_numpy(em)[None])
+        ests = []
+        for r in range(reps):
+            torch.manual_seed(1000 * i + r)
+            with torch.no_grad():
+                est, _, _, _ = ns.Estimators.iwae(sampler, model, 1, k, 0, query_args=None)
+            ests.append(float(est[0]))
+        out[f"tr_{i}"] = tr
+        out[f"iwae_{i}"] = np.asarray(ests)
+    out["k"] = np.int64(k)
+    np.savez_compressed(os.path.join(OUT, "iwae.npz"), **out)
+    print("iwae.npz:", len(sizes), "cases")
+
+
+if __name__ == "__main__":
+    if not rh.available():
+        raise SystemExit("reference not mounted; golden vectors can only be regenerated in the build container")
+    gen_per_sample()
+    gen_parallel()
+    gen_iwae()
