@@ -1,0 +1,171 @@
+/*
+ * nfst_b200.h -- C ABI of the B200 (sm_100a) lattice dynamic-programming library.
+ *
+ * Drop-in boundary for the one hot path of steventan0110/nFST that this repository
+ * accelerates: dynamic programming over batched, acyclic, CSR-packed mark lattices.
+ * Plain C: raw device pointers, explicit sizes, a CUDA stream handle; no C++ or torch
+ * types cross this boundary.  The library never allocates or frees device memory and
+ * keeps no pointer after a call returns; everything is enqueued on the caller's stream
+ * and nothing synchronises with the host.
+ *
+ * Reference interfaces replaced (file:line in steventan0110/nFST):
+ *   nfst_fwd_f32            log-semiring forward pass (alpha, logZ).  No counterpart in
+ *                           the reference; mirror image of the beta pass below.
+ *   nfst_bwd_fused_f32      FSAGRUScorer.compute_beta_per_sample / compute_beta_parallel
+ *                           (src/modules/scorers.py:692-751, :753-856) in the Wh=0 regime,
+ *                           i.e. beta[c] = sum_{c-j->n} exp(theta_j) beta[n] in log space;
+ *                           fused with arc posteriors (the autograd gradient of logZ that
+ *                           the reference cannot produce, quirk Q7), the per-label
+ *                           gradient d logZ / d theta (WFSTScorer, scorers.py:1663-1687)
+ *                           and the tropical-semiring Viterbi recursion + backpointers.
+ *   nfst_backtrace          best-path read-out; replaces best-of-k-samples selection
+ *                           (src/modules/lightning.py:474-479) reached from
+ *                           src/decode/decoder.py:77-79.
+ *   nfst_beta_to_dense_f32  layout of compute_beta()'s return value, real-space
+ *                           beta[B*k, S] (scorers.py:854, :858-875).
+ *   nfst_dense_count_arcs / nfst_dense_extract_arcs
+ *                           the dense-table edge rule `t != 0 and t != i`
+ *                           (scorers.py:704-716, :764-776) over collate()-padded
+ *                           transition[B,S,V] int64 tables (util/dataset_reader.py:175-186).
+ *
+ * Every entry point returns 0 on success or a negative nfst_status; a human-readable
+ * message for the last failure on the calling thread is at nfst_last_error_string().
+ */
+#ifndef NFST_B200_H_
+#define NFST_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NFST_ABI_VERSION 1
+
+typedef enum nfst_status {
+  NFST_OK = 0,
+  NFST_ERR_BAD_ARG = -1,
+  NFST_ERR_CUDA = -2,
+  NFST_ERR_UNSUPPORTED_DEVICE = -3,
+  NFST_ERR_TOO_LARGE = -4
+} nfst_status;
+
+/*
+ * A batch of packed lattices (all arrays are DEVICE pointers, int32 unless noted).
+ *
+ * States of every lattice are renumbered so that they are contiguous per lattice and,
+ * inside a lattice, sorted by topological level (longest distance from the start
+ * state); ids below are these global packed ids.  Arcs are stored twice:
+ *   "out" order (canonical arc id): sorted by (source state, label) -- CSR by source;
+ *        this is the dense-table scan order of the reference (state, then label).
+ *   "in" order: sorted by (destination state, canonical id) -- CSR by destination.
+ * Lattice b has levels 0..L_b-1; level l spans packed states
+ *   [ level_ptr[level_off[b]+l], level_ptr[level_off[b]+l+1] ).
+ */
+typedef struct nfst_packed_lattices {
+  int32_t n_lattices; /* B */
+  int32_t n_states;   /* S: total packed states */
+  int32_t n_arcs;     /* A: total packed arcs   */
+  int32_t vocab;      /* V: labels are in [0, V) */
+  const int32_t* state_off;   /* [B+1] */
+  const int32_t* level_off;   /* [B+1] offsets into level_ptr (lattice b owns L_b+1 entries) */
+  const int32_t* level_ptr;   /* [sum_b (L_b+1)] */
+  const int32_t* start_state; /* [B] packed id of the start state (reference row 0) */
+  const int32_t* sink_off;    /* [B+1] */
+  const int32_t* sinks;       /* packed ids of states without outgoing arcs, grouped by lattice */
+  const int32_t* in_ptr;      /* [S+1] */
+  const int32_t* src_in;      /* [A] source state of the arc at each in-order position */
+  const int32_t* label_in;    /* [A] */
+  const int32_t* in2out;      /* [A] canonical arc id of each in-order position */
+  const int32_t* out_ptr;     /* [S+1] */
+  const int32_t* dst_out;     /* [A] destination state of each canonical arc */
+  const int32_t* label_out;   /* [A] */
+  const uint8_t* lanes_in_log2;  /* [B] log2 of lanes cooperating on one state, forward  */
+  const uint8_t* lanes_out_log2; /* [B] same, backward */
+} nfst_packed_lattices_t;
+
+/*
+ * One kernel launch = one thread block per lattice in `lattice_ids` (NULL = lattices
+ * 0..n_ids-1).  `state_smem_cap` > 0 keeps the per-state DP vectors of a lattice in
+ * shared memory (must be >= the largest lattice of the launch, in states); 0 keeps them
+ * in global memory.  `level_smem_cap` likewise stages the level table (0 = read it from
+ * global memory).
+ */
+typedef struct nfst_launch {
+  const int32_t* lattice_ids;
+  int32_t n_ids;
+  int32_t block_threads;  /* multiple of 32, <= 1024 */
+  int32_t state_smem_cap;
+  int32_t level_smem_cap;
+} nfst_launch_t;
+
+/* Arc scores: w(a) = (arc_scores ? arc_scores[a] : 0) + (theta ? theta[label(a)] : 0);
+ * arc_scores is indexed by canonical arc id. */
+typedef struct nfst_scores {
+  const float* arc_scores; /* [A] or NULL */
+  const float* theta;      /* [V] or NULL */
+} nfst_scores_t;
+
+int nfst_abi_version(void);
+const char* nfst_last_error_string(void);
+
+/* Fails with NFST_ERR_UNSUPPORTED_DEVICE unless `device` is compute capability 10.x.
+ * Any of the out pointers may be NULL. */
+int nfst_device_info(int device, int* sm_count, int* cc_major, int* cc_minor, size_t* max_smem_optin);
+
+/* Dynamic shared memory a launch needs (bytes). n_state_arrays: 1 for fwd, 1 (log or
+ * tropical) or 2 (both) for bwd.  with_theta/with_dtheta: V floats each when V <=
+ * NFST_THETA_SMEM_MAX. */
+#define NFST_THETA_SMEM_MAX 4096
+size_t nfst_launch_smem_bytes(const nfst_launch_t* launch, int32_t vocab, int n_state_arrays, int with_theta,
+                              int with_dtheta);
+
+/* alpha[S] (log space), logz[B] = logsumexp over the lattice's sinks of alpha. */
+int nfst_fwd_f32(const nfst_packed_lattices_t* lat, const nfst_launch_t* launch, const nfst_scores_t* scores,
+                 float* alpha, float* logz, void* cuda_stream);
+
+/*
+ * Fused backward.  Any output may be NULL, with these constraints:
+ *   log semiring  : enabled when beta != NULL.  beta[S] (log space), logz_bwd[B] = beta[start].
+ *       post[A]   : needs alpha and logz from nfst_fwd_f32; post[a] = g_b * exp(alpha[src] + w
+ *                   + beta[dst] - logz[b]) with g_b = grad_logz[b] (1 when grad_logz == NULL).
+ *       dtheta[V] : needs alpha/logz; atomically accumulates sum of post[a] by label
+ *                   (caller zero-fills).
+ *   tropical      : enabled when delta != NULL.  delta[S], backptr[S] (canonical arc id, -1
+ *                   at sinks), vit_score[B] = delta[start].  delta[s] = max_a fl32(w_a +
+ *                   delta[dst_a]); ties -> smallest canonical arc id (= smallest label).
+ */
+int nfst_bwd_fused_f32(const nfst_packed_lattices_t* lat, const nfst_launch_t* launch, const nfst_scores_t* scores,
+                       const float* alpha, const float* logz, const float* grad_logz, float* beta, float* logz_bwd,
+                       float* post, float* dtheta, float* delta, int32_t* backptr, float* vit_score,
+                       void* cuda_stream);
+
+/* Tropical pass only (thin wrapper over nfst_bwd_fused_f32). */
+int nfst_viterbi_f32(const nfst_packed_lattices_t* lat, const nfst_launch_t* launch, const nfst_scores_t* scores,
+                     float* delta, int32_t* backptr, float* vit_score, void* cuda_stream);
+
+/* Follow backptr from each start state.  path_arcs[path_off[b] .. path_off[b]+path_len[b])
+ * receives canonical arc ids; capacity of lattice b is path_off[b+1]-path_off[b] (L_b-1
+ * always suffices). */
+int nfst_backtrace(const nfst_packed_lattices_t* lat, const int32_t* backptr, const int32_t* path_off,
+                   int32_t* path_arcs, int32_t* path_len, void* cuda_stream);
+
+/* out[(b*k+j)*dense_states + orig_state[s]] = exp(beta[s]) for j < k; `out` must be
+ * zero-filled by the caller (states that were trimmed at pack time keep 0). */
+int nfst_beta_to_dense_f32(const nfst_packed_lattices_t* lat, const float* beta, const int32_t* orig_state,
+                           int32_t k, int32_t dense_states, float* out, void* cuda_stream);
+
+/* Dense-table edge rule.  transition is int64 [n_rows = B*S, V] row-major, row r belongs
+ * to state r % S.  count: row_counts[r] = #cells with t != 0 && t != r % S.  extract:
+ * given exclusive prefix sums row_start[r], writes (row, label, dst) in scan order. */
+int nfst_dense_count_arcs(const int64_t* transition, int64_t n_rows, int32_t states_per_lattice, int32_t vocab,
+                          int32_t* row_counts, void* cuda_stream);
+int nfst_dense_extract_arcs(const int64_t* transition, int64_t n_rows, int32_t states_per_lattice, int32_t vocab,
+                            const int64_t* row_start, int32_t* arc_row, int32_t* arc_label, int32_t* arc_dst,
+                            void* cuda_stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NFST_B200_H_ */

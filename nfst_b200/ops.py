@@ -1,0 +1,250 @@
+"""PyTorch operator surface over the C ABI (include/nfst_b200.h).
+
+Mirrors what the reference's modules ask of the lattice:
+
+* ``LatticeLogPartition`` / ``lattice_log_partition`` -- exact log-marginal ``[B]`` of an
+  arc-factored model, the quantity ``Estimators.iwae`` estimates by importance sampling
+  (``src/modules/estimatros.py:32-44`` via ``lightning.py:408-440``); its autograd
+  gradient w.r.t. the arc scores is the arc posterior (which the reference's own DP cannot
+  provide: autograd through ``scorers.py:744-747`` raises, quirk Q7).
+* ``lattice_forward_backward`` -- (logZ, alpha, beta, posteriors).
+* ``lattice_viterbi`` -- best path; replaces best-of-k-samples (``lightning.py:474-479``).
+* ``compute_beta`` -- real-space ``beta[B*k, S]`` with the layout of
+  ``FSAGRUScorer.compute_beta`` (``scorers.py:854,858-875``).
+
+Torch is used for device memory and streams only; all arithmetic runs in the library's
+sm_100a kernels.  CPU tensors are rejected -- there is no fallback.
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+from .pack import LaunchGroup, PackedLattices, pack_dense
+
+# number of library kernels launched since import (bench.py reports the per-step count)
+launch_count = 0
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _check_f32(name: str, t: Optional[torch.Tensor], n: int, dev: torch.device) -> Optional[torch.Tensor]:
+    if t is None:
+        return None
+    if t.device != dev:
+        raise RuntimeError(f"{name} must live on {dev} (nfst_b200 has no CPU fallback), got {t.device}")
+    if t.numel() != n:
+        raise ValueError(f"{name} must have {n} elements, got {t.numel()}")
+    return t.detach().to(torch.float32).contiguous()
+
+
+def _launch(g: LaunchGroup, n_state_arrays_in_smem: bool = True) -> "_lib.LaunchC":
+    c = _lib.LaunchC()
+    c.lattice_ids = g.ids.data_ptr()
+    c.n_ids = g.n
+    c.block_threads = g.block_threads
+    c.state_smem_cap = g.state_cap
+    c.level_smem_cap = g.level_cap
+    return c
+
+
+def _scores(packed: PackedLattices, arc_scores, theta):
+    dev = packed.device
+    a = _check_f32("arc_scores", arc_scores, packed.n_arcs, dev)
+    if packed.static_scores is not None:
+        a = packed.static_scores if a is None else (a + packed.static_scores)
+    t = _check_f32("theta", theta, packed.vocab, dev)
+    c = _lib.ScoresC()
+    c.arc_scores = _ptr(a)
+    c.theta = _ptr(t)
+    return c, (a, t)  # keep the tensors alive for the duration of the call
+
+
+def _stream(dev) -> int:
+    return torch.cuda.current_stream(dev).cuda_stream
+
+
+def lattice_forward(packed: PackedLattices, arc_scores=None, theta=None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """alpha[S] (log space, packed state order) and logZ[B]."""
+    global launch_count
+    lib = _lib.load()
+    dev = packed.device
+    sc, keep = _scores(packed, arc_scores, theta)
+    alpha = torch.empty(packed.n_states, dtype=torch.float32, device=dev)
+    logz = torch.empty(packed.n_lattices, dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        st = _stream(dev)
+        for g in packed.groups:
+            lc = _launch(g)
+            _lib.check(lib.nfst_fwd_f32(packed.c_struct(), lc, sc, alpha.data_ptr(), logz.data_ptr(), st))
+            launch_count += 1
+    del keep
+    return alpha, logz
+
+
+def lattice_backward(
+    packed: PackedLattices,
+    arc_scores=None,
+    theta=None,
+    *,
+    alpha: Optional[torch.Tensor] = None,
+    logz: Optional[torch.Tensor] = None,
+    grad_logz: Optional[torch.Tensor] = None,
+    want_beta: bool = True,
+    want_post: bool = False,
+    want_dtheta: bool = False,
+    want_viterbi: bool = False,
+):
+    """Fused backward pass.  Returns a dict with the requested outputs among
+    ``beta[S]``, ``logz_bwd[B]``, ``post[A]``, ``dtheta[V]``, ``delta[S]``, ``backptr[S]``,
+    ``vit_score[B]``."""
+    global launch_count
+    lib = _lib.load()
+    dev = packed.device
+    sc, keep = _scores(packed, arc_scores, theta)
+    S, A, B, V = packed.n_states, packed.n_arcs, packed.n_lattices, packed.vocab
+    logs = want_beta or want_post or want_dtheta
+    out = {}
+    f32 = dict(dtype=torch.float32, device=dev)
+    beta = torch.empty(S, **f32) if logs else None
+    logz_bwd = torch.empty(B, **f32) if logs else None
+    post = torch.empty(A, **f32) if want_post else None
+    dtheta = torch.zeros(V, **f32) if want_dtheta else None
+    delta = torch.empty(S, **f32) if want_viterbi else None
+    backptr = torch.empty(S, dtype=torch.int32, device=dev) if want_viterbi else None
+    vit = torch.empty(B, **f32) if want_viterbi else None
+    if (want_post or want_dtheta) and (alpha is None or logz is None):
+        raise ValueError("posteriors need alpha and logz from lattice_forward")
+    g32 = _check_f32("grad_logz", grad_logz, B, dev)
+    with torch.cuda.device(dev):
+        st = _stream(dev)
+        for g in packed.groups:
+            lc = _launch(g)
+            _lib.check(
+                lib.nfst_bwd_fused_f32(
+                    packed.c_struct(), lc, sc, _ptr(alpha), _ptr(logz), _ptr(g32), _ptr(beta), _ptr(logz_bwd),
+                    _ptr(post), _ptr(dtheta), _ptr(delta), _ptr(backptr), _ptr(vit), st,
+                )
+            )
+            launch_count += 1
+    del keep
+    for k, v in (("beta", beta), ("logz_bwd", logz_bwd), ("post", post), ("dtheta", dtheta), ("delta", delta),
+                 ("backptr", backptr), ("vit_score", vit)):
+        if v is not None:
+            out[k] = v
+    return out
+
+
+def lattice_forward_backward(packed: PackedLattices, arc_scores=None, theta=None, *, want_dtheta: bool = False):
+    """(logZ[B], alpha[S], beta[S], post[A]) -- plus dtheta[V] when ``want_dtheta``.
+
+    logZ is ``beta[start]`` (the reference's definition, ``log beta[0]``); posteriors are
+    normalised with the forward logZ and agree to fp32 round-off."""
+    alpha, logz_f = lattice_forward(packed, arc_scores, theta)
+    r = lattice_backward(packed, arc_scores, theta, alpha=alpha, logz=logz_f, want_beta=True, want_post=True,
+                         want_dtheta=want_dtheta)
+    if want_dtheta:
+        return r["logz_bwd"], alpha, r["beta"], r["post"], r["dtheta"]
+    return r["logz_bwd"], alpha, r["beta"], r["post"]
+
+
+class LatticeLogPartition(torch.autograd.Function):
+    """logZ[B] = log sum over start->sink paths of exp(sum of arc scores).
+
+    ``arc_scores`` ([A], canonical arc order of ``packed``) and/or ``theta`` ([V], score of
+    an arc = theta[label], the reference's WFSTScorer parametrisation, scorers.py:1672-1675).
+    backward: d logZ_b / d arc_scores[a] = posterior of arc a;  d / d theta[l] = sum of
+    posteriors of the arcs labelled l.
+    """
+
+    @staticmethod
+    def forward(ctx, arc_scores, theta, packed: PackedLattices):
+        alpha, logz = lattice_forward(packed, arc_scores, theta)
+        ctx.packed = packed
+        ctx.save_for_backward(alpha, logz, arc_scores if arc_scores is not None else torch.empty(0),
+                              theta if theta is not None else torch.empty(0))
+        ctx.has = (arc_scores is not None, theta is not None)
+        return logz
+
+    @staticmethod
+    def backward(ctx, grad_logz):
+        alpha, logz, a, t = ctx.saved_tensors
+        has_a, has_t = ctx.has
+        need_a = has_a and ctx.needs_input_grad[0]
+        need_t = has_t and ctx.needs_input_grad[1]
+        if not (need_a or need_t):
+            return None, None, None
+        r = lattice_backward(
+            ctx.packed, a if has_a else None, t if has_t else None, alpha=alpha, logz=logz,
+            grad_logz=grad_logz.contiguous(), want_beta=False, want_post=need_a, want_dtheta=need_t,
+        )
+        return (r.get("post") if need_a else None), (r.get("dtheta") if need_t else None), None
+
+
+def lattice_log_partition(packed: PackedLattices, arc_scores=None, theta=None) -> torch.Tensor:
+    return LatticeLogPartition.apply(arc_scores, theta, packed)
+
+
+def lattice_viterbi(packed: PackedLattices, arc_scores=None, theta=None):
+    """Best path per lattice under SURVEY.md section 8(c)'s rule (bit-exact, first-label
+    tie-break).  Returns (score[B], path_offsets[B+1] int64, path_arcs int32 canonical arc
+    ids, path_labels int32); labels run start->sink, eos included, the sink's pad loop
+    excluded (cf. samplers.py:304-307)."""
+    global launch_count
+    lib = _lib.load()
+    dev = packed.device
+    r = lattice_backward(packed, arc_scores, theta, want_beta=False, want_viterbi=True)
+    cap = torch.clamp(packed.n_levels.to(torch.int64) - 1, min=0)
+    path_off = torch.zeros(packed.n_lattices + 1, dtype=torch.int64, device=dev)
+    torch.cumsum(cap, 0, out=path_off[1:])
+    path_off32 = path_off.to(torch.int32)
+    total = int(packed.n_states)  # >= sum of capacities; avoids a host sync
+    path_buf = torch.empty(max(total, 1), dtype=torch.int32, device=dev)
+    path_len = torch.empty(packed.n_lattices, dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.nfst_backtrace(packed.c_struct(), r["backptr"].data_ptr(), path_off32.data_ptr(),
+                                      path_buf.data_ptr(), path_len.data_ptr(), _stream(dev)))
+        launch_count += 1
+    # compact the per-lattice slots (plumbing; ragged result)
+    lens = path_len.to(torch.int64)
+    offsets = torch.zeros(packed.n_lattices + 1, dtype=torch.int64, device=dev)
+    torch.cumsum(lens, 0, out=offsets[1:])
+    n = int(offsets[-1])
+    lat = torch.repeat_interleave(torch.arange(packed.n_lattices, device=dev), lens, output_size=n)
+    pos = torch.arange(n, device=dev) - offsets[lat] + path_off[lat]
+    path_arcs = path_buf[pos]
+    path_labels = packed.label_out[path_arcs.to(torch.int64)]
+    return r["vit_score"], offsets, path_arcs, path_labels
+
+
+def beta_dense(packed: PackedLattices, beta: torch.Tensor, k: int = 1, dense_states: Optional[int] = None) -> torch.Tensor:
+    """Real-space beta in the reference's layout ``[B*k, S]`` (``scorers.py:854``): row
+    b*k+j is lattice b, column = original state id; trimmed states hold 0."""
+    global launch_count
+    lib = _lib.load()
+    dev = packed.device
+    if dense_states is None:
+        if packed.dense_shape is None:
+            raise ValueError("dense_states is required for lattices that were not packed from dense tables")
+        dense_states = packed.dense_shape[1]
+    out = torch.zeros(packed.n_lattices * k, dense_states, dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.nfst_beta_to_dense_f32(packed.c_struct(), beta.data_ptr(), packed.orig_state.data_ptr(), k,
+                                              dense_states, out.data_ptr(), _stream(dev)))
+        launch_count += 1
+    return out
+
+
+def compute_beta(emission: torch.Tensor, transition: torch.Tensor, theta: torch.Tensor, k: int = 1,
+                 packed: Optional[PackedLattices] = None) -> torch.Tensor:
+    """Drop-in for ``FSAGRUScorer.compute_beta()`` in the Wh = 0 regime
+    (``scorers.py:753-875``): real-space ``beta[B*k, S]`` fp32 for the tables that
+    ``set_masks`` / ``set_k`` would hold, with arc weight ``exp(theta[label])``."""
+    if packed is None:
+        packed = pack_dense(emission, transition, weighted=False)
+    r = lattice_backward(packed, None, theta, want_beta=True)
+    return beta_dense(packed, r["beta"], k)

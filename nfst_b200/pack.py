@@ -1,0 +1,331 @@
+"""Lattice packing: dense tables / arc lists -> level-sorted CSR (the HBM layout).
+
+Boundary of the hot path.  The reference hands its lattice DP two dense tables per
+example, ``emission[S, V]`` and ``transition[S, V]`` (``scorers.py:995-1035``), batched and
+padded by ``collate`` (``util/dataset_reader.py:175-186``), and rebuilds the graph from
+them with Python ``.item()`` loops on every call (``scorers.py:704-716``, ``:764-776``).  Here
+the graph is built once per batch (cacheable per example) with the same edge rule
+
+    cell (i, j) is an arc  i --j--> t   iff   t != 0 and t != i
+
+and stored as int32 CSR by outgoing state ("out" order == canonical arc id == the
+reference's scan order: state, then label) and by incoming state ("in" order), with the
+states of each lattice renumbered by topological level so that a level is a contiguous
+range.  States that are unreachable from the start state (row 0, ``scorers.py:1005``) --
+which includes every row added by ``collate`` padding (quirk Q5) -- are trimmed; their
+beta is reported as 0, which is also what the batched reference leaves there.
+
+All work is torch tensor ops on whatever device the inputs live on (the dense-table scan
+uses the library's CUDA kernels for CUDA inputs); nothing here is on the per-step path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import dataclasses
+import math
+from typing import List, Optional
+
+import torch
+
+from . import _lib
+
+# lattices with at most this many states keep their DP vectors in shared memory
+STATE_SMEM_MAX = 12288
+LEVEL_SMEM_MAX = 4096
+
+
+@dataclasses.dataclass
+class LaunchGroup:
+    """Lattices that share one kernel launch (one thread block per lattice)."""
+
+    ids: torch.Tensor  # int32 [n], lattice indices, heaviest first
+    n: int
+    block_threads: int
+    state_cap: int  # largest lattice of the group in states; 0 = DP vectors in global memory
+    level_cap: int  # 0 = level table read from global memory
+    n_arcs: int
+
+
+class PackedLattices:
+    """A batch of lattices in the layout ``nfst_packed_lattices_t`` describes."""
+
+    _INT_FIELDS = (
+        "state_off", "level_off", "level_ptr", "start_state", "sink_off", "sinks",
+        "in_ptr", "src_in", "label_in", "in2out", "out_ptr", "dst_out", "label_out",
+    )
+
+    def __init__(self, **kw):
+        self.n_lattices: int = kw["n_lattices"]
+        self.n_states: int = kw["n_states"]
+        self.n_arcs: int = kw["n_arcs"]
+        self.vocab: int = kw["vocab"]
+        for f in self._INT_FIELDS:
+            setattr(self, f, kw[f])
+        self.lanes_in_log2: torch.Tensor = kw["lanes_in_log2"]
+        self.lanes_out_log2: torch.Tensor = kw["lanes_out_log2"]
+        self.orig_state: torch.Tensor = kw["orig_state"]  # int32 [S] original local state id
+        self.arc_origin: torch.Tensor = kw["arc_origin"]  # int64 [A] index into the caller's arc list / dense cells
+        self.arc_off: torch.Tensor = kw["arc_off"]  # int32 [B+1] canonical arc range per lattice
+        self.n_levels: torch.Tensor = kw["n_levels"]  # int32 [B]
+        self.static_scores: Optional[torch.Tensor] = kw.get("static_scores")  # float32 [A] (weighted tables)
+        self.dense_shape = kw.get("dense_shape")  # (B, S, V) when packed from dense tables
+        self.groups: List[LaunchGroup] = kw["groups"]
+        self.max_levels: int = kw["max_levels"]
+        self._c = None
+
+    # ---- plumbing ----------------------------------------------------------------
+    @property
+    def device(self) -> torch.device:
+        return self.state_off.device
+
+    def tensors(self):
+        names = list(self._INT_FIELDS) + ["lanes_in_log2", "lanes_out_log2", "orig_state", "arc_origin", "arc_off", "n_levels"]
+        if self.static_scores is not None:
+            names.append("static_scores")
+        return names
+
+    def to(self, device) -> "PackedLattices":
+        kw = {k: getattr(self, k) for k in ("n_lattices", "n_states", "n_arcs", "vocab", "dense_shape", "max_levels")}
+        for name in self.tensors():
+            kw[name] = getattr(self, name).to(device)
+        kw.setdefault("static_scores", None)
+        kw["groups"] = [dataclasses.replace(g, ids=g.ids.to(device)) for g in self.groups]
+        return PackedLattices(**kw)
+
+    def pin_memory(self) -> "PackedLattices":
+        for name in self.tensors():
+            setattr(self, name, getattr(self, name).pin_memory())
+        for g in self.groups:
+            g.ids = g.ids.pin_memory()
+        return self
+
+    def nbytes(self) -> int:
+        return sum(getattr(self, n).numel() * getattr(self, n).element_size() for n in self.tensors())
+
+    def c_struct(self) -> "_lib.PackedLatticesC":
+        """The C view of this batch (device pointers; valid while ``self`` is alive)."""
+        if self._c is None:
+            if self.device.type != "cuda":
+                raise RuntimeError("nfst_b200 kernels need the packed lattices on a CUDA device (no CPU fallback)")
+            c = _lib.PackedLatticesC()
+            c.n_lattices, c.n_states, c.n_arcs, c.vocab = self.n_lattices, self.n_states, self.n_arcs, self.vocab
+            for f in self._INT_FIELDS:
+                t = getattr(self, f)
+                assert t.dtype == torch.int32 and t.is_contiguous()
+                setattr(c, f, t.data_ptr())
+            c.lanes_in_log2 = self.lanes_in_log2.data_ptr()
+            c.lanes_out_log2 = self.lanes_out_log2.data_ptr()
+            self._c = c
+        return self._c
+
+    # ---- algorithmic byte counts ----------------------------
+    def algorithmic_bytes_fwd_bwd(self) -> int:
+        return 20 * self.n_arcs + 20 * self.n_states
+
+    def algorithmic_bytes_viterbi(self, path_len_total: int = 0) -> int:
+        return 8 * self.n_arcs + 12 * self.n_states + 8 * path_len_total
+
+
+def _excl_cumsum(x: torch.Tensor) -> torch.Tensor:
+    out = torch.zeros(x.numel() + 1, dtype=torch.int64, device=x.device)
+    torch.cumsum(x, 0, out=out[1:])
+    return out
+
+
+def _pow2_ceil(x: int) -> int:
+    return 1 if x <= 1 else 1 << (x - 1).bit_length()
+
+
+def pack_arcs(
+    arc_lattice: torch.Tensor,
+    src: torch.Tensor,
+    dst: torch.Tensor,
+    label: torch.Tensor,
+    n_states: torch.Tensor,
+    vocab: int,
+    *,
+    start_state: int = 0,
+    static_scores: Optional[torch.Tensor] = None,
+    dense_shape=None,
+    state_smem_max: int = STATE_SMEM_MAX,
+) -> PackedLattices:
+    """Pack an arc list.  ``arc_lattice/src/dst/label`` are [A0] integer tensors (local
+    state ids), ``n_states`` is [B].  Raises ``ValueError`` for cyclic lattices (the
+    reference's denominator / base machines, which it never feeds to the DP either)."""
+    dev = src.device
+    n_states = n_states.to(device=dev, dtype=torch.int64)
+    B = int(n_states.numel())
+    if B == 0:
+        raise ValueError("empty batch")
+    arc_lattice = arc_lattice.to(torch.int64)
+    so = _excl_cumsum(n_states)  # original global state offsets
+    S0 = int(so[-1])
+    if S0 >= 2**31 or src.numel() >= 2**31:
+        raise ValueError("batch too large for int32 indices; shard it")
+    gsrc = so[arc_lattice] + src.to(torch.int64)
+    gdst = so[arc_lattice] + dst.to(torch.int64)
+    label = label.to(torch.int64)
+    if src.numel() and (int(src.min()) < 0 or int(dst.min()) < 0 or bool((src >= n_states[arc_lattice]).any())
+                        or bool((dst >= n_states[arc_lattice]).any())):
+        raise ValueError("arc endpoint out of range")
+    if label.numel() and (int(label.min()) < 0 or int(label.max()) >= vocab):
+        raise ValueError("label out of range")
+
+    # ---- levels = longest distance from the start state; -1 = unreachable (trimmed) ----
+    level = torch.full((S0,), -1, dtype=torch.int64, device=dev)
+    level[so[:-1] + start_state] = 0
+    max_iter = int(n_states.max()) if B else 0
+    it = 0
+    while gsrc.numel():
+        ls = level[gsrc]
+        cand = torch.where(ls >= 0, ls + 1, ls)
+        new = level.scatter_reduce(0, gdst, cand, reduce="amax", include_self=True)
+        if torch.equal(new, level):
+            break
+        level = new
+        it += 1
+        if it > max_iter:
+            raise ValueError("lattice is cyclic: the DP is defined for acyclic lattices only")
+
+    # ---- state renumbering: (lattice, level, original id) ----
+    lat_of_state = torch.repeat_interleave(torch.arange(B, device=dev), n_states)
+    kept = torch.nonzero(level >= 0).squeeze(1)
+    lv = level[kept]
+    lt = lat_of_state[kept]
+    lmax = int(lv.max()) + 1 if kept.numel() else 1
+    order = torch.argsort(lt * lmax + lv, stable=True)
+    kept_sorted = kept[order]
+    lt_s, lv_s = lt[order], lv[order]
+    S = int(kept_sorted.numel())
+    new_id = torch.full((S0,), -1, dtype=torch.int64, device=dev)
+    new_id[kept_sorted] = torch.arange(S, device=dev)
+    state_off = _excl_cumsum(torch.bincount(lt_s, minlength=B))
+    n_levels = torch.zeros(B, dtype=torch.int64, device=dev).scatter_reduce(0, lt_s, lv_s + 1, reduce="amax")
+    level_off = _excl_cumsum(n_levels + 1)
+    n_slots = int(level_off[-1])
+    slot = level_off[lt_s] + lv_s
+    counts = torch.bincount(slot, minlength=n_slots)
+    level_ptr = torch.cumsum(counts, 0) - counts  # exclusive; the spare slot of lattice b lands on state_off[b+1]
+    orig_state = kept_sorted - so[lt_s]
+    start_packed = new_id[so[:-1] + start_state]
+
+    # ---- arcs: canonical (out) order and in order ----
+    origin = torch.nonzero(level[gsrc] >= 0).squeeze(1)
+    ns, nd, lb = new_id[gsrc[origin]], new_id[gdst[origin]], label[origin]
+    perm = torch.argsort(ns * vocab + lb, stable=True)
+    src_out, dst_out, label_out, origin = ns[perm], nd[perm], lb[perm], origin[perm]
+    A = int(src_out.numel())
+    out_deg = torch.bincount(src_out, minlength=S)
+    out_ptr = _excl_cumsum(out_deg)
+    in2out = torch.argsort(dst_out, stable=True)
+    src_in, label_in = src_out[in2out], label_out[in2out]
+    in_ptr = _excl_cumsum(torch.bincount(dst_out, minlength=S))
+    sinks = torch.nonzero(out_deg == 0).squeeze(1)
+    sink_lat = torch.searchsorted(state_off, sinks, right=True) - 1
+    sink_off = _excl_cumsum(torch.bincount(sink_lat, minlength=B))
+    arc_off = out_ptr[state_off]
+
+    # ---- per-lattice shape statistics -> lanes per state, block size, launch groups ----
+    A_b = (arc_off[1:] - arc_off[:-1]).to(torch.float64)
+    S_b = state_off[1:] - state_off[:-1]
+    n_sinks_b = sink_off[1:] - sink_off[:-1]
+    avg_in = A_b / torch.clamp(S_b - 1, min=1)
+    avg_out = A_b / torch.clamp(S_b - n_sinks_b, min=1)
+
+    def lanes_log2(avg):
+        return torch.clamp(torch.round(torch.log2(torch.clamp(avg * 0.75, min=1.0))), 0, 5).to(torch.int64)
+
+    lg_in, lg_out = lanes_log2(avg_in), lanes_log2(avg_out)
+    slot_lat = torch.repeat_interleave(torch.arange(B, device=dev), n_levels + 1)
+    width = torch.zeros(B, dtype=torch.int64, device=dev).scatter_reduce(0, slot_lat, counts, reduce="amax")
+    threads = width * (1 << torch.maximum(lg_in, lg_out))
+    block_class = torch.clamp(torch.ceil(torch.log2(torch.clamp(threads.to(torch.float64), min=32.0))), 5, 10).to(torch.int64)
+    smem_ok = (S_b <= state_smem_max).to(torch.int64)
+    gkey = (block_class * 2 + smem_ok).cpu()
+    A_b_cpu, S_b_cpu, L_b_cpu = A_b.cpu(), S_b.cpu(), n_levels.cpu()
+    groups: List[LaunchGroup] = []
+    for key in sorted(set(gkey.tolist()), reverse=True):
+        members = torch.nonzero(gkey == key).squeeze(1)
+        members = members[torch.argsort(A_b_cpu[members], descending=True, stable=True)]
+        ok = bool(key & 1)
+        lcap = int(L_b_cpu[members].max())
+        groups.append(
+            LaunchGroup(
+                ids=members.to(torch.int32).to(dev),
+                n=int(members.numel()),
+                block_threads=1 << (key >> 1),
+                state_cap=int(S_b_cpu[members].max()) if ok else 0,
+                level_cap=lcap if lcap <= LEVEL_SMEM_MAX else 0,
+                n_arcs=int(A_b_cpu[members].sum()),
+            )
+        )
+
+    i32 = lambda t: t.to(torch.int32).contiguous()  # noqa: E731
+    return PackedLattices(
+        n_lattices=B, n_states=S, n_arcs=A, vocab=int(vocab),
+        state_off=i32(state_off), level_off=i32(level_off), level_ptr=i32(level_ptr), start_state=i32(start_packed),
+        sink_off=i32(sink_off), sinks=i32(sinks), in_ptr=i32(in_ptr), src_in=i32(src_in), label_in=i32(label_in),
+        in2out=i32(in2out), out_ptr=i32(out_ptr), dst_out=i32(dst_out), label_out=i32(label_out),
+        lanes_in_log2=lg_in.to(torch.uint8).contiguous(), lanes_out_log2=lg_out.to(torch.uint8).contiguous(),
+        orig_state=i32(orig_state), arc_origin=origin.contiguous(), arc_off=i32(arc_off), n_levels=i32(n_levels),
+        static_scores=None if static_scores is None else static_scores[origin].to(torch.float32).contiguous(),
+        dense_shape=dense_shape, groups=groups, max_levels=int(n_levels.max()) if B else 0,
+    )
+
+
+def dense_arcs(transition: torch.Tensor):
+    """Apply the reference's edge rule (``scorers.py:704-716``) to ``transition[B, S, V]``.
+
+    Returns (row, label, dst) int tensors in scan order, ``row = b * S + s``.  CUDA inputs
+    go through the library's kernels (one warp per table row); CPU inputs through
+    ``torch.nonzero`` (host-side preprocessing only -- the DP itself has no CPU path).
+    """
+    if transition.dim() != 3:
+        raise ValueError("transition must be [B, S, V]")  # scorers.py:878-879
+    B, S, V = transition.shape
+    if transition.device.type == "cuda":
+        lib = _lib.load()
+        tr = transition.to(torch.int64).contiguous()
+        n_rows = B * S
+        counts = torch.empty(n_rows, dtype=torch.int32, device=tr.device)
+        st = torch.cuda.current_stream(tr.device).cuda_stream
+        with torch.cuda.device(tr.device):
+            _lib.check(lib.nfst_dense_count_arcs(tr.data_ptr(), n_rows, S, V, counts.data_ptr(), st))
+            row_start = _excl_cumsum(counts.to(torch.int64))
+            A0 = int(row_start[-1])
+            row = torch.empty(A0, dtype=torch.int32, device=tr.device)
+            lab = torch.empty(A0, dtype=torch.int32, device=tr.device)
+            dst = torch.empty(A0, dtype=torch.int32, device=tr.device)
+            _lib.check(lib.nfst_dense_extract_arcs(tr.data_ptr(), n_rows, S, V, row_start.data_ptr(), row.data_ptr(),
+                                                   lab.data_ptr(), dst.data_ptr(), st))
+        return row.to(torch.int64), lab.to(torch.int64), dst.to(torch.int64)
+    rows = torch.arange(S, device=transition.device).view(1, S, 1)
+    keep = (transition != 0) & (transition != rows)
+    b, s, l = torch.nonzero(keep, as_tuple=True)
+    return b * S + s, l, transition[b, s, l].to(torch.int64)
+
+
+def pack_dense(emission: Optional[torch.Tensor], transition: torch.Tensor, *, weighted: Optional[bool] = None,
+               state_smem_max: int = STATE_SMEM_MAX) -> PackedLattices:
+    """Pack collate()-style dense tables ``emission[B, S, V]`` / ``transition[B, S, V]``.
+
+    ``weighted``: treat ``emission`` as float log-weights (``scorers.py:1011-1013,1026-1027``)
+    that become static arc scores; default = emission is a floating tensor.
+    """
+    if transition.dim() != 3 or (emission is not None and emission.shape != transition.shape):
+        raise ValueError("emission and transition must both be [B, S, V]")
+    B, S, V = transition.shape
+    row, lab, dst = dense_arcs(transition)
+    if dst.numel() and int(dst.max()) >= S:
+        raise ValueError("transition points outside the table")
+    if weighted is None:
+        weighted = emission is not None and emission.is_floating_point()
+    static = None
+    if weighted:
+        static = emission.reshape(-1)[row * V + lab].to(torch.float32)
+    n_states = torch.full((B,), S, dtype=torch.int64, device=transition.device)
+    packed = pack_arcs(row // S, row % S, dst, lab, n_states, V, static_scores=static, dense_shape=(B, S, V),
+                       state_smem_max=state_smem_max)
+    # arc_origin indexes the arc list; turn it into the dense cell index (b*S+s)*V+l
+    packed.arc_origin = (row * V + lab)[packed.arc_origin].contiguous()
+    return packed

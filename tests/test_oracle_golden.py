@@ -132,3 +132,57 @@ def test_viterbi_rule_against_brute_force_with_ties():
         # smallest label sequence among the optimal paths
         assert list(labels) == min(tied)
         assert float(lo.path_score_f32_backward(w, path)) == best
+
+
+def _batch_from_tables(tables, theta):
+    from oracle import c_oracle
+
+    lat, src, dst, lab, sc, ns = [], [], [], [], [], []
+    for b, tr in enumerate(tables):
+        s, l, d, _ = lo.arcs_from_dense(tr)
+        lat.append(np.full(len(s), b)); src.append(s); dst.append(d); lab.append(l); sc.append(theta[l]); ns.append(tr.shape[0])
+    cat = np.concatenate
+    return c_oracle.Batch(cat(lat), cat(src), cat(dst), cat(lab), cat(sc), ns)
+
+
+def test_c_oracle_matches_reference_golden():
+    """The plain-C restatement (oracle/lattice_oracle.c) against the reference's own
+    compute_beta_per_sample outputs."""
+    from oracle import c_oracle
+
+    g = _load("beta_per_sample.npz")
+    theta = g["theta0"]
+    tables = [g[f"tr_{i}"] for i in range(int(g["n_cases"]))]
+    batch = _batch_from_tables(tables, theta)
+    logz, alpha, beta, post = c_oracle.forward_backward(batch)
+    for i, tr in enumerate(tables):
+        ref = g[f"beta0_{i}"]
+        sl = slice(batch.state_off[i], batch.state_off[i + 1])
+        # scores reach the C oracle as float32 (what the GPU path is fed)
+        np.testing.assert_allclose(np.exp(beta[sl]), ref, rtol=2e-6)
+        assert abs(logz[i] - np.log(ref[0])) < 1e-5
+
+
+def test_c_oracle_matches_numpy_oracle():
+    from oracle import c_oracle
+    from tests.lattice_gen import random_mark_lattice
+
+    rng = np.random.default_rng(9)
+    tables = [random_mark_lattice(rng, int(n), 24, parallel_arcs=bool(i % 2))[1] for i, n in enumerate(rng.integers(1, 30, size=12))]
+    theta = rng.integers(-2, 1, size=24).astype(np.float64)  # exact in fp32; many Viterbi ties
+    batch = _batch_from_tables(tables, theta)
+    logz, alpha, beta, post = c_oracle.forward_backward(batch)
+    score, paths, labels = c_oracle.viterbi(batch)
+    for i, tr in enumerate(tables):
+        s, l, d, _ = lo.arcs_from_dense(tr)
+        lz, al, be, po = lo.forward_backward(tr.shape[0], s, d, theta[l])
+        sl = slice(batch.state_off[i], batch.state_off[i + 1])
+        al_c = slice(batch.arc_off[i], batch.arc_off[i + 1])
+        assert abs(lz - logz[i]) < 1e-12
+        np.testing.assert_allclose(alpha[sl], al, atol=1e-12)
+        np.testing.assert_allclose(beta[sl], be, atol=1e-12)
+        np.testing.assert_allclose(post[al_c], po, atol=1e-12)
+        vs, vp, vl, _, _ = lo.viterbi_f32(tr.shape[0], s, l, d, theta[l])
+        assert float(vs) == float(score[i])
+        assert list(vl) == list(labels[i])
+        np.testing.assert_array_equal(paths[i] - batch.arc_off[i], vp)
