@@ -1,0 +1,407 @@
+#!/usr/bin/env python
+"""bench.py -- arcs/sec of log-semiring forward-backward on synthetic lattices.
+
+Contract: `python bench.py --gpus N --steps K --warmup W` (N>1 under torchrun) prints ONE
+JSON line on rank 0.  A "step" is one pass of the hot path (forward kernel + fused backward
+kernel emitting beta and arc posteriors) over one batch of synthetic lattices.
+
+  value      whole-job arcs/s, inputs resident in HBM, CUDA-event timed, max over ranks
+  e2e        same metric through the public API with HOST (pinned) buffers: per step the
+             packed batch + scores are copied H2D, logZ[B] is read back D2H
+  roofline   dominant kernel (fused backward): algorithmic bytes (12 B/arc + 12 B/state,
+             SURVEY.md 8d) / its mean CUDA-event duration, vs MEASURED_PEAKS.json hbm_gbs
+  cpu_baseline  oracle/lattice_oracle.c (a C port of the reference recurrence) on the
+             host cores, bounded sample of the same workload
+
+`--impl reference` times that CPU port alone (the reference itself is Python + OpenFst
+wrappers and cannot travel to the GPU box).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "arcs/sec forward-backward (log semiring)"
+UNIT = "arcs/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="nfst_b200", choices=["nfst_b200", "reference"])
+    ap.add_argument("--workload", default="dag", choices=["dag", "translit", "snips", "cipher-uni", "cipher-bi"])
+    ap.add_argument("--arcs", type=int, default=100_000, help="arcs per lattice (dag workload)")
+    ap.add_argument("--batch", type=int, default=1024, help="lattices per GPU (weak scaling)")
+    ap.add_argument("--levels", type=int, default=64)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--sweep", action="store_true", help="also time the other sweep points (N=1 only)")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    return ap.parse_args()
+
+
+def workload_name(a) -> str:
+    if a.workload == "dag":
+        return (f"config4 random-DAG sweep point: {a.arcs} arcs/lattice, S=A/4, {a.levels} levels, "
+                f"in-degree 1+Poisson(3), batch {a.batch}/GPU, scores U(-1,0), seed 3")
+    return {
+        "translit": f"config1 transliteration edit lattices, batch {a.batch}/GPU",
+        "snips": f"config2 SNIPS char x tag grids, batch {a.batch}/GPU",
+        "cipher-uni": f"config3 cipher unigram trellis T=1000, batch {a.batch}/GPU",
+        "cipher-bi": f"config3 cipher bigram trellis T=1000, batch {a.batch}/GPU",
+    }[a.workload]
+
+
+def make_arcs(a, device, seed_offset=0, batch=None, arcs=None):
+    from nfst_b200 import synth
+
+    B = a.batch if batch is None else batch
+    if a.workload == "dag":
+        return synth.random_dag_batch(B, a.arcs if arcs is None else arcs, levels=a.levels, seed=3 + seed_offset,
+                                      device=device)
+    if a.workload == "translit":
+        return synth.transliteration_batch(B, seed=seed_offset).to(device)
+    if a.workload == "snips":
+        return synth.snips_batch(B, seed=1 + seed_offset).to(device)
+    return synth.cipher_batch(B, T=1000, bigram=a.workload == "cipher-bi", seed=2 + seed_offset, device=device)
+
+
+def build_packed(a, device, seed_offset=0, arcs=None):
+    """Generate + pack on the device in chunks of lattices (bounds the packer's temporaries)
+    and collate the chunks."""
+    import torch
+
+    from nfst_b200.pack import concat_packed
+
+    per_lat = (a.arcs if arcs is None else arcs) if a.workload == "dag" else 700_000
+    chunk = max(1, min(a.batch, 60_000_000 // max(per_lat, 1)))
+    parts, scores = [], []
+    done = 0
+    while done < a.batch:
+        n = min(chunk, a.batch - done)
+        ab = make_arcs(a, device, seed_offset=seed_offset * 1000 + done, batch=n, arcs=arcs)
+        p, sc = ab.pack()
+        p.arc_origin = torch.empty(0, dtype=torch.int64, device=device)  # not needed here; frees 8 B/arc
+        parts.append(p)
+        scores.append(sc)
+        del ab
+        done += n
+    packed = concat_packed(parts) if len(parts) > 1 else parts[0]
+    return packed, torch.cat(scores)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def measured_peak_gbs():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def cpu_baseline(a, seconds: float, threads: int = 0):
+    """Time the C oracle (port of the reference recurrence, all host threads) on a bounded
+    sample of the workload: as many lattices as fit in ~`seconds`."""
+    from oracle import c_oracle
+
+    cores = c_oracle.max_threads() if threads <= 0 else threads
+    probe_n = max(1, min(a.batch, cores))
+    ab = make_arcs(a, "cpu", seed_offset=777, batch=probe_n)
+    ob = c_oracle.Batch(ab.arc_lattice.numpy(), ab.src.numpy(), ab.dst.numpy(), ab.label.numpy(), ab.scores.numpy(),
+                        ab.n_states.numpy())
+    t0 = time.perf_counter()
+    c_oracle.forward_backward(ob, want_post=True, n_threads=cores, want_states=True)
+    t_probe = time.perf_counter() - t0
+    reps = max(1, int(seconds / max(t_probe, 1e-4)))
+    reps = min(reps, 50)
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        c_oracle.forward_backward(ob, want_post=True, n_threads=cores, want_states=True)
+    dt = time.perf_counter() - t0
+    arcs = ob.n_arcs * reps
+    return {"value": arcs / dt, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{probe_n} lattices of the workload ({ob.n_arcs} arcs) x {reps} passes, float64 log-space "
+                      f"fwd+bwd+posteriors, oracle/lattice_oracle.c, {cores} OpenMP threads"}, dt / reps, ob.n_arcs
+
+
+def run_reference(a):
+    """--impl reference: the CPU port of the reference recurrence alone, all host threads."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import c_oracle
+
+    cores = c_oracle.max_threads()
+    n = max(1, min(a.batch, cores))
+    ab = make_arcs(a, "cpu", seed_offset=777, batch=n)
+    ob = c_oracle.Batch(ab.arc_lattice.numpy(), ab.src.numpy(), ab.dst.numpy(), ab.label.numpy(), ab.scores.numpy(),
+                        ab.n_states.numpy())
+    for _ in range(min(a.warmup, 2)):
+        c_oracle.forward_backward(ob, n_threads=cores)
+    steps = a.steps
+    t0 = time.perf_counter()
+    c_oracle.forward_backward(ob, n_threads=cores)
+    t1 = time.perf_counter() - t0
+    steps = max(1, min(a.steps, int(120.0 / max(t1, 1e-4))))
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        c_oracle.forward_backward(ob, n_threads=cores)
+    dt = time.perf_counter() - t0
+    val = ob.n_arcs * steps / dt
+    sample = (f"{n} lattices of the workload ({ob.n_arcs} arcs) per step, float64 log-space fwd+bwd+posteriors, "
+              f"oracle/lattice_oracle.c (C port of scorers.py:692-751; the Python reference cannot travel), "
+              f"{cores} OpenMP threads")
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": a.gpus, "steps": steps,
+        "warmup": min(a.warmup, 2), "ms_per_step": 1e3 * dt / steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name(a), "sample": sample},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def main():
+    a = parse_args()
+    if a.impl == "reference":
+        run_reference(a)
+        return
+    import torch
+    import torch.distributed as dist
+
+    import nfst_b200 as nb
+    from nfst_b200 import _lib, ops
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: nfst_b200 has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    _lib.check(_lib.load().nfst_device_info(local, None, None, None, None))
+
+    packed, scores = build_packed(a, dev, seed_offset=rank)
+    A, S, B = packed.n_arcs, packed.n_states, packed.n_lattices
+    loss = torch.zeros(1, device=dev)
+
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3 * a.steps + 2)]
+
+    def step(i=None):
+        if i is not None:
+            ev[3 * i].record()
+        alpha, logz = nb.lattice_forward(packed, arc_scores=scores)
+        if i is not None:
+            ev[3 * i + 1].record()
+        r = nb.lattice_backward(packed, arc_scores=scores, alpha=alpha, logz=logz, want_beta=True, want_post=True)
+        if i is not None:
+            ev[3 * i + 2].record()
+        if world > 1:
+            # the path's only collective: the loss all-reduce (posteriors feed the scorer's own backward)
+            loss.copy_(r["logz_bwd"].sum().reshape(1))
+            dist.all_reduce(loss)
+        return r
+
+    for _ in range(max(a.warmup, 3)):
+        step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    launches0 = ops.launch_count
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    torch.cuda.synchronize()
+    t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_start.record()
+    for i in range(a.steps):
+        step(i)
+    t_end.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    clk = clocks.stop() if rank == 0 else None
+    ms_total = t_start.elapsed_time(t_end)
+    launches = (ops.launch_count - launches0) // a.steps
+    fwd_ms = sum(ev[3 * i].elapsed_time(ev[3 * i + 1]) for i in range(a.steps)) / a.steps
+    bwd_ms = sum(ev[3 * i + 1].elapsed_time(ev[3 * i + 2]) for i in range(a.steps)) / a.steps
+    t = torch.tensor([ms_total, float(A)], device=dev, dtype=torch.float64)
+    if world > 1:
+        tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = t.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        ms_total, arcs_all = float(tmax[0]), float(tsum[1])
+    else:
+        arcs_all = float(A)
+    ms_step = ms_total / a.steps
+    value = arcs_all / (ms_step * 1e-3)
+
+    # ---- e2e: host (pinned) buffers -> H2D -> fwd+bwd -> D2H logZ ----
+    e2e = None
+    if not a.no_e2e:
+        fields = ("state_off", "level_off", "level_ptr", "start_state", "sink_off", "sinks", "in_ptr", "src_in",
+                  "in2out", "out_ptr", "dst_out", "lanes_in_log2", "lanes_out_log2")
+        host = {f: getattr(packed, f).cpu().pin_memory() for f in fields}
+        host_scores = scores.cpu().pin_memory()
+        host_ids = [g.ids.cpu().pin_memory() for g in packed.groups]
+        logz_host = torch.empty(B, dtype=torch.float32).pin_memory()
+        h2d = sum(t_.numel() * t_.element_size() for t_ in host.values()) + host_scores.numel() * 4 + sum(x.numel() * 4 for x in host_ids)
+        d2h = B * 4
+        import dataclasses
+
+        from nfst_b200.pack import PackedLattices
+
+        def e2e_step():
+            kw = {f: host[f].to(dev, non_blocking=True) for f in fields}
+            # label arrays are not read when scores are per-arc; keep the resident ones
+            kw.update(label_in=packed.label_in, label_out=packed.label_out, orig_state=packed.orig_state,
+                      arc_origin=packed.arc_origin, arc_off=packed.arc_off, n_levels=packed.n_levels)
+            groups = [dataclasses.replace(g, ids=h.to(dev, non_blocking=True)) for g, h in zip(packed.groups, host_ids)]
+            p = PackedLattices(n_lattices=B, n_states=S, n_arcs=A, vocab=packed.vocab, static_scores=None,
+                               dense_shape=None, groups=groups, max_levels=packed.max_levels, stats=packed.stats, **kw)
+            sc = host_scores.to(dev, non_blocking=True)
+            logz, alpha, beta, post = nb.lattice_forward_backward(p, arc_scores=sc)
+            logz_host.copy_(logz, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            return float(logz_host[0])
+
+        for _ in range(2):
+            e2e_step()
+        if world > 1:
+            dist.barrier()
+        n_e2e = max(3, min(a.steps, 10))
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(n_e2e):
+            e2e_step()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        te = torch.tensor([dt], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e2e = {"value": arcs_all / (float(te[0]) / n_e2e), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+               "d2h_bytes_per_step": int(d2h), "steps": n_e2e, "ms_per_step": 1e3 * float(te[0]) / n_e2e}
+        del host, host_scores
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peak, peak_src = measured_peak_gbs()
+    bwd_bytes = 12 * A + 12 * S
+    fwd_bytes = 8 * A + 8 * S
+    achieved = bwd_bytes / (bwd_ms * 1e-3) / 1e9
+    out = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": workload_name(a), "lattices_per_gpu": B, "arcs_per_gpu": A, "states_per_gpu": S,
+                   "levels": packed.max_levels, "global_batch": B * world, "parallelism": f"dp{world} (lattices sharded, loss all-reduce only)",
+                   "l2": "inputs larger than L2 (no flush)" if 20 * A > 2 * 126e6 else "inputs fit in L2 (no flush; latency-bound config)",
+                   "scores": "per-arc fp32, canonical order"},
+        "gpu_launches": launches,
+        "clocks": clk,
+        "roofline": {"bound": "hbm", "kernel": "nfst_bwd_kernel (fused beta + posteriors)", "achieved": achieved,
+                     "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                     "algorithmic_bytes_per_launch": bwd_bytes, "kernel_ms": bwd_ms,
+                     "fwd_kernel": {"achieved": fwd_bytes / (fwd_ms * 1e-3) / 1e9, "kernel_ms": fwd_ms,
+                                    "algorithmic_bytes_per_launch": fwd_bytes},
+                     "step": {"achieved": (20 * A + 20 * S) / (ms_step * 1e-3) / 1e9,
+                              "frac": (20 * A + 20 * S) / (ms_step * 1e-3) / 1e9 / peak}},
+    }
+    if e2e:
+        out["e2e"] = e2e
+    if not a.no_cpu:
+        cb, _, _ = cpu_baseline(a, a.cpu_seconds)
+        out["cpu_baseline"] = cb
+    if a.sweep and world == 1 and a.workload == "dag":
+        sweep = []
+        for arcs in (10_000, 30_000, 100_000, 300_000, 1_000_000):
+            del packed, scores
+            torch.cuda.empty_cache()
+            packed, scores = build_packed(a, dev, arcs=arcs)
+            for _ in range(3):
+                step()
+            torch.cuda.synchronize()
+            s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s0.record()
+            for _ in range(a.steps):
+                step()
+            s1.record()
+            torch.cuda.synchronize()
+            ms = s0.elapsed_time(s1) / a.steps
+            sweep.append({"arcs_per_lattice": arcs, "arcs": packed.n_arcs, "ms_per_step": ms,
+                          "arcs_per_s": packed.n_arcs / (ms * 1e-3),
+                          "gbs": (20 * packed.n_arcs + 20 * packed.n_states) / (ms * 1e-3) / 1e9})
+        out["sweep"] = sweep
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

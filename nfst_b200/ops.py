@@ -54,6 +54,8 @@ def _launch(g: LaunchGroup, n_state_arrays_in_smem: bool = True) -> "_lib.Launch
 
 def _scores(packed: PackedLattices, arc_scores, theta):
     dev = packed.device
+    if dev.type != "cuda":
+        raise RuntimeError("nfst_b200 kernels need the packed lattices on a CUDA device (no CPU fallback)")
     a = _check_f32("arc_scores", arc_scores, packed.n_arcs, dev)
     if packed.static_scores is not None:
         a = packed.static_scores if a is None else (a + packed.static_scores)

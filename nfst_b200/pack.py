@@ -71,6 +71,7 @@ class PackedLattices:
         self.dense_shape = kw.get("dense_shape")  # (B, S, V) when packed from dense tables
         self.groups: List[LaunchGroup] = kw["groups"]
         self.max_levels: int = kw["max_levels"]
+        self.stats = kw["stats"]  # per-lattice CPU tensors: arcs, states, levels, block_class
         self._c = None
 
     # ---- plumbing ----------------------------------------------------------------
@@ -84,12 +85,13 @@ class PackedLattices:
             names.append("static_scores")
         return names
 
-    def to(self, device) -> "PackedLattices":
+    def to(self, device, non_blocking: bool = False) -> "PackedLattices":
         kw = {k: getattr(self, k) for k in ("n_lattices", "n_states", "n_arcs", "vocab", "dense_shape", "max_levels")}
         for name in self.tensors():
-            kw[name] = getattr(self, name).to(device)
+            kw[name] = getattr(self, name).to(device, non_blocking=non_blocking)
         kw.setdefault("static_scores", None)
-        kw["groups"] = [dataclasses.replace(g, ids=g.ids.to(device)) for g in self.groups]
+        kw["groups"] = [dataclasses.replace(g, ids=g.ids.to(device, non_blocking=non_blocking)) for g in self.groups]
+        kw["stats"] = self.stats
         return PackedLattices(**kw)
 
     def pin_memory(self) -> "PackedLattices":
@@ -134,6 +136,83 @@ def _excl_cumsum(x: torch.Tensor) -> torch.Tensor:
 
 def _pow2_ceil(x: int) -> int:
     return 1 if x <= 1 else 1 << (x - 1).bit_length()
+
+
+def build_groups(stats, state_smem_max: int, dev) -> List[LaunchGroup]:
+    """Partition the batch into launches: lattices with the same block size, split by
+    whether their DP vectors fit in shared memory; heaviest lattices first."""
+    smem_ok = (stats["states"] <= state_smem_max).to(torch.int64)
+    gkey = stats["block_class"] * 2 + smem_ok
+    groups: List[LaunchGroup] = []
+    for key in sorted(set(gkey.tolist()), reverse=True):
+        members = torch.nonzero(gkey == key).squeeze(1)
+        members = members[torch.argsort(stats["arcs"][members], descending=True, stable=True)]
+        lcap = int(stats["levels"][members].max())
+        groups.append(
+            LaunchGroup(
+                ids=members.to(torch.int32).to(dev),
+                n=int(members.numel()),
+                block_threads=1 << (key >> 1),
+                state_cap=int(stats["states"][members].max()) if (key & 1) else 0,
+                level_cap=lcap if lcap <= LEVEL_SMEM_MAX else 0,
+                n_arcs=int(stats["arcs"][members].sum()),
+            )
+        )
+    return groups
+
+
+def concat_packed(parts: List["PackedLattices"], state_smem_max: int = STATE_SMEM_MAX) -> "PackedLattices":
+    """Collate independently packed lattices (e.g. cached per example) into one batch."""
+    if not parts:
+        raise ValueError("empty batch")
+    dev = parts[0].device
+    vocab = parts[0].vocab
+    if any(p.vocab != vocab for p in parts):
+        raise ValueError("all parts must share one vocabulary")
+    S = A = B = Lv = 0
+    acc = {f: [] for f in PackedLattices._INT_FIELDS}
+    extra = {k: [] for k in ("lanes_in_log2", "lanes_out_log2", "orig_state", "arc_origin", "arc_off", "n_levels")}
+    static = []
+    for i, p in enumerate(parts):
+        last = i == len(parts) - 1
+        cut = (lambda t: t) if last else (lambda t: t[:-1])  # offset arrays: drop the closing entry except at the end
+        acc["state_off"].append(cut(p.state_off + S))
+        acc["level_off"].append(cut(p.level_off + Lv))
+        acc["level_ptr"].append(p.level_ptr + S)
+        acc["start_state"].append(p.start_state + S)
+        acc["sink_off"].append(cut(p.sink_off + (sum(x.numel() for x in acc["sinks"]))))
+        acc["sinks"].append(p.sinks + S)
+        acc["in_ptr"].append(cut(p.in_ptr + A))
+        acc["src_in"].append(p.src_in + S)
+        acc["label_in"].append(p.label_in)
+        acc["in2out"].append(p.in2out + A)
+        acc["out_ptr"].append(cut(p.out_ptr + A))
+        acc["dst_out"].append(p.dst_out + S)
+        acc["label_out"].append(p.label_out)
+        extra["lanes_in_log2"].append(p.lanes_in_log2)
+        extra["lanes_out_log2"].append(p.lanes_out_log2)
+        extra["orig_state"].append(p.orig_state)
+        extra["arc_origin"].append(p.arc_origin)
+        extra["arc_off"].append(cut(p.arc_off + A))
+        extra["n_levels"].append(p.n_levels)
+        if p.static_scores is not None:
+            static.append(p.static_scores)
+        S += p.n_states
+        A += p.n_arcs
+        B += p.n_lattices
+        Lv += int(p.level_ptr.numel())
+    if S >= 2**31 or A >= 2**31:
+        raise ValueError("batch too large for int32 indices; shard it")
+    if static and len(static) != len(parts):
+        raise ValueError("either all or none of the parts may carry static scores")
+    stats = {k: torch.cat([p.stats[k] for p in parts]) for k in parts[0].stats}
+    kw = {f: torch.cat(v).contiguous() for f, v in acc.items()}
+    kw.update({f: torch.cat(v).contiguous() for f, v in extra.items()})
+    return PackedLattices(
+        n_lattices=B, n_states=S, n_arcs=A, vocab=vocab, static_scores=torch.cat(static) if static else None,
+        dense_shape=None, groups=build_groups(stats, state_smem_max, dev), max_levels=max(p.max_levels for p in parts),
+        stats=stats, **kw,
+    )
 
 
 def pack_arcs(
@@ -240,25 +319,13 @@ def pack_arcs(
     width = torch.zeros(B, dtype=torch.int64, device=dev).scatter_reduce(0, slot_lat, counts, reduce="amax")
     threads = width * (1 << torch.maximum(lg_in, lg_out))
     block_class = torch.clamp(torch.ceil(torch.log2(torch.clamp(threads.to(torch.float64), min=32.0))), 5, 10).to(torch.int64)
-    smem_ok = (S_b <= state_smem_max).to(torch.int64)
-    gkey = (block_class * 2 + smem_ok).cpu()
-    A_b_cpu, S_b_cpu, L_b_cpu = A_b.cpu(), S_b.cpu(), n_levels.cpu()
-    groups: List[LaunchGroup] = []
-    for key in sorted(set(gkey.tolist()), reverse=True):
-        members = torch.nonzero(gkey == key).squeeze(1)
-        members = members[torch.argsort(A_b_cpu[members], descending=True, stable=True)]
-        ok = bool(key & 1)
-        lcap = int(L_b_cpu[members].max())
-        groups.append(
-            LaunchGroup(
-                ids=members.to(torch.int32).to(dev),
-                n=int(members.numel()),
-                block_threads=1 << (key >> 1),
-                state_cap=int(S_b_cpu[members].max()) if ok else 0,
-                level_cap=lcap if lcap <= LEVEL_SMEM_MAX else 0,
-                n_arcs=int(A_b_cpu[members].sum()),
-            )
-        )
+    stats = {
+        "arcs": A_b.to(torch.int64).cpu(),
+        "states": S_b.cpu(),
+        "levels": n_levels.cpu(),
+        "block_class": block_class.cpu(),
+    }
+    groups = build_groups(stats, state_smem_max, dev)
 
     i32 = lambda t: t.to(torch.int32).contiguous()  # noqa: E731
     return PackedLattices(
@@ -269,7 +336,7 @@ def pack_arcs(
         lanes_in_log2=lg_in.to(torch.uint8).contiguous(), lanes_out_log2=lg_out.to(torch.uint8).contiguous(),
         orig_state=i32(orig_state), arc_origin=origin.contiguous(), arc_off=i32(arc_off), n_levels=i32(n_levels),
         static_scores=None if static_scores is None else static_scores[origin].to(torch.float32).contiguous(),
-        dense_shape=dense_shape, groups=groups, max_levels=int(n_levels.max()) if B else 0,
+        dense_shape=dense_shape, groups=groups, max_levels=int(n_levels.max()) if B else 0, stats=stats,
     )
 
 

@@ -173,3 +173,22 @@ def test_pack_arcs_coo_roundtrip():
     check_structure(p)
     o = _np(p.arc_origin)
     np.testing.assert_array_equal(np.array(lab)[o], _np(p.label_out))
+
+
+def test_concat_packed_equals_joint_pack():
+    from nfst_b200 import synth
+    from nfst_b200.pack import concat_packed
+
+    ab = synth.transliteration_batch(6, seed=3)
+    joint, _ = ab.pack()
+    parts = []
+    for b in range(6):
+        sel = ab.arc_lattice == b
+        one = synth.ArcBatch(torch.zeros(int(sel.sum()), dtype=torch.int64), ab.src[sel], ab.dst[sel], ab.label[sel],
+                             ab.scores[sel], ab.n_states[b : b + 1], ab.vocab)
+        parts.append(one.pack()[0])
+    cat = concat_packed(parts)
+    check_structure(cat)
+    for f in nb.PackedLattices._INT_FIELDS + ("lanes_in_log2", "lanes_out_log2", "orig_state", "arc_off", "n_levels"):
+        assert torch.equal(getattr(cat, f), getattr(joint, f)), f
+    assert (cat.n_lattices, cat.n_states, cat.n_arcs) == (joint.n_lattices, joint.n_states, joint.n_arcs)
