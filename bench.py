@@ -302,8 +302,8 @@ def main():
     # ---- e2e: host (pinned) buffers -> H2D -> fwd+bwd -> D2H logZ ----
     e2e = None
     if not a.no_e2e:
-        fields = ("state_off", "level_off", "level_ptr", "start_state", "sink_off", "sinks", "in_ptr", "src_in",
-                  "in2out", "out_ptr", "dst_out", "lanes_in_log2", "lanes_out_log2")
+        fields = ("state_off", "start_state", "sink_off", "sinks", "in_ptr", "src_in", "in2out", "out_ptr", "dst_out",
+                  "lanes_in_log2", "lanes_out_log2", "fwd_chunk_off", "fwd_chunks", "bwd_chunk_off", "bwd_chunks")
         host = {f: getattr(packed, f).cpu().pin_memory() for f in fields}
         host_scores = scores.cpu().pin_memory()
         host_ids = [g.ids.cpu().pin_memory() for g in packed.groups]
@@ -318,7 +318,8 @@ def main():
             kw = {f: host[f].to(dev, non_blocking=True) for f in fields}
             # label arrays are not read when scores are per-arc; keep the resident ones
             kw.update(label_in=packed.label_in, label_out=packed.label_out, orig_state=packed.orig_state,
-                      arc_origin=packed.arc_origin, arc_off=packed.arc_off, n_levels=packed.n_levels)
+                      arc_origin=packed.arc_origin, arc_off=packed.arc_off, n_levels=packed.n_levels,
+                      level_off=packed.level_off, level_ptr=packed.level_ptr)
             groups = [dataclasses.replace(g, ids=h.to(dev, non_blocking=True)) for g, h in zip(packed.groups, host_ids)]
             p = PackedLattices(n_lattices=B, n_states=S, n_arcs=A, vocab=packed.vocab, static_scores=None,
                                dense_shape=None, groups=groups, max_levels=packed.max_levels, stats=packed.stats, **kw)

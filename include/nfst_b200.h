@@ -21,7 +21,7 @@
  *   nfst_backtrace          best-path read-out; replaces best-of-k-samples selection
  *                           (src/modules/lightning.py:474-479) reached from
  *                           src/decode/decoder.py:77-79.
- *   nfst_beta_to_dense_f32  layout of compute_beta()'s return value, real-space
+ *   nfst_beta_to_dense      layout of compute_beta()'s return value, real-space
  *                           beta[B*k, S] (scorers.py:854, :858-875).
  *   nfst_dense_count_arcs / nfst_dense_extract_arcs
  *                           the dense-table edge rule `t != 0 and t != i`
@@ -41,7 +41,7 @@
 extern "C" {
 #endif
 
-#define NFST_ABI_VERSION 1
+#define NFST_ABI_VERSION 2
 
 typedef enum nfst_status {
   NFST_OK = 0,
@@ -50,6 +50,13 @@ typedef enum nfst_status {
   NFST_ERR_UNSUPPORTED_DEVICE = -3,
   NFST_ERR_TOO_LARGE = -4
 } nfst_status;
+
+/* One unit of work of a lattice: a run of consecutive states of ONE topological level
+ * together with their (contiguous) CSR arc range.  16 bytes. */
+typedef struct nfst_chunk {
+  int32_t arc_begin, arc_end;     /* in-order positions (forward) / canonical ids (backward) */
+  int32_t state_begin, state_end; /* packed state ids */
+} nfst_chunk_t;
 
 /*
  * A batch of packed lattices (all arrays are DEVICE pointers, int32 unless noted).
@@ -62,6 +69,10 @@ typedef enum nfst_status {
  *   "in" order: sorted by (destination state, canonical id) -- CSR by destination.
  * Lattice b has levels 0..L_b-1; level l spans packed states
  *   [ level_ptr[level_off[b]+l], level_ptr[level_off[b]+l+1] ).
+ * The kernels walk each lattice chunk by chunk: forward chunks in ascending state order,
+ * backward chunks in descending state order; a chunk never crosses a level boundary, so
+ * everything a chunk reads was produced by earlier chunks.
+ * Per-arc arrays must be readable up to the next multiple of 4 elements (128-bit loads).
  */
 typedef struct nfst_packed_lattices {
   int32_t n_lattices; /* B */
@@ -83,25 +94,32 @@ typedef struct nfst_packed_lattices {
   const int32_t* label_out;   /* [A] */
   const uint8_t* lanes_in_log2;  /* [B] log2 of lanes cooperating on one state, forward  */
   const uint8_t* lanes_out_log2; /* [B] same, backward */
+  const int32_t* fwd_chunk_off;     /* [B+1] */
+  const nfst_chunk_t* fwd_chunks;   /* ascending */
+  const int32_t* bwd_chunk_off;     /* [B+1] */
+  const nfst_chunk_t* bwd_chunks;   /* descending */
 } nfst_packed_lattices_t;
 
 /*
  * One kernel launch = one thread block per lattice in `lattice_ids` (NULL = lattices
- * 0..n_ids-1).  `state_smem_cap` > 0 keeps the per-state DP vectors of a lattice in
- * shared memory (must be >= the largest lattice of the launch, in states); 0 keeps them
- * in global memory.  `level_smem_cap` likewise stages the level table (0 = read it from
- * global memory).
+ * 0..n_ids-1).  A chunk of up to 8*block_threads arcs is staged in shared memory; larger
+ * chunks (a state whose degree exceeds that) take a slower block-wide path.
+ * `window_states` (a power of two, >= 32) is the number of most recent per-state DP
+ * values kept in shared memory; older ones are re-read from global memory.
+ * `state_f64` != 0 keeps the log-semiring state vectors (alpha, beta, logZ) in float64:
+ * needed for posteriors within 1e-5 on deep lattices, where |alpha| is in the hundreds
+ * or thousands and an fp32 ulp is no longer small against 1e-5.
  */
 typedef struct nfst_launch {
   const int32_t* lattice_ids;
   int32_t n_ids;
-  int32_t block_threads;  /* multiple of 32, <= 1024 */
-  int32_t state_smem_cap;
-  int32_t level_smem_cap;
+  int32_t block_threads; /* 32, 64, 128 or 256 */
+  int32_t window_states;
+  int32_t state_f64;
 } nfst_launch_t;
 
 /* Arc scores: w(a) = (arc_scores ? arc_scores[a] : 0) + (theta ? theta[label(a)] : 0);
- * arc_scores is indexed by canonical arc id. */
+ * arc_scores is indexed by canonical arc id (readable up to the next multiple of 4). */
 typedef struct nfst_scores {
   const float* arc_scores; /* [A] or NULL */
   const float* theta;      /* [V] or NULL */
@@ -114,30 +132,35 @@ const char* nfst_last_error_string(void);
  * Any of the out pointers may be NULL. */
 int nfst_device_info(int device, int* sm_count, int* cc_major, int* cc_minor, size_t* max_smem_optin);
 
-/* Dynamic shared memory a launch needs (bytes). n_state_arrays: 1 for fwd, 1 (log or
- * tropical) or 2 (both) for bwd.  with_theta/with_dtheta: V floats each when V <=
- * NFST_THETA_SMEM_MAX. */
+/* theta / dtheta are staged in shared memory when V <= NFST_THETA_SMEM_MAX. */
 #define NFST_THETA_SMEM_MAX 4096
-size_t nfst_launch_smem_bytes(const nfst_launch_t* launch, int32_t vocab, int n_state_arrays, int with_theta,
-                              int with_dtheta);
+/* Dynamic shared memory (bytes) of a forward (pass = 0) or backward (pass = 1) launch.
+ * with_log / with_trop select the semirings of the backward pass. */
+size_t nfst_launch_smem_bytes(const nfst_launch_t* launch, int32_t vocab, int pass, int with_log, int with_trop,
+                              int with_post, int with_theta, int with_dtheta);
 
-/* alpha[S] (log space), logz[B] = logsumexp over the lattice's sinks of alpha. */
+/* alpha[S] (log space), logz[B] = logsumexp over the lattice's sinks of alpha.  alpha and
+ * logz are float32, or float64 when launch->state_f64. */
 int nfst_fwd_f32(const nfst_packed_lattices_t* lat, const nfst_launch_t* launch, const nfst_scores_t* scores,
-                 float* alpha, float* logz, void* cuda_stream);
+                 void* alpha, void* logz, void* cuda_stream);
 
 /*
  * Fused backward.  Any output may be NULL, with these constraints:
- *   log semiring  : enabled when beta != NULL.  beta[S] (log space), logz_bwd[B] = beta[start].
- *       post[A]   : needs alpha and logz from nfst_fwd_f32; post[a] = g_b * exp(alpha[src] + w
- *                   + beta[dst] - logz[b]) with g_b = grad_logz[b] (1 when grad_logz == NULL).
- *       dtheta[V] : needs alpha/logz; atomically accumulates sum of post[a] by label
+ *   log semiring  : runs when beta, logz_bwd, post or dtheta is given.  beta[S] (log space),
+ *                   logz_bwd[B] = beta[start]  (float32, or float64 when state_f64; beta is
+ *                   required as the pass's working vector).
+ *       post[A]   : float32; needs alpha and logz from nfst_fwd_f32 (same state dtype);
+ *                   post[a] = g_b * exp(alpha[src] + w + beta[dst] - logz[b]) with
+ *                   g_b = grad_logz[b] (float32; 1 when grad_logz == NULL).
+ *       dtheta[V] : float32; needs alpha/logz; atomically accumulates post[a] by label
  *                   (caller zero-fills).
- *   tropical      : enabled when delta != NULL.  delta[S], backptr[S] (canonical arc id, -1
- *                   at sinks), vit_score[B] = delta[start].  delta[s] = max_a fl32(w_a +
- *                   delta[dst_a]); ties -> smallest canonical arc id (= smallest label).
+ *   tropical      : runs when delta/backptr is given (both required; always float32).
+ *                   delta[S], backptr[S] (canonical arc id, -1 at sinks), vit_score[B] =
+ *                   delta[start].  delta[s] = max_a fl32(w_a + delta[dst_a]); ties ->
+ *                   smallest canonical arc id (= smallest label).
  */
 int nfst_bwd_fused_f32(const nfst_packed_lattices_t* lat, const nfst_launch_t* launch, const nfst_scores_t* scores,
-                       const float* alpha, const float* logz, const float* grad_logz, float* beta, float* logz_bwd,
+                       const void* alpha, const void* logz, const float* grad_logz, void* beta, void* logz_bwd,
                        float* post, float* dtheta, float* delta, int32_t* backptr, float* vit_score,
                        void* cuda_stream);
 
@@ -151,10 +174,11 @@ int nfst_viterbi_f32(const nfst_packed_lattices_t* lat, const nfst_launch_t* lau
 int nfst_backtrace(const nfst_packed_lattices_t* lat, const int32_t* backptr, const int32_t* path_off,
                    int32_t* path_arcs, int32_t* path_len, void* cuda_stream);
 
-/* out[(b*k+j)*dense_states + orig_state[s]] = exp(beta[s]) for j < k; `out` must be
- * zero-filled by the caller (states that were trimmed at pack time keep 0). */
-int nfst_beta_to_dense_f32(const nfst_packed_lattices_t* lat, const float* beta, const int32_t* orig_state,
-                           int32_t k, int32_t dense_states, float* out, void* cuda_stream);
+/* out[(b*k+j)*dense_states + orig_state[s]] = exp(beta[s]) for j < k (float32 out; beta
+ * float32 or float64 per beta_f64); `out` must be zero-filled by the caller (states that
+ * were trimmed at pack time keep 0). */
+int nfst_beta_to_dense(const nfst_packed_lattices_t* lat, const void* beta, int beta_f64, const int32_t* orig_state,
+                       int32_t k, int32_t dense_states, float* out, void* cuda_stream);
 
 /* Dense-table edge rule.  transition is int64 [n_rows = B*S, V] row-major, row r belongs
  * to state r % S.  count: row_counts[r] = #cells with t != 0 && t != r % S.  extract:

@@ -37,6 +37,10 @@ class PackedLatticesC(C.Structure):
         ("label_out", C.c_void_p),
         ("lanes_in_log2", C.c_void_p),
         ("lanes_out_log2", C.c_void_p),
+        ("fwd_chunk_off", C.c_void_p),
+        ("fwd_chunks", C.c_void_p),
+        ("bwd_chunk_off", C.c_void_p),
+        ("bwd_chunks", C.c_void_p),
     ]
 
 
@@ -47,8 +51,8 @@ class LaunchC(C.Structure):
         ("lattice_ids", C.c_void_p),
         ("n_ids", C.c_int32),
         ("block_threads", C.c_int32),
-        ("state_smem_cap", C.c_int32),
-        ("level_smem_cap", C.c_int32),
+        ("window_states", C.c_int32),
+        ("state_f64", C.c_int32),
     ]
 
 
@@ -64,7 +68,7 @@ SYMBOLS = {
     "nfst_abi_version": (C.c_int, []),
     "nfst_last_error_string": (C.c_char_p, []),
     "nfst_device_info": (C.c_int, [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_size_t)]),
-    "nfst_launch_smem_bytes": (C.c_size_t, [C.POINTER(LaunchC), C.c_int32, C.c_int, C.c_int, C.c_int]),
+    "nfst_launch_smem_bytes": (C.c_size_t, [C.POINTER(LaunchC), C.c_int32] + [C.c_int] * 6),
     "nfst_fwd_f32": (C.c_int, [C.POINTER(PackedLatticesC), C.POINTER(LaunchC), C.POINTER(ScoresC), _P, _P, _P]),
     "nfst_bwd_fused_f32": (
         C.c_int,
@@ -72,7 +76,7 @@ SYMBOLS = {
     ),
     "nfst_viterbi_f32": (C.c_int, [C.POINTER(PackedLatticesC), C.POINTER(LaunchC), C.POINTER(ScoresC), _P, _P, _P, _P]),
     "nfst_backtrace": (C.c_int, [C.POINTER(PackedLatticesC), _P, _P, _P, _P, _P]),
-    "nfst_beta_to_dense_f32": (C.c_int, [C.POINTER(PackedLatticesC), _P, _P, C.c_int32, C.c_int32, _P, _P]),
+    "nfst_beta_to_dense": (C.c_int, [C.POINTER(PackedLatticesC), _P, C.c_int, _P, C.c_int32, C.c_int32, _P, _P]),
     "nfst_dense_count_arcs": (C.c_int, [_P, C.c_int64, C.c_int32, C.c_int32, _P, _P]),
     "nfst_dense_extract_arcs": (C.c_int, [_P, C.c_int64, C.c_int32, C.c_int32, _P, _P, _P, _P, _P]),
 }
@@ -100,7 +104,7 @@ def load() -> C.CDLL:
         fn = getattr(lib, name)  # AttributeError if the header and the library disagree
         fn.restype = res
         fn.argtypes = args
-    if lib.nfst_abi_version() != 1:
+    if lib.nfst_abi_version() != 2:
         raise RuntimeError("libnfst_b200.so ABI version mismatch")
     _lib = lib
     return lib

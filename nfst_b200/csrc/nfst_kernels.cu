@@ -6,15 +6,22 @@
 // (src/modules/scorers.py:692-751) / compute_beta_parallel (:753-856) with Wh = 0, in
 // log space:  beta[c] = logsumexp_{c -j-> n} (theta_j + beta[n]).
 //
-// Execution model (v1): one thread block per lattice, level-synchronous.  Inside a level
-// 2^g lanes cooperate on one state (g chosen per lattice at pack time from the mean
-// degree): the lanes stride over the state's contiguous CSR segment with coalesced
-// loads, keep a lane-local online (max, sum) pair, and combine with xor-shuffles.  The
-// per-state DP vectors live in shared memory when the lattice fits, otherwise in global
-// memory (L1/L2-resident; the same block wrote them, so block-scope barriers order
-// them).  The fused backward emits beta, arc posteriors (scaled by the incoming
-// gradient), the per-label gradient and the Viterbi delta/backpointer in one pass over
-// the outgoing arcs.
+// Execution model (v2).  One thread block walks one lattice chunk by chunk (a chunk = a
+// run of consecutive states of one level + their contiguous CSR arc range, built at pack
+// time; at most 8*blockDim arcs are staged at once):
+//   phase 1 (arc-parallel)   every thread owns 4 consecutive arcs: 128-bit coalesced loads
+//            of the arc arrays -- issued one to two chunks AHEAD into registers, so HBM
+//            streaming is decoupled from the per-level barriers -- then gathers of the
+//            neighbour state's DP value from a shared-memory window of the most recent
+//            `window_states` values (global memory beyond it), and a store of
+//            w + value into a shared-memory tile;
+//   phase 2 (state-parallel) 2^g lanes per state reduce the state's segment of the tile
+//            (max pass, sum-of-exp pass, xor-shuffle combine) and write the new DP value
+//            to the window and to global memory; the fused backward also emits the arc
+//            posteriors (scaled by the incoming gradient), the per-label gradient and the
+//            Viterbi delta / backpointer from the same tile.
+// State vectors are float32 or float64 (template ST); the tropical pass is always fp32
+// and uses only one add and exact comparisons, so it is bit-reproducible.
 #include "nfst_b200.h"
 
 #include <cuda_runtime.h>
@@ -37,314 +44,488 @@ int fail(int code, const char* fmt, ...) {
   return code;
 }
 
-#define NFST_CUDA_OK(expr)                                                                   \
-  do {                                                                                       \
-    cudaError_t _e = (expr);                                                                 \
+#define NFST_CUDA_OK(expr)                                                                      \
+  do {                                                                                          \
+    cudaError_t _e = (expr);                                                                    \
     if (_e != cudaSuccess) return fail(NFST_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString(_e)); \
   } while (0)
 
 constexpr float kNegInf = -__builtin_huge_valf();
+constexpr int kChunkArcsPerThread = 8;  // tile capacity = 8 * blockDim arcs
 
-// ---- online logsumexp pair (m, s): value = m + log(s) --------------------------------
-__device__ __forceinline__ void lse_add(float& m, float& s, float v) {
+__device__ __forceinline__ int4 ldg4(const int32_t* p) { return __ldg(reinterpret_cast<const int4*>(p)); }
+__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ int4 chunk_at(const nfst_chunk_t* c, int i, int end) {
+  return i < end ? __ldg(reinterpret_cast<const int4*>(c + i)) : make_int4(0, 0, 0, 0);
+}
+__device__ __forceinline__ int elem(const int4& v, int e) { return e == 0 ? v.x : e == 1 ? v.y : e == 2 ? v.z : v.w; }
+__device__ __forceinline__ float elem(const float4& v, int e) { return e == 0 ? v.x : e == 1 ? v.y : e == 2 ? v.z : v.w; }
+
+// ---- online logsumexp (m, s): value = m + log(s); m in the state type, s in fp32 --------
+template <typename ST>
+__device__ __forceinline__ void lse_add(ST& m, float& s, ST v) {
   if (v > m) {
-    s = s * __expf(m - v) + 1.0f;  // m == -inf: 0 * 0 + 1
+    s = s * __expf(static_cast<float>(m - v)) + 1.0f;  // m == -inf: 0 * 0 + 1
     m = v;
-  } else if (v > kNegInf) {
-    s += __expf(v - m);
+  } else if (v > static_cast<ST>(kNegInf)) {
+    s += __expf(static_cast<float>(v - m));
   }
 }
-__device__ __forceinline__ void lse_merge(float& m, float& s, float m2, float s2) {
+template <typename ST>
+__device__ __forceinline__ void lse_merge(ST& m, float& s, ST m2, float s2) {
   if (m2 > m) {
-    s = s * __expf(m - m2) + s2;
+    s = s * __expf(static_cast<float>(m - m2)) + s2;
     m = m2;
-  } else if (m2 > kNegInf) {
-    s += s2 * __expf(m2 - m);
+  } else if (m2 > static_cast<ST>(kNegInf)) {
+    s += s2 * __expf(static_cast<float>(m2 - m));
   }
 }
-__device__ __forceinline__ float lse_value(float m, float s) { return (m == kNegInf) ? kNegInf : m + logf(s); }
-
-// ---- shared memory carve-up (identical on host and device) ---------------------------
-struct SmemPlan {
-  int lvl, theta, dtheta, st0, st1, words;
-};
-__host__ __device__ inline SmemPlan smem_plan(int level_cap, int state_cap, int vocab, int n_state_arrays,
-                                              bool with_theta, bool with_dtheta) {
-  SmemPlan p;
-  int w = 0;
-  p.lvl = w;
-  w += level_cap > 0 ? level_cap + 1 : 0;
-  p.theta = w;
-  w += with_theta ? vocab : 0;
-  p.dtheta = w;
-  w += with_dtheta ? vocab : 0;
-  p.st0 = w;
-  w += n_state_arrays >= 1 ? state_cap : 0;
-  p.st1 = w;
-  w += n_state_arrays >= 2 ? state_cap : 0;
-  p.words = w;
-  return p;
+template <typename ST>
+__device__ __forceinline__ ST lse_value(ST m, float s) {
+  return (m == static_cast<ST>(kNegInf)) ? static_cast<ST>(kNegInf) : m + static_cast<ST>(logf(s));
 }
 
-// block-wide combine of (m, s) pairs; result valid in thread 0
-__device__ float block_lse(float m, float s) {
-  __shared__ float red_m[32], red_s[32];
+// block-wide combine; result valid in every thread
+template <typename ST>
+__device__ ST block_lse(ST m, float s) {
+  __shared__ double red_m[32];
+  __shared__ float red_s[32];
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
-    float m2 = __shfl_xor_sync(0xffffffffu, m, o);
-    float s2 = __shfl_xor_sync(0xffffffffu, s, o);
+    const ST m2 = __shfl_xor_sync(0xffffffffu, m, o);
+    const float s2 = __shfl_xor_sync(0xffffffffu, s, o);
     lse_merge(m, s, m2, s2);
   }
   const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = (blockDim.x + 31) >> 5;
+  __syncthreads();  // protect red_* against a previous call
   if (lane == 0) {
-    red_m[wid] = m;
+    red_m[wid] = static_cast<double>(m);
     red_s[wid] = s;
   }
   __syncthreads();
-  if (wid == 0) {
-    m = lane < nw ? red_m[lane] : kNegInf;
-    s = lane < nw ? red_s[lane] : 0.0f;
+  m = lane < nw ? static_cast<ST>(red_m[lane]) : static_cast<ST>(kNegInf);
+  s = lane < nw ? red_s[lane] : 0.0f;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      float m2 = __shfl_xor_sync(0xffffffffu, m, o);
-      float s2 = __shfl_xor_sync(0xffffffffu, s, o);
-      lse_merge(m, s, m2, s2);
-    }
+  for (int o = 16; o > 0; o >>= 1) {
+    const ST m2 = __shfl_xor_sync(0xffffffffu, m, o);
+    const float s2 = __shfl_xor_sync(0xffffffffu, s, o);
+    lse_merge(m, s, m2, s2);
   }
   return lse_value(m, s);
+}
+
+// ---- shared memory carve-up (identical on host and device), offsets in bytes ----------
+struct SmemPlan {
+  size_t win, vbuf, abuf, dwin, tbuf, segp, lbuf, theta, dtheta, bytes;
+};
+__host__ __device__ inline SmemPlan smem_plan(int W, int cap, int st_bytes, int vocab, bool bwd, bool logs, bool trop,
+                                              bool post, bool with_theta, bool with_dtheta) {
+  SmemPlan p;
+  size_t o = 0;
+  const bool log_arrays = !bwd || logs;
+  p.win = o;
+  o += log_arrays ? static_cast<size_t>(W) * st_bytes : 0;
+  p.vbuf = o;
+  o += log_arrays ? static_cast<size_t>(cap) * st_bytes : 0;
+  p.abuf = o;
+  o += (bwd && post) ? static_cast<size_t>(cap) * st_bytes : 0;
+  p.dwin = o;
+  o += (bwd && trop) ? static_cast<size_t>(W) * 4 : 0;
+  p.tbuf = o;
+  o += (bwd && trop) ? static_cast<size_t>(cap) * 4 : 0;
+  p.segp = o;
+  o += static_cast<size_t>(cap + 4) * 4;
+  p.lbuf = o;
+  o += (bwd && with_dtheta) ? static_cast<size_t>(cap) * 4 : 0;
+  p.theta = o;
+  o += with_theta ? static_cast<size_t>(vocab) * 4 : 0;
+  p.dtheta = o;
+  o += with_dtheta ? static_cast<size_t>(vocab) * 4 : 0;
+  p.bytes = (o + 15) & ~static_cast<size_t>(15);
+  return p;
 }
 
 // =====================================================================================
 // forward: alpha
 // =====================================================================================
-template <bool SMEM_STATE>
-__global__ void __launch_bounds__(1024) nfst_fwd_kernel(const nfst_packed_lattices_t L, const int32_t* __restrict__ ids,
-                                                        int level_cap, int state_cap,
-                                                        const float* __restrict__ arc_scores,
-                                                        const float* __restrict__ theta, int theta_smem,
-                                                        float* alpha, float* __restrict__ logz) {
-  extern __shared__ __align__(16) float smem[];
-  const int b = ids ? ids[blockIdx.x] : blockIdx.x;
-  const int s0 = L.state_off[b];
-  const int lvl0 = L.level_off[b];
-  const int nlev = L.level_off[b + 1] - lvl0 - 1;
-  const SmemPlan plan = smem_plan(level_cap, state_cap, L.vocab, 1, theta_smem != 0, false);
+template <typename ST>
+__global__ void __launch_bounds__(256)
+    nfst_fwd_kernel(const nfst_packed_lattices_t L, const int32_t* __restrict__ ids, int W,
+                    const float* __restrict__ arc_scores, const float* __restrict__ theta, int theta_smem, ST* alpha,
+                    ST* __restrict__ logz) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int NT = blockDim.x, tid = threadIdx.x;
+  const int cap = NT * kChunkArcsPerThread;
+  const SmemPlan plan = smem_plan(W, cap, sizeof(ST), L.vocab, false, true, false, false, theta_smem != 0, false);
+  ST* win = reinterpret_cast<ST*>(smem_raw + plan.win);
+  ST* vbuf = reinterpret_cast<ST*>(smem_raw + plan.vbuf);
+  int* segp = reinterpret_cast<int*>(smem_raw + plan.segp);
+  const ST neg_inf = static_cast<ST>(kNegInf);
 
-  const int32_t* lp = L.level_ptr + lvl0;
-  if (level_cap > 0 && nlev <= level_cap) {
-    int32_t* slp = reinterpret_cast<int32_t*>(smem + plan.lvl);
-    for (int i = threadIdx.x; i <= nlev; i += blockDim.x) slp[i] = lp[i];
-    lp = slp;
-  }
+  const int b = ids ? ids[blockIdx.x] : blockIdx.x;
+  const int base_s = L.state_off[b];
+  const int start = L.start_state[b];
+  const int wmask = W - 1;
+  const int lg0 = L.lanes_in_log2[b];
   const float* th = theta;
   if (theta && theta_smem) {
-    float* sth = smem + plan.theta;
-    for (int i = threadIdx.x; i < L.vocab; i += blockDim.x) sth[i] = theta[i];
+    float* sth = reinterpret_cast<float*>(smem_raw + plan.theta);
+    for (int i = tid; i < L.vocab; i += NT) sth[i] = theta[i];
     th = sth;
   }
-  float* sA = smem + plan.st0;
   __syncthreads();
 
-  const int lg0 = L.lanes_in_log2[b];
-  const int start = L.start_state[b];
+  const nfst_chunk_t* chunks = L.fwd_chunks;
+  int c = L.fwd_chunk_off[b];
+  const int c_end = L.fwd_chunk_off[b + 1];
 
-  // level 0 holds the start state only (unreachable states are trimmed at pack time)
-  for (int s = lp[0] + threadIdx.x; s < lp[1]; s += blockDim.x) {
-    const float v = (s == start) ? 0.0f : kNegInf;
-    if (SMEM_STATE) sA[s - s0] = v;
-    alpha[s] = v;
-  }
-  __syncthreads();
-
-  for (int l = 1; l < nlev; ++l) {
-    const int sb = lp[l], se = lp[l + 1];
-    // lanes per state: the lattice's default, widened while the level leaves lanes idle
-    int lg = lg0;
-    while (lg < 5 && ((se - sb) << (lg + 1)) <= static_cast<int>(blockDim.x)) ++lg;
-    const int G = 1 << lg;
-    const int lane_g = threadIdx.x & (G - 1);
-    const int grp = threadIdx.x >> lg;
-    const int ngrp = blockDim.x >> lg;
-    for (int base = sb; base < se; base += ngrp) {
-      const int s = base + grp;
-      const bool valid = s < se;
-      int a0 = 0, a1 = 0;
-      if (valid) {
-        a0 = L.in_ptr[s];
-        a1 = L.in_ptr[s + 1];
-      }
-      float m = kNegInf, sum = 0.0f;
-      for (int a = a0 + lane_g; a < a1; a += G) {
-        const int src = L.src_in[a];
-        float w = 0.0f;
-        if (arc_scores) w = arc_scores[L.in2out[a]];
-        if (th) w += th[L.label_in[a]];
-        const float av = SMEM_STATE ? sA[src - s0] : alpha[src];
-        lse_add(m, sum, w + av);
-      }
-      for (int o = G >> 1; o > 0; o >>= 1) {
-        const float m2 = __shfl_xor_sync(0xffffffffu, m, o);
-        const float s2 = __shfl_xor_sync(0xffffffffu, sum, o);
-        lse_merge(m, sum, m2, s2);
-      }
-      if (valid && lane_g == 0) {
-        const float v = lse_value(m, sum);
-        if (SMEM_STATE) sA[s - s0] = v;
-        alpha[s] = v;
+  // ---- register pipeline: arc arrays of chunk c+1 / c+2 are in flight while chunk c is reduced
+  const int4 z4 = make_int4(0, 0, 0, 0);
+  auto gbase = [&](const int4& k) { return (k.x & ~3) + tid * 4; };
+  auto ld_src = [&](const int4& k) { const int g = gbase(k); return g < k.y ? ldg4(L.src_in + g) : z4; };
+  auto ld_idx = [&](const int4& k) { const int g = gbase(k); return (arc_scores && g < k.y) ? ldg4(L.in2out + g) : z4; };
+  auto ld_lab = [&](const int4& k) { const int g = gbase(k); return (th && g < k.y) ? ldg4(L.label_in + g) : z4; };
+  // scores of the (up to) 4 arcs of this thread in chunk k; only arcs inside the chunk are
+  // touched, so whatever the 128-bit loads over-read is never used as an index
+  auto gather_w = [&](const int4& k, int g, const int4& idx, const int4& lab) {
+    float wv[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int a = g + e;
+      if (a >= k.x && a < k.y) {
+        if (arc_scores) wv[e] = __ldg(arc_scores + elem(idx, e));
+        if (th) wv[e] += th[elem(lab, e)];
       }
     }
-    __syncthreads();
+    return make_float4(wv[0], wv[1], wv[2], wv[3]);
+  };
+  int4 k0 = chunk_at(chunks, c, c_end), k1 = chunk_at(chunks, c + 1, c_end);
+  int4 src_c = ld_src(k0);
+  float4 w_c = gather_w(k0, gbase(k0), ld_idx(k0), ld_lab(k0));
+  int4 idx_n = ld_idx(k1), lab_n = ld_lab(k1);
+
+  for (; c < c_end; ++c) {
+    const int4 k2 = chunk_at(chunks, c + 2, c_end);
+    const int4 src_n = ld_src(k1);
+    const float4 w_n = gather_w(k1, gbase(k1), idx_n, lab_n);
+    const int4 idx_nn = ld_idx(k2), lab_nn = ld_lab(k2);
+
+    const int a0 = k0.x, a1 = k0.y, s0 = k0.z, s1 = k0.w;
+    const int n = a1 - a0, ns = s1 - s0;
+    if (n <= cap) {
+      // ---- phase 1: arc-parallel, values into the tile
+      for (int j = tid; j <= ns; j += NT) segp[j] = __ldg(L.in_ptr + s0 + j) - a0;
+      const int lo = s0 - W;
+      int g = gbase(k0);
+      int4 sv = src_c;
+      float4 wv = w_c;
+      while (g < a1) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int a = g + e;
+          if (a >= a0 && a < a1) {
+            const int src = elem(sv, e);
+            const ST av = (src >= lo) ? win[(src - base_s) & wmask] : alpha[src];
+            vbuf[a - a0] = static_cast<ST>(elem(wv, e)) + av;
+          }
+        }
+        g += NT * 4;
+        if (g < a1) {  // second pass of a long chunk: not prefetched
+          sv = ldg4(L.src_in + g);
+          wv = gather_w(k0, g, arc_scores ? ldg4(L.in2out + g) : z4, th ? ldg4(L.label_in + g) : z4);
+        }
+      }
+      __syncthreads();
+      // ---- phase 2: state-parallel segmented logsumexp over the tile
+      int lg = lg0;
+      while (lg < 5 && (ns << (lg + 1)) <= NT) ++lg;
+      const int G = 1 << lg, lane_g = tid & (G - 1), grp = tid >> lg, ngrp = NT >> lg;
+      for (int jb = 0; jb < ns; jb += ngrp) {
+        const int j = jb + grp;
+        const bool valid = j < ns;
+        const int b0 = valid ? segp[j] : 0, b1 = valid ? segp[j + 1] : 0;
+        ST m = neg_inf;
+        for (int i = b0 + lane_g; i < b1; i += G) m = max(m, vbuf[i]);
+        for (int o = G >> 1; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+        float sum = 0.0f;
+        if (m > neg_inf)
+          for (int i = b0 + lane_g; i < b1; i += G) sum += __expf(static_cast<float>(vbuf[i] - m));
+        for (int o = G >> 1; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        if (valid && lane_g == 0) {
+          const int s = s0 + j;
+          const ST v = (s == start) ? static_cast<ST>(0) : lse_value(m, sum);
+          win[(s - base_s) & wmask] = v;
+          alpha[s] = v;
+        }
+      }
+      __syncthreads();
+    } else {
+      // ---- oversize chunk (a state with more than `cap` incoming arcs): block-wide, from global
+      for (int j = 0; j < ns; ++j) {
+        const int s = s0 + j;
+        const int b0 = L.in_ptr[s], b1 = L.in_ptr[s + 1];
+        ST m = neg_inf;
+        float sum = 0.0f;
+        for (int a = b0 + tid; a < b1; a += NT) {
+          float w = 0.0f;
+          if (arc_scores) w = arc_scores[L.in2out[a]];
+          if (th) w += th[L.label_in[a]];
+          const int src = L.src_in[a];
+          const ST av = (src >= s0 - W) ? win[(src - base_s) & wmask] : alpha[src];
+          lse_add(m, sum, static_cast<ST>(w) + av);
+        }
+        const ST v0 = block_lse(m, sum);
+        if (tid == 0) {
+          const ST v = (s == start) ? static_cast<ST>(0) : v0;
+          win[(s - base_s) & wmask] = v;
+          alpha[s] = v;
+        }
+      }
+      __syncthreads();
+    }
+    k0 = k1; k1 = k2; src_c = src_n; w_c = w_n; idx_n = idx_nn; lab_n = lab_nn;
   }
 
-  // logZ = logsumexp over the sinks of alpha  (every zero-out-degree state has beta = 1,
-  // scorers.py:795-805)
-  float m = kNegInf, sum = 0.0f;
-  for (int i = L.sink_off[b] + threadIdx.x; i < L.sink_off[b + 1]; i += blockDim.x) {
-    const int s = L.sinks[i];
-    lse_add(m, sum, SMEM_STATE ? sA[s - s0] : alpha[s]);
-  }
-  const float z = block_lse(m, sum);
-  if (threadIdx.x == 0) logz[b] = z;
+  // logZ = logsumexp over the sinks of alpha (every zero-out-degree state has beta = 1,
+  // scorers.py:795-805); alpha was written by this block and the loop ended on a barrier
+  ST m = neg_inf;
+  float sum = 0.0f;
+  for (int i = L.sink_off[b] + tid; i < L.sink_off[b + 1]; i += NT) lse_add(m, sum, alpha[L.sinks[i]]);
+  const ST z = block_lse(m, sum);
+  if (tid == 0) logz[b] = z;
 }
 
 // =====================================================================================
 // fused backward: beta (+ posteriors, dtheta) and/or Viterbi delta + backpointer
 // =====================================================================================
-template <bool SMEM_STATE, bool LOGS, bool TROP>
-__global__ void __launch_bounds__(1024)
-    nfst_bwd_kernel(const nfst_packed_lattices_t L, const int32_t* __restrict__ ids, int level_cap, int state_cap,
+template <typename ST, bool LOGS, bool TROP>
+__global__ void __launch_bounds__(256)
+    nfst_bwd_kernel(const nfst_packed_lattices_t L, const int32_t* __restrict__ ids, int W,
                     const float* __restrict__ arc_scores, const float* __restrict__ theta, int theta_smem,
-                    int dtheta_smem, const float* __restrict__ alpha, const float* __restrict__ logz,
-                    const float* __restrict__ grad_logz, float* beta, float* __restrict__ logz_bwd,
-                    float* __restrict__ post, float* __restrict__ dtheta, float* delta, int32_t* __restrict__ backptr,
+                    int dtheta_smem, const ST* __restrict__ alpha, const ST* __restrict__ logz,
+                    const float* __restrict__ grad_logz, ST* beta, ST* __restrict__ logz_bwd, float* __restrict__ post,
+                    float* __restrict__ dtheta, float* delta, int32_t* __restrict__ backptr,
                     float* __restrict__ vit_score) {
-  extern __shared__ __align__(16) float smem[];
-  const int b = ids ? ids[blockIdx.x] : blockIdx.x;
-  const int s0 = L.state_off[b];
-  const int lvl0 = L.level_off[b];
-  const int nlev = L.level_off[b + 1] - lvl0 - 1;
-  constexpr int kArrays = (LOGS ? 1 : 0) + (TROP ? 1 : 0);
-  const SmemPlan plan = smem_plan(level_cap, state_cap, L.vocab, kArrays, theta_smem != 0, dtheta_smem != 0);
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int NT = blockDim.x, tid = threadIdx.x;
+  const int cap = NT * kChunkArcsPerThread;
+  const bool want_post = LOGS && (post != nullptr || dtheta != nullptr);
+  const SmemPlan plan =
+      smem_plan(W, cap, sizeof(ST), L.vocab, true, LOGS, TROP, want_post, theta_smem != 0, dtheta_smem != 0);
+  ST* win = reinterpret_cast<ST*>(smem_raw + plan.win);
+  ST* vbuf = reinterpret_cast<ST*>(smem_raw + plan.vbuf);
+  ST* abuf = reinterpret_cast<ST*>(smem_raw + plan.abuf);
+  float* dwin = reinterpret_cast<float*>(smem_raw + plan.dwin);
+  float* tbuf = reinterpret_cast<float*>(smem_raw + plan.tbuf);
+  int* segp = reinterpret_cast<int*>(smem_raw + plan.segp);
+  int* lbuf = reinterpret_cast<int*>(smem_raw + plan.lbuf);
+  const ST neg_inf = static_cast<ST>(kNegInf);
 
-  const int32_t* lp = L.level_ptr + lvl0;
-  if (level_cap > 0 && nlev <= level_cap) {
-    int32_t* slp = reinterpret_cast<int32_t*>(smem + plan.lvl);
-    for (int i = threadIdx.x; i <= nlev; i += blockDim.x) slp[i] = lp[i];
-    lp = slp;
-  }
+  const int b = ids ? ids[blockIdx.x] : blockIdx.x;
+  const int base_s = L.state_off[b];
+  const int wmask = W - 1;
+  const int lg0 = L.lanes_out_log2[b];
   const float* th = theta;
   if (theta && theta_smem) {
-    float* sth = smem + plan.theta;
-    for (int i = threadIdx.x; i < L.vocab; i += blockDim.x) sth[i] = theta[i];
+    float* sth = reinterpret_cast<float*>(smem_raw + plan.theta);
+    for (int i = tid; i < L.vocab; i += NT) sth[i] = theta[i];
     th = sth;
   }
   float* hist = nullptr;
   if (LOGS && dtheta) {
     if (dtheta_smem) {
-      hist = smem + plan.dtheta;
-      for (int i = threadIdx.x; i < L.vocab; i += blockDim.x) hist[i] = 0.0f;
+      hist = reinterpret_cast<float*>(smem_raw + plan.dtheta);
+      for (int i = tid; i < L.vocab; i += NT) hist[i] = 0.0f;
     } else {
       hist = dtheta;
     }
   }
-  float* sB = smem + plan.st0;                   // beta (LOGS) or delta (!LOGS)
-  float* sD = LOGS ? smem + plan.st1 : sB;       // delta
-  __syncthreads();
-
-  const int lg0 = L.lanes_out_log2[b];
-  const bool want_post = LOGS && (post != nullptr || hist != nullptr);
   const bool need_label = (th != nullptr) || (hist != nullptr);
-  float lz = 0.0f, gscale = 1.0f;
+  ST lz = 0;
+  float gscale = 1.0f;
   if (want_post) {
     lz = logz[b];
     if (grad_logz) gscale = grad_logz[b];
   }
+  __syncthreads();
 
-  for (int l = nlev - 1; l >= 0; --l) {
-    const int sb = lp[l], se = lp[l + 1];
-    int lg = lg0;
-    while (lg < 5 && ((se - sb) << (lg + 1)) <= static_cast<int>(blockDim.x)) ++lg;
-    const int G = 1 << lg;
-    const int lane_g = threadIdx.x & (G - 1);
-    const int grp = threadIdx.x >> lg;
-    const int ngrp = blockDim.x >> lg;
-    for (int base = sb; base < se; base += ngrp) {
-      const int s = base + grp;
-      const bool valid = s < se;
-      int a0 = 0, a1 = 0;
-      float am = 0.0f;
-      if (valid) {
-        a0 = L.out_ptr[s];
-        a1 = L.out_ptr[s + 1];
+  const nfst_chunk_t* chunks = L.bwd_chunks;
+  int c = L.bwd_chunk_off[b];
+  const int c_end = L.bwd_chunk_off[b + 1];
+  const int4 z4 = make_int4(0, 0, 0, 0);
+  const float4 zf4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  auto gbase = [&](const int4& k) { return (k.x & ~3) + tid * 4; };
+  auto ld_dst = [&](const int4& k) { const int g = gbase(k); return g < k.y ? ldg4(L.dst_out + g) : z4; };
+  auto ld_w = [&](const int4& k) { const int g = gbase(k); return (arc_scores && g < k.y) ? ldg4(arc_scores + g) : zf4; };
+  auto ld_lab = [&](const int4& k) { const int g = gbase(k); return (need_label && g < k.y) ? ldg4(L.label_out + g) : z4; };
+  int4 k0 = chunk_at(chunks, c, c_end);
+  int4 dst_c = ld_dst(k0), lab_c = ld_lab(k0);
+  float4 w_c = ld_w(k0);
+
+  for (; c < c_end; ++c) {
+    const int4 k1 = chunk_at(chunks, c + 1, c_end);
+    const int4 dst_n = ld_dst(k1), lab_n = ld_lab(k1);
+    const float4 w_n = ld_w(k1);
+
+    const int a0 = k0.x, a1 = k0.y, s0 = k0.z, s1 = k0.w;
+    const int n = a1 - a0, ns = s1 - s0;
+    if (n <= cap) {
+      // ---- phase 1
+      for (int j = tid; j <= ns; j += NT) segp[j] = __ldg(L.out_ptr + s0 + j) - a0;
+      if (want_post)
+        for (int j = tid; j < ns; j += NT) abuf[j] = alpha[s0 + j] - lz;
+      const int hi = s1 + W;
+      int g = gbase(k0);
+      int4 dv = dst_c, lv = lab_c;
+      float4 wv = w_c;
+      while (g < a1) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int a = g + e;
+          if (a >= a0 && a < a1) {
+            const int d = elem(dv, e);
+            float w = elem(wv, e);
+            if (th) w += th[elem(lv, e)];
+            if (LOGS) vbuf[a - a0] = static_cast<ST>(w) + ((d < hi) ? win[(d - base_s) & wmask] : beta[d]);
+            if (TROP) tbuf[a - a0] = __fadd_rn(w, (d < hi) ? dwin[(d - base_s) & wmask] : delta[d]);
+            if (LOGS && hist) lbuf[a - a0] = elem(lv, e);
+          }
+        }
+        g += NT * 4;
+        if (g < a1) {
+          dv = ldg4(L.dst_out + g);
+          wv = arc_scores ? ldg4(arc_scores + g) : zf4;
+          lv = need_label ? ldg4(L.label_out + g) : z4;
+        }
+      }
+      __syncthreads();
+      // ---- phase 2
+      int lg = lg0;
+      while (lg < 5 && (ns << (lg + 1)) <= NT) ++lg;
+      const int G = 1 << lg, lane_g = tid & (G - 1), grp = tid >> lg, ngrp = NT >> lg;
+      for (int jb = 0; jb < ns; jb += ngrp) {
+        const int j = jb + grp;
+        const bool valid = j < ns;
+        const int b0 = valid ? segp[j] : 0, b1 = valid ? segp[j + 1] : 0;
+        const int s = s0 + j;
+        if (LOGS) {
+          ST m = neg_inf;
+          for (int i = b0 + lane_g; i < b1; i += G) m = max(m, vbuf[i]);
+          for (int o = G >> 1; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+          float sum = 0.0f;
+          if (m > neg_inf)
+            for (int i = b0 + lane_g; i < b1; i += G) sum += __expf(static_cast<float>(vbuf[i] - m));
+          for (int o = G >> 1; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+          if (valid && lane_g == 0) {
+            const ST v = (b0 == b1) ? static_cast<ST>(0) : lse_value(m, sum);  // sinks: beta = 1
+            win[(s - base_s) & wmask] = v;
+            beta[s] = v;
+          }
+          if (want_post && valid) {
+            const ST am = abuf[j];
+            for (int i = b0 + lane_g; i < b1; i += G) {
+              const float p = __expf(static_cast<float>(am + vbuf[i])) * gscale;
+              if (post) post[a0 + i] = p;
+              if (hist) atomicAdd(&hist[lbuf[i]], p);
+            }
+          }
+        }
+        if (TROP) {
+          float bt = kNegInf;
+          int bi = 0x7fffffff;
+          for (int i = b0 + lane_g; i < b1; i += G) {
+            const float t = tbuf[i];
+            if (t > bt || (t == bt && i < bi)) { bt = t; bi = i; }
+          }
+          for (int o = G >> 1; o > 0; o >>= 1) {
+            const float t2 = __shfl_xor_sync(0xffffffffu, bt, o);
+            const int i2 = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (t2 > bt || (t2 == bt && i2 < bi)) { bt = t2; bi = i2; }
+          }
+          if (valid && lane_g == 0) {
+            const bool sink = (b0 == b1);
+            const float v = sink ? 0.0f : bt;
+            dwin[(s - base_s) & wmask] = v;
+            delta[s] = v;
+            backptr[s] = sink ? -1 : a0 + bi;
+          }
+        }
+      }
+      __syncthreads();
+    } else {
+      // ---- oversize chunk: one state at a time, block-wide, from global
+      for (int j = 0; j < ns; ++j) {
+        const int s = s0 + j;
+        const int b0 = L.out_ptr[s], b1 = L.out_ptr[s + 1];
+        ST am = 0;
         if (want_post) am = alpha[s] - lz;
-      }
-      float m = kNegInf, sum = 0.0f;
-      float bt = kNegInf;
-      int ba = 0x7fffffff;
-      for (int a = a0 + lane_g; a < a1; a += G) {
-        const int d = L.dst_out[a];
-        int lab = 0;
-        if (need_label) lab = L.label_out[a];
-        float w = 0.0f;
-        if (arc_scores) w = arc_scores[a];
-        if (th) w += th[lab];
+        ST m = neg_inf;
+        float sum = 0.0f;
+        float bt = kNegInf;
+        int bi = 0x7fffffff;
+        for (int a = b0 + tid; a < b1; a += NT) {
+          const int d = L.dst_out[a];
+          int lab = 0;
+          if (need_label) lab = L.label_out[a];
+          float w = arc_scores ? arc_scores[a] : 0.0f;
+          if (th) w += th[lab];
+          if (LOGS) {
+            const ST u = static_cast<ST>(w) + ((d < s1 + W) ? win[(d - base_s) & wmask] : beta[d]);
+            lse_add(m, sum, u);
+            if (want_post) {
+              const float p = __expf(static_cast<float>(am + u)) * gscale;
+              if (post) post[a] = p;
+              if (hist) atomicAdd(&hist[lab], p);
+            }
+          }
+          if (TROP) {
+            const float t = __fadd_rn(w, (d < s1 + W) ? dwin[(d - base_s) & wmask] : delta[d]);
+            if (t > bt || (t == bt && a < bi)) { bt = t; bi = a; }
+          }
+        }
         if (LOGS) {
-          const float u = w + (SMEM_STATE ? sB[d - s0] : beta[d]);
-          lse_add(m, sum, u);
-          if (want_post) {
-            const float p = __expf(am + u) * gscale;
-            if (post) post[a] = p;
-            if (hist) atomicAdd(&hist[lab], p);
+          const ST v0 = block_lse(m, sum);
+          if (tid == 0) {
+            const ST v = (b0 == b1) ? static_cast<ST>(0) : v0;
+            win[(s - base_s) & wmask] = v;
+            beta[s] = v;
           }
         }
         if (TROP) {
-          const float t = __fadd_rn(w, SMEM_STATE ? sD[d - s0] : delta[d]);
-          if (t > bt || (t == bt && a < ba)) {
-            bt = t;
-            ba = a;
+          __shared__ float red_t[32];
+          __shared__ int red_i[32];
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+            const float t2 = __shfl_xor_sync(0xffffffffu, bt, o);
+            const int i2 = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (t2 > bt || (t2 == bt && i2 < bi)) { bt = t2; bi = i2; }
+          }
+          __syncthreads();
+          if ((tid & 31) == 0) { red_t[tid >> 5] = bt; red_i[tid >> 5] = bi; }
+          __syncthreads();
+          if (tid == 0) {
+            for (int w2 = 1; w2 < (NT + 31) / 32; ++w2)
+              if (red_t[w2] > bt || (red_t[w2] == bt && red_i[w2] < bi)) { bt = red_t[w2]; bi = red_i[w2]; }
+            const bool sink = (b0 == b1);
+            const float v = sink ? 0.0f : bt;
+            dwin[(s - base_s) & wmask] = v;
+            delta[s] = v;
+            backptr[s] = sink ? -1 : bi;
           }
         }
       }
-      for (int o = G >> 1; o > 0; o >>= 1) {
-        if (LOGS) {
-          const float m2 = __shfl_xor_sync(0xffffffffu, m, o);
-          const float s2 = __shfl_xor_sync(0xffffffffu, sum, o);
-          lse_merge(m, sum, m2, s2);
-        }
-        if (TROP) {
-          const float t2 = __shfl_xor_sync(0xffffffffu, bt, o);
-          const int a2 = __shfl_xor_sync(0xffffffffu, ba, o);
-          if (t2 > bt || (t2 == bt && a2 < ba)) {
-            bt = t2;
-            ba = a2;
-          }
-        }
-      }
-      if (valid && lane_g == 0) {
-        const bool sink = (a0 == a1);
-        if (LOGS) {
-          const float v = sink ? 0.0f : lse_value(m, sum);
-          if (SMEM_STATE) sB[s - s0] = v;
-          if (!SMEM_STATE || beta) beta[s] = v;
-        }
-        if (TROP) {
-          const float v = sink ? 0.0f : bt;
-          if (SMEM_STATE) sD[s - s0] = v;
-          if (!SMEM_STATE || delta) delta[s] = v;
-          backptr[s] = sink ? -1 : ba;
-        }
-      }
+      __syncthreads();
     }
-    __syncthreads();
+    k0 = k1; dst_c = dst_n; lab_c = lab_n; w_c = w_n;
   }
 
-  if (threadIdx.x == 0) {
+  if (tid == 0) {
     const int start = L.start_state[b];
-    if (LOGS && logz_bwd) logz_bwd[b] = SMEM_STATE ? sB[start - s0] : beta[start];
-    if (TROP && vit_score) vit_score[b] = SMEM_STATE ? sD[start - s0] : delta[start];
+    if (LOGS && logz_bwd) logz_bwd[b] = beta[start];
+    if (TROP && vit_score) vit_score[b] = delta[start];
   }
   if (LOGS && dtheta && dtheta_smem) {
-    for (int i = threadIdx.x; i < L.vocab; i += blockDim.x) {
+    for (int i = tid; i < L.vocab; i += NT) {
       const float v = hist[i];
       if (v != 0.0f) atomicAdd(&dtheta[i], v);
     }
@@ -373,18 +554,18 @@ __global__ void nfst_backtrace_kernel(const nfst_packed_lattices_t L, const int3
   path_len[b] = k;
 }
 
-__global__ void nfst_beta_to_dense_kernel(const nfst_packed_lattices_t L, const float* __restrict__ beta,
+template <typename ST>
+__global__ void nfst_beta_to_dense_kernel(const nfst_packed_lattices_t L, const ST* __restrict__ beta,
                                           const int32_t* __restrict__ orig_state, int k, int dense_states,
                                           float* __restrict__ out) {
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= L.n_states) return;
-  // lattice of state s: last b with state_off[b] <= s
-  int lo = 0, hi = L.n_lattices;
+  int lo = 0, hi = L.n_lattices;  // lattice of state s: last b with state_off[b] <= s
   while (hi - lo > 1) {
     const int mid = (lo + hi) >> 1;
     if (L.state_off[mid] <= s) lo = mid; else hi = mid;
   }
-  const float v = expf(beta[s]);
+  const float v = static_cast<float>(exp(static_cast<double>(beta[s])));
   const size_t row0 = static_cast<size_t>(lo) * k;
   const int col = orig_state[s];
   for (int j = 0; j < k; ++j) out[(row0 + j) * dense_states + col] = v;
@@ -438,10 +619,11 @@ int check_launch(const nfst_packed_lattices_t* lat, const nfst_launch_t* launch)
   if (!lat || !launch) return fail(NFST_ERR_BAD_ARG, "null lattice or launch descriptor");
   if (launch->n_ids < 0 || launch->n_ids > lat->n_lattices)
     return fail(NFST_ERR_BAD_ARG, "n_ids=%d out of range (B=%d)", launch->n_ids, lat->n_lattices);
-  if (launch->block_threads < 32 || launch->block_threads > 1024 || (launch->block_threads & 31))
-    return fail(NFST_ERR_BAD_ARG, "block_threads=%d must be a multiple of 32 in [32,1024]", launch->block_threads);
-  if (launch->state_smem_cap < 0 || launch->level_smem_cap < 0)
-    return fail(NFST_ERR_BAD_ARG, "negative shared-memory capacity");
+  const int bt = launch->block_threads;
+  if (bt != 32 && bt != 64 && bt != 128 && bt != 256)
+    return fail(NFST_ERR_BAD_ARG, "block_threads=%d must be 32, 64, 128 or 256", bt);
+  const int w = launch->window_states;
+  if (w < 32 || (w & (w - 1))) return fail(NFST_ERR_BAD_ARG, "window_states=%d must be a power of two >= 32", w);
   return NFST_OK;
 }
 
@@ -456,6 +638,37 @@ int prepare_smem(K kernel, size_t bytes) {
       return fail(NFST_ERR_TOO_LARGE, "launch needs %zu B of shared memory, device allows %d", bytes, optin);
     NFST_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bytes)));
   }
+  return NFST_OK;
+}
+
+template <typename ST>
+int launch_fwd(const nfst_packed_lattices_t* lat, const nfst_launch_t* launch, const nfst_scores_t* scores, void* alpha,
+               void* logz, cudaStream_t st) {
+  const int theta_smem = scores->theta && lat->vocab <= NFST_THETA_SMEM_MAX;
+  const size_t bytes = nfst_launch_smem_bytes(launch, lat->vocab, 0, 1, 0, 0, scores->theta != nullptr, 0);
+  if (int rc = prepare_smem(nfst_fwd_kernel<ST>, bytes)) return rc;
+  nfst_fwd_kernel<ST><<<launch->n_ids, launch->block_threads, bytes, st>>>(
+      *lat, launch->lattice_ids, launch->window_states, scores->arc_scores, scores->theta, theta_smem,
+      static_cast<ST*>(alpha), static_cast<ST*>(logz));
+  NFST_CUDA_OK(cudaGetLastError());
+  return NFST_OK;
+}
+
+template <typename ST, bool LOGS, bool TROP>
+int launch_bwd(const nfst_packed_lattices_t* lat, const nfst_launch_t* launch, const nfst_scores_t* scores,
+               const void* alpha, const void* logz, const float* grad_logz, void* beta, void* logz_bwd, float* post,
+               float* dtheta, float* delta, int32_t* backptr, float* vit_score, cudaStream_t st) {
+  const bool small_v = lat->vocab <= NFST_THETA_SMEM_MAX;
+  const int theta_smem = scores->theta && small_v;
+  const int dtheta_smem = LOGS && dtheta && small_v;
+  const size_t bytes = nfst_launch_smem_bytes(launch, lat->vocab, 1, LOGS, TROP, LOGS && (post || dtheta),
+                                              scores->theta != nullptr, LOGS && dtheta != nullptr);
+  if (int rc = prepare_smem(nfst_bwd_kernel<ST, LOGS, TROP>, bytes)) return rc;
+  nfst_bwd_kernel<ST, LOGS, TROP><<<launch->n_ids, launch->block_threads, bytes, st>>>(
+      *lat, launch->lattice_ids, launch->window_states, scores->arc_scores, scores->theta, theta_smem, dtheta_smem,
+      static_cast<const ST*>(alpha), static_cast<const ST*>(logz), grad_logz, static_cast<ST*>(beta),
+      static_cast<ST*>(logz_bwd), post, dtheta, delta, backptr, vit_score);
+  NFST_CUDA_OK(cudaGetLastError());
   return NFST_OK;
 }
 
@@ -483,89 +696,53 @@ int nfst_device_info(int device, int* sm_count, int* cc_major, int* cc_minor, si
   return NFST_OK;
 }
 
-size_t nfst_launch_smem_bytes(const nfst_launch_t* launch, int32_t vocab, int n_state_arrays, int with_theta,
-                              int with_dtheta) {
+size_t nfst_launch_smem_bytes(const nfst_launch_t* launch, int32_t vocab, int pass, int with_log, int with_trop,
+                              int with_post, int with_theta, int with_dtheta) {
   if (!launch) return 0;
   const bool small_v = vocab <= NFST_THETA_SMEM_MAX;
-  const SmemPlan p = smem_plan(launch->level_smem_cap, launch->state_smem_cap, vocab, n_state_arrays,
-                               with_theta && small_v, with_dtheta && small_v);
-  return static_cast<size_t>(p.words) * sizeof(float);
+  const SmemPlan p = smem_plan(launch->window_states, launch->block_threads * kChunkArcsPerThread,
+                               launch->state_f64 ? 8 : 4, vocab, pass != 0, with_log != 0, with_trop != 0,
+                               with_post != 0, with_theta && small_v, with_dtheta && small_v);
+  return p.bytes;
 }
 
 int nfst_fwd_f32(const nfst_packed_lattices_t* lat, const nfst_launch_t* launch, const nfst_scores_t* scores,
-                 float* alpha, float* logz, void* cuda_stream) {
+                 void* alpha, void* logz, void* cuda_stream) {
   if (int rc = check_launch(lat, launch)) return rc;
   if (!scores || !alpha || !logz) return fail(NFST_ERR_BAD_ARG, "nfst_fwd_f32: null scores/alpha/logz");
   if (launch->n_ids == 0) return NFST_OK;
-  const int theta_smem = scores->theta && lat->vocab <= NFST_THETA_SMEM_MAX;
-  const size_t bytes = nfst_launch_smem_bytes(launch, lat->vocab, 1, scores->theta != nullptr, 0);
   cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
-  if (launch->state_smem_cap > 0) {
-    if (int rc = prepare_smem(nfst_fwd_kernel<true>, bytes)) return rc;
-    nfst_fwd_kernel<true><<<launch->n_ids, launch->block_threads, bytes, st>>>(
-        *lat, launch->lattice_ids, launch->level_smem_cap, launch->state_smem_cap, scores->arc_scores, scores->theta,
-        theta_smem, alpha, logz);
-  } else {
-    if (int rc = prepare_smem(nfst_fwd_kernel<false>, bytes)) return rc;
-    nfst_fwd_kernel<false><<<launch->n_ids, launch->block_threads, bytes, st>>>(
-        *lat, launch->lattice_ids, launch->level_smem_cap, 0, scores->arc_scores, scores->theta, theta_smem, alpha,
-        logz);
-  }
-  NFST_CUDA_OK(cudaGetLastError());
-  return NFST_OK;
+  return launch->state_f64 ? launch_fwd<double>(lat, launch, scores, alpha, logz, st)
+                           : launch_fwd<float>(lat, launch, scores, alpha, logz, st);
 }
 
 int nfst_bwd_fused_f32(const nfst_packed_lattices_t* lat, const nfst_launch_t* launch, const nfst_scores_t* scores,
-                       const float* alpha, const float* logz, const float* grad_logz, float* beta, float* logz_bwd,
+                       const void* alpha, const void* logz, const float* grad_logz, void* beta, void* logz_bwd,
                        float* post, float* dtheta, float* delta, int32_t* backptr, float* vit_score,
                        void* cuda_stream) {
   if (int rc = check_launch(lat, launch)) return rc;
   if (!scores) return fail(NFST_ERR_BAD_ARG, "nfst_bwd_fused_f32: null scores");
-  const bool smem_state = launch->state_smem_cap > 0;
   const bool want_post = post || dtheta;
-  // the log pass runs when any of its outputs is requested; in global-state mode it
-  // needs the beta buffer as its working vector
   const bool logs = beta || logz_bwd || want_post;
   const bool trop = delta || backptr || vit_score;
   if (!logs && !trop) return fail(NFST_ERR_BAD_ARG, "nfst_bwd_fused_f32: no output requested");
-  if (logs && !smem_state && !beta)
-    return fail(NFST_ERR_BAD_ARG, "log pass with state vectors in global memory needs a beta[S] buffer");
-  if (trop && !backptr) return fail(NFST_ERR_BAD_ARG, "tropical pass needs backptr[S]");
-  if (trop && !smem_state && !delta)
-    return fail(NFST_ERR_BAD_ARG, "tropical pass with state vectors in global memory needs a delta[S] buffer");
+  if (logs && !beta) return fail(NFST_ERR_BAD_ARG, "the log-semiring pass needs a beta[S] buffer (its working vector)");
+  if (trop && (!backptr || !delta)) return fail(NFST_ERR_BAD_ARG, "the tropical pass needs delta[S] and backptr[S]");
   if (want_post && (!alpha || !logz))
     return fail(NFST_ERR_BAD_ARG, "posteriors / dtheta need alpha[S] and logz[B] from nfst_fwd_f32");
   if (launch->n_ids == 0) return NFST_OK;
-
-  const bool small_v = lat->vocab <= NFST_THETA_SMEM_MAX;
-  const int theta_smem = scores->theta && small_v;
-  const int dtheta_smem = dtheta && small_v;
-  const int n_arrays = (logs ? 1 : 0) + (trop ? 1 : 0);
-  const size_t bytes =
-      nfst_launch_smem_bytes(launch, lat->vocab, n_arrays, scores->theta != nullptr, logs && dtheta != nullptr);
   cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
-  const int scap = smem_state ? launch->state_smem_cap : 0;
-
-#define NFST_LAUNCH_BWD(SM, LG, TR)                                                                              \
-  do {                                                                                                           \
-    if (int rc = prepare_smem(nfst_bwd_kernel<SM, LG, TR>, bytes)) return rc;                                    \
-    nfst_bwd_kernel<SM, LG, TR><<<launch->n_ids, launch->block_threads, bytes, st>>>(                            \
-        *lat, launch->lattice_ids, launch->level_smem_cap, scap, scores->arc_scores, scores->theta, theta_smem,  \
-        dtheta_smem, alpha, logz, grad_logz, beta, logz_bwd, post, dtheta, delta, backptr, vit_score);           \
-  } while (0)
-
-  if (smem_state) {
-    if (logs && trop) NFST_LAUNCH_BWD(true, true, true);
-    else if (logs) NFST_LAUNCH_BWD(true, true, false);
-    else NFST_LAUNCH_BWD(true, false, true);
-  } else {
-    if (logs && trop) NFST_LAUNCH_BWD(false, true, true);
-    else if (logs) NFST_LAUNCH_BWD(false, true, false);
-    else NFST_LAUNCH_BWD(false, false, true);
+#define NFST_BWD(ST, LG, TR) \
+  launch_bwd<ST, LG, TR>(lat, launch, scores, alpha, logz, grad_logz, beta, logz_bwd, post, dtheta, delta, backptr, vit_score, st)
+  if (launch->state_f64) {
+    if (logs && trop) return NFST_BWD(double, true, true);
+    if (logs) return NFST_BWD(double, true, false);
+    return NFST_BWD(float, false, true);
   }
-#undef NFST_LAUNCH_BWD
-  NFST_CUDA_OK(cudaGetLastError());
-  return NFST_OK;
+  if (logs && trop) return NFST_BWD(float, true, true);
+  if (logs) return NFST_BWD(float, true, false);
+  return NFST_BWD(float, false, true);
+#undef NFST_BWD
 }
 
 int nfst_viterbi_f32(const nfst_packed_lattices_t* lat, const nfst_launch_t* launch, const nfst_scores_t* scores,
@@ -587,15 +764,20 @@ int nfst_backtrace(const nfst_packed_lattices_t* lat, const int32_t* backptr, co
   return NFST_OK;
 }
 
-int nfst_beta_to_dense_f32(const nfst_packed_lattices_t* lat, const float* beta, const int32_t* orig_state,
-                           int32_t k, int32_t dense_states, float* out, void* cuda_stream) {
+int nfst_beta_to_dense(const nfst_packed_lattices_t* lat, const void* beta, int beta_f64, const int32_t* orig_state,
+                       int32_t k, int32_t dense_states, float* out, void* cuda_stream) {
   if (!lat || !beta || !orig_state || !out || k < 1 || dense_states < 1)
-    return fail(NFST_ERR_BAD_ARG, "nfst_beta_to_dense_f32: bad argument");
+    return fail(NFST_ERR_BAD_ARG, "nfst_beta_to_dense: bad argument");
   if (lat->n_states == 0) return NFST_OK;
   const int threads = 256;
   const int blocks = (lat->n_states + threads - 1) / threads;
-  nfst_beta_to_dense_kernel<<<blocks, threads, 0, static_cast<cudaStream_t>(cuda_stream)>>>(*lat, beta, orig_state, k,
-                                                                                            dense_states, out);
+  cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+  if (beta_f64)
+    nfst_beta_to_dense_kernel<double><<<blocks, threads, 0, st>>>(*lat, static_cast<const double*>(beta), orig_state, k,
+                                                                  dense_states, out);
+  else
+    nfst_beta_to_dense_kernel<float><<<blocks, threads, 0, st>>>(*lat, static_cast<const float*>(beta), orig_state, k,
+                                                                 dense_states, out);
   NFST_CUDA_OK(cudaGetLastError());
   return NFST_OK;
 }

@@ -22,6 +22,7 @@ from typing import Optional, Tuple
 import torch
 
 from . import _lib
+from . import pack as pack_mod
 from .pack import LaunchGroup, PackedLattices, pack_dense
 
 # number of library kernels launched since import (bench.py reports the per-step count)
@@ -32,6 +33,29 @@ def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
     return None if t is None else t.data_ptr()
 
 
+# per-state-vector shared-memory window (bytes); tests shrink it to exercise the
+# global-memory path behind the window
+WINDOW_BYTES_MAX = pack_mod.WINDOW_BYTES_MAX
+# lattices deeper than this default to float64 state vectors (see resolve_state_dtype)
+F64_DEPTH = 128
+
+
+def resolve_state_dtype(packed: PackedLattices, state_dtype="auto") -> torch.dtype:
+    """float32 or float64 for alpha / beta / logZ.
+
+    An fp32 log-value x is only known to ulp(|x|)/2 ~ 6e-8*|x| and that rounding is
+    committed at every level, so posteriors of deep lattices (|alpha| in the hundreds or
+    thousands) cannot be 1e-5-accurate with fp32 state.  "auto" therefore uses float64 for
+    lattices deeper than F64_DEPTH levels -- they are latency-bound, the wider state costs
+    nothing measurable -- and float32 otherwise.
+    """
+    if state_dtype == "auto" or state_dtype is None:
+        return torch.float64 if packed.max_levels > F64_DEPTH else torch.float32
+    if state_dtype in (torch.float32, torch.float64):
+        return state_dtype
+    raise ValueError("state_dtype must be 'auto', torch.float32 or torch.float64")
+
+
 def _check_f32(name: str, t: Optional[torch.Tensor], n: int, dev: torch.device) -> Optional[torch.Tensor]:
     if t is None:
         return None
@@ -39,16 +63,20 @@ def _check_f32(name: str, t: Optional[torch.Tensor], n: int, dev: torch.device) 
         raise RuntimeError(f"{name} must live on {dev} (nfst_b200 has no CPU fallback), got {t.device}")
     if t.numel() != n:
         raise ValueError(f"{name} must have {n} elements, got {t.numel()}")
-    return t.detach().to(torch.float32).contiguous()
+    t = t.detach().to(torch.float32).contiguous()
+    if t.data_ptr() % 16:
+        t = t.clone()  # the kernels read scores with 128-bit loads
+    return t
 
 
-def _launch(g: LaunchGroup, n_state_arrays_in_smem: bool = True) -> "_lib.LaunchC":
+def _launch(g: LaunchGroup, st_dtype: torch.dtype) -> "_lib.LaunchC":
     c = _lib.LaunchC()
     c.lattice_ids = g.ids.data_ptr()
     c.n_ids = g.n
     c.block_threads = g.block_threads
-    c.state_smem_cap = g.state_cap
-    c.level_smem_cap = g.level_cap
+    f64 = st_dtype == torch.float64
+    c.window_states = g.window_states(8 if f64 else 4, WINDOW_BYTES_MAX)
+    c.state_f64 = int(f64)
     return c
 
 
@@ -59,6 +87,8 @@ def _scores(packed: PackedLattices, arc_scores, theta):
     a = _check_f32("arc_scores", arc_scores, packed.n_arcs, dev)
     if packed.static_scores is not None:
         a = packed.static_scores if a is None else (a + packed.static_scores)
+    if packed.n_arcs == 0:
+        a = None
     t = _check_f32("theta", theta, packed.vocab, dev)
     c = _lib.ScoresC()
     c.arc_scores = _ptr(a)
@@ -70,19 +100,20 @@ def _stream(dev) -> int:
     return torch.cuda.current_stream(dev).cuda_stream
 
 
-def lattice_forward(packed: PackedLattices, arc_scores=None, theta=None) -> Tuple[torch.Tensor, torch.Tensor]:
-    """alpha[S] (log space, packed state order) and logZ[B]."""
+def lattice_forward(packed: PackedLattices, arc_scores=None, theta=None, *, state_dtype="auto"
+                    ) -> Tuple[torch.Tensor, torch.Tensor]:
+    """alpha[S] (log space, packed state order) and logZ[B], in the state dtype."""
     global launch_count
     lib = _lib.load()
     dev = packed.device
     sc, keep = _scores(packed, arc_scores, theta)
-    alpha = torch.empty(packed.n_states, dtype=torch.float32, device=dev)
-    logz = torch.empty(packed.n_lattices, dtype=torch.float32, device=dev)
+    st = resolve_state_dtype(packed, state_dtype)
+    alpha = torch.empty(packed.n_states, dtype=st, device=dev)
+    logz = torch.empty(packed.n_lattices, dtype=st, device=dev)
     with torch.cuda.device(dev):
-        st = _stream(dev)
+        stream = _stream(dev)
         for g in packed.groups:
-            lc = _launch(g)
-            _lib.check(lib.nfst_fwd_f32(packed.c_struct(), lc, sc, alpha.data_ptr(), logz.data_ptr(), st))
+            _lib.check(lib.nfst_fwd_f32(packed.c_struct(), _launch(g, st), sc, alpha.data_ptr(), logz.data_ptr(), stream))
             launch_count += 1
     del keep
     return alpha, logz
@@ -100,36 +131,39 @@ def lattice_backward(
     want_post: bool = False,
     want_dtheta: bool = False,
     want_viterbi: bool = False,
+    state_dtype="auto",
 ):
     """Fused backward pass.  Returns a dict with the requested outputs among
-    ``beta[S]``, ``logz_bwd[B]``, ``post[A]``, ``dtheta[V]``, ``delta[S]``, ``backptr[S]``,
-    ``vit_score[B]``."""
+    ``beta[S]``, ``logz_bwd[B]`` (state dtype), ``post[A]``, ``dtheta[V]`` (float32),
+    ``delta[S]``, ``backptr[S]``, ``vit_score[B]`` (float32 / int32)."""
     global launch_count
     lib = _lib.load()
     dev = packed.device
     sc, keep = _scores(packed, arc_scores, theta)
     S, A, B, V = packed.n_states, packed.n_arcs, packed.n_lattices, packed.vocab
     logs = want_beta or want_post or want_dtheta
+    if (want_post or want_dtheta) and (alpha is None or logz is None):
+        raise ValueError("posteriors need alpha and logz from lattice_forward")
+    st = alpha.dtype if alpha is not None else resolve_state_dtype(packed, state_dtype)
+    if alpha is not None and (logz.dtype != st or alpha.numel() != S or logz.numel() != B):
+        raise ValueError("alpha / logz must come from lattice_forward on the same packed batch")
     out = {}
     f32 = dict(dtype=torch.float32, device=dev)
-    beta = torch.empty(S, **f32) if logs else None
-    logz_bwd = torch.empty(B, **f32) if logs else None
+    beta = torch.empty(S, dtype=st, device=dev) if logs else None
+    logz_bwd = torch.empty(B, dtype=st, device=dev) if logs else None
     post = torch.empty(A, **f32) if want_post else None
     dtheta = torch.zeros(V, **f32) if want_dtheta else None
     delta = torch.empty(S, **f32) if want_viterbi else None
     backptr = torch.empty(S, dtype=torch.int32, device=dev) if want_viterbi else None
     vit = torch.empty(B, **f32) if want_viterbi else None
-    if (want_post or want_dtheta) and (alpha is None or logz is None):
-        raise ValueError("posteriors need alpha and logz from lattice_forward")
     g32 = _check_f32("grad_logz", grad_logz, B, dev)
     with torch.cuda.device(dev):
-        st = _stream(dev)
+        stream = _stream(dev)
         for g in packed.groups:
-            lc = _launch(g)
             _lib.check(
                 lib.nfst_bwd_fused_f32(
-                    packed.c_struct(), lc, sc, _ptr(alpha), _ptr(logz), _ptr(g32), _ptr(beta), _ptr(logz_bwd),
-                    _ptr(post), _ptr(dtheta), _ptr(delta), _ptr(backptr), _ptr(vit), st,
+                    packed.c_struct(), _launch(g, st), sc, _ptr(alpha), _ptr(logz), _ptr(g32), _ptr(beta),
+                    _ptr(logz_bwd), _ptr(post), _ptr(dtheta), _ptr(delta), _ptr(backptr), _ptr(vit), stream,
                 )
             )
             launch_count += 1
@@ -141,12 +175,13 @@ def lattice_backward(
     return out
 
 
-def lattice_forward_backward(packed: PackedLattices, arc_scores=None, theta=None, *, want_dtheta: bool = False):
+def lattice_forward_backward(packed: PackedLattices, arc_scores=None, theta=None, *, want_dtheta: bool = False,
+                             state_dtype="auto"):
     """(logZ[B], alpha[S], beta[S], post[A]) -- plus dtheta[V] when ``want_dtheta``.
 
     logZ is ``beta[start]`` (the reference's definition, ``log beta[0]``); posteriors are
-    normalised with the forward logZ and agree to fp32 round-off."""
-    alpha, logz_f = lattice_forward(packed, arc_scores, theta)
+    normalised with the forward logZ and agree to round-off."""
+    alpha, logz_f = lattice_forward(packed, arc_scores, theta, state_dtype=state_dtype)
     r = lattice_backward(packed, arc_scores, theta, alpha=alpha, logz=logz_f, want_beta=True, want_post=True,
                          want_dtheta=want_dtheta)
     if want_dtheta:
@@ -164,8 +199,8 @@ class LatticeLogPartition(torch.autograd.Function):
     """
 
     @staticmethod
-    def forward(ctx, arc_scores, theta, packed: PackedLattices):
-        alpha, logz = lattice_forward(packed, arc_scores, theta)
+    def forward(ctx, arc_scores, theta, packed: PackedLattices, state_dtype="auto"):
+        alpha, logz = lattice_forward(packed, arc_scores, theta, state_dtype=state_dtype)
         ctx.packed = packed
         ctx.save_for_backward(alpha, logz, arc_scores if arc_scores is not None else torch.empty(0),
                               theta if theta is not None else torch.empty(0))
@@ -179,16 +214,17 @@ class LatticeLogPartition(torch.autograd.Function):
         need_a = has_a and ctx.needs_input_grad[0]
         need_t = has_t and ctx.needs_input_grad[1]
         if not (need_a or need_t):
-            return None, None, None
+            return None, None, None, None
         r = lattice_backward(
             ctx.packed, a if has_a else None, t if has_t else None, alpha=alpha, logz=logz,
             grad_logz=grad_logz.contiguous(), want_beta=False, want_post=need_a, want_dtheta=need_t,
         )
-        return (r.get("post") if need_a else None), (r.get("dtheta") if need_t else None), None
+        return (r.get("post") if need_a else None), (r.get("dtheta") if need_t else None), None, None
 
 
-def lattice_log_partition(packed: PackedLattices, arc_scores=None, theta=None) -> torch.Tensor:
-    return LatticeLogPartition.apply(arc_scores, theta, packed)
+def lattice_log_partition(packed: PackedLattices, arc_scores=None, theta=None, state_dtype="auto") -> torch.Tensor:
+    """logZ[B] with autograd (state dtype: float32, or float64 for deep lattices)."""
+    return LatticeLogPartition.apply(arc_scores, theta, packed, state_dtype)
 
 
 def lattice_viterbi(packed: PackedLattices, arc_scores=None, theta=None):
@@ -235,8 +271,8 @@ def beta_dense(packed: PackedLattices, beta: torch.Tensor, k: int = 1, dense_sta
         dense_states = packed.dense_shape[1]
     out = torch.zeros(packed.n_lattices * k, dense_states, dtype=torch.float32, device=dev)
     with torch.cuda.device(dev):
-        _lib.check(lib.nfst_beta_to_dense_f32(packed.c_struct(), beta.data_ptr(), packed.orig_state.data_ptr(), k,
-                                              dense_states, out.data_ptr(), _stream(dev)))
+        _lib.check(lib.nfst_beta_to_dense(packed.c_struct(), beta.data_ptr(), int(beta.dtype == torch.float64),
+                                          packed.orig_state.data_ptr(), k, dense_states, out.data_ptr(), _stream(dev)))
         launch_count += 1
     return out
 

@@ -29,9 +29,10 @@ import torch
 
 from . import _lib
 
-# lattices with at most this many states keep their DP vectors in shared memory
-STATE_SMEM_MAX = 12288
-LEVEL_SMEM_MAX = 4096
+# shared-memory window of the most recent per-state DP values, in bytes per state vector
+WINDOW_BYTES_MAX = 64 * 1024
+# a chunk targets 4 arcs per thread minus slack, so that one 128-bit load per thread covers it
+CHUNK_SLACK = 24
 
 
 @dataclasses.dataclass
@@ -40,10 +41,13 @@ class LaunchGroup:
 
     ids: torch.Tensor  # int32 [n], lattice indices, heaviest first
     n: int
-    block_threads: int
-    state_cap: int  # largest lattice of the group in states; 0 = DP vectors in global memory
-    level_cap: int  # 0 = level table read from global memory
+    block_threads: int  # 32 / 64 / 128 / 256; the lattices' chunks were cut for this size
+    max_states: int  # largest lattice of the group, in states (sizes the shared-memory window)
     n_arcs: int
+
+    def window_states(self, state_bytes: int = 4, window_bytes_max: int = WINDOW_BYTES_MAX) -> int:
+        cap = max(32, window_bytes_max // state_bytes)
+        return max(32, min(_pow2_ceil(self.max_states), _pow2_floor(cap)))
 
 
 class PackedLattices:
@@ -52,6 +56,7 @@ class PackedLattices:
     _INT_FIELDS = (
         "state_off", "level_off", "level_ptr", "start_state", "sink_off", "sinks",
         "in_ptr", "src_in", "label_in", "in2out", "out_ptr", "dst_out", "label_out",
+        "fwd_chunk_off", "fwd_chunks", "bwd_chunk_off", "bwd_chunks",
     )
 
     def __init__(self, **kw):
@@ -113,7 +118,7 @@ class PackedLattices:
             c.n_lattices, c.n_states, c.n_arcs, c.vocab = self.n_lattices, self.n_states, self.n_arcs, self.vocab
             for f in self._INT_FIELDS:
                 t = getattr(self, f)
-                assert t.dtype == torch.int32 and t.is_contiguous()
+                assert t.dtype == torch.int32 and t.is_contiguous() and t.data_ptr() % 16 == 0
                 setattr(c, f, t.data_ptr())
             c.lanes_in_log2 = self.lanes_in_log2.data_ptr()
             c.lanes_out_log2 = self.lanes_out_log2.data_ptr()
@@ -138,30 +143,63 @@ def _pow2_ceil(x: int) -> int:
     return 1 if x <= 1 else 1 << (x - 1).bit_length()
 
 
-def build_groups(stats, state_smem_max: int, dev) -> List[LaunchGroup]:
-    """Partition the batch into launches: lattices with the same block size, split by
-    whether their DP vectors fit in shared memory; heaviest lattices first."""
-    smem_ok = (stats["states"] <= state_smem_max).to(torch.int64)
-    gkey = stats["block_class"] * 2 + smem_ok
+def _pow2_floor(x: int) -> int:
+    return 1 << (max(int(x), 1).bit_length() - 1)
+
+
+def _build_chunks(ptr, slot, level_first, lat_of_state, target, n_lattices, descending):
+    """Cut every level into chunks of consecutive states whose CSR segments END in the same
+    `target`-sized window of the level's arc range (so a chunk has fewer than 2*target arcs
+    unless it is a single heavy state, which gets a chunk of its own).
+
+    ptr [S+1] CSR row pointer; slot [S] global level index of each state; level_first [S]
+    first state of the state's level; target [S] per-state chunk target (its lattice's).
+    Returns (chunk_off [B+1], chunks [NC, 4] = arc_begin, arc_end, state_begin, state_end).
+    """
+    S = ptr.numel() - 1
+    dev = ptr.device
+    deg = ptr[1:] - ptr[:-1]
+    rel_end = ptr[1:] - ptr[level_first]
+    ck = torch.clamp(torch.div(rel_end - 1, target, rounding_mode="floor"), min=0)
+    heavy = (deg > target).to(torch.int64)
+    hk = 2 * torch.cumsum(heavy, 0) - heavy
+    new = torch.ones(S, dtype=torch.bool, device=dev)
+    if S > 1:
+        new[1:] = (slot[1:] != slot[:-1]) | (ck[1:] != ck[:-1]) | (hk[1:] != hk[:-1])
+    sb = torch.nonzero(new).squeeze(1)
+    se = torch.cat([sb[1:], torch.tensor([S], device=dev, dtype=sb.dtype)])
+    chunks = torch.stack([ptr[sb], ptr[se], sb, se], dim=1)
+    clat = lat_of_state[sb]
+    chunk_off = _excl_cumsum(torch.bincount(clat, minlength=n_lattices))
+    if descending:
+        n = chunks.shape[0]
+        pos = torch.arange(n, device=dev)
+        rev = chunk_off[clat] + (chunk_off[clat + 1] - 1 - pos)
+        chunks = chunks[rev]
+    return chunk_off, chunks.to(torch.int32).contiguous()
+
+
+def build_groups(stats, dev) -> List[LaunchGroup]:
+    """Partition the batch into launches: lattices cut for the same block size share a
+    launch; heaviest lattices first (longest-processing-time order)."""
+    gkey = stats["block_class"]
     groups: List[LaunchGroup] = []
     for key in sorted(set(gkey.tolist()), reverse=True):
         members = torch.nonzero(gkey == key).squeeze(1)
         members = members[torch.argsort(stats["arcs"][members], descending=True, stable=True)]
-        lcap = int(stats["levels"][members].max())
         groups.append(
             LaunchGroup(
                 ids=members.to(torch.int32).to(dev),
                 n=int(members.numel()),
-                block_threads=1 << (key >> 1),
-                state_cap=int(stats["states"][members].max()) if (key & 1) else 0,
-                level_cap=lcap if lcap <= LEVEL_SMEM_MAX else 0,
+                block_threads=1 << key,
+                max_states=int(stats["states"][members].max()),
                 n_arcs=int(stats["arcs"][members].sum()),
             )
         )
     return groups
 
 
-def concat_packed(parts: List["PackedLattices"], state_smem_max: int = STATE_SMEM_MAX) -> "PackedLattices":
+def concat_packed(parts: List["PackedLattices"]) -> "PackedLattices":
     """Collate independently packed lattices (e.g. cached per example) into one batch."""
     if not parts:
         raise ValueError("empty batch")
@@ -169,7 +207,7 @@ def concat_packed(parts: List["PackedLattices"], state_smem_max: int = STATE_SME
     vocab = parts[0].vocab
     if any(p.vocab != vocab for p in parts):
         raise ValueError("all parts must share one vocabulary")
-    S = A = B = Lv = 0
+    S = A = B = Lv = nfc = nbc = 0
     acc = {f: [] for f in PackedLattices._INT_FIELDS}
     extra = {k: [] for k in ("lanes_in_log2", "lanes_out_log2", "orig_state", "arc_origin", "arc_off", "n_levels")}
     static = []
@@ -189,6 +227,13 @@ def concat_packed(parts: List["PackedLattices"], state_smem_max: int = STATE_SME
         acc["out_ptr"].append(cut(p.out_ptr + A))
         acc["dst_out"].append(p.dst_out + S)
         acc["label_out"].append(p.label_out)
+        shift = torch.tensor([A, A, S, S], dtype=torch.int32, device=dev)
+        acc["fwd_chunk_off"].append(cut(p.fwd_chunk_off + nfc))
+        acc["fwd_chunks"].append(p.fwd_chunks + shift)
+        acc["bwd_chunk_off"].append(cut(p.bwd_chunk_off + nbc))
+        acc["bwd_chunks"].append(p.bwd_chunks + shift)
+        nfc += int(p.fwd_chunks.shape[0])
+        nbc += int(p.bwd_chunks.shape[0])
         extra["lanes_in_log2"].append(p.lanes_in_log2)
         extra["lanes_out_log2"].append(p.lanes_out_log2)
         extra["orig_state"].append(p.orig_state)
@@ -210,7 +255,7 @@ def concat_packed(parts: List["PackedLattices"], state_smem_max: int = STATE_SME
     kw.update({f: torch.cat(v).contiguous() for f, v in extra.items()})
     return PackedLattices(
         n_lattices=B, n_states=S, n_arcs=A, vocab=vocab, static_scores=torch.cat(static) if static else None,
-        dense_shape=None, groups=build_groups(stats, state_smem_max, dev), max_levels=max(p.max_levels for p in parts),
+        dense_shape=None, groups=build_groups(stats, dev), max_levels=max(p.max_levels for p in parts),
         stats=stats, **kw,
     )
 
@@ -226,7 +271,6 @@ def pack_arcs(
     start_state: int = 0,
     static_scores: Optional[torch.Tensor] = None,
     dense_shape=None,
-    state_smem_max: int = STATE_SMEM_MAX,
 ) -> PackedLattices:
     """Pack an arc list.  ``arc_lattice/src/dst/label`` are [A0] integer tensors (local
     state ids), ``n_states`` is [B].  Raises ``ValueError`` for cyclic lattices (the
@@ -315,17 +359,23 @@ def pack_arcs(
         return torch.clamp(torch.round(torch.log2(torch.clamp(avg * 0.75, min=1.0))), 0, 5).to(torch.int64)
 
     lg_in, lg_out = lanes_log2(avg_in), lanes_log2(avg_out)
+    # block size: 4 arcs per thread over the widest level (in either direction), 32..256 threads
+    lvl_first_state = level_ptr[slot]  # [S] first state of each state's level
     slot_lat = torch.repeat_interleave(torch.arange(B, device=dev), n_levels + 1)
-    width = torch.zeros(B, dtype=torch.int64, device=dev).scatter_reduce(0, slot_lat, counts, reduce="amax")
-    threads = width * (1 << torch.maximum(lg_in, lg_out))
-    block_class = torch.clamp(torch.ceil(torch.log2(torch.clamp(threads.to(torch.float64), min=32.0))), 5, 10).to(torch.int64)
+    lvl_end = torch.cat([level_ptr[1:], level_ptr.new_tensor([S])])
+    lvl_arcs = torch.maximum(in_ptr[lvl_end] - in_ptr[level_ptr], out_ptr[lvl_end] - out_ptr[level_ptr])
+    width_arcs = torch.zeros(B, dtype=torch.int64, device=dev).scatter_reduce(0, slot_lat, lvl_arcs, reduce="amax")
+    block_class = torch.clamp(torch.ceil(torch.log2(torch.clamp(width_arcs.to(torch.float64) / 4.0, min=32.0))), 5, 8).to(torch.int64)
+    target_state = (4 * (1 << block_class) - CHUNK_SLACK)[lt_s]
+    fwd_chunk_off, fwd_chunks = _build_chunks(in_ptr, slot, lvl_first_state, lt_s, target_state, B, False)
+    bwd_chunk_off, bwd_chunks = _build_chunks(out_ptr, slot, lvl_first_state, lt_s, target_state, B, True)
     stats = {
         "arcs": A_b.to(torch.int64).cpu(),
         "states": S_b.cpu(),
         "levels": n_levels.cpu(),
         "block_class": block_class.cpu(),
     }
-    groups = build_groups(stats, state_smem_max, dev)
+    groups = build_groups(stats, dev)
 
     i32 = lambda t: t.to(torch.int32).contiguous()  # noqa: E731
     return PackedLattices(
@@ -333,6 +383,7 @@ def pack_arcs(
         state_off=i32(state_off), level_off=i32(level_off), level_ptr=i32(level_ptr), start_state=i32(start_packed),
         sink_off=i32(sink_off), sinks=i32(sinks), in_ptr=i32(in_ptr), src_in=i32(src_in), label_in=i32(label_in),
         in2out=i32(in2out), out_ptr=i32(out_ptr), dst_out=i32(dst_out), label_out=i32(label_out),
+        fwd_chunk_off=i32(fwd_chunk_off), fwd_chunks=fwd_chunks, bwd_chunk_off=i32(bwd_chunk_off), bwd_chunks=bwd_chunks,
         lanes_in_log2=lg_in.to(torch.uint8).contiguous(), lanes_out_log2=lg_out.to(torch.uint8).contiguous(),
         orig_state=i32(orig_state), arc_origin=origin.contiguous(), arc_off=i32(arc_off), n_levels=i32(n_levels),
         static_scores=None if static_scores is None else static_scores[origin].to(torch.float32).contiguous(),
@@ -372,8 +423,8 @@ def dense_arcs(transition: torch.Tensor):
     return b * S + s, l, transition[b, s, l].to(torch.int64)
 
 
-def pack_dense(emission: Optional[torch.Tensor], transition: torch.Tensor, *, weighted: Optional[bool] = None,
-               state_smem_max: int = STATE_SMEM_MAX) -> PackedLattices:
+def pack_dense(emission: Optional[torch.Tensor], transition: torch.Tensor, *,
+               weighted: Optional[bool] = None) -> PackedLattices:
     """Pack collate()-style dense tables ``emission[B, S, V]`` / ``transition[B, S, V]``.
 
     ``weighted``: treat ``emission`` as float log-weights (``scorers.py:1011-1013,1026-1027``)
@@ -391,8 +442,7 @@ def pack_dense(emission: Optional[torch.Tensor], transition: torch.Tensor, *, we
     if weighted:
         static = emission.reshape(-1)[row * V + lab].to(torch.float32)
     n_states = torch.full((B,), S, dtype=torch.int64, device=transition.device)
-    packed = pack_arcs(row // S, row % S, dst, lab, n_states, V, static_scores=static, dense_shape=(B, S, V),
-                       state_smem_max=state_smem_max)
+    packed = pack_arcs(row // S, row % S, dst, lab, n_states, V, static_scores=static, dense_shape=(B, S, V))
     # arc_origin indexes the arc list; turn it into the dense cell index (b*S+s)*V+l
     packed.arc_origin = (row * V + lab)[packed.arc_origin].contiguous()
     return packed

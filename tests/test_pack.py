@@ -76,6 +76,27 @@ def check_structure(p):
     # launch groups partition the batch
     ids = np.concatenate([_np(g.ids) for g in p.groups])
     assert sorted(ids.tolist()) == list(range(p.n_lattices))
+    block = np.zeros(p.n_lattices, dtype=np.int64)
+    for g in p.groups:
+        block[_np(g.ids)] = g.block_threads
+        assert g.block_threads in (32, 64, 128, 256)
+    # chunks: each direction tiles the states of a lattice exactly once, level by level
+    for off, chunks, ptr, desc in ((p.fwd_chunk_off, p.fwd_chunks, in_ptr, False),
+                                   (p.bwd_chunk_off, p.bwd_chunks, out_ptr, True)):
+        off, chunks = _np(off), _np(chunks)
+        assert off[0] == 0 and off[-1] == len(chunks)
+        for b in range(p.n_lattices):
+            ck = chunks[off[b] : off[b + 1]]
+            if desc:
+                ck = ck[::-1]
+            assert ck[0, 2] == state_off[b] and ck[-1, 3] == state_off[b + 1]
+            np.testing.assert_array_equal(ck[1:, 2], ck[:-1, 3])  # contiguous in state space
+            np.testing.assert_array_equal(ck[:, 0], ptr[ck[:, 2]])
+            np.testing.assert_array_equal(ck[:, 1], ptr[ck[:, 3]])
+            assert np.all(level[ck[:, 2]] == level[ck[:, 3] - 1])  # never crosses a level
+            cap = 8 * block[b]
+            big = (ck[:, 1] - ck[:, 0]) > cap
+            assert np.all((ck[big, 3] - ck[big, 2]) == 1)  # only a single heavy state may exceed the tile
 
 
 @pytest.mark.parametrize("seed", [0, 1, 2])
