@@ -314,17 +314,27 @@ def main():
 
         from nfst_b200.pack import PackedLattices
 
+        # device-side landing buffers (allocated once; refilled from pinned host memory every step)
+        land = {f: (PackedLattices.alloc_padded(host[f].numel(), host[f].dtype, dev) if f in PackedLattices._ARC_FIELDS
+                    else torch.empty_like(host[f], device=dev)) for f in fields}
+        land_scores = torch.empty_like(host_scores, device=dev)
+        land_ids = [torch.empty_like(h, device=dev) for h in host_ids]
+
         def e2e_step():
-            kw = {f: host[f].to(dev, non_blocking=True) for f in fields}
+            for f in fields:
+                land[f].copy_(host[f], non_blocking=True)
+            for d_, h_ in zip(land_ids, host_ids):
+                d_.copy_(h_, non_blocking=True)
+            land_scores.copy_(host_scores, non_blocking=True)
+            kw = dict(land)
             # label arrays are not read when scores are per-arc; keep the resident ones
             kw.update(label_in=packed.label_in, label_out=packed.label_out, orig_state=packed.orig_state,
                       arc_origin=packed.arc_origin, arc_off=packed.arc_off, n_levels=packed.n_levels,
                       level_off=packed.level_off, level_ptr=packed.level_ptr)
-            groups = [dataclasses.replace(g, ids=h.to(dev, non_blocking=True)) for g, h in zip(packed.groups, host_ids)]
+            groups = [dataclasses.replace(g, ids=d_) for g, d_ in zip(packed.groups, land_ids)]
             p = PackedLattices(n_lattices=B, n_states=S, n_arcs=A, vocab=packed.vocab, static_scores=None,
                                dense_shape=None, groups=groups, max_levels=packed.max_levels, stats=packed.stats, **kw)
-            sc = host_scores.to(dev, non_blocking=True)
-            logz, alpha, beta, post = nb.lattice_forward_backward(p, arc_scores=sc)
+            logz, alpha, beta, post = nb.lattice_forward_backward(p, arc_scores=land_scores)
             logz_host.copy_(logz, non_blocking=True)
             torch.cuda.current_stream().synchronize()
             return float(logz_host[0])

@@ -126,17 +126,16 @@ __host__ __device__ inline SmemPlan smem_plan(int W, int cap, int st_bytes, int 
   p.win = o;
   o += log_arrays ? static_cast<size_t>(W) * st_bytes : 0;
   p.vbuf = o;
-  o += log_arrays ? static_cast<size_t>(cap) * st_bytes : 0;
+  o += log_arrays ? static_cast<size_t>(cap + 8) * st_bytes : 0;
   p.abuf = o;
-  o += (bwd && post) ? static_cast<size_t>(cap) * st_bytes : 0;
   p.dwin = o;
   o += (bwd && trop) ? static_cast<size_t>(W) * 4 : 0;
   p.tbuf = o;
-  o += (bwd && trop) ? static_cast<size_t>(cap) * 4 : 0;
+  o += (bwd && trop) ? static_cast<size_t>(cap + 8) * 4 : 0;
   p.segp = o;
-  o += static_cast<size_t>(cap + 4) * 4;
+  o += static_cast<size_t>(cap + 8) * 4;
   p.lbuf = o;
-  o += (bwd && with_dtheta) ? static_cast<size_t>(cap) * 4 : 0;
+  o += (bwd && with_dtheta) ? static_cast<size_t>(cap + 8) * 4 : 0;
   p.theta = o;
   o += with_theta ? static_cast<size_t>(vocab) * 4 : 0;
   p.dtheta = o;
@@ -148,8 +147,52 @@ __host__ __device__ inline SmemPlan smem_plan(int W, int cap, int st_bytes, int 
 // =====================================================================================
 // forward: alpha
 // =====================================================================================
+// Tile layout: tile slot i holds the arc at position (a0 & ~3) + i, so the 4 arcs of one
+// 128-bit load land in one aligned 128-bit shared-memory store.  Slots outside [a0, a1) hold
+// values of neighbouring arcs (the per-arc arrays are zero-padded by 4, so every index read
+// is a valid one); phase 2 never looks at them.
 template <typename ST>
-__global__ void __launch_bounds__(256)
+struct Vec4;
+template <>
+struct Vec4<float> { using type = float4; };
+template <>
+struct Vec4<double> { using type = double4; };
+
+template <typename ST>
+__device__ __forceinline__ void store4(ST* p, ST a, ST b, ST c, ST d);
+template <>
+__device__ __forceinline__ void store4<float>(float* p, float a, float b, float c, float d) {
+  *reinterpret_cast<float4*>(p) = make_float4(a, b, c, d);
+}
+template <>
+__device__ __forceinline__ void store4<double>(double* p, double a, double b, double c, double d) {
+  *reinterpret_cast<double2*>(p) = make_double2(a, b);
+  *reinterpret_cast<double2*>(p + 2) = make_double2(c, d);
+}
+
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kLn2 = 0.6931471805599453f;
+// exp(x) for x <= 0 and log(x) for x >= 1 on the SFU (ex2.approx / lg2.approx)
+__device__ __forceinline__ float fast_exp(float x) { return exp2f(x * kLog2e); }
+__device__ __forceinline__ float fast_log(float x) { return __log2f(x) * kLn2; }
+
+// segmented logsumexp of tile[b0, b1) by one lane group (G lanes, lane_g = my lane)
+template <typename ST>
+__device__ __forceinline__ ST seg_lse(const ST* __restrict__ tile, int b0, int b1, int G, int lane_g, ST neg_inf,
+                                      ST* m_out) {
+  ST m = neg_inf;
+  for (int i = b0 + lane_g; i < b1; i += G) m = max(m, tile[i]);
+  for (int o = G >> 1; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+  float sum = 0.0f;
+  if (m > neg_inf)
+    for (int i = b0 + lane_g; i < b1; i += G) sum += fast_exp(static_cast<float>(tile[i] - m));
+  for (int o = G >> 1; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  *m_out = m;
+  return (m > neg_inf) ? m + static_cast<ST>(fast_log(sum)) : neg_inf;
+}
+
+template <typename ST>
+__global__ void __launch_bounds__(256, 4)
     nfst_fwd_kernel(const nfst_packed_lattices_t L, const int32_t* __restrict__ ids, int W,
                     const float* __restrict__ arc_scores, const float* __restrict__ theta, int theta_smem, ST* alpha,
                     ST* __restrict__ logz) {
@@ -166,7 +209,7 @@ __global__ void __launch_bounds__(256)
   const int base_s = L.state_off[b];
   const int start = L.start_state[b];
   const int wmask = W - 1;
-  const int lg0 = L.lanes_in_log2[b];
+  const bool whole = (L.state_off[b + 1] - base_s) <= W;  // the whole lattice fits the window
   const float* th = theta;
   if (theta && theta_smem) {
     float* sth = reinterpret_cast<float*>(smem_raw + plan.theta);
@@ -179,83 +222,93 @@ __global__ void __launch_bounds__(256)
   int c = L.fwd_chunk_off[b];
   const int c_end = L.fwd_chunk_off[b + 1];
 
-  // ---- register pipeline: arc arrays of chunk c+1 / c+2 are in flight while chunk c is reduced
+  // ---- register pipeline: the arc arrays of chunk c+1 (and the score indices of chunk c+2)
+  // are in flight while chunk c is reduced, so HBM streaming does not wait on the barriers
   const int4 z4 = make_int4(0, 0, 0, 0);
   auto gbase = [&](const int4& k) { return (k.x & ~3) + tid * 4; };
   auto ld_src = [&](const int4& k) { const int g = gbase(k); return g < k.y ? ldg4(L.src_in + g) : z4; };
   auto ld_idx = [&](const int4& k) { const int g = gbase(k); return (arc_scores && g < k.y) ? ldg4(L.in2out + g) : z4; };
   auto ld_lab = [&](const int4& k) { const int g = gbase(k); return (th && g < k.y) ? ldg4(L.label_in + g) : z4; };
-  // scores of the (up to) 4 arcs of this thread in chunk k; only arcs inside the chunk are
-  // touched, so whatever the 128-bit loads over-read is never used as an index
-  auto gather_w = [&](const int4& k, int g, const int4& idx, const int4& lab) {
-    float wv[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const int a = g + e;
-      if (a >= k.x && a < k.y) {
-        if (arc_scores) wv[e] = __ldg(arc_scores + elem(idx, e));
-        if (th) wv[e] += th[elem(lab, e)];
-      }
+  auto gather_w = [&](const int4& idx, const int4& lab) {  // padded arrays: every index is a valid one
+    float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (arc_scores) {
+      w.x = __ldg(arc_scores + idx.x); w.y = __ldg(arc_scores + idx.y);
+      w.z = __ldg(arc_scores + idx.z); w.w = __ldg(arc_scores + idx.w);
     }
-    return make_float4(wv[0], wv[1], wv[2], wv[3]);
+    if (th) { w.x += th[lab.x]; w.y += th[lab.y]; w.z += th[lab.z]; w.w += th[lab.w]; }
+    return w;
   };
   int4 k0 = chunk_at(chunks, c, c_end), k1 = chunk_at(chunks, c + 1, c_end);
   int4 src_c = ld_src(k0);
-  float4 w_c = gather_w(k0, gbase(k0), ld_idx(k0), ld_lab(k0));
+  float4 w_c = gather_w(ld_idx(k0), ld_lab(k0));
   int4 idx_n = ld_idx(k1), lab_n = ld_lab(k1);
 
   for (; c < c_end; ++c) {
     const int4 k2 = chunk_at(chunks, c + 2, c_end);
     const int4 src_n = ld_src(k1);
-    const float4 w_n = gather_w(k1, gbase(k1), idx_n, lab_n);
+    const float4 w_n = gather_w(idx_n, lab_n);
     const int4 idx_nn = ld_idx(k2), lab_nn = ld_lab(k2);
 
     const int a0 = k0.x, a1 = k0.y, s0 = k0.z, s1 = k0.w;
     const int n = a1 - a0, ns = s1 - s0;
+    const int base4 = a0 & ~3;
     if (n <= cap) {
-      // ---- phase 1: arc-parallel, values into the tile
-      for (int j = tid; j <= ns; j += NT) segp[j] = __ldg(L.in_ptr + s0 + j) - a0;
-      const int lo = s0 - W;
-      int g = gbase(k0);
+      // ---- phase 1: arc-parallel, w + alpha[src] into the tile
+      for (int j = tid; j <= ns; j += NT) segp[j] = __ldg(L.in_ptr + s0 + j) - base4;
+      const int lo = whole ? static_cast<int>(0x80000000) : s0 - W;
+      int g = base4 + tid * 4;
       int4 sv = src_c;
       float4 wv = w_c;
       while (g < a1) {
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int a = g + e;
-          if (a >= a0 && a < a1) {
-            const int src = elem(sv, e);
-            const ST av = (src >= lo) ? win[(src - base_s) & wmask] : alpha[src];
-            vbuf[a - a0] = static_cast<ST>(elem(wv, e)) + av;
-          }
+        ST v0, v1, v2, v3;
+        if (min(min(sv.x, sv.y), min(sv.z, sv.w)) >= lo) {
+          v0 = win[(sv.x - base_s) & wmask]; v1 = win[(sv.y - base_s) & wmask];
+          v2 = win[(sv.z - base_s) & wmask]; v3 = win[(sv.w - base_s) & wmask];
+        } else {  // a source older than the window (or a neighbour's arc): global memory
+          v0 = sv.x >= lo ? win[(sv.x - base_s) & wmask] : alpha[sv.x];
+          v1 = sv.y >= lo ? win[(sv.y - base_s) & wmask] : alpha[sv.y];
+          v2 = sv.z >= lo ? win[(sv.z - base_s) & wmask] : alpha[sv.z];
+          v3 = sv.w >= lo ? win[(sv.w - base_s) & wmask] : alpha[sv.w];
         }
+        store4<ST>(vbuf + (g - base4), v0 + static_cast<ST>(wv.x), v1 + static_cast<ST>(wv.y),
+                   v2 + static_cast<ST>(wv.z), v3 + static_cast<ST>(wv.w));
         g += NT * 4;
         if (g < a1) {  // second pass of a long chunk: not prefetched
           sv = ldg4(L.src_in + g);
-          wv = gather_w(k0, g, arc_scores ? ldg4(L.in2out + g) : z4, th ? ldg4(L.label_in + g) : z4);
+          wv = gather_w(arc_scores ? ldg4(L.in2out + g) : z4, th ? ldg4(L.label_in + g) : z4);
         }
       }
       __syncthreads();
       // ---- phase 2: state-parallel segmented logsumexp over the tile
-      int lg = lg0;
-      while (lg < 5 && (ns << (lg + 1)) <= NT) ++lg;
-      const int G = 1 << lg, lane_g = tid & (G - 1), grp = tid >> lg, ngrp = NT >> lg;
-      for (int jb = 0; jb < ns; jb += ngrp) {
-        const int j = jb + grp;
-        const bool valid = j < ns;
-        const int b0 = valid ? segp[j] : 0, b1 = valid ? segp[j + 1] : 0;
-        ST m = neg_inf;
-        for (int i = b0 + lane_g; i < b1; i += G) m = max(m, vbuf[i]);
-        for (int o = G >> 1; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
-        float sum = 0.0f;
-        if (m > neg_inf)
-          for (int i = b0 + lane_g; i < b1; i += G) sum += __expf(static_cast<float>(vbuf[i] - m));
-        for (int o = G >> 1; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-        if (valid && lane_g == 0) {
+      if (ns * 2 > NT) {  // one thread per state
+        for (int j = tid; j < ns; j += NT) {
+          const int b0 = segp[j], b1 = segp[j + 1];
+          ST m = neg_inf;
+          for (int i = b0; i < b1; ++i) m = max(m, vbuf[i]);
+          float sum = 0.0f;
+          for (int i = b0; i < b1; ++i) sum += fast_exp(static_cast<float>(vbuf[i] - m));
           const int s = s0 + j;
-          const ST v = (s == start) ? static_cast<ST>(0) : lse_value(m, sum);
-          win[(s - base_s) & wmask] = v;
+          ST v = (b0 < b1 && m > neg_inf) ? m + static_cast<ST>(fast_log(sum)) : neg_inf;
+          if (s == start) v = 0;
+          if (s >= s1 - W) win[(s - base_s) & wmask] = v;  // only the newest W states own a slot
           alpha[s] = v;
+        }
+      } else {  // narrow chunk: 2^lg lanes per state so that the block stays busy
+        int lg = 1;
+        while (lg < 5 && (ns << (lg + 1)) <= NT) ++lg;
+        const int G = 1 << lg, lane_g = tid & (G - 1), grp = tid >> lg, ngrp = NT >> lg;
+        for (int jb = 0; jb < ns; jb += ngrp) {
+          const int j = jb + grp;
+          const bool valid = j < ns;
+          const int b0 = valid ? segp[j] : 0, b1 = valid ? segp[j + 1] : 0;
+          ST m;
+          ST v = seg_lse(vbuf, b0, b1, G, lane_g, neg_inf, &m);
+          if (valid && lane_g == 0) {
+            const int s = s0 + j;
+            if (s == start) v = 0;
+            if (s >= s1 - W) win[(s - base_s) & wmask] = v;
+            alpha[s] = v;
+          }
         }
       }
       __syncthreads();
@@ -271,7 +324,7 @@ __global__ void __launch_bounds__(256)
           if (arc_scores) w = arc_scores[L.in2out[a]];
           if (th) w += th[L.label_in[a]];
           const int src = L.src_in[a];
-          const ST av = (src >= s0 - W) ? win[(src - base_s) & wmask] : alpha[src];
+          const ST av = (whole || src >= s0 - W) ? win[(src - base_s) & wmask] : alpha[src];
           lse_add(m, sum, static_cast<ST>(w) + av);
         }
         const ST v0 = block_lse(m, sum);
@@ -299,7 +352,7 @@ __global__ void __launch_bounds__(256)
 // fused backward: beta (+ posteriors, dtheta) and/or Viterbi delta + backpointer
 // =====================================================================================
 template <typename ST, bool LOGS, bool TROP>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
     nfst_bwd_kernel(const nfst_packed_lattices_t L, const int32_t* __restrict__ ids, int W,
                     const float* __restrict__ arc_scores, const float* __restrict__ theta, int theta_smem,
                     int dtheta_smem, const ST* __restrict__ alpha, const ST* __restrict__ logz,
@@ -314,7 +367,6 @@ __global__ void __launch_bounds__(256)
       smem_plan(W, cap, sizeof(ST), L.vocab, true, LOGS, TROP, want_post, theta_smem != 0, dtheta_smem != 0);
   ST* win = reinterpret_cast<ST*>(smem_raw + plan.win);
   ST* vbuf = reinterpret_cast<ST*>(smem_raw + plan.vbuf);
-  ST* abuf = reinterpret_cast<ST*>(smem_raw + plan.abuf);
   float* dwin = reinterpret_cast<float*>(smem_raw + plan.dwin);
   float* tbuf = reinterpret_cast<float*>(smem_raw + plan.tbuf);
   int* segp = reinterpret_cast<int*>(smem_raw + plan.segp);
@@ -324,7 +376,7 @@ __global__ void __launch_bounds__(256)
   const int b = ids ? ids[blockIdx.x] : blockIdx.x;
   const int base_s = L.state_off[b];
   const int wmask = W - 1;
-  const int lg0 = L.lanes_out_log2[b];
+  const bool whole = (L.state_off[b + 1] - base_s) <= W;
   const float* th = theta;
   if (theta && theta_smem) {
     float* sth = reinterpret_cast<float*>(smem_raw + plan.theta);
@@ -369,28 +421,42 @@ __global__ void __launch_bounds__(256)
 
     const int a0 = k0.x, a1 = k0.y, s0 = k0.z, s1 = k0.w;
     const int n = a1 - a0, ns = s1 - s0;
+    const int base4 = a0 & ~3;
     if (n <= cap) {
       // ---- phase 1
-      for (int j = tid; j <= ns; j += NT) segp[j] = __ldg(L.out_ptr + s0 + j) - a0;
-      if (want_post)
-        for (int j = tid; j < ns; j += NT) abuf[j] = alpha[s0 + j] - lz;
-      const int hi = s1 + W;
-      int g = gbase(k0);
+      for (int j = tid; j <= ns; j += NT) segp[j] = __ldg(L.out_ptr + s0 + j) - base4;
+      const int hi = whole ? 0x7fffffff : s1 + W;
+      int g = base4 + tid * 4;
       int4 dv = dst_c, lv = lab_c;
       float4 wv = w_c;
       while (g < a1) {
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int a = g + e;
-          if (a >= a0 && a < a1) {
-            const int d = elem(dv, e);
-            float w = elem(wv, e);
-            if (th) w += th[elem(lv, e)];
-            if (LOGS) vbuf[a - a0] = static_cast<ST>(w) + ((d < hi) ? win[(d - base_s) & wmask] : beta[d]);
-            if (TROP) tbuf[a - a0] = __fadd_rn(w, (d < hi) ? dwin[(d - base_s) & wmask] : delta[d]);
-            if (LOGS && hist) lbuf[a - a0] = elem(lv, e);
+        if (th) { wv.x += th[lv.x]; wv.y += th[lv.y]; wv.z += th[lv.z]; wv.w += th[lv.w]; }
+        const bool fast = max(max(dv.x, dv.y), max(dv.z, dv.w)) < hi;
+        const int i0 = (dv.x - base_s) & wmask, i1 = (dv.y - base_s) & wmask, i2 = (dv.z - base_s) & wmask,
+                  i3 = (dv.w - base_s) & wmask;
+        if (LOGS) {
+          ST v0, v1, v2, v3;
+          if (fast) {
+            v0 = win[i0]; v1 = win[i1]; v2 = win[i2]; v3 = win[i3];
+          } else {
+            v0 = dv.x < hi ? win[i0] : beta[dv.x]; v1 = dv.y < hi ? win[i1] : beta[dv.y];
+            v2 = dv.z < hi ? win[i2] : beta[dv.z]; v3 = dv.w < hi ? win[i3] : beta[dv.w];
           }
+          store4<ST>(vbuf + (g - base4), v0 + static_cast<ST>(wv.x), v1 + static_cast<ST>(wv.y),
+                     v2 + static_cast<ST>(wv.z), v3 + static_cast<ST>(wv.w));
         }
+        if (TROP) {
+          float t0, t1, t2, t3;
+          if (fast) {
+            t0 = dwin[i0]; t1 = dwin[i1]; t2 = dwin[i2]; t3 = dwin[i3];
+          } else {
+            t0 = dv.x < hi ? dwin[i0] : delta[dv.x]; t1 = dv.y < hi ? dwin[i1] : delta[dv.y];
+            t2 = dv.z < hi ? dwin[i2] : delta[dv.z]; t3 = dv.w < hi ? dwin[i3] : delta[dv.w];
+          }
+          store4<float>(tbuf + (g - base4), __fadd_rn(wv.x, t0), __fadd_rn(wv.y, t1), __fadd_rn(wv.z, t2),
+                        __fadd_rn(wv.w, t3));
+        }
+        if (LOGS && hist) *reinterpret_cast<int4*>(lbuf + (g - base4)) = lv;
         g += NT * 4;
         if (g < a1) {
           dv = ldg4(L.dst_out + g);
@@ -400,54 +466,89 @@ __global__ void __launch_bounds__(256)
       }
       __syncthreads();
       // ---- phase 2
-      int lg = lg0;
-      while (lg < 5 && (ns << (lg + 1)) <= NT) ++lg;
-      const int G = 1 << lg, lane_g = tid & (G - 1), grp = tid >> lg, ngrp = NT >> lg;
-      for (int jb = 0; jb < ns; jb += ngrp) {
-        const int j = jb + grp;
-        const bool valid = j < ns;
-        const int b0 = valid ? segp[j] : 0, b1 = valid ? segp[j + 1] : 0;
-        const int s = s0 + j;
-        if (LOGS) {
-          ST m = neg_inf;
-          for (int i = b0 + lane_g; i < b1; i += G) m = max(m, vbuf[i]);
-          for (int o = G >> 1; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
-          float sum = 0.0f;
-          if (m > neg_inf)
-            for (int i = b0 + lane_g; i < b1; i += G) sum += __expf(static_cast<float>(vbuf[i] - m));
-          for (int o = G >> 1; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-          if (valid && lane_g == 0) {
-            const ST v = (b0 == b1) ? static_cast<ST>(0) : lse_value(m, sum);  // sinks: beta = 1
-            win[(s - base_s) & wmask] = v;
+      if (ns * 2 > NT) {  // one thread per state
+        for (int j = tid; j < ns; j += NT) {
+          const int b0 = segp[j], b1 = segp[j + 1];
+          const int s = s0 + j;
+          if (LOGS) {
+            ST am = 0;
+            if (want_post) am = alpha[s] - lz;  // issued before the loops, consumed after them
+            ST m = neg_inf;
+            for (int i = b0; i < b1; ++i) m = max(m, vbuf[i]);
+            float sum = 0.0f;
+            for (int i = b0; i < b1; ++i) sum += fast_exp(static_cast<float>(vbuf[i] - m));
+            // sinks: beta = 1 (scorers.py:720)
+            const ST v = (b0 == b1) ? static_cast<ST>(0) : ((m > neg_inf) ? m + static_cast<ST>(fast_log(sum)) : neg_inf);
+            if (s < s0 + W) win[(s - base_s) & wmask] = v;
             beta[s] = v;
-          }
-          if (want_post && valid) {
-            const ST am = abuf[j];
-            for (int i = b0 + lane_g; i < b1; i += G) {
-              const float p = __expf(static_cast<float>(am + vbuf[i])) * gscale;
-              if (post) post[a0 + i] = p;
-              if (hist) atomicAdd(&hist[lbuf[i]], p);
+            if (want_post) {
+              for (int i = b0; i < b1; ++i) {
+                const float p = fast_exp(static_cast<float>(am + vbuf[i])) * gscale;
+                if (post) post[base4 + i] = p;
+                if (hist) atomicAdd(&hist[lbuf[i]], p);
+              }
             }
           }
-        }
-        if (TROP) {
-          float bt = kNegInf;
-          int bi = 0x7fffffff;
-          for (int i = b0 + lane_g; i < b1; i += G) {
-            const float t = tbuf[i];
-            if (t > bt || (t == bt && i < bi)) { bt = t; bi = i; }
-          }
-          for (int o = G >> 1; o > 0; o >>= 1) {
-            const float t2 = __shfl_xor_sync(0xffffffffu, bt, o);
-            const int i2 = __shfl_xor_sync(0xffffffffu, bi, o);
-            if (t2 > bt || (t2 == bt && i2 < bi)) { bt = t2; bi = i2; }
-          }
-          if (valid && lane_g == 0) {
+          if (TROP) {
+            float bt = kNegInf;
+            int bi = b0;
+            for (int i = b0; i < b1; ++i) {
+              const float t = tbuf[i];
+              if (t > bt) { bt = t; bi = i; }  // strict: the first (smallest label) wins ties
+            }
             const bool sink = (b0 == b1);
             const float v = sink ? 0.0f : bt;
-            dwin[(s - base_s) & wmask] = v;
+            if (s < s0 + W) dwin[(s - base_s) & wmask] = v;
             delta[s] = v;
-            backptr[s] = sink ? -1 : a0 + bi;
+            backptr[s] = sink ? -1 : base4 + bi;
+          }
+        }
+      } else {
+        int lg = 1;
+        while (lg < 5 && (ns << (lg + 1)) <= NT) ++lg;
+        const int G = 1 << lg, lane_g = tid & (G - 1), grp = tid >> lg, ngrp = NT >> lg;
+        for (int jb = 0; jb < ns; jb += ngrp) {
+          const int j = jb + grp;
+          const bool valid = j < ns;
+          const int b0 = valid ? segp[j] : 0, b1 = valid ? segp[j + 1] : 0;
+          const int s = s0 + j;
+          if (LOGS) {
+            ST am = 0;
+            if (want_post && valid) am = alpha[s] - lz;
+            ST m;
+            ST v = seg_lse(vbuf, b0, b1, G, lane_g, neg_inf, &m);
+            if (valid && lane_g == 0) {
+              if (b0 == b1) v = 0;
+              if (s < s0 + W) win[(s - base_s) & wmask] = v;
+              beta[s] = v;
+            }
+            if (want_post && valid) {
+              for (int i = b0 + lane_g; i < b1; i += G) {
+                const float p = fast_exp(static_cast<float>(am + vbuf[i])) * gscale;
+                if (post) post[base4 + i] = p;
+                if (hist) atomicAdd(&hist[lbuf[i]], p);
+              }
+            }
+          }
+          if (TROP) {
+            float bt = kNegInf;
+            int bi = 0x7fffffff;
+            for (int i = b0 + lane_g; i < b1; i += G) {
+              const float t = tbuf[i];
+              if (t > bt || (t == bt && i < bi)) { bt = t; bi = i; }
+            }
+            for (int o = G >> 1; o > 0; o >>= 1) {
+              const float t2 = __shfl_xor_sync(0xffffffffu, bt, o);
+              const int i2 = __shfl_xor_sync(0xffffffffu, bi, o);
+              if (t2 > bt || (t2 == bt && i2 < bi)) { bt = t2; bi = i2; }
+            }
+            if (valid && lane_g == 0) {
+              const bool sink = (b0 == b1);
+              const float v = sink ? 0.0f : bt;
+              if (s < s0 + W) dwin[(s - base_s) & wmask] = v;
+              delta[s] = v;
+              backptr[s] = sink ? -1 : base4 + bi;
+            }
           }
         }
       }
@@ -469,17 +570,18 @@ __global__ void __launch_bounds__(256)
           if (need_label) lab = L.label_out[a];
           float w = arc_scores ? arc_scores[a] : 0.0f;
           if (th) w += th[lab];
+          const bool inw = whole || d < s1 + W;
           if (LOGS) {
-            const ST u = static_cast<ST>(w) + ((d < s1 + W) ? win[(d - base_s) & wmask] : beta[d]);
+            const ST u = static_cast<ST>(w) + (inw ? win[(d - base_s) & wmask] : beta[d]);
             lse_add(m, sum, u);
             if (want_post) {
-              const float p = __expf(static_cast<float>(am + u)) * gscale;
+              const float p = fast_exp(static_cast<float>(am + u)) * gscale;
               if (post) post[a] = p;
               if (hist) atomicAdd(&hist[lab], p);
             }
           }
           if (TROP) {
-            const float t = __fadd_rn(w, (d < s1 + W) ? dwin[(d - base_s) & wmask] : delta[d]);
+            const float t = __fadd_rn(w, inw ? dwin[(d - base_s) & wmask] : delta[d]);
             if (t > bt || (t == bt && a < bi)) { bt = t; bi = a; }
           }
         }

@@ -65,7 +65,7 @@ def _check_f32(name: str, t: Optional[torch.Tensor], n: int, dev: torch.device) 
         raise ValueError(f"{name} must have {n} elements, got {t.numel()}")
     t = t.detach().to(torch.float32).contiguous()
     if t.data_ptr() % 16:
-        t = t.clone()  # the kernels read scores with 128-bit loads
+        t = t.clone()  # the kernels read scores with 128-bit loads (values past the end are never used)
     return t
 
 

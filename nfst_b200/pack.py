@@ -42,12 +42,15 @@ class LaunchGroup:
     ids: torch.Tensor  # int32 [n], lattice indices, heaviest first
     n: int
     block_threads: int  # 32 / 64 / 128 / 256; the lattices' chunks were cut for this size
-    max_states: int  # largest lattice of the group, in states (sizes the shared-memory window)
+    max_states: int  # largest lattice of the group, in states
+    max_reach: int  # longest arc of the group, in packed state ids (sizes the shared-memory window)
     n_arcs: int
 
     def window_states(self, state_bytes: int = 4, window_bytes_max: int = WINDOW_BYTES_MAX) -> int:
+        """Power-of-two window: covers every arc of the group if that fits the byte budget
+        (then no neighbour value is ever re-read from global memory)."""
         cap = max(32, window_bytes_max // state_bytes)
-        return max(32, min(_pow2_ceil(self.max_states), _pow2_floor(cap)))
+        return max(32, min(_pow2_ceil(min(self.max_reach, self.max_states)), _pow2_floor(cap)))
 
 
 class PackedLattices:
@@ -59,7 +62,36 @@ class PackedLattices:
         "fwd_chunk_off", "fwd_chunks", "bwd_chunk_off", "bwd_chunks",
     )
 
+    # per-arc arrays the kernels read with 128-bit loads: kept zero-padded by PAD elements
+    _ARC_FIELDS = ("src_in", "label_in", "in2out", "dst_out", "label_out")
+    PAD = 4
+
+    @staticmethod
+    def _padded(t: torch.Tensor) -> torch.Tensor:
+        """Same values, but backed by storage with PAD trailing zeros (so that a 128-bit load
+        that straddles the end reads zeros -- valid indices -- and never garbage)."""
+        n = t.numel()
+        room = t.untyped_storage().nbytes() // t.element_size() - t.storage_offset() - n
+        if room >= PackedLattices.PAD and getattr(t, "_nfst_padded", False):
+            return t
+        buf = torch.zeros(n + PackedLattices.PAD, dtype=t.dtype, device=t.device)
+        buf[:n] = t
+        out = buf[:n]
+        out._nfst_padded = True
+        return out
+
+    @staticmethod
+    def alloc_padded(n: int, dtype, device) -> torch.Tensor:
+        """An uninitialised length-n tensor with zeroed PAD slack behind it (for callers that
+        refill the arc arrays every step, e.g. from pinned host memory)."""
+        buf = torch.zeros(n + PackedLattices.PAD, dtype=dtype, device=device)
+        out = buf[:n]
+        out._nfst_padded = True
+        return out
+
     def __init__(self, **kw):
+        for f in self._ARC_FIELDS:
+            kw[f] = self._padded(kw[f])
         self.n_lattices: int = kw["n_lattices"]
         self.n_states: int = kw["n_states"]
         self.n_arcs: int = kw["n_arcs"]
@@ -161,6 +193,8 @@ def _build_chunks(ptr, slot, level_first, lat_of_state, target, n_lattices, desc
     deg = ptr[1:] - ptr[:-1]
     rel_end = ptr[1:] - ptr[level_first]
     ck = torch.clamp(torch.div(rel_end - 1, target, rounding_mode="floor"), min=0)
+    # ... and at most `target` states (levels full of arc-less states, e.g. many sinks)
+    ck = ck + torch.div(torch.arange(S, device=dev) - level_first, target, rounding_mode="floor")
     heavy = (deg > target).to(torch.int64)
     hk = 2 * torch.cumsum(heavy, 0) - heavy
     new = torch.ones(S, dtype=torch.bool, device=dev)
@@ -193,6 +227,7 @@ def build_groups(stats, dev) -> List[LaunchGroup]:
                 n=int(members.numel()),
                 block_threads=1 << key,
                 max_states=int(stats["states"][members].max()),
+                max_reach=int(stats["reach"][members].max()),
                 n_arcs=int(stats["arcs"][members].sum()),
             )
         )
@@ -316,7 +351,16 @@ def pack_arcs(
     lv = level[kept]
     lt = lat_of_state[kept]
     lmax = int(lv.max()) + 1 if kept.numel() else 1
-    order = torch.argsort(lt * lmax + lv, stable=True)
+    # inside a level states are ordered by (in-degree, out-degree): the 32 states a warp
+    # reduces then have (nearly) equal segment lengths in both passes
+    live = level[gsrc] >= 0
+    deg_in = torch.bincount(gdst[live], minlength=S0)[kept]
+    deg_out = torch.bincount(gsrc[live], minlength=S0)[kept]
+    dmax = int(max(deg_in.max(), deg_out.max())) + 1 if kept.numel() else 1
+    if lmax * dmax * dmax < 2**62 // max(B, 1):
+        order = torch.argsort(((lt * lmax + lv) * dmax + deg_in) * dmax + deg_out, stable=True)
+    else:  # pathological degrees: fall back to level order only
+        order = torch.argsort(lt * lmax + lv, stable=True)
     kept_sorted = kept[order]
     lt_s, lv_s = lt[order], lv[order]
     S = int(kept_sorted.numel())
@@ -369,11 +413,17 @@ def pack_arcs(
     target_state = (4 * (1 << block_class) - CHUNK_SLACK)[lt_s]
     fwd_chunk_off, fwd_chunks = _build_chunks(in_ptr, slot, lvl_first_state, lt_s, target_state, B, False)
     bwd_chunk_off, bwd_chunks = _build_chunks(out_ptr, slot, lvl_first_state, lt_s, target_state, B, True)
+    # how far back (in packed state ids) an arc reaches: sizes the shared-memory window
+    arc_lat = torch.repeat_interleave(torch.arange(B, device=dev), (arc_off[1:] - arc_off[:-1]))
+    reach = torch.zeros(B, dtype=torch.int64, device=dev)
+    if A:
+        reach = reach.scatter_reduce(0, arc_lat, dst_out - src_out, reduce="amax")
     stats = {
         "arcs": A_b.to(torch.int64).cpu(),
         "states": S_b.cpu(),
         "levels": n_levels.cpu(),
         "block_class": block_class.cpu(),
+        "reach": reach.cpu(),
     }
     groups = build_groups(stats, dev)
 
