@@ -58,8 +58,6 @@ __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpre
 __device__ __forceinline__ int4 chunk_at(const nfst_chunk_t* c, int i, int end) {
   return i < end ? __ldg(reinterpret_cast<const int4*>(c + i)) : make_int4(0, 0, 0, 0);
 }
-__device__ __forceinline__ int elem(const int4& v, int e) { return e == 0 ? v.x : e == 1 ? v.y : e == 2 ? v.z : v.w; }
-__device__ __forceinline__ float elem(const float4& v, int e) { return e == 0 ? v.x : e == 1 ? v.y : e == 2 ? v.z : v.w; }
 
 // ---- online logsumexp (m, s): value = m + log(s); m in the state type, s in fp32 --------
 template <typename ST>
@@ -229,37 +227,46 @@ __global__ void __launch_bounds__(256, 4)
   auto ld_src = [&](const int4& k) { const int g = gbase(k); return g < k.y ? ldg4(L.src_in + g) : z4; };
   auto ld_idx = [&](const int4& k) { const int g = gbase(k); return (arc_scores && g < k.y) ? ldg4(L.in2out + g) : z4; };
   auto ld_lab = [&](const int4& k) { const int g = gbase(k); return (th && g < k.y) ? ldg4(L.label_in + g) : z4; };
-  auto gather_w = [&](const int4& idx, const int4& lab) {  // padded arrays: every index is a valid one
+  auto gather_w = [&](const int4& idx) {  // padded arrays: every index is a valid one
     float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
     if (arc_scores) {
       w.x = __ldg(arc_scores + idx.x); w.y = __ldg(arc_scores + idx.y);
       w.z = __ldg(arc_scores + idx.z); w.w = __ldg(arc_scores + idx.w);
     }
-    if (th) { w.x += th[lab.x]; w.y += th[lab.y]; w.z += th[lab.z]; w.w += th[lab.w]; }
     return w;
   };
-  int4 k0 = chunk_at(chunks, c, c_end), k1 = chunk_at(chunks, c + 1, c_end);
-  int4 src_c = ld_src(k0);
-  float4 w_c = gather_w(ld_idx(k0), ld_lab(k0));
-  int4 idx_n = ld_idx(k1), lab_n = ld_lab(k1);
+  auto ld_ptr = [&](const int4& k) { return (k.z + tid <= k.w && k.z < k.w) ? __ldg(L.in_ptr + k.z + tid) : 0; };
+  // stage:            descriptor   score index   src / label / score / row pointer
+  // chunk c   (k0)        -             -          in registers (consumed now)
+  // chunk c+1 (k1)        -          idx_n         issued now
+  // chunk c+2 (k2)     loaded        issued now
+  // chunk c+3 (k3)     issued now
+  int4 k0 = chunk_at(chunks, c, c_end), k1 = chunk_at(chunks, c + 1, c_end), k2 = chunk_at(chunks, c + 2, c_end);
+  int4 src_c = ld_src(k0), lab_c = ld_lab(k0);
+  float4 w_c = gather_w(ld_idx(k0));
+  int ptr_c = ld_ptr(k0);
+  int4 idx_n = ld_idx(k1);
 
   for (; c < c_end; ++c) {
-    const int4 k2 = chunk_at(chunks, c + 2, c_end);
-    const int4 src_n = ld_src(k1);
-    const float4 w_n = gather_w(idx_n, lab_n);
-    const int4 idx_nn = ld_idx(k2), lab_nn = ld_lab(k2);
+    const int4 k3 = chunk_at(chunks, c + 3, c_end);
+    const int4 src_n = ld_src(k1), lab_n = ld_lab(k1);
+    const float4 w_n = gather_w(idx_n);
+    const int ptr_n = ld_ptr(k1);
+    const int4 idx_nn = ld_idx(k2);
 
     const int a0 = k0.x, a1 = k0.y, s0 = k0.z, s1 = k0.w;
     const int n = a1 - a0, ns = s1 - s0;
     const int base4 = a0 & ~3;
     if (n <= cap) {
       // ---- phase 1: arc-parallel, w + alpha[src] into the tile
-      for (int j = tid; j <= ns; j += NT) segp[j] = __ldg(L.in_ptr + s0 + j) - base4;
+      if (tid <= ns) segp[tid] = ptr_c - base4;
+      for (int j = tid + NT; j <= ns; j += NT) segp[j] = __ldg(L.in_ptr + s0 + j) - base4;
       const int lo = whole ? static_cast<int>(0x80000000) : s0 - W;
       int g = base4 + tid * 4;
-      int4 sv = src_c;
+      int4 sv = src_c, lv = lab_c;
       float4 wv = w_c;
       while (g < a1) {
+        if (th) { wv.x += th[lv.x]; wv.y += th[lv.y]; wv.z += th[lv.z]; wv.w += th[lv.w]; }
         ST v0, v1, v2, v3;
         if (min(min(sv.x, sv.y), min(sv.z, sv.w)) >= lo) {
           v0 = win[(sv.x - base_s) & wmask]; v1 = win[(sv.y - base_s) & wmask];
@@ -275,7 +282,8 @@ __global__ void __launch_bounds__(256, 4)
         g += NT * 4;
         if (g < a1) {  // second pass of a long chunk: not prefetched
           sv = ldg4(L.src_in + g);
-          wv = gather_w(arc_scores ? ldg4(L.in2out + g) : z4, th ? ldg4(L.label_in + g) : z4);
+          wv = gather_w(arc_scores ? ldg4(L.in2out + g) : z4);
+          lv = th ? ldg4(L.label_in + g) : z4;
         }
       }
       __syncthreads();
@@ -336,7 +344,7 @@ __global__ void __launch_bounds__(256, 4)
       }
       __syncthreads();
     }
-    k0 = k1; k1 = k2; src_c = src_n; w_c = w_n; idx_n = idx_nn; lab_n = lab_nn;
+    k0 = k1; k1 = k2; k2 = k3; src_c = src_n; lab_c = lab_n; w_c = w_n; ptr_c = ptr_n; idx_n = idx_nn;
   }
 
   // logZ = logsumexp over the sinks of alpha (every zero-out-degree state has beta = 1,
@@ -410,21 +418,25 @@ __global__ void __launch_bounds__(256, 4)
   auto ld_dst = [&](const int4& k) { const int g = gbase(k); return g < k.y ? ldg4(L.dst_out + g) : z4; };
   auto ld_w = [&](const int4& k) { const int g = gbase(k); return (arc_scores && g < k.y) ? ldg4(arc_scores + g) : zf4; };
   auto ld_lab = [&](const int4& k) { const int g = gbase(k); return (need_label && g < k.y) ? ldg4(L.label_out + g) : z4; };
-  int4 k0 = chunk_at(chunks, c, c_end);
+  auto ld_ptr = [&](const int4& k) { return (k.z + tid <= k.w && k.z < k.w) ? __ldg(L.out_ptr + k.z + tid) : 0; };
+  int4 k0 = chunk_at(chunks, c, c_end), k1 = chunk_at(chunks, c + 1, c_end);
   int4 dst_c = ld_dst(k0), lab_c = ld_lab(k0);
   float4 w_c = ld_w(k0);
+  int ptr_c = ld_ptr(k0);
 
   for (; c < c_end; ++c) {
-    const int4 k1 = chunk_at(chunks, c + 1, c_end);
+    const int4 k2 = chunk_at(chunks, c + 2, c_end);  // descriptors run two chunks ahead of the loads
     const int4 dst_n = ld_dst(k1), lab_n = ld_lab(k1);
     const float4 w_n = ld_w(k1);
+    const int ptr_n = ld_ptr(k1);
 
     const int a0 = k0.x, a1 = k0.y, s0 = k0.z, s1 = k0.w;
     const int n = a1 - a0, ns = s1 - s0;
     const int base4 = a0 & ~3;
     if (n <= cap) {
       // ---- phase 1
-      for (int j = tid; j <= ns; j += NT) segp[j] = __ldg(L.out_ptr + s0 + j) - base4;
+      if (tid <= ns) segp[tid] = ptr_c - base4;
+      for (int j = tid + NT; j <= ns; j += NT) segp[j] = __ldg(L.out_ptr + s0 + j) - base4;
       const int hi = whole ? 0x7fffffff : s1 + W;
       int g = base4 + tid * 4;
       int4 dv = dst_c, lv = lab_c;
@@ -618,7 +630,7 @@ __global__ void __launch_bounds__(256, 4)
       }
       __syncthreads();
     }
-    k0 = k1; dst_c = dst_n; lab_c = lab_n; w_c = w_n;
+    k0 = k1; k1 = k2; dst_c = dst_n; lab_c = lab_n; w_c = w_n; ptr_c = ptr_n;
   }
 
   if (tid == 0) {

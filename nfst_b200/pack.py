@@ -415,9 +415,15 @@ def pack_arcs(
     bwd_chunk_off, bwd_chunks = _build_chunks(out_ptr, slot, lvl_first_state, lt_s, target_state, B, True)
     # how far back (in packed state ids) an arc reaches: sizes the shared-memory window
     arc_lat = torch.repeat_interleave(torch.arange(B, device=dev), (arc_off[1:] - arc_off[:-1]))
-    reach = torch.zeros(B, dtype=torch.int64, device=dev)
+    # (99% quantile over the lattice's arcs, rounded up to a power of two, from a log2
+    # histogram -- a few long arcs, e.g. dead ends wired to the sink, take the global path)
+    reach = torch.full((B,), 32, dtype=torch.int64, device=dev)
     if A:
-        reach = reach.scatter_reduce(0, arc_lat, dst_out - src_out, reduce="amax")
+        lg = torch.ceil(torch.log2((dst_out - src_out).to(torch.float64))).to(torch.int64).clamp_(0, 31)
+        hist = torch.bincount(arc_lat * 32 + lg, minlength=B * 32).view(B, 32)
+        cum = torch.cumsum(hist, 1)
+        need = torch.ceil(cum[:, -1:].to(torch.float64) * 0.99).to(torch.int64)
+        reach = torch.ones_like(reach) << (cum < need).sum(1)
     stats = {
         "arcs": A_b.to(torch.int64).cpu(),
         "states": S_b.cpu(),
