@@ -102,8 +102,9 @@ typedef struct nfst_packed_lattices {
 
 /*
  * One kernel launch = one thread block per lattice in `lattice_ids` (NULL = lattices
- * 0..n_ids-1).  A chunk of up to 8*block_threads arcs is staged in shared memory; larger
- * chunks (a state whose degree exceeds that) take a slower block-wide path.
+ * 0..n_ids-1).  The arc arrays of a chunk (up to 8*block_threads arcs) are staged in shared
+ * memory with cp.async, double-buffered; larger chunks (a state whose degree exceeds that)
+ * take a slower block-wide path.
  * `window_states` (a power of two, >= 32) is the number of most recent per-state DP
  * values kept in shared memory; older ones are re-read from global memory.
  * `state_f64` != 0 keeps the log-semiring state vectors (alpha, beta, logZ) in float64:
@@ -137,7 +138,7 @@ int nfst_device_info(int device, int* sm_count, int* cc_major, int* cc_minor, si
 /* Dynamic shared memory (bytes) of a forward (pass = 0) or backward (pass = 1) launch.
  * with_log / with_trop select the semirings of the backward pass. */
 size_t nfst_launch_smem_bytes(const nfst_launch_t* launch, int32_t vocab, int pass, int with_log, int with_trop,
-                              int with_post, int with_theta, int with_dtheta);
+                              int with_post, int with_scores, int with_theta, int with_dtheta);
 
 /* alpha[S] (log space), logz[B] = logsumexp over the lattice's sinks of alpha.  alpha and
  * logz are float32, or float64 when launch->state_f64. */

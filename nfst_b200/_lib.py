@@ -68,7 +68,7 @@ SYMBOLS = {
     "nfst_abi_version": (C.c_int, []),
     "nfst_last_error_string": (C.c_char_p, []),
     "nfst_device_info": (C.c_int, [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_size_t)]),
-    "nfst_launch_smem_bytes": (C.c_size_t, [C.POINTER(LaunchC), C.c_int32] + [C.c_int] * 6),
+    "nfst_launch_smem_bytes": (C.c_size_t, [C.POINTER(LaunchC), C.c_int32] + [C.c_int] * 7),
     "nfst_fwd_f32": (C.c_int, [C.POINTER(PackedLatticesC), C.POINTER(LaunchC), C.POINTER(ScoresC), _P, _P, _P]),
     "nfst_bwd_fused_f32": (
         C.c_int,

@@ -53,8 +53,7 @@ int fail(int code, const char* fmt, ...) {
 constexpr float kNegInf = -__builtin_huge_valf();
 constexpr int kChunkArcsPerThread = 8;  // tile capacity = 8 * blockDim arcs
 
-__device__ __forceinline__ int4 ldg4(const int32_t* p) { return __ldg(reinterpret_cast<const int4*>(p)); }
-__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ int slot_of(int s, int base_s, int wmask) { return (s - base_s) & wmask; }
 __device__ __forceinline__ int4 chunk_at(const nfst_chunk_t* c, int i, int end) {
   return i < end ? __ldg(reinterpret_cast<const int4*>(c + i)) : make_int4(0, 0, 0, 0);
 }
@@ -113,27 +112,29 @@ __device__ ST block_lse(ST m, float s) {
 }
 
 // ---- shared memory carve-up (identical on host and device), offsets in bytes ----------
+// [window ST[W]] [delta window f32[W]] [2 stages x {nbr int[cap+8], aux int[cap+8], lab int[cap+8],
+// ptr int[cap+8]}] [theta f32[V]] [dtheta f32[V]]
 struct SmemPlan {
-  size_t win, vbuf, abuf, dwin, tbuf, segp, lbuf, theta, dtheta, bytes;
+  size_t win, dwin, stage0, stage_bytes, nbr, aux, lab, ptr, theta, dtheta, bytes;
 };
-__host__ __device__ inline SmemPlan smem_plan(int W, int cap, int st_bytes, int vocab, bool bwd, bool logs, bool trop,
-                                              bool post, bool with_theta, bool with_dtheta) {
+__host__ __device__ inline SmemPlan smem_plan(int W, int cap, int st_bytes, int vocab, bool logs, bool trop,
+                                              bool with_scores, bool with_labels, bool with_theta, bool with_dtheta) {
   SmemPlan p;
   size_t o = 0;
-  const bool log_arrays = !bwd || logs;
+  const size_t arr = static_cast<size_t>(cap + 8) * 4;
   p.win = o;
-  o += log_arrays ? static_cast<size_t>(W) * st_bytes : 0;
-  p.vbuf = o;
-  o += log_arrays ? static_cast<size_t>(cap + 8) * st_bytes : 0;
-  p.abuf = o;
+  o += logs ? static_cast<size_t>(W) * st_bytes : 0;
   p.dwin = o;
-  o += (bwd && trop) ? static_cast<size_t>(W) * 4 : 0;
-  p.tbuf = o;
-  o += (bwd && trop) ? static_cast<size_t>(cap + 8) * 4 : 0;
-  p.segp = o;
-  o += static_cast<size_t>(cap + 8) * 4;
-  p.lbuf = o;
-  o += (bwd && with_dtheta) ? static_cast<size_t>(cap + 8) * 4 : 0;
+  o += trop ? static_cast<size_t>(W) * 4 : 0;
+  o = (o + 15) & ~static_cast<size_t>(15);
+  p.stage0 = o;
+  size_t q = 0;
+  p.nbr = q; q += arr;                      // neighbour state of every arc (src_in / dst_out)
+  p.aux = q; q += with_scores ? arr : 0;    // forward: in2out index; backward: the score itself
+  p.lab = q; q += with_labels ? arr : 0;
+  p.ptr = q; q += arr;                      // CSR row pointers of the chunk's states
+  p.stage_bytes = q;
+  o += 2 * q;
   p.theta = o;
   o += with_theta ? static_cast<size_t>(vocab) * 4 : 0;
   p.dtheta = o;
@@ -142,65 +143,89 @@ __host__ __device__ inline SmemPlan smem_plan(int W, int cap, int st_bytes, int 
   return p;
 }
 
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kLn2 = 0.6931471805599453f;
+// 2^x and log2(x) on the SFU, flush-to-zero (MUFU.EX2 / MUFU.LG2, no range fix-up code)
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float lg2_approx(float x) {
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// one step of the online logsumexp: (m, s) <- (m, s) (+) v ; exactly one exp per element
+template <typename ST>
+__device__ __forceinline__ void lse_push(ST& m, float& s, ST v, ST neg_inf) {
+  if (v > neg_inf) {
+    const float d = static_cast<float>(v - m);                 // m == -inf: d = +inf, e = 0
+    const float e = ex2_approx(-fabsf(d) * kLog2e);
+    if (d > 0.0f) { s = fmaf(s, e, 1.0f); m = v; } else { s += e; }
+  }
+}
+template <typename ST>
+__device__ __forceinline__ void lse_join(ST& m, float& s, ST m2, float s2, ST neg_inf) {
+  if (m2 > neg_inf) {
+    const float d = static_cast<float>(m2 - m);
+    const float e = ex2_approx(-fabsf(d) * kLog2e);
+    if (d > 0.0f) { s = fmaf(s, e, s2); m = m2; } else { s = fmaf(s2, e, s); }
+  }
+}
+template <typename ST>
+__device__ __forceinline__ ST lse_finish(ST m, float s, ST neg_inf) {
+  return (m > neg_inf) ? m + static_cast<ST>(lg2_approx(s) * kLn2) : neg_inf;
+}
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+  const unsigned sa = static_cast<unsigned>(__cvta_generic_to_shared(smem));
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
+
+// Stage the arc arrays and row pointers of chunk k (16-byte cp.async copies, all threads).
+// Copies start at the 4-aligned position below the chunk and may run a few elements past
+// it; the per-arc arrays are zero-padded, so whatever is over-read is a valid index.
+__device__ __forceinline__ void stage_chunk(const int4& k, int cap, unsigned char* st, const SmemPlan& plan,
+                                            const int32_t* __restrict__ nbr, const void* __restrict__ aux,
+                                            const int32_t* __restrict__ lab, const int32_t* __restrict__ ptr) {
+  const int n = k.y - k.x;
+  if (k.w > k.z && n <= cap) {
+    const int base4 = k.x & ~3;
+    const int n4 = (k.y - base4 + 3) >> 2;
+    int* s_nbr = reinterpret_cast<int*>(st + plan.nbr);
+    int* s_aux = reinterpret_cast<int*>(st + plan.aux);
+    int* s_lab = reinterpret_cast<int*>(st + plan.lab);
+    int* s_ptr = reinterpret_cast<int*>(st + plan.ptr);
+    for (int i = threadIdx.x; i < n4; i += blockDim.x) {
+      cp_async16(s_nbr + 4 * i, nbr + base4 + 4 * i);
+      if (aux) cp_async16(s_aux + 4 * i, static_cast<const int32_t*>(aux) + base4 + 4 * i);
+      if (lab) cp_async16(s_lab + 4 * i, lab + base4 + 4 * i);
+    }
+    const int pb = k.z & ~3;
+    const int p4 = (k.w + 1 - pb + 3) >> 2;
+    for (int i = threadIdx.x; i < p4; i += blockDim.x) cp_async16(s_ptr + 4 * i, ptr + pb + 4 * i);
+  }
+  cp_async_commit();
+}
+
 // =====================================================================================
 // forward: alpha
 // =====================================================================================
-// Tile layout: tile slot i holds the arc at position (a0 & ~3) + i, so the 4 arcs of one
-// 128-bit load land in one aligned 128-bit shared-memory store.  Slots outside [a0, a1) hold
-// values of neighbouring arcs (the per-arc arrays are zero-padded by 4, so every index read
-// is a valid one); phase 2 never looks at them.
 template <typename ST>
-struct Vec4;
-template <>
-struct Vec4<float> { using type = float4; };
-template <>
-struct Vec4<double> { using type = double4; };
-
-template <typename ST>
-__device__ __forceinline__ void store4(ST* p, ST a, ST b, ST c, ST d);
-template <>
-__device__ __forceinline__ void store4<float>(float* p, float a, float b, float c, float d) {
-  *reinterpret_cast<float4*>(p) = make_float4(a, b, c, d);
-}
-template <>
-__device__ __forceinline__ void store4<double>(double* p, double a, double b, double c, double d) {
-  *reinterpret_cast<double2*>(p) = make_double2(a, b);
-  *reinterpret_cast<double2*>(p + 2) = make_double2(c, d);
-}
-
-constexpr float kLog2e = 1.4426950408889634f;
-constexpr float kLn2 = 0.6931471805599453f;
-// exp(x) for x <= 0 and log(x) for x >= 1 on the SFU (ex2.approx / lg2.approx)
-__device__ __forceinline__ float fast_exp(float x) { return exp2f(x * kLog2e); }
-__device__ __forceinline__ float fast_log(float x) { return __log2f(x) * kLn2; }
-
-// segmented logsumexp of tile[b0, b1) by one lane group (G lanes, lane_g = my lane)
-template <typename ST>
-__device__ __forceinline__ ST seg_lse(const ST* __restrict__ tile, int b0, int b1, int G, int lane_g, ST neg_inf,
-                                      ST* m_out) {
-  ST m = neg_inf;
-  for (int i = b0 + lane_g; i < b1; i += G) m = max(m, tile[i]);
-  for (int o = G >> 1; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
-  float sum = 0.0f;
-  if (m > neg_inf)
-    for (int i = b0 + lane_g; i < b1; i += G) sum += fast_exp(static_cast<float>(tile[i] - m));
-  for (int o = G >> 1; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-  *m_out = m;
-  return (m > neg_inf) ? m + static_cast<ST>(fast_log(sum)) : neg_inf;
-}
-
-template <typename ST>
-__global__ void __launch_bounds__(256, 4)
+__global__ void __launch_bounds__(256, 3)
     nfst_fwd_kernel(const nfst_packed_lattices_t L, const int32_t* __restrict__ ids, int W,
                     const float* __restrict__ arc_scores, const float* __restrict__ theta, int theta_smem, ST* alpha,
                     ST* __restrict__ logz) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int NT = blockDim.x, tid = threadIdx.x;
   const int cap = NT * kChunkArcsPerThread;
-  const SmemPlan plan = smem_plan(W, cap, sizeof(ST), L.vocab, false, true, false, false, theta_smem != 0, false);
+  const SmemPlan plan = smem_plan(W, cap, sizeof(ST), L.vocab, true, false, arc_scores != nullptr, theta != nullptr,
+                                  theta_smem != 0, false);
   ST* win = reinterpret_cast<ST*>(smem_raw + plan.win);
-  ST* vbuf = reinterpret_cast<ST*>(smem_raw + plan.vbuf);
-  int* segp = reinterpret_cast<int*>(smem_raw + plan.segp);
   const ST neg_inf = static_cast<ST>(kNegInf);
 
   const int b = ids ? ids[blockIdx.x] : blockIdx.x;
@@ -214,112 +239,88 @@ __global__ void __launch_bounds__(256, 4)
     for (int i = tid; i < L.vocab; i += NT) sth[i] = theta[i];
     th = sth;
   }
-  __syncthreads();
 
   const nfst_chunk_t* chunks = L.fwd_chunks;
   int c = L.fwd_chunk_off[b];
   const int c_end = L.fwd_chunk_off[b + 1];
+  const int32_t* idx_arr = arc_scores ? L.in2out : nullptr;
+  const int32_t* lab_arr = th ? L.label_in : nullptr;
 
-  // ---- register pipeline: the arc arrays of chunk c+1 (and the score indices of chunk c+2)
-  // are in flight while chunk c is reduced, so HBM streaming does not wait on the barriers
-  const int4 z4 = make_int4(0, 0, 0, 0);
-  auto gbase = [&](const int4& k) { return (k.x & ~3) + tid * 4; };
-  auto ld_src = [&](const int4& k) { const int g = gbase(k); return g < k.y ? ldg4(L.src_in + g) : z4; };
-  auto ld_idx = [&](const int4& k) { const int g = gbase(k); return (arc_scores && g < k.y) ? ldg4(L.in2out + g) : z4; };
-  auto ld_lab = [&](const int4& k) { const int g = gbase(k); return (th && g < k.y) ? ldg4(L.label_in + g) : z4; };
-  auto gather_w = [&](const int4& idx) {  // padded arrays: every index is a valid one
-    float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (arc_scores) {
-      w.x = __ldg(arc_scores + idx.x); w.y = __ldg(arc_scores + idx.y);
-      w.z = __ldg(arc_scores + idx.z); w.w = __ldg(arc_scores + idx.w);
-    }
-    return w;
-  };
-  auto ld_ptr = [&](const int4& k) { return (k.z + tid <= k.w && k.z < k.w) ? __ldg(L.in_ptr + k.z + tid) : 0; };
-  // stage:            descriptor   score index   src / label / score / row pointer
-  // chunk c   (k0)        -             -          in registers (consumed now)
-  // chunk c+1 (k1)        -          idx_n         issued now
-  // chunk c+2 (k2)     loaded        issued now
-  // chunk c+3 (k3)     issued now
-  int4 k0 = chunk_at(chunks, c, c_end), k1 = chunk_at(chunks, c + 1, c_end), k2 = chunk_at(chunks, c + 2, c_end);
-  int4 src_c = ld_src(k0), lab_c = ld_lab(k0);
-  float4 w_c = gather_w(ld_idx(k0));
-  int ptr_c = ld_ptr(k0);
-  int4 idx_n = ld_idx(k1);
+  int4 k0 = chunk_at(chunks, c, c_end), k1 = chunk_at(chunks, c + 1, c_end);
+  int stg = 0;
+  stage_chunk(k0, cap, smem_raw + plan.stage0, plan, L.src_in, idx_arr, lab_arr, L.in_ptr);
+  cp_async_wait_all();
+  __syncthreads();
 
   for (; c < c_end; ++c) {
-    const int4 k3 = chunk_at(chunks, c + 3, c_end);
-    const int4 src_n = ld_src(k1), lab_n = ld_lab(k1);
-    const float4 w_n = gather_w(idx_n);
-    const int ptr_n = ld_ptr(k1);
-    const int4 idx_nn = ld_idx(k2);
+    const int4 k2 = chunk_at(chunks, c + 2, c_end);  // descriptor two chunks ahead of its use
+    // chunk c+1 streams into the other stage while chunk c is reduced
+    stage_chunk(k1, cap, smem_raw + plan.stage0 + (stg ^ 1) * plan.stage_bytes, plan, L.src_in, idx_arr, lab_arr,
+                L.in_ptr);
+    const unsigned char* st = smem_raw + plan.stage0 + stg * plan.stage_bytes;
+    const int* s_src = reinterpret_cast<const int*>(st + plan.nbr);
+    const int* s_idx = reinterpret_cast<const int*>(st + plan.aux);
+    const int* s_lab = reinterpret_cast<const int*>(st + plan.lab);
+    const int* s_ptr = reinterpret_cast<const int*>(st + plan.ptr);
 
     const int a0 = k0.x, a1 = k0.y, s0 = k0.z, s1 = k0.w;
     const int n = a1 - a0, ns = s1 - s0;
     const int base4 = a0 & ~3;
+    const int pofs = s0 & 3;
+    const int lo = whole ? static_cast<int>(0x80000000) : s0 - W;
     if (n <= cap) {
-      // ---- phase 1: arc-parallel, w + alpha[src] into the tile
-      if (tid <= ns) segp[tid] = ptr_c - base4;
-      for (int j = tid + NT; j <= ns; j += NT) segp[j] = __ldg(L.in_ptr + s0 + j) - base4;
-      const int lo = whole ? static_cast<int>(0x80000000) : s0 - W;
-      int g = base4 + tid * 4;
-      int4 sv = src_c, lv = lab_c;
-      float4 wv = w_c;
-      while (g < a1) {
-        if (th) { wv.x += th[lv.x]; wv.y += th[lv.y]; wv.z += th[lv.z]; wv.w += th[lv.w]; }
-        ST v0, v1, v2, v3;
-        if (min(min(sv.x, sv.y), min(sv.z, sv.w)) >= lo) {
-          v0 = win[(sv.x - base_s) & wmask]; v1 = win[(sv.y - base_s) & wmask];
-          v2 = win[(sv.z - base_s) & wmask]; v3 = win[(sv.w - base_s) & wmask];
-        } else {  // a source older than the window (or a neighbour's arc): global memory
-          v0 = sv.x >= lo ? win[(sv.x - base_s) & wmask] : alpha[sv.x];
-          v1 = sv.y >= lo ? win[(sv.y - base_s) & wmask] : alpha[sv.y];
-          v2 = sv.z >= lo ? win[(sv.z - base_s) & wmask] : alpha[sv.z];
-          v3 = sv.w >= lo ? win[(sv.w - base_s) & wmask] : alpha[sv.w];
+      // lanes per state: 1 for wide chunks, widened while the chunk leaves the block idle
+      int lg = 0;
+      while (lg < 5 && (ns << (lg + 1)) <= NT) ++lg;
+      const int G = 1 << lg, lane_g = tid & (G - 1), ngrp = NT >> lg;
+      for (int jb = 0; jb < ns; jb += ngrp) {
+        const int j = jb + (tid >> lg);
+        const bool valid = j < ns;
+        const int b0 = valid ? s_ptr[pofs + j] - base4 : 0, b1 = valid ? s_ptr[pofs + j + 1] - base4 : 0;
+        ST m = neg_inf;
+        float sum = 0.0f;
+        int i = b0 + lane_g;
+        const int step = G;
+        // 4 arcs per trip: the 4 score gathers are in flight together
+        for (; i + 3 * step < b1; i += 4 * step) {
+          const int c0 = s_src[i], c1 = s_src[i + step], c2 = s_src[i + 2 * step], c3 = s_src[i + 3 * step];
+          float w0 = 0.f, w1 = 0.f, w2 = 0.f, w3 = 0.f;
+          if (arc_scores) {
+            w0 = __ldg(arc_scores + s_idx[i]); w1 = __ldg(arc_scores + s_idx[i + step]);
+            w2 = __ldg(arc_scores + s_idx[i + 2 * step]); w3 = __ldg(arc_scores + s_idx[i + 3 * step]);
+          }
+          if (th) {
+            w0 += th[s_lab[i]]; w1 += th[s_lab[i + step]]; w2 += th[s_lab[i + 2 * step]]; w3 += th[s_lab[i + 3 * step]];
+          }
+          const ST v0 = c0 >= lo ? win[(c0 - base_s) & wmask] : alpha[c0];
+          const ST v1 = c1 >= lo ? win[(c1 - base_s) & wmask] : alpha[c1];
+          const ST v2 = c2 >= lo ? win[(c2 - base_s) & wmask] : alpha[c2];
+          const ST v3 = c3 >= lo ? win[(c3 - base_s) & wmask] : alpha[c3];
+          lse_push(m, sum, v0 + static_cast<ST>(w0), neg_inf);
+          lse_push(m, sum, v1 + static_cast<ST>(w1), neg_inf);
+          lse_push(m, sum, v2 + static_cast<ST>(w2), neg_inf);
+          lse_push(m, sum, v3 + static_cast<ST>(w3), neg_inf);
         }
-        store4<ST>(vbuf + (g - base4), v0 + static_cast<ST>(wv.x), v1 + static_cast<ST>(wv.y),
-                   v2 + static_cast<ST>(wv.z), v3 + static_cast<ST>(wv.w));
-        g += NT * 4;
-        if (g < a1) {  // second pass of a long chunk: not prefetched
-          sv = ldg4(L.src_in + g);
-          wv = gather_w(arc_scores ? ldg4(L.in2out + g) : z4);
-          lv = th ? ldg4(L.label_in + g) : z4;
+        for (; i < b1; i += step) {
+          const int c0 = s_src[i];
+          float w0 = 0.f;
+          if (arc_scores) w0 = __ldg(arc_scores + s_idx[i]);
+          if (th) w0 += th[s_lab[i]];
+          const ST v0 = c0 >= lo ? win[(c0 - base_s) & wmask] : alpha[c0];
+          lse_push(m, sum, v0 + static_cast<ST>(w0), neg_inf);
         }
-      }
-      __syncthreads();
-      // ---- phase 2: state-parallel segmented logsumexp over the tile
-      if (ns * 2 > NT) {  // one thread per state
-        for (int j = tid; j < ns; j += NT) {
-          const int b0 = segp[j], b1 = segp[j + 1];
-          ST m = neg_inf;
-          for (int i = b0; i < b1; ++i) m = max(m, vbuf[i]);
-          float sum = 0.0f;
-          for (int i = b0; i < b1; ++i) sum += fast_exp(static_cast<float>(vbuf[i] - m));
+        for (int o = G >> 1; o > 0; o >>= 1) {
+          const ST m2 = __shfl_xor_sync(0xffffffffu, m, o);
+          const float s2 = __shfl_xor_sync(0xffffffffu, sum, o);
+          lse_join(m, sum, m2, s2, neg_inf);
+        }
+        if (valid && lane_g == 0) {
           const int s = s0 + j;
-          ST v = (b0 < b1 && m > neg_inf) ? m + static_cast<ST>(fast_log(sum)) : neg_inf;
-          if (s == start) v = 0;
+          const ST v = (s == start) ? static_cast<ST>(0) : lse_finish(m, sum, neg_inf);
           if (s >= s1 - W) win[(s - base_s) & wmask] = v;  // only the newest W states own a slot
           alpha[s] = v;
         }
-      } else {  // narrow chunk: 2^lg lanes per state so that the block stays busy
-        int lg = 1;
-        while (lg < 5 && (ns << (lg + 1)) <= NT) ++lg;
-        const int G = 1 << lg, lane_g = tid & (G - 1), grp = tid >> lg, ngrp = NT >> lg;
-        for (int jb = 0; jb < ns; jb += ngrp) {
-          const int j = jb + grp;
-          const bool valid = j < ns;
-          const int b0 = valid ? segp[j] : 0, b1 = valid ? segp[j + 1] : 0;
-          ST m;
-          ST v = seg_lse(vbuf, b0, b1, G, lane_g, neg_inf, &m);
-          if (valid && lane_g == 0) {
-            const int s = s0 + j;
-            if (s == start) v = 0;
-            if (s >= s1 - W) win[(s - base_s) & wmask] = v;
-            alpha[s] = v;
-          }
-        }
       }
-      __syncthreads();
     } else {
       // ---- oversize chunk (a state with more than `cap` incoming arcs): block-wide, from global
       for (int j = 0; j < ns; ++j) {
@@ -332,7 +333,7 @@ __global__ void __launch_bounds__(256, 4)
           if (arc_scores) w = arc_scores[L.in2out[a]];
           if (th) w += th[L.label_in[a]];
           const int src = L.src_in[a];
-          const ST av = (whole || src >= s0 - W) ? win[(src - base_s) & wmask] : alpha[src];
+          const ST av = (src >= lo) ? win[(src - base_s) & wmask] : alpha[src];
           lse_add(m, sum, static_cast<ST>(w) + av);
         }
         const ST v0 = block_lse(m, sum);
@@ -342,9 +343,10 @@ __global__ void __launch_bounds__(256, 4)
           alpha[s] = v;
         }
       }
-      __syncthreads();
     }
-    k0 = k1; k1 = k2; k2 = k3; src_c = src_n; lab_c = lab_n; w_c = w_n; ptr_c = ptr_n; idx_n = idx_nn;
+    cp_async_wait_all();
+    __syncthreads();  // alpha of chunk c visible; chunk c+1 staged; stage of chunk c free
+    k0 = k1; k1 = k2; stg ^= 1;
   }
 
   // logZ = logsumexp over the sinks of alpha (every zero-out-degree state has beta = 1,
@@ -360,7 +362,7 @@ __global__ void __launch_bounds__(256, 4)
 // fused backward: beta (+ posteriors, dtheta) and/or Viterbi delta + backpointer
 // =====================================================================================
 template <typename ST, bool LOGS, bool TROP>
-__global__ void __launch_bounds__(256, 4)
+__global__ void __launch_bounds__(256, 3)
     nfst_bwd_kernel(const nfst_packed_lattices_t L, const int32_t* __restrict__ ids, int W,
                     const float* __restrict__ arc_scores, const float* __restrict__ theta, int theta_smem,
                     int dtheta_smem, const ST* __restrict__ alpha, const ST* __restrict__ logz,
@@ -371,14 +373,11 @@ __global__ void __launch_bounds__(256, 4)
   const int NT = blockDim.x, tid = threadIdx.x;
   const int cap = NT * kChunkArcsPerThread;
   const bool want_post = LOGS && (post != nullptr || dtheta != nullptr);
-  const SmemPlan plan =
-      smem_plan(W, cap, sizeof(ST), L.vocab, true, LOGS, TROP, want_post, theta_smem != 0, dtheta_smem != 0);
+  const bool need_label = (theta != nullptr) || (LOGS && dtheta != nullptr);
+  const SmemPlan plan = smem_plan(W, cap, sizeof(ST), L.vocab, LOGS, TROP, arc_scores != nullptr, need_label,
+                                  theta_smem != 0, dtheta_smem != 0);
   ST* win = reinterpret_cast<ST*>(smem_raw + plan.win);
-  ST* vbuf = reinterpret_cast<ST*>(smem_raw + plan.vbuf);
   float* dwin = reinterpret_cast<float*>(smem_raw + plan.dwin);
-  float* tbuf = reinterpret_cast<float*>(smem_raw + plan.tbuf);
-  int* segp = reinterpret_cast<int*>(smem_raw + plan.segp);
-  int* lbuf = reinterpret_cast<int*>(smem_raw + plan.lbuf);
   const ST neg_inf = static_cast<ST>(kNegInf);
 
   const int b = ids ? ids[blockIdx.x] : blockIdx.x;
@@ -400,171 +399,102 @@ __global__ void __launch_bounds__(256, 4)
       hist = dtheta;
     }
   }
-  const bool need_label = (th != nullptr) || (hist != nullptr);
   ST lz = 0;
   float gscale = 1.0f;
   if (want_post) {
     lz = logz[b];
     if (grad_logz) gscale = grad_logz[b];
   }
-  __syncthreads();
 
   const nfst_chunk_t* chunks = L.bwd_chunks;
   int c = L.bwd_chunk_off[b];
   const int c_end = L.bwd_chunk_off[b + 1];
-  const int4 z4 = make_int4(0, 0, 0, 0);
-  const float4 zf4 = make_float4(0.f, 0.f, 0.f, 0.f);
-  auto gbase = [&](const int4& k) { return (k.x & ~3) + tid * 4; };
-  auto ld_dst = [&](const int4& k) { const int g = gbase(k); return g < k.y ? ldg4(L.dst_out + g) : z4; };
-  auto ld_w = [&](const int4& k) { const int g = gbase(k); return (arc_scores && g < k.y) ? ldg4(arc_scores + g) : zf4; };
-  auto ld_lab = [&](const int4& k) { const int g = gbase(k); return (need_label && g < k.y) ? ldg4(L.label_out + g) : z4; };
-  auto ld_ptr = [&](const int4& k) { return (k.z + tid <= k.w && k.z < k.w) ? __ldg(L.out_ptr + k.z + tid) : 0; };
+  const int32_t* lab_arr = need_label ? L.label_out : nullptr;
+
   int4 k0 = chunk_at(chunks, c, c_end), k1 = chunk_at(chunks, c + 1, c_end);
-  int4 dst_c = ld_dst(k0), lab_c = ld_lab(k0);
-  float4 w_c = ld_w(k0);
-  int ptr_c = ld_ptr(k0);
+  int stg = 0;
+  stage_chunk(k0, cap, smem_raw + plan.stage0, plan, L.dst_out, arc_scores, lab_arr, L.out_ptr);
+  cp_async_wait_all();
+  __syncthreads();
 
   for (; c < c_end; ++c) {
-    const int4 k2 = chunk_at(chunks, c + 2, c_end);  // descriptors run two chunks ahead of the loads
-    const int4 dst_n = ld_dst(k1), lab_n = ld_lab(k1);
-    const float4 w_n = ld_w(k1);
-    const int ptr_n = ld_ptr(k1);
+    const int4 k2 = chunk_at(chunks, c + 2, c_end);
+    stage_chunk(k1, cap, smem_raw + plan.stage0 + (stg ^ 1) * plan.stage_bytes, plan, L.dst_out, arc_scores, lab_arr,
+                L.out_ptr);
+    const unsigned char* st = smem_raw + plan.stage0 + stg * plan.stage_bytes;
+    const int* s_dst = reinterpret_cast<const int*>(st + plan.nbr);
+    const float* s_w = reinterpret_cast<const float*>(st + plan.aux);
+    const int* s_lab = reinterpret_cast<const int*>(st + plan.lab);
+    const int* s_ptr = reinterpret_cast<const int*>(st + plan.ptr);
 
     const int a0 = k0.x, a1 = k0.y, s0 = k0.z, s1 = k0.w;
     const int n = a1 - a0, ns = s1 - s0;
     const int base4 = a0 & ~3;
+    const int pofs = s0 & 3;
+    const int hi = whole ? 0x7fffffff : s1 + W;
     if (n <= cap) {
-      // ---- phase 1
-      if (tid <= ns) segp[tid] = ptr_c - base4;
-      for (int j = tid + NT; j <= ns; j += NT) segp[j] = __ldg(L.out_ptr + s0 + j) - base4;
-      const int hi = whole ? 0x7fffffff : s1 + W;
-      int g = base4 + tid * 4;
-      int4 dv = dst_c, lv = lab_c;
-      float4 wv = w_c;
-      while (g < a1) {
-        if (th) { wv.x += th[lv.x]; wv.y += th[lv.y]; wv.z += th[lv.z]; wv.w += th[lv.w]; }
-        const bool fast = max(max(dv.x, dv.y), max(dv.z, dv.w)) < hi;
-        const int i0 = (dv.x - base_s) & wmask, i1 = (dv.y - base_s) & wmask, i2 = (dv.z - base_s) & wmask,
-                  i3 = (dv.w - base_s) & wmask;
-        if (LOGS) {
-          ST v0, v1, v2, v3;
-          if (fast) {
-            v0 = win[i0]; v1 = win[i1]; v2 = win[i2]; v3 = win[i3];
-          } else {
-            v0 = dv.x < hi ? win[i0] : beta[dv.x]; v1 = dv.y < hi ? win[i1] : beta[dv.y];
-            v2 = dv.z < hi ? win[i2] : beta[dv.z]; v3 = dv.w < hi ? win[i3] : beta[dv.w];
-          }
-          store4<ST>(vbuf + (g - base4), v0 + static_cast<ST>(wv.x), v1 + static_cast<ST>(wv.y),
-                     v2 + static_cast<ST>(wv.z), v3 + static_cast<ST>(wv.w));
-        }
-        if (TROP) {
-          float t0, t1, t2, t3;
-          if (fast) {
-            t0 = dwin[i0]; t1 = dwin[i1]; t2 = dwin[i2]; t3 = dwin[i3];
-          } else {
-            t0 = dv.x < hi ? dwin[i0] : delta[dv.x]; t1 = dv.y < hi ? dwin[i1] : delta[dv.y];
-            t2 = dv.z < hi ? dwin[i2] : delta[dv.z]; t3 = dv.w < hi ? dwin[i3] : delta[dv.w];
-          }
-          store4<float>(tbuf + (g - base4), __fadd_rn(wv.x, t0), __fadd_rn(wv.y, t1), __fadd_rn(wv.z, t2),
-                        __fadd_rn(wv.w, t3));
-        }
-        if (LOGS && hist) *reinterpret_cast<int4*>(lbuf + (g - base4)) = lv;
-        g += NT * 4;
-        if (g < a1) {
-          dv = ldg4(L.dst_out + g);
-          wv = arc_scores ? ldg4(arc_scores + g) : zf4;
-          lv = need_label ? ldg4(L.label_out + g) : z4;
-        }
-      }
-      __syncthreads();
-      // ---- phase 2
-      if (ns * 2 > NT) {  // one thread per state
-        for (int j = tid; j < ns; j += NT) {
-          const int b0 = segp[j], b1 = segp[j + 1];
-          const int s = s0 + j;
+      int lg = 0;
+      while (lg < 5 && (ns << (lg + 1)) <= NT) ++lg;
+      const int G = 1 << lg, lane_g = tid & (G - 1), ngrp = NT >> lg;
+      for (int jb = 0; jb < ns; jb += ngrp) {
+        const int j = jb + (tid >> lg);
+        const bool valid = j < ns;
+        const int b0 = valid ? s_ptr[pofs + j] - base4 : 0, b1 = valid ? s_ptr[pofs + j + 1] - base4 : 0;
+        const int s = s0 + j;
+        ST am = 0;
+        if (want_post && valid) am = alpha[s] - lz;  // issued before the arc loop, consumed inside it
+        ST m = neg_inf;
+        float sum = 0.0f;
+        float bt = kNegInf;
+        int bi = 0x7fffffff;
+        for (int i = b0 + lane_g; i < b1; i += G) {
+          const int d = s_dst[i];
+          float w = arc_scores ? s_w[i] : 0.0f;
+          int lab = 0;
+          if (need_label) lab = s_lab[i];
+          if (th) w += th[lab];
+          const int slot = (d - base_s) & wmask;
           if (LOGS) {
-            ST am = 0;
-            if (want_post) am = alpha[s] - lz;  // issued before the loops, consumed after them
-            ST m = neg_inf;
-            for (int i = b0; i < b1; ++i) m = max(m, vbuf[i]);
-            float sum = 0.0f;
-            for (int i = b0; i < b1; ++i) sum += fast_exp(static_cast<float>(vbuf[i] - m));
-            // sinks: beta = 1 (scorers.py:720)
-            const ST v = (b0 == b1) ? static_cast<ST>(0) : ((m > neg_inf) ? m + static_cast<ST>(fast_log(sum)) : neg_inf);
-            if (s < s0 + W) win[(s - base_s) & wmask] = v;
-            beta[s] = v;
+            const ST u = static_cast<ST>(w) + (d < hi ? win[slot] : beta[d]);
+            lse_push(m, sum, u, neg_inf);
             if (want_post) {
-              for (int i = b0; i < b1; ++i) {
-                const float p = fast_exp(static_cast<float>(am + vbuf[i])) * gscale;
-                if (post) post[base4 + i] = p;
-                if (hist) atomicAdd(&hist[lbuf[i]], p);
-              }
+              const float p = ex2_approx(static_cast<float>(am + u) * kLog2e) * gscale;
+              if (post) post[base4 + i] = p;
+              if (hist) atomicAdd(&hist[lab], p);
             }
           }
           if (TROP) {
-            float bt = kNegInf;
-            int bi = b0;
-            for (int i = b0; i < b1; ++i) {
-              const float t = tbuf[i];
-              if (t > bt) { bt = t; bi = i; }  // strict: the first (smallest label) wins ties
-            }
-            const bool sink = (b0 == b1);
+            const float t = __fadd_rn(w, d < hi ? dwin[slot] : delta[d]);
+            if (t > bt) { bt = t; bi = i; }  // strict: within a lane arcs come in label order
+          }
+        }
+        for (int o = G >> 1; o > 0; o >>= 1) {
+          if (LOGS) {
+            const ST m2 = __shfl_xor_sync(0xffffffffu, m, o);
+            const float s2 = __shfl_xor_sync(0xffffffffu, sum, o);
+            lse_join(m, sum, m2, s2, neg_inf);
+          }
+          if (TROP) {
+            const float t2 = __shfl_xor_sync(0xffffffffu, bt, o);
+            const int i2 = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (t2 > bt || (t2 == bt && i2 < bi)) { bt = t2; bi = i2; }
+          }
+        }
+        if (valid && lane_g == 0) {
+          const bool sink = (b0 == b1);  // sinks: beta = 1 (scorers.py:720), delta = 0
+          if (LOGS) {
+            const ST v = sink ? static_cast<ST>(0) : lse_finish(m, sum, neg_inf);
+            if (s < s0 + W) win[slot_of(s, base_s, wmask)] = v;
+            beta[s] = v;
+          }
+          if (TROP) {
             const float v = sink ? 0.0f : bt;
-            if (s < s0 + W) dwin[(s - base_s) & wmask] = v;
+            if (s < s0 + W) dwin[slot_of(s, base_s, wmask)] = v;
             delta[s] = v;
             backptr[s] = sink ? -1 : base4 + bi;
           }
         }
-      } else {
-        int lg = 1;
-        while (lg < 5 && (ns << (lg + 1)) <= NT) ++lg;
-        const int G = 1 << lg, lane_g = tid & (G - 1), grp = tid >> lg, ngrp = NT >> lg;
-        for (int jb = 0; jb < ns; jb += ngrp) {
-          const int j = jb + grp;
-          const bool valid = j < ns;
-          const int b0 = valid ? segp[j] : 0, b1 = valid ? segp[j + 1] : 0;
-          const int s = s0 + j;
-          if (LOGS) {
-            ST am = 0;
-            if (want_post && valid) am = alpha[s] - lz;
-            ST m;
-            ST v = seg_lse(vbuf, b0, b1, G, lane_g, neg_inf, &m);
-            if (valid && lane_g == 0) {
-              if (b0 == b1) v = 0;
-              if (s < s0 + W) win[(s - base_s) & wmask] = v;
-              beta[s] = v;
-            }
-            if (want_post && valid) {
-              for (int i = b0 + lane_g; i < b1; i += G) {
-                const float p = fast_exp(static_cast<float>(am + vbuf[i])) * gscale;
-                if (post) post[base4 + i] = p;
-                if (hist) atomicAdd(&hist[lbuf[i]], p);
-              }
-            }
-          }
-          if (TROP) {
-            float bt = kNegInf;
-            int bi = 0x7fffffff;
-            for (int i = b0 + lane_g; i < b1; i += G) {
-              const float t = tbuf[i];
-              if (t > bt || (t == bt && i < bi)) { bt = t; bi = i; }
-            }
-            for (int o = G >> 1; o > 0; o >>= 1) {
-              const float t2 = __shfl_xor_sync(0xffffffffu, bt, o);
-              const int i2 = __shfl_xor_sync(0xffffffffu, bi, o);
-              if (t2 > bt || (t2 == bt && i2 < bi)) { bt = t2; bi = i2; }
-            }
-            if (valid && lane_g == 0) {
-              const bool sink = (b0 == b1);
-              const float v = sink ? 0.0f : bt;
-              if (s < s0 + W) dwin[(s - base_s) & wmask] = v;
-              delta[s] = v;
-              backptr[s] = sink ? -1 : base4 + bi;
-            }
-          }
-        }
       }
-      __syncthreads();
     } else {
       // ---- oversize chunk: one state at a time, block-wide, from global
       for (int j = 0; j < ns; ++j) {
@@ -582,12 +512,12 @@ __global__ void __launch_bounds__(256, 4)
           if (need_label) lab = L.label_out[a];
           float w = arc_scores ? arc_scores[a] : 0.0f;
           if (th) w += th[lab];
-          const bool inw = whole || d < s1 + W;
+          const bool inw = d < hi;
           if (LOGS) {
             const ST u = static_cast<ST>(w) + (inw ? win[(d - base_s) & wmask] : beta[d]);
             lse_add(m, sum, u);
             if (want_post) {
-              const float p = fast_exp(static_cast<float>(am + u)) * gscale;
+              const float p = ex2_approx(static_cast<float>(am + u) * kLog2e) * gscale;
               if (post) post[a] = p;
               if (hist) atomicAdd(&hist[lab], p);
             }
@@ -628,9 +558,10 @@ __global__ void __launch_bounds__(256, 4)
           }
         }
       }
-      __syncthreads();
     }
-    k0 = k1; k1 = k2; dst_c = dst_n; lab_c = lab_n; w_c = w_n; ptr_c = ptr_n;
+    cp_async_wait_all();
+    __syncthreads();
+    k0 = k1; k1 = k2; stg ^= 1;
   }
 
   if (tid == 0) {
@@ -759,7 +690,8 @@ template <typename ST>
 int launch_fwd(const nfst_packed_lattices_t* lat, const nfst_launch_t* launch, const nfst_scores_t* scores, void* alpha,
                void* logz, cudaStream_t st) {
   const int theta_smem = scores->theta && lat->vocab <= NFST_THETA_SMEM_MAX;
-  const size_t bytes = nfst_launch_smem_bytes(launch, lat->vocab, 0, 1, 0, 0, scores->theta != nullptr, 0);
+  const size_t bytes = nfst_launch_smem_bytes(launch, lat->vocab, 0, 1, 0, 0, scores->arc_scores != nullptr,
+                                              scores->theta != nullptr, 0);
   if (int rc = prepare_smem(nfst_fwd_kernel<ST>, bytes)) return rc;
   nfst_fwd_kernel<ST><<<launch->n_ids, launch->block_threads, bytes, st>>>(
       *lat, launch->lattice_ids, launch->window_states, scores->arc_scores, scores->theta, theta_smem,
@@ -776,7 +708,8 @@ int launch_bwd(const nfst_packed_lattices_t* lat, const nfst_launch_t* launch, c
   const int theta_smem = scores->theta && small_v;
   const int dtheta_smem = LOGS && dtheta && small_v;
   const size_t bytes = nfst_launch_smem_bytes(launch, lat->vocab, 1, LOGS, TROP, LOGS && (post || dtheta),
-                                              scores->theta != nullptr, LOGS && dtheta != nullptr);
+                                              scores->arc_scores != nullptr, scores->theta != nullptr,
+                                              LOGS && dtheta != nullptr);
   if (int rc = prepare_smem(nfst_bwd_kernel<ST, LOGS, TROP>, bytes)) return rc;
   nfst_bwd_kernel<ST, LOGS, TROP><<<launch->n_ids, launch->block_threads, bytes, st>>>(
       *lat, launch->lattice_ids, launch->window_states, scores->arc_scores, scores->theta, theta_smem, dtheta_smem,
@@ -811,12 +744,15 @@ int nfst_device_info(int device, int* sm_count, int* cc_major, int* cc_minor, si
 }
 
 size_t nfst_launch_smem_bytes(const nfst_launch_t* launch, int32_t vocab, int pass, int with_log, int with_trop,
-                              int with_post, int with_theta, int with_dtheta) {
+                              int with_post, int with_scores, int with_theta, int with_dtheta) {
   if (!launch) return 0;
   const bool small_v = vocab <= NFST_THETA_SMEM_MAX;
+  (void)with_post;
+  const bool bwd = pass != 0;
   const SmemPlan p = smem_plan(launch->window_states, launch->block_threads * kChunkArcsPerThread,
-                               launch->state_f64 ? 8 : 4, vocab, pass != 0, with_log != 0, with_trop != 0,
-                               with_post != 0, with_theta && small_v, with_dtheta && small_v);
+                               launch->state_f64 ? 8 : 4, vocab, !bwd || with_log != 0, bwd && with_trop != 0,
+                               with_scores != 0, with_theta != 0 || (bwd && with_dtheta != 0), with_theta && small_v,
+                               bwd && with_dtheta && small_v);
   return p.bytes;
 }
 

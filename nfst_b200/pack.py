@@ -62,8 +62,8 @@ class PackedLattices:
         "fwd_chunk_off", "fwd_chunks", "bwd_chunk_off", "bwd_chunks",
     )
 
-    # per-arc arrays the kernels read with 128-bit loads: kept zero-padded by PAD elements
-    _ARC_FIELDS = ("src_in", "label_in", "in2out", "dst_out", "label_out")
+    # arrays the kernels stage with 16-byte copies: kept zero-padded by PAD elements
+    _ARC_FIELDS = ("src_in", "label_in", "in2out", "dst_out", "label_out", "in_ptr", "out_ptr")
     PAD = 4
 
     @staticmethod
