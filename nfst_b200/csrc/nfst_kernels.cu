@@ -115,10 +115,11 @@ __device__ ST block_lse(ST m, float s) {
 // [window ST[W]] [delta window f32[W]] [2 stages x {nbr int[cap+8], aux int[cap+8], lab int[cap+8],
 // ptr int[cap+8]}] [theta f32[V]] [dtheta f32[V]]
 struct SmemPlan {
-  size_t win, dwin, stage0, stage_bytes, nbr, aux, lab, ptr, theta, dtheta, bytes;
+  size_t win, dwin, stage0, stage_bytes, nbr, aux, wsc, lab, ptr, theta, dtheta, bytes;
 };
 __host__ __device__ inline SmemPlan smem_plan(int W, int cap, int st_bytes, int vocab, bool logs, bool trop,
-                                              bool with_scores, bool with_labels, bool with_theta, bool with_dtheta) {
+                                              bool with_scores, bool with_labels, bool with_theta, bool with_dtheta,
+                                              int n_stages = 2, bool gathered_scores = false) {
   SmemPlan p;
   size_t o = 0;
   const size_t arr = static_cast<size_t>(cap + 8) * 4;
@@ -131,10 +132,11 @@ __host__ __device__ inline SmemPlan smem_plan(int W, int cap, int st_bytes, int 
   size_t q = 0;
   p.nbr = q; q += arr;                      // neighbour state of every arc (src_in / dst_out)
   p.aux = q; q += with_scores ? arr : 0;    // forward: in2out index; backward: the score itself
+  p.wsc = q; q += (with_scores && gathered_scores) ? arr : 0;  // forward: scores gathered through aux
   p.lab = q; q += with_labels ? arr : 0;
   p.ptr = q; q += arr;                      // CSR row pointers of the chunk's states
   p.stage_bytes = q;
-  o += 2 * q;
+  o += static_cast<size_t>(n_stages) * q;
   p.theta = o;
   o += with_theta ? static_cast<size_t>(vocab) * 4 : 0;
   p.dtheta = o;
@@ -183,6 +185,10 @@ __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
   const unsigned sa = static_cast<unsigned>(__cvta_generic_to_shared(smem));
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gmem));
 }
+__device__ __forceinline__ void cp_async4(void* smem, const void* gmem) {
+  const unsigned sa = static_cast<unsigned>(__cvta_generic_to_shared(smem));
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(sa), "l"(gmem));
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
 
@@ -209,7 +215,19 @@ __device__ __forceinline__ void stage_chunk(const int4& k, int cap, unsigned cha
     const int p4 = (k.w + 1 - pb + 3) >> 2;
     for (int i = threadIdx.x; i < p4; i += blockDim.x) cp_async16(s_ptr + 4 * i, ptr + pb + 4 * i);
   }
-  cp_async_commit();
+}
+
+// Gather the scores of a staged chunk through its staged index array, straight into shared
+// memory (4-byte cp.async, no registers): scores[idx[pos]] -> wsc[pos] for every staged slot.
+__device__ __forceinline__ void gather_scores(const int4& k, int cap, unsigned char* st, const SmemPlan& plan,
+                                              const float* __restrict__ scores) {
+  const int n = k.y - k.x;
+  if (scores && k.w > k.z && n <= cap) {
+    const int n_slots = ((k.y - (k.x & ~3) + 3) >> 2) << 2;
+    const int* s_idx = reinterpret_cast<const int*>(st + plan.aux);
+    float* s_w = reinterpret_cast<float*>(st + plan.wsc);
+    for (int i = threadIdx.x; i < n_slots; i += blockDim.x) cp_async4(s_w + i, scores + s_idx[i]);
+  }
 }
 
 // =====================================================================================
@@ -224,9 +242,10 @@ __global__ void __launch_bounds__(256, 3)
   const int NT = blockDim.x, tid = threadIdx.x;
   const int cap = NT * kChunkArcsPerThread;
   const SmemPlan plan = smem_plan(W, cap, sizeof(ST), L.vocab, true, false, arc_scores != nullptr, theta != nullptr,
-                                  theta_smem != 0, false);
+                                  theta_smem != 0, false, 3, true);
   ST* win = reinterpret_cast<ST*>(smem_raw + plan.win);
   const ST neg_inf = static_cast<ST>(kNegInf);
+  auto stage = [&](int i) { return smem_raw + plan.stage0 + static_cast<size_t>(i) * plan.stage_bytes; };
 
   const int b = ids ? ids[blockIdx.x] : blockIdx.x;
   const int base_s = L.state_off[b];
@@ -246,20 +265,30 @@ __global__ void __launch_bounds__(256, 3)
   const int32_t* idx_arr = arc_scores ? L.in2out : nullptr;
   const int32_t* lab_arr = th ? L.label_in : nullptr;
 
-  int4 k0 = chunk_at(chunks, c, c_end), k1 = chunk_at(chunks, c + 1, c_end);
-  int stg = 0;
-  stage_chunk(k0, cap, smem_raw + plan.stage0, plan, L.src_in, idx_arr, lab_arr, L.in_ptr);
+  // Three-stage software pipeline, all through cp.async (no staging registers):
+  //   chunk c   : arc arrays + gathered scores resident  -> reduced now
+  //   chunk c+1 : arc arrays resident                     -> its scores are gathered now (4 B copies)
+  //   chunk c+2 :                                            its arc arrays stream in now (16 B copies)
+  int4 k0 = chunk_at(chunks, c, c_end), k1 = chunk_at(chunks, c + 1, c_end), k2 = chunk_at(chunks, c + 2, c_end);
+  int s_cur = 0, s_nxt = 1, s_nn = 2;
+  stage_chunk(k0, cap, stage(0), plan, L.src_in, idx_arr, lab_arr, L.in_ptr);
+  stage_chunk(k1, cap, stage(1), plan, L.src_in, idx_arr, lab_arr, L.in_ptr);
+  cp_async_commit();
+  cp_async_wait_all();
+  __syncthreads();
+  gather_scores(k0, cap, stage(0), plan, arc_scores);
+  cp_async_commit();
   cp_async_wait_all();
   __syncthreads();
 
   for (; c < c_end; ++c) {
-    const int4 k2 = chunk_at(chunks, c + 2, c_end);  // descriptor two chunks ahead of its use
-    // chunk c+1 streams into the other stage while chunk c is reduced
-    stage_chunk(k1, cap, smem_raw + plan.stage0 + (stg ^ 1) * plan.stage_bytes, plan, L.src_in, idx_arr, lab_arr,
-                L.in_ptr);
-    const unsigned char* st = smem_raw + plan.stage0 + stg * plan.stage_bytes;
+    const int4 k3 = chunk_at(chunks, c + 3, c_end);  // descriptors run ahead of their use
+    stage_chunk(k2, cap, stage(s_nn), plan, L.src_in, idx_arr, lab_arr, L.in_ptr);
+    gather_scores(k1, cap, stage(s_nxt), plan, arc_scores);
+    cp_async_commit();
+    const unsigned char* st = stage(s_cur);
     const int* s_src = reinterpret_cast<const int*>(st + plan.nbr);
-    const int* s_idx = reinterpret_cast<const int*>(st + plan.aux);
+    const float* s_w = reinterpret_cast<const float*>(st + plan.wsc);
     const int* s_lab = reinterpret_cast<const int*>(st + plan.lab);
     const int* s_ptr = reinterpret_cast<const int*>(st + plan.ptr);
 
@@ -267,7 +296,9 @@ __global__ void __launch_bounds__(256, 3)
     const int n = a1 - a0, ns = s1 - s0;
     const int base4 = a0 & ~3;
     const int pofs = s0 & 3;
-    const int lo = whole ? static_cast<int>(0x80000000) : s0 - W;
+    // readable window: states [s1 - W, s0).  The slots of [s0 - W, s1 - W) are being
+    // overwritten by this chunk's own results, so those states are re-read from global.
+    const int lo = whole ? static_cast<int>(0x80000000) : s1 - W;
     if (n <= cap) {
       // lanes per state: 1 for wide chunks, widened while the chunk leaves the block idle
       int lg = 0;
@@ -285,10 +316,7 @@ __global__ void __launch_bounds__(256, 3)
         for (; i + 3 * step < b1; i += 4 * step) {
           const int c0 = s_src[i], c1 = s_src[i + step], c2 = s_src[i + 2 * step], c3 = s_src[i + 3 * step];
           float w0 = 0.f, w1 = 0.f, w2 = 0.f, w3 = 0.f;
-          if (arc_scores) {
-            w0 = __ldg(arc_scores + s_idx[i]); w1 = __ldg(arc_scores + s_idx[i + step]);
-            w2 = __ldg(arc_scores + s_idx[i + 2 * step]); w3 = __ldg(arc_scores + s_idx[i + 3 * step]);
-          }
+          if (arc_scores) { w0 = s_w[i]; w1 = s_w[i + step]; w2 = s_w[i + 2 * step]; w3 = s_w[i + 3 * step]; }
           if (th) {
             w0 += th[s_lab[i]]; w1 += th[s_lab[i + step]]; w2 += th[s_lab[i + 2 * step]]; w3 += th[s_lab[i + 3 * step]];
           }
@@ -304,7 +332,7 @@ __global__ void __launch_bounds__(256, 3)
         for (; i < b1; i += step) {
           const int c0 = s_src[i];
           float w0 = 0.f;
-          if (arc_scores) w0 = __ldg(arc_scores + s_idx[i]);
+          if (arc_scores) w0 = s_w[i];
           if (th) w0 += th[s_lab[i]];
           const ST v0 = c0 >= lo ? win[(c0 - base_s) & wmask] : alpha[c0];
           lse_push(m, sum, v0 + static_cast<ST>(w0), neg_inf);
@@ -345,8 +373,9 @@ __global__ void __launch_bounds__(256, 3)
       }
     }
     cp_async_wait_all();
-    __syncthreads();  // alpha of chunk c visible; chunk c+1 staged; stage of chunk c free
-    k0 = k1; k1 = k2; stg ^= 1;
+    __syncthreads();  // alpha of chunk c visible; scores of c+1 and arrays of c+2 landed; stage of c free
+    k0 = k1; k1 = k2; k2 = k3;
+    const int t = s_cur; s_cur = s_nxt; s_nxt = s_nn; s_nn = t;
   }
 
   // logZ = logsumexp over the sinks of alpha (every zero-out-degree state has beta = 1,
@@ -414,6 +443,7 @@ __global__ void __launch_bounds__(256, 3)
   int4 k0 = chunk_at(chunks, c, c_end), k1 = chunk_at(chunks, c + 1, c_end);
   int stg = 0;
   stage_chunk(k0, cap, smem_raw + plan.stage0, plan, L.dst_out, arc_scores, lab_arr, L.out_ptr);
+  cp_async_commit();
   cp_async_wait_all();
   __syncthreads();
 
@@ -421,6 +451,7 @@ __global__ void __launch_bounds__(256, 3)
     const int4 k2 = chunk_at(chunks, c + 2, c_end);
     stage_chunk(k1, cap, smem_raw + plan.stage0 + (stg ^ 1) * plan.stage_bytes, plan, L.dst_out, arc_scores, lab_arr,
                 L.out_ptr);
+    cp_async_commit();
     const unsigned char* st = smem_raw + plan.stage0 + stg * plan.stage_bytes;
     const int* s_dst = reinterpret_cast<const int*>(st + plan.nbr);
     const float* s_w = reinterpret_cast<const float*>(st + plan.aux);
@@ -431,7 +462,8 @@ __global__ void __launch_bounds__(256, 3)
     const int n = a1 - a0, ns = s1 - s0;
     const int base4 = a0 & ~3;
     const int pofs = s0 & 3;
-    const int hi = whole ? 0x7fffffff : s1 + W;
+    // readable window: states [s1, s0 + W) (see the forward kernel)
+    const int hi = whole ? 0x7fffffff : s0 + W;
     if (n <= cap) {
       int lg = 0;
       while (lg < 5 && (ns << (lg + 1)) <= NT) ++lg;
@@ -752,7 +784,7 @@ size_t nfst_launch_smem_bytes(const nfst_launch_t* launch, int32_t vocab, int pa
   const SmemPlan p = smem_plan(launch->window_states, launch->block_threads * kChunkArcsPerThread,
                                launch->state_f64 ? 8 : 4, vocab, !bwd || with_log != 0, bwd && with_trop != 0,
                                with_scores != 0, with_theta != 0 || (bwd && with_dtheta != 0), with_theta && small_v,
-                               bwd && with_dtheta && small_v);
+                               bwd && with_dtheta && small_v, bwd ? 2 : 3, !bwd);
   return p.bytes;
 }
 
