@@ -41,7 +41,7 @@
 extern "C" {
 #endif
 
-#define NFST_ABI_VERSION 2
+#define NFST_ABI_VERSION 3
 
 typedef enum nfst_status {
   NFST_OK = 0,
@@ -102,9 +102,9 @@ typedef struct nfst_packed_lattices {
 
 /*
  * One kernel launch = one thread block per lattice in `lattice_ids` (NULL = lattices
- * 0..n_ids-1).  The arc arrays of a chunk (up to 8*block_threads arcs) are staged in shared
- * memory with cp.async, double-buffered; larger chunks (a state whose degree exceeds that)
- * take a slower block-wide path.
+ * 0..n_ids-1).  The arc arrays of a chunk (up to `chunk_cap` arcs and states) are staged in
+ * shared memory with cp.async, multi-buffered; larger chunks (a single state whose degree
+ * exceeds that) take a slower block-wide path.
  * `window_states` (a power of two, >= 32) is the number of most recent per-state DP
  * values kept in shared memory; older ones are re-read from global memory.
  * `state_f64` != 0 keeps the log-semiring state vectors (alpha, beta, logZ) in float64:
@@ -117,6 +117,7 @@ typedef struct nfst_launch {
   int32_t block_threads; /* 32, 64, 128 or 256 */
   int32_t window_states;
   int32_t state_f64;
+  int32_t chunk_cap; /* multiple of 8; >= the largest staged chunk of the launch, in arcs and in states */
 } nfst_launch_t;
 
 /* Arc scores: w(a) = (arc_scores ? arc_scores[a] : 0) + (theta ? theta[label(a)] : 0);

@@ -53,6 +53,7 @@ class LaunchC(C.Structure):
         ("block_threads", C.c_int32),
         ("window_states", C.c_int32),
         ("state_f64", C.c_int32),
+        ("chunk_cap", C.c_int32),
     ]
 
 
@@ -104,7 +105,7 @@ def load() -> C.CDLL:
         fn = getattr(lib, name)  # AttributeError if the header and the library disagree
         fn.restype = res
         fn.argtypes = args
-    if lib.nfst_abi_version() != 2:
+    if lib.nfst_abi_version() != 3:
         raise RuntimeError("libnfst_b200.so ABI version mismatch")
     _lib = lib
     return lib

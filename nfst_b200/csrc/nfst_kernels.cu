@@ -51,9 +51,7 @@ int fail(int code, const char* fmt, ...) {
   } while (0)
 
 constexpr float kNegInf = -__builtin_huge_valf();
-constexpr int kChunkArcsPerThread = 8;  // tile capacity = 8 * blockDim arcs
 
-__device__ __forceinline__ int slot_of(int s, int base_s, int wmask) { return (s - base_s) & wmask; }
 __device__ __forceinline__ int4 chunk_at(const nfst_chunk_t* c, int i, int end) {
   return i < end ? __ldg(reinterpret_cast<const int4*>(c + i)) : make_int4(0, 0, 0, 0);
 }
@@ -132,7 +130,7 @@ __host__ __device__ inline SmemPlan smem_plan(int W, int cap, int st_bytes, int 
   size_t q = 0;
   p.nbr = q; q += arr;                      // neighbour state of every arc (src_in / dst_out)
   p.aux = q; q += with_scores ? arr : 0;    // forward: in2out index; backward: the score itself
-  p.wsc = q; q += (with_scores && gathered_scores) ? arr : 0;  // forward: scores gathered through aux
+  p.wsc = p.aux; (void)gathered_scores;      // forward: scores are gathered IN PLACE over their indices
   p.lab = q; q += with_labels ? arr : 0;
   p.ptr = q; q += arr;                      // CSR row pointers of the chunk's states
   p.stage_bytes = q;
@@ -192,24 +190,30 @@ __device__ __forceinline__ void cp_async4(void* smem, const void* gmem) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
 
-// Stage the arc arrays and row pointers of chunk k (16-byte cp.async copies, all threads).
-// Copies start at the 4-aligned position below the chunk and may run a few elements past
-// it; the per-arc arrays are zero-padded, so whatever is over-read is a valid index.
-__device__ __forceinline__ void stage_chunk(const int4& k, int cap, unsigned char* st, const SmemPlan& plan,
+// All dynamic shared memory is addressed as 32-bit words off one typed extern array (keeps
+// the accesses in the shared address space for the compiler: plain LDS/STS with immediate
+// offsets, no generic-pointer conversions in the loops).
+extern __shared__ __align__(16) float smem_f[];
+
+// Stage the arc arrays and row pointers of chunk k into the stage at word offset `st`
+// (16-byte cp.async copies, all threads).  Copies start at the 4-aligned position below the
+// chunk and may run a few elements past it; the arrays are zero-padded, so whatever is
+// over-read is a valid index.
+template <bool AUX, bool LAB>
+__device__ __forceinline__ void stage_chunk(const int4& k, int cap, int st, const SmemPlan& plan,
                                             const int32_t* __restrict__ nbr, const void* __restrict__ aux,
                                             const int32_t* __restrict__ lab, const int32_t* __restrict__ ptr) {
-  const int n = k.y - k.x;
-  if (k.w > k.z && n <= cap) {
+  if (k.w > k.z && k.y - k.x <= cap) {
     const int base4 = k.x & ~3;
     const int n4 = (k.y - base4 + 3) >> 2;
-    int* s_nbr = reinterpret_cast<int*>(st + plan.nbr);
-    int* s_aux = reinterpret_cast<int*>(st + plan.aux);
-    int* s_lab = reinterpret_cast<int*>(st + plan.lab);
-    int* s_ptr = reinterpret_cast<int*>(st + plan.ptr);
+    float* s_nbr = smem_f + st + plan.nbr / 4;
+    float* s_aux = smem_f + st + plan.aux / 4;
+    float* s_lab = smem_f + st + plan.lab / 4;
+    float* s_ptr = smem_f + st + plan.ptr / 4;
     for (int i = threadIdx.x; i < n4; i += blockDim.x) {
       cp_async16(s_nbr + 4 * i, nbr + base4 + 4 * i);
-      if (aux) cp_async16(s_aux + 4 * i, static_cast<const int32_t*>(aux) + base4 + 4 * i);
-      if (lab) cp_async16(s_lab + 4 * i, lab + base4 + 4 * i);
+      if (AUX) cp_async16(s_aux + 4 * i, static_cast<const int32_t*>(aux) + base4 + 4 * i);
+      if (LAB) cp_async16(s_lab + 4 * i, lab + base4 + 4 * i);
     }
     const int pb = k.z & ~3;
     const int p4 = (k.w + 1 - pb + 3) >> 2;
@@ -219,13 +223,13 @@ __device__ __forceinline__ void stage_chunk(const int4& k, int cap, unsigned cha
 
 // Gather the scores of a staged chunk through its staged index array, straight into shared
 // memory (4-byte cp.async, no registers): scores[idx[pos]] -> wsc[pos] for every staged slot.
-__device__ __forceinline__ void gather_scores(const int4& k, int cap, unsigned char* st, const SmemPlan& plan,
+__device__ __forceinline__ void gather_scores(const int4& k, int cap, int st, const SmemPlan& plan,
                                               const float* __restrict__ scores) {
-  const int n = k.y - k.x;
-  if (scores && k.w > k.z && n <= cap) {
+  if (k.w > k.z && k.y - k.x <= cap) {
     const int n_slots = ((k.y - (k.x & ~3) + 3) >> 2) << 2;
-    const int* s_idx = reinterpret_cast<const int*>(st + plan.aux);
-    float* s_w = reinterpret_cast<float*>(st + plan.wsc);
+    const int* s_idx = reinterpret_cast<const int*>(smem_f + st + plan.aux / 4);
+    float* s_w = smem_f + st + plan.wsc / 4;
+    // in place: each slot's index is read (LDS) before the copy that overwrites it is issued
     for (int i = threadIdx.x; i < n_slots; i += blockDim.x) cp_async4(s_w + i, scores + s_idx[i]);
   }
 }
@@ -233,19 +237,19 @@ __device__ __forceinline__ void gather_scores(const int4& k, int cap, unsigned c
 // =====================================================================================
 // forward: alpha
 // =====================================================================================
-template <typename ST>
+// SC: per-arc scores given; TH: theta[label] given (at least one of them).
+template <typename ST, bool SC, bool TH>
 __global__ void __launch_bounds__(256, 3)
-    nfst_fwd_kernel(const nfst_packed_lattices_t L, const int32_t* __restrict__ ids, int W,
+    nfst_fwd_kernel(const nfst_packed_lattices_t L, const int32_t* __restrict__ ids, int W, int cap,
                     const float* __restrict__ arc_scores, const float* __restrict__ theta, int theta_smem, ST* alpha,
                     ST* __restrict__ logz) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
   const int NT = blockDim.x, tid = threadIdx.x;
-  const int cap = NT * kChunkArcsPerThread;
-  const SmemPlan plan = smem_plan(W, cap, sizeof(ST), L.vocab, true, false, arc_scores != nullptr, theta != nullptr,
-                                  theta_smem != 0, false, 3, true);
-  ST* win = reinterpret_cast<ST*>(smem_raw + plan.win);
+  const SmemPlan plan = smem_plan(W, cap, sizeof(ST), L.vocab, true, false, SC, TH, theta_smem != 0, false, 3, true);
+  ST* const win = reinterpret_cast<ST*>(smem_f + plan.win / 4);
   const ST neg_inf = static_cast<ST>(kNegInf);
-  auto stage = [&](int i) { return smem_raw + plan.stage0 + static_cast<size_t>(i) * plan.stage_bytes; };
+  const int stage0 = static_cast<int>(plan.stage0 / 4), stage_words = static_cast<int>(plan.stage_bytes / 4);
+  const int o_nbr = static_cast<int>(plan.nbr / 4), o_wsc = static_cast<int>(plan.wsc / 4),
+            o_lab = static_cast<int>(plan.lab / 4), o_ptr = static_cast<int>(plan.ptr / 4);
 
   const int b = ids ? ids[blockIdx.x] : blockIdx.x;
   const int base_s = L.state_off[b];
@@ -253,8 +257,8 @@ __global__ void __launch_bounds__(256, 3)
   const int wmask = W - 1;
   const bool whole = (L.state_off[b + 1] - base_s) <= W;  // the whole lattice fits the window
   const float* th = theta;
-  if (theta && theta_smem) {
-    float* sth = reinterpret_cast<float*>(smem_raw + plan.theta);
+  if (TH && theta_smem) {
+    float* sth = smem_f + plan.theta / 4;
     for (int i = tid; i < L.vocab; i += NT) sth[i] = theta[i];
     th = sth;
   }
@@ -262,91 +266,99 @@ __global__ void __launch_bounds__(256, 3)
   const nfst_chunk_t* chunks = L.fwd_chunks;
   int c = L.fwd_chunk_off[b];
   const int c_end = L.fwd_chunk_off[b + 1];
-  const int32_t* idx_arr = arc_scores ? L.in2out : nullptr;
-  const int32_t* lab_arr = th ? L.label_in : nullptr;
 
   // Three-stage software pipeline, all through cp.async (no staging registers):
   //   chunk c   : arc arrays + gathered scores resident  -> reduced now
   //   chunk c+1 : arc arrays resident                     -> its scores are gathered now (4 B copies)
   //   chunk c+2 :                                            its arc arrays stream in now (16 B copies)
   int4 k0 = chunk_at(chunks, c, c_end), k1 = chunk_at(chunks, c + 1, c_end), k2 = chunk_at(chunks, c + 2, c_end);
-  int s_cur = 0, s_nxt = 1, s_nn = 2;
-  stage_chunk(k0, cap, stage(0), plan, L.src_in, idx_arr, lab_arr, L.in_ptr);
-  stage_chunk(k1, cap, stage(1), plan, L.src_in, idx_arr, lab_arr, L.in_ptr);
+  int s_cur = stage0, s_nxt = stage0 + stage_words, s_nn = stage0 + 2 * stage_words;
+  stage_chunk<SC, TH>(k0, cap, s_cur, plan, L.src_in, L.in2out, L.label_in, L.in_ptr);
+  stage_chunk<SC, TH>(k1, cap, s_nxt, plan, L.src_in, L.in2out, L.label_in, L.in_ptr);
   cp_async_commit();
   cp_async_wait_all();
   __syncthreads();
-  gather_scores(k0, cap, stage(0), plan, arc_scores);
+  if (SC) gather_scores(k0, cap, s_cur, plan, arc_scores);
   cp_async_commit();
   cp_async_wait_all();
   __syncthreads();
 
+#pragma unroll 1
   for (; c < c_end; ++c) {
     const int4 k3 = chunk_at(chunks, c + 3, c_end);  // descriptors run ahead of their use
-    stage_chunk(k2, cap, stage(s_nn), plan, L.src_in, idx_arr, lab_arr, L.in_ptr);
-    gather_scores(k1, cap, stage(s_nxt), plan, arc_scores);
+    stage_chunk<SC, TH>(k2, cap, s_nn, plan, L.src_in, L.in2out, L.label_in, L.in_ptr);
+    if (SC) gather_scores(k1, cap, s_nxt, plan, arc_scores);
     cp_async_commit();
-    const unsigned char* st = stage(s_cur);
-    const int* s_src = reinterpret_cast<const int*>(st + plan.nbr);
-    const float* s_w = reinterpret_cast<const float*>(st + plan.wsc);
-    const int* s_lab = reinterpret_cast<const int*>(st + plan.lab);
-    const int* s_ptr = reinterpret_cast<const int*>(st + plan.ptr);
+    const int* s_src = reinterpret_cast<const int*>(smem_f + s_cur + o_nbr);
+    const float* s_w = smem_f + s_cur + o_wsc;
+    const int* s_lab = reinterpret_cast<const int*>(smem_f + s_cur + o_lab);
 
     const int a0 = k0.x, a1 = k0.y, s0 = k0.z, s1 = k0.w;
     const int n = a1 - a0, ns = s1 - s0;
     const int base4 = a0 & ~3;
-    const int pofs = s0 & 3;
+    // row pointers relative to the stage arrays
+    const int* s_ptr = reinterpret_cast<const int*>(smem_f + s_cur + o_ptr) + (s0 & 3);
     // readable window: states [s1 - W, s0).  The slots of [s0 - W, s1 - W) are being
     // overwritten by this chunk's own results, so those states are re-read from global.
     const int lo = whole ? static_cast<int>(0x80000000) : s1 - W;
+    auto value_of = [&](int src) -> ST {
+      if (src >= lo) return win[(src - base_s) & wmask];
+      return alpha[src];
+    };
+    auto arc_value = [&](int i) -> ST {
+      float w = SC ? s_w[i] : 0.0f;
+      if (TH) w += th[s_lab[i]];
+      return value_of(s_src[i]) + static_cast<ST>(w);
+    };
     if (n <= cap) {
-      // lanes per state: 1 for wide chunks, widened while the chunk leaves the block idle
-      int lg = 0;
-      while (lg < 5 && (ns << (lg + 1)) <= NT) ++lg;
-      const int G = 1 << lg, lane_g = tid & (G - 1), ngrp = NT >> lg;
-      for (int jb = 0; jb < ns; jb += ngrp) {
-        const int j = jb + (tid >> lg);
-        const bool valid = j < ns;
-        const int b0 = valid ? s_ptr[pofs + j] - base4 : 0, b1 = valid ? s_ptr[pofs + j + 1] - base4 : 0;
-        ST m = neg_inf;
-        float sum = 0.0f;
-        int i = b0 + lane_g;
-        const int step = G;
-        // 4 arcs per trip: the 4 score gathers are in flight together
-        for (; i + 3 * step < b1; i += 4 * step) {
-          const int c0 = s_src[i], c1 = s_src[i + step], c2 = s_src[i + 2 * step], c3 = s_src[i + 3 * step];
-          float w0 = 0.f, w1 = 0.f, w2 = 0.f, w3 = 0.f;
-          if (arc_scores) { w0 = s_w[i]; w1 = s_w[i + step]; w2 = s_w[i + 2 * step]; w3 = s_w[i + 3 * step]; }
-          if (th) {
-            w0 += th[s_lab[i]]; w1 += th[s_lab[i + step]]; w2 += th[s_lab[i + 2 * step]]; w3 += th[s_lab[i + 3 * step]];
+      if (ns * 2 > NT) {
+        // ---- wide chunk: one thread per state, arcs straight from the staged arrays
+#pragma unroll 1
+        for (int j = tid; j < ns; j += NT) {
+          int i = s_ptr[j] - base4;
+          const int b1 = s_ptr[j + 1] - base4;
+          ST m = neg_inf;
+          float sum = 0.0f;
+#pragma unroll 1
+          for (; i + 3 < b1; i += 4) {  // 4 arcs per trip: independent loads first
+            const ST v0 = arc_value(i), v1 = arc_value(i + 1), v2 = arc_value(i + 2), v3 = arc_value(i + 3);
+            lse_push(m, sum, v0, neg_inf);
+            lse_push(m, sum, v1, neg_inf);
+            lse_push(m, sum, v2, neg_inf);
+            lse_push(m, sum, v3, neg_inf);
           }
-          const ST v0 = c0 >= lo ? win[(c0 - base_s) & wmask] : alpha[c0];
-          const ST v1 = c1 >= lo ? win[(c1 - base_s) & wmask] : alpha[c1];
-          const ST v2 = c2 >= lo ? win[(c2 - base_s) & wmask] : alpha[c2];
-          const ST v3 = c3 >= lo ? win[(c3 - base_s) & wmask] : alpha[c3];
-          lse_push(m, sum, v0 + static_cast<ST>(w0), neg_inf);
-          lse_push(m, sum, v1 + static_cast<ST>(w1), neg_inf);
-          lse_push(m, sum, v2 + static_cast<ST>(w2), neg_inf);
-          lse_push(m, sum, v3 + static_cast<ST>(w3), neg_inf);
-        }
-        for (; i < b1; i += step) {
-          const int c0 = s_src[i];
-          float w0 = 0.f;
-          if (arc_scores) w0 = s_w[i];
-          if (th) w0 += th[s_lab[i]];
-          const ST v0 = c0 >= lo ? win[(c0 - base_s) & wmask] : alpha[c0];
-          lse_push(m, sum, v0 + static_cast<ST>(w0), neg_inf);
-        }
-        for (int o = G >> 1; o > 0; o >>= 1) {
-          const ST m2 = __shfl_xor_sync(0xffffffffu, m, o);
-          const float s2 = __shfl_xor_sync(0xffffffffu, sum, o);
-          lse_join(m, sum, m2, s2, neg_inf);
-        }
-        if (valid && lane_g == 0) {
+#pragma unroll 1
+          for (; i < b1; ++i) lse_push(m, sum, arc_value(i), neg_inf);
           const int s = s0 + j;
           const ST v = (s == start) ? static_cast<ST>(0) : lse_finish(m, sum, neg_inf);
           if (s >= s1 - W) win[(s - base_s) & wmask] = v;  // only the newest W states own a slot
           alpha[s] = v;
+        }
+      } else {
+        // ---- narrow chunk: 2^lg lanes per state so that the block stays busy
+        int lg = 1;
+        while (lg < 5 && (ns << (lg + 1)) <= NT) ++lg;
+        const int G = 1 << lg, lane_g = tid & (G - 1), ngrp = NT >> lg;
+#pragma unroll 1
+        for (int jb = 0; jb < ns; jb += ngrp) {
+          const int j = jb + (tid >> lg);
+          const bool valid = j < ns;
+          const int b0 = valid ? s_ptr[j] - base4 : 0, b1 = valid ? s_ptr[j + 1] - base4 : 0;
+          ST m = neg_inf;
+          float sum = 0.0f;
+#pragma unroll 1
+          for (int i = b0 + lane_g; i < b1; i += G) lse_push(m, sum, arc_value(i), neg_inf);
+          for (int o = G >> 1; o > 0; o >>= 1) {
+            const ST m2 = __shfl_xor_sync(0xffffffffu, m, o);
+            const float s2 = __shfl_xor_sync(0xffffffffu, sum, o);
+            lse_join(m, sum, m2, s2, neg_inf);
+          }
+          if (valid && lane_g == 0) {
+            const int s = s0 + j;
+            const ST v = (s == start) ? static_cast<ST>(0) : lse_finish(m, sum, neg_inf);
+            if (s >= s1 - W) win[(s - base_s) & wmask] = v;
+            alpha[s] = v;
+          }
         }
       }
     } else {
@@ -358,11 +370,9 @@ __global__ void __launch_bounds__(256, 3)
         float sum = 0.0f;
         for (int a = b0 + tid; a < b1; a += NT) {
           float w = 0.0f;
-          if (arc_scores) w = arc_scores[L.in2out[a]];
-          if (th) w += th[L.label_in[a]];
-          const int src = L.src_in[a];
-          const ST av = (src >= lo) ? win[(src - base_s) & wmask] : alpha[src];
-          lse_add(m, sum, static_cast<ST>(w) + av);
+          if (SC) w = arc_scores[L.in2out[a]];
+          if (TH) w += th[L.label_in[a]];
+          lse_add(m, sum, static_cast<ST>(w) + value_of(L.src_in[a]));
         }
         const ST v0 = block_lse(m, sum);
         if (tid == 0) {
@@ -390,39 +400,41 @@ __global__ void __launch_bounds__(256, 3)
 // =====================================================================================
 // fused backward: beta (+ posteriors, dtheta) and/or Viterbi delta + backpointer
 // =====================================================================================
-template <typename ST, bool LOGS, bool TROP>
+// LOGS / TROP: semirings; SC / TH: score sources; POST: posteriors (post and/or dtheta).
+template <typename ST, bool LOGS, bool TROP, bool SC, bool TH, bool POST>
 __global__ void __launch_bounds__(256, 3)
-    nfst_bwd_kernel(const nfst_packed_lattices_t L, const int32_t* __restrict__ ids, int W,
+    nfst_bwd_kernel(const nfst_packed_lattices_t L, const int32_t* __restrict__ ids, int W, int cap,
                     const float* __restrict__ arc_scores, const float* __restrict__ theta, int theta_smem,
                     int dtheta_smem, const ST* __restrict__ alpha, const ST* __restrict__ logz,
                     const float* __restrict__ grad_logz, ST* beta, ST* __restrict__ logz_bwd, float* __restrict__ post,
                     float* __restrict__ dtheta, float* delta, int32_t* __restrict__ backptr,
                     float* __restrict__ vit_score) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
   const int NT = blockDim.x, tid = threadIdx.x;
-  const int cap = NT * kChunkArcsPerThread;
-  const bool want_post = LOGS && (post != nullptr || dtheta != nullptr);
-  const bool need_label = (theta != nullptr) || (LOGS && dtheta != nullptr);
-  const SmemPlan plan = smem_plan(W, cap, sizeof(ST), L.vocab, LOGS, TROP, arc_scores != nullptr, need_label,
-                                  theta_smem != 0, dtheta_smem != 0);
-  ST* win = reinterpret_cast<ST*>(smem_raw + plan.win);
-  float* dwin = reinterpret_cast<float*>(smem_raw + plan.dwin);
+  const bool want_hist = POST && dtheta != nullptr;
+  const bool need_label = TH || want_hist;
+  const SmemPlan plan =
+      smem_plan(W, cap, sizeof(ST), L.vocab, LOGS, TROP, SC, need_label, theta_smem != 0, dtheta_smem != 0);
+  ST* const win = reinterpret_cast<ST*>(smem_f + plan.win / 4);
+  float* const dwin = smem_f + plan.dwin / 4;
   const ST neg_inf = static_cast<ST>(kNegInf);
+  const int stage0 = static_cast<int>(plan.stage0 / 4), stage_words = static_cast<int>(plan.stage_bytes / 4);
+  const int o_nbr = static_cast<int>(plan.nbr / 4), o_aux = static_cast<int>(plan.aux / 4),
+            o_lab = static_cast<int>(plan.lab / 4), o_ptr = static_cast<int>(plan.ptr / 4);
 
   const int b = ids ? ids[blockIdx.x] : blockIdx.x;
   const int base_s = L.state_off[b];
   const int wmask = W - 1;
   const bool whole = (L.state_off[b + 1] - base_s) <= W;
   const float* th = theta;
-  if (theta && theta_smem) {
-    float* sth = reinterpret_cast<float*>(smem_raw + plan.theta);
+  if (TH && theta_smem) {
+    float* sth = smem_f + plan.theta / 4;
     for (int i = tid; i < L.vocab; i += NT) sth[i] = theta[i];
     th = sth;
   }
   float* hist = nullptr;
-  if (LOGS && dtheta) {
+  if (want_hist) {
     if (dtheta_smem) {
-      hist = reinterpret_cast<float*>(smem_raw + plan.dtheta);
+      hist = smem_f + plan.dtheta / 4;
       for (int i = tid; i < L.vocab; i += NT) hist[i] = 0.0f;
     } else {
       hist = dtheta;
@@ -430,7 +442,7 @@ __global__ void __launch_bounds__(256, 3)
   }
   ST lz = 0;
   float gscale = 1.0f;
-  if (want_post) {
+  if (POST) {
     lz = logz[b];
     if (grad_logz) gscale = grad_logz[b];
   }
@@ -441,90 +453,119 @@ __global__ void __launch_bounds__(256, 3)
   const int32_t* lab_arr = need_label ? L.label_out : nullptr;
 
   int4 k0 = chunk_at(chunks, c, c_end), k1 = chunk_at(chunks, c + 1, c_end);
-  int stg = 0;
-  stage_chunk(k0, cap, smem_raw + plan.stage0, plan, L.dst_out, arc_scores, lab_arr, L.out_ptr);
+  int s_cur = stage0, s_nxt = stage0 + stage_words;
+  auto stage_in = [&](const int4& k, int st) {
+    if (need_label) stage_chunk<SC, true>(k, cap, st, plan, L.dst_out, arc_scores, lab_arr, L.out_ptr);
+    else stage_chunk<SC, false>(k, cap, st, plan, L.dst_out, arc_scores, lab_arr, L.out_ptr);
+  };
+  stage_in(k0, s_cur);
   cp_async_commit();
   cp_async_wait_all();
   __syncthreads();
 
+#pragma unroll 1
   for (; c < c_end; ++c) {
     const int4 k2 = chunk_at(chunks, c + 2, c_end);
-    stage_chunk(k1, cap, smem_raw + plan.stage0 + (stg ^ 1) * plan.stage_bytes, plan, L.dst_out, arc_scores, lab_arr,
-                L.out_ptr);
+    stage_in(k1, s_nxt);
     cp_async_commit();
-    const unsigned char* st = smem_raw + plan.stage0 + stg * plan.stage_bytes;
-    const int* s_dst = reinterpret_cast<const int*>(st + plan.nbr);
-    const float* s_w = reinterpret_cast<const float*>(st + plan.aux);
-    const int* s_lab = reinterpret_cast<const int*>(st + plan.lab);
-    const int* s_ptr = reinterpret_cast<const int*>(st + plan.ptr);
+    const int* s_dst = reinterpret_cast<const int*>(smem_f + s_cur + o_nbr);
+    const float* s_w = smem_f + s_cur + o_aux;
+    const int* s_lab = reinterpret_cast<const int*>(smem_f + s_cur + o_lab);
 
     const int a0 = k0.x, a1 = k0.y, s0 = k0.z, s1 = k0.w;
     const int n = a1 - a0, ns = s1 - s0;
     const int base4 = a0 & ~3;
-    const int pofs = s0 & 3;
+    const int* s_ptr = reinterpret_cast<const int*>(smem_f + s_cur + o_ptr) + (s0 & 3);
     // readable window: states [s1, s0 + W) (see the forward kernel)
     const int hi = whole ? 0x7fffffff : s0 + W;
+    auto beta_of = [&](int d) -> ST {
+      if (d < hi) return win[(d - base_s) & wmask];
+      return beta[d];
+    };
+    auto delta_of = [&](int d) -> float {
+      if (d < hi) return dwin[(d - base_s) & wmask];
+      return delta[d];
+    };
+    // one arc of the staged chunk: log-semiring push (+ posterior) and/or tropical candidate
+    auto visit = [&](int i, ST am, ST& m, float& sum, float& bt, int& bi) {
+      const int d = s_dst[i];
+      float w = SC ? s_w[i] : 0.0f;
+      int lab = 0;
+      if (TH || POST) { if (need_label) lab = s_lab[i]; }
+      if (TH) w += th[lab];
+      if (LOGS) {
+        const ST u = static_cast<ST>(w) + beta_of(d);
+        lse_push(m, sum, u, neg_inf);
+        if (POST) {
+          const float p = ex2_approx(static_cast<float>(am + u) * kLog2e) * gscale;
+          if (post) post[base4 + i] = p;
+          if (hist) atomicAdd(&hist[lab], p);
+        }
+      }
+      if (TROP) {
+        const float t = __fadd_rn(w, delta_of(d));
+        if (t > bt) { bt = t; bi = i; }  // strict: within a lane arcs come in label order
+      }
+    };
+    auto finish = [&](int s, bool sink, ST m, float sum, float bt, int bi) {
+      // sinks: beta = 1 (scorers.py:720), delta = 0
+      if (LOGS) {
+        const ST v = sink ? static_cast<ST>(0) : lse_finish(m, sum, neg_inf);
+        if (s < s0 + W) win[(s - base_s) & wmask] = v;
+        beta[s] = v;
+      }
+      if (TROP) {
+        const float v = sink ? 0.0f : bt;
+        if (s < s0 + W) dwin[(s - base_s) & wmask] = v;
+        delta[s] = v;
+        backptr[s] = sink ? -1 : base4 + bi;
+      }
+    };
     if (n <= cap) {
-      int lg = 0;
-      while (lg < 5 && (ns << (lg + 1)) <= NT) ++lg;
-      const int G = 1 << lg, lane_g = tid & (G - 1), ngrp = NT >> lg;
-      for (int jb = 0; jb < ns; jb += ngrp) {
-        const int j = jb + (tid >> lg);
-        const bool valid = j < ns;
-        const int b0 = valid ? s_ptr[pofs + j] - base4 : 0, b1 = valid ? s_ptr[pofs + j + 1] - base4 : 0;
-        const int s = s0 + j;
-        ST am = 0;
-        if (want_post && valid) am = alpha[s] - lz;  // issued before the arc loop, consumed inside it
-        ST m = neg_inf;
-        float sum = 0.0f;
-        float bt = kNegInf;
-        int bi = 0x7fffffff;
-        for (int i = b0 + lane_g; i < b1; i += G) {
-          const int d = s_dst[i];
-          float w = arc_scores ? s_w[i] : 0.0f;
-          int lab = 0;
-          if (need_label) lab = s_lab[i];
-          if (th) w += th[lab];
-          const int slot = (d - base_s) & wmask;
-          if (LOGS) {
-            const ST u = static_cast<ST>(w) + (d < hi ? win[slot] : beta[d]);
-            lse_push(m, sum, u, neg_inf);
-            if (want_post) {
-              const float p = ex2_approx(static_cast<float>(am + u) * kLog2e) * gscale;
-              if (post) post[base4 + i] = p;
-              if (hist) atomicAdd(&hist[lab], p);
+      if (ns * 2 > NT) {
+#pragma unroll 1
+        for (int j = tid; j < ns; j += NT) {
+          const int b0 = s_ptr[j] - base4, b1 = s_ptr[j + 1] - base4;
+          const int s = s0 + j;
+          ST am = 0;
+          if (POST) am = alpha[s] - lz;  // issued before the arc loop, consumed inside it
+          ST m = neg_inf;
+          float sum = 0.0f, bt = kNegInf;
+          int bi = 0x7fffffff;
+#pragma unroll 2
+          for (int i = b0; i < b1; ++i) visit(i, am, m, sum, bt, bi);
+          finish(s, b0 == b1, m, sum, bt, bi);
+        }
+      } else {
+        int lg = 1;
+        while (lg < 5 && (ns << (lg + 1)) <= NT) ++lg;
+        const int G = 1 << lg, lane_g = tid & (G - 1), ngrp = NT >> lg;
+#pragma unroll 1
+        for (int jb = 0; jb < ns; jb += ngrp) {
+          const int j = jb + (tid >> lg);
+          const bool valid = j < ns;
+          const int b0 = valid ? s_ptr[j] - base4 : 0, b1 = valid ? s_ptr[j + 1] - base4 : 0;
+          const int s = s0 + j;
+          ST am = 0;
+          if (POST && valid) am = alpha[s] - lz;
+          ST m = neg_inf;
+          float sum = 0.0f, bt = kNegInf;
+          int bi = 0x7fffffff;
+#pragma unroll 1
+          for (int i = b0 + lane_g; i < b1; i += G) visit(i, am, m, sum, bt, bi);
+          for (int o = G >> 1; o > 0; o >>= 1) {
+            if (LOGS) {
+              const ST m2 = __shfl_xor_sync(0xffffffffu, m, o);
+              const float s2 = __shfl_xor_sync(0xffffffffu, sum, o);
+              lse_join(m, sum, m2, s2, neg_inf);
+            }
+            if (TROP) {
+              const float t2 = __shfl_xor_sync(0xffffffffu, bt, o);
+              const int i2 = __shfl_xor_sync(0xffffffffu, bi, o);
+              if (t2 > bt || (t2 == bt && i2 < bi)) { bt = t2; bi = i2; }
             }
           }
-          if (TROP) {
-            const float t = __fadd_rn(w, d < hi ? dwin[slot] : delta[d]);
-            if (t > bt) { bt = t; bi = i; }  // strict: within a lane arcs come in label order
-          }
-        }
-        for (int o = G >> 1; o > 0; o >>= 1) {
-          if (LOGS) {
-            const ST m2 = __shfl_xor_sync(0xffffffffu, m, o);
-            const float s2 = __shfl_xor_sync(0xffffffffu, sum, o);
-            lse_join(m, sum, m2, s2, neg_inf);
-          }
-          if (TROP) {
-            const float t2 = __shfl_xor_sync(0xffffffffu, bt, o);
-            const int i2 = __shfl_xor_sync(0xffffffffu, bi, o);
-            if (t2 > bt || (t2 == bt && i2 < bi)) { bt = t2; bi = i2; }
-          }
-        }
-        if (valid && lane_g == 0) {
-          const bool sink = (b0 == b1);  // sinks: beta = 1 (scorers.py:720), delta = 0
-          if (LOGS) {
-            const ST v = sink ? static_cast<ST>(0) : lse_finish(m, sum, neg_inf);
-            if (s < s0 + W) win[slot_of(s, base_s, wmask)] = v;
-            beta[s] = v;
-          }
-          if (TROP) {
-            const float v = sink ? 0.0f : bt;
-            if (s < s0 + W) dwin[slot_of(s, base_s, wmask)] = v;
-            delta[s] = v;
-            backptr[s] = sink ? -1 : base4 + bi;
-          }
+          if (valid && lane_g == 0) finish(s, b0 == b1, m, sum, bt, bi);
         }
       }
     } else {
@@ -533,7 +574,7 @@ __global__ void __launch_bounds__(256, 3)
         const int s = s0 + j;
         const int b0 = L.out_ptr[s], b1 = L.out_ptr[s + 1];
         ST am = 0;
-        if (want_post) am = alpha[s] - lz;
+        if (POST) am = alpha[s] - lz;
         ST m = neg_inf;
         float sum = 0.0f;
         float bt = kNegInf;
@@ -542,20 +583,19 @@ __global__ void __launch_bounds__(256, 3)
           const int d = L.dst_out[a];
           int lab = 0;
           if (need_label) lab = L.label_out[a];
-          float w = arc_scores ? arc_scores[a] : 0.0f;
-          if (th) w += th[lab];
-          const bool inw = d < hi;
+          float w = SC ? arc_scores[a] : 0.0f;
+          if (TH) w += th[lab];
           if (LOGS) {
-            const ST u = static_cast<ST>(w) + (inw ? win[(d - base_s) & wmask] : beta[d]);
+            const ST u = static_cast<ST>(w) + beta_of(d);
             lse_add(m, sum, u);
-            if (want_post) {
+            if (POST) {
               const float p = ex2_approx(static_cast<float>(am + u) * kLog2e) * gscale;
               if (post) post[a] = p;
               if (hist) atomicAdd(&hist[lab], p);
             }
           }
           if (TROP) {
-            const float t = __fadd_rn(w, inw ? dwin[(d - base_s) & wmask] : delta[d]);
+            const float t = __fadd_rn(w, delta_of(d));
             if (t > bt || (t == bt && a < bi)) { bt = t; bi = a; }
           }
         }
@@ -593,7 +633,8 @@ __global__ void __launch_bounds__(256, 3)
     }
     cp_async_wait_all();
     __syncthreads();
-    k0 = k1; k1 = k2; stg ^= 1;
+    k0 = k1; k1 = k2;
+    const int t = s_cur; s_cur = s_nxt; s_nxt = t;
   }
 
   if (tid == 0) {
@@ -601,7 +642,7 @@ __global__ void __launch_bounds__(256, 3)
     if (LOGS && logz_bwd) logz_bwd[b] = beta[start];
     if (TROP && vit_score) vit_score[b] = delta[start];
   }
-  if (LOGS && dtheta && dtheta_smem) {
+  if (want_hist && dtheta_smem) {
     for (int i = tid; i < L.vocab; i += NT) {
       const float v = hist[i];
       if (v != 0.0f) atomicAdd(&dtheta[i], v);
@@ -701,6 +742,8 @@ int check_launch(const nfst_packed_lattices_t* lat, const nfst_launch_t* launch)
     return fail(NFST_ERR_BAD_ARG, "block_threads=%d must be 32, 64, 128 or 256", bt);
   const int w = launch->window_states;
   if (w < 32 || (w & (w - 1))) return fail(NFST_ERR_BAD_ARG, "window_states=%d must be a power of two >= 32", w);
+  if (launch->chunk_cap < 32 || (launch->chunk_cap & 7))
+    return fail(NFST_ERR_BAD_ARG, "chunk_cap=%d must be a multiple of 8, >= 32", launch->chunk_cap);
   return NFST_OK;
 }
 
@@ -718,16 +761,42 @@ int prepare_smem(K kernel, size_t bytes) {
   return NFST_OK;
 }
 
+template <typename ST, bool SC, bool TH>
+int launch_fwd2(const nfst_packed_lattices_t* lat, const nfst_launch_t* launch, const nfst_scores_t* scores,
+                void* alpha, void* logz, cudaStream_t st) {
+  const int theta_smem = TH && lat->vocab <= NFST_THETA_SMEM_MAX;
+  const size_t bytes = nfst_launch_smem_bytes(launch, lat->vocab, 0, 1, 0, 0, SC, TH, 0);
+  if (int rc = prepare_smem(nfst_fwd_kernel<ST, SC, TH>, bytes)) return rc;
+  nfst_fwd_kernel<ST, SC, TH><<<launch->n_ids, launch->block_threads, bytes, st>>>(
+      *lat, launch->lattice_ids, launch->window_states, launch->chunk_cap, scores->arc_scores, scores->theta,
+      theta_smem, static_cast<ST*>(alpha), static_cast<ST*>(logz));
+  NFST_CUDA_OK(cudaGetLastError());
+  return NFST_OK;
+}
+
 template <typename ST>
 int launch_fwd(const nfst_packed_lattices_t* lat, const nfst_launch_t* launch, const nfst_scores_t* scores, void* alpha,
                void* logz, cudaStream_t st) {
-  const int theta_smem = scores->theta && lat->vocab <= NFST_THETA_SMEM_MAX;
-  const size_t bytes = nfst_launch_smem_bytes(launch, lat->vocab, 0, 1, 0, 0, scores->arc_scores != nullptr,
-                                              scores->theta != nullptr, 0);
-  if (int rc = prepare_smem(nfst_fwd_kernel<ST>, bytes)) return rc;
-  nfst_fwd_kernel<ST><<<launch->n_ids, launch->block_threads, bytes, st>>>(
-      *lat, launch->lattice_ids, launch->window_states, scores->arc_scores, scores->theta, theta_smem,
-      static_cast<ST*>(alpha), static_cast<ST*>(logz));
+  const bool sc = scores->arc_scores != nullptr, th = scores->theta != nullptr;
+  if (sc && th) return launch_fwd2<ST, true, true>(lat, launch, scores, alpha, logz, st);
+  if (sc) return launch_fwd2<ST, true, false>(lat, launch, scores, alpha, logz, st);
+  return launch_fwd2<ST, false, true>(lat, launch, scores, alpha, logz, st);
+}
+
+template <typename ST, bool LOGS, bool TROP, bool SC, bool TH, bool POST>
+int launch_bwd3(const nfst_packed_lattices_t* lat, const nfst_launch_t* launch, const nfst_scores_t* scores,
+                const void* alpha, const void* logz, const float* grad_logz, void* beta, void* logz_bwd, float* post,
+                float* dtheta, float* delta, int32_t* backptr, float* vit_score, cudaStream_t st) {
+  const bool small_v = lat->vocab <= NFST_THETA_SMEM_MAX;
+  const int theta_smem = TH && small_v;
+  const int dtheta_smem = POST && dtheta && small_v;
+  const size_t bytes = nfst_launch_smem_bytes(launch, lat->vocab, 1, LOGS, TROP, POST, SC, TH, POST && dtheta != nullptr);
+  if (int rc = prepare_smem(nfst_bwd_kernel<ST, LOGS, TROP, SC, TH, POST>, bytes)) return rc;
+  nfst_bwd_kernel<ST, LOGS, TROP, SC, TH, POST><<<launch->n_ids, launch->block_threads, bytes, st>>>(
+      *lat, launch->lattice_ids, launch->window_states, launch->chunk_cap, scores->arc_scores, scores->theta,
+      theta_smem, dtheta_smem,
+      static_cast<const ST*>(alpha), static_cast<const ST*>(logz), grad_logz, static_cast<ST*>(beta),
+      static_cast<ST*>(logz_bwd), post, dtheta, delta, backptr, vit_score);
   NFST_CUDA_OK(cudaGetLastError());
   return NFST_OK;
 }
@@ -736,19 +805,16 @@ template <typename ST, bool LOGS, bool TROP>
 int launch_bwd(const nfst_packed_lattices_t* lat, const nfst_launch_t* launch, const nfst_scores_t* scores,
                const void* alpha, const void* logz, const float* grad_logz, void* beta, void* logz_bwd, float* post,
                float* dtheta, float* delta, int32_t* backptr, float* vit_score, cudaStream_t st) {
-  const bool small_v = lat->vocab <= NFST_THETA_SMEM_MAX;
-  const int theta_smem = scores->theta && small_v;
-  const int dtheta_smem = LOGS && dtheta && small_v;
-  const size_t bytes = nfst_launch_smem_bytes(launch, lat->vocab, 1, LOGS, TROP, LOGS && (post || dtheta),
-                                              scores->arc_scores != nullptr, scores->theta != nullptr,
-                                              LOGS && dtheta != nullptr);
-  if (int rc = prepare_smem(nfst_bwd_kernel<ST, LOGS, TROP>, bytes)) return rc;
-  nfst_bwd_kernel<ST, LOGS, TROP><<<launch->n_ids, launch->block_threads, bytes, st>>>(
-      *lat, launch->lattice_ids, launch->window_states, scores->arc_scores, scores->theta, theta_smem, dtheta_smem,
-      static_cast<const ST*>(alpha), static_cast<const ST*>(logz), grad_logz, static_cast<ST*>(beta),
-      static_cast<ST*>(logz_bwd), post, dtheta, delta, backptr, vit_score);
-  NFST_CUDA_OK(cudaGetLastError());
-  return NFST_OK;
+  const bool sc = scores->arc_scores != nullptr, th = scores->theta != nullptr;
+  const bool ps = LOGS && (post || dtheta);
+#define NFST_GO(SC, TH, PS)                                                                                      \
+  return launch_bwd3<ST, LOGS, TROP, SC, TH, (LOGS && PS)>(lat, launch, scores, alpha, logz, grad_logz, beta, logz_bwd, \
+                                                           post, dtheta, delta, backptr, vit_score, st)
+  if (sc && th) { if (ps) NFST_GO(true, true, true); NFST_GO(true, true, false); }
+  if (sc) { if (ps) NFST_GO(true, false, true); NFST_GO(true, false, false); }
+  if (ps) NFST_GO(false, true, true);
+  NFST_GO(false, true, false);
+#undef NFST_GO
 }
 
 }  // namespace
@@ -781,7 +847,7 @@ size_t nfst_launch_smem_bytes(const nfst_launch_t* launch, int32_t vocab, int pa
   const bool small_v = vocab <= NFST_THETA_SMEM_MAX;
   (void)with_post;
   const bool bwd = pass != 0;
-  const SmemPlan p = smem_plan(launch->window_states, launch->block_threads * kChunkArcsPerThread,
+  const SmemPlan p = smem_plan(launch->window_states, launch->chunk_cap,
                                launch->state_f64 ? 8 : 4, vocab, !bwd || with_log != 0, bwd && with_trop != 0,
                                with_scores != 0, with_theta != 0 || (bwd && with_dtheta != 0), with_theta && small_v,
                                bwd && with_dtheta && small_v, bwd ? 2 : 3, !bwd);
@@ -792,6 +858,7 @@ int nfst_fwd_f32(const nfst_packed_lattices_t* lat, const nfst_launch_t* launch,
                  void* alpha, void* logz, void* cuda_stream) {
   if (int rc = check_launch(lat, launch)) return rc;
   if (!scores || !alpha || !logz) return fail(NFST_ERR_BAD_ARG, "nfst_fwd_f32: null scores/alpha/logz");
+  if (!scores->arc_scores && !scores->theta) return fail(NFST_ERR_BAD_ARG, "need arc_scores and/or theta");
   if (launch->n_ids == 0) return NFST_OK;
   cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
   return launch->state_f64 ? launch_fwd<double>(lat, launch, scores, alpha, logz, st)
@@ -804,6 +871,7 @@ int nfst_bwd_fused_f32(const nfst_packed_lattices_t* lat, const nfst_launch_t* l
                        void* cuda_stream) {
   if (int rc = check_launch(lat, launch)) return rc;
   if (!scores) return fail(NFST_ERR_BAD_ARG, "nfst_bwd_fused_f32: null scores");
+  if (!scores->arc_scores && !scores->theta) return fail(NFST_ERR_BAD_ARG, "need arc_scores and/or theta");
   const bool want_post = post || dtheta;
   const bool logs = beta || logz_bwd || want_post;
   const bool trop = delta || backptr || vit_score;

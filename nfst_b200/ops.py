@@ -77,6 +77,7 @@ def _launch(g: LaunchGroup, st_dtype: torch.dtype) -> "_lib.LaunchC":
     f64 = st_dtype == torch.float64
     c.window_states = g.window_states(8 if f64 else 4, WINDOW_BYTES_MAX)
     c.state_f64 = int(f64)
+    c.chunk_cap = g.chunk_cap
     return c
 
 

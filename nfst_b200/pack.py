@@ -23,6 +23,7 @@ from __future__ import annotations
 import ctypes as C
 import dataclasses
 import math
+import os
 from typing import List, Optional
 
 import torch
@@ -31,8 +32,19 @@ from . import _lib
 
 # shared-memory window of the most recent per-state DP values, in bytes per state vector
 WINDOW_BYTES_MAX = 64 * 1024
-# a chunk targets 4 arcs per thread minus slack, so that one 128-bit load per thread covers it
-CHUNK_SLACK = 24
+# chunk geometry (tunable): a chunk targets ARCS_PER_THREAD arcs per thread of a block of at
+# most BLOCK_MAX threads; a state with more than target/HEAVY_DIV arcs gets a chunk of its own
+BLOCK_MAX = int(os.environ.get("NFST_BLOCK_MAX", "128"))
+ARCS_PER_THREAD = int(os.environ.get("NFST_ARCS_PER_THREAD", "12"))
+HEAVY_DIV = 4
+
+
+def chunk_geometry(block_threads: int):
+    """(target, heavy threshold, stage capacity) in arcs for a block size."""
+    target = ARCS_PER_THREAD * block_threads
+    heavy = max(target // HEAVY_DIV, 8)
+    cap = (target + heavy + 7) // 8 * 8
+    return target, heavy, cap
 
 
 @dataclasses.dataclass
@@ -45,6 +57,7 @@ class LaunchGroup:
     max_states: int  # largest lattice of the group, in states
     max_reach: int  # longest arc of the group, in packed state ids (sizes the shared-memory window)
     n_arcs: int
+    chunk_cap: int = 0  # stage capacity the lattices' chunks were cut for
 
     def window_states(self, state_bytes: int = 4, window_bytes_max: int = WINDOW_BYTES_MAX) -> int:
         """Power-of-two window: covers every arc of the group if that fits the byte budget
@@ -179,7 +192,7 @@ def _pow2_floor(x: int) -> int:
     return 1 << (max(int(x), 1).bit_length() - 1)
 
 
-def _build_chunks(ptr, slot, level_first, lat_of_state, target, n_lattices, descending):
+def _build_chunks(ptr, slot, level_first, lat_of_state, target, heavy_thr, n_lattices, descending):
     """Cut every level into chunks of consecutive states whose CSR segments END in the same
     `target`-sized window of the level's arc range (so a chunk has fewer than 2*target arcs
     unless it is a single heavy state, which gets a chunk of its own).
@@ -195,7 +208,7 @@ def _build_chunks(ptr, slot, level_first, lat_of_state, target, n_lattices, desc
     ck = torch.clamp(torch.div(rel_end - 1, target, rounding_mode="floor"), min=0)
     # ... and at most `target` states (levels full of arc-less states, e.g. many sinks)
     ck = ck + torch.div(torch.arange(S, device=dev) - level_first, target, rounding_mode="floor")
-    heavy = (deg > target).to(torch.int64)
+    heavy = (deg > heavy_thr).to(torch.int64)
     hk = 2 * torch.cumsum(heavy, 0) - heavy
     new = torch.ones(S, dtype=torch.bool, device=dev)
     if S > 1:
@@ -229,6 +242,7 @@ def build_groups(stats, dev) -> List[LaunchGroup]:
                 max_states=int(stats["states"][members].max()),
                 max_reach=int(stats["reach"][members].max()),
                 n_arcs=int(stats["arcs"][members].sum()),
+                chunk_cap=int(stats["chunk_cap"][members].max()),
             )
         )
     return groups
@@ -409,10 +423,13 @@ def pack_arcs(
     lvl_end = torch.cat([level_ptr[1:], level_ptr.new_tensor([S])])
     lvl_arcs = torch.maximum(in_ptr[lvl_end] - in_ptr[level_ptr], out_ptr[lvl_end] - out_ptr[level_ptr])
     width_arcs = torch.zeros(B, dtype=torch.int64, device=dev).scatter_reduce(0, slot_lat, lvl_arcs, reduce="amax")
-    block_class = torch.clamp(torch.ceil(torch.log2(torch.clamp(width_arcs.to(torch.float64) / 4.0, min=32.0))), 5, 8).to(torch.int64)
-    target_state = (4 * (1 << block_class) - CHUNK_SLACK)[lt_s]
-    fwd_chunk_off, fwd_chunks = _build_chunks(in_ptr, slot, lvl_first_state, lt_s, target_state, B, False)
-    bwd_chunk_off, bwd_chunks = _build_chunks(out_ptr, slot, lvl_first_state, lt_s, target_state, B, True)
+    bmax = int(math.log2(BLOCK_MAX))
+    block_class = torch.clamp(torch.ceil(torch.log2(torch.clamp(
+        width_arcs.to(torch.float64) / ARCS_PER_THREAD, min=32.0))), 5, bmax).to(torch.int64)
+    geo = torch.tensor([chunk_geometry(1 << k) if k >= 5 else (0, 0, 0) for k in range(bmax + 1)], device=dev)
+    target_state, heavy_state = geo[block_class, 0][lt_s], geo[block_class, 1][lt_s]
+    fwd_chunk_off, fwd_chunks = _build_chunks(in_ptr, slot, lvl_first_state, lt_s, target_state, heavy_state, B, False)
+    bwd_chunk_off, bwd_chunks = _build_chunks(out_ptr, slot, lvl_first_state, lt_s, target_state, heavy_state, B, True)
     # how far back (in packed state ids) an arc reaches: sizes the shared-memory window
     arc_lat = torch.repeat_interleave(torch.arange(B, device=dev), (arc_off[1:] - arc_off[:-1]))
     # (99% quantile over the lattice's arcs, rounded up to a power of two, from a log2
@@ -429,6 +446,7 @@ def pack_arcs(
         "states": S_b.cpu(),
         "levels": n_levels.cpu(),
         "block_class": block_class.cpu(),
+        "chunk_cap": geo[block_class, 2].cpu(),
         "reach": reach.cpu(),
     }
     groups = build_groups(stats, dev)

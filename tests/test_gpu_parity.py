@@ -204,7 +204,7 @@ def test_random_dag_tiny_window_and_heavy_states(tiny_window):
     p, sc, _ = check_fwd_bwd(ab)
     deg_in = (p.in_ptr[1:] - p.in_ptr[:-1]).max().item()
     deg_out = (p.out_ptr[1:] - p.out_ptr[:-1]).max().item()
-    assert deg_in > 8 * 256 and deg_out > 8 * 256
+    assert deg_in > p.groups[0].chunk_cap and deg_out > p.groups[0].chunk_cap
     score, off, arcs, labels = nb.lattice_viterbi(p, arc_scores=sc)
     o_score, o_paths, _ = c_oracle.viterbi(oracle_batch(ab))
     assert np.array_equal(score.cpu().numpy().view(np.uint32), o_score.view(np.uint32))
@@ -359,7 +359,7 @@ def test_c_abi_error_codes():
     ab = synth.transliteration_batch(2, seed=0)
     p, sc = ab.to(DEV).pack()
     lc = _lib.LaunchC()
-    lc.lattice_ids = None; lc.n_ids = 2; lc.block_threads = 48; lc.window_states = 64; lc.state_f64 = 0
+    lc.lattice_ids = None; lc.n_ids = 2; lc.block_threads = 48; lc.window_states = 64; lc.state_f64 = 0; lc.chunk_cap = 512
     s = _lib.ScoresC(); s.arc_scores = sc.data_ptr(); s.theta = None
     alpha = torch.empty(p.n_states, device=DEV); logz = torch.empty(2, device=DEV)
     rc = lib.nfst_fwd_f32(p.c_struct(), lc, s, alpha.data_ptr(), logz.data_ptr(), None)

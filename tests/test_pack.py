@@ -76,10 +76,10 @@ def check_structure(p):
     # launch groups partition the batch
     ids = np.concatenate([_np(g.ids) for g in p.groups])
     assert sorted(ids.tolist()) == list(range(p.n_lattices))
-    block = np.zeros(p.n_lattices, dtype=np.int64)
+    capb = np.zeros(p.n_lattices, dtype=np.int64)
     for g in p.groups:
-        block[_np(g.ids)] = g.block_threads
-        assert g.block_threads in (32, 64, 128, 256)
+        capb[_np(g.ids)] = g.chunk_cap
+        assert g.block_threads in (32, 64, 128, 256) and g.chunk_cap % 8 == 0
     # chunks: each direction tiles the states of a lattice exactly once, level by level
     for off, chunks, ptr, desc in ((p.fwd_chunk_off, p.fwd_chunks, in_ptr, False),
                                    (p.bwd_chunk_off, p.bwd_chunks, out_ptr, True)):
@@ -94,9 +94,9 @@ def check_structure(p):
             np.testing.assert_array_equal(ck[:, 0], ptr[ck[:, 2]])
             np.testing.assert_array_equal(ck[:, 1], ptr[ck[:, 3]])
             assert np.all(level[ck[:, 2]] == level[ck[:, 3] - 1])  # never crosses a level
-            cap = 8 * block[b]
-            big = (ck[:, 1] - ck[:, 0]) > cap
-            assert np.all((ck[big, 3] - ck[big, 2]) == 1)  # only a single heavy state may exceed the tile
+            big = (ck[:, 1] - ck[:, 0]) > capb[b]
+            assert np.all((ck[big, 3] - ck[big, 2]) == 1)  # only a single heavy state may exceed a stage
+            assert np.all((ck[:, 3] - ck[:, 2]) <= capb[b])  # states of a chunk fit the row-pointer stage
 
 
 @pytest.mark.parametrize("seed", [0, 1, 2])
