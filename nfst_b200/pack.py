@@ -34,8 +34,8 @@ from . import _lib
 WINDOW_BYTES_MAX = 64 * 1024
 # chunk geometry (tunable): a chunk targets ARCS_PER_THREAD arcs per thread of a block of at
 # most BLOCK_MAX threads; a state with more than target/HEAVY_DIV arcs gets a chunk of its own
-BLOCK_MAX = int(os.environ.get("NFST_BLOCK_MAX", "128"))
-ARCS_PER_THREAD = int(os.environ.get("NFST_ARCS_PER_THREAD", "12"))
+BLOCK_MAX = int(os.environ.get("NFST_BLOCK_MAX", "256"))
+ARCS_PER_THREAD = int(os.environ.get("NFST_ARCS_PER_THREAD", "4"))
 HEAVY_DIV = 4
 
 

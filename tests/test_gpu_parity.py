@@ -388,3 +388,46 @@ def test_empty_and_ragged_batches():
     assert abs(float(logz[1]) - np.log(n_paths)) < 1e-5
     score, off, arcs, labels = nb.lattice_viterbi(p, theta=theta)
     assert off.tolist()[1] == 0 and off.tolist()[3] - off.tolist()[2] == 2
+
+
+# --------------------------------------------------------------------------------------
+# drop-in surface of the reference module (set_masks / set_k / compute_beta)
+# --------------------------------------------------------------------------------------
+def test_scorer_mirror_and_monkeypatch_against_reference_golden():
+    from types import SimpleNamespace
+
+    from nfst_b200.scorer import LatticeBetaScorer, label_scores, patch_compute_beta
+
+    g = np.load(os.path.join(G, "beta_parallel.npz"))
+    theta = torch.from_numpy(g["theta0"]).float().to(DEV)
+    tr = torch.from_numpy(g["tr_0"]).to(DEV)
+    ref = g["beta_0"]
+    n_states = g["n_states_0"]
+    sc = LatticeBetaScorer(theta)
+    with pytest.raises(AssertionError):
+        sc.set_masks(tr[0] != 0, tr[0])  # tables must be 3-D (scorers.py:878-879)
+    sc.set_masks(tr != 0, tr)
+    sc.set_k(int(g["k"]))
+    beta = sc.compute_beta().cpu().numpy()
+    assert beta.shape == ref.shape
+    for b in range(tr.shape[0]):
+        nb_ = int(n_states[b])
+        np.testing.assert_allclose(beta[2 * b, :nb_], ref[2 * b, :nb_], rtol=2e-5)
+    # monkeypatch onto an object with the reference module's attribute names
+    H, V = 8, tr.shape[2]
+    gen = torch.Generator().manual_seed(0)
+    mod = SimpleNamespace(
+        embeddings=SimpleNamespace(weight=torch.randn(V, H, generator=gen).to(DEV)),
+        Wx=torch.randn(H, H, generator=gen).to(DEV), Wh=torch.zeros(H, H, device=DEV),
+        W=torch.randn(1, H, generator=gen).to(DEV), beta_bias=torch.zeros(H, device=DEV),
+        emission=(tr != 0), transition=tr, k=3)
+    patch_compute_beta(mod)
+    out = mod.compute_beta()
+    assert out.shape == (tr.shape[0] * 3, tr.shape[1])
+    th = label_scores(mod.embeddings.weight, mod.Wx, mod.W, mod.beta_bias)
+    src, lab, dst, _ = lo.arcs_from_dense(g["tr_0"][0][: int(n_states[0])])
+    be = lo.beta_log(int(n_states[0]), src, dst, th.cpu().double().numpy()[lab])
+    np.testing.assert_allclose(out[0, : int(n_states[0])].cpu().numpy(), np.exp(be), rtol=2e-5)
+    mod.Wh = torch.ones(H, H, device=DEV)
+    with pytest.raises(NotImplementedError):
+        patch_compute_beta(mod)
