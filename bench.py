@@ -161,6 +161,22 @@ def measured_peak_gbs():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def profiled_traffic(kernel: str, arcs_per_gpu: int):
+    """DRAM bytes per launch of `kernel` from the newest committed `ncu --set full` capture
+    (profiles/r*_traffic.json), if it was taken on this very workload; else None."""
+    import glob
+
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_traffic.json")), reverse=True):
+        try:
+            with open(path) as f:
+                d = json.load(f)
+            if int(d.get("workload_arcs_per_gpu", -1)) == int(arcs_per_gpu):
+                return float(d["kernels"][kernel]["dram_bytes"]), os.path.basename(path)
+        except Exception:
+            continue
+    return None, None
+
+
 def cpu_baseline(a, seconds: float, threads: int = 0):
     """Time the C oracle (port of the reference recurrence, all host threads) on a bounded
     sample of the workload: as many lattices as fit in ~`seconds`."""
@@ -366,6 +382,7 @@ def main():
     bwd_bytes = 12 * A + 12 * S
     fwd_bytes = 8 * A + 8 * S
     achieved = bwd_bytes / (bwd_ms * 1e-3) / 1e9
+    traffic, traffic_src = profiled_traffic("nfst_bwd_kernel", A)
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
@@ -377,7 +394,7 @@ def main():
         "gpu_launches": launches,
         "clocks": clk,
         "roofline": {"bound": "hbm", "kernel": "nfst_bwd_kernel (fused beta + posteriors)", "achieved": achieved,
-                     "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                     "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
                      "algorithmic_bytes_per_launch": bwd_bytes, "kernel_ms": bwd_ms,
                      "fwd_kernel": {"achieved": fwd_bytes / (fwd_ms * 1e-3) / 1e9, "kernel_ms": fwd_ms,
                                     "algorithmic_bytes_per_launch": fwd_bytes},
