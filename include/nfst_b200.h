@@ -114,7 +114,7 @@ typedef struct nfst_packed_lattices {
 typedef struct nfst_launch {
   const int32_t* lattice_ids;
   int32_t n_ids;
-  int32_t block_threads; /* 32, 64, 128 or 256 */
+  int32_t block_threads; /* consumer threads: 32, 64, 128 or 256 (one producer warp is added) */
   int32_t window_states;
   int32_t state_f64;
   int32_t chunk_cap; /* multiple of 8; >= the largest staged chunk of the launch, in arcs and in states */

@@ -157,26 +157,29 @@ __device__ __forceinline__ float lg2_approx(float x) {
   return y;
 }
 
-// one step of the online logsumexp: (m, s) <- (m, s) (+) v ; exactly one exp per element
+// Online logsumexp with a FINITE floor for the running max (kFloor instead of -inf), so the
+// update is branch-free and NaN-free: v = -inf gives d = -inf, e = 0; the first finite v
+// gives d ~ +1e30, e = 0, (m, s) = (v, 1).  Exactly one exp per element.
+constexpr float kFloor = -1.0e30f;
 template <typename ST>
-__device__ __forceinline__ void lse_push(ST& m, float& s, ST v, ST neg_inf) {
-  if (v > neg_inf) {
-    const float d = static_cast<float>(v - m);                 // m == -inf: d = +inf, e = 0
-    const float e = ex2_approx(-fabsf(d) * kLog2e);
-    if (d > 0.0f) { s = fmaf(s, e, 1.0f); m = v; } else { s += e; }
-  }
+__device__ __forceinline__ void lse_push(ST& m, float& s, ST v, ST) {
+  const float d = static_cast<float>(v - m);
+  const float e = ex2_approx(-fabsf(d) * kLog2e);
+  const bool up = d > 0.0f;
+  s = up ? fmaf(s, e, 1.0f) : s + e;
+  m = up ? v : m;
 }
 template <typename ST>
-__device__ __forceinline__ void lse_join(ST& m, float& s, ST m2, float s2, ST neg_inf) {
-  if (m2 > neg_inf) {
-    const float d = static_cast<float>(m2 - m);
-    const float e = ex2_approx(-fabsf(d) * kLog2e);
-    if (d > 0.0f) { s = fmaf(s, e, s2); m = m2; } else { s = fmaf(s2, e, s); }
-  }
+__device__ __forceinline__ void lse_join(ST& m, float& s, ST m2, float s2, ST) {
+  const float d = static_cast<float>(m2 - m);
+  const float e = ex2_approx(-fabsf(d) * kLog2e);
+  const bool up = d > 0.0f;
+  s = up ? fmaf(s, e, s2) : fmaf(s2, e, s);
+  m = up ? m2 : m;
 }
 template <typename ST>
 __device__ __forceinline__ ST lse_finish(ST m, float s, ST neg_inf) {
-  return (m > neg_inf) ? m + static_cast<ST>(lg2_approx(s) * kLn2) : neg_inf;
+  return (m > static_cast<ST>(kFloor)) ? m + static_cast<ST>(lg2_approx(s) * kLn2) : neg_inf;
 }
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
@@ -202,7 +205,8 @@ extern __shared__ __align__(16) float smem_f[];
 template <bool AUX, bool LAB>
 __device__ __forceinline__ void stage_chunk(const int4& k, int cap, int st, const SmemPlan& plan,
                                             const int32_t* __restrict__ nbr, const void* __restrict__ aux,
-                                            const int32_t* __restrict__ lab, const int32_t* __restrict__ ptr) {
+                                            const int32_t* __restrict__ lab, const int32_t* __restrict__ ptr, int t,
+                                            int nt) {
   if (k.w > k.z && k.y - k.x <= cap) {
     const int base4 = k.x & ~3;
     const int n4 = (k.y - base4 + 3) >> 2;
@@ -210,40 +214,50 @@ __device__ __forceinline__ void stage_chunk(const int4& k, int cap, int st, cons
     float* s_aux = smem_f + st + plan.aux / 4;
     float* s_lab = smem_f + st + plan.lab / 4;
     float* s_ptr = smem_f + st + plan.ptr / 4;
-    for (int i = threadIdx.x; i < n4; i += blockDim.x) {
+    for (int i = t; i < n4; i += nt) {
       cp_async16(s_nbr + 4 * i, nbr + base4 + 4 * i);
       if (AUX) cp_async16(s_aux + 4 * i, static_cast<const int32_t*>(aux) + base4 + 4 * i);
       if (LAB) cp_async16(s_lab + 4 * i, lab + base4 + 4 * i);
     }
     const int pb = k.z & ~3;
     const int p4 = (k.w + 1 - pb + 3) >> 2;
-    for (int i = threadIdx.x; i < p4; i += blockDim.x) cp_async16(s_ptr + 4 * i, ptr + pb + 4 * i);
+    for (int i = t; i < p4; i += nt) cp_async16(s_ptr + 4 * i, ptr + pb + 4 * i);
   }
 }
 
 // Gather the scores of a staged chunk through its staged index array, straight into shared
 // memory (4-byte cp.async, no registers): scores[idx[pos]] -> wsc[pos] for every staged slot.
 __device__ __forceinline__ void gather_scores(const int4& k, int cap, int st, const SmemPlan& plan,
-                                              const float* __restrict__ scores) {
+                                              const float* __restrict__ scores, int t, int nt) {
   if (k.w > k.z && k.y - k.x <= cap) {
     const int n_slots = ((k.y - (k.x & ~3) + 3) >> 2) << 2;
     const int* s_idx = reinterpret_cast<const int*>(smem_f + st + plan.aux / 4);
     float* s_w = smem_f + st + plan.wsc / 4;
     // in place: each slot's index is read (LDS) before the copy that overwrites it is issued
-    for (int i = threadIdx.x; i < n_slots; i += blockDim.x) cp_async4(s_w + i, scores + s_idx[i]);
+    for (int i = t; i < n_slots; i += nt) cp_async4(s_w + i, scores + s_idx[i]);
   }
 }
+
+// rare path: a neighbour older than the shared-memory window (kept out of line so that the
+// hot loops carry no 64-bit address arithmetic)
+template <typename T>
+__device__ __noinline__ T load_behind_window(const T* p, int i) { return p[i]; }
 
 // =====================================================================================
 // forward: alpha
 // =====================================================================================
-// SC: per-arc scores given; TH: theta[label] given (at least one of them).
+// Block = `block_threads` consumer threads + ONE producer warp.  The producer warp issues
+// every cp.async of the pipeline (arc arrays two chunks ahead, score gather one chunk ahead);
+// the consumer warps only reduce.  SC: per-arc scores given; TH: theta[label] given (at least one of them).
 template <typename ST, bool SC, bool TH>
-__global__ void __launch_bounds__(256, 3)
+__global__ void __launch_bounds__(288, 3)
     nfst_fwd_kernel(const nfst_packed_lattices_t L, const int32_t* __restrict__ ids, int W, int cap,
                     const float* __restrict__ arc_scores, const float* __restrict__ theta, int theta_smem, ST* alpha,
                     ST* __restrict__ logz) {
   const int NT = blockDim.x, tid = threadIdx.x;
+  const int NTc = NT - 32;            // consumer threads; the last warp is the producer
+  const bool producer = tid >= NTc;
+  const int ptid = tid - NTc;
   const SmemPlan plan = smem_plan(W, cap, sizeof(ST), L.vocab, true, false, SC, TH, theta_smem != 0, false, 3, true);
   ST* const win = reinterpret_cast<ST*>(smem_f + plan.win / 4);
   const ST neg_inf = static_cast<ST>(kNegInf);
@@ -273,12 +287,12 @@ __global__ void __launch_bounds__(256, 3)
   //   chunk c+2 :                                            its arc arrays stream in now (16 B copies)
   int4 k0 = chunk_at(chunks, c, c_end), k1 = chunk_at(chunks, c + 1, c_end), k2 = chunk_at(chunks, c + 2, c_end);
   int s_cur = stage0, s_nxt = stage0 + stage_words, s_nn = stage0 + 2 * stage_words;
-  stage_chunk<SC, TH>(k0, cap, s_cur, plan, L.src_in, L.in2out, L.label_in, L.in_ptr);
-  stage_chunk<SC, TH>(k1, cap, s_nxt, plan, L.src_in, L.in2out, L.label_in, L.in_ptr);
+  stage_chunk<SC, TH>(k0, cap, s_cur, plan, L.src_in, L.in2out, L.label_in, L.in_ptr, tid, NT);
+  stage_chunk<SC, TH>(k1, cap, s_nxt, plan, L.src_in, L.in2out, L.label_in, L.in_ptr, tid, NT);
   cp_async_commit();
   cp_async_wait_all();
   __syncthreads();
-  if (SC) gather_scores(k0, cap, s_cur, plan, arc_scores);
+  if (SC) gather_scores(k0, cap, s_cur, plan, arc_scores, tid, NT);
   cp_async_commit();
   cp_async_wait_all();
   __syncthreads();
@@ -286,9 +300,11 @@ __global__ void __launch_bounds__(256, 3)
 #pragma unroll 1
   for (; c < c_end; ++c) {
     const int4 k3 = chunk_at(chunks, c + 3, c_end);  // descriptors run ahead of their use
-    stage_chunk<SC, TH>(k2, cap, s_nn, plan, L.src_in, L.in2out, L.label_in, L.in_ptr);
-    if (SC) gather_scores(k1, cap, s_nxt, plan, arc_scores);
-    cp_async_commit();
+    if (producer) {
+      stage_chunk<SC, TH>(k2, cap, s_nn, plan, L.src_in, L.in2out, L.label_in, L.in_ptr, ptid, 32);
+      if (SC) gather_scores(k1, cap, s_nxt, plan, arc_scores, ptid, 32);
+      cp_async_commit();
+    }
     const int* s_src = reinterpret_cast<const int*>(smem_f + s_cur + o_nbr);
     const float* s_w = smem_f + s_cur + o_wsc;
     const int* s_lab = reinterpret_cast<const int*>(smem_f + s_cur + o_lab);
@@ -303,7 +319,7 @@ __global__ void __launch_bounds__(256, 3)
     const int lo = whole ? static_cast<int>(0x80000000) : s1 - W;
     auto value_of = [&](int src) -> ST {
       if (src >= lo) return win[(src - base_s) & wmask];
-      return alpha[src];
+      return load_behind_window(alpha, src);
     };
     auto arc_value = [&](int i) -> ST {
       float w = SC ? s_w[i] : 0.0f;
@@ -311,13 +327,15 @@ __global__ void __launch_bounds__(256, 3)
       return value_of(s_src[i]) + static_cast<ST>(w);
     };
     if (n <= cap) {
-      if (ns * 2 > NT) {
+      if (producer) {
+        // nothing to reduce: the producer warp goes straight to the completion wait
+      } else if (ns * 2 > NTc) {
         // ---- wide chunk: one thread per state, arcs straight from the staged arrays
 #pragma unroll 1
-        for (int j = tid; j < ns; j += NT) {
+        for (int j = tid; j < ns; j += NTc) {
           int i = s_ptr[j] - base4;
           const int b1 = s_ptr[j + 1] - base4;
-          ST m = neg_inf;
+          ST m = static_cast<ST>(kFloor);
           float sum = 0.0f;
 #pragma unroll 1
           for (; i + 3 < b1; i += 4) {  // 4 arcs per trip: independent loads first
@@ -337,14 +355,14 @@ __global__ void __launch_bounds__(256, 3)
       } else {
         // ---- narrow chunk: 2^lg lanes per state so that the block stays busy
         int lg = 1;
-        while (lg < 5 && (ns << (lg + 1)) <= NT) ++lg;
-        const int G = 1 << lg, lane_g = tid & (G - 1), ngrp = NT >> lg;
+        while (lg < 5 && (ns << (lg + 1)) <= NTc) ++lg;
+        const int G = 1 << lg, lane_g = tid & (G - 1), ngrp = NTc >> lg;
 #pragma unroll 1
         for (int jb = 0; jb < ns; jb += ngrp) {
           const int j = jb + (tid >> lg);
           const bool valid = j < ns;
           const int b0 = valid ? s_ptr[j] - base4 : 0, b1 = valid ? s_ptr[j + 1] - base4 : 0;
-          ST m = neg_inf;
+          ST m = static_cast<ST>(kFloor);
           float sum = 0.0f;
 #pragma unroll 1
           for (int i = b0 + lane_g; i < b1; i += G) lse_push(m, sum, arc_value(i), neg_inf);
@@ -402,7 +420,7 @@ __global__ void __launch_bounds__(256, 3)
 // =====================================================================================
 // LOGS / TROP: semirings; SC / TH: score sources; POST: posteriors (post and/or dtheta).
 template <typename ST, bool LOGS, bool TROP, bool SC, bool TH, bool POST>
-__global__ void __launch_bounds__(256, 3)
+__global__ void __launch_bounds__(288, 3)
     nfst_bwd_kernel(const nfst_packed_lattices_t L, const int32_t* __restrict__ ids, int W, int cap,
                     const float* __restrict__ arc_scores, const float* __restrict__ theta, int theta_smem,
                     int dtheta_smem, const ST* __restrict__ alpha, const ST* __restrict__ logz,
@@ -410,6 +428,9 @@ __global__ void __launch_bounds__(256, 3)
                     float* __restrict__ dtheta, float* delta, int32_t* __restrict__ backptr,
                     float* __restrict__ vit_score) {
   const int NT = blockDim.x, tid = threadIdx.x;
+  const int NTc = NT - 32;  // consumer threads; the last warp is the producer
+  const bool producer = tid >= NTc;
+  const int ptid = tid - NTc;
   const bool want_hist = POST && dtheta != nullptr;
   const bool need_label = TH || want_hist;
   const SmemPlan plan =
@@ -454,11 +475,11 @@ __global__ void __launch_bounds__(256, 3)
 
   int4 k0 = chunk_at(chunks, c, c_end), k1 = chunk_at(chunks, c + 1, c_end);
   int s_cur = stage0, s_nxt = stage0 + stage_words;
-  auto stage_in = [&](const int4& k, int st) {
-    if (need_label) stage_chunk<SC, true>(k, cap, st, plan, L.dst_out, arc_scores, lab_arr, L.out_ptr);
-    else stage_chunk<SC, false>(k, cap, st, plan, L.dst_out, arc_scores, lab_arr, L.out_ptr);
+  auto stage_in = [&](const int4& k, int st, int t, int nt) {
+    if (need_label) stage_chunk<SC, true>(k, cap, st, plan, L.dst_out, arc_scores, lab_arr, L.out_ptr, t, nt);
+    else stage_chunk<SC, false>(k, cap, st, plan, L.dst_out, arc_scores, lab_arr, L.out_ptr, t, nt);
   };
-  stage_in(k0, s_cur);
+  stage_in(k0, s_cur, tid, NT);
   cp_async_commit();
   cp_async_wait_all();
   __syncthreads();
@@ -466,8 +487,10 @@ __global__ void __launch_bounds__(256, 3)
 #pragma unroll 1
   for (; c < c_end; ++c) {
     const int4 k2 = chunk_at(chunks, c + 2, c_end);
-    stage_in(k1, s_nxt);
-    cp_async_commit();
+    if (producer) {
+      stage_in(k1, s_nxt, ptid, 32);
+      cp_async_commit();
+    }
     const int* s_dst = reinterpret_cast<const int*>(smem_f + s_cur + o_nbr);
     const float* s_w = smem_f + s_cur + o_aux;
     const int* s_lab = reinterpret_cast<const int*>(smem_f + s_cur + o_lab);
@@ -480,11 +503,11 @@ __global__ void __launch_bounds__(256, 3)
     const int hi = whole ? 0x7fffffff : s0 + W;
     auto beta_of = [&](int d) -> ST {
       if (d < hi) return win[(d - base_s) & wmask];
-      return beta[d];
+      return load_behind_window(beta, d);
     };
     auto delta_of = [&](int d) -> float {
       if (d < hi) return dwin[(d - base_s) & wmask];
-      return delta[d];
+      return load_behind_window(delta, d);
     };
     // one arc of the staged chunk: log-semiring push (+ posterior) and/or tropical candidate
     auto visit = [&](int i, ST am, ST& m, float& sum, float& bt, int& bi) {
@@ -522,14 +545,16 @@ __global__ void __launch_bounds__(256, 3)
       }
     };
     if (n <= cap) {
-      if (ns * 2 > NT) {
+      if (producer) {
+        // the producer warp only moves data
+      } else if (ns * 2 > NTc) {
 #pragma unroll 1
-        for (int j = tid; j < ns; j += NT) {
+        for (int j = tid; j < ns; j += NTc) {
           const int b0 = s_ptr[j] - base4, b1 = s_ptr[j + 1] - base4;
           const int s = s0 + j;
           ST am = 0;
           if (POST) am = alpha[s] - lz;  // issued before the arc loop, consumed inside it
-          ST m = neg_inf;
+          ST m = static_cast<ST>(kFloor);
           float sum = 0.0f, bt = kNegInf;
           int bi = 0x7fffffff;
 #pragma unroll 2
@@ -538,8 +563,8 @@ __global__ void __launch_bounds__(256, 3)
         }
       } else {
         int lg = 1;
-        while (lg < 5 && (ns << (lg + 1)) <= NT) ++lg;
-        const int G = 1 << lg, lane_g = tid & (G - 1), ngrp = NT >> lg;
+        while (lg < 5 && (ns << (lg + 1)) <= NTc) ++lg;
+        const int G = 1 << lg, lane_g = tid & (G - 1), ngrp = NTc >> lg;
 #pragma unroll 1
         for (int jb = 0; jb < ns; jb += ngrp) {
           const int j = jb + (tid >> lg);
@@ -548,7 +573,7 @@ __global__ void __launch_bounds__(256, 3)
           const int s = s0 + j;
           ST am = 0;
           if (POST && valid) am = alpha[s] - lz;
-          ST m = neg_inf;
+          ST m = static_cast<ST>(kFloor);
           float sum = 0.0f, bt = kNegInf;
           int bi = 0x7fffffff;
 #pragma unroll 1
@@ -767,7 +792,7 @@ int launch_fwd2(const nfst_packed_lattices_t* lat, const nfst_launch_t* launch, 
   const int theta_smem = TH && lat->vocab <= NFST_THETA_SMEM_MAX;
   const size_t bytes = nfst_launch_smem_bytes(launch, lat->vocab, 0, 1, 0, 0, SC, TH, 0);
   if (int rc = prepare_smem(nfst_fwd_kernel<ST, SC, TH>, bytes)) return rc;
-  nfst_fwd_kernel<ST, SC, TH><<<launch->n_ids, launch->block_threads, bytes, st>>>(
+  nfst_fwd_kernel<ST, SC, TH><<<launch->n_ids, launch->block_threads + 32, bytes, st>>>(
       *lat, launch->lattice_ids, launch->window_states, launch->chunk_cap, scores->arc_scores, scores->theta,
       theta_smem, static_cast<ST*>(alpha), static_cast<ST*>(logz));
   NFST_CUDA_OK(cudaGetLastError());
@@ -792,7 +817,7 @@ int launch_bwd3(const nfst_packed_lattices_t* lat, const nfst_launch_t* launch, 
   const int dtheta_smem = POST && dtheta && small_v;
   const size_t bytes = nfst_launch_smem_bytes(launch, lat->vocab, 1, LOGS, TROP, POST, SC, TH, POST && dtheta != nullptr);
   if (int rc = prepare_smem(nfst_bwd_kernel<ST, LOGS, TROP, SC, TH, POST>, bytes)) return rc;
-  nfst_bwd_kernel<ST, LOGS, TROP, SC, TH, POST><<<launch->n_ids, launch->block_threads, bytes, st>>>(
+  nfst_bwd_kernel<ST, LOGS, TROP, SC, TH, POST><<<launch->n_ids, launch->block_threads + 32, bytes, st>>>(
       *lat, launch->lattice_ids, launch->window_states, launch->chunk_cap, scores->arc_scores, scores->theta,
       theta_smem, dtheta_smem,
       static_cast<const ST*>(alpha), static_cast<const ST*>(logz), grad_logz, static_cast<ST*>(beta),

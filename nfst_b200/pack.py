@@ -37,6 +37,7 @@ WINDOW_BYTES_MAX = 64 * 1024
 BLOCK_MAX = int(os.environ.get("NFST_BLOCK_MAX", "256"))
 ARCS_PER_THREAD = int(os.environ.get("NFST_ARCS_PER_THREAD", "4"))
 HEAVY_DIV = 4
+DEGREE_SORT = int(os.environ.get("NFST_DEGREE_SORT", "1"))
 
 
 def chunk_geometry(block_threads: int):
@@ -371,7 +372,7 @@ def pack_arcs(
     deg_in = torch.bincount(gdst[live], minlength=S0)[kept]
     deg_out = torch.bincount(gsrc[live], minlength=S0)[kept]
     dmax = int(max(deg_in.max(), deg_out.max())) + 1 if kept.numel() else 1
-    if lmax * dmax * dmax < 2**62 // max(B, 1):
+    if DEGREE_SORT and lmax * dmax * dmax < 2**62 // max(B, 1):
         order = torch.argsort(((lt * lmax + lv) * dmax + deg_in) * dmax + deg_out, stable=True)
     else:  # pathological degrees: fall back to level order only
         order = torch.argsort(lt * lmax + lv, stable=True)
