@@ -169,6 +169,19 @@ __device__ __forceinline__ void lse_push(ST& m, float& s, ST v, ST) {
   s = up ? fmaf(s, e, 1.0f) : s + e;
   m = up ? v : m;
 }
+// Four values at once: one max tree, then five INDEPENDENT exps (4 terms + the rescale of the
+// running sum) instead of a 4-long dependent chain through (m, s).
+template <typename ST>
+__device__ __forceinline__ void lse_push4(ST& m, float& s, ST v0, ST v1, ST v2, ST v3) {
+  const ST mx = max(max(max(v0, v1), max(v2, v3)), m);
+  const float r = ex2_approx(static_cast<float>(m - mx) * kLog2e);
+  const float e0 = ex2_approx(static_cast<float>(v0 - mx) * kLog2e);
+  const float e1 = ex2_approx(static_cast<float>(v1 - mx) * kLog2e);
+  const float e2 = ex2_approx(static_cast<float>(v2 - mx) * kLog2e);
+  const float e3 = ex2_approx(static_cast<float>(v3 - mx) * kLog2e);
+  s = fmaf(s, r, (e0 + e1) + (e2 + e3));
+  m = mx;
+}
 template <typename ST>
 __device__ __forceinline__ void lse_join(ST& m, float& s, ST m2, float s2, ST) {
   const float d = static_cast<float>(m2 - m);
@@ -340,10 +353,7 @@ __global__ void __launch_bounds__(288, 3)
 #pragma unroll 1
           for (; i + 3 < b1; i += 4) {  // 4 arcs per trip: independent loads first
             const ST v0 = arc_value(i), v1 = arc_value(i + 1), v2 = arc_value(i + 2), v3 = arc_value(i + 3);
-            lse_push(m, sum, v0, neg_inf);
-            lse_push(m, sum, v1, neg_inf);
-            lse_push(m, sum, v2, neg_inf);
-            lse_push(m, sum, v3, neg_inf);
+            lse_push4(m, sum, v0, v1, v2, v3);
           }
 #pragma unroll 1
           for (; i < b1; ++i) lse_push(m, sum, arc_value(i), neg_inf);
@@ -530,6 +540,34 @@ __global__ void __launch_bounds__(288, 3)
         if (t > bt) { bt = t; bi = i; }  // strict: within a lane arcs come in label order
       }
     };
+    // four consecutive arcs of one state: independent loads and exps (see lse_push4)
+    auto visit4 = [&](int i, ST am, ST& m, float& sum, float& bt, int& bi) {
+      ST u[4];
+      int lab[4] = {0, 0, 0, 0};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int d = s_dst[i + k];
+        float w = SC ? s_w[i + k] : 0.0f;
+        if (TH || POST) { if (need_label) lab[k] = s_lab[i + k]; }
+        if (TH) w += th[lab[k]];
+        if (LOGS) u[k] = static_cast<ST>(w) + beta_of(d);
+        if (TROP) {
+          const float t = __fadd_rn(w, delta_of(d));
+          if (t > bt) { bt = t; bi = i + k; }
+        }
+      }
+      if (LOGS) {
+        lse_push4(m, sum, u[0], u[1], u[2], u[3]);
+        if (POST) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const float p = ex2_approx(static_cast<float>(am + u[k]) * kLog2e) * gscale;
+            if (post) post[base4 + i + k] = p;
+            if (hist) atomicAdd(&hist[lab[k]], p);
+          }
+        }
+      }
+    };
     auto finish = [&](int s, bool sink, ST m, float sum, float bt, int bi) {
       // sinks: beta = 1 (scorers.py:720), delta = 0
       if (LOGS) {
@@ -557,8 +595,11 @@ __global__ void __launch_bounds__(288, 3)
           ST m = static_cast<ST>(kFloor);
           float sum = 0.0f, bt = kNegInf;
           int bi = 0x7fffffff;
-#pragma unroll 2
-          for (int i = b0; i < b1; ++i) visit(i, am, m, sum, bt, bi);
+          int i = b0;
+#pragma unroll 1
+          for (; i + 3 < b1; i += 4) visit4(i, am, m, sum, bt, bi);
+#pragma unroll 1
+          for (; i < b1; ++i) visit(i, am, m, sum, bt, bi);
           finish(s, b0 == b1, m, sum, bt, bi);
         }
       } else {
