@@ -195,60 +195,106 @@ __device__ __forceinline__ ST lse_finish(ST m, float s, ST neg_inf) {
   return (m > static_cast<ST>(kFloor)) ? m + static_cast<ST>(lg2_approx(s) * kLn2) : neg_inf;
 }
 
-__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
-  const unsigned sa = static_cast<unsigned>(__cvta_generic_to_shared(smem));
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gmem));
-}
 __device__ __forceinline__ void cp_async4(void* smem, const void* gmem) {
   const unsigned sa = static_cast<unsigned>(__cvta_generic_to_shared(smem));
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(sa), "l"(gmem));
 }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
 
 // All dynamic shared memory is addressed as 32-bit words off one typed extern array (keeps
 // the accesses in the shared address space for the compiler: plain LDS/STS with immediate
 // offsets, no generic-pointer conversions in the loops).
 extern __shared__ __align__(16) float smem_f[];
 
-// Stage the arc arrays and row pointers of chunk k into the stage at word offset `st`
-// (16-byte cp.async copies, all threads).  Copies start at the 4-aligned position below the
-// chunk and may run a few elements past it; the arrays are zero-padded, so whatever is
-// over-read is a valid index.
+// ---- mbarrier / TMA bulk-copy primitives (sm_90+ PTX; SASS: SYNCS.*, UBLKCP) --------------
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return static_cast<unsigned>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// wait for the phase with the given parity; bounded spin, then trap (a hang would cost a GPU)
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  const unsigned addr = smem_u32(bar);
+  unsigned ok = 0;
+  for (int spins = 0; spins < (1 << 22); ++spins) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (ok) return;
+  }
+  __trap();
+}
+// one TMA bulk copy global -> shared (16-byte aligned, size a multiple of 16); completion is
+// credited to `bar` as transaction bytes
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+// arrive on `bar` once every cp.async this thread has issued so far has landed
+__device__ __forceinline__ void cpasync_mbar_arrive(unsigned long long* bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// Producer lane 0: stream the arc arrays and row pointers of chunk k into the stage at word
+// offset `st` with TMA bulk copies, completion on `bar`.  Copies start at the 4-aligned
+// position below the chunk and may run a few elements past it; the arrays are zero-padded, so
+// whatever is over-read is a valid index.  Oversize chunks are not staged (plain arrive).
 template <bool AUX, bool LAB>
-__device__ __forceinline__ void stage_chunk(const int4& k, int cap, int st, const SmemPlan& plan,
-                                            const int32_t* __restrict__ nbr, const void* __restrict__ aux,
-                                            const int32_t* __restrict__ lab, const int32_t* __restrict__ ptr, int t,
-                                            int nt) {
-  if (k.w > k.z && k.y - k.x <= cap) {
+__device__ __forceinline__ void stage_chunk_bulk(const int4& k, int cap, int st, const SmemPlan& plan,
+                                                 const int32_t* __restrict__ nbr, const void* __restrict__ aux,
+                                                 const int32_t* __restrict__ lab, const int32_t* __restrict__ ptr,
+                                                 unsigned long long* bar) {
+  if (k.y - k.x <= cap) {
     const int base4 = k.x & ~3;
-    const int n4 = (k.y - base4 + 3) >> 2;
-    float* s_nbr = smem_f + st + plan.nbr / 4;
-    float* s_aux = smem_f + st + plan.aux / 4;
-    float* s_lab = smem_f + st + plan.lab / 4;
-    float* s_ptr = smem_f + st + plan.ptr / 4;
-    for (int i = t; i < n4; i += nt) {
-      cp_async16(s_nbr + 4 * i, nbr + base4 + 4 * i);
-      if (AUX) cp_async16(s_aux + 4 * i, static_cast<const int32_t*>(aux) + base4 + 4 * i);
-      if (LAB) cp_async16(s_lab + 4 * i, lab + base4 + 4 * i);
-    }
+    const unsigned nb = static_cast<unsigned>((k.y - base4 + 3) >> 2) << 4;  // bytes per arc array
     const int pb = k.z & ~3;
-    const int p4 = (k.w + 1 - pb + 3) >> 2;
-    for (int i = t; i < p4; i += nt) cp_async16(s_ptr + 4 * i, ptr + pb + 4 * i);
+    const unsigned pbytes = static_cast<unsigned>((k.w + 1 - pb + 3) >> 2) << 4;
+    const unsigned total = nb * (1u + (AUX ? 1u : 0u) + (LAB ? 1u : 0u)) + pbytes;
+    fence_proxy_async();  // earlier generic-proxy reads of this stage are ordered before the refill
+    mbar_arrive_expect_tx(bar, total);
+    if (nb) {
+      bulk_g2s(smem_f + st + plan.nbr / 4, nbr + base4, nb, bar);
+      if (AUX) bulk_g2s(smem_f + st + plan.aux / 4, static_cast<const int32_t*>(aux) + base4, nb, bar);
+      if (LAB) bulk_g2s(smem_f + st + plan.lab / 4, lab + base4, nb, bar);
+    }
+    bulk_g2s(smem_f + st + plan.ptr / 4, ptr + pb, pbytes, bar);
+  } else {
+    mbar_arrive(bar);
   }
 }
 
-// Gather the scores of a staged chunk through its staged index array, straight into shared
-// memory (4-byte cp.async, no registers): scores[idx[pos]] -> wsc[pos] for every staged slot.
+// Producer warp: gather the scores of a staged chunk through its staged index array, straight
+// into shared memory and IN PLACE over the indices (4-byte cp.async, no registers):
+// scores[idx[pos]] -> slot pos.  Each lane then arrives on `bar` when its copies have landed.
 __device__ __forceinline__ void gather_scores(const int4& k, int cap, int st, const SmemPlan& plan,
-                                              const float* __restrict__ scores, int t, int nt) {
-  if (k.w > k.z && k.y - k.x <= cap) {
+                                              const float* __restrict__ scores, int lane, unsigned long long* bar) {
+  if (k.y - k.x <= cap) {
     const int n_slots = ((k.y - (k.x & ~3) + 3) >> 2) << 2;
     const int* s_idx = reinterpret_cast<const int*>(smem_f + st + plan.aux / 4);
     float* s_w = smem_f + st + plan.wsc / 4;
-    // in place: each slot's index is read (LDS) before the copy that overwrites it is issued
-    for (int i = t; i < n_slots; i += nt) cp_async4(s_w + i, scores + s_idx[i]);
+    int i = lane;
+    for (; i + 96 < n_slots; i += 128) {  // 4 independent index loads, then 4 copies
+      const int i0 = s_idx[i], i1 = s_idx[i + 32], i2 = s_idx[i + 64], i3 = s_idx[i + 96];
+      cp_async4(s_w + i, scores + i0);
+      cp_async4(s_w + i + 32, scores + i1);
+      cp_async4(s_w + i + 64, scores + i2);
+      cp_async4(s_w + i + 96, scores + i3);
+    }
+    for (; i < n_slots; i += 32) cp_async4(s_w + i, scores + s_idx[i]);
   }
+  cpasync_mbar_arrive(bar);
 }
 
 // rare path: a neighbour older than the shared-memory window (kept out of line so that the
@@ -271,7 +317,7 @@ __global__ void __launch_bounds__(288, 3)
   const int NTc = NT - 32;            // consumer threads; the last warp is the producer
   const bool producer = tid >= NTc;
   const int ptid = tid - NTc;
-  const SmemPlan plan = smem_plan(W, cap, sizeof(ST), L.vocab, true, false, SC, TH, theta_smem != 0, false, 3, true);
+  const SmemPlan plan = smem_plan(W, cap, sizeof(ST), L.vocab, true, false, SC, TH, theta_smem != 0, false, 4, true);
   ST* const win = reinterpret_cast<ST*>(smem_f + plan.win / 4);
   const ST neg_inf = static_cast<ST>(kNegInf);
   const int stage0 = static_cast<int>(plan.stage0 / 4), stage_words = static_cast<int>(plan.stage_bytes / 4);
@@ -290,33 +336,58 @@ __global__ void __launch_bounds__(288, 3)
     th = sth;
   }
 
-  const nfst_chunk_t* chunks = L.fwd_chunks;
-  int c = L.fwd_chunk_off[b];
-  const int c_end = L.fwd_chunk_off[b + 1];
+  const nfst_chunk_t* chunks = L.fwd_chunks + L.fwd_chunk_off[b];
+  const int n_chunks = L.fwd_chunk_off[b + 1] - L.fwd_chunk_off[b];
 
-  // Three-stage software pipeline, all through cp.async (no staging registers):
-  //   chunk c   : arc arrays + gathered scores resident  -> reduced now
-  //   chunk c+1 : arc arrays resident                     -> its scores are gathered now (4 B copies)
-  //   chunk c+2 :                                            its arc arrays stream in now (16 B copies)
-  int4 k0 = chunk_at(chunks, c, c_end), k1 = chunk_at(chunks, c + 1, c_end), k2 = chunk_at(chunks, c + 2, c_end);
-  int s_cur = stage0, s_nxt = stage0 + stage_words, s_nn = stage0 + 2 * stage_words;
-  stage_chunk<SC, TH>(k0, cap, s_cur, plan, L.src_in, L.in2out, L.label_in, L.in_ptr, tid, NT);
-  stage_chunk<SC, TH>(k1, cap, s_nxt, plan, L.src_in, L.in2out, L.label_in, L.in_ptr, tid, NT);
-  cp_async_commit();
-  cp_async_wait_all();
+  // ---- pipeline: a ring of kRing stages, one mbarrier pair per stage ----------------------
+  //   chunk i   : arc arrays + gathered scores resident  -> reduced by the consumer warps
+  //   chunk i+2 : arrays resident -> the producer warp gathers its scores now (4-byte LDGSTS)
+  //   chunk i+3 :                    its arc arrays stream in now (TMA bulk copies)
+  // Every wait is on an operation issued at least one iteration earlier; the only block-wide
+  // barrier is the one at the end of a chunk (results visible, stage free).
+  constexpr int kRing = 4, kLeadArr = 3, kLeadGat = 2;
+  __shared__ __align__(8) unsigned long long bar_arr[kRing], bar_w[kRing];
+  if (tid == 0) {
+    for (int i = 0; i < kRing; ++i) {
+      mbar_init(&bar_arr[i], 1);
+      mbar_init(&bar_w[i], 32);
+    }
+    mbar_fence_init();
+  }
   __syncthreads();
-  if (SC) gather_scores(k0, cap, s_cur, plan, arc_scores, tid, NT);
-  cp_async_commit();
-  cp_async_wait_all();
-  __syncthreads();
+  auto stage_of = [&](int i) { return stage0 + (i & (kRing - 1)) * stage_words; };
+  if (producer) {
+    for (int j = 0; j < kLeadArr && j < n_chunks; ++j)
+      if (ptid == 0)
+        stage_chunk_bulk<SC, TH>(chunk_at(chunks, j, n_chunks), cap, stage_of(j), plan, L.src_in, L.in2out, L.label_in,
+                                 L.in_ptr, &bar_arr[j & (kRing - 1)]);
+    if (SC)
+      for (int j = 0; j < kLeadGat && j < n_chunks; ++j) {
+        mbar_wait(&bar_arr[j & (kRing - 1)], 0);
+        gather_scores(chunk_at(chunks, j, n_chunks), cap, stage_of(j), plan, arc_scores, ptid, &bar_w[j & (kRing - 1)]);
+      }
+  }
+  // chunk descriptors: k0 = chunk i (consumers), kg = chunk i+2, ka = chunk i+3 (producer);
+  // each is loaded one iteration before its first use
+  int4 k0 = chunk_at(chunks, 0, n_chunks), k1 = chunk_at(chunks, 1, n_chunks), kg = chunk_at(chunks, kLeadGat, n_chunks),
+       ka = chunk_at(chunks, kLeadArr, n_chunks);
 
 #pragma unroll 1
-  for (; c < c_end; ++c) {
-    const int4 k3 = chunk_at(chunks, c + 3, c_end);  // descriptors run ahead of their use
+  for (int it = 0; it < n_chunks; ++it) {
+    const int4 k2n = chunk_at(chunks, it + 2, n_chunks);
+    const int4 kgn = chunk_at(chunks, it + 1 + kLeadGat, n_chunks), kan = chunk_at(chunks, it + 1 + kLeadArr, n_chunks);
+    const int s_cur = stage_of(it);
     if (producer) {
-      stage_chunk<SC, TH>(k2, cap, s_nn, plan, L.src_in, L.in2out, L.label_in, L.in_ptr, ptid, 32);
-      if (SC) gather_scores(k1, cap, s_nxt, plan, arc_scores, ptid, 32);
-      cp_async_commit();
+      if (ptid == 0 && it + kLeadArr < n_chunks)
+        stage_chunk_bulk<SC, TH>(ka, cap, stage_of(it + kLeadArr), plan, L.src_in, L.in2out, L.label_in, L.in_ptr,
+                                 &bar_arr[(it + kLeadArr) & (kRing - 1)]);
+      if (SC && it + kLeadGat < n_chunks) {
+        mbar_wait(&bar_arr[(it + kLeadGat) & (kRing - 1)], ((it + kLeadGat) / kRing) & 1);
+        gather_scores(kg, cap, stage_of(it + kLeadGat), plan, arc_scores, ptid, &bar_w[(it + kLeadGat) & (kRing - 1)]);
+      }
+    } else {
+      mbar_wait(&bar_arr[it & (kRing - 1)], (it / kRing) & 1);
+      if (SC) mbar_wait(&bar_w[it & (kRing - 1)], (it / kRing) & 1);
     }
     const int* s_src = reinterpret_cast<const int*>(smem_f + s_cur + o_nbr);
     const float* s_w = smem_f + s_cur + o_wsc;
@@ -410,10 +481,8 @@ __global__ void __launch_bounds__(288, 3)
         }
       }
     }
-    cp_async_wait_all();
-    __syncthreads();  // alpha of chunk c visible; scores of c+1 and arrays of c+2 landed; stage of c free
-    k0 = k1; k1 = k2; k2 = k3;
-    const int t = s_cur; s_cur = s_nxt; s_nxt = s_nn; s_nn = t;
+    __syncthreads();  // alpha of chunk i visible to the block; its stage is free for chunk i+4
+    k0 = k1; k1 = k2n; kg = kgn; ka = kan;
   }
 
   // logZ = logsumexp over the sinks of alpha (every zero-out-degree state has beta = 1,
@@ -444,7 +513,7 @@ __global__ void __launch_bounds__(288, 3)
   const bool want_hist = POST && dtheta != nullptr;
   const bool need_label = TH || want_hist;
   const SmemPlan plan =
-      smem_plan(W, cap, sizeof(ST), L.vocab, LOGS, TROP, SC, need_label, theta_smem != 0, dtheta_smem != 0);
+      smem_plan(W, cap, sizeof(ST), L.vocab, LOGS, TROP, SC, need_label, theta_smem != 0, dtheta_smem != 0, 3, false);
   ST* const win = reinterpret_cast<ST*>(smem_f + plan.win / 4);
   float* const dwin = smem_f + plan.dwin / 4;
   const ST neg_inf = static_cast<ST>(kNegInf);
@@ -478,28 +547,36 @@ __global__ void __launch_bounds__(288, 3)
     if (grad_logz) gscale = grad_logz[b];
   }
 
-  const nfst_chunk_t* chunks = L.bwd_chunks;
-  int c = L.bwd_chunk_off[b];
-  const int c_end = L.bwd_chunk_off[b + 1];
+  const nfst_chunk_t* chunks = L.bwd_chunks + L.bwd_chunk_off[b];
+  const int n_chunks = L.bwd_chunk_off[b + 1] - L.bwd_chunk_off[b];
   const int32_t* lab_arr = need_label ? L.label_out : nullptr;
 
-  int4 k0 = chunk_at(chunks, c, c_end), k1 = chunk_at(chunks, c + 1, c_end);
-  int s_cur = stage0, s_nxt = stage0 + stage_words;
-  auto stage_in = [&](const int4& k, int st, int t, int nt) {
-    if (need_label) stage_chunk<SC, true>(k, cap, st, plan, L.dst_out, arc_scores, lab_arr, L.out_ptr, t, nt);
-    else stage_chunk<SC, false>(k, cap, st, plan, L.dst_out, arc_scores, lab_arr, L.out_ptr, t, nt);
-  };
-  stage_in(k0, s_cur, tid, NT);
-  cp_async_commit();
-  cp_async_wait_all();
+  // ---- pipeline: ring of 3 stages, TMA bulk copies two chunks ahead, one mbarrier per stage
+  constexpr int kRing = 3, kLead = 2;
+  __shared__ __align__(8) unsigned long long bar_arr[kRing];
+  if (tid == 0) {
+    for (int i = 0; i < kRing; ++i) mbar_init(&bar_arr[i], 1);
+    mbar_fence_init();
+  }
   __syncthreads();
+  auto stage_in = [&](const int4& k, int slot) {
+    const int st = stage0 + slot * stage_words;
+    if (need_label) stage_chunk_bulk<SC, true>(k, cap, st, plan, L.dst_out, arc_scores, lab_arr, L.out_ptr, &bar_arr[slot]);
+    else stage_chunk_bulk<SC, false>(k, cap, st, plan, L.dst_out, arc_scores, lab_arr, L.out_ptr, &bar_arr[slot]);
+  };
+  if (producer && ptid == 0)
+    for (int j = 0; j < kLead && j < n_chunks; ++j) stage_in(chunk_at(chunks, j, n_chunks), j);
+  int4 k0 = chunk_at(chunks, 0, n_chunks), k1 = chunk_at(chunks, 1, n_chunks), ka = chunk_at(chunks, kLead, n_chunks);
+  int slot = 0, slot_a = kLead % kRing, phase = 0;  // consumer slot, producer slot, consumer phase parity
 
 #pragma unroll 1
-  for (; c < c_end; ++c) {
-    const int4 k2 = chunk_at(chunks, c + 2, c_end);
+  for (int it = 0; it < n_chunks; ++it) {
+    const int4 k2 = chunk_at(chunks, it + 2, n_chunks), kan = chunk_at(chunks, it + 1 + kLead, n_chunks);
+    const int s_cur = stage0 + slot * stage_words;
     if (producer) {
-      stage_in(k1, s_nxt, ptid, 32);
-      cp_async_commit();
+      if (ptid == 0 && it + kLead < n_chunks) stage_in(ka, slot_a);
+    } else {
+      mbar_wait(&bar_arr[slot], phase);
     }
     const int* s_dst = reinterpret_cast<const int*>(smem_f + s_cur + o_nbr);
     const float* s_w = smem_f + s_cur + o_aux;
@@ -697,10 +774,10 @@ __global__ void __launch_bounds__(288, 3)
         }
       }
     }
-    cp_async_wait_all();
-    __syncthreads();
-    k0 = k1; k1 = k2;
-    const int t = s_cur; s_cur = s_nxt; s_nxt = t;
+    __syncthreads();  // results of chunk i visible to the block; its stage is free for chunk i+3
+    k0 = k1; k1 = k2; ka = kan;
+    if (++slot == kRing) { slot = 0; phase ^= 1; }
+    if (++slot_a == kRing) slot_a = 0;
   }
 
   if (tid == 0) {
@@ -916,7 +993,7 @@ size_t nfst_launch_smem_bytes(const nfst_launch_t* launch, int32_t vocab, int pa
   const SmemPlan p = smem_plan(launch->window_states, launch->chunk_cap,
                                launch->state_f64 ? 8 : 4, vocab, !bwd || with_log != 0, bwd && with_trop != 0,
                                with_scores != 0, with_theta != 0 || (bwd && with_dtheta != 0), with_theta && small_v,
-                               bwd && with_dtheta && small_v, bwd ? 2 : 3, !bwd);
+                               bwd && with_dtheta && small_v, bwd ? 3 : 4, !bwd);
   return p.bytes;
 }
 
