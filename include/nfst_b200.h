@@ -41,7 +41,7 @@
 extern "C" {
 #endif
 
-#define NFST_ABI_VERSION 3
+#define NFST_ABI_VERSION 4
 
 typedef enum nfst_status {
   NFST_OK = 0,
@@ -98,6 +98,7 @@ typedef struct nfst_packed_lattices {
   const nfst_chunk_t* fwd_chunks;   /* ascending */
   const int32_t* bwd_chunk_off;     /* [B+1] */
   const nfst_chunk_t* bwd_chunks;   /* descending */
+  const int32_t* fwd_gather;        /* [n_fwd_chunks][2]: canonical-id range [lo, hi) the chunk's arcs gather from */
 } nfst_packed_lattices_t;
 
 /*

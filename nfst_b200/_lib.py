@@ -41,6 +41,7 @@ class PackedLatticesC(C.Structure):
         ("fwd_chunks", C.c_void_p),
         ("bwd_chunk_off", C.c_void_p),
         ("bwd_chunks", C.c_void_p),
+        ("fwd_gather", C.c_void_p),
     ]
 
 
@@ -105,7 +106,7 @@ def load() -> C.CDLL:
         fn = getattr(lib, name)  # AttributeError if the header and the library disagree
         fn.restype = res
         fn.argtypes = args
-    if lib.nfst_abi_version() != 3:
+    if lib.nfst_abi_version() != 4:
         raise RuntimeError("libnfst_b200.so ABI version mismatch")
     _lib = lib
     return lib

@@ -245,6 +245,14 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned by
 __device__ __forceinline__ void cpasync_mbar_arrive(unsigned long long* bar) {
   asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// pull [p, p + bytes) into L2 (no shared memory, no registers, no completion to wait for)
+__device__ __forceinline__ void l2_prefetch(const void* p, long long bytes) {
+  if (bytes <= 0) return;
+  const unsigned long long a = reinterpret_cast<unsigned long long>(p);
+  const unsigned long long a16 = a & ~15ULL;
+  const unsigned n = static_cast<unsigned>((a + bytes - a16 + 15) & ~15ULL);
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a16), "r"(n) : "memory");
+}
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // Producer lane 0: stream the arc arrays and row pointers of chunk k into the stage at word
@@ -279,22 +287,34 @@ __device__ __forceinline__ void stage_chunk_bulk(const int4& k, int cap, int st,
 // into shared memory and IN PLACE over the indices (4-byte cp.async, no registers):
 // scores[idx[pos]] -> slot pos.  Each lane then arrives on `bar` when its copies have landed.
 __device__ __forceinline__ void gather_scores(const int4& k, int cap, int st, const SmemPlan& plan,
-                                              const float* __restrict__ scores, int lane, unsigned long long* bar) {
+                                              const float* __restrict__ scores, int t, int nt, unsigned long long* bar) {
   if (k.y - k.x <= cap) {
     const int n_slots = ((k.y - (k.x & ~3) + 3) >> 2) << 2;
     const int* s_idx = reinterpret_cast<const int*>(smem_f + st + plan.aux / 4);
     float* s_w = smem_f + st + plan.wsc / 4;
-    int i = lane;
-    for (; i + 96 < n_slots; i += 128) {  // 4 independent index loads, then 4 copies
-      const int i0 = s_idx[i], i1 = s_idx[i + 32], i2 = s_idx[i + 64], i3 = s_idx[i + 96];
+    int i = t;
+    for (; i + 3 * nt < n_slots; i += 4 * nt) {  // 4 independent index loads, then 4 copies
+      const int i0 = s_idx[i], i1 = s_idx[i + nt], i2 = s_idx[i + 2 * nt], i3 = s_idx[i + 3 * nt];
       cp_async4(s_w + i, scores + i0);
-      cp_async4(s_w + i + 32, scores + i1);
-      cp_async4(s_w + i + 64, scores + i2);
-      cp_async4(s_w + i + 96, scores + i3);
+      cp_async4(s_w + i + nt, scores + i1);
+      cp_async4(s_w + i + 2 * nt, scores + i2);
+      cp_async4(s_w + i + 3 * nt, scores + i3);
     }
-    for (; i < n_slots; i += 32) cp_async4(s_w + i, scores + s_idx[i]);
+    for (; i < n_slots; i += nt) cp_async4(s_w + i, scores + s_idx[i]);
   }
   cpasync_mbar_arrive(bar);
+}
+
+// L2 prefetch of everything chunk k will stream (one lane, several chunks ahead of the copies)
+template <bool AUX, bool LAB>
+__device__ __forceinline__ void prefetch_chunk_l2(const int4& k, const int32_t* __restrict__ nbr,
+                                                  const void* __restrict__ aux, const int32_t* __restrict__ lab,
+                                                  const int32_t* __restrict__ ptr) {
+  const long long nb = static_cast<long long>(k.y - k.x) * 4;
+  l2_prefetch(nbr + k.x, nb);
+  if (AUX) l2_prefetch(static_cast<const int32_t*>(aux) + k.x, nb);
+  if (LAB) l2_prefetch(lab + k.x, nb);
+  l2_prefetch(ptr + k.z, static_cast<long long>(k.w - k.z + 1) * 4);
 }
 
 // rare path: a neighbour older than the shared-memory window (kept out of line so that the
@@ -350,23 +370,34 @@ __global__ void __launch_bounds__(288, 3)
   if (tid == 0) {
     for (int i = 0; i < kRing; ++i) {
       mbar_init(&bar_arr[i], 1);
-      mbar_init(&bar_w[i], 32);
+      mbar_init(&bar_w[i], NT);  // every thread of the block takes part in the score gather
     }
     mbar_fence_init();
   }
   __syncthreads();
   auto stage_of = [&](int i) { return stage0 + (i & (kRing - 1)) * stage_words; };
-  if (producer) {
-    for (int j = 0; j < kLeadArr && j < n_chunks; ++j)
-      if (ptid == 0)
-        stage_chunk_bulk<SC, TH>(chunk_at(chunks, j, n_chunks), cap, stage_of(j), plan, L.src_in, L.in2out, L.label_in,
-                                 L.in_ptr, &bar_arr[j & (kRing - 1)]);
-    if (SC)
-      for (int j = 0; j < kLeadGat && j < n_chunks; ++j) {
-        mbar_wait(&bar_arr[j & (kRing - 1)], 0);
-        gather_scores(chunk_at(chunks, j, n_chunks), cap, stage_of(j), plan, arc_scores, ptid, &bar_w[j & (kRing - 1)]);
+  constexpr int kPrefetch = 8;  // L2 prefetch distance, in chunks
+  const int32_t* gat = L.fwd_gather + 2 * L.fwd_chunk_off[b];
+  auto prefetch = [&](int j) {  // producer lane 0 only
+    if (j < n_chunks) {
+      prefetch_chunk_l2<SC, TH>(chunk_at(chunks, j, n_chunks), L.src_in, L.in2out, L.label_in, L.in_ptr);
+      if (SC) {
+        const int lo = __ldg(gat + 2 * j), hi = __ldg(gat + 2 * j + 1);
+        l2_prefetch(arc_scores + lo, static_cast<long long>(hi - lo) * 4);
       }
+    }
+  };
+  if (producer && ptid == 0) {
+    for (int j = 0; j < kLeadArr && j < n_chunks; ++j)
+      stage_chunk_bulk<SC, TH>(chunk_at(chunks, j, n_chunks), cap, stage_of(j), plan, L.src_in, L.in2out, L.label_in,
+                               L.in_ptr, &bar_arr[j & (kRing - 1)]);
+    for (int j = 0; j < kPrefetch; ++j) prefetch(j);
   }
+  if (SC)
+    for (int j = 0; j < kLeadGat && j < n_chunks; ++j) {
+      mbar_wait(&bar_arr[j & (kRing - 1)], 0);
+      gather_scores(chunk_at(chunks, j, n_chunks), cap, stage_of(j), plan, arc_scores, tid, NT, &bar_w[j & (kRing - 1)]);
+    }
   // chunk descriptors: k0 = chunk i (consumers), kg = chunk i+2, ka = chunk i+3 (producer);
   // each is loaded one iteration before its first use
   int4 k0 = chunk_at(chunks, 0, n_chunks), k1 = chunk_at(chunks, 1, n_chunks), kg = chunk_at(chunks, kLeadGat, n_chunks),
@@ -377,15 +408,17 @@ __global__ void __launch_bounds__(288, 3)
     const int4 k2n = chunk_at(chunks, it + 2, n_chunks);
     const int4 kgn = chunk_at(chunks, it + 1 + kLeadGat, n_chunks), kan = chunk_at(chunks, it + 1 + kLeadArr, n_chunks);
     const int s_cur = stage_of(it);
-    if (producer) {
-      if (ptid == 0 && it + kLeadArr < n_chunks)
+    if (producer && ptid == 0) {
+      if (it + kLeadArr < n_chunks)
         stage_chunk_bulk<SC, TH>(ka, cap, stage_of(it + kLeadArr), plan, L.src_in, L.in2out, L.label_in, L.in_ptr,
                                  &bar_arr[(it + kLeadArr) & (kRing - 1)]);
-      if (SC && it + kLeadGat < n_chunks) {
-        mbar_wait(&bar_arr[(it + kLeadGat) & (kRing - 1)], ((it + kLeadGat) / kRing) & 1);
-        gather_scores(kg, cap, stage_of(it + kLeadGat), plan, arc_scores, ptid, &bar_w[(it + kLeadGat) & (kRing - 1)]);
-      }
-    } else {
+      prefetch(it + kPrefetch);
+    }
+    if (SC && it + kLeadGat < n_chunks) {  // all threads: gather the scores of chunk it+2
+      mbar_wait(&bar_arr[(it + kLeadGat) & (kRing - 1)], ((it + kLeadGat) / kRing) & 1);
+      gather_scores(kg, cap, stage_of(it + kLeadGat), plan, arc_scores, tid, NT, &bar_w[(it + kLeadGat) & (kRing - 1)]);
+    }
+    if (!producer) {
       mbar_wait(&bar_arr[it & (kRing - 1)], (it / kRing) & 1);
       if (SC) mbar_wait(&bar_w[it & (kRing - 1)], (it / kRing) & 1);
     }
@@ -564,8 +597,19 @@ __global__ void __launch_bounds__(288, 3)
     if (need_label) stage_chunk_bulk<SC, true>(k, cap, st, plan, L.dst_out, arc_scores, lab_arr, L.out_ptr, &bar_arr[slot]);
     else stage_chunk_bulk<SC, false>(k, cap, st, plan, L.dst_out, arc_scores, lab_arr, L.out_ptr, &bar_arr[slot]);
   };
-  if (producer && ptid == 0)
+  constexpr int kPrefetch = 8;  // L2 prefetch distance, in chunks
+  auto prefetch = [&](int j) {  // producer lane 0 only
+    if (j < n_chunks) {
+      const int4 k = chunk_at(chunks, j, n_chunks);
+      if (need_label) prefetch_chunk_l2<SC, true>(k, L.dst_out, arc_scores, lab_arr, L.out_ptr);
+      else prefetch_chunk_l2<SC, false>(k, L.dst_out, arc_scores, lab_arr, L.out_ptr);
+      if (POST) l2_prefetch(alpha + k.z, static_cast<long long>(k.w - k.z) * sizeof(ST));
+    }
+  };
+  if (producer && ptid == 0) {
     for (int j = 0; j < kLead && j < n_chunks; ++j) stage_in(chunk_at(chunks, j, n_chunks), j);
+    for (int j = 0; j < kPrefetch; ++j) prefetch(j);
+  }
   int4 k0 = chunk_at(chunks, 0, n_chunks), k1 = chunk_at(chunks, 1, n_chunks), ka = chunk_at(chunks, kLead, n_chunks);
   int slot = 0, slot_a = kLead % kRing, phase = 0;  // consumer slot, producer slot, consumer phase parity
 
@@ -574,7 +618,10 @@ __global__ void __launch_bounds__(288, 3)
     const int4 k2 = chunk_at(chunks, it + 2, n_chunks), kan = chunk_at(chunks, it + 1 + kLead, n_chunks);
     const int s_cur = stage0 + slot * stage_words;
     if (producer) {
-      if (ptid == 0 && it + kLead < n_chunks) stage_in(ka, slot_a);
+      if (ptid == 0) {
+        if (it + kLead < n_chunks) stage_in(ka, slot_a);
+        prefetch(it + kPrefetch);
+      }
     } else {
       mbar_wait(&bar_arr[slot], phase);
     }

@@ -73,7 +73,7 @@ class PackedLattices:
     _INT_FIELDS = (
         "state_off", "level_off", "level_ptr", "start_state", "sink_off", "sinks",
         "in_ptr", "src_in", "label_in", "in2out", "out_ptr", "dst_out", "label_out",
-        "fwd_chunk_off", "fwd_chunks", "bwd_chunk_off", "bwd_chunks",
+        "fwd_chunk_off", "fwd_chunks", "bwd_chunk_off", "bwd_chunks", "fwd_gather",
     )
 
     # arrays the kernels stage with 16-byte copies: kept zero-padded by PAD elements
@@ -282,6 +282,8 @@ def concat_packed(parts: List["PackedLattices"]) -> "PackedLattices":
         acc["fwd_chunks"].append(p.fwd_chunks + shift)
         acc["bwd_chunk_off"].append(cut(p.bwd_chunk_off + nbc))
         acc["bwd_chunks"].append(p.bwd_chunks + shift)
+        nonempty = (p.fwd_gather[:, 1] > p.fwd_gather[:, 0]).to(torch.int32).unsqueeze(1)
+        acc["fwd_gather"].append(p.fwd_gather + A * nonempty)
         nfc += int(p.fwd_chunks.shape[0])
         nbc += int(p.bwd_chunks.shape[0])
         extra["lanes_in_log2"].append(p.lanes_in_log2)
@@ -431,6 +433,19 @@ def pack_arcs(
     target_state, heavy_state = geo[block_class, 0][lt_s], geo[block_class, 1][lt_s]
     fwd_chunk_off, fwd_chunks = _build_chunks(in_ptr, slot, lvl_first_state, lt_s, target_state, heavy_state, B, False)
     bwd_chunk_off, bwd_chunks = _build_chunks(out_ptr, slot, lvl_first_state, lt_s, target_state, heavy_state, B, True)
+    # canonical-id range [lo, hi) that the arcs of each forward chunk gather their scores from
+    # (the kernel prefetches it into L2 several chunks ahead)
+    nfc = int(fwd_chunks.shape[0])
+    fc = fwd_chunks.to(torch.int64)
+    n_arc_c = fc[:, 1] - fc[:, 0]
+    g_lo = torch.full((nfc,), A, dtype=torch.int64, device=dev)
+    g_hi = torch.zeros(nfc, dtype=torch.int64, device=dev)
+    if A:
+        cid = torch.repeat_interleave(torch.arange(nfc, device=dev), n_arc_c)  # fwd chunks tile the in-order arcs
+        g_lo = g_lo.scatter_reduce(0, cid, in2out, reduce="amin")
+        g_hi = g_hi.scatter_reduce(0, cid, in2out + 1, reduce="amax")
+    g_lo = torch.where(n_arc_c > 0, g_lo, torch.zeros_like(g_lo))
+    fwd_gather = torch.stack([g_lo, torch.maximum(g_hi, g_lo)], dim=1)
     # how far back (in packed state ids) an arc reaches: sizes the shared-memory window
     arc_lat = torch.repeat_interleave(torch.arange(B, device=dev), (arc_off[1:] - arc_off[:-1]))
     # (99% quantile over the lattice's arcs, rounded up to a power of two, from a log2
@@ -459,6 +474,7 @@ def pack_arcs(
         sink_off=i32(sink_off), sinks=i32(sinks), in_ptr=i32(in_ptr), src_in=i32(src_in), label_in=i32(label_in),
         in2out=i32(in2out), out_ptr=i32(out_ptr), dst_out=i32(dst_out), label_out=i32(label_out),
         fwd_chunk_off=i32(fwd_chunk_off), fwd_chunks=fwd_chunks, bwd_chunk_off=i32(bwd_chunk_off), bwd_chunks=bwd_chunks,
+        fwd_gather=i32(fwd_gather),
         lanes_in_log2=lg_in.to(torch.uint8).contiguous(), lanes_out_log2=lg_out.to(torch.uint8).contiguous(),
         orig_state=i32(orig_state), arc_origin=origin.contiguous(), arc_off=i32(arc_off), n_levels=i32(n_levels),
         static_scores=None if static_scores is None else static_scores[origin].to(torch.float32).contiguous(),
