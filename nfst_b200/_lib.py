@@ -87,7 +87,7 @@ _lib = None
 
 
 def library_path() -> str:
-    return _build.LIB
+    return os.environ.get("NFST_LIB", _build.LIB)  # NFST_LIB: load a variant build (timing hooks)
 
 
 def load() -> C.CDLL:

@@ -32,12 +32,15 @@ def is_stale() -> bool:
     return any(os.path.getmtime(p) > t for p in SRC + HDR)
 
 
-def build_library(force: bool = False, verbose: bool = False) -> str:
-    """Compile nfst_b200/csrc/*.cu into nfst_b200/lib/libnfst_b200.so for sm_100a."""
-    if not force and not is_stale():
-        return LIB
-    os.makedirs(os.path.dirname(LIB), exist_ok=True)
-    cmd = [_nvcc(), *NVCC_FLAGS, "-I", os.path.join(ROOT, "include"), "-o", LIB, *SRC]
+def build_library(force: bool = False, verbose: bool = False, out: str = None, defines=()) -> str:
+    """Compile nfst_b200/csrc/*.cu into nfst_b200/lib/libnfst_b200.so for sm_100a.
+    `out` / `defines` build a variant elsewhere (e.g. -DNFST_TIMING for tools/phase_timing.py)."""
+    if out is None:
+        if not force and not is_stale():
+            return LIB
+        out = LIB
+    os.makedirs(os.path.dirname(out), exist_ok=True)
+    cmd = [_nvcc(), *NVCC_FLAGS, *[f"-D{d}" for d in defines], "-I", os.path.join(ROOT, "include"), "-o", out, *SRC]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     res = subprocess.run(cmd, capture_output=True, text=True)
@@ -45,7 +48,7 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
         raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
     if verbose:
         print(res.stderr)
-    return LIB
+    return out
 
 
 if __name__ == "__main__":

@@ -110,31 +110,18 @@ __device__ ST block_lse(ST m, float s) {
 }
 
 // ---- shared memory carve-up (identical on host and device), offsets in bytes ----------
-// [window ST[W]] [delta window f32[W]] [2 stages x {nbr int[cap+8], aux int[cap+8], lab int[cap+8],
-// ptr int[cap+8]}] [theta f32[V]] [dtheta f32[V]]
+// [window ST[W]] [delta window f32[W]] [theta f32[V]] [dtheta f32[V]]
 struct SmemPlan {
-  size_t win, dwin, stage0, stage_bytes, nbr, aux, wsc, lab, ptr, theta, dtheta, bytes;
+  size_t win, dwin, theta, dtheta, bytes;
 };
-__host__ __device__ inline SmemPlan smem_plan(int W, int cap, int st_bytes, int vocab, bool logs, bool trop,
-                                              bool with_scores, bool with_labels, bool with_theta, bool with_dtheta,
-                                              int n_stages = 2, bool gathered_scores = false) {
+__host__ __device__ inline SmemPlan smem_plan(int W, int st_bytes, int vocab, bool logs, bool trop, bool with_theta,
+                                              bool with_dtheta) {
   SmemPlan p;
   size_t o = 0;
-  const size_t arr = static_cast<size_t>(cap + 8) * 4;
   p.win = o;
   o += logs ? static_cast<size_t>(W) * st_bytes : 0;
   p.dwin = o;
   o += trop ? static_cast<size_t>(W) * 4 : 0;
-  o = (o + 15) & ~static_cast<size_t>(15);
-  p.stage0 = o;
-  size_t q = 0;
-  p.nbr = q; q += arr;                      // neighbour state of every arc (src_in / dst_out)
-  p.aux = q; q += with_scores ? arr : 0;    // forward: in2out index; backward: the score itself
-  p.wsc = p.aux; (void)gathered_scores;      // forward: scores are gathered IN PLACE over their indices
-  p.lab = q; q += with_labels ? arr : 0;
-  p.ptr = q; q += arr;                      // CSR row pointers of the chunk's states
-  p.stage_bytes = q;
-  o += static_cast<size_t>(n_stages) * q;
   p.theta = o;
   o += with_theta ? static_cast<size_t>(vocab) * 4 : 0;
   p.dtheta = o;
@@ -195,56 +182,12 @@ __device__ __forceinline__ ST lse_finish(ST m, float s, ST neg_inf) {
   return (m > static_cast<ST>(kFloor)) ? m + static_cast<ST>(lg2_approx(s) * kLn2) : neg_inf;
 }
 
-__device__ __forceinline__ void cp_async4(void* smem, const void* gmem) {
-  const unsigned sa = static_cast<unsigned>(__cvta_generic_to_shared(smem));
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(sa), "l"(gmem));
-}
 
 // All dynamic shared memory is addressed as 32-bit words off one typed extern array (keeps
 // the accesses in the shared address space for the compiler: plain LDS/STS with immediate
 // offsets, no generic-pointer conversions in the loops).
 extern __shared__ __align__(16) float smem_f[];
 
-// ---- mbarrier / TMA bulk-copy primitives (sm_90+ PTX; SASS: SYNCS.*, UBLKCP) --------------
-__device__ __forceinline__ unsigned smem_u32(const void* p) { return static_cast<unsigned>(__cvta_generic_to_shared(p)); }
-__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long* bar, unsigned bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-// wait for the phase with the given parity; bounded spin, then trap (a hang would cost a GPU)
-__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
-  const unsigned addr = smem_u32(bar);
-  unsigned ok = 0;
-  for (int spins = 0; spins < (1 << 22); ++spins) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(addr), "r"(parity)
-        : "memory");
-    if (ok) return;
-  }
-  __trap();
-}
-// one TMA bulk copy global -> shared (16-byte aligned, size a multiple of 16); completion is
-// credited to `bar` as transaction bytes
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                   smem_u32(dst)),
-               "l"(src), "r"(bytes), "r"(smem_u32(bar))
-               : "memory");
-}
-// arrive on `bar` once every cp.async this thread has issued so far has landed
-__device__ __forceinline__ void cpasync_mbar_arrive(unsigned long long* bar) {
-  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
 // pull [p, p + bytes) into L2 (no shared memory, no registers, no completion to wait for)
 __device__ __forceinline__ void l2_prefetch(const void* p, long long bytes) {
   if (bytes <= 0) return;
@@ -253,69 +196,16 @@ __device__ __forceinline__ void l2_prefetch(const void* p, long long bytes) {
   const unsigned n = static_cast<unsigned>((a + bytes - a16 + 15) & ~15ULL);
   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a16), "r"(n) : "memory");
 }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-
-// Producer lane 0: stream the arc arrays and row pointers of chunk k into the stage at word
-// offset `st` with TMA bulk copies, completion on `bar`.  Copies start at the 4-aligned
-// position below the chunk and may run a few elements past it; the arrays are zero-padded, so
-// whatever is over-read is a valid index.  Oversize chunks are not staged (plain arrive).
-template <bool AUX, bool LAB>
-__device__ __forceinline__ void stage_chunk_bulk(const int4& k, int cap, int st, const SmemPlan& plan,
-                                                 const int32_t* __restrict__ nbr, const void* __restrict__ aux,
-                                                 const int32_t* __restrict__ lab, const int32_t* __restrict__ ptr,
-                                                 unsigned long long* bar) {
-  if (k.y - k.x <= cap) {
-    const int base4 = k.x & ~3;
-    const unsigned nb = static_cast<unsigned>((k.y - base4 + 3) >> 2) << 4;  // bytes per arc array
-    const int pb = k.z & ~3;
-    const unsigned pbytes = static_cast<unsigned>((k.w + 1 - pb + 3) >> 2) << 4;
-    const unsigned total = nb * (1u + (AUX ? 1u : 0u) + (LAB ? 1u : 0u)) + pbytes;
-    fence_proxy_async();  // earlier generic-proxy reads of this stage are ordered before the refill
-    mbar_arrive_expect_tx(bar, total);
-    if (nb) {
-      bulk_g2s(smem_f + st + plan.nbr / 4, nbr + base4, nb, bar);
-      if (AUX) bulk_g2s(smem_f + st + plan.aux / 4, static_cast<const int32_t*>(aux) + base4, nb, bar);
-      if (LAB) bulk_g2s(smem_f + st + plan.lab / 4, lab + base4, nb, bar);
-    }
-    bulk_g2s(smem_f + st + plan.ptr / 4, ptr + pb, pbytes, bar);
-  } else {
-    mbar_arrive(bar);
-  }
-}
-
-// Producer warp: gather the scores of a staged chunk through its staged index array, straight
-// into shared memory and IN PLACE over the indices (4-byte cp.async, no registers):
-// scores[idx[pos]] -> slot pos.  Each lane then arrives on `bar` when its copies have landed.
-__device__ __forceinline__ void gather_scores(const int4& k, int cap, int st, const SmemPlan& plan,
-                                              const float* __restrict__ scores, int t, int nt, unsigned long long* bar) {
-  if (k.y - k.x <= cap) {
-    const int n_slots = ((k.y - (k.x & ~3) + 3) >> 2) << 2;
-    const int* s_idx = reinterpret_cast<const int*>(smem_f + st + plan.aux / 4);
-    float* s_w = smem_f + st + plan.wsc / 4;
-    int i = t;
-    for (; i + 3 * nt < n_slots; i += 4 * nt) {  // 4 independent index loads, then 4 copies
-      const int i0 = s_idx[i], i1 = s_idx[i + nt], i2 = s_idx[i + 2 * nt], i3 = s_idx[i + 3 * nt];
-      cp_async4(s_w + i, scores + i0);
-      cp_async4(s_w + i + nt, scores + i1);
-      cp_async4(s_w + i + 2 * nt, scores + i2);
-      cp_async4(s_w + i + 3 * nt, scores + i3);
-    }
-    for (; i < n_slots; i += nt) cp_async4(s_w + i, scores + s_idx[i]);
-  }
-  cpasync_mbar_arrive(bar);
-}
-
-// L2 prefetch of everything chunk k will stream (one lane, several chunks ahead of the copies)
-template <bool AUX, bool LAB>
-__device__ __forceinline__ void prefetch_chunk_l2(const int4& k, const int32_t* __restrict__ nbr,
-                                                  const void* __restrict__ aux, const int32_t* __restrict__ lab,
-                                                  const int32_t* __restrict__ ptr) {
-  const long long nb = static_cast<long long>(k.y - k.x) * 4;
-  l2_prefetch(nbr + k.x, nb);
-  if (AUX) l2_prefetch(static_cast<const int32_t*>(aux) + k.x, nb);
-  if (LAB) l2_prefetch(lab + k.x, nb);
-  l2_prefetch(ptr + k.z, static_cast<long long>(k.w - k.z + 1) * 4);
-}
+// ---- optional per-phase cycle counters (build with -DNFST_TIMING; see tools/phase_timing.py)
+#ifdef NFST_TIMING
+__device__ unsigned long long g_dbg[32];
+#define NFST_T(var) const long long var = clock64()
+#define NFST_ACC(cond, slot, cycles) \
+  do { if (cond) atomicAdd(&g_dbg[slot], static_cast<unsigned long long>(cycles)); } while (0)
+#else
+#define NFST_T(var) do {} while (0)
+#define NFST_ACC(cond, slot, cycles) do {} while (0)
+#endif
 
 // rare path: a neighbour older than the shared-memory window (kept out of line so that the
 // hot loops carry no 64-bit address arithmetic)
@@ -325,24 +215,24 @@ __device__ __noinline__ T load_behind_window(const T* p, int i) { return p[i]; }
 // =====================================================================================
 // forward: alpha
 // =====================================================================================
-// Block = `block_threads` consumer threads + ONE producer warp.  The producer warp issues
-// every cp.async of the pipeline (arc arrays two chunks ahead, score gather one chunk ahead);
-// the consumer warps only reduce.  SC: per-arc scores given; TH: theta[label] given (at least one of them).
+// One block per lattice, one chunk (a run of states of one level) per iteration, one barrier per
+// chunk.  Nothing is staged: one lane prefetches the arrays of the chunk kPrefetch iterations
+// ahead into L2 (and the region of the score array that chunk gathers from), the threads then
+// read their arcs straight from global memory (L2 / L1 hits).  Shared memory only holds the
+// window of recent DP values, so many blocks -- ideally every lattice of the batch -- are
+// resident at once and hide each other's latency.
+// SC: per-arc scores given; TH: theta[label] given (at least one of them).
+constexpr int kPrefetch = 6;  // L2 prefetch distance, in chunks
+
 template <typename ST, bool SC, bool TH>
-__global__ void __launch_bounds__(288, 3)
+__global__ void __launch_bounds__(256, 4)
     nfst_fwd_kernel(const nfst_packed_lattices_t L, const int32_t* __restrict__ ids, int W, int cap,
                     const float* __restrict__ arc_scores, const float* __restrict__ theta, int theta_smem, ST* alpha,
                     ST* __restrict__ logz) {
   const int NT = blockDim.x, tid = threadIdx.x;
-  const int NTc = NT - 32;            // consumer threads; the last warp is the producer
-  const bool producer = tid >= NTc;
-  const int ptid = tid - NTc;
-  const SmemPlan plan = smem_plan(W, cap, sizeof(ST), L.vocab, true, false, SC, TH, theta_smem != 0, false, 4, true);
+  const SmemPlan plan = smem_plan(W, sizeof(ST), L.vocab, true, false, theta_smem != 0, false);
   ST* const win = reinterpret_cast<ST*>(smem_f + plan.win / 4);
   const ST neg_inf = static_cast<ST>(kNegInf);
-  const int stage0 = static_cast<int>(plan.stage0 / 4), stage_words = static_cast<int>(plan.stage_bytes / 4);
-  const int o_nbr = static_cast<int>(plan.nbr / 4), o_wsc = static_cast<int>(plan.wsc / 4),
-            o_lab = static_cast<int>(plan.lab / 4), o_ptr = static_cast<int>(plan.ptr / 4);
 
   const int b = ids ? ids[blockIdx.x] : blockIdx.x;
   const int base_s = L.state_off[b];
@@ -358,79 +248,42 @@ __global__ void __launch_bounds__(288, 3)
 
   const nfst_chunk_t* chunks = L.fwd_chunks + L.fwd_chunk_off[b];
   const int n_chunks = L.fwd_chunk_off[b + 1] - L.fwd_chunk_off[b];
+  const int2* gat = reinterpret_cast<const int2*>(L.fwd_gather) + L.fwd_chunk_off[b];
+  const int32_t* __restrict__ in_ptr = L.in_ptr;
+  const int32_t* __restrict__ src_in = L.src_in;
+  const int32_t* __restrict__ in2out = L.in2out;
+  const int32_t* __restrict__ label_in = L.label_in;
 
-  // ---- pipeline: a ring of kRing stages, one mbarrier pair per stage ----------------------
-  //   chunk i   : arc arrays + gathered scores resident  -> reduced by the consumer warps
-  //   chunk i+2 : arrays resident -> the producer warp gathers its scores now (4-byte LDGSTS)
-  //   chunk i+3 :                    its arc arrays stream in now (TMA bulk copies)
-  // Every wait is on an operation issued at least one iteration earlier; the only block-wide
-  // barrier is the one at the end of a chunk (results visible, stage free).
-  constexpr int kRing = 4, kLeadArr = 3, kLeadGat = 2;
-  __shared__ __align__(8) unsigned long long bar_arr[kRing], bar_w[kRing];
-  if (tid == 0) {
-    for (int i = 0; i < kRing; ++i) {
-      mbar_init(&bar_arr[i], 1);
-      mbar_init(&bar_w[i], NT);  // every thread of the block takes part in the score gather
-    }
-    mbar_fence_init();
-  }
-  __syncthreads();
-  auto stage_of = [&](int i) { return stage0 + (i & (kRing - 1)) * stage_words; };
-  constexpr int kPrefetch = 8;  // L2 prefetch distance, in chunks
-  const int32_t* gat = L.fwd_gather + 2 * L.fwd_chunk_off[b];
-  auto prefetch = [&](int j) {  // producer lane 0 only
-    if (j < n_chunks) {
-      prefetch_chunk_l2<SC, TH>(chunk_at(chunks, j, n_chunks), L.src_in, L.in2out, L.label_in, L.in_ptr);
-      if (SC) {
-        const int lo = __ldg(gat + 2 * j), hi = __ldg(gat + 2 * j + 1);
-        l2_prefetch(arc_scores + lo, static_cast<long long>(hi - lo) * 4);
-      }
+  auto prefetch = [&](const int4& k, const int2& g) {  // one lane; (k, g) were loaded an iteration ago
+    if (k.w > k.z) {
+      const long long nb = static_cast<long long>(k.y - k.x) * 4;
+      l2_prefetch(src_in + k.x, nb);
+      if (SC) l2_prefetch(in2out + k.x, nb);
+      if (TH) l2_prefetch(label_in + k.x, nb);
+      l2_prefetch(in_ptr + k.z, static_cast<long long>(k.w - k.z + 1) * 4);
+      if (SC) l2_prefetch(arc_scores + g.x, static_cast<long long>(g.y - g.x) * 4);
     }
   };
-  if (producer && ptid == 0) {
-    for (int j = 0; j < kLeadArr && j < n_chunks; ++j)
-      stage_chunk_bulk<SC, TH>(chunk_at(chunks, j, n_chunks), cap, stage_of(j), plan, L.src_in, L.in2out, L.label_in,
-                               L.in_ptr, &bar_arr[j & (kRing - 1)]);
-    for (int j = 0; j < kPrefetch; ++j) prefetch(j);
-  }
-  if (SC)
-    for (int j = 0; j < kLeadGat && j < n_chunks; ++j) {
-      mbar_wait(&bar_arr[j & (kRing - 1)], 0);
-      gather_scores(chunk_at(chunks, j, n_chunks), cap, stage_of(j), plan, arc_scores, tid, NT, &bar_w[j & (kRing - 1)]);
-    }
-  // chunk descriptors: k0 = chunk i (consumers), kg = chunk i+2, ka = chunk i+3 (producer);
-  // each is loaded one iteration before its first use
-  int4 k0 = chunk_at(chunks, 0, n_chunks), k1 = chunk_at(chunks, 1, n_chunks), kg = chunk_at(chunks, kLeadGat, n_chunks),
-       ka = chunk_at(chunks, kLeadArr, n_chunks);
+  auto gather_range = [&](int j) { return (SC && j < n_chunks) ? __ldg(gat + j) : make_int2(0, 0); };
+  if (tid == 0)
+    for (int j = 0; j < kPrefetch; ++j) prefetch(chunk_at(chunks, j, n_chunks), gather_range(j));
+  int4 k0 = chunk_at(chunks, 0, n_chunks), k1 = chunk_at(chunks, 1, n_chunks);
+  int4 kp = chunk_at(chunks, kPrefetch, n_chunks);
+  int2 gp = gather_range(kPrefetch);
+  __syncthreads();
 
 #pragma unroll 1
   for (int it = 0; it < n_chunks; ++it) {
-    const int4 k2n = chunk_at(chunks, it + 2, n_chunks);
-    const int4 kgn = chunk_at(chunks, it + 1 + kLeadGat, n_chunks), kan = chunk_at(chunks, it + 1 + kLeadArr, n_chunks);
-    const int s_cur = stage_of(it);
-    if (producer && ptid == 0) {
-      if (it + kLeadArr < n_chunks)
-        stage_chunk_bulk<SC, TH>(ka, cap, stage_of(it + kLeadArr), plan, L.src_in, L.in2out, L.label_in, L.in_ptr,
-                                 &bar_arr[(it + kLeadArr) & (kRing - 1)]);
-      prefetch(it + kPrefetch);
+    const int4 k2 = chunk_at(chunks, it + 2, n_chunks);
+    int4 kpn = make_int4(0, 0, 0, 0);
+    int2 gpn = make_int2(0, 0);
+    if (tid == 0) {
+      kpn = chunk_at(chunks, it + 1 + kPrefetch, n_chunks);
+      gpn = gather_range(it + 1 + kPrefetch);
+      prefetch(kp, gp);
     }
-    if (SC && it + kLeadGat < n_chunks) {  // all threads: gather the scores of chunk it+2
-      mbar_wait(&bar_arr[(it + kLeadGat) & (kRing - 1)], ((it + kLeadGat) / kRing) & 1);
-      gather_scores(kg, cap, stage_of(it + kLeadGat), plan, arc_scores, tid, NT, &bar_w[(it + kLeadGat) & (kRing - 1)]);
-    }
-    if (!producer) {
-      mbar_wait(&bar_arr[it & (kRing - 1)], (it / kRing) & 1);
-      if (SC) mbar_wait(&bar_w[it & (kRing - 1)], (it / kRing) & 1);
-    }
-    const int* s_src = reinterpret_cast<const int*>(smem_f + s_cur + o_nbr);
-    const float* s_w = smem_f + s_cur + o_wsc;
-    const int* s_lab = reinterpret_cast<const int*>(smem_f + s_cur + o_lab);
-
-    const int a0 = k0.x, a1 = k0.y, s0 = k0.z, s1 = k0.w;
-    const int n = a1 - a0, ns = s1 - s0;
-    const int base4 = a0 & ~3;
-    // row pointers relative to the stage arrays
-    const int* s_ptr = reinterpret_cast<const int*>(smem_f + s_cur + o_ptr) + (s0 & 3);
+    const int a1 = k0.y, s0 = k0.z, s1 = k0.w;
+    const int n = a1 - k0.x, ns = s1 - s0;
     // readable window: states [s1 - W, s0).  The slots of [s0 - W, s1 - W) are being
     // overwritten by this chunk's own results, so those states are re-read from global.
     const int lo = whole ? static_cast<int>(0x80000000) : s1 - W;
@@ -438,29 +291,27 @@ __global__ void __launch_bounds__(288, 3)
       if (src >= lo) return win[(src - base_s) & wmask];
       return load_behind_window(alpha, src);
     };
-    auto arc_value = [&](int i) -> ST {
-      float w = SC ? s_w[i] : 0.0f;
-      if (TH) w += th[s_lab[i]];
-      return value_of(s_src[i]) + static_cast<ST>(w);
+    auto arc_value = [&](int a) -> ST {
+      float w = SC ? __ldg(arc_scores + __ldg(in2out + a)) : 0.0f;
+      if (TH) w += th[__ldg(label_in + a)];
+      return value_of(__ldg(src_in + a)) + static_cast<ST>(w);
     };
     if (n <= cap) {
-      if (producer) {
-        // nothing to reduce: the producer warp goes straight to the completion wait
-      } else if (ns * 2 > NTc) {
-        // ---- wide chunk: one thread per state, arcs straight from the staged arrays
+      if (ns * 2 > NT) {
+        // ---- wide chunk: one thread per state
 #pragma unroll 1
-        for (int j = tid; j < ns; j += NTc) {
-          int i = s_ptr[j] - base4;
-          const int b1 = s_ptr[j + 1] - base4;
+        for (int j = tid; j < ns; j += NT) {
+          int a = __ldg(in_ptr + s0 + j);
+          const int b1 = __ldg(in_ptr + s0 + j + 1);
           ST m = static_cast<ST>(kFloor);
           float sum = 0.0f;
 #pragma unroll 1
-          for (; i + 3 < b1; i += 4) {  // 4 arcs per trip: independent loads first
-            const ST v0 = arc_value(i), v1 = arc_value(i + 1), v2 = arc_value(i + 2), v3 = arc_value(i + 3);
+          for (; a + 3 < b1; a += 4) {  // 4 arcs per trip: independent loads first
+            const ST v0 = arc_value(a), v1 = arc_value(a + 1), v2 = arc_value(a + 2), v3 = arc_value(a + 3);
             lse_push4(m, sum, v0, v1, v2, v3);
           }
 #pragma unroll 1
-          for (; i < b1; ++i) lse_push(m, sum, arc_value(i), neg_inf);
+          for (; a < b1; ++a) lse_push(m, sum, arc_value(a), neg_inf);
           const int s = s0 + j;
           const ST v = (s == start) ? static_cast<ST>(0) : lse_finish(m, sum, neg_inf);
           if (s >= s1 - W) win[(s - base_s) & wmask] = v;  // only the newest W states own a slot
@@ -469,17 +320,17 @@ __global__ void __launch_bounds__(288, 3)
       } else {
         // ---- narrow chunk: 2^lg lanes per state so that the block stays busy
         int lg = 1;
-        while (lg < 5 && (ns << (lg + 1)) <= NTc) ++lg;
-        const int G = 1 << lg, lane_g = tid & (G - 1), ngrp = NTc >> lg;
+        while (lg < 5 && (ns << (lg + 1)) <= NT) ++lg;
+        const int G = 1 << lg, lane_g = tid & (G - 1), ngrp = NT >> lg;
 #pragma unroll 1
         for (int jb = 0; jb < ns; jb += ngrp) {
           const int j = jb + (tid >> lg);
           const bool valid = j < ns;
-          const int b0 = valid ? s_ptr[j] - base4 : 0, b1 = valid ? s_ptr[j + 1] - base4 : 0;
+          const int b0 = valid ? __ldg(in_ptr + s0 + j) : 0, b1 = valid ? __ldg(in_ptr + s0 + j + 1) : 0;
           ST m = static_cast<ST>(kFloor);
           float sum = 0.0f;
 #pragma unroll 1
-          for (int i = b0 + lane_g; i < b1; i += G) lse_push(m, sum, arc_value(i), neg_inf);
+          for (int a = b0 + lane_g; a < b1; a += G) lse_push(m, sum, arc_value(a), neg_inf);
           for (int o = G >> 1; o > 0; o >>= 1) {
             const ST m2 = __shfl_xor_sync(0xffffffffu, m, o);
             const float s2 = __shfl_xor_sync(0xffffffffu, sum, o);
@@ -494,18 +345,13 @@ __global__ void __launch_bounds__(288, 3)
         }
       }
     } else {
-      // ---- oversize chunk (a state with more than `cap` incoming arcs): block-wide, from global
+      // ---- heavy chunk (a state with more than `cap` incoming arcs): block-wide
       for (int j = 0; j < ns; ++j) {
         const int s = s0 + j;
-        const int b0 = L.in_ptr[s], b1 = L.in_ptr[s + 1];
+        const int b0 = in_ptr[s], b1 = in_ptr[s + 1];
         ST m = neg_inf;
         float sum = 0.0f;
-        for (int a = b0 + tid; a < b1; a += NT) {
-          float w = 0.0f;
-          if (SC) w = arc_scores[L.in2out[a]];
-          if (TH) w += th[L.label_in[a]];
-          lse_add(m, sum, static_cast<ST>(w) + value_of(L.src_in[a]));
-        }
+        for (int a = b0 + tid; a < b1; a += NT) lse_add(m, sum, arc_value(a));
         const ST v0 = block_lse(m, sum);
         if (tid == 0) {
           const ST v = (s == start) ? static_cast<ST>(0) : v0;
@@ -514,8 +360,8 @@ __global__ void __launch_bounds__(288, 3)
         }
       }
     }
-    __syncthreads();  // alpha of chunk i visible to the block; its stage is free for chunk i+4
-    k0 = k1; k1 = k2n; kg = kgn; ka = kan;
+    __syncthreads();  // alpha of this chunk visible to the block
+    k0 = k1; k1 = k2; kp = kpn; gp = gpn;
   }
 
   // logZ = logsumexp over the sinks of alpha (every zero-out-degree state has beta = 1,
@@ -532,7 +378,7 @@ __global__ void __launch_bounds__(288, 3)
 // =====================================================================================
 // LOGS / TROP: semirings; SC / TH: score sources; POST: posteriors (post and/or dtheta).
 template <typename ST, bool LOGS, bool TROP, bool SC, bool TH, bool POST>
-__global__ void __launch_bounds__(288, 3)
+__global__ void __launch_bounds__(256, 4)
     nfst_bwd_kernel(const nfst_packed_lattices_t L, const int32_t* __restrict__ ids, int W, int cap,
                     const float* __restrict__ arc_scores, const float* __restrict__ theta, int theta_smem,
                     int dtheta_smem, const ST* __restrict__ alpha, const ST* __restrict__ logz,
@@ -540,19 +386,12 @@ __global__ void __launch_bounds__(288, 3)
                     float* __restrict__ dtheta, float* delta, int32_t* __restrict__ backptr,
                     float* __restrict__ vit_score) {
   const int NT = blockDim.x, tid = threadIdx.x;
-  const int NTc = NT - 32;  // consumer threads; the last warp is the producer
-  const bool producer = tid >= NTc;
-  const int ptid = tid - NTc;
   const bool want_hist = POST && dtheta != nullptr;
   const bool need_label = TH || want_hist;
-  const SmemPlan plan =
-      smem_plan(W, cap, sizeof(ST), L.vocab, LOGS, TROP, SC, need_label, theta_smem != 0, dtheta_smem != 0, 3, false);
+  const SmemPlan plan = smem_plan(W, sizeof(ST), L.vocab, LOGS, TROP, theta_smem != 0, dtheta_smem != 0);
   ST* const win = reinterpret_cast<ST*>(smem_f + plan.win / 4);
   float* const dwin = smem_f + plan.dwin / 4;
   const ST neg_inf = static_cast<ST>(kNegInf);
-  const int stage0 = static_cast<int>(plan.stage0 / 4), stage_words = static_cast<int>(plan.stage_bytes / 4);
-  const int o_nbr = static_cast<int>(plan.nbr / 4), o_aux = static_cast<int>(plan.aux / 4),
-            o_lab = static_cast<int>(plan.lab / 4), o_ptr = static_cast<int>(plan.ptr / 4);
 
   const int b = ids ? ids[blockIdx.x] : blockIdx.x;
   const int base_s = L.state_off[b];
@@ -582,57 +421,35 @@ __global__ void __launch_bounds__(288, 3)
 
   const nfst_chunk_t* chunks = L.bwd_chunks + L.bwd_chunk_off[b];
   const int n_chunks = L.bwd_chunk_off[b + 1] - L.bwd_chunk_off[b];
-  const int32_t* lab_arr = need_label ? L.label_out : nullptr;
+  const int32_t* __restrict__ out_ptr = L.out_ptr;
+  const int32_t* __restrict__ dst_out = L.dst_out;
+  const int32_t* __restrict__ label_out = L.label_out;
 
-  // ---- pipeline: ring of 3 stages, TMA bulk copies two chunks ahead, one mbarrier per stage
-  constexpr int kRing = 3, kLead = 2;
-  __shared__ __align__(8) unsigned long long bar_arr[kRing];
-  if (tid == 0) {
-    for (int i = 0; i < kRing; ++i) mbar_init(&bar_arr[i], 1);
-    mbar_fence_init();
-  }
-  __syncthreads();
-  auto stage_in = [&](const int4& k, int slot) {
-    const int st = stage0 + slot * stage_words;
-    if (need_label) stage_chunk_bulk<SC, true>(k, cap, st, plan, L.dst_out, arc_scores, lab_arr, L.out_ptr, &bar_arr[slot]);
-    else stage_chunk_bulk<SC, false>(k, cap, st, plan, L.dst_out, arc_scores, lab_arr, L.out_ptr, &bar_arr[slot]);
-  };
-  constexpr int kPrefetch = 8;  // L2 prefetch distance, in chunks
-  auto prefetch = [&](int j) {  // producer lane 0 only
-    if (j < n_chunks) {
-      const int4 k = chunk_at(chunks, j, n_chunks);
-      if (need_label) prefetch_chunk_l2<SC, true>(k, L.dst_out, arc_scores, lab_arr, L.out_ptr);
-      else prefetch_chunk_l2<SC, false>(k, L.dst_out, arc_scores, lab_arr, L.out_ptr);
+  auto prefetch = [&](const int4& k) {  // one lane; k loaded an iteration ago
+    if (k.w > k.z) {
+      const long long nb = static_cast<long long>(k.y - k.x) * 4;
+      l2_prefetch(dst_out + k.x, nb);
+      if (SC) l2_prefetch(arc_scores + k.x, nb);
+      if (need_label) l2_prefetch(label_out + k.x, nb);
+      l2_prefetch(out_ptr + k.z, static_cast<long long>(k.w - k.z + 1) * 4);
       if (POST) l2_prefetch(alpha + k.z, static_cast<long long>(k.w - k.z) * sizeof(ST));
     }
   };
-  if (producer && ptid == 0) {
-    for (int j = 0; j < kLead && j < n_chunks; ++j) stage_in(chunk_at(chunks, j, n_chunks), j);
-    for (int j = 0; j < kPrefetch; ++j) prefetch(j);
-  }
-  int4 k0 = chunk_at(chunks, 0, n_chunks), k1 = chunk_at(chunks, 1, n_chunks), ka = chunk_at(chunks, kLead, n_chunks);
-  int slot = 0, slot_a = kLead % kRing, phase = 0;  // consumer slot, producer slot, consumer phase parity
+  if (tid == 0)
+    for (int j = 0; j < kPrefetch; ++j) prefetch(chunk_at(chunks, j, n_chunks));
+  int4 k0 = chunk_at(chunks, 0, n_chunks), k1 = chunk_at(chunks, 1, n_chunks), kp = chunk_at(chunks, kPrefetch, n_chunks);
+  __syncthreads();
 
 #pragma unroll 1
   for (int it = 0; it < n_chunks; ++it) {
-    const int4 k2 = chunk_at(chunks, it + 2, n_chunks), kan = chunk_at(chunks, it + 1 + kLead, n_chunks);
-    const int s_cur = stage0 + slot * stage_words;
-    if (producer) {
-      if (ptid == 0) {
-        if (it + kLead < n_chunks) stage_in(ka, slot_a);
-        prefetch(it + kPrefetch);
-      }
-    } else {
-      mbar_wait(&bar_arr[slot], phase);
+    const int4 k2 = chunk_at(chunks, it + 2, n_chunks);
+    int4 kpn = make_int4(0, 0, 0, 0);
+    if (tid == 0) {
+      kpn = chunk_at(chunks, it + 1 + kPrefetch, n_chunks);
+      prefetch(kp);
     }
-    const int* s_dst = reinterpret_cast<const int*>(smem_f + s_cur + o_nbr);
-    const float* s_w = smem_f + s_cur + o_aux;
-    const int* s_lab = reinterpret_cast<const int*>(smem_f + s_cur + o_lab);
-
-    const int a0 = k0.x, a1 = k0.y, s0 = k0.z, s1 = k0.w;
-    const int n = a1 - a0, ns = s1 - s0;
-    const int base4 = a0 & ~3;
-    const int* s_ptr = reinterpret_cast<const int*>(smem_f + s_cur + o_ptr) + (s0 & 3);
+    const int a1 = k0.y, s0 = k0.z, s1 = k0.w;
+    const int n = a1 - k0.x, ns = s1 - s0;
     // readable window: states [s1, s0 + W) (see the forward kernel)
     const int hi = whole ? 0x7fffffff : s0 + W;
     auto beta_of = [&](int d) -> ST {
@@ -643,41 +460,41 @@ __global__ void __launch_bounds__(288, 3)
       if (d < hi) return dwin[(d - base_s) & wmask];
       return load_behind_window(delta, d);
     };
-    // one arc of the staged chunk: log-semiring push (+ posterior) and/or tropical candidate
-    auto visit = [&](int i, ST am, ST& m, float& sum, float& bt, int& bi) {
-      const int d = s_dst[i];
-      float w = SC ? s_w[i] : 0.0f;
+    // one arc: log-semiring push (+ posterior) and/or tropical candidate
+    auto visit = [&](int a, ST am, ST& m, float& sum, float& bt, int& bi) {
+      const int d = __ldg(dst_out + a);
+      float w = SC ? __ldg(arc_scores + a) : 0.0f;
       int lab = 0;
-      if (TH || POST) { if (need_label) lab = s_lab[i]; }
+      if (TH || POST) { if (need_label) lab = __ldg(label_out + a); }
       if (TH) w += th[lab];
       if (LOGS) {
         const ST u = static_cast<ST>(w) + beta_of(d);
         lse_push(m, sum, u, neg_inf);
         if (POST) {
           const float p = ex2_approx(static_cast<float>(am + u) * kLog2e) * gscale;
-          if (post) post[base4 + i] = p;
+          if (post) post[a] = p;
           if (hist) atomicAdd(&hist[lab], p);
         }
       }
       if (TROP) {
         const float t = __fadd_rn(w, delta_of(d));
-        if (t > bt) { bt = t; bi = i; }  // strict: within a lane arcs come in label order
+        if (t > bt) { bt = t; bi = a; }  // strict: within a lane arcs come in label order
       }
     };
     // four consecutive arcs of one state: independent loads and exps (see lse_push4)
-    auto visit4 = [&](int i, ST am, ST& m, float& sum, float& bt, int& bi) {
+    auto visit4 = [&](int a, ST am, ST& m, float& sum, float& bt, int& bi) {
       ST u[4];
       int lab[4] = {0, 0, 0, 0};
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        const int d = s_dst[i + k];
-        float w = SC ? s_w[i + k] : 0.0f;
-        if (TH || POST) { if (need_label) lab[k] = s_lab[i + k]; }
+        const int d = __ldg(dst_out + a + k);
+        float w = SC ? __ldg(arc_scores + a + k) : 0.0f;
+        if (TH || POST) { if (need_label) lab[k] = __ldg(label_out + a + k); }
         if (TH) w += th[lab[k]];
         if (LOGS) u[k] = static_cast<ST>(w) + beta_of(d);
         if (TROP) {
           const float t = __fadd_rn(w, delta_of(d));
-          if (t > bt) { bt = t; bi = i + k; }
+          if (t > bt) { bt = t; bi = a + k; }
         }
       }
       if (LOGS) {
@@ -686,7 +503,7 @@ __global__ void __launch_bounds__(288, 3)
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
             const float p = ex2_approx(static_cast<float>(am + u[k]) * kLog2e) * gscale;
-            if (post) post[base4 + i + k] = p;
+            if (post) post[a + k] = p;
             if (hist) atomicAdd(&hist[lab[k]], p);
           }
         }
@@ -703,38 +520,36 @@ __global__ void __launch_bounds__(288, 3)
         const float v = sink ? 0.0f : bt;
         if (s < s0 + W) dwin[(s - base_s) & wmask] = v;
         delta[s] = v;
-        backptr[s] = sink ? -1 : base4 + bi;
+        backptr[s] = sink ? -1 : bi;
       }
     };
     if (n <= cap) {
-      if (producer) {
-        // the producer warp only moves data
-      } else if (ns * 2 > NTc) {
+      if (ns * 2 > NT) {
 #pragma unroll 1
-        for (int j = tid; j < ns; j += NTc) {
-          const int b0 = s_ptr[j] - base4, b1 = s_ptr[j + 1] - base4;
+        for (int j = tid; j < ns; j += NT) {
+          const int b0 = __ldg(out_ptr + s0 + j), b1 = __ldg(out_ptr + s0 + j + 1);
           const int s = s0 + j;
           ST am = 0;
           if (POST) am = alpha[s] - lz;  // issued before the arc loop, consumed inside it
           ST m = static_cast<ST>(kFloor);
           float sum = 0.0f, bt = kNegInf;
           int bi = 0x7fffffff;
-          int i = b0;
+          int a = b0;
 #pragma unroll 1
-          for (; i + 3 < b1; i += 4) visit4(i, am, m, sum, bt, bi);
+          for (; a + 3 < b1; a += 4) visit4(a, am, m, sum, bt, bi);
 #pragma unroll 1
-          for (; i < b1; ++i) visit(i, am, m, sum, bt, bi);
+          for (; a < b1; ++a) visit(a, am, m, sum, bt, bi);
           finish(s, b0 == b1, m, sum, bt, bi);
         }
       } else {
         int lg = 1;
-        while (lg < 5 && (ns << (lg + 1)) <= NTc) ++lg;
-        const int G = 1 << lg, lane_g = tid & (G - 1), ngrp = NTc >> lg;
+        while (lg < 5 && (ns << (lg + 1)) <= NT) ++lg;
+        const int G = 1 << lg, lane_g = tid & (G - 1), ngrp = NT >> lg;
 #pragma unroll 1
         for (int jb = 0; jb < ns; jb += ngrp) {
           const int j = jb + (tid >> lg);
           const bool valid = j < ns;
-          const int b0 = valid ? s_ptr[j] - base4 : 0, b1 = valid ? s_ptr[j + 1] - base4 : 0;
+          const int b0 = valid ? __ldg(out_ptr + s0 + j) : 0, b1 = valid ? __ldg(out_ptr + s0 + j + 1) : 0;
           const int s = s0 + j;
           ST am = 0;
           if (POST && valid) am = alpha[s] - lz;
@@ -742,7 +557,7 @@ __global__ void __launch_bounds__(288, 3)
           float sum = 0.0f, bt = kNegInf;
           int bi = 0x7fffffff;
 #pragma unroll 1
-          for (int i = b0 + lane_g; i < b1; i += G) visit(i, am, m, sum, bt, bi);
+          for (int a = b0 + lane_g; a < b1; a += G) visit(a, am, m, sum, bt, bi);
           for (int o = G >> 1; o > 0; o >>= 1) {
             if (LOGS) {
               const ST m2 = __shfl_xor_sync(0xffffffffu, m, o);
@@ -759,10 +574,10 @@ __global__ void __launch_bounds__(288, 3)
         }
       }
     } else {
-      // ---- oversize chunk: one state at a time, block-wide, from global
+      // ---- heavy chunk: one state at a time, block-wide
       for (int j = 0; j < ns; ++j) {
         const int s = s0 + j;
-        const int b0 = L.out_ptr[s], b1 = L.out_ptr[s + 1];
+        const int b0 = out_ptr[s], b1 = out_ptr[s + 1];
         ST am = 0;
         if (POST) am = alpha[s] - lz;
         ST m = neg_inf;
@@ -770,9 +585,9 @@ __global__ void __launch_bounds__(288, 3)
         float bt = kNegInf;
         int bi = 0x7fffffff;
         for (int a = b0 + tid; a < b1; a += NT) {
-          const int d = L.dst_out[a];
+          const int d = dst_out[a];
           int lab = 0;
-          if (need_label) lab = L.label_out[a];
+          if (need_label) lab = label_out[a];
           float w = SC ? arc_scores[a] : 0.0f;
           if (TH) w += th[lab];
           if (LOGS) {
@@ -821,10 +636,8 @@ __global__ void __launch_bounds__(288, 3)
         }
       }
     }
-    __syncthreads();  // results of chunk i visible to the block; its stage is free for chunk i+3
-    k0 = k1; k1 = k2; ka = kan;
-    if (++slot == kRing) { slot = 0; phase ^= 1; }
-    if (++slot_a == kRing) slot_a = 0;
+    __syncthreads();  // results of this chunk visible to the block
+    k0 = k1; k1 = k2; kp = kpn;
   }
 
   if (tid == 0) {
@@ -957,7 +770,7 @@ int launch_fwd2(const nfst_packed_lattices_t* lat, const nfst_launch_t* launch, 
   const int theta_smem = TH && lat->vocab <= NFST_THETA_SMEM_MAX;
   const size_t bytes = nfst_launch_smem_bytes(launch, lat->vocab, 0, 1, 0, 0, SC, TH, 0);
   if (int rc = prepare_smem(nfst_fwd_kernel<ST, SC, TH>, bytes)) return rc;
-  nfst_fwd_kernel<ST, SC, TH><<<launch->n_ids, launch->block_threads + 32, bytes, st>>>(
+  nfst_fwd_kernel<ST, SC, TH><<<launch->n_ids, launch->block_threads, bytes, st>>>(
       *lat, launch->lattice_ids, launch->window_states, launch->chunk_cap, scores->arc_scores, scores->theta,
       theta_smem, static_cast<ST*>(alpha), static_cast<ST*>(logz));
   NFST_CUDA_OK(cudaGetLastError());
@@ -982,7 +795,7 @@ int launch_bwd3(const nfst_packed_lattices_t* lat, const nfst_launch_t* launch, 
   const int dtheta_smem = POST && dtheta && small_v;
   const size_t bytes = nfst_launch_smem_bytes(launch, lat->vocab, 1, LOGS, TROP, POST, SC, TH, POST && dtheta != nullptr);
   if (int rc = prepare_smem(nfst_bwd_kernel<ST, LOGS, TROP, SC, TH, POST>, bytes)) return rc;
-  nfst_bwd_kernel<ST, LOGS, TROP, SC, TH, POST><<<launch->n_ids, launch->block_threads + 32, bytes, st>>>(
+  nfst_bwd_kernel<ST, LOGS, TROP, SC, TH, POST><<<launch->n_ids, launch->block_threads, bytes, st>>>(
       *lat, launch->lattice_ids, launch->window_states, launch->chunk_cap, scores->arc_scores, scores->theta,
       theta_smem, dtheta_smem,
       static_cast<const ST*>(alpha), static_cast<const ST*>(logz), grad_logz, static_cast<ST*>(beta),
@@ -1016,6 +829,17 @@ extern "C" {
 
 int nfst_abi_version(void) { return NFST_ABI_VERSION; }
 
+#ifdef NFST_TIMING
+int nfst_debug_read(unsigned long long* out, int reset) {
+  cudaMemcpyFromSymbol(out, g_dbg, sizeof(unsigned long long) * 32);
+  if (reset) {
+    unsigned long long z[32] = {0};
+    cudaMemcpyToSymbol(g_dbg, z, sizeof(z));
+  }
+  return 0;
+}
+#endif
+
 const char* nfst_last_error_string(void) { return g_last_error.c_str(); }
 
 int nfst_device_info(int device, int* sm_count, int* cc_major, int* cc_minor, size_t* max_smem_optin) {
@@ -1036,11 +860,10 @@ size_t nfst_launch_smem_bytes(const nfst_launch_t* launch, int32_t vocab, int pa
   if (!launch) return 0;
   const bool small_v = vocab <= NFST_THETA_SMEM_MAX;
   (void)with_post;
+  (void)with_scores;
   const bool bwd = pass != 0;
-  const SmemPlan p = smem_plan(launch->window_states, launch->chunk_cap,
-                               launch->state_f64 ? 8 : 4, vocab, !bwd || with_log != 0, bwd && with_trop != 0,
-                               with_scores != 0, with_theta != 0 || (bwd && with_dtheta != 0), with_theta && small_v,
-                               bwd && with_dtheta && small_v, bwd ? 3 : 4, !bwd);
+  const SmemPlan p = smem_plan(launch->window_states, launch->state_f64 ? 8 : 4, vocab, !bwd || with_log != 0,
+                               bwd && with_trop != 0, with_theta && small_v, bwd && with_dtheta && small_v);
   return p.bytes;
 }
 

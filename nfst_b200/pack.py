@@ -31,7 +31,7 @@ import torch
 from . import _lib
 
 # shared-memory window of the most recent per-state DP values, in bytes per state vector
-WINDOW_BYTES_MAX = 64 * 1024
+WINDOW_BYTES_MAX = int(os.environ.get("NFST_WINDOW_BYTES", str(64 * 1024)))
 # chunk geometry (tunable): a chunk targets ARCS_PER_THREAD arcs per thread of a block of at
 # most BLOCK_MAX threads; a state with more than target/HEAVY_DIV arcs gets a chunk of its own
 BLOCK_MAX = int(os.environ.get("NFST_BLOCK_MAX", "256"))
