@@ -51,6 +51,9 @@ int fail(int code, const char* fmt, ...) {
   } while (0)
 
 constexpr float kNegInf = -__builtin_huge_valf();
+#ifndef NFST_MIN_BLOCKS
+#define NFST_MIN_BLOCKS 3  // resident blocks per SM the register allocation aims for
+#endif
 
 __device__ __forceinline__ int4 chunk_at(const nfst_chunk_t* c, int i, int end) {
   return i < end ? __ldg(reinterpret_cast<const int4*>(c + i)) : make_int4(0, 0, 0, 0);
@@ -110,18 +113,31 @@ __device__ ST block_lse(ST m, float s) {
 }
 
 // ---- shared memory carve-up (identical on host and device), offsets in bytes ----------
-// [window ST[W]] [delta window f32[W]] [theta f32[V]] [dtheta f32[V]]
+// [window ST[W]] [delta window f32[W]] [2 stages x {nbr int[cap+8], aux int[cap+8], lab int[cap+8],
+// ptr int[cap+8]}] [theta f32[V]] [dtheta f32[V]]
 struct SmemPlan {
-  size_t win, dwin, theta, dtheta, bytes;
+  size_t win, dwin, stage0, stage_bytes, nbr, aux, wsc, lab, ptr, theta, dtheta, bytes;
 };
-__host__ __device__ inline SmemPlan smem_plan(int W, int st_bytes, int vocab, bool logs, bool trop, bool with_theta,
-                                              bool with_dtheta) {
+__host__ __device__ inline SmemPlan smem_plan(int W, int cap, int st_bytes, int vocab, bool logs, bool trop,
+                                              bool with_scores, bool with_labels, bool with_theta, bool with_dtheta,
+                                              int n_stages = 2, bool gathered_scores = false) {
   SmemPlan p;
   size_t o = 0;
+  const size_t arr = static_cast<size_t>(cap + 8) * 4;
   p.win = o;
   o += logs ? static_cast<size_t>(W) * st_bytes : 0;
   p.dwin = o;
   o += trop ? static_cast<size_t>(W) * 4 : 0;
+  o = (o + 15) & ~static_cast<size_t>(15);
+  p.stage0 = o;
+  size_t q = 0;
+  p.nbr = q; q += arr;                      // neighbour state of every arc (src_in / dst_out)
+  p.aux = q; q += with_scores ? arr : 0;    // forward: in2out index; backward: the score itself
+  p.wsc = p.aux; (void)gathered_scores;      // forward: scores are gathered IN PLACE over their indices
+  p.lab = q; q += with_labels ? arr : 0;
+  p.ptr = q; q += arr;                      // CSR row pointers of the chunk's states
+  p.stage_bytes = q;
+  o += static_cast<size_t>(n_stages) * q;
   p.theta = o;
   o += with_theta ? static_cast<size_t>(vocab) * 4 : 0;
   p.dtheta = o;
@@ -182,20 +198,66 @@ __device__ __forceinline__ ST lse_finish(ST m, float s, ST neg_inf) {
   return (m > static_cast<ST>(kFloor)) ? m + static_cast<ST>(lg2_approx(s) * kLn2) : neg_inf;
 }
 
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+  const unsigned sa = static_cast<unsigned>(__cvta_generic_to_shared(smem));
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async4(void* smem, const void* gmem) {
+  const unsigned sa = static_cast<unsigned>(__cvta_generic_to_shared(smem));
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(sa), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
 
 // All dynamic shared memory is addressed as 32-bit words off one typed extern array (keeps
 // the accesses in the shared address space for the compiler: plain LDS/STS with immediate
 // offsets, no generic-pointer conversions in the loops).
 extern __shared__ __align__(16) float smem_f[];
 
-// pull [p, p + bytes) into L2 (no shared memory, no registers, no completion to wait for)
-__device__ __forceinline__ void l2_prefetch(const void* p, long long bytes) {
-  if (bytes <= 0) return;
-  const unsigned long long a = reinterpret_cast<unsigned long long>(p);
-  const unsigned long long a16 = a & ~15ULL;
-  const unsigned n = static_cast<unsigned>((a + bytes - a16 + 15) & ~15ULL);
-  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a16), "r"(n) : "memory");
+// Stage the arc arrays and row pointers of chunk k into the stage at word offset `st`
+// (16-byte cp.async copies, all threads).  Copies start at the 4-aligned position below the
+// chunk and may run a few elements past it; the arrays are zero-padded, so whatever is
+// over-read is a valid index.
+template <bool AUX, bool LAB>
+__device__ __forceinline__ void stage_chunk(const int4& k, int cap, int st, const SmemPlan& plan,
+                                            const int32_t* __restrict__ nbr, const void* __restrict__ aux,
+                                            const int32_t* __restrict__ lab, const int32_t* __restrict__ ptr) {
+  if (k.w > k.z && k.y - k.x <= cap) {
+    const int base4 = k.x & ~3;
+    const int n4 = (k.y - base4 + 3) >> 2;
+    float* s_nbr = smem_f + st + plan.nbr / 4;
+    float* s_aux = smem_f + st + plan.aux / 4;
+    float* s_lab = smem_f + st + plan.lab / 4;
+    float* s_ptr = smem_f + st + plan.ptr / 4;
+    for (int i = threadIdx.x; i < n4; i += blockDim.x) {
+      cp_async16(s_nbr + 4 * i, nbr + base4 + 4 * i);
+      if (AUX) cp_async16(s_aux + 4 * i, static_cast<const int32_t*>(aux) + base4 + 4 * i);
+      if (LAB) cp_async16(s_lab + 4 * i, lab + base4 + 4 * i);
+    }
+    const int pb = k.z & ~3;
+    const int p4 = (k.w + 1 - pb + 3) >> 2;
+    for (int i = threadIdx.x; i < p4; i += blockDim.x) cp_async16(s_ptr + 4 * i, ptr + pb + 4 * i);
+  }
 }
+
+// Gather the scores of a staged chunk through its staged index array, straight into shared
+// memory (4-byte cp.async, no registers): scores[idx[pos]] -> wsc[pos] for every staged slot.
+__device__ __forceinline__ void gather_scores(const int4& k, int cap, int st, const SmemPlan& plan,
+                                              const float* __restrict__ scores) {
+  if (k.w > k.z && k.y - k.x <= cap) {
+    const int n_slots = ((k.y - (k.x & ~3) + 3) >> 2) << 2;
+    const int* s_idx = reinterpret_cast<const int*>(smem_f + st + plan.aux / 4);
+    float* s_w = smem_f + st + plan.wsc / 4;
+    // in place: each slot's index is read (LDS) before the copy that overwrites it is issued
+    for (int i = threadIdx.x; i < n_slots; i += blockDim.x) cp_async4(s_w + i, scores + s_idx[i]);
+  }
+}
+
+// rare path: a neighbour older than the shared-memory window (kept out of line so that the
+// hot loops carry no 64-bit address arithmetic)
+template <typename T>
+__device__ __noinline__ T load_behind_window(const T* p, int i) { return p[i]; }
+
 // ---- optional per-phase cycle counters (build with -DNFST_TIMING; see tools/phase_timing.py)
 #ifdef NFST_TIMING
 __device__ unsigned long long g_dbg[32];
@@ -207,32 +269,22 @@ __device__ unsigned long long g_dbg[32];
 #define NFST_ACC(cond, slot, cycles) do {} while (0)
 #endif
 
-// rare path: a neighbour older than the shared-memory window (kept out of line so that the
-// hot loops carry no 64-bit address arithmetic)
-template <typename T>
-__device__ __noinline__ T load_behind_window(const T* p, int i) { return p[i]; }
-
 // =====================================================================================
 // forward: alpha
 // =====================================================================================
-// One block per lattice, one chunk (a run of states of one level) per iteration, one barrier per
-// chunk.  Nothing is staged: one lane prefetches the arrays of the chunk kPrefetch iterations
-// ahead into L2 (and the region of the score array that chunk gathers from), the threads then
-// read their arcs straight from global memory (L2 / L1 hits).  Shared memory only holds the
-// window of recent DP values, so many blocks -- ideally every lattice of the batch -- are
-// resident at once and hide each other's latency.
 // SC: per-arc scores given; TH: theta[label] given (at least one of them).
-constexpr int kPrefetch = 6;  // L2 prefetch distance, in chunks
-
 template <typename ST, bool SC, bool TH>
-__global__ void __launch_bounds__(256, 4)
+__global__ void __launch_bounds__(256, NFST_MIN_BLOCKS)
     nfst_fwd_kernel(const nfst_packed_lattices_t L, const int32_t* __restrict__ ids, int W, int cap,
                     const float* __restrict__ arc_scores, const float* __restrict__ theta, int theta_smem, ST* alpha,
                     ST* __restrict__ logz) {
   const int NT = blockDim.x, tid = threadIdx.x;
-  const SmemPlan plan = smem_plan(W, sizeof(ST), L.vocab, true, false, theta_smem != 0, false);
+  const SmemPlan plan = smem_plan(W, cap, sizeof(ST), L.vocab, true, false, SC, TH, theta_smem != 0, false, 3, true);
   ST* const win = reinterpret_cast<ST*>(smem_f + plan.win / 4);
   const ST neg_inf = static_cast<ST>(kNegInf);
+  const int stage0 = static_cast<int>(plan.stage0 / 4), stage_words = static_cast<int>(plan.stage_bytes / 4);
+  const int o_nbr = static_cast<int>(plan.nbr / 4), o_wsc = static_cast<int>(plan.wsc / 4),
+            o_lab = static_cast<int>(plan.lab / 4), o_ptr = static_cast<int>(plan.ptr / 4);
 
   const int b = ids ? ids[blockIdx.x] : blockIdx.x;
   const int base_s = L.state_off[b];
@@ -246,44 +298,41 @@ __global__ void __launch_bounds__(256, 4)
     th = sth;
   }
 
-  const nfst_chunk_t* chunks = L.fwd_chunks + L.fwd_chunk_off[b];
-  const int n_chunks = L.fwd_chunk_off[b + 1] - L.fwd_chunk_off[b];
-  const int2* gat = reinterpret_cast<const int2*>(L.fwd_gather) + L.fwd_chunk_off[b];
-  const int32_t* __restrict__ in_ptr = L.in_ptr;
-  const int32_t* __restrict__ src_in = L.src_in;
-  const int32_t* __restrict__ in2out = L.in2out;
-  const int32_t* __restrict__ label_in = L.label_in;
+  const nfst_chunk_t* chunks = L.fwd_chunks;
+  int c = L.fwd_chunk_off[b];
+  const int c_end = L.fwd_chunk_off[b + 1];
 
-  auto prefetch = [&](const int4& k, const int2& g) {  // one lane; (k, g) were loaded an iteration ago
-    if (k.w > k.z) {
-      const long long nb = static_cast<long long>(k.y - k.x) * 4;
-      l2_prefetch(src_in + k.x, nb);
-      if (SC) l2_prefetch(in2out + k.x, nb);
-      if (TH) l2_prefetch(label_in + k.x, nb);
-      l2_prefetch(in_ptr + k.z, static_cast<long long>(k.w - k.z + 1) * 4);
-      if (SC) l2_prefetch(arc_scores + g.x, static_cast<long long>(g.y - g.x) * 4);
-    }
-  };
-  auto gather_range = [&](int j) { return (SC && j < n_chunks) ? __ldg(gat + j) : make_int2(0, 0); };
-  if (tid == 0)
-    for (int j = 0; j < kPrefetch; ++j) prefetch(chunk_at(chunks, j, n_chunks), gather_range(j));
-  int4 k0 = chunk_at(chunks, 0, n_chunks), k1 = chunk_at(chunks, 1, n_chunks);
-  int4 kp = chunk_at(chunks, kPrefetch, n_chunks);
-  int2 gp = gather_range(kPrefetch);
+  // Three-stage software pipeline, all through cp.async (no staging registers):
+  //   chunk c   : arc arrays + gathered scores resident  -> reduced now
+  //   chunk c+1 : arc arrays resident                     -> its scores are gathered now (4 B copies)
+  //   chunk c+2 :                                            its arc arrays stream in now (16 B copies)
+  int4 k0 = chunk_at(chunks, c, c_end), k1 = chunk_at(chunks, c + 1, c_end), k2 = chunk_at(chunks, c + 2, c_end);
+  int s_cur = stage0, s_nxt = stage0 + stage_words, s_nn = stage0 + 2 * stage_words;
+  stage_chunk<SC, TH>(k0, cap, s_cur, plan, L.src_in, L.in2out, L.label_in, L.in_ptr);
+  stage_chunk<SC, TH>(k1, cap, s_nxt, plan, L.src_in, L.in2out, L.label_in, L.in_ptr);
+  cp_async_commit();
+  cp_async_wait_all();
+  __syncthreads();
+  if (SC) gather_scores(k0, cap, s_cur, plan, arc_scores);
+  cp_async_commit();
+  cp_async_wait_all();
   __syncthreads();
 
 #pragma unroll 1
-  for (int it = 0; it < n_chunks; ++it) {
-    const int4 k2 = chunk_at(chunks, it + 2, n_chunks);
-    int4 kpn = make_int4(0, 0, 0, 0);
-    int2 gpn = make_int2(0, 0);
-    if (tid == 0) {
-      kpn = chunk_at(chunks, it + 1 + kPrefetch, n_chunks);
-      gpn = gather_range(it + 1 + kPrefetch);
-      prefetch(kp, gp);
-    }
-    const int a1 = k0.y, s0 = k0.z, s1 = k0.w;
-    const int n = a1 - k0.x, ns = s1 - s0;
+  for (; c < c_end; ++c) {
+    const int4 k3 = chunk_at(chunks, c + 3, c_end);  // descriptors run ahead of their use
+    stage_chunk<SC, TH>(k2, cap, s_nn, plan, L.src_in, L.in2out, L.label_in, L.in_ptr);
+    if (SC) gather_scores(k1, cap, s_nxt, plan, arc_scores);
+    cp_async_commit();
+    const int* s_src = reinterpret_cast<const int*>(smem_f + s_cur + o_nbr);
+    const float* s_w = smem_f + s_cur + o_wsc;
+    const int* s_lab = reinterpret_cast<const int*>(smem_f + s_cur + o_lab);
+
+    const int a0 = k0.x, a1 = k0.y, s0 = k0.z, s1 = k0.w;
+    const int n = a1 - a0, ns = s1 - s0;
+    const int base4 = a0 & ~3;
+    // row pointers relative to the stage arrays
+    const int* s_ptr = reinterpret_cast<const int*>(smem_f + s_cur + o_ptr) + (s0 & 3);
     // readable window: states [s1 - W, s0).  The slots of [s0 - W, s1 - W) are being
     // overwritten by this chunk's own results, so those states are re-read from global.
     const int lo = whole ? static_cast<int>(0x80000000) : s1 - W;
@@ -291,27 +340,27 @@ __global__ void __launch_bounds__(256, 4)
       if (src >= lo) return win[(src - base_s) & wmask];
       return load_behind_window(alpha, src);
     };
-    auto arc_value = [&](int a) -> ST {
-      float w = SC ? __ldg(arc_scores + __ldg(in2out + a)) : 0.0f;
-      if (TH) w += th[__ldg(label_in + a)];
-      return value_of(__ldg(src_in + a)) + static_cast<ST>(w);
+    auto arc_value = [&](int i) -> ST {
+      float w = SC ? s_w[i] : 0.0f;
+      if (TH) w += th[s_lab[i]];
+      return value_of(s_src[i]) + static_cast<ST>(w);
     };
     if (n <= cap) {
       if (ns * 2 > NT) {
-        // ---- wide chunk: one thread per state
+        // ---- wide chunk: one thread per state, arcs straight from the staged arrays
 #pragma unroll 1
         for (int j = tid; j < ns; j += NT) {
-          int a = __ldg(in_ptr + s0 + j);
-          const int b1 = __ldg(in_ptr + s0 + j + 1);
+          int i = s_ptr[j] - base4;
+          const int b1 = s_ptr[j + 1] - base4;
           ST m = static_cast<ST>(kFloor);
           float sum = 0.0f;
 #pragma unroll 1
-          for (; a + 3 < b1; a += 4) {  // 4 arcs per trip: independent loads first
-            const ST v0 = arc_value(a), v1 = arc_value(a + 1), v2 = arc_value(a + 2), v3 = arc_value(a + 3);
+          for (; i + 3 < b1; i += 4) {  // 4 arcs per trip: independent loads first
+            const ST v0 = arc_value(i), v1 = arc_value(i + 1), v2 = arc_value(i + 2), v3 = arc_value(i + 3);
             lse_push4(m, sum, v0, v1, v2, v3);
           }
 #pragma unroll 1
-          for (; a < b1; ++a) lse_push(m, sum, arc_value(a), neg_inf);
+          for (; i < b1; ++i) lse_push(m, sum, arc_value(i), neg_inf);
           const int s = s0 + j;
           const ST v = (s == start) ? static_cast<ST>(0) : lse_finish(m, sum, neg_inf);
           if (s >= s1 - W) win[(s - base_s) & wmask] = v;  // only the newest W states own a slot
@@ -326,11 +375,11 @@ __global__ void __launch_bounds__(256, 4)
         for (int jb = 0; jb < ns; jb += ngrp) {
           const int j = jb + (tid >> lg);
           const bool valid = j < ns;
-          const int b0 = valid ? __ldg(in_ptr + s0 + j) : 0, b1 = valid ? __ldg(in_ptr + s0 + j + 1) : 0;
+          const int b0 = valid ? s_ptr[j] - base4 : 0, b1 = valid ? s_ptr[j + 1] - base4 : 0;
           ST m = static_cast<ST>(kFloor);
           float sum = 0.0f;
 #pragma unroll 1
-          for (int a = b0 + lane_g; a < b1; a += G) lse_push(m, sum, arc_value(a), neg_inf);
+          for (int i = b0 + lane_g; i < b1; i += G) lse_push(m, sum, arc_value(i), neg_inf);
           for (int o = G >> 1; o > 0; o >>= 1) {
             const ST m2 = __shfl_xor_sync(0xffffffffu, m, o);
             const float s2 = __shfl_xor_sync(0xffffffffu, sum, o);
@@ -345,13 +394,18 @@ __global__ void __launch_bounds__(256, 4)
         }
       }
     } else {
-      // ---- heavy chunk (a state with more than `cap` incoming arcs): block-wide
+      // ---- oversize chunk (a state with more than `cap` incoming arcs): block-wide, from global
       for (int j = 0; j < ns; ++j) {
         const int s = s0 + j;
-        const int b0 = in_ptr[s], b1 = in_ptr[s + 1];
+        const int b0 = L.in_ptr[s], b1 = L.in_ptr[s + 1];
         ST m = neg_inf;
         float sum = 0.0f;
-        for (int a = b0 + tid; a < b1; a += NT) lse_add(m, sum, arc_value(a));
+        for (int a = b0 + tid; a < b1; a += NT) {
+          float w = 0.0f;
+          if (SC) w = arc_scores[L.in2out[a]];
+          if (TH) w += th[L.label_in[a]];
+          lse_add(m, sum, static_cast<ST>(w) + value_of(L.src_in[a]));
+        }
         const ST v0 = block_lse(m, sum);
         if (tid == 0) {
           const ST v = (s == start) ? static_cast<ST>(0) : v0;
@@ -360,8 +414,10 @@ __global__ void __launch_bounds__(256, 4)
         }
       }
     }
-    __syncthreads();  // alpha of this chunk visible to the block
-    k0 = k1; k1 = k2; kp = kpn; gp = gpn;
+    cp_async_wait_all();
+    __syncthreads();  // alpha of chunk c visible; scores of c+1 and arrays of c+2 landed; stage of c free
+    k0 = k1; k1 = k2; k2 = k3;
+    const int t = s_cur; s_cur = s_nxt; s_nxt = s_nn; s_nn = t;
   }
 
   // logZ = logsumexp over the sinks of alpha (every zero-out-degree state has beta = 1,
@@ -378,7 +434,7 @@ __global__ void __launch_bounds__(256, 4)
 // =====================================================================================
 // LOGS / TROP: semirings; SC / TH: score sources; POST: posteriors (post and/or dtheta).
 template <typename ST, bool LOGS, bool TROP, bool SC, bool TH, bool POST>
-__global__ void __launch_bounds__(256, 4)
+__global__ void __launch_bounds__(256, NFST_MIN_BLOCKS)
     nfst_bwd_kernel(const nfst_packed_lattices_t L, const int32_t* __restrict__ ids, int W, int cap,
                     const float* __restrict__ arc_scores, const float* __restrict__ theta, int theta_smem,
                     int dtheta_smem, const ST* __restrict__ alpha, const ST* __restrict__ logz,
@@ -388,10 +444,14 @@ __global__ void __launch_bounds__(256, 4)
   const int NT = blockDim.x, tid = threadIdx.x;
   const bool want_hist = POST && dtheta != nullptr;
   const bool need_label = TH || want_hist;
-  const SmemPlan plan = smem_plan(W, sizeof(ST), L.vocab, LOGS, TROP, theta_smem != 0, dtheta_smem != 0);
+  const SmemPlan plan =
+      smem_plan(W, cap, sizeof(ST), L.vocab, LOGS, TROP, SC, need_label, theta_smem != 0, dtheta_smem != 0);
   ST* const win = reinterpret_cast<ST*>(smem_f + plan.win / 4);
   float* const dwin = smem_f + plan.dwin / 4;
   const ST neg_inf = static_cast<ST>(kNegInf);
+  const int stage0 = static_cast<int>(plan.stage0 / 4), stage_words = static_cast<int>(plan.stage_bytes / 4);
+  const int o_nbr = static_cast<int>(plan.nbr / 4), o_aux = static_cast<int>(plan.aux / 4),
+            o_lab = static_cast<int>(plan.lab / 4), o_ptr = static_cast<int>(plan.ptr / 4);
 
   const int b = ids ? ids[blockIdx.x] : blockIdx.x;
   const int base_s = L.state_off[b];
@@ -419,37 +479,35 @@ __global__ void __launch_bounds__(256, 4)
     if (grad_logz) gscale = grad_logz[b];
   }
 
-  const nfst_chunk_t* chunks = L.bwd_chunks + L.bwd_chunk_off[b];
-  const int n_chunks = L.bwd_chunk_off[b + 1] - L.bwd_chunk_off[b];
-  const int32_t* __restrict__ out_ptr = L.out_ptr;
-  const int32_t* __restrict__ dst_out = L.dst_out;
-  const int32_t* __restrict__ label_out = L.label_out;
+  const nfst_chunk_t* chunks = L.bwd_chunks;
+  int c = L.bwd_chunk_off[b];
+  const int c_end = L.bwd_chunk_off[b + 1];
+  const int32_t* lab_arr = need_label ? L.label_out : nullptr;
 
-  auto prefetch = [&](const int4& k) {  // one lane; k loaded an iteration ago
-    if (k.w > k.z) {
-      const long long nb = static_cast<long long>(k.y - k.x) * 4;
-      l2_prefetch(dst_out + k.x, nb);
-      if (SC) l2_prefetch(arc_scores + k.x, nb);
-      if (need_label) l2_prefetch(label_out + k.x, nb);
-      l2_prefetch(out_ptr + k.z, static_cast<long long>(k.w - k.z + 1) * 4);
-      if (POST) l2_prefetch(alpha + k.z, static_cast<long long>(k.w - k.z) * sizeof(ST));
-    }
+  int4 k0 = chunk_at(chunks, c, c_end), k1 = chunk_at(chunks, c + 1, c_end);
+  int s_cur = stage0, s_nxt = stage0 + stage_words;
+  auto stage_in = [&](const int4& k, int st) {
+    if (need_label) stage_chunk<SC, true>(k, cap, st, plan, L.dst_out, arc_scores, lab_arr, L.out_ptr);
+    else stage_chunk<SC, false>(k, cap, st, plan, L.dst_out, arc_scores, lab_arr, L.out_ptr);
   };
-  if (tid == 0)
-    for (int j = 0; j < kPrefetch; ++j) prefetch(chunk_at(chunks, j, n_chunks));
-  int4 k0 = chunk_at(chunks, 0, n_chunks), k1 = chunk_at(chunks, 1, n_chunks), kp = chunk_at(chunks, kPrefetch, n_chunks);
+  stage_in(k0, s_cur);
+  cp_async_commit();
+  cp_async_wait_all();
   __syncthreads();
 
 #pragma unroll 1
-  for (int it = 0; it < n_chunks; ++it) {
-    const int4 k2 = chunk_at(chunks, it + 2, n_chunks);
-    int4 kpn = make_int4(0, 0, 0, 0);
-    if (tid == 0) {
-      kpn = chunk_at(chunks, it + 1 + kPrefetch, n_chunks);
-      prefetch(kp);
-    }
-    const int a1 = k0.y, s0 = k0.z, s1 = k0.w;
-    const int n = a1 - k0.x, ns = s1 - s0;
+  for (; c < c_end; ++c) {
+    const int4 k2 = chunk_at(chunks, c + 2, c_end);
+    stage_in(k1, s_nxt);
+    cp_async_commit();
+    const int* s_dst = reinterpret_cast<const int*>(smem_f + s_cur + o_nbr);
+    const float* s_w = smem_f + s_cur + o_aux;
+    const int* s_lab = reinterpret_cast<const int*>(smem_f + s_cur + o_lab);
+
+    const int a0 = k0.x, a1 = k0.y, s0 = k0.z, s1 = k0.w;
+    const int n = a1 - a0, ns = s1 - s0;
+    const int base4 = a0 & ~3;
+    const int* s_ptr = reinterpret_cast<const int*>(smem_f + s_cur + o_ptr) + (s0 & 3);
     // readable window: states [s1, s0 + W) (see the forward kernel)
     const int hi = whole ? 0x7fffffff : s0 + W;
     auto beta_of = [&](int d) -> ST {
@@ -460,41 +518,41 @@ __global__ void __launch_bounds__(256, 4)
       if (d < hi) return dwin[(d - base_s) & wmask];
       return load_behind_window(delta, d);
     };
-    // one arc: log-semiring push (+ posterior) and/or tropical candidate
-    auto visit = [&](int a, ST am, ST& m, float& sum, float& bt, int& bi) {
-      const int d = __ldg(dst_out + a);
-      float w = SC ? __ldg(arc_scores + a) : 0.0f;
+    // one arc of the staged chunk: log-semiring push (+ posterior) and/or tropical candidate
+    auto visit = [&](int i, ST am, ST& m, float& sum, float& bt, int& bi) {
+      const int d = s_dst[i];
+      float w = SC ? s_w[i] : 0.0f;
       int lab = 0;
-      if (TH || POST) { if (need_label) lab = __ldg(label_out + a); }
+      if (TH || POST) { if (need_label) lab = s_lab[i]; }
       if (TH) w += th[lab];
       if (LOGS) {
         const ST u = static_cast<ST>(w) + beta_of(d);
         lse_push(m, sum, u, neg_inf);
         if (POST) {
           const float p = ex2_approx(static_cast<float>(am + u) * kLog2e) * gscale;
-          if (post) post[a] = p;
+          if (post) post[base4 + i] = p;
           if (hist) atomicAdd(&hist[lab], p);
         }
       }
       if (TROP) {
         const float t = __fadd_rn(w, delta_of(d));
-        if (t > bt) { bt = t; bi = a; }  // strict: within a lane arcs come in label order
+        if (t > bt) { bt = t; bi = i; }  // strict: within a lane arcs come in label order
       }
     };
     // four consecutive arcs of one state: independent loads and exps (see lse_push4)
-    auto visit4 = [&](int a, ST am, ST& m, float& sum, float& bt, int& bi) {
+    auto visit4 = [&](int i, ST am, ST& m, float& sum, float& bt, int& bi) {
       ST u[4];
       int lab[4] = {0, 0, 0, 0};
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        const int d = __ldg(dst_out + a + k);
-        float w = SC ? __ldg(arc_scores + a + k) : 0.0f;
-        if (TH || POST) { if (need_label) lab[k] = __ldg(label_out + a + k); }
+        const int d = s_dst[i + k];
+        float w = SC ? s_w[i + k] : 0.0f;
+        if (TH || POST) { if (need_label) lab[k] = s_lab[i + k]; }
         if (TH) w += th[lab[k]];
         if (LOGS) u[k] = static_cast<ST>(w) + beta_of(d);
         if (TROP) {
           const float t = __fadd_rn(w, delta_of(d));
-          if (t > bt) { bt = t; bi = a + k; }
+          if (t > bt) { bt = t; bi = i + k; }
         }
       }
       if (LOGS) {
@@ -503,7 +561,7 @@ __global__ void __launch_bounds__(256, 4)
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
             const float p = ex2_approx(static_cast<float>(am + u[k]) * kLog2e) * gscale;
-            if (post) post[a + k] = p;
+            if (post) post[base4 + i + k] = p;
             if (hist) atomicAdd(&hist[lab[k]], p);
           }
         }
@@ -520,25 +578,25 @@ __global__ void __launch_bounds__(256, 4)
         const float v = sink ? 0.0f : bt;
         if (s < s0 + W) dwin[(s - base_s) & wmask] = v;
         delta[s] = v;
-        backptr[s] = sink ? -1 : bi;
+        backptr[s] = sink ? -1 : base4 + bi;
       }
     };
     if (n <= cap) {
       if (ns * 2 > NT) {
 #pragma unroll 1
         for (int j = tid; j < ns; j += NT) {
-          const int b0 = __ldg(out_ptr + s0 + j), b1 = __ldg(out_ptr + s0 + j + 1);
+          const int b0 = s_ptr[j] - base4, b1 = s_ptr[j + 1] - base4;
           const int s = s0 + j;
           ST am = 0;
           if (POST) am = alpha[s] - lz;  // issued before the arc loop, consumed inside it
           ST m = static_cast<ST>(kFloor);
           float sum = 0.0f, bt = kNegInf;
           int bi = 0x7fffffff;
-          int a = b0;
+          int i = b0;
 #pragma unroll 1
-          for (; a + 3 < b1; a += 4) visit4(a, am, m, sum, bt, bi);
+          for (; i + 3 < b1; i += 4) visit4(i, am, m, sum, bt, bi);
 #pragma unroll 1
-          for (; a < b1; ++a) visit(a, am, m, sum, bt, bi);
+          for (; i < b1; ++i) visit(i, am, m, sum, bt, bi);
           finish(s, b0 == b1, m, sum, bt, bi);
         }
       } else {
@@ -549,7 +607,7 @@ __global__ void __launch_bounds__(256, 4)
         for (int jb = 0; jb < ns; jb += ngrp) {
           const int j = jb + (tid >> lg);
           const bool valid = j < ns;
-          const int b0 = valid ? __ldg(out_ptr + s0 + j) : 0, b1 = valid ? __ldg(out_ptr + s0 + j + 1) : 0;
+          const int b0 = valid ? s_ptr[j] - base4 : 0, b1 = valid ? s_ptr[j + 1] - base4 : 0;
           const int s = s0 + j;
           ST am = 0;
           if (POST && valid) am = alpha[s] - lz;
@@ -557,7 +615,7 @@ __global__ void __launch_bounds__(256, 4)
           float sum = 0.0f, bt = kNegInf;
           int bi = 0x7fffffff;
 #pragma unroll 1
-          for (int a = b0 + lane_g; a < b1; a += G) visit(a, am, m, sum, bt, bi);
+          for (int i = b0 + lane_g; i < b1; i += G) visit(i, am, m, sum, bt, bi);
           for (int o = G >> 1; o > 0; o >>= 1) {
             if (LOGS) {
               const ST m2 = __shfl_xor_sync(0xffffffffu, m, o);
@@ -574,10 +632,10 @@ __global__ void __launch_bounds__(256, 4)
         }
       }
     } else {
-      // ---- heavy chunk: one state at a time, block-wide
+      // ---- oversize chunk: one state at a time, block-wide, from global
       for (int j = 0; j < ns; ++j) {
         const int s = s0 + j;
-        const int b0 = out_ptr[s], b1 = out_ptr[s + 1];
+        const int b0 = L.out_ptr[s], b1 = L.out_ptr[s + 1];
         ST am = 0;
         if (POST) am = alpha[s] - lz;
         ST m = neg_inf;
@@ -585,9 +643,9 @@ __global__ void __launch_bounds__(256, 4)
         float bt = kNegInf;
         int bi = 0x7fffffff;
         for (int a = b0 + tid; a < b1; a += NT) {
-          const int d = dst_out[a];
+          const int d = L.dst_out[a];
           int lab = 0;
-          if (need_label) lab = label_out[a];
+          if (need_label) lab = L.label_out[a];
           float w = SC ? arc_scores[a] : 0.0f;
           if (TH) w += th[lab];
           if (LOGS) {
@@ -636,8 +694,10 @@ __global__ void __launch_bounds__(256, 4)
         }
       }
     }
-    __syncthreads();  // results of this chunk visible to the block
-    k0 = k1; k1 = k2; kp = kpn;
+    cp_async_wait_all();
+    __syncthreads();
+    k0 = k1; k1 = k2;
+    const int t = s_cur; s_cur = s_nxt; s_nxt = t;
   }
 
   if (tid == 0) {
@@ -860,10 +920,11 @@ size_t nfst_launch_smem_bytes(const nfst_launch_t* launch, int32_t vocab, int pa
   if (!launch) return 0;
   const bool small_v = vocab <= NFST_THETA_SMEM_MAX;
   (void)with_post;
-  (void)with_scores;
   const bool bwd = pass != 0;
-  const SmemPlan p = smem_plan(launch->window_states, launch->state_f64 ? 8 : 4, vocab, !bwd || with_log != 0,
-                               bwd && with_trop != 0, with_theta && small_v, bwd && with_dtheta && small_v);
+  const SmemPlan p = smem_plan(launch->window_states, launch->chunk_cap,
+                               launch->state_f64 ? 8 : 4, vocab, !bwd || with_log != 0, bwd && with_trop != 0,
+                               with_scores != 0, with_theta != 0 || (bwd && with_dtheta != 0), with_theta && small_v,
+                               bwd && with_dtheta && small_v, bwd ? 2 : 3, !bwd);
   return p.bytes;
 }
 
