@@ -347,7 +347,8 @@ def main():
             # label arrays are not read when scores are per-arc; keep the resident ones
             kw.update(label_in=packed.label_in, label_out=packed.label_out, orig_state=packed.orig_state,
                       arc_origin=packed.arc_origin, arc_off=packed.arc_off, n_levels=packed.n_levels,
-                      level_off=packed.level_off, level_ptr=packed.level_ptr)
+                      level_off=packed.level_off, level_ptr=packed.level_ptr,
+                      fwd_chunk_level=packed.fwd_chunk_level, bwd_chunk_level=packed.bwd_chunk_level)
             groups = [dataclasses.replace(g, ids=d_) for g, d_ in zip(packed.groups, land_ids)]
             p = PackedLattices(n_lattices=B, n_states=S, n_arcs=A, vocab=packed.vocab, static_scores=None,
                                dense_shape=None, groups=groups, max_levels=packed.max_levels, stats=packed.stats, **kw)

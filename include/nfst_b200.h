@@ -41,7 +41,7 @@
 extern "C" {
 #endif
 
-#define NFST_ABI_VERSION 4
+#define NFST_ABI_VERSION 5
 
 typedef enum nfst_status {
   NFST_OK = 0,
@@ -119,6 +119,17 @@ typedef struct nfst_launch {
   int32_t window_states;
   int32_t state_f64;
   int32_t chunk_cap; /* multiple of 8; >= the largest staged chunk of the launch, in arcs and in states */
+  /* Level-major execution (for lattices with wide levels): when fwd_level_chunks / bwd_level_chunks
+   * are non-NULL the pass runs as ONE KERNEL LAUNCH PER TOPOLOGICAL LEVEL, one thread block per
+   * chunk, over the chunks of all lattices of the group, instead of one block per lattice.
+   * *_level_chunks: DEVICE arrays of the group's chunks sorted by level; *_level_off: HOST arrays
+   * [n_levels+1] of offsets into them; bwd_level_lat: DEVICE lattice id of every backward chunk. */
+  int32_t n_levels;
+  const nfst_chunk_t* fwd_level_chunks;
+  const int32_t* fwd_level_off;
+  const nfst_chunk_t* bwd_level_chunks;
+  const int32_t* bwd_level_off;
+  const int32_t* bwd_level_lat;
 } nfst_launch_t;
 
 /* Arc scores: w(a) = (arc_scores ? arc_scores[a] : 0) + (theta ? theta[label(a)] : 0);

@@ -55,6 +55,12 @@ class LaunchC(C.Structure):
         ("window_states", C.c_int32),
         ("state_f64", C.c_int32),
         ("chunk_cap", C.c_int32),
+        ("n_levels", C.c_int32),
+        ("fwd_level_chunks", C.c_void_p),
+        ("fwd_level_off", C.c_void_p),
+        ("bwd_level_chunks", C.c_void_p),
+        ("bwd_level_off", C.c_void_p),
+        ("bwd_level_lat", C.c_void_p),
     ]
 
 
@@ -106,7 +112,7 @@ def load() -> C.CDLL:
         fn = getattr(lib, name)  # AttributeError if the header and the library disagree
         fn.restype = res
         fn.argtypes = args
-    if lib.nfst_abi_version() != 4:
+    if lib.nfst_abi_version() != 5:
         raise RuntimeError("libnfst_b200.so ABI version mismatch")
     _lib = lib
     return lib

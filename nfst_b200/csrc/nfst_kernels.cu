@@ -714,6 +714,315 @@ __global__ void __launch_bounds__(256, NFST_MIN_BLOCKS)
 }
 
 // =====================================================================================
+// level-major kernels: one launch per topological level, one block per chunk of that level,
+// over ALL lattices of the launch group.  For lattices whose levels are wide (thousands of arcs)
+// this exposes every chunk of a level at once: no in-kernel barrier, no per-lattice serial
+// chain; the neighbour DP values were written by earlier launches and are read through L2/L1.
+// =====================================================================================
+template <typename ST, bool SC, bool TH>
+__global__ void __launch_bounds__(256, 4)
+    nfst_fwd_level_kernel(const nfst_packed_lattices_t L, const nfst_chunk_t* __restrict__ chunks, int cap,
+                          const float* __restrict__ arc_scores, const float* __restrict__ th,
+                          ST* __restrict__ alpha) {
+  const int NT = blockDim.x, tid = threadIdx.x;
+  const ST neg_inf = static_cast<ST>(kNegInf);
+  const int4 k = __ldg(reinterpret_cast<const int4*>(chunks) + blockIdx.x);
+  const int s0 = k.z, ns = k.w - k.z, n = k.y - k.x;
+  const int32_t* __restrict__ in_ptr = L.in_ptr;
+  const int32_t* __restrict__ src_in = L.src_in;
+  const int32_t* __restrict__ in2out = L.in2out;
+  const int32_t* __restrict__ label_in = L.label_in;
+  auto arc_value = [&](int a) -> ST {
+    float w = SC ? __ldg(arc_scores + __ldg(in2out + a)) : 0.0f;
+    if (TH) w += __ldg(th + __ldg(label_in + a));
+    return alpha[__ldg(src_in + a)] + static_cast<ST>(w);  // alpha of earlier levels: earlier launches
+  };
+  if (n <= cap) {
+    if (ns * 2 > NT) {
+#pragma unroll 1
+      for (int j = tid; j < ns; j += NT) {
+        int a = __ldg(in_ptr + s0 + j);
+        const int b1 = __ldg(in_ptr + s0 + j + 1);
+        ST m = static_cast<ST>(kFloor);
+        float sum = 0.0f;
+#pragma unroll 1
+        for (; a + 3 < b1; a += 4) {
+          const ST v0 = arc_value(a), v1 = arc_value(a + 1), v2 = arc_value(a + 2), v3 = arc_value(a + 3);
+          lse_push4(m, sum, v0, v1, v2, v3);
+        }
+#pragma unroll 1
+        for (; a < b1; ++a) lse_push(m, sum, arc_value(a), neg_inf);
+        alpha[s0 + j] = lse_finish(m, sum, neg_inf);
+      }
+    } else {
+      int lg = 1;
+      while (lg < 5 && (ns << (lg + 1)) <= NT) ++lg;
+      const int G = 1 << lg, lane_g = tid & (G - 1), ngrp = NT >> lg;
+#pragma unroll 1
+      for (int jb = 0; jb < ns; jb += ngrp) {
+        const int j = jb + (tid >> lg);
+        const bool valid = j < ns;
+        const int b0 = valid ? __ldg(in_ptr + s0 + j) : 0, b1 = valid ? __ldg(in_ptr + s0 + j + 1) : 0;
+        ST m = static_cast<ST>(kFloor);
+        float sum = 0.0f;
+#pragma unroll 1
+        for (int a = b0 + lane_g; a < b1; a += G) lse_push(m, sum, arc_value(a), neg_inf);
+        for (int o = G >> 1; o > 0; o >>= 1) {
+          const ST m2 = __shfl_xor_sync(0xffffffffu, m, o);
+          const float s2 = __shfl_xor_sync(0xffffffffu, sum, o);
+          lse_join(m, sum, m2, s2, neg_inf);
+        }
+        if (valid && lane_g == 0) alpha[s0 + j] = lse_finish(m, sum, neg_inf);
+      }
+    }
+  } else {
+    for (int j = 0; j < ns; ++j) {  // heavy chunk: block-wide
+      const int s = s0 + j;
+      const int b0 = in_ptr[s], b1 = in_ptr[s + 1];
+      ST m = neg_inf;
+      float sum = 0.0f;
+      for (int a = b0 + tid; a < b1; a += NT) lse_add(m, sum, arc_value(a));
+      const ST v0 = block_lse(m, sum);
+      if (tid == 0) alpha[s] = v0;
+    }
+  }
+}
+
+// alpha[start] = 0 before the level launches; logZ = logsumexp_{sinks} alpha after them
+template <typename ST>
+__global__ void nfst_fwd_init_kernel(const nfst_packed_lattices_t L, const int32_t* __restrict__ ids, int n,
+                                     ST* __restrict__ alpha) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) alpha[L.start_state[ids ? ids[i] : i]] = static_cast<ST>(0);
+}
+template <typename ST>
+__global__ void __launch_bounds__(128)
+    nfst_logz_kernel(const nfst_packed_lattices_t L, const int32_t* __restrict__ ids, const ST* __restrict__ alpha,
+                     ST* __restrict__ logz) {
+  const int b = ids ? ids[blockIdx.x] : blockIdx.x;
+  ST m = static_cast<ST>(kNegInf);
+  float sum = 0.0f;
+  for (int i = L.sink_off[b] + threadIdx.x; i < L.sink_off[b + 1]; i += blockDim.x) lse_add(m, sum, alpha[L.sinks[i]]);
+  const ST z = block_lse(m, sum);
+  if (threadIdx.x == 0) logz[b] = z;
+}
+
+template <typename ST, bool LOGS, bool TROP, bool SC, bool TH, bool POST>
+__global__ void __launch_bounds__(256, 4)
+    nfst_bwd_level_kernel(const nfst_packed_lattices_t L, const nfst_chunk_t* __restrict__ chunks,
+                          const int32_t* __restrict__ chunk_lat, int cap, const float* __restrict__ arc_scores,
+                          const float* __restrict__ th, int dtheta_smem, const ST* __restrict__ alpha,
+                          const ST* __restrict__ logz, const float* __restrict__ grad_logz, ST* __restrict__ beta,
+                          float* __restrict__ post, float* __restrict__ dtheta, float* __restrict__ delta,
+                          int32_t* __restrict__ backptr) {
+  const int NT = blockDim.x, tid = threadIdx.x;
+  const ST neg_inf = static_cast<ST>(kNegInf);
+  const bool want_hist = POST && dtheta != nullptr;
+  const bool need_label = TH || want_hist;
+  const int4 k = __ldg(reinterpret_cast<const int4*>(chunks) + blockIdx.x);
+  const int s0 = k.z, ns = k.w - k.z, n = k.y - k.x;
+  const int32_t* __restrict__ out_ptr = L.out_ptr;
+  const int32_t* __restrict__ dst_out = L.dst_out;
+  const int32_t* __restrict__ label_out = L.label_out;
+  float* hist = nullptr;
+  if (want_hist) {
+    if (dtheta_smem) {
+      hist = smem_f;
+      for (int i = tid; i < L.vocab; i += NT) hist[i] = 0.0f;
+      __syncthreads();
+    } else {
+      hist = dtheta;
+    }
+  }
+  ST lz = 0;
+  float gscale = 1.0f;
+  if (POST) {
+    const int b = __ldg(chunk_lat + blockIdx.x);
+    lz = logz[b];
+    if (grad_logz) gscale = grad_logz[b];
+  }
+  auto visit = [&](int a, ST am, ST& m, float& sum, float& bt, int& bi) {
+    const int d = __ldg(dst_out + a);
+    float w = SC ? __ldg(arc_scores + a) : 0.0f;
+    int lab = 0;
+    if (TH || POST) { if (need_label) lab = __ldg(label_out + a); }
+    if (TH) w += __ldg(th + lab);
+    if (LOGS) {
+      const ST u = static_cast<ST>(w) + beta[d];
+      lse_push(m, sum, u, neg_inf);
+      if (POST) {
+        const float p = ex2_approx(static_cast<float>(am + u) * kLog2e) * gscale;
+        if (post) post[a] = p;
+        if (hist) atomicAdd(&hist[lab], p);
+      }
+    }
+    if (TROP) {
+      const float t = __fadd_rn(w, delta[d]);
+      if (t > bt) { bt = t; bi = a; }
+    }
+  };
+  auto visit4 = [&](int a, ST am, ST& m, float& sum, float& bt, int& bi) {
+    ST u[4];
+    int lab[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int d = __ldg(dst_out + a + q);
+      float w = SC ? __ldg(arc_scores + a + q) : 0.0f;
+      if (TH || POST) { if (need_label) lab[q] = __ldg(label_out + a + q); }
+      if (TH) w += __ldg(th + lab[q]);
+      if (LOGS) u[q] = static_cast<ST>(w) + beta[d];
+      if (TROP) {
+        const float t = __fadd_rn(w, delta[d]);
+        if (t > bt) { bt = t; bi = a + q; }
+      }
+    }
+    if (LOGS) {
+      lse_push4(m, sum, u[0], u[1], u[2], u[3]);
+      if (POST) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float p = ex2_approx(static_cast<float>(am + u[q]) * kLog2e) * gscale;
+          if (post) post[a + q] = p;
+          if (hist) atomicAdd(&hist[lab[q]], p);
+        }
+      }
+    }
+  };
+  auto finish = [&](int s, bool sink, ST m, float sum, float bt, int bi) {
+    if (LOGS) beta[s] = sink ? static_cast<ST>(0) : lse_finish(m, sum, neg_inf);
+    if (TROP) {
+      delta[s] = sink ? 0.0f : bt;
+      backptr[s] = sink ? -1 : bi;
+    }
+  };
+  if (n <= cap) {
+    if (ns * 2 > NT) {
+#pragma unroll 1
+      for (int j = tid; j < ns; j += NT) {
+        const int b0 = __ldg(out_ptr + s0 + j), b1 = __ldg(out_ptr + s0 + j + 1);
+        const int s = s0 + j;
+        ST am = 0;
+        if (POST) am = alpha[s] - lz;
+        ST m = static_cast<ST>(kFloor);
+        float sum = 0.0f, bt = kNegInf;
+        int bi = 0x7fffffff;
+        int a = b0;
+#pragma unroll 1
+        for (; a + 3 < b1; a += 4) visit4(a, am, m, sum, bt, bi);
+#pragma unroll 1
+        for (; a < b1; ++a) visit(a, am, m, sum, bt, bi);
+        finish(s, b0 == b1, m, sum, bt, bi);
+      }
+    } else {
+      int lg = 1;
+      while (lg < 5 && (ns << (lg + 1)) <= NT) ++lg;
+      const int G = 1 << lg, lane_g = tid & (G - 1), ngrp = NT >> lg;
+#pragma unroll 1
+      for (int jb = 0; jb < ns; jb += ngrp) {
+        const int j = jb + (tid >> lg);
+        const bool valid = j < ns;
+        const int b0 = valid ? __ldg(out_ptr + s0 + j) : 0, b1 = valid ? __ldg(out_ptr + s0 + j + 1) : 0;
+        const int s = s0 + j;
+        ST am = 0;
+        if (POST && valid) am = alpha[s] - lz;
+        ST m = static_cast<ST>(kFloor);
+        float sum = 0.0f, bt = kNegInf;
+        int bi = 0x7fffffff;
+#pragma unroll 1
+        for (int a = b0 + lane_g; a < b1; a += G) visit(a, am, m, sum, bt, bi);
+        for (int o = G >> 1; o > 0; o >>= 1) {
+          if (LOGS) {
+            const ST m2 = __shfl_xor_sync(0xffffffffu, m, o);
+            const float s2 = __shfl_xor_sync(0xffffffffu, sum, o);
+            lse_join(m, sum, m2, s2, neg_inf);
+          }
+          if (TROP) {
+            const float t2 = __shfl_xor_sync(0xffffffffu, bt, o);
+            const int i2 = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (t2 > bt || (t2 == bt && i2 < bi)) { bt = t2; bi = i2; }
+          }
+        }
+        if (valid && lane_g == 0) finish(s, b0 == b1, m, sum, bt, bi);
+      }
+    }
+  } else {
+    for (int j = 0; j < ns; ++j) {  // heavy chunk: block-wide
+      const int s = s0 + j;
+      const int b0 = out_ptr[s], b1 = out_ptr[s + 1];
+      ST am = 0;
+      if (POST) am = alpha[s] - lz;
+      ST m = neg_inf;
+      float sum = 0.0f, bt = kNegInf;
+      int bi = 0x7fffffff;
+      for (int a = b0 + tid; a < b1; a += NT) {
+        const int d = dst_out[a];
+        int lab = 0;
+        if (need_label) lab = label_out[a];
+        float w = SC ? arc_scores[a] : 0.0f;
+        if (TH) w += th[lab];
+        if (LOGS) {
+          const ST u = static_cast<ST>(w) + beta[d];
+          lse_add(m, sum, u);
+          if (POST) {
+            const float p = ex2_approx(static_cast<float>(am + u) * kLog2e) * gscale;
+            if (post) post[a] = p;
+            if (hist) atomicAdd(&hist[lab], p);
+          }
+        }
+        if (TROP) {
+          const float t = __fadd_rn(w, delta[d]);
+          if (t > bt || (t == bt && a < bi)) { bt = t; bi = a; }
+        }
+      }
+      if (LOGS) {
+        const ST v0 = block_lse(m, sum);
+        if (tid == 0) beta[s] = (b0 == b1) ? static_cast<ST>(0) : v0;
+      }
+      if (TROP) {
+        __shared__ float red_t[32];
+        __shared__ int red_i[32];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          const float t2 = __shfl_xor_sync(0xffffffffu, bt, o);
+          const int i2 = __shfl_xor_sync(0xffffffffu, bi, o);
+          if (t2 > bt || (t2 == bt && i2 < bi)) { bt = t2; bi = i2; }
+        }
+        __syncthreads();
+        if ((tid & 31) == 0) { red_t[tid >> 5] = bt; red_i[tid >> 5] = bi; }
+        __syncthreads();
+        if (tid == 0) {
+          for (int w2 = 1; w2 < (NT + 31) / 32; ++w2)
+            if (red_t[w2] > bt || (red_t[w2] == bt && red_i[w2] < bi)) { bt = red_t[w2]; bi = red_i[w2]; }
+          const bool sink = (b0 == b1);
+          delta[s] = sink ? 0.0f : bt;
+          backptr[s] = sink ? -1 : bi;
+        }
+      }
+    }
+  }
+  if (want_hist && dtheta_smem) {
+    __syncthreads();
+    for (int i = tid; i < L.vocab; i += NT) {
+      const float v = hist[i];
+      if (v != 0.0f) atomicAdd(&dtheta[i], v);
+    }
+  }
+}
+
+// logz_bwd[b] = beta[start], vit_score[b] = delta[start]
+template <typename ST>
+__global__ void nfst_pick_start_kernel(const nfst_packed_lattices_t L, const int32_t* __restrict__ ids, int n,
+                                       const ST* __restrict__ beta, ST* __restrict__ logz_bwd,
+                                       const float* __restrict__ delta, float* __restrict__ vit_score) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int b = ids ? ids[i] : i;
+  const int s = L.start_state[b];
+  if (beta && logz_bwd) logz_bwd[b] = beta[s];
+  if (delta && vit_score) vit_score[b] = delta[s];
+}
+
+// =====================================================================================
 // small kernels
 // =====================================================================================
 __global__ void nfst_backtrace_kernel(const nfst_packed_lattices_t L, const int32_t* __restrict__ backptr,
@@ -837,10 +1146,32 @@ int launch_fwd2(const nfst_packed_lattices_t* lat, const nfst_launch_t* launch, 
   return NFST_OK;
 }
 
+template <typename ST, bool SC, bool TH>
+int launch_fwd_levels(const nfst_packed_lattices_t* lat, const nfst_launch_t* launch, const nfst_scores_t* scores,
+                      void* alpha, void* logz, cudaStream_t st) {
+  ST* a = static_cast<ST*>(alpha);
+  const int n = launch->n_ids;
+  nfst_fwd_init_kernel<ST><<<(n + 127) / 128, 128, 0, st>>>(*lat, launch->lattice_ids, n, a);
+  for (int l = 1; l < launch->n_levels; ++l) {  // level 0 holds the start states only
+    const int c0 = launch->fwd_level_off[l], c1 = launch->fwd_level_off[l + 1];
+    if (c1 > c0)
+      nfst_fwd_level_kernel<ST, SC, TH><<<c1 - c0, launch->block_threads, 0, st>>>(
+          *lat, launch->fwd_level_chunks + c0, launch->chunk_cap, scores->arc_scores, scores->theta, a);
+  }
+  nfst_logz_kernel<ST><<<n, 128, 0, st>>>(*lat, launch->lattice_ids, a, static_cast<ST*>(logz));
+  NFST_CUDA_OK(cudaGetLastError());
+  return NFST_OK;
+}
+
 template <typename ST>
 int launch_fwd(const nfst_packed_lattices_t* lat, const nfst_launch_t* launch, const nfst_scores_t* scores, void* alpha,
                void* logz, cudaStream_t st) {
   const bool sc = scores->arc_scores != nullptr, th = scores->theta != nullptr;
+  if (launch->fwd_level_chunks) {
+    if (sc && th) return launch_fwd_levels<ST, true, true>(lat, launch, scores, alpha, logz, st);
+    if (sc) return launch_fwd_levels<ST, true, false>(lat, launch, scores, alpha, logz, st);
+    return launch_fwd_levels<ST, false, true>(lat, launch, scores, alpha, logz, st);
+  }
   if (sc && th) return launch_fwd2<ST, true, true>(lat, launch, scores, alpha, logz, st);
   if (sc) return launch_fwd2<ST, true, false>(lat, launch, scores, alpha, logz, st);
   return launch_fwd2<ST, false, true>(lat, launch, scores, alpha, logz, st);
@@ -864,12 +1195,45 @@ int launch_bwd3(const nfst_packed_lattices_t* lat, const nfst_launch_t* launch, 
   return NFST_OK;
 }
 
+template <typename ST, bool LOGS, bool TROP, bool SC, bool TH, bool POST>
+int launch_bwd_levels(const nfst_packed_lattices_t* lat, const nfst_launch_t* launch, const nfst_scores_t* scores,
+                      const void* alpha, const void* logz, const float* grad_logz, void* beta, void* logz_bwd,
+                      float* post, float* dtheta, float* delta, int32_t* backptr, float* vit_score, cudaStream_t st) {
+  const int dtheta_smem = POST && dtheta && lat->vocab <= NFST_THETA_SMEM_MAX;
+  const size_t bytes = dtheta_smem ? static_cast<size_t>(lat->vocab) * 4 : 0;
+  for (int l = launch->n_levels - 1; l >= 0; --l) {
+    const int c0 = launch->bwd_level_off[l], c1 = launch->bwd_level_off[l + 1];
+    if (c1 > c0)
+      nfst_bwd_level_kernel<ST, LOGS, TROP, SC, TH, POST><<<c1 - c0, launch->block_threads, bytes, st>>>(
+          *lat, launch->bwd_level_chunks + c0, launch->bwd_level_lat + c0, launch->chunk_cap, scores->arc_scores,
+          scores->theta, dtheta_smem, static_cast<const ST*>(alpha), static_cast<const ST*>(logz), grad_logz,
+          static_cast<ST*>(beta), post, dtheta, delta, backptr);
+  }
+  const int n = launch->n_ids;
+  nfst_pick_start_kernel<ST><<<(n + 127) / 128, 128, 0, st>>>(*lat, launch->lattice_ids, n,
+                                                               LOGS ? static_cast<const ST*>(beta) : nullptr,
+                                                               static_cast<ST*>(logz_bwd), TROP ? delta : nullptr,
+                                                               vit_score);
+  NFST_CUDA_OK(cudaGetLastError());
+  return NFST_OK;
+}
+
 template <typename ST, bool LOGS, bool TROP>
 int launch_bwd(const nfst_packed_lattices_t* lat, const nfst_launch_t* launch, const nfst_scores_t* scores,
                const void* alpha, const void* logz, const float* grad_logz, void* beta, void* logz_bwd, float* post,
                float* dtheta, float* delta, int32_t* backptr, float* vit_score, cudaStream_t st) {
   const bool sc = scores->arc_scores != nullptr, th = scores->theta != nullptr;
   const bool ps = LOGS && (post || dtheta);
+  if (launch->bwd_level_chunks) {
+#define NFST_GOL(SC, TH, PS)                                                                                     \
+  return launch_bwd_levels<ST, LOGS, TROP, SC, TH, (LOGS && PS)>(lat, launch, scores, alpha, logz, grad_logz, beta, \
+                                                                 logz_bwd, post, dtheta, delta, backptr, vit_score, st)
+    if (sc && th) { if (ps) NFST_GOL(true, true, true); NFST_GOL(true, true, false); }
+    if (sc) { if (ps) NFST_GOL(true, false, true); NFST_GOL(true, false, false); }
+    if (ps) NFST_GOL(false, true, true);
+    NFST_GOL(false, true, false);
+#undef NFST_GOL
+  }
 #define NFST_GO(SC, TH, PS)                                                                                      \
   return launch_bwd3<ST, LOGS, TROP, SC, TH, (LOGS && PS)>(lat, launch, scores, alpha, logz, grad_logz, beta, logz_bwd, \
                                                            post, dtheta, delta, backptr, vit_score, st)

@@ -37,7 +37,7 @@ def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
 # global-memory path behind the window
 WINDOW_BYTES_MAX = pack_mod.WINDOW_BYTES_MAX
 # lattices deeper than this default to float64 state vectors (see resolve_state_dtype)
-F64_DEPTH = 128
+F64_DEPTH = 96
 
 
 def resolve_state_dtype(packed: PackedLattices, state_dtype="auto") -> torch.dtype:
@@ -78,6 +78,13 @@ def _launch(g: LaunchGroup, st_dtype: torch.dtype) -> "_lib.LaunchC":
     c.window_states = g.window_states(8 if f64 else 4, WINDOW_BYTES_MAX)
     c.state_f64 = int(f64)
     c.chunk_cap = g.chunk_cap
+    if g.fwd_level_chunks is not None:  # level-major group: one launch per topological level
+        c.n_levels = g.n_levels
+        c.fwd_level_chunks = g.fwd_level_chunks.data_ptr()
+        c.fwd_level_off = g.fwd_level_off.data_ptr()  # host array
+        c.bwd_level_chunks = g.bwd_level_chunks.data_ptr()
+        c.bwd_level_off = g.bwd_level_off.data_ptr()
+        c.bwd_level_lat = g.bwd_level_lat.data_ptr()
     return c
 
 

@@ -37,6 +37,9 @@ WINDOW_BYTES_MAX = int(os.environ.get("NFST_WINDOW_BYTES", str(64 * 1024)))
 BLOCK_MAX = int(os.environ.get("NFST_BLOCK_MAX", "256"))
 ARCS_PER_THREAD = int(os.environ.get("NFST_ARCS_PER_THREAD", "4"))
 HEAVY_DIV = 4
+# lattices whose widest level has at least this many arcs run level-major (one launch per
+# topological level over all their chunks) instead of one block per lattice
+LEVEL_MODE_MIN_ARCS = int(os.environ.get("NFST_LEVEL_MODE_MIN", "4096"))
 DEGREE_SORT = int(os.environ.get("NFST_DEGREE_SORT", "1"))
 
 
@@ -59,6 +62,18 @@ class LaunchGroup:
     max_reach: int  # longest arc of the group, in packed state ids (sizes the shared-memory window)
     n_arcs: int
     chunk_cap: int = 0  # stage capacity the lattices' chunks were cut for
+    # level-major execution (wide lattices): the group's chunks sorted by level
+    n_levels: int = 0
+    fwd_level_chunks: Optional[torch.Tensor] = None  # int32 [n, 4] device
+    fwd_level_off: Optional[torch.Tensor] = None  # int32 [n_levels + 1] HOST
+    bwd_level_chunks: Optional[torch.Tensor] = None
+    bwd_level_off: Optional[torch.Tensor] = None
+    bwd_level_lat: Optional[torch.Tensor] = None  # int32 [n] device
+
+    def to(self, device, non_blocking: bool = False) -> "LaunchGroup":
+        mv = lambda t: None if t is None else t.to(device, non_blocking=non_blocking)  # noqa: E731
+        return dataclasses.replace(self, ids=mv(self.ids), fwd_level_chunks=mv(self.fwd_level_chunks),
+                                   bwd_level_chunks=mv(self.bwd_level_chunks), bwd_level_lat=mv(self.bwd_level_lat))
 
     def window_states(self, state_bytes: int = 4, window_bytes_max: int = WINDOW_BYTES_MAX) -> int:
         """Power-of-two window: covers every arc of the group if that fits the byte budget
@@ -74,6 +89,7 @@ class PackedLattices:
         "state_off", "level_off", "level_ptr", "start_state", "sink_off", "sinks",
         "in_ptr", "src_in", "label_in", "in2out", "out_ptr", "dst_out", "label_out",
         "fwd_chunk_off", "fwd_chunks", "bwd_chunk_off", "bwd_chunks", "fwd_gather",
+        "fwd_chunk_level", "bwd_chunk_level",
     )
 
     # arrays the kernels stage with 16-byte copies: kept zero-padded by PAD elements
@@ -141,7 +157,7 @@ class PackedLattices:
         for name in self.tensors():
             kw[name] = getattr(self, name).to(device, non_blocking=non_blocking)
         kw.setdefault("static_scores", None)
-        kw["groups"] = [dataclasses.replace(g, ids=g.ids.to(device, non_blocking=non_blocking)) for g in self.groups]
+        kw["groups"] = [g.to(device, non_blocking) for g in self.groups]
         kw["stats"] = self.stats
         return PackedLattices(**kw)
 
@@ -163,6 +179,8 @@ class PackedLattices:
             c = _lib.PackedLatticesC()
             c.n_lattices, c.n_states, c.n_arcs, c.vocab = self.n_lattices, self.n_states, self.n_arcs, self.vocab
             for f in self._INT_FIELDS:
+                if f.endswith("_chunk_level"):
+                    continue  # host-side bookkeeping, not part of nfst_packed_lattices_t
                 t = getattr(self, f)
                 assert t.dtype == torch.int32 and t.is_contiguous() and t.data_ptr() % 16 == 0
                 setattr(c, f, t.data_ptr())
@@ -227,25 +245,43 @@ def _build_chunks(ptr, slot, level_first, lat_of_state, target, heavy_thr, n_lat
     return chunk_off, chunks.to(torch.int32).contiguous()
 
 
-def build_groups(stats, dev) -> List[LaunchGroup]:
+def build_groups(stats, dev, chunk_info=None) -> List[LaunchGroup]:
     """Partition the batch into launches: lattices cut for the same block size share a
-    launch; heaviest lattices first (longest-processing-time order)."""
-    gkey = stats["block_class"]
+    launch; heaviest lattices first (longest-processing-time order).  Lattices with wide
+    levels form level-major groups (see LaunchGroup / nfst_launch_t)."""
+    wide = (stats["width_arcs"] >= LEVEL_MODE_MIN_ARCS).to(torch.int64)
+    gkey = stats["block_class"] * 2 + wide
     groups: List[LaunchGroup] = []
+    B = int(gkey.numel())
     for key in sorted(set(gkey.tolist()), reverse=True):
         members = torch.nonzero(gkey == key).squeeze(1)
         members = members[torch.argsort(stats["arcs"][members], descending=True, stable=True)]
-        groups.append(
-            LaunchGroup(
-                ids=members.to(torch.int32).to(dev),
-                n=int(members.numel()),
-                block_threads=1 << key,
-                max_states=int(stats["states"][members].max()),
-                max_reach=int(stats["reach"][members].max()),
-                n_arcs=int(stats["arcs"][members].sum()),
-                chunk_cap=int(stats["chunk_cap"][members].max()),
-            )
+        g = LaunchGroup(
+            ids=members.to(torch.int32).to(dev),
+            n=int(members.numel()),
+            block_threads=1 << (key >> 1),
+            max_states=int(stats["states"][members].max()),
+            max_reach=int(stats["reach"][members].max()),
+            n_arcs=int(stats["arcs"][members].sum()),
+            chunk_cap=int(stats["chunk_cap"][members].max()),
         )
+        if (key & 1) and chunk_info is not None:
+            member_mask = torch.zeros(B, dtype=torch.bool, device=dev)
+            member_mask[members.to(dev)] = True
+            n_levels = int(stats["levels"][members].max())
+            g.n_levels = n_levels
+            for direction in ("fwd", "bwd"):
+                off, chunks, level = chunk_info[direction]
+                clat = torch.repeat_interleave(torch.arange(B, device=dev), (off[1:] - off[:-1]).to(torch.int64))
+                sel = torch.nonzero(member_mask[clat]).squeeze(1)
+                lv = level[sel].to(torch.int64)
+                order = torch.argsort(lv, stable=True)
+                lvl_off = _excl_cumsum(torch.bincount(lv, minlength=n_levels)).to(torch.int32).cpu().contiguous()
+                setattr(g, f"{direction}_level_chunks", chunks[sel][order].contiguous())
+                setattr(g, f"{direction}_level_off", lvl_off)
+                if direction == "bwd":
+                    g.bwd_level_lat = clat[sel][order].to(torch.int32).contiguous()
+        groups.append(g)
     return groups
 
 
@@ -282,6 +318,8 @@ def concat_packed(parts: List["PackedLattices"]) -> "PackedLattices":
         acc["fwd_chunks"].append(p.fwd_chunks + shift)
         acc["bwd_chunk_off"].append(cut(p.bwd_chunk_off + nbc))
         acc["bwd_chunks"].append(p.bwd_chunks + shift)
+        acc["fwd_chunk_level"].append(p.fwd_chunk_level)
+        acc["bwd_chunk_level"].append(p.bwd_chunk_level)
         nonempty = (p.fwd_gather[:, 1] > p.fwd_gather[:, 0]).to(torch.int32).unsqueeze(1)
         acc["fwd_gather"].append(p.fwd_gather + A * nonempty)
         nfc += int(p.fwd_chunks.shape[0])
@@ -305,9 +343,10 @@ def concat_packed(parts: List["PackedLattices"]) -> "PackedLattices":
     stats = {k: torch.cat([p.stats[k] for p in parts]) for k in parts[0].stats}
     kw = {f: torch.cat(v).contiguous() for f, v in acc.items()}
     kw.update({f: torch.cat(v).contiguous() for f, v in extra.items()})
+    ci = {d: (kw[f"{d}_chunk_off"].to(torch.int64), kw[f"{d}_chunks"], kw[f"{d}_chunk_level"]) for d in ("fwd", "bwd")}
     return PackedLattices(
         n_lattices=B, n_states=S, n_arcs=A, vocab=vocab, static_scores=torch.cat(static) if static else None,
-        dense_shape=None, groups=build_groups(stats, dev), max_levels=max(p.max_levels for p in parts),
+        dense_shape=None, groups=build_groups(stats, dev, ci), max_levels=max(p.max_levels for p in parts),
         stats=stats, **kw,
     )
 
@@ -457,7 +496,10 @@ def pack_arcs(
         cum = torch.cumsum(hist, 1)
         need = torch.ceil(cum[:, -1:].to(torch.float64) * 0.99).to(torch.int64)
         reach = torch.ones_like(reach) << (cum < need).sum(1)
+    fwd_chunk_level = lv_s[fwd_chunks[:, 2].to(torch.int64)]
+    bwd_chunk_level = lv_s[bwd_chunks[:, 2].to(torch.int64)]
     stats = {
+        "width_arcs": width_arcs.cpu(),
         "arcs": A_b.to(torch.int64).cpu(),
         "states": S_b.cpu(),
         "levels": n_levels.cpu(),
@@ -465,7 +507,8 @@ def pack_arcs(
         "chunk_cap": geo[block_class, 2].cpu(),
         "reach": reach.cpu(),
     }
-    groups = build_groups(stats, dev)
+    groups = build_groups(stats, dev, {"fwd": (fwd_chunk_off, fwd_chunks, fwd_chunk_level),
+                                       "bwd": (bwd_chunk_off, bwd_chunks, bwd_chunk_level)})
 
     i32 = lambda t: t.to(torch.int32).contiguous()  # noqa: E731
     return PackedLattices(
@@ -474,7 +517,7 @@ def pack_arcs(
         sink_off=i32(sink_off), sinks=i32(sinks), in_ptr=i32(in_ptr), src_in=i32(src_in), label_in=i32(label_in),
         in2out=i32(in2out), out_ptr=i32(out_ptr), dst_out=i32(dst_out), label_out=i32(label_out),
         fwd_chunk_off=i32(fwd_chunk_off), fwd_chunks=fwd_chunks, bwd_chunk_off=i32(bwd_chunk_off), bwd_chunks=bwd_chunks,
-        fwd_gather=i32(fwd_gather),
+        fwd_gather=i32(fwd_gather), fwd_chunk_level=i32(fwd_chunk_level), bwd_chunk_level=i32(bwd_chunk_level),
         lanes_in_log2=lg_in.to(torch.uint8).contiguous(), lanes_out_log2=lg_out.to(torch.uint8).contiguous(),
         orig_state=i32(orig_state), arc_origin=origin.contiguous(), arc_off=i32(arc_off), n_levels=i32(n_levels),
         static_scores=None if static_scores is None else static_scores[origin].to(torch.float32).contiguous(),

@@ -53,6 +53,12 @@ def tiny_window(monkeypatch):
     monkeypatch.setattr(nb.ops, "WINDOW_BYTES_MAX", 128)
 
 
+@pytest.fixture
+def level_major(monkeypatch):
+    """Run every lattice level-major (one launch per topological level over all chunks)."""
+    monkeypatch.setattr(nb.pack, "LEVEL_MODE_MIN_ARCS", 1)
+
+
 def check_fwd_bwd(ab: synth.ArcBatch, *, state_dtype="auto", strict=False):
     abd = ab.to(DEV)
     p, sc = abd.pack()
@@ -431,3 +437,32 @@ def test_scorer_mirror_and_monkeypatch_against_reference_golden():
     mod.Wh = torch.ones(H, H, device=DEV)
     with pytest.raises(NotImplementedError):
         patch_compute_beta(mod)
+
+
+# --------------------------------------------------------------------------------------
+# level-major execution (wide lattices): same results as block-per-lattice
+# --------------------------------------------------------------------------------------
+def test_level_major_matches_oracle_and_block_mode(level_major):
+    for ab in (synth.transliteration_batch(12, seed=3), synth.random_dag_batch(5, 40_000, levels=16, seed=8),
+               synth.cipher_batch(3, T=60, bigram=True, seed=2), synth.random_dag_batch(2, 400_000, levels=8, seed=5)):
+        p, sc, _ = check_fwd_bwd(ab)
+        assert all(g.fwd_level_chunks is not None for g in p.groups)
+        score, off, arcs, labels = nb.lattice_viterbi(p, arc_scores=sc)
+        o_score, o_paths, _ = c_oracle.viterbi(oracle_batch(ab))
+        assert np.array_equal(score.cpu().numpy().view(np.uint32), o_score.view(np.uint32))
+        origin, offc, arcs_c = p.arc_origin.cpu().numpy(), off.cpu().numpy(), arcs.cpu().numpy()
+        for b in range(p.n_lattices):
+            np.testing.assert_array_equal(origin[arcs_c[offc[b]:offc[b + 1]]], o_paths[b])
+
+
+def test_level_major_theta_gradient(level_major):
+    ab = synth.snips_batch(6, seed=2)
+    p, _ = ab.to(DEV).pack()
+    theta = torch.randn(p.vocab, device=DEV, requires_grad=True)
+    nb.lattice_log_partition(p, theta=theta).sum().backward()
+    w = theta.detach().cpu().numpy()[ab.label.numpy()]
+    ab2 = synth.ArcBatch(ab.arc_lattice, ab.src, ab.dst, ab.label, torch.from_numpy(w), ab.n_states, ab.vocab)
+    _, _, _, po = c_oracle.forward_backward(oracle_batch(ab2))
+    dth = np.zeros(p.vocab)
+    np.add.at(dth, ab.label.numpy(), po)
+    np.testing.assert_allclose(theta.grad.cpu().numpy(), dth, rtol=1e-4, atol=1e-5)

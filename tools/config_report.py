@@ -1,0 +1,131 @@
+"""Throughput + parity over the five BASELINE.json configs on one GPU (not the bench line).
+
+    python tools/config_report.py [--quick] > profiles/rN_configs.txt
+
+For every config: pack time, forward+fused-backward (beta + posteriors) and Viterbi+backtrace
+time (CUDA events, 3 warm-ups, L2 flushed between iterations when the inputs fit in L2),
+arcs/s, algorithmic GB/s, the C oracle (CPU port, all host threads) on a bounded sample, and
+parity of the GPU results against that oracle on the same sample.
+"""
+import argparse
+import os
+import sys
+import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+import nfst_b200 as nb  # noqa: E402
+from nfst_b200 import synth  # noqa: E402
+from nfst_b200.pack import concat_packed  # noqa: E402
+from oracle import c_oracle  # noqa: E402
+
+DEV = torch.device("cuda", 0)
+ap = argparse.ArgumentParser()
+ap.add_argument("--quick", action="store_true")
+ap.add_argument("--steps", type=int, default=10)
+args = ap.parse_args()
+
+flush_buf = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=DEV)  # > 126 MB L2
+
+
+def timed(fn, steps, flush):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    tot = 0.0
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for _ in range(steps):
+        if flush:
+            flush_buf.zero_()
+        e0.record()
+        fn()
+        e1.record()
+        torch.cuda.synchronize()
+        tot += e0.elapsed_time(e1)
+    return tot / steps
+
+
+def build(gen, B, per_chunk):
+    parts, scores, sample = [], [], None
+    done = 0
+    t0 = time.perf_counter()
+    while done < B:
+        n = min(per_chunk, B - done)
+        ab = gen(n, done)
+        if sample is None:
+            sample = ab
+        p, sc = ab.to(DEV).pack()
+        parts.append(p)
+        scores.append(sc)
+        done += n
+    packed = concat_packed(parts) if len(parts) > 1 else parts[0]
+    torch.cuda.synchronize()
+    return packed, torch.cat(scores), sample, time.perf_counter() - t0
+
+
+def parity(sample: synth.ArcBatch, n_max=16):
+    """GPU vs C oracle on (a slice of) the first generated chunk."""
+    B = min(int(sample.n_states.numel()), n_max)
+    sel = (sample.arc_lattice < B).cpu()
+    ab = synth.ArcBatch(sample.arc_lattice.cpu()[sel], sample.src.cpu()[sel], sample.dst.cpu()[sel], sample.label.cpu()[sel],
+                        sample.scores.cpu()[sel], sample.n_states.cpu()[:B], sample.vocab)
+    p, sc = ab.to(DEV).pack()
+    logz, alpha, beta, post = nb.lattice_forward_backward(p, arc_scores=sc)
+    vs, off, arcs, labels = nb.lattice_viterbi(p, arc_scores=sc)
+    ob = c_oracle.Batch(ab.arc_lattice.numpy(), ab.src.numpy(), ab.dst.numpy(), ab.label.numpy(), ab.scores.numpy(),
+                        ab.n_states.numpy())
+    t0 = time.perf_counter()
+    o_logz, _, _, o_post = c_oracle.forward_backward(ob)
+    t_cpu = time.perf_counter() - t0
+    o_vs, o_paths, _ = c_oracle.viterbi(ob)
+    ref = o_post[p.arc_origin.cpu().numpy()]
+    got = post.cpu().numpy().astype(np.float64)
+    big = ref > 1e-6
+    perr = float(np.max(np.abs(got[big] - ref[big]) / ref[big])) if big.any() else 0.0
+    zerr = float(np.max(np.abs(logz.cpu().numpy() - o_logz) / np.maximum(1.0, np.abs(o_logz))))
+    vexact = int(np.sum(vs.cpu().numpy().view(np.uint32) == o_vs.view(np.uint32)))
+    origin, offc, arcs_c = p.arc_origin.cpu().numpy(), off.cpu().numpy(), arcs.cpu().numpy()
+    pexact = sum(int(np.array_equal(origin[arcs_c[offc[b]:offc[b + 1]]], o_paths[b])) for b in range(B))
+    return dict(B=B, state=str(alpha.dtype).replace("torch.", ""), logz_rel=zerr, post_rel=perr, vit_scores_exact=f"{vexact}/{B}",
+                vit_paths_exact=f"{pexact}/{B}", cpu_arcs_per_s=ob.n_arcs / t_cpu, cpu_threads=c_oracle.max_threads())
+
+
+q = args.quick
+CONFIGS = [
+    ("config1 transliteration B=32", lambda n, o: synth.transliteration_batch(n, seed=o), 32, 32),
+    ("config2 SNIPS B=256", lambda n, o: synth.snips_batch(n, seed=1 + o), 256, 256),
+    ("config3 cipher unigram T=1000 B=64", lambda n, o: synth.cipher_batch(n, T=1000, bigram=False, seed=2 + o, device=DEV), 64, 64),
+    ("config3 cipher bigram T=1000 B=64", lambda n, o: synth.cipher_batch(n, T=1000, bigram=True, seed=2 + o, device=DEV), 16 if q else 64, 16),
+    ("config5 Viterbi transliteration B=4096", lambda n, o: synth.transliteration_batch(n, seed=4 + o), 512 if q else 4096, 512),
+    ("config5 Viterbi integer scores B=4096", lambda n, o: synth.transliteration_batch(n, seed=4 + o, integer_scores=True), 512 if q else 4096, 512),
+]
+for arcs in (10_000, 30_000, 100_000, 300_000, 1_000_000):
+    B = 1024 if not q else 128
+    CONFIGS.append((f"config4 random DAG A={arcs} B={B}", (lambda a: lambda n, o: synth.random_dag_batch(n, a, seed=3 + o, device=DEV))(arcs),
+                    B, max(1, 60_000_000 // arcs)))
+
+print(f"{'config':44s} {'arcs':>11s} {'states':>10s} {'lvls':>5s} {'pack s':>7s} {'f+b ms':>8s} {'f+b Garc/s':>10s} {'alg GB/s':>8s} "
+      f"{'vit ms':>8s} {'vit Garc/s':>10s} | {'CPU Marc/s':>10s} {'thr':>3s} | parity (GPU vs C oracle sample)")
+for name, gen, B, per_chunk in CONFIGS:
+    packed, sc, sample, t_pack = build(gen, B, per_chunk)
+    A, S = packed.n_arcs, packed.n_states
+    flush = 20 * A < 2 * 126e6
+
+    def fb():
+        al, lz = nb.lattice_forward(packed, arc_scores=sc)
+        nb.lattice_backward(packed, arc_scores=sc, alpha=al, logz=lz, want_beta=True, want_post=True)
+
+    def vit():
+        nb.lattice_viterbi(packed, arc_scores=sc)
+
+    ms_fb = timed(fb, args.steps, flush)
+    ms_v = timed(vit, args.steps, flush)
+    par = parity(sample)
+    print(f"{name:44s} {A:11d} {S:10d} {packed.max_levels:5d} {t_pack:7.2f} {ms_fb:8.3f} {A / ms_fb / 1e6:10.2f} "
+          f"{(20 * A + 20 * S) / ms_fb / 1e6:8.0f} {ms_v:8.3f} {A / ms_v / 1e6:10.2f} | {par['cpu_arcs_per_s'] / 1e6:10.1f} {par['cpu_threads']:3d} | "
+          f"state {par['state']} logZ rel {par['logz_rel']:.1e} post rel {par['post_rel']:.1e} "
+          f"Viterbi scores {par['vit_scores_exact']} paths {par['vit_paths_exact']} (first {par['B']} lattices)", flush=True)
+    del packed, sc, sample
+    torch.cuda.empty_cache()
