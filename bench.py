@@ -182,7 +182,8 @@ def cpu_baseline(a, seconds: float, threads: int = 0):
     sample of the workload: as many lattices as fit in ~`seconds`."""
     from oracle import c_oracle
 
-    cores = c_oracle.max_threads() if threads <= 0 else threads
+    # torchrun exports OMP_NUM_THREADS=1: ask for every host core explicitly
+    cores = (os.cpu_count() or c_oracle.max_threads()) if threads <= 0 else threads
     probe_n = max(1, min(a.batch, cores))
     ab = make_arcs(a, "cpu", seed_offset=777, batch=probe_n)
     ob = c_oracle.Batch(ab.arc_lattice.numpy(), ab.src.numpy(), ab.dst.numpy(), ab.label.numpy(), ab.scores.numpy(),
@@ -209,7 +210,7 @@ def run_reference(a):
         return
     from oracle import c_oracle
 
-    cores = c_oracle.max_threads()
+    cores = os.cpu_count() or c_oracle.max_threads()  # torchrun exports OMP_NUM_THREADS=1
     n = max(1, min(a.batch, cores))
     ab = make_arcs(a, "cpu", seed_offset=777, batch=n)
     ob = c_oracle.Batch(ab.arc_lattice.numpy(), ab.src.numpy(), ab.dst.numpy(), ab.label.numpy(), ab.scores.numpy(),
@@ -405,7 +406,7 @@ def main():
     }
     if e2e:
         out["e2e"] = e2e
-    if not a.no_cpu:
+    if not a.no_cpu and world == 1:  # CPU baseline: rank 0 at N=1 only
         cb, _, _ = cpu_baseline(a, a.cpu_seconds)
         out["cpu_baseline"] = cb
     if a.sweep and world == 1 and a.workload == "dag":

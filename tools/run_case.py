@@ -19,16 +19,20 @@ ap.add_argument("--batch", type=int, default=296)
 ap.add_argument("--levels", type=int, default=64)
 ap.add_argument("--steps", type=int, default=3)
 ap.add_argument("--viterbi", action="store_true")
+ap.add_argument("--theta", action="store_true", help="scores = theta[label] (WFSTScorer mode) instead of per-arc")
 a = ap.parse_args()
 dev = torch.device("cuda", 0)
 packed, scores = bench.build_packed(a, dev)
+kw = dict(arc_scores=scores)
+if a.theta:
+    kw = dict(theta=-torch.rand(packed.vocab, device=dev))
 torch.cuda.synchronize()
 ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
 for i in range(a.steps):
     ev[0].record()
-    alpha, logz = nb.lattice_forward(packed, arc_scores=scores)
+    alpha, logz = nb.lattice_forward(packed, **kw)
     ev[1].record()
-    r = nb.lattice_backward(packed, arc_scores=scores, alpha=alpha, logz=logz, want_beta=True, want_post=True,
+    r = nb.lattice_backward(packed, alpha=alpha, logz=logz, want_beta=True, want_post=True, want_dtheta=a.theta, **kw,
                             want_viterbi=a.viterbi)
     ev[2].record()
     torch.cuda.synchronize()
