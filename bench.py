@@ -321,7 +321,7 @@ def main():
     if not a.no_e2e:
         fields = ("state_off", "start_state", "sink_off", "sinks", "in_ptr", "src_in", "in2out", "out_ptr", "dst_out",
                   "lanes_in_log2", "lanes_out_log2", "fwd_chunk_off", "fwd_chunks", "bwd_chunk_off", "bwd_chunks",
-                  "fwd_gather")
+                  "fwd_gather", "bwd_order")
         host = {f: getattr(packed, f).cpu().pin_memory() for f in fields}
         host_scores = scores.cpu().pin_memory()
         host_ids = [g.ids.cpu().pin_memory() for g in packed.groups]

@@ -41,7 +41,7 @@
 extern "C" {
 #endif
 
-#define NFST_ABI_VERSION 5
+#define NFST_ABI_VERSION 6
 
 typedef enum nfst_status {
   NFST_OK = 0,
@@ -99,6 +99,8 @@ typedef struct nfst_packed_lattices {
   const int32_t* bwd_chunk_off;     /* [B+1] */
   const nfst_chunk_t* bwd_chunks;   /* descending */
   const int32_t* fwd_gather;        /* [n_fwd_chunks][2]: canonical-id range [lo, hi) the chunk's arcs gather from */
+  const int32_t* bwd_order;         /* [S] states in backward processing order: a permutation inside every
+                                       backward chunk's state range, sorted by out-degree */
 } nfst_packed_lattices_t;
 
 /*

@@ -42,6 +42,7 @@ class PackedLatticesC(C.Structure):
         ("bwd_chunk_off", C.c_void_p),
         ("bwd_chunks", C.c_void_p),
         ("fwd_gather", C.c_void_p),
+        ("bwd_order", C.c_void_p),
     ]
 
 
@@ -112,7 +113,7 @@ def load() -> C.CDLL:
         fn = getattr(lib, name)  # AttributeError if the header and the library disagree
         fn.restype = res
         fn.argtypes = args
-    if lib.nfst_abi_version() != 5:
+    if lib.nfst_abi_version() != 6:
         raise RuntimeError("libnfst_b200.so ABI version mismatch")
     _lib = lib
     return lib

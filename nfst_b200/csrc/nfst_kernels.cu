@@ -492,6 +492,7 @@ __global__ void __launch_bounds__(256, NFST_MIN_BLOCKS)
   };
   stage_in(k0, s_cur);
   cp_async_commit();
+  int sid_cur = (k0.z + tid < k0.w) ? __ldg(L.bwd_order + k0.z + tid) : 0;
   cp_async_wait_all();
   __syncthreads();
 
@@ -581,12 +582,15 @@ __global__ void __launch_bounds__(256, NFST_MIN_BLOCKS)
         backptr[s] = sink ? -1 : base4 + bi;
       }
     };
+    // first state of this thread in the NEXT chunk's processing order (consumed next iteration)
+    const int sid_next = (k1.z + tid < k1.w) ? __ldg(L.bwd_order + k1.z + tid) : 0;
     if (n <= cap) {
       if (ns * 2 > NT) {
 #pragma unroll 1
         for (int j = tid; j < ns; j += NT) {
-          const int b0 = s_ptr[j] - base4, b1 = s_ptr[j + 1] - base4;
-          const int s = s0 + j;
+          // states are visited in out-degree order, so a warp's 32 states have equal trip counts
+          const int s = (j == tid) ? sid_cur : __ldg(L.bwd_order + s0 + j);
+          const int b0 = s_ptr[s - s0] - base4, b1 = s_ptr[s - s0 + 1] - base4;
           ST am = 0;
           if (POST) am = alpha[s] - lz;  // issued before the arc loop, consumed inside it
           ST m = static_cast<ST>(kFloor);
@@ -696,7 +700,7 @@ __global__ void __launch_bounds__(256, NFST_MIN_BLOCKS)
     }
     cp_async_wait_all();
     __syncthreads();
-    k0 = k1; k1 = k2;
+    k0 = k1; k1 = k2; sid_cur = sid_next;
     const int t = s_cur; s_cur = s_nxt; s_nxt = t;
   }
 
@@ -899,8 +903,8 @@ __global__ void __launch_bounds__(256, 4)
     if (ns * 2 > NT) {
 #pragma unroll 1
       for (int j = tid; j < ns; j += NT) {
-        const int b0 = __ldg(out_ptr + s0 + j), b1 = __ldg(out_ptr + s0 + j + 1);
-        const int s = s0 + j;
+        const int s = __ldg(L.bwd_order + s0 + j);  // out-degree order inside the chunk
+        const int b0 = __ldg(out_ptr + s), b1 = __ldg(out_ptr + s + 1);
         ST am = 0;
         if (POST) am = alpha[s] - lz;
         ST m = static_cast<ST>(kFloor);

@@ -89,7 +89,7 @@ class PackedLattices:
         "state_off", "level_off", "level_ptr", "start_state", "sink_off", "sinks",
         "in_ptr", "src_in", "label_in", "in2out", "out_ptr", "dst_out", "label_out",
         "fwd_chunk_off", "fwd_chunks", "bwd_chunk_off", "bwd_chunks", "fwd_gather",
-        "fwd_chunk_level", "bwd_chunk_level",
+        "fwd_chunk_level", "bwd_chunk_level", "bwd_order",
     )
 
     # arrays the kernels stage with 16-byte copies: kept zero-padded by PAD elements
@@ -235,6 +235,11 @@ def _build_chunks(ptr, slot, level_first, lat_of_state, target, heavy_thr, n_lat
     sb = torch.nonzero(new).squeeze(1)
     se = torch.cat([sb[1:], torch.tensor([S], device=dev, dtype=sb.dtype)])
     chunks = torch.stack([ptr[sb], ptr[se], sb, se], dim=1)
+    # processing order inside a chunk: its states sorted by degree, so that the 32 states a
+    # warp reduces have equal trip counts even where the state numbering cannot provide it
+    cid = torch.cumsum(new.to(torch.int64), 0) - 1
+    dmax = int(deg.max()) + 1 if S else 1
+    order = torch.argsort(cid * dmax + deg, stable=True)
     clat = lat_of_state[sb]
     chunk_off = _excl_cumsum(torch.bincount(clat, minlength=n_lattices))
     if descending:
@@ -242,7 +247,7 @@ def _build_chunks(ptr, slot, level_first, lat_of_state, target, heavy_thr, n_lat
         pos = torch.arange(n, device=dev)
         rev = chunk_off[clat] + (chunk_off[clat + 1] - 1 - pos)
         chunks = chunks[rev]
-    return chunk_off, chunks.to(torch.int32).contiguous()
+    return chunk_off, chunks.to(torch.int32).contiguous(), order.to(torch.int32).contiguous()
 
 
 def build_groups(stats, dev, chunk_info=None) -> List[LaunchGroup]:
@@ -318,6 +323,7 @@ def concat_packed(parts: List["PackedLattices"]) -> "PackedLattices":
         acc["fwd_chunks"].append(p.fwd_chunks + shift)
         acc["bwd_chunk_off"].append(cut(p.bwd_chunk_off + nbc))
         acc["bwd_chunks"].append(p.bwd_chunks + shift)
+        acc["bwd_order"].append(p.bwd_order + S)
         acc["fwd_chunk_level"].append(p.fwd_chunk_level)
         acc["bwd_chunk_level"].append(p.bwd_chunk_level)
         nonempty = (p.fwd_gather[:, 1] > p.fwd_gather[:, 0]).to(torch.int32).unsqueeze(1)
@@ -470,8 +476,8 @@ def pack_arcs(
         width_arcs.to(torch.float64) / ARCS_PER_THREAD, min=32.0))), 5, bmax).to(torch.int64)
     geo = torch.tensor([chunk_geometry(1 << k) if k >= 5 else (0, 0, 0) for k in range(bmax + 1)], device=dev)
     target_state, heavy_state = geo[block_class, 0][lt_s], geo[block_class, 1][lt_s]
-    fwd_chunk_off, fwd_chunks = _build_chunks(in_ptr, slot, lvl_first_state, lt_s, target_state, heavy_state, B, False)
-    bwd_chunk_off, bwd_chunks = _build_chunks(out_ptr, slot, lvl_first_state, lt_s, target_state, heavy_state, B, True)
+    fwd_chunk_off, fwd_chunks, _ = _build_chunks(in_ptr, slot, lvl_first_state, lt_s, target_state, heavy_state, B, False)
+    bwd_chunk_off, bwd_chunks, bwd_order = _build_chunks(out_ptr, slot, lvl_first_state, lt_s, target_state, heavy_state, B, True)
     # canonical-id range [lo, hi) that the arcs of each forward chunk gather their scores from
     # (the kernel prefetches it into L2 several chunks ahead)
     nfc = int(fwd_chunks.shape[0])
@@ -518,6 +524,7 @@ def pack_arcs(
         in2out=i32(in2out), out_ptr=i32(out_ptr), dst_out=i32(dst_out), label_out=i32(label_out),
         fwd_chunk_off=i32(fwd_chunk_off), fwd_chunks=fwd_chunks, bwd_chunk_off=i32(bwd_chunk_off), bwd_chunks=bwd_chunks,
         fwd_gather=i32(fwd_gather), fwd_chunk_level=i32(fwd_chunk_level), bwd_chunk_level=i32(bwd_chunk_level),
+        bwd_order=bwd_order,
         lanes_in_log2=lg_in.to(torch.uint8).contiguous(), lanes_out_log2=lg_out.to(torch.uint8).contiguous(),
         orig_state=i32(orig_state), arc_origin=origin.contiguous(), arc_off=i32(arc_off), n_levels=i32(n_levels),
         static_scores=None if static_scores is None else static_scores[origin].to(torch.float32).contiguous(),
