@@ -253,16 +253,6 @@ __device__ __forceinline__ void gather_scores(const int4& k, int cap, int st, co
   }
 }
 
-// pull [p, p + bytes) into L2 (no shared memory, no registers, no completion to wait for)
-__device__ __forceinline__ void l2_prefetch(const void* p, long long bytes) {
-  if (bytes <= 0) return;
-  const unsigned long long a = reinterpret_cast<unsigned long long>(p);
-  const unsigned long long a16 = a & ~15ULL;
-  const unsigned n = static_cast<unsigned>((a + bytes - a16 + 15) & ~15ULL);
-  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a16), "r"(n) : "memory");
-}
-constexpr int kPrefetch = 6;  // L2 prefetch distance of the block-per-lattice kernels, in chunks
-
 // rare path: a neighbour older than the shared-memory window (kept out of line so that the
 // hot loops carry no 64-bit address arithmetic)
 template <typename T>
@@ -318,24 +308,6 @@ __global__ void __launch_bounds__(256, NFST_MIN_BLOCKS)
   //   chunk c+2 :                                            its arc arrays stream in now (16 B copies)
   int4 k0 = chunk_at(chunks, c, c_end), k1 = chunk_at(chunks, c + 1, c_end), k2 = chunk_at(chunks, c + 2, c_end);
   int s_cur = stage0, s_nxt = stage0 + stage_words, s_nn = stage0 + 2 * stage_words;
-  // one thread keeps L2 kPrefetch chunks ahead of the copies (arrays + the score region the
-  // chunk gathers from), so the cp.async traffic below hits L2 instead of HBM
-  const int2* gat = reinterpret_cast<const int2*>(L.fwd_gather);
-  auto prefetch = [&](const int4& k, const int2& g) {
-    if (k.w > k.z) {
-      const long long nb = static_cast<long long>(k.y - k.x) * 4;
-      l2_prefetch(L.src_in + k.x, nb);
-      if (SC) l2_prefetch(L.in2out + k.x, nb);
-      if (TH) l2_prefetch(L.label_in + k.x, nb);
-      l2_prefetch(L.in_ptr + k.z, static_cast<long long>(k.w - k.z + 1) * 4);
-      if (SC) l2_prefetch(arc_scores + g.x, static_cast<long long>(g.y - g.x) * 4);
-    }
-  };
-  auto gather_range = [&](int j) { return (SC && j < c_end) ? __ldg(gat + j) : make_int2(0, 0); };
-  if (tid == 0)
-    for (int j = 3; j < kPrefetch; ++j) prefetch(chunk_at(chunks, c + j, c_end), gather_range(c + j));
-  int4 kp = chunk_at(chunks, c + kPrefetch, c_end);
-  int2 gp = gather_range(c + kPrefetch);
   stage_chunk<SC, TH>(k0, cap, s_cur, plan, L.src_in, L.in2out, L.label_in, L.in_ptr);
   stage_chunk<SC, TH>(k1, cap, s_nxt, plan, L.src_in, L.in2out, L.label_in, L.in_ptr);
   cp_async_commit();
@@ -349,13 +321,6 @@ __global__ void __launch_bounds__(256, NFST_MIN_BLOCKS)
 #pragma unroll 1
   for (; c < c_end; ++c) {
     const int4 k3 = chunk_at(chunks, c + 3, c_end);  // descriptors run ahead of their use
-    int4 kpn = make_int4(0, 0, 0, 0);
-    int2 gpn = make_int2(0, 0);
-    if (tid == 0) {
-      kpn = chunk_at(chunks, c + 1 + kPrefetch, c_end);
-      gpn = gather_range(c + 1 + kPrefetch);
-      prefetch(kp, gp);
-    }
     stage_chunk<SC, TH>(k2, cap, s_nn, plan, L.src_in, L.in2out, L.label_in, L.in_ptr);
     if (SC) gather_scores(k1, cap, s_nxt, plan, arc_scores);
     cp_async_commit();
@@ -451,7 +416,7 @@ __global__ void __launch_bounds__(256, NFST_MIN_BLOCKS)
     }
     cp_async_wait_all();
     __syncthreads();  // alpha of chunk c visible; scores of c+1 and arrays of c+2 landed; stage of c free
-    k0 = k1; k1 = k2; k2 = k3; kp = kpn; gp = gpn;
+    k0 = k1; k1 = k2; k2 = k3;
     const int t = s_cur; s_cur = s_nxt; s_nxt = s_nn; s_nn = t;
   }
 
@@ -525,20 +490,6 @@ __global__ void __launch_bounds__(256, NFST_MIN_BLOCKS)
     if (need_label) stage_chunk<SC, true>(k, cap, st, plan, L.dst_out, arc_scores, lab_arr, L.out_ptr);
     else stage_chunk<SC, false>(k, cap, st, plan, L.dst_out, arc_scores, lab_arr, L.out_ptr);
   };
-  auto prefetch = [&](const int4& k) {
-    if (k.w > k.z) {
-      const long long nb = static_cast<long long>(k.y - k.x) * 4;
-      l2_prefetch(L.dst_out + k.x, nb);
-      if (SC) l2_prefetch(arc_scores + k.x, nb);
-      if (need_label) l2_prefetch(L.label_out + k.x, nb);
-      l2_prefetch(L.out_ptr + k.z, static_cast<long long>(k.w - k.z + 1) * 4);
-      l2_prefetch(L.bwd_order + k.z, static_cast<long long>(k.w - k.z) * 4);
-      if (POST) l2_prefetch(alpha + k.z, static_cast<long long>(k.w - k.z) * sizeof(ST));
-    }
-  };
-  if (tid == 0)
-    for (int j = 2; j < kPrefetch; ++j) prefetch(chunk_at(chunks, c + j, c_end));
-  int4 kp = chunk_at(chunks, c + kPrefetch, c_end);
   stage_in(k0, s_cur);
   cp_async_commit();
   int sid_cur = (k0.z + tid < k0.w) ? __ldg(L.bwd_order + k0.z + tid) : 0;
@@ -548,11 +499,6 @@ __global__ void __launch_bounds__(256, NFST_MIN_BLOCKS)
 #pragma unroll 1
   for (; c < c_end; ++c) {
     const int4 k2 = chunk_at(chunks, c + 2, c_end);
-    int4 kpn = make_int4(0, 0, 0, 0);
-    if (tid == 0) {
-      kpn = chunk_at(chunks, c + 1 + kPrefetch, c_end);
-      prefetch(kp);
-    }
     stage_in(k1, s_nxt);
     cp_async_commit();
     const int* s_dst = reinterpret_cast<const int*>(smem_f + s_cur + o_nbr);
@@ -754,7 +700,7 @@ __global__ void __launch_bounds__(256, NFST_MIN_BLOCKS)
     }
     cp_async_wait_all();
     __syncthreads();
-    k0 = k1; k1 = k2; sid_cur = sid_next; kp = kpn;
+    k0 = k1; k1 = k2; sid_cur = sid_next;
     const int t = s_cur; s_cur = s_nxt; s_nxt = t;
   }
 
