@@ -492,7 +492,7 @@ __global__ void __launch_bounds__(256, NFST_MIN_BLOCKS)
   };
   stage_in(k0, s_cur);
   cp_async_commit();
-  int sid_cur = (k0.z + tid < k0.w) ? __ldg(L.bwd_order + k0.z + tid) : 0;
+  int sid_cur = (LOGS && k0.z + tid < k0.w) ? __ldg(L.bwd_order + k0.z + tid) : 0;
   cp_async_wait_all();
   __syncthreads();
 
@@ -583,13 +583,14 @@ __global__ void __launch_bounds__(256, NFST_MIN_BLOCKS)
       }
     };
     // first state of this thread in the NEXT chunk's processing order (consumed next iteration)
-    const int sid_next = (k1.z + tid < k1.w) ? __ldg(L.bwd_order + k1.z + tid) : 0;
+    const int sid_next = (LOGS && k1.z + tid < k1.w) ? __ldg(L.bwd_order + k1.z + tid) : 0;
     if (n <= cap) {
       if (ns * 2 > NT) {
 #pragma unroll 1
         for (int j = tid; j < ns; j += NT) {
           // states are visited in out-degree order, so a warp's 32 states have equal trip counts
-          const int s = (j == tid) ? sid_cur : __ldg(L.bwd_order + s0 + j);
+          // (log semiring only: the tropical-only pass has too little work per arc to pay for it)
+          const int s = !LOGS ? s0 + j : ((j == tid) ? sid_cur : __ldg(L.bwd_order + s0 + j));
           const int b0 = s_ptr[s - s0] - base4, b1 = s_ptr[s - s0 + 1] - base4;
           ST am = 0;
           if (POST) am = alpha[s] - lz;  // issued before the arc loop, consumed inside it
