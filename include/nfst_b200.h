@@ -41,7 +41,7 @@
 extern "C" {
 #endif
 
-#define NFST_ABI_VERSION 6
+#define NFST_ABI_VERSION 7
 
 typedef enum nfst_status {
   NFST_OK = 0,
@@ -132,6 +132,10 @@ typedef struct nfst_launch {
   const nfst_chunk_t* bwd_level_chunks;
   const int32_t* bwd_level_off;
   const int32_t* bwd_level_lat;
+  /* Small-lattice execution: when small_max_arcs > 0 every lattice of the group fits in shared
+   * memory (at most small_max_states states, small_max_arcs arcs, small_max_levels levels) and is
+   * processed there in one piece (nfst_small_kernel). */
+  int32_t small_max_states, small_max_arcs, small_max_levels;
 } nfst_launch_t;
 
 /* Arc scores: w(a) = (arc_scores ? arc_scores[a] : 0) + (theta ? theta[label(a)] : 0);
@@ -179,6 +183,12 @@ int nfst_bwd_fused_f32(const nfst_packed_lattices_t* lat, const nfst_launch_t* l
                        const void* alpha, const void* logz, const float* grad_logz, void* beta, void* logz_bwd,
                        float* post, float* dtheta, float* delta, int32_t* backptr, float* vit_score,
                        void* cuda_stream);
+
+/* Forward + fused backward in ONE launch for a small-lattice group (launch->small_max_arcs > 0):
+ * alpha never leaves the SM.  logz is required; alpha, beta, logz_bwd, post, dtheta optional. */
+int nfst_fwd_bwd_small_f32(const nfst_packed_lattices_t* lat, const nfst_launch_t* launch, const nfst_scores_t* scores,
+                           const float* grad_logz, void* alpha, void* logz, void* beta, void* logz_bwd, float* post,
+                           float* dtheta, void* cuda_stream);
 
 /* Tropical pass only (thin wrapper over nfst_bwd_fused_f32). */
 int nfst_viterbi_f32(const nfst_packed_lattices_t* lat, const nfst_launch_t* launch, const nfst_scores_t* scores,

@@ -62,6 +62,9 @@ class LaunchC(C.Structure):
         ("bwd_level_chunks", C.c_void_p),
         ("bwd_level_off", C.c_void_p),
         ("bwd_level_lat", C.c_void_p),
+        ("small_max_states", C.c_int32),
+        ("small_max_arcs", C.c_int32),
+        ("small_max_levels", C.c_int32),
     ]
 
 
@@ -83,6 +86,7 @@ SYMBOLS = {
         C.c_int,
         [C.POINTER(PackedLatticesC), C.POINTER(LaunchC), C.POINTER(ScoresC), _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P],
     ),
+    "nfst_fwd_bwd_small_f32": (C.c_int, [C.POINTER(PackedLatticesC), C.POINTER(LaunchC), C.POINTER(ScoresC)] + [_P] * 8),
     "nfst_viterbi_f32": (C.c_int, [C.POINTER(PackedLatticesC), C.POINTER(LaunchC), C.POINTER(ScoresC), _P, _P, _P, _P]),
     "nfst_backtrace": (C.c_int, [C.POINTER(PackedLatticesC), _P, _P, _P, _P, _P]),
     "nfst_beta_to_dense": (C.c_int, [C.POINTER(PackedLatticesC), _P, C.c_int, _P, C.c_int32, C.c_int32, _P, _P]),
@@ -113,7 +117,7 @@ def load() -> C.CDLL:
         fn = getattr(lib, name)  # AttributeError if the header and the library disagree
         fn.restype = res
         fn.argtypes = args
-    if lib.nfst_abi_version() != 6:
+    if lib.nfst_abi_version() != 7:
         raise RuntimeError("libnfst_b200.so ABI version mismatch")
     _lib = lib
     return lib

@@ -719,6 +719,224 @@ __global__ void __launch_bounds__(256, NFST_MIN_BLOCKS)
 }
 
 // =====================================================================================
+// small lattices (the size nFST's own lattices have: hundreds to a few thousand arcs): the
+// WHOLE lattice -- CSR arrays, scores in both arc orders, DP vectors -- is loaded into shared
+// memory once, then every level costs shared-memory latency + one barrier.  Forward, backward,
+// posteriors and the Viterbi recursion can run in ONE launch (DO_FWD && DO_BWD), with alpha
+// never leaving the SM; or as two launches around an autograd boundary.
+// =====================================================================================
+struct SmallPlan {  // offsets in 32-bit words
+  int a, b, d, lp, inp, outp, src, win, dst, wout, lab, bp, hist, words;
+};
+__host__ __device__ inline SmallPlan small_plan(int S, int A, int Lv, int st_words, bool fwd, bool bwd, bool trop,
+                                                bool labels, int hist_words) {
+  SmallPlan p;
+  int o = 0;
+  auto take = [&](int n) { const int at = o; o += (n + 3) & ~3; return at; };
+  p.a = take(S * st_words);
+  p.b = take(bwd ? S * st_words : 0);
+  p.d = take(trop ? S : 0);
+  p.bp = take(trop ? S : 0);
+  p.lp = take(Lv + 1);
+  p.inp = take(fwd ? S + 1 : 0);
+  p.outp = take(bwd ? S + 1 : 0);
+  p.src = take(fwd ? A : 0);
+  p.win = take(fwd ? A : 0);
+  p.dst = take(bwd ? A : 0);
+  p.wout = take(A);
+  p.lab = take(labels ? A : 0);
+  p.hist = take(hist_words);
+  p.words = o;
+  return p;
+}
+
+template <typename ST, bool SC, bool TH, bool DO_FWD, bool DO_BWD, bool LOGS, bool TROP, bool POST>
+__global__ void __launch_bounds__(256, 4)
+    nfst_small_kernel(const nfst_packed_lattices_t L, const int32_t* __restrict__ ids, int capS, int capA, int capL,
+                      const float* __restrict__ arc_scores, const float* __restrict__ theta, int dtheta_smem,
+                      ST* __restrict__ alpha_g, ST* __restrict__ logz_g, const float* __restrict__ grad_logz,
+                      ST* __restrict__ beta_g, ST* __restrict__ logz_bwd, float* __restrict__ post,
+                      float* __restrict__ dtheta, float* __restrict__ delta_g, int32_t* __restrict__ backptr,
+                      float* __restrict__ vit_score) {
+  const int NT = blockDim.x, tid = threadIdx.x;
+  const ST neg_inf = static_cast<ST>(kNegInf);
+  const bool want_hist = POST && dtheta != nullptr;
+  const SmallPlan P = small_plan(capS, capA, capL, sizeof(ST) / 4, DO_FWD, DO_BWD, DO_BWD && TROP, want_hist,
+                                 (want_hist && dtheta_smem) ? L.vocab : 0);
+  ST* const sA = reinterpret_cast<ST*>(smem_f + P.a);
+  ST* const sB = reinterpret_cast<ST*>(smem_f + P.b);
+  float* const sD = smem_f + P.d;
+  int* const sBP = reinterpret_cast<int*>(smem_f + P.bp);
+  int* const s_lp = reinterpret_cast<int*>(smem_f + P.lp);
+  int* const s_inp = reinterpret_cast<int*>(smem_f + P.inp);
+  int* const s_outp = reinterpret_cast<int*>(smem_f + P.outp);
+  int* const s_src = reinterpret_cast<int*>(smem_f + P.src);
+  float* const s_win = smem_f + P.win;
+  int* const s_dst = reinterpret_cast<int*>(smem_f + P.dst);
+  float* const s_wout = smem_f + P.wout;
+  int* const s_lab = reinterpret_cast<int*>(smem_f + P.lab);
+
+  const int b = ids ? ids[blockIdx.x] : blockIdx.x;
+  const int s_lo = L.state_off[b], Sb = L.state_off[b + 1] - s_lo;
+  const int a_lo = L.out_ptr[s_lo], Ab = L.out_ptr[s_lo + Sb] - a_lo;  // arcs are grouped by lattice in both orders
+  const int lvl0 = L.level_off[b], nlev = L.level_off[b + 1] - lvl0 - 1;
+  const int start = L.start_state[b] - s_lo;
+  float* hist = nullptr;
+  if (want_hist) {
+    if (dtheta_smem) {
+      hist = smem_f + P.hist;
+      for (int i = tid; i < L.vocab; i += NT) hist[i] = 0.0f;
+    } else {
+      hist = dtheta;
+    }
+  }
+
+  // ---- load the lattice (everything made lattice-local)
+  for (int i = tid; i <= nlev; i += NT) s_lp[i] = L.level_ptr[lvl0 + i] - s_lo;
+  for (int i = tid; i <= Sb; i += NT) {
+    if (DO_FWD) s_inp[i] = L.in_ptr[s_lo + i] - a_lo;
+    if (DO_BWD) s_outp[i] = L.out_ptr[s_lo + i] - a_lo;
+  }
+  for (int i = tid; i < Ab; i += NT) {
+    float w = SC ? arc_scores[a_lo + i] : 0.0f;
+    if (TH || want_hist) {
+      const int lab = L.label_out[a_lo + i];
+      if (TH) w += __ldg(theta + lab);
+      if (want_hist) s_lab[i] = lab;
+    }
+    s_wout[i] = w;
+    if (DO_FWD) s_src[i] = L.src_in[a_lo + i] - s_lo;
+    if (DO_BWD) s_dst[i] = L.dst_out[a_lo + i] - s_lo;
+  }
+  if (!DO_FWD && DO_BWD && POST)
+    for (int i = tid; i < Sb; i += NT) sA[i] = alpha_g[s_lo + i];
+  __syncthreads();
+  if (DO_FWD) {
+    for (int i = tid; i < Ab; i += NT) s_win[i] = s_wout[L.in2out[a_lo + i] - a_lo];  // scores in in-order
+    if (tid == 0) sA[start] = static_cast<ST>(0);
+    __syncthreads();
+  }
+
+  // lanes per state for a level of `ns` states: as many as keep the block busy (<= 32)
+  auto lanes_log2 = [&](int ns) {
+    int lg = 0;
+    while (lg < 5 && (ns << (lg + 1)) <= NT) ++lg;
+    return lg;
+  };
+
+  ST lz = 0;
+  if (DO_FWD) {
+    // ---- forward over levels 1..L-1 (level 0 is the start state)
+    for (int l = 1; l < nlev; ++l) {
+      const int sb = s_lp[l], ns = s_lp[l + 1] - sb;
+      const int lg = lanes_log2(ns), G = 1 << lg, lane_g = tid & (G - 1), ngrp = NT >> lg;
+      for (int jb = 0; jb < ns; jb += ngrp) {
+        const int j = jb + (tid >> lg);
+        const bool valid = j < ns;
+        const int s = sb + j;
+        const int b0 = valid ? s_inp[s] : 0, b1 = valid ? s_inp[s + 1] : 0;
+        ST m = static_cast<ST>(kFloor);
+        float sum = 0.0f;
+        for (int i = b0 + lane_g; i < b1; i += G) lse_push(m, sum, sA[s_src[i]] + static_cast<ST>(s_win[i]), neg_inf);
+        for (int o = G >> 1; o > 0; o >>= 1) {
+          const ST m2 = __shfl_xor_sync(0xffffffffu, m, o);
+          const float s2 = __shfl_xor_sync(0xffffffffu, sum, o);
+          lse_join(m, sum, m2, s2, neg_inf);
+        }
+        if (valid && lane_g == 0) sA[s] = lse_finish(m, sum, neg_inf);
+      }
+      __syncthreads();
+    }
+    // logZ = logsumexp over the sinks (scorers.py:795-805: every arc-less state has beta = 1)
+    ST m = neg_inf;
+    float sum = 0.0f;
+    for (int i = L.sink_off[b] + tid; i < L.sink_off[b + 1]; i += NT) lse_add(m, sum, sA[L.sinks[i] - s_lo]);
+    lz = block_lse(m, sum);
+    if (tid == 0) logz_g[b] = lz;
+    if (alpha_g)
+      for (int i = tid; i < Sb; i += NT) alpha_g[s_lo + i] = sA[i];
+  } else if (POST) {
+    lz = logz_g[b];
+  }
+
+  if (DO_BWD) {
+    float gscale = 1.0f;
+    if (POST && grad_logz) gscale = grad_logz[b];
+    // ---- backward over levels L-1..0: beta, posteriors, and/or the tropical recursion
+    for (int l = nlev - 1; l >= 0; --l) {
+      const int sb = s_lp[l], ns = s_lp[l + 1] - sb;
+      const int lg = lanes_log2(ns), G = 1 << lg, lane_g = tid & (G - 1), ngrp = NT >> lg;
+      for (int jb = 0; jb < ns; jb += ngrp) {
+        const int j = jb + (tid >> lg);
+        const bool valid = j < ns;
+        const int s = sb + j;
+        const int b0 = valid ? s_outp[s] : 0, b1 = valid ? s_outp[s + 1] : 0;
+        ST am = 0;
+        if (POST && valid) am = sA[s] - lz;
+        ST m = static_cast<ST>(kFloor);
+        float sum = 0.0f, bt = kNegInf;
+        int bi = 0x7fffffff;
+        for (int i = b0 + lane_g; i < b1; i += G) {
+          const int d = s_dst[i];
+          const float w = s_wout[i];
+          if (LOGS) {
+            const ST u = static_cast<ST>(w) + sB[d];
+            lse_push(m, sum, u, neg_inf);
+            if (POST) {
+              const float p = ex2_approx(static_cast<float>(am + u) * kLog2e) * gscale;
+              if (post) post[a_lo + i] = p;
+              if (hist) atomicAdd(&hist[s_lab[i]], p);
+            }
+          }
+          if (TROP) {
+            const float t = __fadd_rn(w, sD[d]);
+            if (t > bt) { bt = t; bi = i; }
+          }
+        }
+        for (int o = G >> 1; o > 0; o >>= 1) {
+          if (LOGS) {
+            const ST m2 = __shfl_xor_sync(0xffffffffu, m, o);
+            const float s2 = __shfl_xor_sync(0xffffffffu, sum, o);
+            lse_join(m, sum, m2, s2, neg_inf);
+          }
+          if (TROP) {
+            const float t2 = __shfl_xor_sync(0xffffffffu, bt, o);
+            const int i2 = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (t2 > bt || (t2 == bt && i2 < bi)) { bt = t2; bi = i2; }
+          }
+        }
+        if (valid && lane_g == 0) {
+          const bool sink = (b0 == b1);  // sinks: beta = 1 (scorers.py:720), delta = 0
+          if (LOGS) sB[s] = sink ? static_cast<ST>(0) : lse_finish(m, sum, neg_inf);
+          if (TROP) {
+            sD[s] = sink ? 0.0f : bt;
+            sBP[s] = sink ? -1 : a_lo + bi;
+          }
+        }
+      }
+      __syncthreads();
+    }
+    for (int i = tid; i < Sb; i += NT) {
+      if (LOGS && beta_g) beta_g[s_lo + i] = sB[i];
+      if (TROP) {
+        if (delta_g) delta_g[s_lo + i] = sD[i];
+        backptr[s_lo + i] = sBP[i];
+      }
+    }
+    if (tid == 0) {
+      if (LOGS && logz_bwd) logz_bwd[b] = sB[start];
+      if (TROP && vit_score) vit_score[b] = sD[start];
+    }
+    if (want_hist && dtheta_smem) {
+      for (int i = tid; i < L.vocab; i += NT) {
+        const float v = hist[i];
+        if (v != 0.0f) atomicAdd(&dtheta[i], v);
+      }
+    }
+  }
+}
+
+// =====================================================================================
 // level-major kernels: one launch per topological level, one block per chunk of that level,
 // over ALL lattices of the launch group.  For lattices whose levels are wide (thousands of arcs)
 // this exposes every chunk of a level at once: no in-kernel barrier, no per-lattice serial
@@ -1151,6 +1369,40 @@ int launch_fwd2(const nfst_packed_lattices_t* lat, const nfst_launch_t* launch, 
   return NFST_OK;
 }
 
+template <typename ST, bool SC, bool TH, bool DO_FWD, bool DO_BWD, bool LOGS, bool TROP, bool POST>
+int launch_small(const nfst_packed_lattices_t* lat, const nfst_launch_t* launch, const nfst_scores_t* scores,
+                 void* alpha, void* logz, const float* grad_logz, void* beta, void* logz_bwd, float* post, float* dtheta,
+                 float* delta, int32_t* backptr, float* vit_score, cudaStream_t st) {
+  const bool want_hist = POST && dtheta != nullptr;
+  const int dtheta_smem = want_hist && lat->vocab <= NFST_THETA_SMEM_MAX;
+  const SmallPlan P = small_plan(launch->small_max_states, launch->small_max_arcs, launch->small_max_levels,
+                                 sizeof(ST) / 4, DO_FWD, DO_BWD, DO_BWD && TROP, want_hist, dtheta_smem ? lat->vocab : 0);
+  const size_t bytes = static_cast<size_t>(P.words) * 4;
+  auto kernel = nfst_small_kernel<ST, SC, TH, DO_FWD, DO_BWD, LOGS, TROP, POST>;
+  if (int rc = prepare_smem(kernel, bytes)) return rc;
+  kernel<<<launch->n_ids, launch->block_threads, bytes, st>>>(
+      *lat, launch->lattice_ids, launch->small_max_states, launch->small_max_arcs, launch->small_max_levels,
+      scores->arc_scores, scores->theta, dtheta_smem, static_cast<ST*>(alpha), static_cast<ST*>(logz), grad_logz,
+      static_cast<ST*>(beta), static_cast<ST*>(logz_bwd), post, dtheta, delta, backptr, vit_score);
+  NFST_CUDA_OK(cudaGetLastError());
+  return NFST_OK;
+}
+
+// score-mode dispatch for the small path
+template <typename ST, bool DO_FWD, bool DO_BWD, bool LOGS, bool TROP, bool POST>
+int launch_small_sc(const nfst_packed_lattices_t* lat, const nfst_launch_t* launch, const nfst_scores_t* scores,
+                    void* alpha, void* logz, const float* grad_logz, void* beta, void* logz_bwd, float* post,
+                    float* dtheta, float* delta, int32_t* backptr, float* vit_score, cudaStream_t st) {
+  const bool sc = scores->arc_scores != nullptr, th = scores->theta != nullptr;
+#define NFST_SM(SC, TH)                                                                                          \
+  return launch_small<ST, SC, TH, DO_FWD, DO_BWD, LOGS, TROP, POST>(lat, launch, scores, alpha, logz, grad_logz, beta, \
+                                                                    logz_bwd, post, dtheta, delta, backptr, vit_score, st)
+  if (sc && th) NFST_SM(true, true);
+  if (sc) NFST_SM(true, false);
+  NFST_SM(false, true);
+#undef NFST_SM
+}
+
 template <typename ST, bool SC, bool TH>
 int launch_fwd_levels(const nfst_packed_lattices_t* lat, const nfst_launch_t* launch, const nfst_scores_t* scores,
                       void* alpha, void* logz, cudaStream_t st) {
@@ -1172,6 +1424,9 @@ template <typename ST>
 int launch_fwd(const nfst_packed_lattices_t* lat, const nfst_launch_t* launch, const nfst_scores_t* scores, void* alpha,
                void* logz, cudaStream_t st) {
   const bool sc = scores->arc_scores != nullptr, th = scores->theta != nullptr;
+  if (launch->small_max_arcs > 0)
+    return launch_small_sc<ST, true, false, true, false, false>(lat, launch, scores, alpha, logz, nullptr, nullptr,
+                                                                nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, st);
   if (launch->fwd_level_chunks) {
     if (sc && th) return launch_fwd_levels<ST, true, true>(lat, launch, scores, alpha, logz, st);
     if (sc) return launch_fwd_levels<ST, true, false>(lat, launch, scores, alpha, logz, st);
@@ -1229,6 +1484,14 @@ int launch_bwd(const nfst_packed_lattices_t* lat, const nfst_launch_t* launch, c
                float* dtheta, float* delta, int32_t* backptr, float* vit_score, cudaStream_t st) {
   const bool sc = scores->arc_scores != nullptr, th = scores->theta != nullptr;
   const bool ps = LOGS && (post || dtheta);
+  if (launch->small_max_arcs > 0) {
+    void* a = const_cast<void*>(alpha);
+    void* z = const_cast<void*>(logz);
+    if (ps) return launch_small_sc<ST, false, true, LOGS, TROP, LOGS>(lat, launch, scores, a, z, grad_logz, beta, logz_bwd,
+                                                                      post, dtheta, delta, backptr, vit_score, st);
+    return launch_small_sc<ST, false, true, LOGS, TROP, false>(lat, launch, scores, a, z, grad_logz, beta, logz_bwd, post,
+                                                               dtheta, delta, backptr, vit_score, st);
+  }
   if (launch->bwd_level_chunks) {
 #define NFST_GOL(SC, TH, PS)                                                                                     \
   return launch_bwd_levels<ST, LOGS, TROP, SC, TH, (LOGS && PS)>(lat, launch, scores, alpha, logz, grad_logz, beta, \
@@ -1319,8 +1582,11 @@ int nfst_bwd_fused_f32(const nfst_packed_lattices_t* lat, const nfst_launch_t* l
   const bool logs = beta || logz_bwd || want_post;
   const bool trop = delta || backptr || vit_score;
   if (!logs && !trop) return fail(NFST_ERR_BAD_ARG, "nfst_bwd_fused_f32: no output requested");
-  if (logs && !beta) return fail(NFST_ERR_BAD_ARG, "the log-semiring pass needs a beta[S] buffer (its working vector)");
-  if (trop && (!backptr || !delta)) return fail(NFST_ERR_BAD_ARG, "the tropical pass needs delta[S] and backptr[S]");
+  const bool small = launch->small_max_arcs > 0;  // small lattices keep their working vectors in shared memory
+  if (logs && !beta && !small)
+    return fail(NFST_ERR_BAD_ARG, "the log-semiring pass needs a beta[S] buffer (its working vector)");
+  if (trop && (!backptr || (!delta && !small)))
+    return fail(NFST_ERR_BAD_ARG, "the tropical pass needs delta[S] and backptr[S]");
   if (want_post && (!alpha || !logz))
     return fail(NFST_ERR_BAD_ARG, "posteriors / dtheta need alpha[S] and logz[B] from nfst_fwd_f32");
   if (launch->n_ids == 0) return NFST_OK;
@@ -1336,6 +1602,24 @@ int nfst_bwd_fused_f32(const nfst_packed_lattices_t* lat, const nfst_launch_t* l
   if (logs) return NFST_BWD(float, true, false);
   return NFST_BWD(float, false, true);
 #undef NFST_BWD
+}
+
+int nfst_fwd_bwd_small_f32(const nfst_packed_lattices_t* lat, const nfst_launch_t* launch, const nfst_scores_t* scores,
+                           const float* grad_logz, void* alpha, void* logz, void* beta, void* logz_bwd, float* post,
+                           float* dtheta, void* cuda_stream) {
+  if (int rc = check_launch(lat, launch)) return rc;
+  if (!scores || (!scores->arc_scores && !scores->theta)) return fail(NFST_ERR_BAD_ARG, "need arc_scores and/or theta");
+  if (launch->small_max_arcs <= 0) return fail(NFST_ERR_BAD_ARG, "nfst_fwd_bwd_small_f32 needs a small-lattice launch group");
+  if (!logz) return fail(NFST_ERR_BAD_ARG, "nfst_fwd_bwd_small_f32: logz is required");
+  if (launch->n_ids == 0) return NFST_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+  const bool ps = post || dtheta;
+  if (launch->state_f64) {
+    if (ps) return launch_small_sc<double, true, true, true, false, true>(lat, launch, scores, alpha, logz, grad_logz, beta, logz_bwd, post, dtheta, nullptr, nullptr, nullptr, st);
+    return launch_small_sc<double, true, true, true, false, false>(lat, launch, scores, alpha, logz, grad_logz, beta, logz_bwd, post, dtheta, nullptr, nullptr, nullptr, st);
+  }
+  if (ps) return launch_small_sc<float, true, true, true, false, true>(lat, launch, scores, alpha, logz, grad_logz, beta, logz_bwd, post, dtheta, nullptr, nullptr, nullptr, st);
+  return launch_small_sc<float, true, true, true, false, false>(lat, launch, scores, alpha, logz, grad_logz, beta, logz_bwd, post, dtheta, nullptr, nullptr, nullptr, st);
 }
 
 int nfst_viterbi_f32(const nfst_packed_lattices_t* lat, const nfst_launch_t* launch, const nfst_scores_t* scores,

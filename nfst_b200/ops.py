@@ -78,6 +78,7 @@ def _launch(g: LaunchGroup, st_dtype: torch.dtype) -> "_lib.LaunchC":
     c.window_states = g.window_states(8 if f64 else 4, WINDOW_BYTES_MAX)
     c.state_f64 = int(f64)
     c.chunk_cap = g.chunk_cap
+    c.small_max_states, c.small_max_arcs, c.small_max_levels = g.small_max_states, g.small_max_arcs, g.small_max_levels
     if g.fwd_level_chunks is not None:  # level-major group: one launch per topological level
         c.n_levels = g.n_levels
         c.fwd_level_chunks = g.fwd_level_chunks.data_ptr()
@@ -188,13 +189,41 @@ def lattice_forward_backward(packed: PackedLattices, arc_scores=None, theta=None
     """(logZ[B], alpha[S], beta[S], post[A]) -- plus dtheta[V] when ``want_dtheta``.
 
     logZ is ``beta[start]`` (the reference's definition, ``log beta[0]``); posteriors are
-    normalised with the forward logZ and agree to round-off."""
-    alpha, logz_f = lattice_forward(packed, arc_scores, theta, state_dtype=state_dtype)
-    r = lattice_backward(packed, arc_scores, theta, alpha=alpha, logz=logz_f, want_beta=True, want_post=True,
-                         want_dtheta=want_dtheta)
+    normalised with the forward logZ and agree to round-off.  Groups of small lattices run
+    forward + backward in ONE launch (``nfst_fwd_bwd_small_f32``: the lattice lives in shared
+    memory, alpha never leaves the SM); the others run the forward and the fused backward
+    kernels back to back."""
+    global launch_count
+    lib = _lib.load()
+    dev = packed.device
+    sc, keep = _scores(packed, arc_scores, theta)
+    st = resolve_state_dtype(packed, state_dtype)
+    S, A, B, V = packed.n_states, packed.n_arcs, packed.n_lattices, packed.vocab
+    alpha = torch.empty(S, dtype=st, device=dev)
+    beta = torch.empty(S, dtype=st, device=dev)
+    logz = torch.empty(B, dtype=st, device=dev)
+    logz_bwd = torch.empty(B, dtype=st, device=dev)
+    post = torch.empty(A, dtype=torch.float32, device=dev)
+    dtheta = torch.zeros(V, dtype=torch.float32, device=dev) if want_dtheta else None
+    with torch.cuda.device(dev):
+        stream = _stream(dev)
+        for g in packed.groups:
+            lc = _launch(g, st)
+            if g.small_max_arcs > 0:
+                _lib.check(lib.nfst_fwd_bwd_small_f32(packed.c_struct(), lc, sc, None, alpha.data_ptr(), logz.data_ptr(),
+                                                      beta.data_ptr(), logz_bwd.data_ptr(), post.data_ptr(),
+                                                      _ptr(dtheta), stream))
+                launch_count += 1
+            else:
+                _lib.check(lib.nfst_fwd_f32(packed.c_struct(), lc, sc, alpha.data_ptr(), logz.data_ptr(), stream))
+                _lib.check(lib.nfst_bwd_fused_f32(packed.c_struct(), lc, sc, alpha.data_ptr(), logz.data_ptr(), None,
+                                                  beta.data_ptr(), logz_bwd.data_ptr(), post.data_ptr(), _ptr(dtheta),
+                                                  None, None, None, stream))
+                launch_count += 2
+    del keep
     if want_dtheta:
-        return r["logz_bwd"], alpha, r["beta"], r["post"], r["dtheta"]
-    return r["logz_bwd"], alpha, r["beta"], r["post"]
+        return logz_bwd, alpha, beta, post, dtheta
+    return logz_bwd, alpha, beta, post
 
 
 class LatticeLogPartition(torch.autograd.Function):

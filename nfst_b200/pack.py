@@ -40,6 +40,15 @@ HEAVY_DIV = 4
 # lattices whose widest level has at least this many arcs run level-major (one launch per
 # topological level over all their chunks) instead of one block per lattice
 LEVEL_MODE_MIN_ARCS = int(os.environ.get("NFST_LEVEL_MODE_MIN", "4096"))
+# lattices whose whole working set fits this much shared memory run in one piece (nfst_small_kernel)
+SMALL_SMEM_BYTES = int(os.environ.get("NFST_SMALL_SMEM_BYTES", str(64 * 1024)))
+SMALL_BLOCK_MIN = int(os.environ.get("NFST_SMALL_BLOCK", "64"))
+
+
+def small_footprint_bytes(states, arcs, levels, vocab):
+    """Upper bound of nfst_small_kernel's shared memory for one lattice (fp64 state, both
+    semirings, labels and a dtheta histogram)."""
+    return 4 * (6 * states + (levels + 1) + 2 * (states + 1) + 5 * arcs + min(vocab, 4096) + 64)
 DEGREE_SORT = int(os.environ.get("NFST_DEGREE_SORT", "1"))
 
 
@@ -69,6 +78,10 @@ class LaunchGroup:
     bwd_level_chunks: Optional[torch.Tensor] = None
     bwd_level_off: Optional[torch.Tensor] = None
     bwd_level_lat: Optional[torch.Tensor] = None  # int32 [n] device
+    # small-lattice execution: every lattice of the group fits in shared memory
+    small_max_states: int = 0
+    small_max_arcs: int = 0
+    small_max_levels: int = 0
 
     def to(self, device, non_blocking: bool = False) -> "LaunchGroup":
         mv = lambda t: None if t is None else t.to(device, non_blocking=non_blocking)  # noqa: E731
@@ -255,7 +268,9 @@ def build_groups(stats, dev, chunk_info=None) -> List[LaunchGroup]:
     launch; heaviest lattices first (longest-processing-time order).  Lattices with wide
     levels form level-major groups (see LaunchGroup / nfst_launch_t)."""
     wide = (stats["width_arcs"] >= LEVEL_MODE_MIN_ARCS).to(torch.int64)
-    gkey = stats["block_class"] * 2 + wide
+    small = (small_footprint_bytes(stats["states"], stats["arcs"], stats["levels"], int(stats["vocab"][0]))
+             <= SMALL_SMEM_BYTES).to(torch.int64) * (1 - wide)
+    gkey = (stats["block_class"] * 2 + wide) * 2 + small
     groups: List[LaunchGroup] = []
     B = int(gkey.numel())
     for key in sorted(set(gkey.tolist()), reverse=True):
@@ -264,13 +279,18 @@ def build_groups(stats, dev, chunk_info=None) -> List[LaunchGroup]:
         g = LaunchGroup(
             ids=members.to(torch.int32).to(dev),
             n=int(members.numel()),
-            block_threads=1 << (key >> 1),
+            block_threads=1 << (key >> 2),
             max_states=int(stats["states"][members].max()),
             max_reach=int(stats["reach"][members].max()),
             n_arcs=int(stats["arcs"][members].sum()),
             chunk_cap=int(stats["chunk_cap"][members].max()),
         )
-        if (key & 1) and chunk_info is not None:
+        if key & 1:
+            g.block_threads = max(g.block_threads, SMALL_BLOCK_MIN)
+            g.small_max_states = int(stats["states"][members].max())
+            g.small_max_arcs = max(int(stats["arcs"][members].max()), 1)
+            g.small_max_levels = int(stats["levels"][members].max())
+        if (key & 2) and chunk_info is not None:
             member_mask = torch.zeros(B, dtype=torch.bool, device=dev)
             member_mask[members.to(dev)] = True
             n_levels = int(stats["levels"][members].max())
@@ -510,6 +530,7 @@ def pack_arcs(
         "states": S_b.cpu(),
         "levels": n_levels.cpu(),
         "block_class": block_class.cpu(),
+        "vocab": torch.full((B,), int(vocab), dtype=torch.int64),
         "chunk_cap": geo[block_class, 2].cpu(),
         "reach": reach.cpu(),
     }

@@ -53,9 +53,28 @@ def tiny_window(monkeypatch):
     monkeypatch.setattr(nb.ops, "WINDOW_BYTES_MAX", 128)
 
 
+@pytest.fixture(params=["auto", "block", "level"])
+def exec_mode(request, monkeypatch):
+    """Every execution model on the same inputs: "auto" (small lattices take the fused
+    shared-memory kernel), "block" (one block per lattice, cp.async pipeline), "level" (one
+    launch per topological level)."""
+    if request.param == "block":
+        monkeypatch.setattr(nb.pack, "SMALL_SMEM_BYTES", 0)
+    elif request.param == "level":
+        monkeypatch.setattr(nb.pack, "SMALL_SMEM_BYTES", 0)
+        monkeypatch.setattr(nb.pack, "LEVEL_MODE_MIN_ARCS", 1)
+    return request.param
+
+
+@pytest.fixture
+def block_mode(monkeypatch):
+    monkeypatch.setattr(nb.pack, "SMALL_SMEM_BYTES", 0)
+
+
 @pytest.fixture
 def level_major(monkeypatch):
     """Run every lattice level-major (one launch per topological level over all chunks)."""
+    monkeypatch.setattr(nb.pack, "SMALL_SMEM_BYTES", 0)
     monkeypatch.setattr(nb.pack, "LEVEL_MODE_MIN_ARCS", 1)
 
 
@@ -131,7 +150,7 @@ def test_logz_brackets_reference_iwae_golden():
 # oracle parity on seeded inputs
 # --------------------------------------------------------------------------------------
 @pytest.mark.parametrize("seed", [0, 1, 2, 3])
-def test_dense_tables_fwd_bwd_vs_oracle(seed):
+def test_dense_tables_fwd_bwd_vs_oracle(seed, exec_mode):
     rng = np.random.default_rng(seed)
     tabs = [random_mark_lattice(rng, int(n), 32, parallel_arcs=bool(i % 2))[1]
             for i, n in enumerate(rng.integers(1, 60, size=9))]
@@ -168,17 +187,19 @@ def test_dense_tables_fwd_bwd_vs_oracle(seed):
 
 
 @pytest.mark.parametrize("state_dtype", [torch.float32, torch.float64])
-def test_transliteration_batch_config1(state_dtype):
-    check_fwd_bwd(synth.transliteration_batch(32, seed=0), state_dtype=state_dtype)
+def test_transliteration_batch_config1(state_dtype, exec_mode):
+    p, _, _ = check_fwd_bwd(synth.transliteration_batch(32, seed=0), state_dtype=state_dtype)
+    assert all((g.small_max_arcs > 0) == (exec_mode == "auto") for g in p.groups)
+    assert all((g.fwd_level_chunks is not None) == (exec_mode == "level") for g in p.groups)
 
 
-def test_transliteration_batch_tiny_window(tiny_window):
+def test_transliteration_batch_tiny_window(tiny_window, block_mode):
     p, _, _ = check_fwd_bwd(synth.transliteration_batch(32, seed=0))
     assert nb.ops._launch(p.groups[0], torch.float32).window_states == 32
 
 
 @pytest.mark.parametrize("state_dtype", [torch.float32, torch.float64])
-def test_snips_batch_config2_sample(state_dtype):
+def test_snips_batch_config2_sample(state_dtype, exec_mode):
     check_fwd_bwd(synth.snips_batch(24, seed=1), state_dtype=state_dtype)
 
 
@@ -220,7 +241,7 @@ def test_random_dag_tiny_window_and_heavy_states(tiny_window):
     check_fwd_bwd(synth.random_dag_batch(3, 10_000, levels=64, seed=6), state_dtype=torch.float64)
 
 
-def test_autograd_posteriors_and_dtheta():
+def test_autograd_posteriors_and_dtheta(exec_mode):
     ab = synth.transliteration_batch(12, seed=5)
     p, sc = ab.to(DEV).pack()
     sc = sc.clone().requires_grad_(True)
@@ -256,7 +277,7 @@ def test_autograd_posteriors_and_dtheta():
 # Viterbi: bit-exact
 # --------------------------------------------------------------------------------------
 @pytest.mark.parametrize("integer_scores", [False, True])
-def test_viterbi_bit_exact_config5_sample(integer_scores):
+def test_viterbi_bit_exact_config5_sample(integer_scores, exec_mode):
     ab = synth.transliteration_batch(256, seed=4, integer_scores=integer_scores)
     p, sc = ab.to(DEV).pack()
     score, off, arcs, labels = nb.lattice_viterbi(p, arc_scores=sc)
@@ -285,7 +306,7 @@ def test_viterbi_dense_golden_lattices_with_ties_and_theta():
         assert labels.cpu().tolist() == list(vl)
 
 
-def test_fused_backward_emits_beta_and_backpointers_in_one_pass():
+def test_fused_backward_emits_beta_and_backpointers_in_one_pass(exec_mode):
     ab = synth.snips_batch(8, seed=11)
     p, sc = ab.to(DEV).pack()
     alpha, logz = nb.lattice_forward(p, arc_scores=sc)
