@@ -726,24 +726,28 @@ __global__ void __launch_bounds__(256, NFST_MIN_BLOCKS)
 // never leaving the SM; or as two launches around an autograd boundary.
 // =====================================================================================
 struct SmallPlan {  // offsets in 32-bit words
-  int a, b, d, lp, inp, outp, src, win, dst, wout, lab, bp, hist, words;
+  int a, b, d, lp, lg, inp, outp, src, win, dst, wout, lab, bp, hist, words;
 };
+// Lattice-local state and arc indices are 16-bit (a small lattice has < 65536 of either).
+typedef unsigned short small_idx_t;
 __host__ __device__ inline SmallPlan small_plan(int S, int A, int Lv, int st_words, bool fwd, bool bwd, bool trop,
                                                 bool labels, int hist_words) {
   SmallPlan p;
   int o = 0;
   auto take = [&](int n) { const int at = o; o += (n + 3) & ~3; return at; };
+  auto take16 = [&](int n) { return take((n + 1) >> 1); };
   p.a = take(S * st_words);
   p.b = take(bwd ? S * st_words : 0);
   p.d = take(trop ? S : 0);
   p.bp = take(trop ? S : 0);
   p.lp = take(Lv + 1);
-  p.inp = take(fwd ? S + 1 : 0);
-  p.outp = take(bwd ? S + 1 : 0);
-  p.src = take(fwd ? A : 0);
+  p.lg = take(Lv + 1);
+  p.inp = take16(fwd ? S + 1 : 0);
+  p.outp = take16(bwd ? S + 1 : 0);
+  p.src = take16(fwd ? A : 0);
   p.win = take(fwd ? A : 0);
-  p.dst = take(bwd ? A : 0);
-  p.wout = take(A);
+  p.dst = take16(bwd ? A : 0);
+  p.wout = take(bwd ? A : 0);
   p.lab = take(labels ? A : 0);
   p.hist = take(hist_words);
   p.words = o;
@@ -768,11 +772,11 @@ __global__ void __launch_bounds__(256, 4)
   float* const sD = smem_f + P.d;
   int* const sBP = reinterpret_cast<int*>(smem_f + P.bp);
   int* const s_lp = reinterpret_cast<int*>(smem_f + P.lp);
-  int* const s_inp = reinterpret_cast<int*>(smem_f + P.inp);
-  int* const s_outp = reinterpret_cast<int*>(smem_f + P.outp);
-  int* const s_src = reinterpret_cast<int*>(smem_f + P.src);
+  small_idx_t* const s_inp = reinterpret_cast<small_idx_t*>(smem_f + P.inp);
+  small_idx_t* const s_outp = reinterpret_cast<small_idx_t*>(smem_f + P.outp);
+  small_idx_t* const s_src = reinterpret_cast<small_idx_t*>(smem_f + P.src);
   float* const s_win = smem_f + P.win;
-  int* const s_dst = reinterpret_cast<int*>(smem_f + P.dst);
+  small_idx_t* const s_dst = reinterpret_cast<small_idx_t*>(smem_f + P.dst);
   float* const s_wout = smem_f + P.wout;
   int* const s_lab = reinterpret_cast<int*>(smem_f + P.lab);
 
@@ -791,62 +795,151 @@ __global__ void __launch_bounds__(256, 4)
     }
   }
 
-  // ---- load the lattice (everything made lattice-local)
+  NFST_T(t_start);
+  // ---- load the lattice (everything made lattice-local); all global loads are independent
   for (int i = tid; i <= nlev; i += NT) s_lp[i] = L.level_ptr[lvl0 + i] - s_lo;
   for (int i = tid; i <= Sb; i += NT) {
-    if (DO_FWD) s_inp[i] = L.in_ptr[s_lo + i] - a_lo;
-    if (DO_BWD) s_outp[i] = L.out_ptr[s_lo + i] - a_lo;
+    if (DO_FWD) s_inp[i] = static_cast<small_idx_t>(L.in_ptr[s_lo + i] - a_lo);
+    if (DO_BWD) s_outp[i] = static_cast<small_idx_t>(L.out_ptr[s_lo + i] - a_lo);
   }
   for (int i = tid; i < Ab; i += NT) {
-    float w = SC ? arc_scores[a_lo + i] : 0.0f;
-    if (TH || want_hist) {
-      const int lab = L.label_out[a_lo + i];
-      if (TH) w += __ldg(theta + lab);
-      if (want_hist) s_lab[i] = lab;
+    if (DO_BWD) {
+      float w = SC ? arc_scores[a_lo + i] : 0.0f;
+      if (TH || want_hist) {
+        const int lab = L.label_out[a_lo + i];
+        if (TH) w += __ldg(theta + lab);
+        if (want_hist) s_lab[i] = lab;
+      }
+      s_wout[i] = w;
+      s_dst[i] = static_cast<small_idx_t>(L.dst_out[a_lo + i] - s_lo);
     }
-    s_wout[i] = w;
-    if (DO_FWD) s_src[i] = L.src_in[a_lo + i] - s_lo;
-    if (DO_BWD) s_dst[i] = L.dst_out[a_lo + i] - s_lo;
+    if (DO_FWD) {
+      float w = SC ? arc_scores[L.in2out[a_lo + i]] : 0.0f;  // scores in in-order
+      if (TH) w += __ldg(theta + L.label_in[a_lo + i]);
+      s_win[i] = w;
+      s_src[i] = static_cast<small_idx_t>(L.src_in[a_lo + i] - s_lo);
+    }
   }
   if (!DO_FWD && DO_BWD && POST)
     for (int i = tid; i < Sb; i += NT) sA[i] = alpha_g[s_lo + i];
+  if (DO_FWD && tid == 0) sA[start] = static_cast<ST>(0);
   __syncthreads();
-  if (DO_FWD) {
-    for (int i = tid; i < Ab; i += NT) s_win[i] = s_wout[L.in2out[a_lo + i] - a_lo];  // scores in in-order
-    if (tid == 0) sA[start] = static_cast<ST>(0);
-    __syncthreads();
+  // Level schedule, once: 2^lg lanes per state for every level and direction -- about two arcs
+  // per lane, never more lanes than fill the block; lg = 0 (one thread per state) is the lean
+  // path below.  Kept in the spare high bits of the level pointers (bits 24-26 fwd, 28-30 bwd).
+  constexpr int kLvMask = 0xffffff;
+  int* const s_lg = reinterpret_cast<int*>(smem_f + P.lg);
+  for (int l = tid; l < nlev; l += NT) {
+    const int sb = s_lp[l], se = s_lp[l + 1], ns = se - sb;
+    int enc = 0;
+    if (DO_FWD) {
+      const int na = s_inp[se] - s_inp[sb];
+      int lg = 0;
+      while (lg < 5 && (ns << (lg + 1)) <= NT && (ns << (lg + 2)) <= na) ++lg;
+      enc |= lg << 24;
+    }
+    if (DO_BWD) {
+      const int na = s_outp[se] - s_outp[sb];
+      int lg = 0;
+      while (lg < 5 && (ns << (lg + 1)) <= NT && (ns << (lg + 2)) <= na) ++lg;
+      enc |= lg << 28;
+    }
+    s_lg[l] = enc;
   }
+  __syncthreads();
+  for (int l = tid; l < nlev; l += NT) s_lp[l] |= s_lg[l];
+  __syncthreads();
 
-  // lanes per state for a level of `ns` states: as many as keep the block busy (<= 32)
-  auto lanes_log2 = [&](int ns) {
-    int lg = 0;
-    while (lg < 5 && (ns << (lg + 1)) <= NT) ++lg;
-    return lg;
+  NFST_T(t_loaded);
+  NFST_ACC(tid == 0, 16, t_loaded - t_start);
+  NFST_ACC(tid == 0, 20, 1);
+  NFST_ACC(tid == 0, 21, nlev);
+  // One warp per lattice needs no block barrier.
+  auto level_barrier = [&]() {
+    if (NT == 32) __syncwarp(); else __syncthreads();
+  };
+  // Software pipeline over levels (registers): none of a level's index data depends on DP
+  // values, so the level pointers are fetched three levels ahead, this thread's CSR range two
+  // levels ahead and its first two arcs one level ahead.  What is left on the level-to-level
+  // critical path is: DP value of the neighbour (LDS) -> add -> [max, exp, log] -> store -> barrier.
+  struct Range { int b0, b1; };
+  struct Arc2 { int n0, n1; float w0, w1; };
+  auto load_range = [&](int enc, int enc_next, const small_idx_t* s_ptr) {
+    const int s = (enc & kLvMask) + tid;
+    Range r{0, 0};
+    if (s < (enc_next & kLvMask)) { r.b0 = s_ptr[s]; r.b1 = s_ptr[s + 1]; }
+    return r;
+  };
+  auto load_arcs = [&](const Range& r, const small_idx_t* s_nbr, const float* s_w) {
+    Arc2 q{0, 0, 0.0f, 0.0f};
+    if (r.b0 < r.b1) { q.n0 = s_nbr[r.b0]; q.w0 = s_w[r.b0]; }
+    if (r.b0 + 1 < r.b1) { q.n1 = s_nbr[r.b0 + 1]; q.w1 = s_w[r.b0 + 1]; }
+    return q;
   };
 
   ST lz = 0;
   if (DO_FWD) {
     // ---- forward over levels 1..L-1 (level 0 is the start state)
-    for (int l = 1; l < nlev; ++l) {
-      const int sb = s_lp[l], ns = s_lp[l + 1] - sb;
-      const int lg = lanes_log2(ns), G = 1 << lg, lane_g = tid & (G - 1), ngrp = NT >> lg;
-      for (int jb = 0; jb < ns; jb += ngrp) {
-        const int j = jb + (tid >> lg);
-        const bool valid = j < ns;
-        const int s = sb + j;
-        const int b0 = valid ? s_inp[s] : 0, b1 = valid ? s_inp[s + 1] : 0;
-        ST m = static_cast<ST>(kFloor);
-        float sum = 0.0f;
-        for (int i = b0 + lane_g; i < b1; i += G) lse_push(m, sum, sA[s_src[i]] + static_cast<ST>(s_win[i]), neg_inf);
-        for (int o = G >> 1; o > 0; o >>= 1) {
-          const ST m2 = __shfl_xor_sync(0xffffffffu, m, o);
-          const float s2 = __shfl_xor_sync(0xffffffffu, sum, o);
-          lse_join(m, sum, m2, s2, neg_inf);
-        }
-        if (valid && lane_g == 0) sA[s] = lse_finish(m, sum, neg_inf);
+    auto lv = [&](int l) { return s_lp[min(l, max(nlev, 0))]; };
+    // one state from its arcs: logsumexp in two passes (max, then exp-sum); one arc = plain add
+    auto fwd_state = [&](int s, const Range& r, const Arc2& q) {
+      const int deg = r.b1 - r.b0;
+      const ST u0 = sA[q.n0] + static_cast<ST>(q.w0);
+      ST v = u0;
+      if (deg > 1) {
+        const ST u1 = sA[q.n1] + static_cast<ST>(q.w1);
+        ST m = max(max(u0, u1), static_cast<ST>(kFloor));
+        for (int i = r.b0 + 2; i < r.b1; ++i) m = max(m, sA[s_src[i]] + static_cast<ST>(s_win[i]));
+        float sum = ex2_approx(static_cast<float>(u0 - m) * kLog2e) + ex2_approx(static_cast<float>(u1 - m) * kLog2e);
+        for (int i = r.b0 + 2; i < r.b1; ++i)
+          sum += ex2_approx(static_cast<float>(sA[s_src[i]] + static_cast<ST>(s_win[i]) - m) * kLog2e);
+        v = sum > 0.0f ? m + static_cast<ST>(lg2_approx(sum) * kLn2) : neg_inf;
       }
-      __syncthreads();
+      sA[s] = v;
+    };
+    int e0 = lv(1), e1 = lv(2), e2 = lv(3), e3 = lv(4);
+    Range r0 = load_range(e0, e1, s_inp), r1 = load_range(e1, e2, s_inp);
+    Arc2 q0 = load_arcs(r0, s_src, s_win);
+    for (int l = 1; l < nlev; ++l) {
+      const int e4 = lv(l + 4);
+      const Range r2 = load_range(e2, e3, s_inp);
+      const Arc2 q1 = load_arcs(r1, s_src, s_win);
+      const int sb = e0 & kLvMask, se = e1 & kLvMask, lg = (e0 >> 24) & 7;
+      if (lg == 0) {
+        int s = sb + tid;
+        if (s < se) fwd_state(s, r0, q0);
+        for (s += NT; s < se; s += NT) {
+          const Range r{s_inp[s], s_inp[s + 1]};
+          fwd_state(s, r, load_arcs(r, s_src, s_win));
+        }
+      } else {
+        // lanes-per-state path: G lanes stride over a state's arcs, two shuffle trees (max, sum)
+        const int G = 1 << lg, lane_g = tid & (G - 1), ngrp = NT >> lg, ns = se - sb;
+        for (int jb = 0; jb < ns; jb += ngrp) {
+          const int j = jb + (tid >> lg);
+          const bool valid = j < ns;
+          const int b0 = valid ? s_inp[sb + j] : 0, b1 = valid ? s_inp[sb + j + 1] : 0;
+          const int i0 = b0 + lane_g, i1 = i0 + G;
+          ST u0 = neg_inf, u1 = neg_inf;
+          if (i0 < b1) u0 = sA[s_src[i0]] + static_cast<ST>(s_win[i0]);
+          if (i1 < b1) u1 = sA[s_src[i1]] + static_cast<ST>(s_win[i1]);
+          ST m = max(max(u0, u1), static_cast<ST>(kFloor));
+          for (int i = i1 + G; i < b1; i += G) m = max(m, sA[s_src[i]] + static_cast<ST>(s_win[i]));
+          for (int o = G >> 1; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+          float sum = ex2_approx(static_cast<float>(u0 - m) * kLog2e) + ex2_approx(static_cast<float>(u1 - m) * kLog2e);
+          for (int i = i1 + G; i < b1; i += G)
+            sum += ex2_approx(static_cast<float>(sA[s_src[i]] + static_cast<ST>(s_win[i]) - m) * kLog2e);
+          for (int o = G >> 1; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+          if (valid && lane_g == 0)
+            sA[sb + j] = sum > 0.0f ? m + static_cast<ST>(lg2_approx(sum) * kLn2) : neg_inf;
+        }
+      }
+      level_barrier();
+      e0 = e1; e1 = e2; e2 = e3; e3 = e4;
+      r0 = r1; r1 = r2; q0 = q1;
     }
+    NFST_T(t_fwd);
+    NFST_ACC(tid == 0, 17, t_fwd - t_loaded);
     // logZ = logsumexp over the sinks (scorers.py:795-805: every arc-less state has beta = 1)
     ST m = neg_inf;
     float sum = 0.0f;
@@ -863,59 +956,143 @@ __global__ void __launch_bounds__(256, 4)
     float gscale = 1.0f;
     if (POST && grad_logz) gscale = grad_logz[b];
     // ---- backward over levels L-1..0: beta, posteriors, and/or the tropical recursion
+    NFST_T(t_bwd0);
+    auto lv = [&](int l) { return s_lp[max(l, 0)]; };       // level l's encoded pointer
+    auto lv_end = [&](int l) { return s_lp[min(max(l, 0) + 1, max(nlev, 0))]; };  // its end = next level's pointer
+    // pass 1 of one arc: posterior + tropical candidate; returns the log-semiring term
+    auto bwd_state = [&](int s, const Range& r, const Arc2& q, ST am) {
+      const int deg = r.b1 - r.b0;
+      if (deg == 0) {  // sinks: beta = 1 (scorers.py:720), delta = 0
+        if (LOGS) sB[s] = static_cast<ST>(0);
+        if (TROP) { sD[s] = 0.0f; sBP[s] = -1; }
+        return;
+      }
+      float bt = kNegInf;
+      int bi = 0x7fffffff;
+      auto visit = [&](int i, int d, float w) -> ST {
+        ST u = neg_inf;
+        if (LOGS) {
+          u = static_cast<ST>(w) + sB[d];
+          if (POST) {
+            const float pz = ex2_approx(static_cast<float>(am + u) * kLog2e) * gscale;
+            if (post) post[a_lo + i] = pz;
+            if (hist) atomicAdd(&hist[s_lab[i]], pz);
+          }
+        }
+        if (TROP) {
+          const float t = __fadd_rn(w, sD[d]);
+          if (t > bt) { bt = t; bi = i; }
+        }
+        return u;
+      };
+      const ST u0 = visit(r.b0, q.n0, q.w0);
+      ST v = u0;
+      if (deg > 1) {
+        const ST u1 = visit(r.b0 + 1, q.n1, q.w1);
+        ST m = max(max(u0, u1), static_cast<ST>(kFloor));
+        for (int i = r.b0 + 2; i < r.b1; ++i) {
+          const ST u = visit(i, s_dst[i], s_wout[i]);
+          if (LOGS) m = max(m, u);
+        }
+        if (LOGS) {
+          float sum = ex2_approx(static_cast<float>(u0 - m) * kLog2e) + ex2_approx(static_cast<float>(u1 - m) * kLog2e);
+          for (int i = r.b0 + 2; i < r.b1; ++i)
+            sum += ex2_approx(static_cast<float>(static_cast<ST>(s_wout[i]) + sB[s_dst[i]] - m) * kLog2e);
+          v = sum > 0.0f ? m + static_cast<ST>(lg2_approx(sum) * kLn2) : neg_inf;
+        }
+      }
+      if (LOGS) sB[s] = v;
+      if (TROP) { sD[s] = bt; sBP[s] = a_lo + bi; }
+    };
+    int e0 = lv(nlev - 1), f0 = lv_end(nlev - 1), e1 = lv(nlev - 2), e2 = lv(nlev - 3), e3 = lv(nlev - 4);
+    Range r0 = load_range(e0, f0, s_outp), r1 = load_range(e1, e0, s_outp);
+    Arc2 q0 = load_arcs(r0, s_dst, s_wout);
+    ST am0 = 0;
+    if (POST && (e0 & kLvMask) + tid < (f0 & kLvMask)) am0 = sA[(e0 & kLvMask) + tid] - lz;
     for (int l = nlev - 1; l >= 0; --l) {
-      const int sb = s_lp[l], ns = s_lp[l + 1] - sb;
-      const int lg = lanes_log2(ns), G = 1 << lg, lane_g = tid & (G - 1), ngrp = NT >> lg;
-      for (int jb = 0; jb < ns; jb += ngrp) {
-        const int j = jb + (tid >> lg);
-        const bool valid = j < ns;
-        const int s = sb + j;
-        const int b0 = valid ? s_outp[s] : 0, b1 = valid ? s_outp[s + 1] : 0;
-        ST am = 0;
-        if (POST && valid) am = sA[s] - lz;
-        ST m = static_cast<ST>(kFloor);
-        float sum = 0.0f, bt = kNegInf;
-        int bi = 0x7fffffff;
-        for (int i = b0 + lane_g; i < b1; i += G) {
-          const int d = s_dst[i];
-          const float w = s_wout[i];
-          if (LOGS) {
-            const ST u = static_cast<ST>(w) + sB[d];
-            lse_push(m, sum, u, neg_inf);
-            if (POST) {
-              const float p = ex2_approx(static_cast<float>(am + u) * kLog2e) * gscale;
-              if (post) post[a_lo + i] = p;
-              if (hist) atomicAdd(&hist[s_lab[i]], p);
+      const int e4 = lv(l - 4);
+      const Range r2 = load_range(e2, e1, s_outp);
+      const Arc2 q1 = load_arcs(r1, s_dst, s_wout);
+      ST am1 = 0;
+      if (POST && (e1 & kLvMask) + tid < (e0 & kLvMask)) am1 = sA[(e1 & kLvMask) + tid] - lz;
+      const int sb = e0 & kLvMask, se = f0 & kLvMask, lg = (e0 >> 28) & 7;
+      if (lg == 0) {
+        int s = sb + tid;
+        if (s < se) bwd_state(s, r0, q0, am0);
+        for (s += NT; s < se; s += NT) {
+          const Range r{s_outp[s], s_outp[s + 1]};
+          ST am = 0;
+          if (POST) am = sA[s] - lz;
+          bwd_state(s, r, load_arcs(r, s_dst, s_wout), am);
+        }
+      } else {
+        const int G = 1 << lg, lane_g = tid & (G - 1), ngrp = NT >> lg, ns = se - sb;
+        for (int jb = 0; jb < ns; jb += ngrp) {
+          const int j = jb + (tid >> lg);
+          const bool valid = j < ns;
+          const int s = sb + j;
+          const int b0 = valid ? s_outp[s] : 0, b1 = valid ? s_outp[s + 1] : 0;
+          ST am = 0;
+          if (POST && valid) am = sA[s] - lz;
+          ST m = static_cast<ST>(kFloor), u0 = neg_inf, u1 = neg_inf;
+          float sum = 0.0f, bt = kNegInf;
+          int bi = 0x7fffffff;
+          auto visit = [&](int i) -> ST {
+            const int d = s_dst[i];
+            const float w = s_wout[i];
+            ST u = neg_inf;
+            if (LOGS) {
+              u = static_cast<ST>(w) + sB[d];
+              if (POST) {
+                const float pz = ex2_approx(static_cast<float>(am + u) * kLog2e) * gscale;
+                if (post) post[a_lo + i] = pz;
+                if (hist) atomicAdd(&hist[s_lab[i]], pz);
+              }
+            }
+            if (TROP) {
+              const float t = __fadd_rn(w, sD[d]);
+              if (t > bt) { bt = t; bi = i; }
+            }
+            return u;
+          };
+          const int i0 = b0 + lane_g, i1 = i0 + G;
+          if (i0 < b1) u0 = visit(i0);
+          if (i1 < b1) u1 = visit(i1);
+          if (LOGS) m = max(max(u0, u1), m);
+          for (int i = i1 + G; i < b1; i += G) {
+            const ST u = visit(i);
+            if (LOGS) m = max(m, u);
+          }
+          for (int o = G >> 1; o > 0; o >>= 1) {
+            if (LOGS) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+            if (TROP) {
+              const float t2 = __shfl_xor_sync(0xffffffffu, bt, o);
+              const int i2 = __shfl_xor_sync(0xffffffffu, bi, o);
+              if (t2 > bt || (t2 == bt && i2 < bi)) { bt = t2; bi = i2; }
             }
           }
-          if (TROP) {
-            const float t = __fadd_rn(w, sD[d]);
-            if (t > bt) { bt = t; bi = i; }
-          }
-        }
-        for (int o = G >> 1; o > 0; o >>= 1) {
           if (LOGS) {
-            const ST m2 = __shfl_xor_sync(0xffffffffu, m, o);
-            const float s2 = __shfl_xor_sync(0xffffffffu, sum, o);
-            lse_join(m, sum, m2, s2, neg_inf);
+            sum = ex2_approx(static_cast<float>(u0 - m) * kLog2e) + ex2_approx(static_cast<float>(u1 - m) * kLog2e);
+            for (int i = i1 + G; i < b1; i += G)
+              sum += ex2_approx(static_cast<float>(static_cast<ST>(s_wout[i]) + sB[s_dst[i]] - m) * kLog2e);
+            for (int o = G >> 1; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
           }
-          if (TROP) {
-            const float t2 = __shfl_xor_sync(0xffffffffu, bt, o);
-            const int i2 = __shfl_xor_sync(0xffffffffu, bi, o);
-            if (t2 > bt || (t2 == bt && i2 < bi)) { bt = t2; bi = i2; }
-          }
-        }
-        if (valid && lane_g == 0) {
-          const bool sink = (b0 == b1);  // sinks: beta = 1 (scorers.py:720), delta = 0
-          if (LOGS) sB[s] = sink ? static_cast<ST>(0) : lse_finish(m, sum, neg_inf);
-          if (TROP) {
-            sD[s] = sink ? 0.0f : bt;
-            sBP[s] = sink ? -1 : a_lo + bi;
+          if (valid && lane_g == 0) {
+            const bool sink = (b0 == b1);
+            if (LOGS) sB[s] = sink ? static_cast<ST>(0) : (sum > 0.0f ? m + static_cast<ST>(lg2_approx(sum) * kLn2) : neg_inf);
+            if (TROP) {
+              sD[s] = sink ? 0.0f : bt;
+              sBP[s] = sink ? -1 : a_lo + bi;
+            }
           }
         }
       }
-      __syncthreads();
+      level_barrier();
+      f0 = e0; e0 = e1; e1 = e2; e2 = e3; e3 = e4;
+      r0 = r1; r1 = r2; q0 = q1; am0 = am1;
     }
+    NFST_T(t_bwd1);
+    NFST_ACC(tid == 0, 18, t_bwd1 - t_bwd0);
     for (int i = tid; i < Sb; i += NT) {
       if (LOGS && beta_g) beta_g[s_lo + i] = sB[i];
       if (TROP) {
@@ -928,6 +1105,7 @@ __global__ void __launch_bounds__(256, 4)
       if (TROP && vit_score) vit_score[b] = sD[start];
     }
     if (want_hist && dtheta_smem) {
+      __syncthreads();
       for (int i = tid; i < L.vocab; i += NT) {
         const float v = hist[i];
         if (v != 0.0f) atomicAdd(&dtheta[i], v);
@@ -1339,12 +1517,15 @@ int check_launch(const nfst_packed_lattices_t* lat, const nfst_launch_t* launch)
   if (w < 32 || (w & (w - 1))) return fail(NFST_ERR_BAD_ARG, "window_states=%d must be a power of two >= 32", w);
   if (launch->chunk_cap < 32 || (launch->chunk_cap & 7))
     return fail(NFST_ERR_BAD_ARG, "chunk_cap=%d must be a multiple of 8, >= 32", launch->chunk_cap);
+  if (launch->small_max_arcs > 65535 || launch->small_max_states > 65535 || launch->small_max_levels >= (1 << 24))
+    return fail(NFST_ERR_TOO_LARGE, "small-lattice group: at most 65535 states and arcs per lattice (got %d, %d)",
+                launch->small_max_states, launch->small_max_arcs);
   return NFST_OK;
 }
 
 template <typename K>
 int prepare_smem(K kernel, size_t bytes) {
-  if (bytes > 48 * 1024) {
+  if (bytes > 40 * 1024) {  // static shared memory counts against the default 48 KB too
     int dev = 0;
     NFST_CUDA_OK(cudaGetDevice(&dev));
     int optin = 0;
@@ -1384,7 +1565,9 @@ int launch_small(const nfst_packed_lattices_t* lat, const nfst_launch_t* launch,
       *lat, launch->lattice_ids, launch->small_max_states, launch->small_max_arcs, launch->small_max_levels,
       scores->arc_scores, scores->theta, dtheta_smem, static_cast<ST*>(alpha), static_cast<ST*>(logz), grad_logz,
       static_cast<ST*>(beta), static_cast<ST*>(logz_bwd), post, dtheta, delta, backptr, vit_score);
-  NFST_CUDA_OK(cudaGetLastError());
+  if (cudaError_t e = cudaGetLastError())
+    return fail(NFST_ERR_CUDA, "small-lattice launch (grid %d, block %d, %zu B shared): %s", launch->n_ids,
+                launch->block_threads, bytes, cudaGetErrorString(e));
   return NFST_OK;
 }
 

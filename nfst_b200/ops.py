@@ -17,6 +17,7 @@ sm_100a kernels.  CPU tensors are rejected -- there is no fallback.
 """
 from __future__ import annotations
 
+import os
 from typing import Optional, Tuple
 
 import torch
@@ -109,6 +110,33 @@ def _stream(dev) -> int:
     return torch.cuda.current_stream(dev).cuda_stream
 
 
+# Launch groups of one call are independent (disjoint lattices), and the small / deep ones are
+# latency-bound: they run concurrently, group 0 on the caller's stream and the others on side
+# streams that fork from it and are joined before the call returns.
+PARALLEL_GROUPS = int(os.environ.get("NFST_PARALLEL_GROUPS", "1"))
+_side_streams = {}
+
+
+class _GroupStreams:
+    def __init__(self, dev, n: int):
+        self.main = torch.cuda.current_stream(dev)
+        self.streams = [self.main]
+        if n > 1 and PARALLEL_GROUPS:
+            pool = _side_streams.setdefault(dev.index, [])
+            while len(pool) < n - 1:
+                pool.append(torch.cuda.Stream(dev))
+            for s in pool[: n - 1]:
+                s.wait_stream(self.main)
+                self.streams.append(s)
+
+    def __getitem__(self, i: int) -> int:
+        return self.streams[i % len(self.streams)].cuda_stream
+
+    def join(self):
+        for s in self.streams[1:]:
+            self.main.wait_stream(s)
+
+
 def lattice_forward(packed: PackedLattices, arc_scores=None, theta=None, *, state_dtype="auto"
                     ) -> Tuple[torch.Tensor, torch.Tensor]:
     """alpha[S] (log space, packed state order) and logZ[B], in the state dtype."""
@@ -120,10 +148,11 @@ def lattice_forward(packed: PackedLattices, arc_scores=None, theta=None, *, stat
     alpha = torch.empty(packed.n_states, dtype=st, device=dev)
     logz = torch.empty(packed.n_lattices, dtype=st, device=dev)
     with torch.cuda.device(dev):
-        stream = _stream(dev)
-        for g in packed.groups:
-            _lib.check(lib.nfst_fwd_f32(packed.c_struct(), _launch(g, st), sc, alpha.data_ptr(), logz.data_ptr(), stream))
+        streams = _GroupStreams(dev, len(packed.groups))
+        for i, g in enumerate(packed.groups):
+            _lib.check(lib.nfst_fwd_f32(packed.c_struct(), _launch(g, st), sc, alpha.data_ptr(), logz.data_ptr(), streams[i]))
             launch_count += 1
+        streams.join()
     del keep
     return alpha, logz
 
@@ -167,15 +196,16 @@ def lattice_backward(
     vit = torch.empty(B, **f32) if want_viterbi else None
     g32 = _check_f32("grad_logz", grad_logz, B, dev)
     with torch.cuda.device(dev):
-        stream = _stream(dev)
-        for g in packed.groups:
+        streams = _GroupStreams(dev, len(packed.groups))
+        for i, g in enumerate(packed.groups):
             _lib.check(
                 lib.nfst_bwd_fused_f32(
                     packed.c_struct(), _launch(g, st), sc, _ptr(alpha), _ptr(logz), _ptr(g32), _ptr(beta),
-                    _ptr(logz_bwd), _ptr(post), _ptr(dtheta), _ptr(delta), _ptr(backptr), _ptr(vit), stream,
+                    _ptr(logz_bwd), _ptr(post), _ptr(dtheta), _ptr(delta), _ptr(backptr), _ptr(vit), streams[i],
                 )
             )
             launch_count += 1
+        streams.join()
     del keep
     for k, v in (("beta", beta), ("logz_bwd", logz_bwd), ("post", post), ("dtheta", dtheta), ("delta", delta),
                  ("backptr", backptr), ("vit_score", vit)):
@@ -206,9 +236,10 @@ def lattice_forward_backward(packed: PackedLattices, arc_scores=None, theta=None
     post = torch.empty(A, dtype=torch.float32, device=dev)
     dtheta = torch.zeros(V, dtype=torch.float32, device=dev) if want_dtheta else None
     with torch.cuda.device(dev):
-        stream = _stream(dev)
-        for g in packed.groups:
+        streams = _GroupStreams(dev, len(packed.groups))
+        for i, g in enumerate(packed.groups):
             lc = _launch(g, st)
+            stream = streams[i]
             if g.small_max_arcs > 0:
                 _lib.check(lib.nfst_fwd_bwd_small_f32(packed.c_struct(), lc, sc, None, alpha.data_ptr(), logz.data_ptr(),
                                                       beta.data_ptr(), logz_bwd.data_ptr(), post.data_ptr(),
@@ -220,6 +251,7 @@ def lattice_forward_backward(packed: PackedLattices, arc_scores=None, theta=None
                                                   beta.data_ptr(), logz_bwd.data_ptr(), post.data_ptr(), _ptr(dtheta),
                                                   None, None, None, stream))
                 launch_count += 2
+        streams.join()
     del keep
     if want_dtheta:
         return logz_bwd, alpha, beta, post, dtheta

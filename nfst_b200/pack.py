@@ -41,14 +41,14 @@ HEAVY_DIV = 4
 # topological level over all their chunks) instead of one block per lattice
 LEVEL_MODE_MIN_ARCS = int(os.environ.get("NFST_LEVEL_MODE_MIN", "4096"))
 # lattices whose whole working set fits this much shared memory run in one piece (nfst_small_kernel)
-SMALL_SMEM_BYTES = int(os.environ.get("NFST_SMALL_SMEM_BYTES", str(64 * 1024)))
-SMALL_BLOCK_MIN = int(os.environ.get("NFST_SMALL_BLOCK", "64"))
+SMALL_SMEM_BYTES = int(os.environ.get("NFST_SMALL_SMEM_BYTES", str(96 * 1024)))
+SMALL_BLOCK_MIN = int(os.environ.get("NFST_SMALL_BLOCK", "32"))
 
 
 def small_footprint_bytes(states, arcs, levels, vocab):
     """Upper bound of nfst_small_kernel's shared memory for one lattice (fp64 state, both
-    semirings, labels and a dtheta histogram)."""
-    return 4 * (6 * states + (levels + 1) + 2 * (states + 1) + 5 * arcs + min(vocab, 4096) + 64)
+    semirings, labels and a dtheta histogram; state / arc indices are 16-bit)."""
+    return 4 * (6 * states + 2 * (levels + 1) + (states + 2) + 4 * arcs + min(vocab, 4096) + 64)
 DEGREE_SORT = int(os.environ.get("NFST_DEGREE_SORT", "1"))
 
 
@@ -268,8 +268,8 @@ def build_groups(stats, dev, chunk_info=None) -> List[LaunchGroup]:
     launch; heaviest lattices first (longest-processing-time order).  Lattices with wide
     levels form level-major groups (see LaunchGroup / nfst_launch_t)."""
     wide = (stats["width_arcs"] >= LEVEL_MODE_MIN_ARCS).to(torch.int64)
-    small = (small_footprint_bytes(stats["states"], stats["arcs"], stats["levels"], int(stats["vocab"][0]))
-             <= SMALL_SMEM_BYTES).to(torch.int64) * (1 - wide)
+    foot = small_footprint_bytes(stats["states"], stats["arcs"], stats["levels"], int(stats["vocab"][0]))
+    small = ((foot <= SMALL_SMEM_BYTES) & (stats["states"] < 65536) & (stats["arcs"] < 65536)).to(torch.int64) * (1 - wide)
     gkey = (stats["block_class"] * 2 + wide) * 2 + small
     groups: List[LaunchGroup] = []
     B = int(gkey.numel())

@@ -25,6 +25,7 @@ DEV = torch.device("cuda", 0)
 ap = argparse.ArgumentParser()
 ap.add_argument("--quick", action="store_true")
 ap.add_argument("--steps", type=int, default=10)
+ap.add_argument("--no-dag", action="store_true", help="skip the config-4 sweep")
 args = ap.parse_args()
 
 flush_buf = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=DEV)  # > 126 MB L2
@@ -101,7 +102,7 @@ CONFIGS = [
     ("config5 Viterbi transliteration B=4096", lambda n, o: synth.transliteration_batch(n, seed=4 + o), 512 if q else 4096, 512),
     ("config5 Viterbi integer scores B=4096", lambda n, o: synth.transliteration_batch(n, seed=4 + o, integer_scores=True), 512 if q else 4096, 512),
 ]
-for arcs in (10_000, 30_000, 100_000, 300_000, 1_000_000):
+for arcs in (() if args.no_dag else (10_000, 30_000, 100_000, 300_000, 1_000_000)):
     B = 1024 if not q else 128
     CONFIGS.append((f"config4 random DAG A={arcs} B={B}", (lambda a: lambda n, o: synth.random_dag_batch(n, a, seed=3 + o, device=DEV))(arcs),
                     B, max(1, 60_000_000 // arcs)))
