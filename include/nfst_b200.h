@@ -21,6 +21,8 @@
  *   nfst_backtrace          best-path read-out; replaces best-of-k-samples selection
  *                           (src/modules/lightning.py:474-479) reached from
  *                           src/decode/decoder.py:77-79.
+ *   nfst_beta_hat_level_f32 the same recurrence with Wh != 0 (the beta-hat messages,
+ *                           scorers.py:732-747), one topological level per call.
  *   nfst_beta_to_dense      layout of compute_beta()'s return value, real-space
  *                           beta[B*k, S] (scorers.py:854, :858-875).
  *   nfst_dense_count_arcs / nfst_dense_extract_arcs
@@ -41,7 +43,7 @@
 extern "C" {
 #endif
 
-#define NFST_ABI_VERSION 7
+#define NFST_ABI_VERSION 8
 
 typedef enum nfst_status {
   NFST_OK = 0,
@@ -214,6 +216,17 @@ int nfst_dense_count_arcs(const int64_t* transition, int64_t n_rows, int32_t sta
 int nfst_dense_extract_arcs(const int64_t* transition, int64_t n_rows, int32_t states_per_lattice, int32_t vocab,
                             const int64_t* row_start, int32_t* arc_row, int32_t* arc_label, int32_t* arc_dst,
                             void* cuda_stream);
+
+/* One level of the beta-hat recurrence (FSAGRUScorer.compute_beta_per_sample with Wh != 0,
+ * scorers.py:732-747), for the `n_states` packed state ids in `states` (all of one topological
+ * level, any lattices; call for the deepest level first -- every arc's destination must be done):
+ *   m_hat = tanh(label_proj[label] + h_proj[dst]),  log m = w . m_hat + log_beta[dst],
+ *   log_beta[s] = logsumexp(log m),  beta_hat[s] = sum softmax(log m) m_hat,  h_proj[s] = Wh beta_hat[s].
+ * label_proj [V, hidden] = Wx e_l + b;  wh_t [hidden, hidden] = Wh transposed;  w [hidden];
+ * log_beta [S];  beta_hat, h_proj [S, hidden].  hidden <= 1024.  Sinks get beta = 1, beta_hat = 0. */
+int nfst_beta_hat_level_f32(const nfst_packed_lattices_t* lat, const int32_t* states, int32_t n_states, int32_t hidden,
+                            const float* label_proj, const float* wh_t, const float* w, float* log_beta,
+                            float* beta_hat, float* h_proj, void* cuda_stream);
 
 #ifdef __cplusplus
 }

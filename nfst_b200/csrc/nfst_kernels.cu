@@ -1445,6 +1445,72 @@ __global__ void nfst_backtrace_kernel(const nfst_packed_lattices_t L, const int3
   path_len[b] = k;
 }
 
+// =====================================================================================
+// beta-hat recurrence (the reference's full compute_beta, Wh != 0; scorers.py:692-751):
+//   message over arc c --j--> n :  m_hat = tanh(Wx e_j + Wh beta_hat[n] + b)     (:732-735)
+//                                  m     = exp(W . m_hat) * beta[n]              (:736-738)
+//   aggregation at c            :  beta[c] = sum m ;  beta_hat[c] = sum (m / beta[c]) m_hat   (:741-747)
+// The arc weight depends on the destination's beta_hat, so the pass is stepped level by level
+// (one launch per topological level, deepest first); within a launch one thread block per
+// state, one thread per hidden unit.  Wx e_j + b is a per-LABEL table and Wh beta_hat[n] a
+// per-STATE vector (computed once, when n is finished), so an arc costs H tanh + one dot
+// product.  beta is kept in log space (online logsumexp over the arcs).
+// =====================================================================================
+__global__ void nfst_beta_hat_level_kernel(const nfst_packed_lattices_t L, const int32_t* __restrict__ states, int H,
+                                           const float* __restrict__ label_proj,  // [V, H] = Wx e_l + b
+                                           const float* __restrict__ wh_t,        // [H, H], wh_t[k*H + i] = Wh[i][k]
+                                           const float* __restrict__ w,           // [H]
+                                           float* log_beta, float* beta_hat, float* h_proj) {
+  extern __shared__ float sh[];  // [blockDim.x] beta_hat of this state (for the projection)
+  __shared__ float red[32];
+  const int s = states[blockIdx.x];
+  const int i = threadIdx.x;
+  const bool act = i < H;
+  const int nw = (blockDim.x + 31) >> 5;
+  const int b0 = L.out_ptr[s], b1 = L.out_ptr[s + 1];
+  const size_t row = static_cast<size_t>(s) * H;
+  if (b0 == b1) {  // sink: beta = 1 (scorers.py:720), beta_hat = 0
+    if (i == 0) log_beta[s] = 0.0f;
+    if (act) { beta_hat[row + i] = 0.0f; h_proj[row + i] = 0.0f; }
+    return;
+  }
+  const float wi = act ? w[i] : 0.0f;
+  float mx = kNegInf, sum = 0.0f, acc = 0.0f;
+  for (int a = b0; a < b1; ++a) {
+    const int n = L.dst_out[a], lab = L.label_out[a];
+    const float mh = act ? tanhf(label_proj[static_cast<size_t>(lab) * H + i] + h_proj[static_cast<size_t>(n) * H + i]) : 0.0f;
+    float part = wi * mh;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+    __syncthreads();  // red[] free
+    if ((i & 31) == 0) red[i >> 5] = part;
+    __syncthreads();
+    float score = 0.0f;
+    for (int q = 0; q < nw; ++q) score += red[q];  // same order in every thread
+    const float lm = score + log_beta[n];
+    if (lm > mx) {
+      const float r = expf(mx - lm);  // mx = -inf: 0
+      sum = sum * r + 1.0f;
+      acc = acc * r + mh;
+      mx = lm;
+    } else if (lm > kNegInf) {
+      const float e = expf(lm - mx);
+      sum += e;
+      acc += e * mh;
+    }
+  }
+  const float bh = (sum > 0.0f) ? acc / sum : 0.0f;
+  if (i == 0) log_beta[s] = (sum > 0.0f) ? mx + logf(sum) : kNegInf;
+  if (act) beta_hat[row + i] = bh;
+  sh[i] = act ? bh : 0.0f;
+  __syncthreads();
+  if (act) {  // h = Wh beta_hat: column i of wh_t, coalesced across the block
+    float h = 0.0f;
+    for (int k = 0; k < H; ++k) h = fmaf(wh_t[static_cast<size_t>(k) * H + i], sh[k], h);
+    h_proj[row + i] = h;
+  }
+}
+
 template <typename ST>
 __global__ void nfst_beta_to_dense_kernel(const nfst_packed_lattices_t L, const ST* __restrict__ beta,
                                           const int32_t* __restrict__ orig_state, int k, int dense_states,
@@ -1868,6 +1934,21 @@ int nfst_dense_extract_arcs(const int64_t* transition, int64_t n_rows, int32_t s
   if (blocks > 0x7fffffffLL) return fail(NFST_ERR_TOO_LARGE, "too many table rows");
   nfst_dense_extract_kernel<<<static_cast<unsigned>(blocks), threads, 0, static_cast<cudaStream_t>(cuda_stream)>>>(
       transition, n_rows, states_per_lattice, vocab, row_start, arc_row, arc_label, arc_dst);
+  NFST_CUDA_OK(cudaGetLastError());
+  return NFST_OK;
+}
+
+int nfst_beta_hat_level_f32(const nfst_packed_lattices_t* lat, const int32_t* states, int32_t n_states, int32_t hidden,
+                            const float* label_proj, const float* wh_t, const float* w, float* log_beta,
+                            float* beta_hat, float* h_proj, void* cuda_stream) {
+  if (!lat || !states || !label_proj || !wh_t || !w || !log_beta || !beta_hat || !h_proj)
+    return fail(NFST_ERR_BAD_ARG, "nfst_beta_hat_level_f32: null argument");
+  if (hidden < 1 || hidden > 1024) return fail(NFST_ERR_BAD_ARG, "hidden=%d must be in 1..1024", hidden);
+  if (n_states < 0) return fail(NFST_ERR_BAD_ARG, "n_states=%d", n_states);
+  if (n_states == 0) return NFST_OK;
+  const int threads = (hidden + 31) & ~31;
+  nfst_beta_hat_level_kernel<<<n_states, threads, threads * sizeof(float), static_cast<cudaStream_t>(cuda_stream)>>>(
+      *lat, states, hidden, label_proj, wh_t, w, log_beta, beta_hat, h_proj);
   NFST_CUDA_OK(cudaGetLastError());
   return NFST_OK;
 }

@@ -328,6 +328,66 @@ def lattice_viterbi(packed: PackedLattices, arc_scores=None, theta=None):
     return r["vit_score"], offsets, path_arcs, path_labels
 
 
+def _level_state_lists(packed: PackedLattices):
+    """(states[S] int32 sorted by topological level, host offsets[L+1]) -- cached on `packed`."""
+    cached = getattr(packed, "_level_lists", None)
+    if cached is not None:
+        return cached
+    dev = packed.device
+    lp = packed.level_ptr.to(torch.int64)  # per lattice: first state of each level, then the end
+    lo = packed.level_off.to(torch.int64)
+    n_lev = packed.n_levels.to(torch.int64)
+    B = packed.n_lattices
+    # global slot index of every (lattice, level); its size = next pointer - this pointer
+    slot_lat = torch.repeat_interleave(torch.arange(B, device=dev), n_lev)
+    slot_first = lo[:-1][slot_lat]
+    slot_level = torch.arange(int(n_lev.sum()), device=dev) - torch.repeat_interleave(
+        torch.cumsum(n_lev, 0) - n_lev, n_lev)
+    begin = lp[slot_first + slot_level]
+    size = lp[slot_first + slot_level + 1] - begin
+    level_of_state = torch.repeat_interleave(slot_level, size)  # states are numbered level by level
+    order = torch.argsort(level_of_state, stable=True).to(torch.int32)
+    counts = torch.bincount(level_of_state, minlength=max(packed.max_levels, 1))
+    off = [0] + torch.cumsum(counts, 0).cpu().tolist()
+    packed._level_lists = (order, off)
+    return packed._level_lists
+
+
+def lattice_beta_hat(packed: PackedLattices, label_proj: torch.Tensor, Wh: torch.Tensor, W: torch.Tensor
+                     ) -> Tuple[torch.Tensor, torch.Tensor]:
+    """The reference's full beta recurrence (``scorers.py:692-751``, Wh != 0):
+    ``m_hat = tanh(label_proj[label] + Wh beta_hat[dst])``, ``m = exp(W.m_hat) beta[dst]``,
+    ``beta[c] = sum m``, ``beta_hat[c] = sum (m/beta[c]) m_hat``.  ``label_proj[V, H]`` is
+    ``Wx e_l + b`` for every label.  Returns (log beta[S] float32 in packed state order,
+    beta_hat[S, H]).  One launch per topological level, deepest level first."""
+    global launch_count
+    lib = _lib.load()
+    dev = packed.device
+    if dev.type != "cuda":
+        raise RuntimeError("nfst_b200 kernels need the packed lattices on a CUDA device (no CPU fallback)")
+    V, H = label_proj.shape
+    if V != packed.vocab or tuple(Wh.shape) != (H, H) or W.numel() != H:
+        raise ValueError("label_proj must be [vocab, H], Wh [H, H], W [H]")
+    f32 = lambda t: t.detach().to(device=dev, dtype=torch.float32).contiguous()  # noqa: E731
+    proj, wh_t, w = f32(label_proj), f32(Wh.t()), f32(W.reshape(-1))
+    S = packed.n_states
+    log_beta = torch.empty(S, dtype=torch.float32, device=dev)
+    beta_hat = torch.empty(S, H, dtype=torch.float32, device=dev)
+    h_proj = torch.empty(S, H, dtype=torch.float32, device=dev)
+    order, off = _level_state_lists(packed)
+    with torch.cuda.device(dev):
+        stream = _stream(dev)
+        for lvl in range(len(off) - 2, -1, -1):
+            n = off[lvl + 1] - off[lvl]
+            if n == 0:
+                continue
+            _lib.check(lib.nfst_beta_hat_level_f32(packed.c_struct(), order.data_ptr() + 4 * off[lvl], n, H,
+                                                   proj.data_ptr(), wh_t.data_ptr(), w.data_ptr(), log_beta.data_ptr(),
+                                                   beta_hat.data_ptr(), h_proj.data_ptr(), stream))
+            launch_count += 1
+    return log_beta, beta_hat
+
+
 def beta_dense(packed: PackedLattices, beta: torch.Tensor, k: int = 1, dense_states: Optional[int] = None) -> torch.Tensor:
     """Real-space beta in the reference's layout ``[B*k, S]`` (``scorers.py:854``): row
     b*k+j is lattice b, column = original state id; trimmed states hold 0."""

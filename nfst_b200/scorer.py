@@ -4,11 +4,13 @@ The reference module is driven as ``set_masks(emission, transition)`` -> ``set_k
 ``compute_beta()`` (called from ``Sampler.stateful_sample``, samplers.py:196-198) and
 returns real-space ``beta[B*k, S]``.  ``LatticeBetaScorer`` offers the same three calls on
 top of the CUDA path; ``patch_compute_beta`` swaps ``compute_beta`` on an existing reference
-module for the Wh = 0 regime, where the arc weight is a function of the arc label alone:
+module.  With Wh = 0 the arc weight is a function of the arc label alone,
 
     theta[l] = W . tanh(Wx e_l + b)          (scorers.py:732-738 with Wh = 0)
 
-so that beta is the log-semiring backward pass with arc score theta[label].
+and beta is the log-semiring backward pass with arc score theta[label] (the fused backward
+kernel).  With Wh != 0 the weight also depends on the destination's beta-hat and the pass is
+stepped level by level (``ops.lattice_beta_hat`` / ``nfst_beta_hat_level_f32``).
 """
 from __future__ import annotations
 
@@ -17,7 +19,7 @@ from typing import Optional
 
 import torch
 
-from .ops import beta_dense, lattice_backward
+from .ops import beta_dense, lattice_backward, lattice_beta_hat
 from .pack import PackedLattices, pack_dense
 
 
@@ -61,21 +63,29 @@ class LatticeBetaScorer:
         r = lattice_backward(self.packed, None, theta, want_beta=True)
         return beta_dense(self.packed, r["beta"], self.k)
 
+    def compute_beta_recurrent(self, embeddings: torch.Tensor, Wx: torch.Tensor, Wh: torch.Tensor, W: torch.Tensor,
+                               bias: torch.Tensor, return_beta_hat: bool = False):
+        """The full recurrence of ``compute_beta_per_sample`` (scorers.py:692-751), Wh != 0."""
+        proj = embeddings @ Wx.T + bias  # [V, H]: the label part of every message
+        log_beta, beta_hat = lattice_beta_hat(self.packed, proj, Wh, W)
+        beta = beta_dense(self.packed, log_beta, self.k)
+        return (beta, beta_hat) if return_beta_hat else beta
+
 
 def patch_compute_beta(module) -> None:
     """Replace ``module.compute_beta`` (a reference ``FSAGRUScorer`` built with
-    ``use_beta=True``) by the CUDA path.  Raises if the module's Wh is not zero: the
-    beta-hat recurrence (Wh != 0) is a level-stepped computation that this path does not
-    cover."""
-    if float(module.Wh.detach().abs().max()) != 0.0:
-        raise NotImplementedError("compute_beta drop-in covers the Wh = 0 regime only")
+    ``use_beta=True``) by the CUDA path: the fused log-semiring backward kernel while the
+    module's Wh is zero, the level-stepped beta-hat recurrence otherwise."""
     impl = LatticeBetaScorer()
 
     def compute_beta(self):
         if impl.transition is not self.transition:
             impl.set_masks(self.emission, self.transition)
         impl.set_k(self.k)
-        theta = label_scores(self.embeddings.weight.detach(), self.Wx.detach(), self.W.detach(), self.beta_bias.detach())
-        return impl.compute_beta(theta)
+        emb, Wx, Wh = self.embeddings.weight.detach(), self.Wx.detach(), self.Wh.detach()
+        W, bias = self.W.detach(), self.beta_bias.detach()
+        if float(Wh.abs().max()) != 0.0:
+            return impl.compute_beta_recurrent(emb, Wx, Wh, W, bias)
+        return impl.compute_beta(label_scores(emb, Wx, W, bias))
 
     module.compute_beta = types.MethodType(compute_beta, module)

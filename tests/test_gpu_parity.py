@@ -455,9 +455,68 @@ def test_scorer_mirror_and_monkeypatch_against_reference_golden():
     src, lab, dst, _ = lo.arcs_from_dense(g["tr_0"][0][: int(n_states[0])])
     be = lo.beta_log(int(n_states[0]), src, dst, th.cpu().double().numpy()[lab])
     np.testing.assert_allclose(out[0, : int(n_states[0])].cpu().numpy(), np.exp(be), rtol=2e-5)
-    mod.Wh = torch.ones(H, H, device=DEV)
-    with pytest.raises(NotImplementedError):
-        patch_compute_beta(mod)
+    # Wh != 0: the patched method switches to the level-stepped beta-hat recurrence
+    mod.Wh = 0.3 * torch.randn(H, H, generator=gen).to(DEV)
+    out = mod.compute_beta()
+    P = [t.cpu().double().numpy() for t in (mod.embeddings.weight, mod.Wx, mod.Wh, mod.W, mod.beta_bias)]
+    be, _ = lo.beta_recurrent(int(n_states[0]), src, lab, dst, *P)
+    np.testing.assert_allclose(out[0, : int(n_states[0])].cpu().numpy(), be, rtol=2e-5)
+
+
+# --------------------------------------------------------------------------------------
+# beta-hat recurrence (Wh != 0): reference golden + float64 oracle
+# --------------------------------------------------------------------------------------
+def test_beta_recurrent_matches_reference_golden():
+    # fixtures from the UNMODIFIED reference compute_beta_per_sample with its default (non-zero) Wh
+    from nfst_b200.scorer import LatticeBetaScorer
+
+    g = np.load(os.path.join(G, "beta_per_sample.npz"))
+    P = {k: torch.from_numpy(g["p1_" + k]).to(DEV) for k in ("emb", "Wx", "Wh", "W", "bias")}
+    for i in range(int(g["n_cases"])):
+        tr = torch.from_numpy(g[f"tr_{i}"]).to(DEV)[None]
+        sc = LatticeBetaScorer()
+        sc.set_masks(tr != 0, tr)
+        beta = sc.compute_beta_recurrent(P["emb"], P["Wx"], P["Wh"], P["W"], P["bias"])
+        ref = g[f"beta1_{i}"]  # real space, float64
+        np.testing.assert_allclose(beta[0].cpu().numpy(), ref, rtol=1e-5)  # tolerance: fp32 path vs float64 reference
+
+
+@pytest.mark.parametrize("H", [8, 64, 256])
+def test_beta_recurrent_matches_oracle_on_transliteration_lattices(H):
+    ab = synth.transliteration_batch(6, seed=11)
+    p, _ = ab.to(DEV).pack()
+    gen = torch.Generator().manual_seed(H)
+    V = ab.vocab
+    emb = torch.randn(V, H, generator=gen, dtype=torch.float64)
+    Wx = torch.randn(H, H, generator=gen, dtype=torch.float64) / H ** 0.5
+    Wh = torch.randn(H, H, generator=gen, dtype=torch.float64) / H ** 0.5
+    W = torch.randn(1, H, generator=gen, dtype=torch.float64) / H ** 0.5
+    bias = 0.1 * torch.randn(H, generator=gen, dtype=torch.float64)
+    log_beta, beta_hat = nb.ops.lattice_beta_hat(p, (emb @ Wx.T + bias).to(DEV), Wh.to(DEV), W.to(DEV))
+    log_beta, beta_hat = log_beta.cpu().numpy().astype(np.float64), beta_hat.cpu().numpy().astype(np.float64)
+    g2o = gpu_state_to_orig(p, ab.n_states.numpy())
+    off = np.concatenate([[0], np.cumsum(ab.n_states.numpy())])
+    lat, src, dst, lab = (t.numpy() for t in (ab.arc_lattice, ab.src, ab.dst, ab.label))
+    ref_lb = np.full(int(off[-1]), -np.inf)
+    ref_bh = np.zeros((int(off[-1]), H))
+    for b in range(len(off) - 1):
+        m = lat == b
+        be, bh = lo.beta_recurrent(int(ab.n_states[b]), src[m], lab[m], dst[m], emb.numpy(), Wx.numpy(), Wh.numpy(),
+                                   W.numpy(), bias.numpy())
+        ref_lb[off[b]:off[b + 1]] = np.log(be)
+        ref_bh[off[b]:off[b + 1]] = bh
+    # tolerance 1e-5 relative on log beta (fp32 messages, ~50 levels), 1e-4 absolute on beta_hat in [-1, 1]
+    np.testing.assert_allclose(log_beta, ref_lb[g2o], rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(beta_hat, ref_bh[g2o], rtol=0, atol=1e-4)
+
+
+def test_beta_recurrent_rejects_bad_shapes():
+    p, _ = synth.transliteration_batch(2, seed=1).to(DEV).pack()
+    with pytest.raises(ValueError):
+        nb.ops.lattice_beta_hat(p, torch.zeros(p.vocab + 1, 8, device=DEV), torch.zeros(8, 8, device=DEV), torch.zeros(8, device=DEV))
+    lib = nb._lib.load()
+    rc = lib.nfst_beta_hat_level_f32(p.c_struct(), p.state_off.data_ptr(), 1, 2048, 1, 1, 1, 1, 1, 1, None)
+    assert rc < 0 and b"hidden" in lib.nfst_last_error_string()
 
 
 # --------------------------------------------------------------------------------------
