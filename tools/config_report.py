@@ -93,6 +93,41 @@ def parity(sample: synth.ArcBatch, n_max=16):
                 vit_paths_exact=f"{pexact}/{B}", cpu_arcs_per_s=ob.n_arcs / t_cpu, cpu_threads=c_oracle.max_threads())
 
 
+def recurrent_beta_report(B=32, H=256):
+    """compute_beta with Wh != 0 (the beta-hat recurrence) on config-1 lattices,
+    GPU (level-stepped kernel) next to the float64 numpy port of the reference recurrence."""
+    from oracle import lattice_oracle as lo
+
+    ab = synth.transliteration_batch(B, seed=0)
+    p, _ = ab.to(DEV).pack()
+    gen = torch.Generator().manual_seed(0)
+    V = ab.vocab
+    emb = torch.randn(V, H, generator=gen, dtype=torch.float64)
+    Wx, Wh = (torch.randn(H, H, generator=gen, dtype=torch.float64) / H ** 0.5 for _ in range(2))
+    W = torch.randn(1, H, generator=gen, dtype=torch.float64) / H ** 0.5
+    bias = 0.1 * torch.randn(H, generator=gen, dtype=torch.float64)
+    proj, Whd, Wd = (emb @ Wx.T + bias).to(DEV), Wh.to(DEV), W.to(DEV)
+    ms = timed(lambda: nb.ops.lattice_beta_hat(p, proj, Whd, Wd), args.steps, True)
+    log_beta, _ = nb.ops.lattice_beta_hat(p, proj, Whd, Wd)
+    lat, src, dst, lab = (t.numpy() for t in (ab.arc_lattice, ab.src, ab.dst, ab.label))
+    n_cpu = 2
+    t0 = time.perf_counter()
+    refs = [lo.beta_recurrent(int(ab.n_states[b]), src[lat == b], lab[lat == b], dst[lat == b], emb.numpy(), Wx.numpy(),
+                              Wh.numpy(), W.numpy(), bias.numpy())[0] for b in range(n_cpu)]
+    t_cpu = time.perf_counter() - t0
+    arcs_cpu = int(sum((lat == b).sum() for b in range(n_cpu)))
+    so = p.state_off.cpu().numpy()
+    orig = p.orig_state.cpu().numpy()
+    err = 0.0
+    for b in range(n_cpu):
+        got = log_beta[so[b]:so[b + 1]].cpu().numpy().astype(np.float64)
+        err = max(err, float(np.max(np.abs(got - np.log(refs[b][orig[so[b]:so[b + 1]]])))))
+    print(f"{'config1 beta-hat recurrence H=' + str(H) + ' B=' + str(B):44s} {p.n_arcs:11d} {p.n_states:10d} {p.max_levels:5d} "
+          f"{'':7s} {ms:8.3f} {p.n_arcs / ms / 1e6:10.3f}  (compute_beta, Wh != 0; one launch per level) | "
+          f"numpy float64 port {arcs_cpu / t_cpu / 1e6:.4f} Marc/s 1 thr | max |log beta - oracle| {err:.1e} (first {n_cpu} lattices)",
+          flush=True)
+
+
 q = args.quick
 CONFIGS = [
     ("config1 transliteration B=32", lambda n, o: synth.transliteration_batch(n, seed=o), 32, 32),
@@ -130,3 +165,4 @@ for name, gen, B, per_chunk in CONFIGS:
           f"Viterbi scores {par['vit_scores_exact']} paths {par['vit_paths_exact']} (first {par['B']} lattices)", flush=True)
     del packed, sc, sample
     torch.cuda.empty_cache()
+recurrent_beta_report()
