@@ -311,64 +311,92 @@ def build_groups(stats, dev, chunk_info=None) -> List[LaunchGroup]:
 
 
 def concat_packed(parts: List["PackedLattices"]) -> "PackedLattices":
-    """Collate independently packed lattices (e.g. cached per example) into one batch."""
+    """Collate independently packed lattices (e.g. cached per example) into one batch.
+
+    This is the per-step collate when packs are cached per example, so it is written as a fixed
+    number of tensor ops (one concatenation per array plus one gathered offset add), independent
+    of the number of parts."""
     if not parts:
         raise ValueError("empty batch")
     dev = parts[0].device
     vocab = parts[0].vocab
     if any(p.vocab != vocab for p in parts):
         raise ValueError("all parts must share one vocabulary")
-    S = A = B = Lv = nfc = nbc = 0
-    acc = {f: [] for f in PackedLattices._INT_FIELDS}
-    extra = {k: [] for k in ("lanes_in_log2", "lanes_out_log2", "orig_state", "arc_origin", "arc_off", "n_levels")}
-    static = []
-    for i, p in enumerate(parts):
-        last = i == len(parts) - 1
-        cut = (lambda t: t) if last else (lambda t: t[:-1])  # offset arrays: drop the closing entry except at the end
-        acc["state_off"].append(cut(p.state_off + S))
-        acc["level_off"].append(cut(p.level_off + Lv))
-        acc["level_ptr"].append(p.level_ptr + S)
-        acc["start_state"].append(p.start_state + S)
-        acc["sink_off"].append(cut(p.sink_off + (sum(x.numel() for x in acc["sinks"]))))
-        acc["sinks"].append(p.sinks + S)
-        acc["in_ptr"].append(cut(p.in_ptr + A))
-        acc["src_in"].append(p.src_in + S)
-        acc["label_in"].append(p.label_in)
-        acc["in2out"].append(p.in2out + A)
-        acc["out_ptr"].append(cut(p.out_ptr + A))
-        acc["dst_out"].append(p.dst_out + S)
-        acc["label_out"].append(p.label_out)
-        shift = torch.tensor([A, A, S, S], dtype=torch.int32, device=dev)
-        acc["fwd_chunk_off"].append(cut(p.fwd_chunk_off + nfc))
-        acc["fwd_chunks"].append(p.fwd_chunks + shift)
-        acc["bwd_chunk_off"].append(cut(p.bwd_chunk_off + nbc))
-        acc["bwd_chunks"].append(p.bwd_chunks + shift)
-        acc["bwd_order"].append(p.bwd_order + S)
-        acc["fwd_chunk_level"].append(p.fwd_chunk_level)
-        acc["bwd_chunk_level"].append(p.bwd_chunk_level)
-        nonempty = (p.fwd_gather[:, 1] > p.fwd_gather[:, 0]).to(torch.int32).unsqueeze(1)
-        acc["fwd_gather"].append(p.fwd_gather + A * nonempty)
-        nfc += int(p.fwd_chunks.shape[0])
-        nbc += int(p.bwd_chunks.shape[0])
-        extra["lanes_in_log2"].append(p.lanes_in_log2)
-        extra["lanes_out_log2"].append(p.lanes_out_log2)
-        extra["orig_state"].append(p.orig_state)
-        extra["arc_origin"].append(p.arc_origin)
-        extra["arc_off"].append(cut(p.arc_off + A))
-        extra["n_levels"].append(p.n_levels)
-        if p.static_scores is not None:
-            static.append(p.static_scores)
-        S += p.n_states
-        A += p.n_arcs
-        B += p.n_lattices
-        Lv += int(p.level_ptr.numel())
+    P = len(parts)
+    # element counts of every index space, per part (host integers: no device sync)
+    n_state = [p.n_states for p in parts]
+    n_arc = [p.n_arcs for p in parts]
+    n_lat = [p.n_lattices for p in parts]
+    n_lvl = [int(p.level_ptr.numel()) for p in parts]
+    n_sink = [int(p.sinks.numel()) for p in parts]
+    n_fc = [int(p.fwd_chunks.shape[0]) for p in parts]
+    n_bc = [int(p.bwd_chunks.shape[0]) for p in parts]
+
+    def starts(counts):
+        out, t = [], 0
+        for c in counts:
+            out.append(t)
+            t += c
+        return out, t
+
+    (oS, S), (oA, A), (oB, B), (oL, Lv), (oK, n_sinks), (oF, nfc), (oC, nbc) = (
+        starts(c) for c in (n_state, n_arc, n_lat, n_lvl, n_sink, n_fc, n_bc))
     if S >= 2**31 or A >= 2**31:
         raise ValueError("batch too large for int32 indices; shard it")
-    if static and len(static) != len(parts):
+    table = torch.tensor([oS, oA, oL, oK, oF, oC, n_state, n_arc, n_lat, n_lvl, n_sink, n_fc, n_bc],
+                         dtype=torch.int64).to(dev, non_blocking=True)
+    offS, offA, offL, offK, offF, offC = (table[i].to(torch.int32) for i in range(6))
+    pid = torch.arange(P, device=dev)
+    rep = lambda row, total: torch.repeat_interleave(pid, table[row], output_size=total)  # noqa: E731
+    by_state, by_arc, by_lat, by_lvl, by_sink, by_fc, by_bc = (
+        rep(6, S), rep(7, A), rep(8, B), rep(9, Lv), rep(10, n_sinks), rep(11, nfc), rep(12, nbc))
+
+    def cat(name, cut=False):
+        ts = [getattr(p, name) for p in parts]
+        return torch.cat([t[:-1] for t in ts] if cut else ts)
+
+    def closed(name, space, off, total):
+        """an offset array [n+1] per part -> [N+1] for the batch"""
+        body = cat(name, cut=True) + off[space]
+        return torch.cat([body, torch.tensor([total], dtype=body.dtype, device=dev)])
+
+    kw = {
+        "state_off": closed("state_off", by_lat, offS, S),
+        "level_off": closed("level_off", by_lat, offL, Lv),
+        "level_ptr": cat("level_ptr") + offS[by_lvl],
+        "start_state": cat("start_state") + offS[by_lat],
+        "sink_off": closed("sink_off", by_lat, offK, n_sinks),
+        "sinks": cat("sinks") + offS[by_sink],
+        "in_ptr": closed("in_ptr", by_state, offA, A),
+        "src_in": cat("src_in") + offS[by_arc],
+        "label_in": cat("label_in"),
+        "in2out": cat("in2out") + offA[by_arc],
+        "out_ptr": closed("out_ptr", by_state, offA, A),
+        "dst_out": cat("dst_out") + offS[by_arc],
+        "label_out": cat("label_out"),
+        "fwd_chunk_off": closed("fwd_chunk_off", by_lat, offF, nfc),
+        "bwd_chunk_off": closed("bwd_chunk_off", by_lat, offC, nbc),
+        "bwd_order": cat("bwd_order") + offS[by_state],
+        "fwd_chunk_level": cat("fwd_chunk_level"),
+        "bwd_chunk_level": cat("bwd_chunk_level"),
+        "lanes_in_log2": cat("lanes_in_log2"),
+        "lanes_out_log2": cat("lanes_out_log2"),
+        "orig_state": cat("orig_state"),
+        "arc_origin": cat("arc_origin"),
+        "arc_off": closed("arc_off", by_lat, offA, A),
+        "n_levels": cat("n_levels"),
+    }
+    for name, space, off_c in (("fwd_chunks", by_fc, offF), ("bwd_chunks", by_bc, offC)):
+        shift = torch.stack([offA[space], offA[space], offS[space], offS[space]], dim=1)
+        kw[name] = cat(name) + shift
+    fg = cat("fwd_gather")
+    nonempty = (fg[:, 1] > fg[:, 0]).to(torch.int32).unsqueeze(1)  # empty chunks keep [0, 0)
+    kw["fwd_gather"] = fg + offA[by_fc].unsqueeze(1) * nonempty
+    kw = {k: v.contiguous() for k, v in kw.items()}
+    static = [p.static_scores for p in parts if p.static_scores is not None]
+    if static and len(static) != P:
         raise ValueError("either all or none of the parts may carry static scores")
     stats = {k: torch.cat([p.stats[k] for p in parts]) for k in parts[0].stats}
-    kw = {f: torch.cat(v).contiguous() for f, v in acc.items()}
-    kw.update({f: torch.cat(v).contiguous() for f, v in extra.items()})
     ci = {d: (kw[f"{d}_chunk_off"].to(torch.int64), kw[f"{d}_chunks"], kw[f"{d}_chunk_level"]) for d in ("fwd", "bwd")}
     return PackedLattices(
         n_lattices=B, n_states=S, n_arcs=A, vocab=vocab, static_scores=torch.cat(static) if static else None,
@@ -417,14 +445,14 @@ def pack_arcs(
     max_iter = int(n_states.max()) if B else 0
     it = 0
     while gsrc.numel():
-        ls = level[gsrc]
-        cand = torch.where(ls >= 0, ls + 1, ls)
-        new = level.scatter_reduce(0, gdst, cand, reduce="amax", include_self=True)
-        if torch.equal(new, level):
+        before = level
+        for _ in range(8):  # relaxation sweeps between convergence checks (each check is a host sync)
+            ls = level[gsrc]
+            level = level.scatter_reduce(0, gdst, torch.where(ls >= 0, ls + 1, ls), reduce="amax", include_self=True)
+        if torch.equal(before, level):
             break
-        level = new
-        it += 1
-        if it > max_iter:
+        it += 8
+        if it > max_iter + 8:
             raise ValueError("lattice is cyclic: the DP is defined for acyclic lattices only")
 
     # ---- state renumbering: (lattice, level, original id) ----

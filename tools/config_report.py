@@ -128,6 +128,39 @@ def recurrent_beta_report(B=32, H=256):
           flush=True)
 
 
+def training_step_report():
+    """Config 2 as the reference trains it: arc score = theta[label] (WFSTScorer, scorers.py:1663-1687),
+    loss = -mean logZ, gradient d loss / d theta through the autograd Function (posterior label counts)."""
+    ab = synth.snips_batch(256, seed=1).to(DEV)
+    p, _ = ab.pack()
+    theta = (-torch.rand(p.vocab, device=DEV)).requires_grad_(True)
+
+    def step():
+        theta.grad = None
+        logz = nb.lattice_log_partition(p, theta=theta)
+        (-logz.mean()).backward()
+
+    ms = timed(step, args.steps, True)
+    step()
+    g = theta.grad.detach().cpu().numpy().astype(np.float64)
+    # oracle: posteriors summed per label, on the first 16 lattices
+    B = 16
+    sel = (ab.arc_lattice < B).cpu()
+    sub = synth.ArcBatch(ab.arc_lattice.cpu()[sel], ab.src.cpu()[sel], ab.dst.cpu()[sel], ab.label.cpu()[sel],
+                         theta.detach().cpu()[ab.label.cpu()[sel]], ab.n_states.cpu()[:B], ab.vocab)
+    ob = c_oracle.Batch(sub.arc_lattice.numpy(), sub.src.numpy(), sub.dst.numpy(), sub.label.numpy(), sub.scores.numpy(),
+                        sub.n_states.numpy())
+    _, _, _, o_post = c_oracle.forward_backward(ob)
+    ref = np.bincount(sub.label.numpy(), weights=o_post, minlength=ab.vocab)
+    p16, _ = sub.to(DEV).pack()
+    th2 = theta.detach().clone().requires_grad_(True)
+    nb.lattice_log_partition(p16, theta=th2).sum().backward()
+    err = float(np.max(np.abs(th2.grad.cpu().numpy() - ref) / np.maximum(ref, 1e-3)))
+    print(f"{'config2 SNIPS training step (theta mode) B=256':44s} {p.n_arcs:11d} {p.n_states:10d} {p.max_levels:5d} {'':7s} {ms:8.3f} "
+          f"{p.n_arcs / ms / 1e6:10.2f}  (logZ forward + autograd backward -> d theta[V]; grad sum {g.sum():.3f}) | "
+          f"d theta vs C oracle rel {err:.1e} (first {B} lattices)", flush=True)
+
+
 q = args.quick
 CONFIGS = [
     ("config1 transliteration B=32", lambda n, o: synth.transliteration_batch(n, seed=o), 32, 32),
@@ -166,3 +199,4 @@ for name, gen, B, per_chunk in CONFIGS:
     del packed, sc, sample
     torch.cuda.empty_cache()
 recurrent_beta_report()
+training_step_report()
