@@ -7,10 +7,12 @@ behind a C ABI (``include/nfst_b200.h``); no Triton, no CPU fallback.
 """
 from .pack import PackedLattices, pack_arcs, pack_dense, dense_arcs  # noqa: F401
 from .ops import (  # noqa: F401
+    CapturedForwardBackward,
     LatticeLogPartition,
     beta_dense,
     compute_beta,
     lattice_backward,
+    lattice_beta_hat,
     lattice_forward,
     lattice_forward_backward,
     lattice_log_partition,

@@ -258,6 +258,35 @@ def lattice_forward_backward(packed: PackedLattices, arc_scores=None, theta=None
     return logz_bwd, alpha, beta, post
 
 
+class CapturedForwardBackward:
+    """``lattice_forward_backward`` of one packed batch captured in a CUDA graph.
+
+    The operators only enqueue kernels (no host synchronisation; buffers come from torch's
+    capture pool), so a step over a FIXED lattice structure can be replayed with new scores:
+    ``run(scores)`` copies them into the captured input and replays.  Worth it where a step is
+    many launches -- the level-major groups issue one kernel per topological level: -22 % at
+    64 x 300k-arc lattices, -15 % at 32 x 1M (tools/graph_timing.py); nothing for the two-launch
+    groups.  Outputs are the graph's static tensors (overwritten by the next ``run``)."""
+
+    def __init__(self, packed: PackedLattices, *, theta_mode: bool = False, want_dtheta: bool = False,
+                 state_dtype="auto"):
+        dev = packed.device
+        n = packed.vocab if theta_mode else packed.n_arcs
+        self._in = torch.zeros(n, dtype=torch.float32, device=dev)
+        kw = dict(theta=self._in) if theta_mode else dict(arc_scores=self._in)
+        run = lambda: lattice_forward_backward(packed, want_dtheta=want_dtheta, state_dtype=state_dtype, **kw)  # noqa: E731
+        run()  # warm-up outside the capture: library load, shared-memory opt-in, side streams
+        torch.cuda.synchronize(dev)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.outputs = run()
+
+    def run(self, scores: torch.Tensor):
+        self._in.copy_(scores, non_blocking=True)
+        self.graph.replay()
+        return self.outputs
+
+
 class LatticeLogPartition(torch.autograd.Function):
     """logZ[B] = log sum over start->sink paths of exp(sum of arc scores).
 

@@ -546,3 +546,39 @@ def test_level_major_theta_gradient(level_major):
     dth = np.zeros(p.vocab)
     np.add.at(dth, ab.label.numpy(), po)
     np.testing.assert_allclose(theta.grad.cpu().numpy(), dth, rtol=1e-4, atol=1e-5)
+
+
+# --------------------------------------------------------------------------------------
+# CUDA graphs: the operators enqueue kernels only (no host sync, no hidden allocation outside
+# torch's capture pool); a captured step replays on new scores -- including the forked side
+# streams of a multi-group batch
+# --------------------------------------------------------------------------------------
+def test_forward_backward_is_cuda_graph_capturable():
+    # small-lattice group + block-per-lattice group + level-major group in one batch
+    parts = [synth.transliteration_batch(6, seed=1), synth.random_dag_batch(3, 30_000, levels=32, seed=2),
+             synth.random_dag_batch(2, 300_000, levels=16, seed=3)]
+    packed_parts, scores = zip(*[ab.to(DEV).pack() for ab in parts])
+    from nfst_b200.pack import concat_packed
+
+    p = concat_packed(list(packed_parts))
+    assert len(p.groups) >= 3
+    sc = torch.cat(scores).clone()
+    static_in = sc.clone()
+    nb.lattice_forward_backward(p, arc_scores=static_in)  # warm-up: loads the library, sizes shared memory
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        out = nb.lattice_forward_backward(p, arc_scores=static_in)
+    for trial in range(2):
+        new_sc = sc - 0.25 * trial * torch.rand_like(sc)
+        static_in.copy_(new_sc)
+        g.replay()
+        torch.cuda.synchronize()
+        ref = nb.lattice_forward_backward(p, arc_scores=new_sc)
+        for a, b in zip(out, ref):
+            assert torch.equal(a, b)  # same kernels on the same inputs: bit-identical
+    cap = nb.CapturedForwardBackward(p)
+    got = cap.run(sc)
+    torch.cuda.synchronize()
+    for a, b in zip(got, nb.lattice_forward_backward(p, arc_scores=sc)):
+        assert torch.equal(a, b)
