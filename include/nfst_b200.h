@@ -43,7 +43,7 @@
 extern "C" {
 #endif
 
-#define NFST_ABI_VERSION 8
+#define NFST_ABI_VERSION 9
 
 typedef enum nfst_status {
   NFST_OK = 0,
@@ -201,6 +201,20 @@ int nfst_viterbi_f32(const nfst_packed_lattices_t* lat, const nfst_launch_t* lau
  * always suffices). */
 int nfst_backtrace(const nfst_packed_lattices_t* lat, const int32_t* backptr, const int32_t* path_off,
                    int32_t* path_arcs, int32_t* path_len, void* cuda_stream);
+
+/* Viterbi recursion + best-path read-out for one launch group: as nfst_viterbi_f32 followed by
+ * nfst_backtrace restricted to the group's lattices; small-lattice groups follow the
+ * backpointers inside the kernel, from shared memory (delta may then be NULL). */
+int nfst_viterbi_paths_f32(const nfst_packed_lattices_t* lat, const nfst_launch_t* launch, const nfst_scores_t* scores,
+                           float* delta, int32_t* backptr, float* vit_score, const int32_t* path_off,
+                           int32_t* path_arcs, int32_t* path_len, void* cuda_stream);
+
+/* Ragged result: copies every lattice's path_len[b] arcs from its slot path_buf[path_off[b]..] to
+ * out_arcs[out_off[b]..] and (if out_labels != NULL) their labels to out_labels (path_labels of
+ * lattice_viterbi; replaces the best-sample read-out of lightning.py:474-479). */
+int nfst_compact_paths(const nfst_packed_lattices_t* lat, const int32_t* path_off, const int32_t* path_len,
+                       const int32_t* path_buf, const int64_t* out_off, int32_t* out_arcs, int32_t* out_labels,
+                       void* cuda_stream);
 
 /* out[(b*k+j)*dense_states + orig_state[s]] = exp(beta[s]) for j < k (float32 out; beta
  * float32 or float64 per beta_f64); `out` must be zero-filled by the caller (states that

@@ -89,6 +89,8 @@ SYMBOLS = {
     "nfst_fwd_bwd_small_f32": (C.c_int, [C.POINTER(PackedLatticesC), C.POINTER(LaunchC), C.POINTER(ScoresC)] + [_P] * 8),
     "nfst_viterbi_f32": (C.c_int, [C.POINTER(PackedLatticesC), C.POINTER(LaunchC), C.POINTER(ScoresC), _P, _P, _P, _P]),
     "nfst_backtrace": (C.c_int, [C.POINTER(PackedLatticesC), _P, _P, _P, _P, _P]),
+    "nfst_viterbi_paths_f32": (C.c_int, [C.POINTER(PackedLatticesC), C.POINTER(LaunchC), C.POINTER(ScoresC), _P, _P, _P, _P, _P, _P, _P]),
+    "nfst_compact_paths": (C.c_int, [C.POINTER(PackedLatticesC), _P, _P, _P, _P, _P, _P, _P]),
     "nfst_beta_hat_level_f32": (C.c_int, [C.POINTER(PackedLatticesC), _P, C.c_int32, C.c_int32, _P, _P, _P, _P, _P, _P, _P]),
     "nfst_beta_to_dense": (C.c_int, [C.POINTER(PackedLatticesC), _P, C.c_int, _P, C.c_int32, C.c_int32, _P, _P]),
     "nfst_dense_count_arcs": (C.c_int, [_P, C.c_int64, C.c_int32, C.c_int32, _P, _P]),
@@ -118,7 +120,7 @@ def load() -> C.CDLL:
         fn = getattr(lib, name)  # AttributeError if the header and the library disagree
         fn.restype = res
         fn.argtypes = args
-    if lib.nfst_abi_version() != 8:
+    if lib.nfst_abi_version() != 9:
         raise RuntimeError("libnfst_b200.so ABI version mismatch")
     _lib = lib
     return lib

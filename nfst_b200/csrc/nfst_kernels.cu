@@ -725,6 +725,13 @@ __global__ void __launch_bounds__(256, NFST_MIN_BLOCKS)
 // posteriors and the Viterbi recursion can run in ONE launch (DO_FWD && DO_BWD), with alpha
 // never leaving the SM; or as two launches around an autograd boundary.
 // =====================================================================================
+// optional best-path read-out fused into the tropical pass (small-lattice kernel): all null = off
+struct PathOut {
+  const int32_t* path_off;  // [B+1] capacity offsets into path_arcs
+  int32_t* path_arcs;       // canonical arc ids, start -> sink
+  int32_t* path_len;        // [B]
+};
+
 struct SmallPlan {  // offsets in 32-bit words
   int a, b, d, lp, lg, inp, outp, src, win, dst, wout, lab, bp, hist, words;
 };
@@ -761,7 +768,7 @@ __global__ void __launch_bounds__(256, 4)
                       ST* __restrict__ alpha_g, ST* __restrict__ logz_g, const float* __restrict__ grad_logz,
                       ST* __restrict__ beta_g, ST* __restrict__ logz_bwd, float* __restrict__ post,
                       float* __restrict__ dtheta, float* __restrict__ delta_g, int32_t* __restrict__ backptr,
-                      float* __restrict__ vit_score) {
+                      float* __restrict__ vit_score, const PathOut paths) {
   const int NT = blockDim.x, tid = threadIdx.x;
   const ST neg_inf = static_cast<ST>(kNegInf);
   const bool want_hist = POST && dtheta != nullptr;
@@ -1103,6 +1110,18 @@ __global__ void __launch_bounds__(256, 4)
     if (tid == 0) {
       if (LOGS && logz_bwd) logz_bwd[b] = sB[start];
       if (TROP && vit_score) vit_score[b] = sD[start];
+      if (TROP && paths.path_arcs) {  // follow the backpointers while they are still in shared memory
+        const int off = paths.path_off[b], room = paths.path_off[b + 1] - off;
+        int s = start, k = 0;
+        while (k < room) {
+          const int a = sBP[s];
+          if (a < 0) break;
+          paths.path_arcs[off + k] = a;
+          ++k;
+          s = s_dst[a - a_lo];
+        }
+        paths.path_len[b] = k;
+      }
     }
     if (want_hist && dtheta_smem) {
       __syncthreads();
@@ -1426,11 +1445,12 @@ __global__ void nfst_pick_start_kernel(const nfst_packed_lattices_t L, const int
 // =====================================================================================
 // small kernels
 // =====================================================================================
-__global__ void nfst_backtrace_kernel(const nfst_packed_lattices_t L, const int32_t* __restrict__ backptr,
-                                      const int32_t* __restrict__ path_off, int32_t* __restrict__ path_arcs,
-                                      int32_t* __restrict__ path_len) {
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= L.n_lattices) return;
+__global__ void nfst_backtrace_kernel(const nfst_packed_lattices_t L, const int32_t* __restrict__ ids, int n,
+                                      const int32_t* __restrict__ backptr, const int32_t* __restrict__ path_off,
+                                      int32_t* __restrict__ path_arcs, int32_t* __restrict__ path_len) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  const int b = ids ? ids[t] : t;
   const int off = path_off[b];
   const int cap = path_off[b + 1] - off;
   int s = L.start_state[b];
@@ -1443,6 +1463,23 @@ __global__ void nfst_backtrace_kernel(const nfst_packed_lattices_t L, const int3
     s = L.dst_out[a];
   }
   path_len[b] = k;
+}
+
+// ragged result: path slots (capacity offsets) -> dense runs (out_off), plus the labels; one warp per lattice
+__global__ void nfst_compact_paths_kernel(const nfst_packed_lattices_t L, const int32_t* __restrict__ path_off,
+                                          const int32_t* __restrict__ path_len, const int32_t* __restrict__ path_buf,
+                                          const int64_t* __restrict__ out_off, int32_t* __restrict__ out_arcs,
+                                          int32_t* __restrict__ out_labels) {
+  const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (b >= L.n_lattices) return;
+  const int lane = threadIdx.x & 31;
+  const int src0 = path_off[b], len = path_len[b];
+  const int64_t dst0 = out_off[b];
+  for (int k = lane; k < len; k += 32) {
+    const int a = path_buf[src0 + k];
+    out_arcs[dst0 + k] = a;
+    if (out_labels) out_labels[dst0 + k] = L.label_out[a];
+  }
 }
 
 // =====================================================================================
@@ -1619,7 +1656,7 @@ int launch_fwd2(const nfst_packed_lattices_t* lat, const nfst_launch_t* launch, 
 template <typename ST, bool SC, bool TH, bool DO_FWD, bool DO_BWD, bool LOGS, bool TROP, bool POST>
 int launch_small(const nfst_packed_lattices_t* lat, const nfst_launch_t* launch, const nfst_scores_t* scores,
                  void* alpha, void* logz, const float* grad_logz, void* beta, void* logz_bwd, float* post, float* dtheta,
-                 float* delta, int32_t* backptr, float* vit_score, cudaStream_t st) {
+                 float* delta, int32_t* backptr, float* vit_score, cudaStream_t st, PathOut paths = PathOut{nullptr, nullptr, nullptr}) {
   const bool want_hist = POST && dtheta != nullptr;
   const int dtheta_smem = want_hist && lat->vocab <= NFST_THETA_SMEM_MAX;
   const SmallPlan P = small_plan(launch->small_max_states, launch->small_max_arcs, launch->small_max_levels,
@@ -1630,7 +1667,7 @@ int launch_small(const nfst_packed_lattices_t* lat, const nfst_launch_t* launch,
   kernel<<<launch->n_ids, launch->block_threads, bytes, st>>>(
       *lat, launch->lattice_ids, launch->small_max_states, launch->small_max_arcs, launch->small_max_levels,
       scores->arc_scores, scores->theta, dtheta_smem, static_cast<ST*>(alpha), static_cast<ST*>(logz), grad_logz,
-      static_cast<ST*>(beta), static_cast<ST*>(logz_bwd), post, dtheta, delta, backptr, vit_score);
+      static_cast<ST*>(beta), static_cast<ST*>(logz_bwd), post, dtheta, delta, backptr, vit_score, paths);
   if (cudaError_t e = cudaGetLastError())
     return fail(NFST_ERR_CUDA, "small-lattice launch (grid %d, block %d, %zu B shared): %s", launch->n_ids,
                 launch->block_threads, bytes, cudaGetErrorString(e));
@@ -1641,11 +1678,12 @@ int launch_small(const nfst_packed_lattices_t* lat, const nfst_launch_t* launch,
 template <typename ST, bool DO_FWD, bool DO_BWD, bool LOGS, bool TROP, bool POST>
 int launch_small_sc(const nfst_packed_lattices_t* lat, const nfst_launch_t* launch, const nfst_scores_t* scores,
                     void* alpha, void* logz, const float* grad_logz, void* beta, void* logz_bwd, float* post,
-                    float* dtheta, float* delta, int32_t* backptr, float* vit_score, cudaStream_t st) {
+                    float* dtheta, float* delta, int32_t* backptr, float* vit_score, cudaStream_t st,
+                    PathOut paths = PathOut{nullptr, nullptr, nullptr}) {
   const bool sc = scores->arc_scores != nullptr, th = scores->theta != nullptr;
 #define NFST_SM(SC, TH)                                                                                          \
   return launch_small<ST, SC, TH, DO_FWD, DO_BWD, LOGS, TROP, POST>(lat, launch, scores, alpha, logz, grad_logz, beta, \
-                                                                    logz_bwd, post, dtheta, delta, backptr, vit_score, st)
+                                                                    logz_bwd, post, dtheta, delta, backptr, vit_score, st, paths)
   if (sc && th) NFST_SM(true, true);
   if (sc) NFST_SM(true, false);
   NFST_SM(false, true);
@@ -1884,8 +1922,45 @@ int nfst_backtrace(const nfst_packed_lattices_t* lat, const int32_t* backptr, co
   if (lat->n_lattices == 0) return NFST_OK;
   const int threads = 128;
   const int blocks = (lat->n_lattices + threads - 1) / threads;
-  nfst_backtrace_kernel<<<blocks, threads, 0, static_cast<cudaStream_t>(cuda_stream)>>>(*lat, backptr, path_off,
-                                                                                        path_arcs, path_len);
+  nfst_backtrace_kernel<<<blocks, threads, 0, static_cast<cudaStream_t>(cuda_stream)>>>(
+      *lat, nullptr, lat->n_lattices, backptr, path_off, path_arcs, path_len);
+  NFST_CUDA_OK(cudaGetLastError());
+  return NFST_OK;
+}
+
+int nfst_viterbi_paths_f32(const nfst_packed_lattices_t* lat, const nfst_launch_t* launch, const nfst_scores_t* scores,
+                           float* delta, int32_t* backptr, float* vit_score, const int32_t* path_off,
+                           int32_t* path_arcs, int32_t* path_len, void* cuda_stream) {
+  if (int rc = check_launch(lat, launch)) return rc;
+  if (!scores || (!scores->arc_scores && !scores->theta)) return fail(NFST_ERR_BAD_ARG, "need arc_scores and/or theta");
+  if (!backptr || !path_off || !path_arcs || !path_len)
+    return fail(NFST_ERR_BAD_ARG, "nfst_viterbi_paths_f32: backptr, path_off, path_arcs and path_len are required");
+  if (launch->n_ids == 0) return NFST_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+  if (launch->small_max_arcs > 0)  // backpointers are followed inside the kernel, from shared memory
+    return launch_small_sc<float, false, true, false, true, false>(lat, launch, scores, nullptr, nullptr, nullptr, nullptr,
+                                                                   nullptr, nullptr, nullptr, delta, backptr, vit_score, st,
+                                                                   PathOut{path_off, path_arcs, path_len});
+  if (int rc = nfst_bwd_fused_f32(lat, launch, scores, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, delta,
+                                  backptr, vit_score, cuda_stream))
+    return rc;
+  const int threads = 128;
+  nfst_backtrace_kernel<<<(launch->n_ids + threads - 1) / threads, threads, 0, st>>>(
+      *lat, launch->lattice_ids, launch->n_ids, backptr, path_off, path_arcs, path_len);
+  NFST_CUDA_OK(cudaGetLastError());
+  return NFST_OK;
+}
+
+int nfst_compact_paths(const nfst_packed_lattices_t* lat, const int32_t* path_off, const int32_t* path_len,
+                       const int32_t* path_buf, const int64_t* out_off, int32_t* out_arcs, int32_t* out_labels,
+                       void* cuda_stream) {
+  if (!lat || !path_off || !path_len || !path_buf || !out_off || !out_arcs)
+    return fail(NFST_ERR_BAD_ARG, "nfst_compact_paths: null argument");
+  if (lat->n_lattices == 0) return NFST_OK;
+  const int threads = 256;
+  const int blocks = (lat->n_lattices * 32 + threads - 1) / threads;
+  nfst_compact_paths_kernel<<<blocks, threads, 0, static_cast<cudaStream_t>(cuda_stream)>>>(
+      *lat, path_off, path_len, path_buf, out_off, out_arcs, out_labels);
   NFST_CUDA_OK(cudaGetLastError());
   return NFST_OK;
 }

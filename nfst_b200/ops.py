@@ -325,6 +325,17 @@ def lattice_log_partition(packed: PackedLattices, arc_scores=None, theta=None, s
     return LatticeLogPartition.apply(arc_scores, theta, packed, state_dtype)
 
 
+def _path_slots(packed: PackedLattices) -> torch.Tensor:
+    """int32 [B+1]: every lattice's slot in the path buffer (a path has at most L_b - 1 arcs); cached."""
+    cached = getattr(packed, "_path_off", None)
+    if cached is None:
+        cap = torch.clamp(packed.n_levels.to(torch.int64) - 1, min=0)
+        off = torch.zeros(packed.n_lattices + 1, dtype=torch.int64, device=packed.device)
+        torch.cumsum(cap, 0, out=off[1:])
+        cached = packed._path_off = off.to(torch.int32)
+    return cached
+
+
 def lattice_viterbi(packed: PackedLattices, arc_scores=None, theta=None):
     """Best path per lattice under SURVEY.md section 8(c)'s rule (bit-exact, first-label
     tie-break).  Returns (score[B], path_offsets[B+1] int64, path_arcs int32 canonical arc
@@ -333,28 +344,34 @@ def lattice_viterbi(packed: PackedLattices, arc_scores=None, theta=None):
     global launch_count
     lib = _lib.load()
     dev = packed.device
-    r = lattice_backward(packed, arc_scores, theta, want_beta=False, want_viterbi=True)
-    cap = torch.clamp(packed.n_levels.to(torch.int64) - 1, min=0)
-    path_off = torch.zeros(packed.n_lattices + 1, dtype=torch.int64, device=dev)
-    torch.cumsum(cap, 0, out=path_off[1:])
-    path_off32 = path_off.to(torch.int32)
-    total = int(packed.n_states)  # >= sum of capacities; avoids a host sync
-    path_buf = torch.empty(max(total, 1), dtype=torch.int32, device=dev)
-    path_len = torch.empty(packed.n_lattices, dtype=torch.int32, device=dev)
+    sc, keep = _scores(packed, arc_scores, theta)
+    S, B = packed.n_states, packed.n_lattices
+    i32 = dict(dtype=torch.int32, device=dev)
+    delta = torch.empty(S, dtype=torch.float32, device=dev)
+    backptr = torch.empty(S, **i32)
+    vit = torch.empty(B, dtype=torch.float32, device=dev)
+    path_off = _path_slots(packed)
+    path_buf = torch.empty(max(S, 1), **i32)  # >= the sum of the slots; avoids a host sync
+    path_len = torch.empty(B, **i32)
     with torch.cuda.device(dev):
-        _lib.check(lib.nfst_backtrace(packed.c_struct(), r["backptr"].data_ptr(), path_off32.data_ptr(),
-                                      path_buf.data_ptr(), path_len.data_ptr(), _stream(dev)))
+        streams = _GroupStreams(dev, len(packed.groups))
+        for i, g in enumerate(packed.groups):
+            _lib.check(lib.nfst_viterbi_paths_f32(packed.c_struct(), _launch(g, torch.float32), sc, delta.data_ptr(),
+                                                  backptr.data_ptr(), vit.data_ptr(), path_off.data_ptr(),
+                                                  path_buf.data_ptr(), path_len.data_ptr(), streams[i]))
+            launch_count += 1 if g.small_max_arcs > 0 else 2
+        streams.join()
+        # ragged result: one cumsum, one host read of the total, one kernel
+        offsets = torch.zeros(B + 1, dtype=torch.int64, device=dev)
+        torch.cumsum(path_len, 0, out=offsets[1:])
+        n = int(offsets[-1])
+        path_arcs = torch.empty(n, **i32)
+        path_labels = torch.empty(n, **i32)
+        _lib.check(lib.nfst_compact_paths(packed.c_struct(), path_off.data_ptr(), path_len.data_ptr(), path_buf.data_ptr(),
+                                          offsets.data_ptr(), path_arcs.data_ptr(), path_labels.data_ptr(), _stream(dev)))
         launch_count += 1
-    # compact the per-lattice slots (plumbing; ragged result)
-    lens = path_len.to(torch.int64)
-    offsets = torch.zeros(packed.n_lattices + 1, dtype=torch.int64, device=dev)
-    torch.cumsum(lens, 0, out=offsets[1:])
-    n = int(offsets[-1])
-    lat = torch.repeat_interleave(torch.arange(packed.n_lattices, device=dev), lens, output_size=n)
-    pos = torch.arange(n, device=dev) - offsets[lat] + path_off[lat]
-    path_arcs = path_buf[pos]
-    path_labels = packed.label_out[path_arcs.to(torch.int64)]
-    return r["vit_score"], offsets, path_arcs, path_labels
+    del keep
+    return vit, offsets, path_arcs, path_labels
 
 
 def _level_state_lists(packed: PackedLattices):
