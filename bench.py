@@ -268,18 +268,24 @@ def main():
 
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(3 * a.steps + 2)]
 
+    all_sell = all(g.sell for g in packed.groups)
+    beta_buf = torch.empty(S, dtype=ops.resolve_state_dtype(packed), device=dev) if packed.has_sell else None
+
     def step(i=None):
+        """first pass: logZ (+ beta and the arc conditionals for sliced-column groups, alpha for CSR groups);
+        second pass: arc posteriors (+ beta for CSR groups)."""
         if i is not None:
             ev[3 * i].record()
-        alpha, logz = nb.lattice_forward(packed, arc_scores=scores)
+        logz, alpha, cond = ops.lattice_pull(packed, arc_scores=scores, beta_out=beta_buf)
         if i is not None:
             ev[3 * i + 1].record()
-        r = nb.lattice_backward(packed, arc_scores=scores, alpha=alpha, logz=logz, want_beta=True, want_post=True)
+        r = nb.lattice_backward(packed, arc_scores=scores, alpha=alpha, logz=logz, cond=cond, want_beta=not all_sell,
+                                want_post=True)
         if i is not None:
             ev[3 * i + 2].record()
         if world > 1:
             # the path's only collective: the loss all-reduce (posteriors feed the scorer's own backward)
-            loss.copy_(r["logz_bwd"].sum().reshape(1))
+            loss.copy_(logz.sum().reshape(1))
             dist.all_reduce(loss)
         return r
 
@@ -319,9 +325,12 @@ def main():
     # ---- e2e: host (pinned) buffers -> H2D -> fwd+bwd -> D2H logZ ----
     e2e = None
     if not a.no_e2e:
-        fields = ("state_off", "start_state", "sink_off", "sinks", "in_ptr", "src_in", "in2out", "out_ptr", "dst_out",
-                  "lanes_in_log2", "lanes_out_log2", "fwd_chunk_off", "fwd_chunks", "bwd_chunk_off", "bwd_chunks",
-                  "fwd_gather", "bwd_order")
+        if all_sell:  # the sliced-column kernels read nothing else (no in-order arrays, no chunk lists)
+            fields = ("state_off", "start_state", "level_off", "level_ptr", "out_ptr", "dst_out", "out_deg8")
+        else:
+            fields = ("state_off", "start_state", "sink_off", "sinks", "in_ptr", "src_in", "in2out", "out_ptr", "dst_out",
+                      "lanes_in_log2", "lanes_out_log2", "fwd_chunk_off", "fwd_chunks", "bwd_chunk_off", "bwd_chunks",
+                      "fwd_gather", "bwd_order", "out_deg8", "level_off", "level_ptr")
         host = {f: getattr(packed, f).cpu().pin_memory() for f in fields}
         host_scores = scores.cpu().pin_memory()
         host_ids = [g.ids.cpu().pin_memory() for g in packed.groups]
@@ -344,12 +353,13 @@ def main():
             for d_, h_ in zip(land_ids, host_ids):
                 d_.copy_(h_, non_blocking=True)
             land_scores.copy_(host_scores, non_blocking=True)
-            kw = dict(land)
-            # label arrays are not read when scores are per-arc; keep the resident ones
-            kw.update(label_in=packed.label_in, label_out=packed.label_out, orig_state=packed.orig_state,
-                      arc_origin=packed.arc_origin, arc_off=packed.arc_off, n_levels=packed.n_levels,
-                      level_off=packed.level_off, level_ptr=packed.level_ptr,
-                      fwd_chunk_level=packed.fwd_chunk_level, bwd_chunk_level=packed.bwd_chunk_level)
+            # arrays the kernels of this batch never read (labels when scores are per-arc, host-side
+            # bookkeeping, and for sliced-column batches the in-order arrays and chunk lists) stay resident
+            kw = {f: getattr(packed, f) for f in PackedLattices._INT_FIELDS}
+            kw.update(lanes_in_log2=packed.lanes_in_log2, lanes_out_log2=packed.lanes_out_log2, out_deg8=packed.out_deg8,
+                      src_out=packed.src_out, orig_state=packed.orig_state, arc_origin=packed.arc_origin,
+                      arc_off=packed.arc_off, n_levels=packed.n_levels)
+            kw.update(land)
             groups = [dataclasses.replace(g, ids=d_) for g, d_ in zip(packed.groups, land_ids)]
             p = PackedLattices(n_lattices=B, n_states=S, n_arcs=A, vocab=packed.vocab, static_scores=None,
                                dense_shape=None, groups=groups, max_levels=packed.max_levels, stats=packed.stats, **kw)
@@ -382,10 +392,21 @@ def main():
         return
 
     peak, peak_src = measured_peak_gbs()
-    bwd_bytes = 12 * A + 12 * S
-    fwd_bytes = 8 * A + 8 * S
-    achieved = bwd_bytes / (bwd_ms * 1e-3) / 1e9
-    traffic, traffic_src = profiled_traffic("nfst_bwd_kernel", A)
+    if all_sell:
+        # sliced-column passes: pull = dst + score read, cond write per arc, beta write per
+        # state; flow = dst + cond read, post write per arc.  Their sum, 24 A + 4 S, equals SURVEY 8(d)'s
+        # 20 A + 20 S at S = A/4.
+        names = ("sell_pull_kernel (beta + logZ + arc conditionals)", "sell_flow_kernel (arc posteriors)")
+        fwd_bytes, bwd_bytes = 12 * A + 4 * S, 12 * A
+    else:
+        names = ("nfst_fwd_kernel", "nfst_bwd_kernel (fused beta + posteriors)")
+        fwd_bytes, bwd_bytes = 8 * A + 8 * S, 12 * A + 12 * S
+    first = {"kernel": names[0], "achieved": fwd_bytes / (fwd_ms * 1e-3) / 1e9, "kernel_ms": fwd_ms,
+             "algorithmic_bytes_per_launch": fwd_bytes}
+    second = {"kernel": names[1], "achieved": bwd_bytes / (bwd_ms * 1e-3) / 1e9, "kernel_ms": bwd_ms,
+              "algorithmic_bytes_per_launch": bwd_bytes}
+    dom, other = (first, second) if fwd_ms >= bwd_ms else (second, first)
+    traffic, traffic_src = profiled_traffic(dom["kernel"].split(" ")[0], A)
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
@@ -393,14 +414,15 @@ def main():
         "config": {"workload": workload_name(a), "lattices_per_gpu": B, "arcs_per_gpu": A, "states_per_gpu": S,
                    "levels": packed.max_levels, "global_batch": B * world, "parallelism": f"dp{world} (lattices sharded, loss all-reduce only)",
                    "l2": "inputs larger than L2 (no flush)" if 20 * A > 2 * 126e6 else "inputs fit in L2 (no flush; latency-bound config)",
-                   "scores": "per-arc fp32, canonical order"},
+                   "scores": "per-arc fp32, canonical order",
+                   "execution": "sliced-column (nfst_sell.cu)" if all_sell else "CSR kernels (nfst_kernels.cu)"},
         "gpu_launches": launches,
         "clocks": clk,
-        "roofline": {"bound": "hbm", "kernel": "nfst_bwd_kernel (fused beta + posteriors)", "achieved": achieved,
-                     "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
-                     "algorithmic_bytes_per_launch": bwd_bytes, "kernel_ms": bwd_ms,
-                     "fwd_kernel": {"achieved": fwd_bytes / (fwd_ms * 1e-3) / 1e9, "kernel_ms": fwd_ms,
-                                    "algorithmic_bytes_per_launch": fwd_bytes},
+        "roofline": {"bound": "hbm", "kernel": dom["kernel"], "achieved": dom["achieved"],
+                     "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": dom["achieved"] / peak,
+                     "traffic": traffic, "traffic_source": traffic_src,
+                     "algorithmic_bytes_per_launch": dom["algorithmic_bytes_per_launch"], "kernel_ms": dom["kernel_ms"],
+                     "other_kernel": dict(other, frac=other["achieved"] / peak),
                      "step": {"achieved": (20 * A + 20 * S) / (ms_step * 1e-3) / 1e9,
                               "frac": (20 * A + 20 * S) / (ms_step * 1e-3) / 1e9 / peak}},
     }

@@ -43,7 +43,7 @@
 extern "C" {
 #endif
 
-#define NFST_ABI_VERSION 9
+#define NFST_ABI_VERSION 10
 
 typedef enum nfst_status {
   NFST_OK = 0,
@@ -103,6 +103,22 @@ typedef struct nfst_packed_lattices {
   const int32_t* fwd_gather;        /* [n_fwd_chunks][2]: canonical-id range [lo, hi) the chunk's arcs gather from */
   const int32_t* bwd_order;         /* [S] states in backward processing order: a permutation inside every
                                        backward chunk's state range, sorted by out-degree */
+  /* Sliced-column lattices (launch groups with nfst_launch_t.sell != 0; see nfst_sell_pull_f32).  The states
+   * of every level are sorted by out-degree, descending, and cut into SLICES of 32 consecutive states; the
+   * arcs of a slice occupy the canonical ids [out_ptr[first], out_ptr[end of slice]) like in CSR, but
+   * COLUMN-MAJOR without padding: first the label-wise 1st arc of every state of the slice that has one (in
+   * state order), then the 2nd arcs, ...  Lane i of a warp owns state i, so each column is one coalesced load.
+   * out_ptr[s+1] - out_ptr[s] is still the out-degree; out_deg8[s] = min(out-degree, 255) (255 = look at
+   * out_ptr).  Once a single state of a slice is left, its remaining arcs are contiguous. */
+  const uint8_t* out_deg8;          /* [S] */
+  /* One 16-byte descriptor per slice of the sliced-column lattices, in (lattice, level, position) order:
+   *   [0] canonical id of the slice's first arc, [1] id behind its last arc,
+   *   [2] bytes: start of column 1, 2, 3, 4 relative to [0]   (column 0 starts at 0),
+   *   [3] bytes: start of column 5, 6, 7; top byte = min(largest out-degree of the slice, 255).
+   * sell_lvl_slice is aligned with level_ptr: entry level_off[b]+l is the index of the first slice of level l
+   * of lattice b (the spare entry of each lattice closes its last level); CSR lattices own no slices. */
+  const int32_t* sell_desc;         /* [n_slices][4] */
+  const int32_t* sell_lvl_slice;    /* [sum_b (L_b+1)] */
 } nfst_packed_lattices_t;
 
 /*
@@ -138,6 +154,14 @@ typedef struct nfst_launch {
    * memory (at most small_max_states states, small_max_arcs arcs, small_max_levels levels) and is
    * processed there in one piece (nfst_small_kernel). */
   int32_t small_max_states, small_max_arcs, small_max_levels;
+  /* Sliced-column execution (sell != 0): one thread block of block_threads (32..1024) per lattice, one
+   * barrier per level, arcs read column by column straight into registers; window_states (a power of two) is
+   * the size of the shared-memory ring of DP values (>= the widest level of the group).  An arc is served from the ring iff
+   * dst < (first state of src's level) + window_states; the others (sell_far != 0 announces that some exist)
+   * go through global memory: the pull pass re-reads beta / delta, the flow pass adds into gamma_far.
+   * n_levels = largest level count of the group. */
+  int32_t sell;
+  int32_t sell_far;
 } nfst_launch_t;
 
 /* Arc scores: w(a) = (arc_scores ? arc_scores[a] : 0) + (theta ? theta[label(a)] : 0);
@@ -230,6 +254,33 @@ int nfst_dense_count_arcs(const int64_t* transition, int64_t n_rows, int32_t sta
 int nfst_dense_extract_arcs(const int64_t* transition, int64_t n_rows, int32_t states_per_lattice, int32_t vocab,
                             const int64_t* row_start, int32_t* arc_row, int32_t* arc_label, int32_t* arc_dst,
                             void* cuda_stream);
+
+/*
+ * Sliced-column passes (launch->sell != 0).
+ *
+ * nfst_sell_pull_f32 -- deepest level first.  Log semiring when beta, logz_bwd or cond is given:
+ *   beta[S] / logz_bwd[B] (float32, or float64 when launch->state_f64; the recurrence itself always runs
+ *   in float64 with fp32 exponentials), and cond[A] (float32, real space):
+ *   cond[a] = exp(w_a + beta[dst_a] - beta[src_a]), the probability of arc a given its source state.
+ *   Tropical semiring when backptr is given: delta[S] (optional), backptr[S], vit_score[B] (optional),
+ *   same rule as nfst_bwd_fused_f32.  Groups with sell_far need beta (resp. delta): arcs longer than the
+ *   ring re-read them from global memory.  Replaces FSAGRUScorer.compute_beta_* (scorers.py:692-856, Wh = 0).
+ * nfst_sell_flow_f32 -- start level first: gamma[start] = grad_logz[b] (1 if NULL),
+ *   post[a] = gamma[src_a] * cond[a], gamma[dst_a] += post[a]; post may alias cond (in place).
+ *   post[a] = grad * d logZ / d w_a, the arc posterior.  Optional: dtheta[V] += post by label (caller
+ *   zero-fills); alpha[S] = log(gamma[s] / grad) + logz[b] - beta[s] (needs beta, logz in the launch's state
+ *   dtype; -inf where the state posterior underflows fp32).  gamma is accumulated with shared-memory
+ *   atomics: posteriors are reproducible to rounding (~1e-7 relative), not bit for bit.
+ *   gamma_far[S] (float32, zero-filled by the caller) is required for groups with sell_far and whenever alpha
+ *   is requested: it receives the flow of arcs longer than the ring (and, for alpha, into the last level).
+ */
+size_t nfst_sell_smem_bytes(const nfst_launch_t* launch, int32_t vocab, int pass, int with_trop, int with_table);
+int nfst_sell_pull_f32(const nfst_packed_lattices_t* lat, const nfst_launch_t* launch, const nfst_scores_t* scores,
+                       void* beta, void* logz_bwd, float* cond, float* delta, int32_t* backptr, float* vit_score,
+                       void* cuda_stream);
+int nfst_sell_flow_f32(const nfst_packed_lattices_t* lat, const nfst_launch_t* launch, const float* cond,
+                       const float* grad_logz, float* post, const void* beta, const void* logz, void* alpha,
+                       float* dtheta, float* gamma_far, void* cuda_stream);
 
 /* One level of the beta-hat recurrence (FSAGRUScorer.compute_beta_per_sample with Wh != 0,
  * scorers.py:732-747), for the `n_states` packed state ids in `states` (all of one topological

@@ -43,6 +43,9 @@ class PackedLatticesC(C.Structure):
         ("bwd_chunks", C.c_void_p),
         ("fwd_gather", C.c_void_p),
         ("bwd_order", C.c_void_p),
+        ("out_deg8", C.c_void_p),
+        ("sell_desc", C.c_void_p),
+        ("sell_lvl_slice", C.c_void_p),
     ]
 
 
@@ -65,6 +68,8 @@ class LaunchC(C.Structure):
         ("small_max_states", C.c_int32),
         ("small_max_arcs", C.c_int32),
         ("small_max_levels", C.c_int32),
+        ("sell", C.c_int32),
+        ("sell_far", C.c_int32),
     ]
 
 
@@ -91,6 +96,9 @@ SYMBOLS = {
     "nfst_backtrace": (C.c_int, [C.POINTER(PackedLatticesC), _P, _P, _P, _P, _P]),
     "nfst_viterbi_paths_f32": (C.c_int, [C.POINTER(PackedLatticesC), C.POINTER(LaunchC), C.POINTER(ScoresC), _P, _P, _P, _P, _P, _P, _P]),
     "nfst_compact_paths": (C.c_int, [C.POINTER(PackedLatticesC), _P, _P, _P, _P, _P, _P, _P]),
+    "nfst_sell_smem_bytes": (C.c_size_t, [C.POINTER(LaunchC), C.c_int32, C.c_int, C.c_int, C.c_int]),
+    "nfst_sell_pull_f32": (C.c_int, [C.POINTER(PackedLatticesC), C.POINTER(LaunchC), C.POINTER(ScoresC)] + [_P] * 7),
+    "nfst_sell_flow_f32": (C.c_int, [C.POINTER(PackedLatticesC), C.POINTER(LaunchC)] + [_P] * 9),
     "nfst_beta_hat_level_f32": (C.c_int, [C.POINTER(PackedLatticesC), _P, C.c_int32, C.c_int32, _P, _P, _P, _P, _P, _P, _P]),
     "nfst_beta_to_dense": (C.c_int, [C.POINTER(PackedLatticesC), _P, C.c_int, _P, C.c_int32, C.c_int32, _P, _P]),
     "nfst_dense_count_arcs": (C.c_int, [_P, C.c_int64, C.c_int32, C.c_int32, _P, _P]),
@@ -120,7 +128,7 @@ def load() -> C.CDLL:
         fn = getattr(lib, name)  # AttributeError if the header and the library disagree
         fn.restype = res
         fn.argtypes = args
-    if lib.nfst_abi_version() != 9:
+    if lib.nfst_abi_version() != 10:
         raise RuntimeError("libnfst_b200.so ABI version mismatch")
     _lib = lib
     return lib

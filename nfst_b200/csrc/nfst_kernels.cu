@@ -50,6 +50,21 @@ int fail(int code, const char* fmt, ...) {
     if (_e != cudaSuccess) return fail(NFST_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString(_e)); \
   } while (0)
 
+}  // namespace
+
+// error reporting for the library's other translation units (nfst_sell.cu)
+int nfst_fail_msg(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_last_error = buf;
+  return code;
+}
+
+namespace {
+
 constexpr float kNegInf = -__builtin_huge_valf();
 #ifndef NFST_MIN_BLOCKS
 #define NFST_MIN_BLOCKS 3  // resident blocks per SM the register allocation aims for
@@ -1611,6 +1626,8 @@ __global__ void nfst_dense_extract_kernel(const int64_t* __restrict__ tr, int64_
 // ---- host helpers ------------------------------------------------------------------
 int check_launch(const nfst_packed_lattices_t* lat, const nfst_launch_t* launch) {
   if (!lat || !launch) return fail(NFST_ERR_BAD_ARG, "null lattice or launch descriptor");
+  if (launch->sell)
+    return fail(NFST_ERR_BAD_ARG, "sliced-column launch group: its arcs are not CSR, use nfst_sell_pull_f32 / nfst_sell_flow_f32");
   if (launch->n_ids < 0 || launch->n_ids > lat->n_lattices)
     return fail(NFST_ERR_BAD_ARG, "n_ids=%d out of range (B=%d)", launch->n_ids, lat->n_lattices);
   const int bt = launch->block_threads;
@@ -1931,7 +1948,9 @@ int nfst_backtrace(const nfst_packed_lattices_t* lat, const int32_t* backptr, co
 int nfst_viterbi_paths_f32(const nfst_packed_lattices_t* lat, const nfst_launch_t* launch, const nfst_scores_t* scores,
                            float* delta, int32_t* backptr, float* vit_score, const int32_t* path_off,
                            int32_t* path_arcs, int32_t* path_len, void* cuda_stream) {
-  if (int rc = check_launch(lat, launch)) return rc;
+  if (!launch || !launch->sell) {
+    if (int rc = check_launch(lat, launch)) return rc;
+  }
   if (!scores || (!scores->arc_scores && !scores->theta)) return fail(NFST_ERR_BAD_ARG, "need arc_scores and/or theta");
   if (!backptr || !path_off || !path_arcs || !path_len)
     return fail(NFST_ERR_BAD_ARG, "nfst_viterbi_paths_f32: backptr, path_off, path_arcs and path_len are required");
@@ -1941,9 +1960,13 @@ int nfst_viterbi_paths_f32(const nfst_packed_lattices_t* lat, const nfst_launch_
     return launch_small_sc<float, false, true, false, true, false>(lat, launch, scores, nullptr, nullptr, nullptr, nullptr,
                                                                    nullptr, nullptr, nullptr, delta, backptr, vit_score, st,
                                                                    PathOut{path_off, path_arcs, path_len});
-  if (int rc = nfst_bwd_fused_f32(lat, launch, scores, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, delta,
-                                  backptr, vit_score, cuda_stream))
+  if (launch->sell) {  // sliced-column group: tropical pull pass (nfst_sell.cu), then the same read-out
+    if (int rc = nfst_sell_pull_f32(lat, launch, scores, nullptr, nullptr, nullptr, delta, backptr, vit_score, cuda_stream))
+      return rc;
+  } else if (int rc = nfst_bwd_fused_f32(lat, launch, scores, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr,
+                                         delta, backptr, vit_score, cuda_stream)) {
     return rc;
+  }
   const int threads = 128;
   nfst_backtrace_kernel<<<(launch->n_ids + threads - 1) / threads, threads, 0, st>>>(
       *lat, launch->lattice_ids, launch->n_ids, backptr, path_off, path_arcs, path_len);

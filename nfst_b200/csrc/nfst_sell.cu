@@ -1,0 +1,857 @@
+// nfst_sell.cu -- "sliced column" execution model of the lattice DP (sm_100a).
+//
+// Same recurrence as nfst_kernels.cu (the reference's FSAGRUScorer.compute_beta_per_sample,
+// src/modules/scorers.py:692-751, with Wh = 0, in log space), for lattices whose levels are at
+// least a warp wide.  The packer stores the arcs of such a lattice slice by slice: a SLICE is
+// 32 consecutive states of one topological level (sorted by out-degree, descending), and the
+// slice's arcs are laid out column-major without padding -- column k holds the k-th arc of every
+// state of the slice that has more than k arcs, in lane order.  Lane i of a warp owns state i of
+// the slice, so the k-th arcs of 32 states are ONE coalesced 128-byte load, straight from global
+// memory into registers: no shared-memory staging, no row pointers (one base offset per slice
+// and one degree byte per state), ~10 thread-instructions per arc.
+//
+// A thread block owns one lattice and walks its levels with one barrier per level.  None of the
+// index / score loads depends on a DP value, so every warp runs ahead of the barriers over its
+// static list of slices: degree bytes and slice bounds are loaded two slices ahead, the arc
+// columns of the next slice are pulled into L2 (prefetch.global.L2, no registers held), and the
+// current slice's columns are then loaded together -- one L2 latency per slice, HBM latency
+// hidden.  (Holding the next slice's columns in registers instead costs 32 registers: at 64
+// registers per thread ptxas spills them, and a spilled load result stalls on its own load.)
+// The only data that crosses levels, the per-state DP value, lives in a shared-memory ring.
+//
+//   pull pass (deepest level first): beta[s] = logsumexp_k (w_k + beta[dst_k]) in float64
+//       (exp in fp32), and the arc's conditional probability cond[a] = exp(w + beta[dst] - beta[s])
+//       written in real space next to it; or the tropical recursion delta / backpointer
+//       (one fp32 add per arc, first maximum in label order wins -- bit-exact rule).
+//   flow pass (start level first): gamma[start] = g_b; post[a] = gamma[src] * cond[a];
+//       gamma[dst] += post[a] (shared-memory atomics).  post is d logZ / d w_a scaled by the
+//       incoming gradient -- no second logsumexp, no alpha pass, both passes stream the same
+//       arrays in the same order.  alpha[s] = log gamma[s] + logZ - beta[s] on request.
+#include "nfst_b200.h"
+
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <type_traits>
+#include <utility>
+
+int nfst_fail_msg(int code, const char* fmt, ...);  // nfst_kernels.cu (sets the thread's last error)
+
+namespace {
+
+#define SELL_CUDA_OK(expr)                                                                                  \
+  do {                                                                                                      \
+    cudaError_t _e = (expr);                                                                                \
+    if (_e != cudaSuccess) return nfst_fail_msg(NFST_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString(_e)); \
+  } while (0)
+
+constexpr int KU = 8;  // arc columns held in registers per slice; deeper columns take the tail loops
+constexpr int TW = 4;  // columns per tail window (loads issued together)
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kLn2 = 0.6931471805599453f;
+constexpr float kFloor = -1.0e30f;
+constexpr float kNegInf = -__builtin_huge_valf();
+
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float lg2_approx(float x) {
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+extern __shared__ __align__(16) unsigned char sell_smem[];
+
+// position of a slice in a lattice: level l, slice j of that level
+struct Pos {
+  int l, j;
+  bool ok;
+};
+// degree byte + descriptor of a slice (loaded two slices ahead; nothing here waits for a load)
+struct StA {
+  int s;     // this lane's state (global packed id); 0x7fffffff for idle lanes
+  int degb;  // its out-degree byte (0 for idle lanes; 255 = saturated, see slice_degree)
+  int4 d;    // nfst_packed_lattices_t.sell_desc: arc range, column starts, largest degree
+};
+// start of column K (0..7) of a slice, relative to its first arc -- no warp vote on the hot path
+template <int K>
+__device__ __forceinline__ int col_start(const int4& d) {
+  if (K == 0) return 0;
+  const unsigned w = static_cast<unsigned>(K <= 4 ? d.z : d.w);
+  return (w >> (8 * ((K - 1) & 3))) & 0xff;
+}
+__device__ __forceinline__ int slice_dmax8(const int4& d) { return static_cast<unsigned>(d.w) >> 24; }
+
+// lsl[l] = index of the first slice of level l (lsl[n_levels] closes the last level)
+template <bool DESC>
+__device__ __forceinline__ void advance(Pos& p, const int* lsl, int n_levels, int warp, int nw) {
+  p.j += nw;
+  while (DESC ? p.l >= 0 : p.l < n_levels) {
+    if (p.j < lsl[p.l + 1] - lsl[p.l]) {
+      p.ok = true;
+      return;
+    }
+    p.l += DESC ? -1 : 1;
+    p.j = warp;
+  }
+  p.ok = false;
+}
+
+__device__ __forceinline__ StA load_a(const Pos& p, const int* lvl, const int* lsl, int lane,
+                                      const uint8_t* __restrict__ deg8, const int4* __restrict__ desc) {
+  StA a;
+  a.s = 0x7fffffff;
+  a.degb = 0;
+  a.d = make_int4(0, 0, 0, 0);
+  if (p.ok) {
+    const int first = lvl[p.l] + 32 * p.j;
+    if (first + lane < lvl[p.l + 1]) {
+      a.s = first + lane;
+      a.degb = __ldg(deg8 + a.s);
+    }
+    a.d = __ldg(desc + lsl[p.l] + p.j);
+  }
+  return a;
+}
+// true out-degree (the byte saturates at 255)
+__device__ __forceinline__ int slice_degree(const StA& a, const int32_t* __restrict__ out_ptr) {
+  int deg = a.degb;
+  if (deg == 255) deg = __ldg(out_ptr + a.s + 1) - __ldg(out_ptr + a.s);
+  return deg;
+}
+// Visit columns 0..KU-1 of a slice: f(k, on, arc) with k a compile-time constant for the caller's register
+// arrays.  Straight-line and predicated per lane (on = the lane's state has a k-th arc): no warp vote, no
+// branch on the slice's largest degree -- the branches cost more in reconvergence and register moves than the
+// idle columns do.
+template <int K, typename F>
+__device__ __forceinline__ void for_columns(const int4& d, int deg, int lane, F&& f) {
+  if constexpr (K < KU) {
+    f(std::integral_constant<int, K>{}, deg > K, d.x + col_start<K>(d) + lane);
+    for_columns<K + 1>(d, deg, lane, f);
+  }
+}
+// pull the arcs [b0, b1) of a per-arc array into L2: lane j touches the j-th 128-byte line
+__device__ __forceinline__ void prefetch_arcs(const void* arr, int b0, int b1, int lane) {
+  if (b1 <= b0) return;
+  const char* first = reinterpret_cast<const char*>((reinterpret_cast<uintptr_t>(arr) + 4ull * b0) & ~uintptr_t(127));
+  const char* last = reinterpret_cast<const char*>(arr) + 4ull * (b1 - 1);
+  for (const char* q = first + 128 * lane; q <= last; q += 4096) asm volatile("prefetch.global.L2 [%0];" ::"l"(q));
+}
+
+// rare path: an arc longer than the shared-memory ring (kept out of line: no 64-bit address arithmetic in
+// the hot loops).  The value was written by this block before an earlier level barrier.
+#ifdef SELL_FAR_INLINE
+#define SELL_FAR_ATTR __forceinline__
+#else
+#define SELL_FAR_ATTR __noinline__
+#endif
+template <typename T>
+__device__ SELL_FAR_ATTR T far_load(const T* p, int i) {
+  return *reinterpret_cast<const volatile T*>(p + i);
+}
+
+// ---- columns k >= KU of a slice (states with more arcs than the register window holds) ----
+// tail_windows: while more than one state is still active, hands out further windows of TW columns --
+// win(a, on): a[j] = this lane's arc in column k + j, on[j] = the lane has one -- so that a window's loads are
+// issued together (one memory latency per window, not per column).  Returns with (col, k) at the first
+// column that has at most one active state.  Degrees descend inside a slice, so that state is lane 0's and
+// the rest of ITS arcs are contiguous from `col` (single-entry columns): the caller strides the whole warp
+// over them (tail_rest) and reduces what the helper lanes computed back into lane 0.
+template <typename Win>
+__device__ __forceinline__ void tail_windows(int deg, int& col, int& k, int lane, Win win) {
+  for (;;) {
+    if (__popc(__ballot_sync(0xffffffffu, deg > k)) <= 1) return;
+    int a[TW];
+    bool on[TW];
+#pragma unroll
+    for (int j = 0; j < TW; ++j) {
+      on[j] = deg > k + j;
+      a[j] = col + lane;
+      col += __popc(__ballot_sync(0xffffffffu, on[j]));
+    }
+    k += TW;
+    win(a, on);
+  }
+}
+__device__ __forceinline__ int tail_rest(int deg, int k) {
+  const int r = __shfl_sync(0xffffffffu, deg, 0) - k;
+  return r > 0 ? r : 0;
+}
+
+// online logsumexp pair (m, s): value = m + log(s); branch-free, finite floor instead of -inf
+template <typename RT>
+__device__ __forceinline__ void lse_push(RT& m, float& s, RT v) {
+  const float d = static_cast<float>(v - m);
+  const float e = ex2_approx(-fabsf(d) * kLog2e);
+  const bool up = d > 0.0f;
+  s = up ? fmaf(s, e, 1.0f) : s + e;
+  m = up ? v : m;
+}
+template <typename RT>
+__device__ __forceinline__ void lse_join(RT& m, float& s, RT m2, float s2) {
+  const float d = static_cast<float>(m2 - m);
+  const float e = ex2_approx(-fabsf(d) * kLog2e);
+  const bool up = d > 0.0f;
+  s = up ? fmaf(s, e, s2) : fmaf(s2, e, s);
+  m = up ? m2 : m;
+}
+
+// =====================================================================================
+// pull pass
+// =====================================================================================
+// NT_MAX: largest block the instantiation may be launched with; both variants are held to 64 registers
+// (8 blocks of 128 threads per SM: 1024 lattices fit the 148 SMs in ONE wave)
+template <bool TROP, bool SC, bool TH, bool COND, typename OT, int NT_MAX>
+__global__ void __launch_bounds__(NT_MAX, NT_MAX == 256 ? 4 : 1)
+    sell_pull_kernel(const nfst_packed_lattices_t L, const int32_t* __restrict__ ids, int W, int max_levels,
+                     int theta_smem, int far, const float* __restrict__ arc_scores, const float* __restrict__ theta,
+                     OT* beta, OT* __restrict__ logz, float* __restrict__ cond, float* delta,
+                     int32_t* __restrict__ backptr, float* __restrict__ vit_score) {
+  using RT = typename std::conditional<TROP, float, double>::type;
+  using RingT = typename std::conditional<TROP, float, OT>::type;  // ring precision = the state dtype
+  RingT* const ring = reinterpret_cast<RingT*>(sell_smem);
+  const int lvl_words = (max_levels + 2 + 3) & ~3;
+  int* const lvl = reinterpret_cast<int*>(sell_smem + static_cast<size_t>(W) * sizeof(RingT));
+  int* const lsl = lvl + lvl_words;
+  const float* th = theta;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
+  const int b = ids ? ids[blockIdx.x] : blockIdx.x;
+  const int lo = L.level_off[b];
+  const int n_levels = L.level_off[b + 1] - lo - 1;
+  for (int i = tid; i <= n_levels; i += blockDim.x) {
+    lvl[i] = L.level_ptr[lo + i];
+    lsl[i] = L.sell_lvl_slice[lo + i];
+  }
+  const int4* __restrict__ desc = reinterpret_cast<const int4*>(L.sell_desc);
+  if (TH && theta_smem) {
+    float* sth = reinterpret_cast<float*>(lsl + lvl_words);
+    for (int i = tid; i < L.vocab; i += blockDim.x) sth[i] = theta[i];
+    th = sth;
+  }
+  __syncthreads();
+  const int mask = W - 1;
+  const int start = L.start_state[b];
+  const uint8_t* __restrict__ deg8 = L.out_deg8;
+  const int32_t* __restrict__ dst_out = L.dst_out;
+  const int32_t* __restrict__ label_out = L.label_out;
+  // DP value of an arc's destination.  States of the last level are final: beta = 1 (scorers.py:720),
+  // delta = 0 -- no load.  Otherwise from the ring while dst < lim (= first state of the current level + W:
+  // the state that would overwrite dst's slot has not been reached), else from global memory.
+  const int last0 = lvl[n_levels - 1];
+  int lim = 0x7fffffff;
+  int lim2 = last0;
+  // slow part of the rule (d >= lim2 = min(lim, last0), set per level below)
+  auto nbr_slow = [&](int d) -> RT {
+    if (d >= last0) return static_cast<RT>(0);
+    return TROP ? static_cast<RT>(far_load(delta, d)) : static_cast<RT>(far_load(beta, d));
+  };
+  auto nbr = [&](int d) -> RT {
+    if (d < lim2) return static_cast<RT>(ring[d & mask]);
+    return nbr_slow(d);
+  };
+  auto arc_score = [&](int a) -> float {
+    float w = SC ? arc_scores[a] : 0.0f;
+    if (TH) w += th[label_out[a]];
+    return w;
+  };
+  // values of one window of tail columns, loads first
+  auto window_values = [&](const int (&a)[TW], const bool (&on)[TW], RT (&v)[TW], RT fill) {
+    int d[TW];
+    float w[TW];
+#pragma unroll
+    for (int j = 0; j < TW; ++j) {
+      d[j] = 0;
+      w[j] = 0.0f;
+      if (on[j]) {
+        d[j] = dst_out[a[j]];
+        w[j] = arc_score(a[j]);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < TW; ++j) v[j] = on[j] ? (TROP ? static_cast<RT>(__fadd_rn(w[j], static_cast<float>(nbr(d[j]))))
+                                                      : static_cast<RT>(w[j]) + nbr(d[j]))
+                                              : fill;
+  };
+
+  // ---- pipeline state: slice being computed, the next one (prefetched into L2), the one after (descriptor loading)
+  Pos pc, pn, pa;
+  pc.l = n_levels - 1; pc.j = warp - nw; pc.ok = false;
+  advance<true>(pc, lsl, n_levels, warp, nw);
+  pn = pc;
+  if (pn.ok) advance<true>(pn, lsl, n_levels, warp, nw);
+  StA ac = load_a(pc, lvl, lsl, lane, deg8, desc);
+  StA an = load_a(pn, lvl, lsl, lane, deg8, desc);
+  const int lim_cap = last0;  // ring reads need dst < min(lim, last0)
+
+#pragma unroll 1
+  for (int l = n_levels - 1; l >= 0; --l) {
+    if (far) {
+      lim = lvl[l] + W;
+      lim2 = min(lim, lim_cap);
+    }
+#pragma unroll 1
+    while (pc.ok && pc.l == l) {
+      // descriptor of the slice after next; arcs of the next slice into L2
+      pa = pn;
+      if (pa.ok) advance<true>(pa, lsl, n_levels, warp, nw);
+      const StA aa = load_a(pa, lvl, lsl, lane, deg8, desc);
+      if (pn.ok) {
+        prefetch_arcs(dst_out, an.d.x, an.d.y, lane);
+        if (SC) prefetch_arcs(arc_scores, an.d.x, an.d.y, lane);
+        if (TH) prefetch_arcs(label_out, an.d.x, an.d.y, lane);
+      }
+
+      // ---- the current slice's register window: all loads first ----
+      const int deg = slice_degree(ac, L.out_ptr), s = ac.s;
+      const int dmax = slice_dmax8(ac.d);  // 255 = "255 or more"
+      int dstc[KU];
+      float wc[KU];
+      for_columns<0>(ac.d, deg, lane, [&](auto kc, bool on, int a) {
+        constexpr int k = decltype(kc)::value;
+        dstc[k] = 0;
+        wc[k] = 0.0f;
+        if (on) {
+          dstc[k] = __ldg(dst_out + a);
+          if (SC) wc[k] = __ldg(arc_scores + a);
+          if (TH) wc[k] += th[__ldg(label_out + a)];
+        }
+      });
+      // destinations' DP values: from the ring, straight-line; the rare ones beyond it are patched afterwards
+      RingT rv[KU];
+      bool any_slow = false;
+      for_columns<0>(ac.d, deg, lane, [&](auto kc, bool on, int) {
+        constexpr int k = decltype(kc)::value;
+        rv[k] = ring[dstc[k] & mask];
+        any_slow |= on && dstc[k] >= lim2;
+      });
+      if (any_slow) {
+        for_columns<0>(ac.d, deg, lane, [&](auto kc, bool on, int) {
+          constexpr int k = decltype(kc)::value;
+          if (on && dstc[k] >= lim2) rv[k] = static_cast<RingT>(nbr_slow(dstc[k]));
+        });
+      }
+
+      // ---- DP of the current slice ----
+      if (!TROP) {
+        // register window: two passes over registers (max, then exponentials)
+        // t_k = w_k + beta[dst_k] in float64; kept as float32 offsets from the first finite one (t0): the
+        // offsets are small numbers, so nothing is lost, and 8 registers hold the window instead of 16
+        RT t0 = static_cast<RT>(wc[0]) + static_cast<RT>(rv[0]);
+        if (deg > 0 && !(t0 > static_cast<RT>(kFloor))) {  // rare: the first arc scores -inf -- take the largest
+          t0 = static_cast<RT>(kFloor);
+          for_columns<0>(ac.d, deg, lane, [&](auto kc, bool on, int) {
+            constexpr int k = decltype(kc)::value;
+            const RT t = static_cast<RT>(wc[k]) + static_cast<RT>(rv[k]);
+            if (on && t > t0) t0 = t;
+          });
+        }
+        float tf[KU];
+        for_columns<0>(ac.d, deg, lane, [&](auto kc, bool on, int) {
+          constexpr int k = decltype(kc)::value;
+          const float off = static_cast<float>(static_cast<RT>(wc[k]) + static_cast<RT>(rv[k]) - t0);
+          tf[k] = on ? off : kFloor;
+        });
+        float mf = kFloor;
+#pragma unroll
+        for (int k = 0; k < KU; ++k) mf = fmaxf(mf, tf[k]);
+        float e[KU];
+        float sum = 0.0f;
+        for_columns<0>(ac.d, deg, lane, [&](auto kc, bool, int) {
+          constexpr int k = decltype(kc)::value;
+          e[k] = ex2_approx((tf[k] - mf) * kLog2e);  // idle lanes / -inf arcs: exp(-huge) = 0
+          sum += e[k];
+        });
+        RT m = mf > kFloor ? t0 + static_cast<RT>(mf) : static_cast<RT>(kFloor);
+        if (!(mf > kFloor)) sum = 0.0f;  // no finite arc: every term above was exp(0)
+        // further columns: merged online into (m, sum); the window's exponentials are rescaled at the end
+        const RT m_reg = m;
+        int col_tail = 0;
+        if (dmax > KU) {
+          int col = ac.d.x + col_start<KU - 1>(ac.d) + __popc(__ballot_sync(0xffffffffu, deg > KU - 1));
+          col_tail = col;
+          int k = KU;
+          tail_windows(deg, col, k, lane, [&](const int (&a)[TW], const bool (&on)[TW]) {
+            RT v[TW];
+            window_values(a, on, v, static_cast<RT>(kFloor));
+            RT mx = m;
+#pragma unroll
+            for (int j = 0; j < TW; ++j) mx = v[j] > mx ? v[j] : mx;
+            float add = 0.0f;
+#pragma unroll
+            for (int j = 0; j < TW; ++j) add += ex2_approx(static_cast<float>(v[j] - mx) * kLog2e);
+            sum = fmaf(sum, ex2_approx(static_cast<float>(m - mx) * kLog2e), add);
+            m = mx;
+          });
+          const int rest = tail_rest(deg, k);
+          if (rest > 0) {  // lane 0's state alone: every lane takes a share of its remaining arcs
+            RT hm = static_cast<RT>(kFloor);
+            float hs = 0.0f;
+#pragma unroll 4
+            for (int i = lane; i < rest; i += 32) {
+              const int a = col + i;
+              lse_push(hm, hs, static_cast<RT>(arc_score(a)) + nbr(dst_out[a]));
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+              const RT m2 = __shfl_xor_sync(0xffffffffu, hm, o);
+              const float s2 = __shfl_xor_sync(0xffffffffu, hs, o);
+              lse_join(hm, hs, m2, s2);
+            }
+            if (lane == 0) lse_join(m, sum, hm, hs);
+          }
+        }
+        // sinks: beta = 1 (scorers.py:720); a state whose arcs all score -inf: beta = -inf
+        RT bv = static_cast<RT>(0);
+        if (deg > 0) bv = sum > 0.0f ? m + static_cast<RT>(lg2_approx(sum) * kLn2) : static_cast<RT>(kNegInf);
+        if (COND) {
+          const float inv = sum > 0.0f ? __frcp_rn(sum) : 0.0f;
+          const float inv_reg = inv * ex2_approx(static_cast<float>(m_reg - m) * kLog2e);
+          for_columns<0>(ac.d, deg, lane, [&](auto kc, bool on, int a) {
+            constexpr int k = decltype(kc)::value;
+            if (on) cond[a] = e[k] * inv_reg;
+          });
+          if (dmax > KU) {
+            int col = col_tail, k = KU;
+            tail_windows(deg, col, k, lane, [&](const int (&a)[TW], const bool (&on)[TW]) {
+              RT v[TW];
+              window_values(a, on, v, static_cast<RT>(kFloor));
+#pragma unroll
+              for (int j = 0; j < TW; ++j)
+                if (on[j]) cond[a[j]] = ex2_approx(static_cast<float>(v[j] - m) * kLog2e) * inv;
+            });
+            const int rest = tail_rest(deg, k);
+            if (rest > 0) {
+              const RT m0 = __shfl_sync(0xffffffffu, m, 0);
+              const float inv0 = __shfl_sync(0xffffffffu, inv, 0);
+#pragma unroll 4
+              for (int i = lane; i < rest; i += 32) {
+                const int a = col + i;
+                const RT v = static_cast<RT>(arc_score(a)) + nbr(dst_out[a]);
+                cond[a] = ex2_approx(static_cast<float>(v - m0) * kLog2e) * inv0;
+              }
+            }
+          }
+        }
+        if (s != 0x7fffffff) {
+          // the ring slot of s is only read by shallower levels, i.e. after the level barrier
+          ring[s & mask] = static_cast<RingT>(bv);
+          if (beta) beta[s] = static_cast<OT>(bv);
+          if (s == start && logz) logz[b] = static_cast<OT>(bv);
+        }
+      } else {
+        float best = 0.0f;
+        int arg = -1;
+        for_columns<0>(ac.d, deg, lane, [&](auto kc, bool on, int a) {
+          constexpr int k = decltype(kc)::value;
+          const float c = __fadd_rn(wc[k], rv[k]);
+          if (on && (arg < 0 || c > best)) {  // strict: arcs of a state come in label order
+            best = c;
+            arg = a;
+          }
+        });
+        if (dmax > KU) {
+          int col = ac.d.x + col_start<KU - 1>(ac.d) + __popc(__ballot_sync(0xffffffffu, deg > KU - 1)), k = KU;
+          tail_windows(deg, col, k, lane, [&](const int (&a)[TW], const bool (&on)[TW]) {
+            RT v[TW];
+            window_values(a, on, v, kNegInf);
+#pragma unroll
+            for (int j = 0; j < TW; ++j)
+              if (on[j] && v[j] > best) {
+                best = v[j];
+                arg = a[j];
+              }
+          });
+          const int rest = tail_rest(deg, k);
+          if (rest > 0) {
+            float hbest = kNegInf;
+            int harg = 0x7fffffff;
+#pragma unroll 4
+            for (int i = lane; i < rest; i += 32) {
+              const int a = col + i;
+              const float c = __fadd_rn(arc_score(a), nbr(dst_out[a]));
+              if (harg == 0x7fffffff || c > hbest) {  // a lane's arcs ascend: its first maximum stays
+                hbest = c;
+                harg = a;
+              }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+              const float ob = __shfl_xor_sync(0xffffffffu, hbest, o);
+              const int oa = __shfl_xor_sync(0xffffffffu, harg, o);
+              if (oa != 0x7fffffff && (harg == 0x7fffffff || ob > hbest || (ob == hbest && oa < harg))) {
+                hbest = ob;
+                harg = oa;
+              }
+            }
+            if (lane == 0 && harg != 0x7fffffff && hbest > best) {  // earlier columns win ties (smaller label)
+              best = hbest;
+              arg = harg;
+            }
+          }
+        }
+        if (s != 0x7fffffff) {
+          ring[s & mask] = best;  // sinks: delta = 0, backpointer -1
+          if (delta) delta[s] = best;
+          backptr[s] = arg;
+          if (s == start && vit_score) vit_score[b] = best;
+        }
+      }
+
+      // ---- rotate the pipeline ----
+      pc = pn;
+      pn = pa;
+      ac = an;
+      an = aa;
+    }
+    __syncthreads();
+  }
+}
+
+// =====================================================================================
+// flow pass
+// =====================================================================================
+template <bool DTH, bool ALPHA, typename OT, int NT_MAX>
+__global__ void __launch_bounds__(NT_MAX, NT_MAX == 256 ? 4 : 1)
+    sell_flow_kernel(const nfst_packed_lattices_t L, const int32_t* __restrict__ ids, int W, int max_levels,
+                     int dtheta_smem, int far, const float* cond, const float* __restrict__ grad_logz, float* post,
+                     const OT* __restrict__ beta, const OT* __restrict__ logz, OT* __restrict__ alpha,
+                     float* __restrict__ dtheta, float* gamma_far) {
+  float* const ring = reinterpret_cast<float*>(sell_smem);
+  const int lvl_words = (max_levels + 2 + 3) & ~3;
+  int* const lvl = reinterpret_cast<int*>(sell_smem + static_cast<size_t>(W) * sizeof(float));
+  int* const lsl = lvl + lvl_words;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
+  const int b = ids ? ids[blockIdx.x] : blockIdx.x;
+  const int lo = L.level_off[b];
+  const int n_levels = L.level_off[b + 1] - lo - 1;
+  for (int i = tid; i <= n_levels; i += blockDim.x) {
+    lvl[i] = L.level_ptr[lo + i];
+    lsl[i] = L.sell_lvl_slice[lo + i];
+  }
+  const int4* __restrict__ desc = reinterpret_cast<const int4*>(L.sell_desc);
+  for (int i = tid; i < W; i += blockDim.x) ring[i] = 0.0f;
+  float* hist = dtheta;
+  if (DTH && dtheta_smem) {
+    hist = reinterpret_cast<float*>(lsl + lvl_words);
+    for (int i = tid; i < L.vocab; i += blockDim.x) hist[i] = 0.0f;
+  }
+  __syncthreads();
+  const int mask = W - 1;
+  const int start = L.start_state[b];
+  const float g = grad_logz ? grad_logz[b] : 1.0f;
+  if (tid == 0) ring[start & mask] = g;
+  __syncthreads();
+  const uint8_t* __restrict__ deg8 = L.out_deg8;
+  const int32_t* __restrict__ dst_out = L.dst_out;
+  const int32_t* __restrict__ label_out = L.label_out;
+  const double lz = ALPHA ? static_cast<double>(logz[b]) : 0.0;
+  const float inv_g = ALPHA ? 1.0f / g : 0.0f;
+  // gamma[dst] += p.  States of the last level have no arcs: their gamma is only needed for alpha (then it
+  // goes through gamma_far).  Otherwise in the ring while dst < lim (= first state of the current level + W:
+  // the previous owner of the slot has been consumed), else in global memory (gamma_far, read back when dst
+  // is reached).
+  const int last0 = lvl[n_levels - 1];
+  int lim = 0x7fffffff;
+  auto push = [&](int d, float p) {
+    if (d >= last0) {
+      if (ALPHA) atomicAdd(gamma_far + d, p);
+    } else if (d < lim) {
+      atomicAdd(&ring[d & mask], p);
+    } else {
+      atomicAdd(gamma_far + d, p);
+    }
+  };
+  const bool read_far = far || ALPHA;
+
+  Pos pc, pn, pa;
+  pc.l = 0; pc.j = warp - nw; pc.ok = false;
+  advance<false>(pc, lsl, n_levels, warp, nw);
+  pn = pc;
+  if (pn.ok) advance<false>(pn, lsl, n_levels, warp, nw);
+  StA ac = load_a(pc, lvl, lsl, lane, deg8, desc);
+  StA an = load_a(pn, lvl, lsl, lane, deg8, desc);
+
+#pragma unroll 1
+  for (int l = 0; l < n_levels; ++l) {
+    if (far) lim = lvl[l] + W;
+    const int lim2 = min(lim, last0);  // ring pushes need dst < lim2
+#pragma unroll 1
+    while (pc.ok && pc.l == l) {
+      pa = pn;
+      if (pa.ok) advance<false>(pa, lsl, n_levels, warp, nw);
+      const StA aa = load_a(pa, lvl, lsl, lane, deg8, desc);
+      if (pn.ok) {
+        prefetch_arcs(dst_out, an.d.x, an.d.y, lane);
+        prefetch_arcs(cond, an.d.x, an.d.y, lane);
+        if (DTH) prefetch_arcs(label_out, an.d.x, an.d.y, lane);
+      }
+
+      const int deg = slice_degree(ac, L.out_ptr), s = ac.s;
+      const int dmax = slice_dmax8(ac.d);
+      int dstc[KU], labc[KU];
+      float cc[KU];
+      for_columns<0>(ac.d, deg, lane, [&](auto kc, bool on, int a) {
+        constexpr int k = decltype(kc)::value;
+        dstc[k] = 0;
+        cc[k] = 0.0f;
+        labc[k] = 0;
+        if (on) {
+          dstc[k] = __ldg(dst_out + a);
+          cc[k] = cond[a];
+          if (DTH) labc[k] = __ldg(label_out + a);
+        }
+      });
+      float gs = 0.0f;
+      if (s != 0x7fffffff) {
+        // every arc into s comes from a shallower level: gamma[s] is final; free the slot
+        gs = ring[s & mask];
+        ring[s & mask] = 0.0f;
+        if (read_far) gs += *reinterpret_cast<volatile float*>(gamma_far + s);  // complete: earlier levels are done
+        if (ALPHA) {
+          const float r = gs * inv_g;
+          alpha[s] = r > 0.0f ? static_cast<OT>(static_cast<double>(lg2_approx(r) * kLn2) + lz -
+                                                static_cast<double>(beta[s]))
+                              : static_cast<OT>(kNegInf);
+        }
+      }
+      bool any_slow = false;
+      for_columns<0>(ac.d, deg, lane, [&](auto kc, bool on, int a) {
+        constexpr int k = decltype(kc)::value;
+        const float p = gs * cc[k];
+        if (on) {
+          post[a] = p;
+          if (dstc[k] < lim2) atomicAdd(&ring[dstc[k] & mask], p);
+          else any_slow = true;
+          if (DTH) atomicAdd(&hist[labc[k]], p);
+        }
+      });
+      if (any_slow) {  // rare: flow into the last level (alpha only) or beyond the ring
+        for_columns<0>(ac.d, deg, lane, [&](auto kc, bool on, int) {
+          constexpr int k = decltype(kc)::value;
+          if (on && dstc[k] >= lim2) push(dstc[k], gs * cc[k]);
+        });
+      }
+      if (dmax > KU) {
+        int col = ac.d.x + col_start<KU - 1>(ac.d) + __popc(__ballot_sync(0xffffffffu, deg > KU - 1)), k = KU;
+        tail_windows(deg, col, k, lane, [&](const int (&a)[TW], const bool (&on)[TW]) {
+          int d[TW];
+          float c[TW];
+          int lab[TW];
+#pragma unroll
+          for (int j = 0; j < TW; ++j) {
+            d[j] = 0;
+            c[j] = 0.0f;
+            lab[j] = 0;
+            if (on[j]) {
+              d[j] = dst_out[a[j]];
+              c[j] = cond[a[j]];
+              if (DTH) lab[j] = label_out[a[j]];
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < TW; ++j)
+            if (on[j]) {
+              const float p = gs * c[j];
+              post[a[j]] = p;
+              push(d[j], p);
+              if (DTH) atomicAdd(&hist[lab[j]], p);
+            }
+        });
+        const int rest = tail_rest(deg, k);
+        if (rest > 0) {
+          const float gs0 = __shfl_sync(0xffffffffu, gs, 0);
+#pragma unroll 4
+          for (int i = lane; i < rest; i += 32) {
+            const int a = col + i;
+            const float p = gs0 * cond[a];
+            post[a] = p;
+            push(dst_out[a], p);
+            if (DTH) atomicAdd(&hist[label_out[a]], p);
+          }
+        }
+      }
+
+      pc = pn;
+      pn = pa;
+      ac = an;
+      an = aa;
+    }
+    __syncthreads();
+  }
+  if (DTH && dtheta_smem) {
+    for (int i = tid; i < L.vocab; i += blockDim.x) {
+      const float v = hist[i];
+      if (v != 0.0f) atomicAdd(dtheta + i, v);
+    }
+  }
+}
+
+size_t pull_smem(int W, int max_levels, int vocab, int ring_bytes, bool theta_smem) {
+  size_t o = static_cast<size_t>(W) * ring_bytes;
+  o += 2 * static_cast<size_t>((max_levels + 2 + 3) & ~3) * 4;
+  if (theta_smem) o += static_cast<size_t>(vocab) * 4;
+  return (o + 15) & ~static_cast<size_t>(15);
+}
+size_t flow_smem(int W, int max_levels, int vocab, bool dtheta_smem) {
+  size_t o = static_cast<size_t>(W) * 4;
+  o += 2 * static_cast<size_t>((max_levels + 2 + 3) & ~3) * 4;
+  if (dtheta_smem) o += static_cast<size_t>(vocab) * 4;
+  return (o + 15) & ~static_cast<size_t>(15);
+}
+
+template <typename K>
+int prepare(K kernel, size_t smem) {
+  if (smem > 48 * 1024) {
+    SELL_CUDA_OK(cudaFuncSetAttribute(reinterpret_cast<const void*>(kernel),
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  }
+  return 0;
+}
+
+// blocks above 256 threads need the 64-register instantiation (NFST_SELL_REGS64=1 forces it, for experiments)
+bool big_blocks(const nfst_launch_t* launch) {
+  static const bool force = getenv("NFST_SELL_REGS64") != nullptr && getenv("NFST_SELL_REGS64")[0] == '1';
+  return force || launch->block_threads > 256;
+}
+
+int check_launch(const nfst_packed_lattices_t* lat, const nfst_launch_t* launch) {
+  if (!lat || !launch) return nfst_fail_msg(NFST_ERR_BAD_ARG, "null argument");
+  if (!launch->sell) return nfst_fail_msg(NFST_ERR_BAD_ARG, "launch group is not a sliced-column group");
+  if (!lat->out_deg8 || !lat->sell_desc || !lat->sell_lvl_slice)
+    return nfst_fail_msg(NFST_ERR_BAD_ARG, "packed lattices carry no sliced-column arrays (out_deg8, sell_desc, sell_lvl_slice)");
+  const int W = launch->window_states;
+  if (W < 32 || (W & (W - 1))) return nfst_fail_msg(NFST_ERR_BAD_ARG, "window_states must be a power of two >= 32");
+  const int nt = launch->block_threads;
+  if (nt < 32 || nt > 1024 || (nt & 31)) return nfst_fail_msg(NFST_ERR_BAD_ARG, "block_threads must be 32..1024, a multiple of 32");
+  if (launch->n_levels <= 0) return nfst_fail_msg(NFST_ERR_BAD_ARG, "n_levels (largest level count of the group) is required");
+  return 0;
+}
+
+template <bool TROP, bool COND, typename OT>
+int launch_pull(const nfst_packed_lattices_t* lat, const nfst_launch_t* launch, const nfst_scores_t* sc, OT* beta,
+                OT* logz, float* cond, float* delta, int32_t* backptr, float* vit, cudaStream_t stream) {
+  const bool has_sc = sc->arc_scores != nullptr, has_th = sc->theta != nullptr;
+  const bool th_smem = has_th && lat->vocab <= NFST_THETA_SMEM_MAX;
+  const size_t smem = pull_smem(launch->window_states, launch->n_levels, lat->vocab, TROP ? 4 : static_cast<int>(sizeof(OT)), th_smem);
+  if (smem > 227 * 1024) return nfst_fail_msg(NFST_ERR_TOO_LARGE, "sliced-column window needs %zu bytes of shared memory", smem);
+#define SELL_PULL_NT(SCv, THv, NTv)                                                                               \
+  do {                                                                                                            \
+    auto k = sell_pull_kernel<TROP, SCv, THv, COND, OT, NTv>;                                                     \
+    if (int rc = prepare(k, smem)) return rc;                                                                     \
+    k<<<launch->n_ids, launch->block_threads, smem, stream>>>(                                                    \
+        *lat, launch->lattice_ids, launch->window_states, launch->n_levels, th_smem ? 1 : 0, launch->sell_far,    \
+        sc->arc_scores, sc->theta, beta, logz, cond, delta, backptr, vit);                                        \
+  } while (0)
+#define SELL_PULL(SCv, THv)                                                                                       \
+  do {                                                                                                            \
+    if (big_blocks(launch)) SELL_PULL_NT(SCv, THv, 1024);                                                         \
+    else SELL_PULL_NT(SCv, THv, 256);                                                                             \
+  } while (0)
+  if (has_sc && has_th) SELL_PULL(true, true);
+  else if (has_th) SELL_PULL(false, true);
+  else SELL_PULL(true, false);  // no scores at all: SC with a null pointer is rejected by the caller
+#undef SELL_PULL
+#undef SELL_PULL_NT
+  SELL_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+size_t nfst_sell_smem_bytes(const nfst_launch_t* launch, int32_t vocab, int pass, int with_trop, int with_table) {
+  if (!launch) return 0;
+  const bool tab = with_table && vocab <= NFST_THETA_SMEM_MAX;
+  return pass == 0 ? pull_smem(launch->window_states, launch->n_levels, vocab, (with_trop || !launch->state_f64) ? 4 : 8, tab)
+                   : flow_smem(launch->window_states, launch->n_levels, vocab, tab);
+}
+
+int nfst_sell_pull_f32(const nfst_packed_lattices_t* lat, const nfst_launch_t* launch, const nfst_scores_t* scores,
+                       void* beta, void* logz_bwd, float* cond, float* delta, int32_t* backptr, float* vit_score,
+                       void* cuda_stream) {
+  if (int rc = check_launch(lat, launch)) return rc;
+  if (!scores || (!scores->arc_scores && !scores->theta))
+    return nfst_fail_msg(NFST_ERR_BAD_ARG, "arc_scores or theta is required");
+  if (launch->n_ids == 0) return 0;
+  cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
+  const bool logs = beta || logz_bwd || cond;
+  const bool trop = delta || backptr || vit_score;
+  if (trop && !backptr) return nfst_fail_msg(NFST_ERR_BAD_ARG, "the tropical pass needs backptr[S]");
+  if (launch->sell_far && ((logs && !beta) || (trop && !delta)))
+    return nfst_fail_msg(NFST_ERR_BAD_ARG, "a group with arcs longer than its ring (sell_far) needs beta[S] / delta[S]");
+  if (logs) {
+    int rc;
+    if (launch->state_f64) {
+      rc = cond ? launch_pull<false, true, double>(lat, launch, scores, static_cast<double*>(beta),
+                                                   static_cast<double*>(logz_bwd), cond, nullptr, nullptr, nullptr, stream)
+                : launch_pull<false, false, double>(lat, launch, scores, static_cast<double*>(beta),
+                                                    static_cast<double*>(logz_bwd), nullptr, nullptr, nullptr, nullptr, stream);
+    } else {
+      rc = cond ? launch_pull<false, true, float>(lat, launch, scores, static_cast<float*>(beta),
+                                                  static_cast<float*>(logz_bwd), cond, nullptr, nullptr, nullptr, stream)
+                : launch_pull<false, false, float>(lat, launch, scores, static_cast<float*>(beta),
+                                                   static_cast<float*>(logz_bwd), nullptr, nullptr, nullptr, nullptr, stream);
+    }
+    if (rc) return rc;
+  }
+  if (trop) {
+    if (int rc = launch_pull<true, false, float>(lat, launch, scores, nullptr, nullptr, nullptr, delta, backptr,
+                                                 vit_score, stream))
+      return rc;
+  }
+  return 0;
+}
+
+int nfst_sell_flow_f32(const nfst_packed_lattices_t* lat, const nfst_launch_t* launch, const float* cond,
+                       const float* grad_logz, float* post, const void* beta, const void* logz, void* alpha,
+                       float* dtheta, float* gamma_far, void* cuda_stream) {
+  if (int rc = check_launch(lat, launch)) return rc;
+  if (!cond || !post) return nfst_fail_msg(NFST_ERR_BAD_ARG, "cond[A] and post[A] are required");
+  if ((launch->sell_far || alpha) && !gamma_far)
+    return nfst_fail_msg(NFST_ERR_BAD_ARG, "gamma_far[S] is required for groups with arcs longer than their ring "
+                                           "(sell_far) and whenever alpha is requested");
+  if (alpha && (!beta || !logz)) return nfst_fail_msg(NFST_ERR_BAD_ARG, "alpha needs beta[S] and logz[B]");
+  if (launch->n_ids == 0) return 0;
+  cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
+  const bool dth_smem = dtheta && lat->vocab <= NFST_THETA_SMEM_MAX;
+  const size_t smem = flow_smem(launch->window_states, launch->n_levels, lat->vocab, dth_smem);
+  if (smem > 227 * 1024) return nfst_fail_msg(NFST_ERR_TOO_LARGE, "sliced-column window needs %zu bytes of shared memory", smem);
+#define SELL_FLOW(DTHv, ALv, OT)                                                                                  \
+  do {                                                                                                            \
+    if (big_blocks(launch)) SELL_FLOW_NT(DTHv, ALv, OT, 1024);                                                    \
+    else SELL_FLOW_NT(DTHv, ALv, OT, 256);                                                                        \
+  } while (0)
+#define SELL_FLOW_NT(DTHv, ALv, OT, NTv)                                                                          \
+  do {                                                                                                            \
+    auto k = sell_flow_kernel<DTHv, ALv, OT, NTv>;                                                                \
+    if (int rc = prepare(k, smem)) return rc;                                                                     \
+    k<<<launch->n_ids, launch->block_threads, smem, stream>>>(                                                    \
+        *lat, launch->lattice_ids, launch->window_states, launch->n_levels, dth_smem ? 1 : 0, launch->sell_far,   \
+        cond, grad_logz,                                                                                          \
+        post, static_cast<const OT*>(beta), static_cast<const OT*>(logz), static_cast<OT*>(alpha), dtheta,        \
+        gamma_far);                                                                                               \
+  } while (0)
+  if (launch->state_f64) {
+    if (dtheta && alpha) SELL_FLOW(true, true, double);
+    else if (dtheta) SELL_FLOW(true, false, double);
+    else if (alpha) SELL_FLOW(false, true, double);
+    else SELL_FLOW(false, false, double);
+  } else {
+    if (dtheta && alpha) SELL_FLOW(true, true, float);
+    else if (dtheta) SELL_FLOW(true, false, float);
+    else if (alpha) SELL_FLOW(false, true, float);
+    else SELL_FLOW(false, false, float);
+  }
+#undef SELL_FLOW
+#undef SELL_FLOW_NT
+  SELL_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+}  // extern "C"

@@ -80,6 +80,11 @@ def _launch(g: LaunchGroup, st_dtype: torch.dtype) -> "_lib.LaunchC":
     c.state_f64 = int(f64)
     c.chunk_cap = g.chunk_cap
     c.small_max_states, c.small_max_arcs, c.small_max_levels = g.small_max_states, g.small_max_arcs, g.small_max_levels
+    if g.sell:  # sliced-column group: the ring must cover every arc (no global-memory path behind it)
+        c.sell = 1
+        c.sell_far = int(g.sell_far)
+        c.window_states = g.sell_window
+        c.n_levels = g.n_levels
     if g.fwd_level_chunks is not None:  # level-major group: one launch per topological level
         c.n_levels = g.n_levels
         c.fwd_level_chunks = g.fwd_level_chunks.data_ptr()
@@ -87,6 +92,20 @@ def _launch(g: LaunchGroup, st_dtype: torch.dtype) -> "_lib.LaunchC":
         c.bwd_level_chunks = g.bwd_level_chunks.data_ptr()
         c.bwd_level_off = g.bwd_level_off.data_ptr()
         c.bwd_level_lat = g.bwd_level_lat.data_ptr()
+    return c
+
+
+def _launch_csr_forward(g: LaunchGroup, st_dtype: torch.dtype) -> "_lib.LaunchC":
+    """A sliced-column group as the CSR forward kernel sees it (its in-order arrays are ordinary CSR by
+    destination): used where alpha itself is asked for -- the sliced-column passes never compute it."""
+    c = _lib.LaunchC()
+    c.lattice_ids = g.ids.data_ptr()
+    c.n_ids = g.n
+    c.block_threads = g.csr_block_threads
+    f64 = st_dtype == torch.float64
+    c.window_states = g.window_states(8 if f64 else 4, WINDOW_BYTES_MAX)
+    c.state_f64 = int(f64)
+    c.chunk_cap = g.chunk_cap
     return c
 
 
@@ -104,6 +123,14 @@ def _scores(packed: PackedLattices, arc_scores, theta):
     c.arc_scores = _ptr(a)
     c.theta = _ptr(t)
     return c, (a, t)  # keep the tensors alive for the duration of the call
+
+
+def _gamma_far(packed: PackedLattices, alpha: bool = False) -> Optional[torch.Tensor]:
+    """zero-filled float32 [S] for the flow pass of groups whose ring does not cover every arc (and of every
+    sliced-column group when alpha is wanted: the flow into the last level is only needed for it)"""
+    if any(g.sell and (g.sell_far or alpha) for g in packed.groups):
+        return torch.zeros(packed.n_states, dtype=torch.float32, device=packed.device)
+    return None
 
 
 def _stream(dev) -> int:
@@ -150,11 +177,49 @@ def lattice_forward(packed: PackedLattices, arc_scores=None, theta=None, *, stat
     with torch.cuda.device(dev):
         streams = _GroupStreams(dev, len(packed.groups))
         for i, g in enumerate(packed.groups):
-            _lib.check(lib.nfst_fwd_f32(packed.c_struct(), _launch(g, st), sc, alpha.data_ptr(), logz.data_ptr(), streams[i]))
+            # sliced-column groups: their in-order arrays are plain CSR by destination, the forward kernel runs on them
+            lc = _launch_csr_forward(g, st) if g.sell else _launch(g, st)
+            _lib.check(lib.nfst_fwd_f32(packed.c_struct(), lc, sc, alpha.data_ptr(), logz.data_ptr(), streams[i]))
             launch_count += 1
         streams.join()
     del keep
     return alpha, logz
+
+
+def lattice_pull(packed: PackedLattices, arc_scores=None, theta=None, *, state_dtype="auto",
+                 beta_out: Optional[torch.Tensor] = None):
+    """First half of the exact log-marginal: ``logZ[B]`` plus what the gradient pass needs.
+
+    Returns ``(logz, alpha, cond)``: ``alpha[S]`` (forward pass) for the CSR launch groups, ``cond[A]`` --
+    the probability of every arc given its source state, ``exp(w + beta[dst] - beta[src])`` -- for the
+    sliced-column groups (beta pass; their posteriors then need no second logsumexp).  Either may be None.
+    ``beta_out[S]`` (state dtype) additionally receives beta of the sliced-column groups."""
+    global launch_count
+    lib = _lib.load()
+    dev = packed.device
+    sc, keep = _scores(packed, arc_scores, theta)
+    st = resolve_state_dtype(packed, state_dtype)
+    any_csr = any(not g.sell for g in packed.groups)
+    alpha = torch.empty(packed.n_states, dtype=st, device=dev) if any_csr else None
+    cond = torch.empty(packed.n_arcs, dtype=torch.float32, device=dev) if packed.has_sell else None
+    logz = torch.empty(packed.n_lattices, dtype=st, device=dev)
+    if beta_out is not None and (beta_out.dtype != st or beta_out.numel() != packed.n_states or beta_out.device != dev):
+        raise ValueError("beta_out must be [S] in the state dtype on the lattices' device")
+    if beta_out is None and any(g.sell and g.sell_far for g in packed.groups):
+        beta_out = torch.empty(packed.n_states, dtype=st, device=dev)  # arcs longer than the ring re-read beta
+    with torch.cuda.device(dev):
+        streams = _GroupStreams(dev, len(packed.groups))
+        for i, g in enumerate(packed.groups):
+            lc = _launch(g, st)
+            if g.sell:
+                _lib.check(lib.nfst_sell_pull_f32(packed.c_struct(), lc, sc, _ptr(beta_out), logz.data_ptr(),
+                                                  cond.data_ptr(), None, None, None, streams[i]))
+            else:
+                _lib.check(lib.nfst_fwd_f32(packed.c_struct(), lc, sc, alpha.data_ptr(), logz.data_ptr(), streams[i]))
+            launch_count += 1
+        streams.join()
+    del keep
+    return logz, alpha, cond
 
 
 def lattice_backward(
@@ -165,6 +230,7 @@ def lattice_backward(
     alpha: Optional[torch.Tensor] = None,
     logz: Optional[torch.Tensor] = None,
     grad_logz: Optional[torch.Tensor] = None,
+    cond: Optional[torch.Tensor] = None,
     want_beta: bool = True,
     want_post: bool = False,
     want_dtheta: bool = False,
@@ -173,16 +239,20 @@ def lattice_backward(
 ):
     """Fused backward pass.  Returns a dict with the requested outputs among
     ``beta[S]``, ``logz_bwd[B]`` (state dtype), ``post[A]``, ``dtheta[V]`` (float32),
-    ``delta[S]``, ``backptr[S]``, ``vit_score[B]`` (float32 / int32)."""
+    ``delta[S]``, ``backptr[S]``, ``vit_score[B]`` (float32 / int32).
+
+    Posteriors of CSR launch groups need ``alpha`` / ``logz`` (``lattice_forward`` or ``lattice_pull``);
+    sliced-column groups compute them from ``cond`` (``lattice_pull``; recomputed here when not given)."""
     global launch_count
     lib = _lib.load()
     dev = packed.device
     sc, keep = _scores(packed, arc_scores, theta)
     S, A, B, V = packed.n_states, packed.n_arcs, packed.n_lattices, packed.vocab
     logs = want_beta or want_post or want_dtheta
-    if (want_post or want_dtheta) and (alpha is None or logz is None):
+    any_csr = any(not g.sell for g in packed.groups)
+    if (want_post or want_dtheta) and any_csr and (alpha is None or logz is None):
         raise ValueError("posteriors need alpha and logz from lattice_forward")
-    st = alpha.dtype if alpha is not None else resolve_state_dtype(packed, state_dtype)
+    st = alpha.dtype if alpha is not None else (logz.dtype if logz is not None else resolve_state_dtype(packed, state_dtype))
     if alpha is not None and (logz.dtype != st or alpha.numel() != S or logz.numel() != B):
         raise ValueError("alpha / logz must come from lattice_forward on the same packed batch")
     out = {}
@@ -195,9 +265,29 @@ def lattice_backward(
     backptr = torch.empty(S, dtype=torch.int32, device=dev) if want_viterbi else None
     vit = torch.empty(B, **f32) if want_viterbi else None
     g32 = _check_f32("grad_logz", grad_logz, B, dev)
+    flow = (want_post or want_dtheta) and packed.has_sell
+    have_cond = cond is not None
+    gfar = _gamma_far(packed) if flow else None
+    if flow and not have_cond:
+        cond = post if want_post else torch.empty(A, **f32)  # the flow pass may run in place
     with torch.cuda.device(dev):
         streams = _GroupStreams(dev, len(packed.groups))
         for i, g in enumerate(packed.groups):
+            if g.sell:
+                lc = _launch(g, st)
+                need_pull = want_beta or want_viterbi or (flow and not have_cond)
+                if need_pull:
+                    _lib.check(lib.nfst_sell_pull_f32(
+                        packed.c_struct(), lc, sc, _ptr(beta) if (want_beta or (g.sell_far and flow and not have_cond)) else None,
+                        _ptr(logz_bwd) if logs else None,
+                        _ptr(cond) if (flow and not have_cond) else None, _ptr(delta), _ptr(backptr), _ptr(vit), streams[i]))
+                    launch_count += int(logs) + int(want_viterbi)
+                if flow:
+                    dst = post if want_post else (torch.empty(A, **f32) if have_cond else cond)
+                    _lib.check(lib.nfst_sell_flow_f32(packed.c_struct(), lc, cond.data_ptr(), _ptr(g32), dst.data_ptr(),
+                                                      None, None, None, _ptr(dtheta), _ptr(gfar), streams[i]))
+                    launch_count += 1
+                continue
             _lib.check(
                 lib.nfst_bwd_fused_f32(
                     packed.c_struct(), _launch(g, st), sc, _ptr(alpha), _ptr(logz), _ptr(g32), _ptr(beta),
@@ -235,12 +325,21 @@ def lattice_forward_backward(packed: PackedLattices, arc_scores=None, theta=None
     logz_bwd = torch.empty(B, dtype=st, device=dev)
     post = torch.empty(A, dtype=torch.float32, device=dev)
     dtheta = torch.zeros(V, dtype=torch.float32, device=dev) if want_dtheta else None
+    gfar = _gamma_far(packed)
     with torch.cuda.device(dev):
         streams = _GroupStreams(dev, len(packed.groups))
         for i, g in enumerate(packed.groups):
             lc = _launch(g, st)
             stream = streams[i]
-            if g.small_max_arcs > 0:
+            if g.sell:  # beta pass (cond written into post), then the flow pass in place; alpha by the CSR forward kernel
+                _lib.check(lib.nfst_sell_pull_f32(packed.c_struct(), lc, sc, beta.data_ptr(), logz_bwd.data_ptr(),
+                                                  post.data_ptr(), None, None, None, stream))
+                _lib.check(lib.nfst_sell_flow_f32(packed.c_struct(), lc, post.data_ptr(), None, post.data_ptr(),
+                                                  None, None, None, _ptr(dtheta), _ptr(gfar), stream))
+                _lib.check(lib.nfst_fwd_f32(packed.c_struct(), _launch_csr_forward(g, st), sc, alpha.data_ptr(),
+                                            logz.data_ptr(), stream))
+                launch_count += 3
+            elif g.small_max_arcs > 0:
                 _lib.check(lib.nfst_fwd_bwd_small_f32(packed.c_struct(), lc, sc, None, alpha.data_ptr(), logz.data_ptr(),
                                                       beta.data_ptr(), logz_bwd.data_ptr(), post.data_ptr(),
                                                       _ptr(dtheta), stream))
@@ -298,24 +397,26 @@ class LatticeLogPartition(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, arc_scores, theta, packed: PackedLattices, state_dtype="auto"):
-        alpha, logz = lattice_forward(packed, arc_scores, theta, state_dtype=state_dtype)
+        logz, alpha, cond = lattice_pull(packed, arc_scores, theta, state_dtype=state_dtype)
         ctx.packed = packed
-        ctx.save_for_backward(alpha, logz, arc_scores if arc_scores is not None else torch.empty(0),
-                              theta if theta is not None else torch.empty(0))
-        ctx.has = (arc_scores is not None, theta is not None)
+        none = torch.empty(0)
+        ctx.save_for_backward(alpha if alpha is not None else none, logz, cond if cond is not None else none,
+                              arc_scores if arc_scores is not None else none, theta if theta is not None else none)
+        ctx.has = (arc_scores is not None, theta is not None, alpha is not None, cond is not None)
         return logz
 
     @staticmethod
     def backward(ctx, grad_logz):
-        alpha, logz, a, t = ctx.saved_tensors
-        has_a, has_t = ctx.has
+        alpha, logz, cond, a, t = ctx.saved_tensors
+        has_a, has_t, has_alpha, has_cond = ctx.has
         need_a = has_a and ctx.needs_input_grad[0]
         need_t = has_t and ctx.needs_input_grad[1]
         if not (need_a or need_t):
             return None, None, None, None
         r = lattice_backward(
-            ctx.packed, a if has_a else None, t if has_t else None, alpha=alpha, logz=logz,
-            grad_logz=grad_logz.contiguous(), want_beta=False, want_post=need_a, want_dtheta=need_t,
+            ctx.packed, a if has_a else None, t if has_t else None, alpha=alpha if has_alpha else None, logz=logz,
+            cond=cond if has_cond else None, grad_logz=grad_logz.contiguous(), want_beta=False, want_post=need_a,
+            want_dtheta=need_t,
         )
         return (r.get("post") if need_a else None), (r.get("dtheta") if need_t else None), None, None
 
@@ -411,6 +512,8 @@ def lattice_beta_hat(packed: PackedLattices, label_proj: torch.Tensor, Wh: torch
     dev = packed.device
     if dev.type != "cuda":
         raise RuntimeError("nfst_b200 kernels need the packed lattices on a CUDA device (no CPU fallback)")
+    if packed.has_sell:
+        raise ValueError("the beta-hat recurrence reads CSR arcs: pack with sell=False")
     V, H = label_proj.shape
     if V != packed.vocab or tuple(Wh.shape) != (H, H) or W.numel() != H:
         raise ValueError("label_proj must be [vocab, H], Wh [H, H], W [H]")

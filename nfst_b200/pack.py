@@ -50,6 +50,14 @@ def small_footprint_bytes(states, arcs, levels, vocab):
     semirings, labels and a dtheta histogram; state / arc indices are 16-bit)."""
     return 4 * (6 * states + 2 * (levels + 1) + (states + 2) + 4 * arcs + min(vocab, 4096) + 64)
 DEGREE_SORT = int(os.environ.get("NFST_DEGREE_SORT", "1"))
+# Sliced-column execution (nfst_sell.cu): lattices whose levels average at least SELL_MIN_WIDTH states
+# (a warp's worth); their DP ring holds at most SELL_WINDOW_MAX states, longer arcs go through global memory
+SELL = int(os.environ.get("NFST_SELL", "1"))
+SELL_MIN_WIDTH = int(os.environ.get("NFST_SELL_MIN_WIDTH", "32"))
+SELL_WINDOW_MAX = int(os.environ.get("NFST_SELL_WINDOW_MAX", "16384"))
+SELL_WINDOW_QUANTILE = float(os.environ.get("NFST_SELL_WINDOW_QUANTILE", "0.995"))
+SELL_SLICES_PER_WARP = float(os.environ.get("NFST_SELL_SPW", "3"))
+SELL_THREADS = int(os.environ.get("NFST_SELL_THREADS", "0"))  # 0 = from the level width
 
 
 def chunk_geometry(block_threads: int):
@@ -82,6 +90,11 @@ class LaunchGroup:
     small_max_states: int = 0
     small_max_arcs: int = 0
     small_max_levels: int = 0
+    # sliced-column execution (nfst_sell.cu): one block per lattice, arcs column-major per 32-state slice
+    sell: bool = False
+    sell_window: int = 0  # states in the shared-memory DP ring (a power of two)
+    sell_far: bool = False  # some arc spans more than the ring: (end of dst's level - start of src's level) > window
+    csr_block_threads: int = 0  # sliced-column groups: block size their in-order (CSR by destination) chunks were cut for
 
     def to(self, device, non_blocking: bool = False) -> "LaunchGroup":
         mv = lambda t: None if t is None else t.to(device, non_blocking=non_blocking)  # noqa: E731
@@ -102,7 +115,7 @@ class PackedLattices:
         "state_off", "level_off", "level_ptr", "start_state", "sink_off", "sinks",
         "in_ptr", "src_in", "label_in", "in2out", "out_ptr", "dst_out", "label_out",
         "fwd_chunk_off", "fwd_chunks", "bwd_chunk_off", "bwd_chunks", "fwd_gather",
-        "fwd_chunk_level", "bwd_chunk_level", "bwd_order",
+        "fwd_chunk_level", "bwd_chunk_level", "bwd_order", "sell_desc", "sell_lvl_slice",
     )
 
     # arrays the kernels stage with 16-byte copies: kept zero-padded by PAD elements
@@ -143,6 +156,8 @@ class PackedLattices:
             setattr(self, f, kw[f])
         self.lanes_in_log2: torch.Tensor = kw["lanes_in_log2"]
         self.lanes_out_log2: torch.Tensor = kw["lanes_out_log2"]
+        self.out_deg8: torch.Tensor = kw["out_deg8"]  # uint8 [S] min(out-degree, 255)
+        self.src_out: torch.Tensor = kw["src_out"]  # int32 [A] source state of each canonical arc (host-side view)
         self.orig_state: torch.Tensor = kw["orig_state"]  # int32 [S] original local state id
         self.arc_origin: torch.Tensor = kw["arc_origin"]  # int64 [A] index into the caller's arc list / dense cells
         self.arc_off: torch.Tensor = kw["arc_off"]  # int32 [B+1] canonical arc range per lattice
@@ -159,8 +174,13 @@ class PackedLattices:
     def device(self) -> torch.device:
         return self.state_off.device
 
+    @property
+    def has_sell(self) -> bool:
+        return any(g.sell for g in self.groups)
+
     def tensors(self):
-        names = list(self._INT_FIELDS) + ["lanes_in_log2", "lanes_out_log2", "orig_state", "arc_origin", "arc_off", "n_levels"]
+        names = list(self._INT_FIELDS) + ["lanes_in_log2", "lanes_out_log2", "out_deg8", "src_out", "orig_state",
+                                          "arc_origin", "arc_off", "n_levels"]
         if self.static_scores is not None:
             names.append("static_scores")
         return names
@@ -199,6 +219,7 @@ class PackedLattices:
                 setattr(c, f, t.data_ptr())
             c.lanes_in_log2 = self.lanes_in_log2.data_ptr()
             c.lanes_out_log2 = self.lanes_out_log2.data_ptr()
+            c.out_deg8 = self.out_deg8.data_ptr()
             self._c = c
         return self._c
 
@@ -263,6 +284,15 @@ def _build_chunks(ptr, slot, level_first, lat_of_state, target, heavy_thr, n_lat
     return chunk_off, chunks.to(torch.int32).contiguous(), order.to(torch.int32).contiguous()
 
 
+def _sell_block_log2(states: torch.Tensor, levels: torch.Tensor) -> torch.Tensor:
+    """log2 of the warps per block of a sliced-column lattice: about SELL_SLICES_PER_WARP slices per warp
+    and level (tunable), 1..32 warps."""
+    if SELL_THREADS:
+        return torch.full_like(states, max(int(math.log2(max(SELL_THREADS // 32, 1))), 0))
+    slices = states.to(torch.float64) / torch.clamp(levels, min=1).to(torch.float64) / 32.0
+    return torch.clamp(torch.round(torch.log2(torch.clamp(slices / SELL_SLICES_PER_WARP, min=1.0))), 0, 5).to(torch.int64)
+
+
 def build_groups(stats, dev, chunk_info=None) -> List[LaunchGroup]:
     """Partition the batch into launches: lattices cut for the same block size share a
     launch; heaviest lattices first (longest-processing-time order).  Lattices with wide
@@ -270,12 +300,27 @@ def build_groups(stats, dev, chunk_info=None) -> List[LaunchGroup]:
     wide = (stats["width_arcs"] >= LEVEL_MODE_MIN_ARCS).to(torch.int64)
     foot = small_footprint_bytes(stats["states"], stats["arcs"], stats["levels"], int(stats["vocab"][0]))
     small = ((foot <= SMALL_SMEM_BYTES) & (stats["states"] < 65536) & (stats["arcs"] < 65536)).to(torch.int64) * (1 - wide)
-    gkey = (stats["block_class"] * 2 + wide) * 2 + small
+    sell = stats["sell"].to(torch.int64)
+    wide, small = wide * (1 - sell), small * (1 - sell)
+    # sliced-column lattices: one group per block size (a power of two of warps)
+    gkey = torch.where(sell > 0, (stats["sell_block"] * 2) * 2 + 4096, (stats["block_class"] * 2 + wide) * 2 + small)
     groups: List[LaunchGroup] = []
     B = int(gkey.numel())
     for key in sorted(set(gkey.tolist()), reverse=True):
         members = torch.nonzero(gkey == key).squeeze(1)
         members = members[torch.argsort(stats["arcs"][members], descending=True, stable=True)]
+        if key >= 4096:
+            groups.append(LaunchGroup(
+                ids=members.to(torch.int32).to(dev), n=int(members.numel()),
+                block_threads=32 << ((key - 4096) >> 2),
+                max_states=int(stats["states"][members].max()), max_reach=int(stats["reach"][members].max()),
+                n_arcs=int(stats["arcs"][members].sum()), n_levels=int(stats["levels"][members].max()),
+                chunk_cap=int(stats["chunk_cap"][members].max()),  # for the CSR forward kernel (exact alpha)
+                csr_block_threads=1 << int(stats["block_class"][members].max()),
+                sell=True, sell_window=int(stats["sell_window"][members].max()),
+                sell_far=bool((stats["sell_bound"][members] > int(stats["sell_window"][members].max())).any()),
+            ))
+            continue
         g = LaunchGroup(
             ids=members.to(torch.int32).to(dev),
             n=int(members.numel()),
@@ -331,6 +376,7 @@ def concat_packed(parts: List["PackedLattices"]) -> "PackedLattices":
     n_sink = [int(p.sinks.numel()) for p in parts]
     n_fc = [int(p.fwd_chunks.shape[0]) for p in parts]
     n_bc = [int(p.bwd_chunks.shape[0]) for p in parts]
+    n_sl = [int(p.sell_desc.shape[0]) for p in parts]
 
     def starts(counts):
         out, t = [], 0
@@ -339,17 +385,18 @@ def concat_packed(parts: List["PackedLattices"]) -> "PackedLattices":
             t += c
         return out, t
 
-    (oS, S), (oA, A), (oB, B), (oL, Lv), (oK, n_sinks), (oF, nfc), (oC, nbc) = (
-        starts(c) for c in (n_state, n_arc, n_lat, n_lvl, n_sink, n_fc, n_bc))
+    (oS, S), (oA, A), (oB, B), (oL, Lv), (oK, n_sinks), (oF, nfc), (oC, nbc), (oQ, nsl) = (
+        starts(c) for c in (n_state, n_arc, n_lat, n_lvl, n_sink, n_fc, n_bc, n_sl))
     if S >= 2**31 or A >= 2**31:
         raise ValueError("batch too large for int32 indices; shard it")
-    table = torch.tensor([oS, oA, oL, oK, oF, oC, n_state, n_arc, n_lat, n_lvl, n_sink, n_fc, n_bc],
+    table = torch.tensor([oS, oA, oL, oK, oF, oC, n_state, n_arc, n_lat, n_lvl, n_sink, n_fc, n_bc, oQ, n_sl],
                          dtype=torch.int64).to(dev, non_blocking=True)
     offS, offA, offL, offK, offF, offC = (table[i].to(torch.int32) for i in range(6))
     pid = torch.arange(P, device=dev)
     rep = lambda row, total: torch.repeat_interleave(pid, table[row], output_size=total)  # noqa: E731
-    by_state, by_arc, by_lat, by_lvl, by_sink, by_fc, by_bc = (
-        rep(6, S), rep(7, A), rep(8, B), rep(9, Lv), rep(10, n_sinks), rep(11, nfc), rep(12, nbc))
+    by_state, by_arc, by_lat, by_lvl, by_sink, by_fc, by_bc, by_sl = (
+        rep(6, S), rep(7, A), rep(8, B), rep(9, Lv), rep(10, n_sinks), rep(11, nfc), rep(12, nbc), rep(14, nsl))
+    offQ = table[13].to(torch.int32)
 
     def cat(name, cut=False):
         ts = [getattr(p, name) for p in parts]
@@ -381,6 +428,9 @@ def concat_packed(parts: List["PackedLattices"]) -> "PackedLattices":
         "bwd_chunk_level": cat("bwd_chunk_level"),
         "lanes_in_log2": cat("lanes_in_log2"),
         "lanes_out_log2": cat("lanes_out_log2"),
+        "out_deg8": cat("out_deg8"),
+        "sell_lvl_slice": cat("sell_lvl_slice") + offQ[by_lvl],
+        "src_out": cat("src_out") + offS[by_arc],
         "orig_state": cat("orig_state"),
         "arc_origin": cat("arc_origin"),
         "arc_off": closed("arc_off", by_lat, offA, A),
@@ -389,6 +439,8 @@ def concat_packed(parts: List["PackedLattices"]) -> "PackedLattices":
     for name, space, off_c in (("fwd_chunks", by_fc, offF), ("bwd_chunks", by_bc, offC)):
         shift = torch.stack([offA[space], offA[space], offS[space], offS[space]], dim=1)
         kw[name] = cat(name) + shift
+    sd = cat("sell_desc")
+    kw["sell_desc"] = sd + torch.stack([offA[by_sl], offA[by_sl], torch.zeros_like(offA[by_sl]), torch.zeros_like(offA[by_sl])], dim=1)
     fg = cat("fwd_gather")
     nonempty = (fg[:, 1] > fg[:, 0]).to(torch.int32).unsqueeze(1)  # empty chunks keep [0, 0)
     kw["fwd_gather"] = fg + offA[by_fc].unsqueeze(1) * nonempty
@@ -416,10 +468,12 @@ def pack_arcs(
     start_state: int = 0,
     static_scores: Optional[torch.Tensor] = None,
     dense_shape=None,
+    sell: Optional[bool] = None,
 ) -> PackedLattices:
     """Pack an arc list.  ``arc_lattice/src/dst/label`` are [A0] integer tensors (local
     state ids), ``n_states`` is [B].  Raises ``ValueError`` for cyclic lattices (the
-    reference's denominator / base machines, which it never feeds to the DP either)."""
+    reference's denominator / base machines, which it never feeds to the DP either).
+    ``sell``: allow the sliced-column layout for wide lattices (default: the NFST_SELL knob)."""
     dev = src.device
     n_states = n_states.to(device=dev, dtype=torch.int64)
     B = int(n_states.numel())
@@ -455,34 +509,68 @@ def pack_arcs(
         if it > max_iter + 8:
             raise ValueError("lattice is cyclic: the DP is defined for acyclic lattices only")
 
-    # ---- state renumbering: (lattice, level, original id) ----
+    # ---- state renumbering: (lattice, level, degree key, original id) ----
     lat_of_state = torch.repeat_interleave(torch.arange(B, device=dev), n_states)
     kept = torch.nonzero(level >= 0).squeeze(1)
     lv = level[kept]
     lt = lat_of_state[kept]
     lmax = int(lv.max()) + 1 if kept.numel() else 1
-    # inside a level states are ordered by (in-degree, out-degree): the 32 states a warp
-    # reduces then have (nearly) equal segment lengths in both passes
     live = level[gsrc] >= 0
     deg_in = torch.bincount(gdst[live], minlength=S0)[kept]
     deg_out = torch.bincount(gsrc[live], minlength=S0)[kept]
     dmax = int(max(deg_in.max(), deg_out.max())) + 1 if kept.numel() else 1
+    # level bookkeeping does not depend on the order inside a level
+    n_levels = torch.zeros(B, dtype=torch.int64, device=dev).scatter_reduce(0, lt, lv + 1, reduce="amax")
+    level_off = _excl_cumsum(n_levels + 1)
+    n_slots = int(level_off[-1])
+    slot_kept = level_off[lt] + lv
+    counts = torch.bincount(slot_kept, minlength=n_slots)
+    level_ptr = torch.cumsum(counts, 0) - counts  # exclusive; the spare slot of lattice b lands on state_off[b+1]
+    S_b0 = torch.bincount(lt, minlength=B)
+
+    # ---- sliced-column eligibility (nfst_sell.cu): wide levels, out-degree <= 255, bounded arc span ----
+    sell_lat = torch.zeros(B, dtype=torch.bool, device=dev)
+    sell_bound = torch.zeros(B, dtype=torch.int64, device=dev)
+    sell_win = torch.full((B,), 32, dtype=torch.int64, device=dev)
+    if (SELL if sell is None else sell) and kept.numel():
+        slot_of = torch.full((S0,), 0, dtype=torch.int64, device=dev)
+        slot_of[kept] = slot_kept
+        # arcs into the LAST level need no ring: its states are final (beta = 0, delta = 0), the kernels
+        # know them by their id
+        inner = live & (level[gdst] < n_levels[arc_lattice] - 1)
+        la = arc_lattice[inner]
+        span = (level_ptr[slot_of[gdst[inner]]] + counts[slot_of[gdst[inner]]]) - level_ptr[slot_of[gsrc[inner]]]
+        sell_bound = sell_bound.scatter_reduce(0, la, span, reduce="amax")
+        sell_lat = S_b0 >= SELL_MIN_WIDTH * n_levels
+        # ring size: covers SELL_WINDOW_QUANTILE of the lattice's arcs (log2 histogram of the spans); the few
+        # longer ones -- e.g. dead ends wired to the sink -- go through global memory
+        lgs = torch.ceil(torch.log2(span.to(torch.float64))).to(torch.int64).clamp_(0, 31)
+        cum = torch.cumsum(torch.bincount(la * 32 + lgs, minlength=B * 32).view(B, 32), 1)
+        need = torch.ceil(cum[:, -1:].to(torch.float64) * SELL_WINDOW_QUANTILE).to(torch.int64)
+        sell_win = torch.clamp(torch.ones(B, dtype=torch.int64, device=dev) << (cum < need).sum(1), 32, SELL_WINDOW_MAX)
+        # ... and a whole level: two states of one level must never share a ring slot
+        slot_lat0 = torch.repeat_interleave(torch.arange(B, device=dev), n_levels + 1)
+        lvl_width = torch.zeros(B, dtype=torch.int64, device=dev).scatter_reduce(0, slot_lat0, counts, reduce="amax")
+        pow2_width = torch.ones(B, dtype=torch.int64, device=dev) << torch.ceil(
+            torch.log2(torch.clamp(lvl_width, min=1).to(torch.float64))).to(torch.int64)
+        sell_win = torch.maximum(sell_win, pow2_width)
+        sell_lat = sell_lat & (sell_win <= SELL_WINDOW_MAX)
+    # inside a level states are ordered by (in-degree, out-degree): the 32 states a warp reduces then
+    # have (nearly) equal segment lengths in both passes; sliced-column lattices by out-degree,
+    # descending, so that the states of a slice that own a k-th arc are a prefix of the slice
     if DEGREE_SORT and lmax * dmax * dmax < 2**62 // max(B, 1):
-        order = torch.argsort(((lt * lmax + lv) * dmax + deg_in) * dmax + deg_out, stable=True)
+        dkey = torch.where(sell_lat[lt], (dmax - 1 - deg_out) * dmax, deg_in * dmax + deg_out)
+        order = torch.argsort((lt * lmax + lv) * dmax * dmax + dkey, stable=True)
     else:  # pathological degrees: fall back to level order only
+        sell_lat = torch.zeros_like(sell_lat)
         order = torch.argsort(lt * lmax + lv, stable=True)
     kept_sorted = kept[order]
     lt_s, lv_s = lt[order], lv[order]
     S = int(kept_sorted.numel())
     new_id = torch.full((S0,), -1, dtype=torch.int64, device=dev)
     new_id[kept_sorted] = torch.arange(S, device=dev)
-    state_off = _excl_cumsum(torch.bincount(lt_s, minlength=B))
-    n_levels = torch.zeros(B, dtype=torch.int64, device=dev).scatter_reduce(0, lt_s, lv_s + 1, reduce="amax")
-    level_off = _excl_cumsum(n_levels + 1)
-    n_slots = int(level_off[-1])
+    state_off = _excl_cumsum(S_b0)
     slot = level_off[lt_s] + lv_s
-    counts = torch.bincount(slot, minlength=n_slots)
-    level_ptr = torch.cumsum(counts, 0) - counts  # exclusive; the spare slot of lattice b lands on state_off[b+1]
     orig_state = kept_sorted - so[lt_s]
     start_packed = new_id[so[:-1] + start_state]
 
@@ -494,6 +582,21 @@ def pack_arcs(
     A = int(src_out.numel())
     out_deg = torch.bincount(src_out, minlength=S)
     out_ptr = _excl_cumsum(out_deg)
+    if bool(sell_lat.any()) and A:
+        # column-major inside every 32-state slice: key (first arc of the slice, k, lane)
+        pos = torch.arange(A, device=dev)
+        k_in_state = pos - out_ptr[src_out]
+        rel = src_out - level_ptr[slot[src_out]]
+        lane = rel % 32
+        is_sell = sell_lat[lt_s[src_out]]
+        zero = torch.zeros_like(pos)
+        kmul = int(k_in_state[is_sell].max()) + 1 if bool(is_sell.any()) else 1
+        if A * kmul * 32 >= 2**62:
+            raise ValueError("batch too large to sort into slices; shard it")
+        key = (torch.where(is_sell, out_ptr[src_out - lane], pos) * kmul + torch.where(is_sell, k_in_state, zero)) * 32 \
+            + torch.where(is_sell, lane, zero)
+        perm2 = torch.argsort(key, stable=True)
+        src_out, dst_out, label_out, origin = src_out[perm2], dst_out[perm2], label_out[perm2], origin[perm2]
     in2out = torch.argsort(dst_out, stable=True)
     src_in, label_in = src_out[in2out], label_out[in2out]
     in_ptr = _excl_cumsum(torch.bincount(dst_out, minlength=S))
@@ -501,6 +604,28 @@ def pack_arcs(
     sink_lat = torch.searchsorted(state_off, sinks, right=True) - 1
     sink_off = _excl_cumsum(torch.bincount(sink_lat, minlength=B))
     arc_off = out_ptr[state_off]
+
+    # ---- slice descriptors of the sliced-column lattices (nfst_packed_lattices_t.sell_desc) ----
+    sell_slot = torch.repeat_interleave(sell_lat, n_levels + 1)
+    nsl_slot = torch.where(sell_slot, (counts + 31) // 32, torch.zeros_like(counts))
+    slice_start = _excl_cumsum(nsl_slot)
+    NS = int(slice_start[-1])
+    sell_lvl_slice = slice_start[:-1]
+    sell_desc = torch.zeros((NS, 4), dtype=torch.int64, device=dev)
+    if NS:
+        st_ids = torch.nonzero(sell_lat[lt_s]).squeeze(1)
+        sid = slice_start[slot[st_ids]] + (st_ids - level_ptr[slot[st_ids]]) // 32
+        first = torch.full((NS,), S, dtype=torch.int64, device=dev).scatter_reduce(0, sid, st_ids, reduce="amin")
+        cnt = torch.bincount(sid, minlength=NS)
+        dg = out_deg[st_ids]
+        n_k = torch.stack([torch.bincount(sid[dg > k], minlength=NS) for k in range(7)], dim=1)
+        cs = torch.cumsum(n_k, 1)  # start of column 1..7 (<= 224)
+        dmax8 = torch.clamp(torch.zeros(NS, dtype=torch.int64, device=dev).scatter_reduce(0, sid, dg, reduce="amax"), max=255)
+        sell_desc[:, 0] = out_ptr[first]
+        sell_desc[:, 1] = out_ptr[first + cnt]
+        sell_desc[:, 2] = cs[:, 0] | (cs[:, 1] << 8) | (cs[:, 2] << 16) | (cs[:, 3] << 24)
+        sell_desc[:, 3] = cs[:, 4] | (cs[:, 5] << 8) | (cs[:, 6] << 16) | (dmax8 << 24)
+        sell_desc = torch.where(sell_desc >= 2**31, sell_desc - 2**32, sell_desc)  # bit pattern as int32
 
     # ---- per-lattice shape statistics -> lanes per state, block size, launch groups ----
     A_b = (arc_off[1:] - arc_off[:-1]).to(torch.float64)
@@ -561,6 +686,10 @@ def pack_arcs(
         "vocab": torch.full((B,), int(vocab), dtype=torch.int64),
         "chunk_cap": geo[block_class, 2].cpu(),
         "reach": reach.cpu(),
+        "sell": sell_lat.cpu(),
+        "sell_bound": sell_bound.cpu(),
+        "sell_window": sell_win.cpu(),
+        "sell_block": _sell_block_log2(S_b.cpu(), n_levels.cpu()),
     }
     groups = build_groups(stats, dev, {"fwd": (fwd_chunk_off, fwd_chunks, fwd_chunk_level),
                                        "bwd": (bwd_chunk_off, bwd_chunks, bwd_chunk_level)})
@@ -573,8 +702,9 @@ def pack_arcs(
         in2out=i32(in2out), out_ptr=i32(out_ptr), dst_out=i32(dst_out), label_out=i32(label_out),
         fwd_chunk_off=i32(fwd_chunk_off), fwd_chunks=fwd_chunks, bwd_chunk_off=i32(bwd_chunk_off), bwd_chunks=bwd_chunks,
         fwd_gather=i32(fwd_gather), fwd_chunk_level=i32(fwd_chunk_level), bwd_chunk_level=i32(bwd_chunk_level),
-        bwd_order=bwd_order,
+        bwd_order=bwd_order, sell_desc=i32(sell_desc), sell_lvl_slice=i32(sell_lvl_slice),
         lanes_in_log2=lg_in.to(torch.uint8).contiguous(), lanes_out_log2=lg_out.to(torch.uint8).contiguous(),
+        out_deg8=torch.clamp(out_deg, max=255).to(torch.uint8).contiguous(), src_out=i32(src_out),
         orig_state=i32(orig_state), arc_origin=origin.contiguous(), arc_off=i32(arc_off), n_levels=i32(n_levels),
         static_scores=None if static_scores is None else static_scores[origin].to(torch.float32).contiguous(),
         dense_shape=dense_shape, groups=groups, max_levels=int(n_levels.max()) if B else 0, stats=stats,
