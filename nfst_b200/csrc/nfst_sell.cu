@@ -10,14 +10,16 @@
 // memory into registers: no shared-memory staging, no row pointers (one base offset per slice
 // and one degree byte per state), ~10 thread-instructions per arc.
 //
-// A thread block owns one lattice and walks its levels with one barrier per level.  None of the
-// index / score loads depends on a DP value, so every warp runs ahead of the barriers over its
-// static list of slices: degree bytes and slice bounds are loaded two slices ahead, the arc
-// columns of the next slice are pulled into L2 (prefetch.global.L2, no registers held), and the
-// current slice's columns are then loaded together -- one L2 latency per slice, HBM latency
-// hidden.  (Holding the next slice's columns in registers instead costs 32 registers: at 64
-// registers per thread ptxas spills them, and a spilled load result stalls on its own load.)
-// The only data that crosses levels, the per-state DP value, lives in a shared-memory ring.
+// A thread block owns one lattice and walks its levels with one barrier per level; a warp takes
+// every nw-th slice of a level.  Per slice: one 16-byte descriptor (arc range, column starts,
+// largest degree -- loaded one slice ahead), one degree byte per lane, then all columns of the
+// register window are loaded together, branch-free.  At 64 registers eight 128-thread blocks fit
+// an SM, so 1024 lattices run in ONE wave and the other warps of a scheduler cover the exposed
+// load latency; the kernels are bound by instruction issue, which is why the hot path carries no
+// warp votes, no per-column branches and no prefetch code (measured: register double buffering
+// spilled, and a spilled load result stalls on its own load; L2 prefetch cost ~120 instructions
+// per slice).  The only data that crosses levels, the per-state DP value, lives in a
+// shared-memory ring.
 //
 //   pull pass (deepest level first): beta[s] = logsumexp_k (w_k + beta[dst_k]) in float64
 //       (exp in fp32), and the arc's conditional probability cond[a] = exp(w + beta[dst] - beta[s])
@@ -135,14 +137,6 @@ __device__ __forceinline__ void for_columns(const int4& d, int deg, int lane, F&
     for_columns<K + 1>(d, deg, lane, f);
   }
 }
-// pull the arcs [b0, b1) of a per-arc array into L2: lane j touches the j-th 128-byte line
-__device__ __forceinline__ void prefetch_arcs(const void* arr, int b0, int b1, int lane) {
-  if (b1 <= b0) return;
-  const char* first = reinterpret_cast<const char*>((reinterpret_cast<uintptr_t>(arr) + 4ull * b0) & ~uintptr_t(127));
-  const char* last = reinterpret_cast<const char*>(arr) + 4ull * (b1 - 1);
-  for (const char* q = first + 128 * lane; q <= last; q += 4096) asm volatile("prefetch.global.L2 [%0];" ::"l"(q));
-}
-
 // rare path: an arc longer than the shared-memory ring (kept out of line: no 64-bit address arithmetic in
 // the hot loops).  The value was written by this block before an earlier level barrier.
 #ifdef SELL_FAR_INLINE
@@ -278,14 +272,16 @@ __global__ void __launch_bounds__(NT_MAX, NT_MAX == 256 ? 4 : 1)
                                               : fill;
   };
 
-  // ---- pipeline state: slice being computed, the next one (prefetched into L2), the one after (descriptor loading)
-  Pos pc, pn, pa;
+  // ---- pipeline state: the slice being computed and the next one (descriptor + degree byte in flight).
+  // The arc columns themselves are not prefetched: with 8 warps per scheduler the kernel is bound by
+  // instruction issue, the other warps cover a slice's one exposed load latency, and every prefetch
+  // scheme tried (register double buffering, L2 prefetch) cost more instructions than it saved.
+  Pos pc, pn;
   pc.l = n_levels - 1; pc.j = warp - nw; pc.ok = false;
   advance<true>(pc, lsl, n_levels, warp, nw);
   pn = pc;
   if (pn.ok) advance<true>(pn, lsl, n_levels, warp, nw);
   StA ac = load_a(pc, lvl, lsl, lane, deg8, desc);
-  StA an = load_a(pn, lvl, lsl, lane, deg8, desc);
   const int lim_cap = last0;  // ring reads need dst < min(lim, last0)
 
 #pragma unroll 1
@@ -296,30 +292,21 @@ __global__ void __launch_bounds__(NT_MAX, NT_MAX == 256 ? 4 : 1)
     }
 #pragma unroll 1
     while (pc.ok && pc.l == l) {
-      // descriptor of the slice after next; arcs of the next slice into L2
-      pa = pn;
-      if (pa.ok) advance<true>(pa, lsl, n_levels, warp, nw);
-      const StA aa = load_a(pa, lvl, lsl, lane, deg8, desc);
-      if (pn.ok) {
-        prefetch_arcs(dst_out, an.d.x, an.d.y, lane);
-        if (SC) prefetch_arcs(arc_scores, an.d.x, an.d.y, lane);
-        if (TH) prefetch_arcs(label_out, an.d.x, an.d.y, lane);
-      }
+      const StA an = load_a(pn, lvl, lsl, lane, deg8, desc);  // consumed in the next iteration
 
       // ---- the current slice's register window: all loads first ----
       const int deg = slice_degree(ac, L.out_ptr), s = ac.s;
       const int dmax = slice_dmax8(ac.d);  // 255 = "255 or more"
       int dstc[KU];
       float wc[KU];
+      // branch-free: lanes without a k-th arc re-read the slice's first arc (a valid, cached address) and
+      // ignore the value -- cheaper than a reconvergence point per column
       for_columns<0>(ac.d, deg, lane, [&](auto kc, bool on, int a) {
         constexpr int k = decltype(kc)::value;
-        dstc[k] = 0;
-        wc[k] = 0.0f;
-        if (on) {
-          dstc[k] = __ldg(dst_out + a);
-          if (SC) wc[k] = __ldg(arc_scores + a);
-          if (TH) wc[k] += th[__ldg(label_out + a)];
-        }
+        const int aa = on ? a : ac.d.x;
+        dstc[k] = __ldg(dst_out + aa);
+        wc[k] = SC ? __ldg(arc_scores + aa) : 0.0f;
+        if (TH) wc[k] += th[__ldg(label_out + aa)];
       });
       // destinations' DP values: from the ring, straight-line; the rare ones beyond it are patched afterwards
       RingT rv[KU];
@@ -504,9 +491,8 @@ __global__ void __launch_bounds__(NT_MAX, NT_MAX == 256 ? 4 : 1)
 
       // ---- rotate the pipeline ----
       pc = pn;
-      pn = pa;
+      if (pn.ok) advance<true>(pn, lsl, n_levels, warp, nw);
       ac = an;
-      an = aa;
     }
     __syncthreads();
   }
@@ -568,13 +554,12 @@ __global__ void __launch_bounds__(NT_MAX, NT_MAX == 256 ? 4 : 1)
   };
   const bool read_far = far || ALPHA;
 
-  Pos pc, pn, pa;
+  Pos pc, pn;
   pc.l = 0; pc.j = warp - nw; pc.ok = false;
   advance<false>(pc, lsl, n_levels, warp, nw);
   pn = pc;
   if (pn.ok) advance<false>(pn, lsl, n_levels, warp, nw);
   StA ac = load_a(pc, lvl, lsl, lane, deg8, desc);
-  StA an = load_a(pn, lvl, lsl, lane, deg8, desc);
 
 #pragma unroll 1
   for (int l = 0; l < n_levels; ++l) {
@@ -582,29 +567,18 @@ __global__ void __launch_bounds__(NT_MAX, NT_MAX == 256 ? 4 : 1)
     const int lim2 = min(lim, last0);  // ring pushes need dst < lim2
 #pragma unroll 1
     while (pc.ok && pc.l == l) {
-      pa = pn;
-      if (pa.ok) advance<false>(pa, lsl, n_levels, warp, nw);
-      const StA aa = load_a(pa, lvl, lsl, lane, deg8, desc);
-      if (pn.ok) {
-        prefetch_arcs(dst_out, an.d.x, an.d.y, lane);
-        prefetch_arcs(cond, an.d.x, an.d.y, lane);
-        if (DTH) prefetch_arcs(label_out, an.d.x, an.d.y, lane);
-      }
+      const StA an = load_a(pn, lvl, lsl, lane, deg8, desc);  // consumed in the next iteration
 
       const int deg = slice_degree(ac, L.out_ptr), s = ac.s;
       const int dmax = slice_dmax8(ac.d);
       int dstc[KU], labc[KU];
       float cc[KU];
-      for_columns<0>(ac.d, deg, lane, [&](auto kc, bool on, int a) {
+      for_columns<0>(ac.d, deg, lane, [&](auto kc, bool on, int a) {  // branch-free, see the pull pass
         constexpr int k = decltype(kc)::value;
-        dstc[k] = 0;
-        cc[k] = 0.0f;
-        labc[k] = 0;
-        if (on) {
-          dstc[k] = __ldg(dst_out + a);
-          cc[k] = cond[a];
-          if (DTH) labc[k] = __ldg(label_out + a);
-        }
+        const int aa = on ? a : ac.d.x;
+        dstc[k] = __ldg(dst_out + aa);
+        cc[k] = cond[aa];
+        labc[k] = DTH ? __ldg(label_out + aa) : 0;
       });
       float gs = 0.0f;
       if (s != 0x7fffffff) {
@@ -677,9 +651,8 @@ __global__ void __launch_bounds__(NT_MAX, NT_MAX == 256 ? 4 : 1)
       }
 
       pc = pn;
-      pn = pa;
+      if (pn.ok) advance<false>(pn, lsl, n_levels, warp, nw);
       ac = an;
-      an = aa;
     }
     __syncthreads();
   }

@@ -10,7 +10,7 @@ import nfst_b200 as nb
 from nfst_b200 import synth
 from nfst_b200.pack import concat_packed
 from oracle import c_oracle
-from tests.test_gpu_parity import DEV, check_fwd_bwd, gpu_state_to_orig, oracle_batch
+from tests.test_gpu_parity import DEV, check_fwd_bwd, gpu_state_to_orig, oracle_batch, post_rtol
 
 pytestmark = pytest.mark.gpu
 
@@ -118,11 +118,13 @@ def test_sell_mixed_batch_and_lattice_backward_outputs():
     off_a = 0
     off_b = 0
     for ab, pk in zip(parts, packs):
-        o_logz, _, o_beta, o_post = c_oracle.forward_backward(oracle_batch(ab))
+        o_logz, o_alpha, o_beta, o_post = c_oracle.forward_backward(oracle_batch(ab))
         np.testing.assert_allclose(logz[off_b:off_b + pk.n_lattices].cpu().numpy(), o_logz, rtol=1e-5)
         ref = o_post[pk.arc_origin.cpu().numpy()]
         got = post[off_a:off_a + pk.n_arcs].cpu().numpy().astype(np.float64)
-        assert np.all(np.abs(got - ref) <= 1e-5 * ref + 1e-7)
+        # sliced-column part: 1e-5 flat; the fp32 CSR kernels: depth-scaled (tests/test_gpu_parity.py)
+        rt = 1e-5 if pk.has_sell else post_rtol(float(np.abs(o_alpha).max() + np.abs(o_beta).max()))
+        assert np.all(np.abs(got - ref) <= rt * ref + 1e-7)
         off_a += pk.n_arcs
         off_b += pk.n_lattices
     # separate calls: forward (alpha, logZ) and the fused backward with every output
