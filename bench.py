@@ -2,14 +2,15 @@
 """bench.py -- arcs/sec of log-semiring forward-backward on synthetic lattices.
 
 Contract: `python bench.py --gpus N --steps K --warmup W` (N>1 under torchrun) prints ONE
-JSON line on rank 0.  A "step" is one pass of the hot path (forward kernel + fused backward
-kernel emitting beta and arc posteriors) over one batch of synthetic lattices.
+JSON line on rank 0.  A "step" is one pass of the hot path over one batch of synthetic lattices:
+logZ + beta (first kernel) and the arc posteriors (second kernel) -- the sliced-column pull / flow
+kernels for wide lattices, the CSR forward / fused-backward kernels otherwise.
 
   value      whole-job arcs/s, inputs resident in HBM, CUDA-event timed, max over ranks
   e2e        same metric through the public API with HOST (pinned) buffers: per step the
              packed batch + scores are copied H2D, logZ[B] is read back D2H
-  roofline   dominant kernel (fused backward): algorithmic bytes (12 B/arc + 12 B/state,
-             SURVEY.md 8d) / its mean CUDA-event duration, vs MEASURED_PEAKS.json hbm_gbs
+  roofline   dominant kernel of the step: its algorithmic bytes (DESIGN.md section 4 / SURVEY.md 8d)
+             / its mean CUDA-event duration, vs MEASURED_PEAKS.json hbm_gbs
   cpu_baseline  oracle/lattice_oracle.c (a C port of the reference recurrence) on the
              host cores, bounded sample of the same workload
 
@@ -326,7 +327,8 @@ def main():
     e2e = None
     if not a.no_e2e:
         if all_sell:  # the sliced-column kernels read nothing else (no in-order arrays, no chunk lists)
-            fields = ("state_off", "start_state", "level_off", "level_ptr", "out_ptr", "dst_out", "out_deg8")
+            fields = ("state_off", "start_state", "level_off", "level_ptr", "out_ptr", "dst_out", "out_deg8",
+                      "sell_desc", "sell_lvl_slice")
         else:
             fields = ("state_off", "start_state", "sink_off", "sinks", "in_ptr", "src_in", "in2out", "out_ptr", "dst_out",
                       "lanes_in_log2", "lanes_out_log2", "fwd_chunk_off", "fwd_chunks", "bwd_chunk_off", "bwd_chunks",
@@ -363,7 +365,10 @@ def main():
             groups = [dataclasses.replace(g, ids=d_) for g, d_ in zip(packed.groups, land_ids)]
             p = PackedLattices(n_lattices=B, n_states=S, n_arcs=A, vocab=packed.vocab, static_scores=None,
                                dense_shape=None, groups=groups, max_levels=packed.max_levels, stats=packed.stats, **kw)
-            logz, alpha, beta, post = nb.lattice_forward_backward(p, arc_scores=land_scores)
+            # the training-step surface: logZ (first pass), arc posteriors (second pass)
+            logz, alpha, cond = ops.lattice_pull(p, arc_scores=land_scores)
+            nb.lattice_backward(p, arc_scores=land_scores, alpha=alpha, logz=logz, cond=cond, want_beta=not all_sell,
+                                want_post=True)
             logz_host.copy_(logz, non_blocking=True)
             torch.cuda.current_stream().synchronize()
             return float(logz_host[0])

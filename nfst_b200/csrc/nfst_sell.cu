@@ -111,12 +111,15 @@ __device__ __forceinline__ StA load_a(const Pos& p, const int* lvl, const int* l
   a.degb = 0;
   a.d = make_int4(0, 0, 0, 0);
   if (p.ok) {
-    const int first = lvl[p.l] + 32 * p.j;
+    // p.j counts from the END of the level: degrees descend along a level, so the warp that gets one slice
+    // more than the others (warp 0) gets the lightest ones
+    const int jj = lsl[p.l + 1] - lsl[p.l] - 1 - p.j;
+    const int first = lvl[p.l] + 32 * jj;
     if (first + lane < lvl[p.l + 1]) {
       a.s = first + lane;
       a.degb = __ldg(deg8 + a.s);
     }
-    a.d = __ldg(desc + lsl[p.l] + p.j);
+    a.d = __ldg(desc + lsl[p.l] + jj);
   }
   return a;
 }
@@ -571,6 +574,10 @@ __global__ void __launch_bounds__(NT_MAX, NT_MAX == 256 ? 4 : 1)
 
       const int deg = slice_degree(ac, L.out_ptr), s = ac.s;
       const int dmax = slice_dmax8(ac.d);
+      // flow that reached s through global memory (complete: earlier levels are done); issued with the
+      // column loads so that it costs no latency of its own
+      float g_far = 0.0f;
+      if (read_far && s != 0x7fffffff) g_far = *reinterpret_cast<volatile float*>(gamma_far + s);
       int dstc[KU], labc[KU];
       float cc[KU];
       for_columns<0>(ac.d, deg, lane, [&](auto kc, bool on, int a) {  // branch-free, see the pull pass
@@ -583,9 +590,8 @@ __global__ void __launch_bounds__(NT_MAX, NT_MAX == 256 ? 4 : 1)
       float gs = 0.0f;
       if (s != 0x7fffffff) {
         // every arc into s comes from a shallower level: gamma[s] is final; free the slot
-        gs = ring[s & mask];
+        gs = ring[s & mask] + g_far;
         ring[s & mask] = 0.0f;
-        if (read_far) gs += *reinterpret_cast<volatile float*>(gamma_far + s);  // complete: earlier levels are done
         if (ALPHA) {
           const float r = gs * inv_g;
           alpha[s] = r > 0.0f ? static_cast<OT>(static_cast<double>(lg2_approx(r) * kLn2) + lz -

@@ -50,14 +50,17 @@ def small_footprint_bytes(states, arcs, levels, vocab):
     semirings, labels and a dtheta histogram; state / arc indices are 16-bit)."""
     return 4 * (6 * states + 2 * (levels + 1) + (states + 2) + 4 * arcs + min(vocab, 4096) + 64)
 DEGREE_SORT = int(os.environ.get("NFST_DEGREE_SORT", "1"))
-# Sliced-column execution (nfst_sell.cu): lattices whose levels average at least SELL_MIN_WIDTH states
-# (a warp's worth); their DP ring holds at most SELL_WINDOW_MAX states, longer arcs go through global memory
+# Sliced-column execution (nfst_sell.cu): lattices whose levels average at least SELL_MIN_WIDTH states and
+# whose DP ring (SELL_WINDOW_QUANTILE of the arc spans, and the widest level) fits SELL_WINDOW_MAX states; the
+# few longer arcs go through global memory.  Measured on B200 against the CSR kernels (config 4, B = 1024,
+# fwd+bwd): narrower lattices are latency-bound and the CSR kernels' cp.async staging wins (10k arcs: 0.49 vs
+# 0.26 ms, 30k: 1.03 vs 0.55 ms); from ~250 states per level the sliced columns win (100k: 1.29 vs 1.42 ms,
+# 300k: 4.10 vs 5.12 ms); lattices whose ring would not fit stay CSR (1M arcs per lattice).
 SELL = int(os.environ.get("NFST_SELL", "1"))
-SELL_MIN_WIDTH = int(os.environ.get("NFST_SELL_MIN_WIDTH", "32"))
+SELL_MIN_WIDTH = int(os.environ.get("NFST_SELL_MIN_WIDTH", "256"))
 SELL_WINDOW_MAX = int(os.environ.get("NFST_SELL_WINDOW_MAX", "16384"))
 SELL_WINDOW_QUANTILE = float(os.environ.get("NFST_SELL_WINDOW_QUANTILE", "0.995"))
-SELL_SLICES_PER_WARP = float(os.environ.get("NFST_SELL_SPW", "3"))
-SELL_THREADS = int(os.environ.get("NFST_SELL_THREADS", "0"))  # 0 = from the level width
+SELL_THREADS = int(os.environ.get("NFST_SELL_THREADS", "0"))  # 0 = from the level width (128, or 256 from 1024 states per level)
 
 
 def chunk_geometry(block_threads: int):
@@ -285,12 +288,12 @@ def _build_chunks(ptr, slot, level_first, lat_of_state, target, heavy_thr, n_lat
 
 
 def _sell_block_log2(states: torch.Tensor, levels: torch.Tensor) -> torch.Tensor:
-    """log2 of the warps per block of a sliced-column lattice: about SELL_SLICES_PER_WARP slices per warp
-    and level (tunable), 1..32 warps."""
+    """log2 of the warps per block of a sliced-column lattice: 4 warps, 8 from 1024 states per level
+    (measured: 128 threads best at 400 states per level, 256 at 1200)."""
     if SELL_THREADS:
         return torch.full_like(states, max(int(math.log2(max(SELL_THREADS // 32, 1))), 0))
-    slices = states.to(torch.float64) / torch.clamp(levels, min=1).to(torch.float64) / 32.0
-    return torch.clamp(torch.round(torch.log2(torch.clamp(slices / SELL_SLICES_PER_WARP, min=1.0))), 0, 5).to(torch.int64)
+    width = states.to(torch.float64) / torch.clamp(levels, min=1).to(torch.float64)
+    return torch.where(width >= 1024, torch.full_like(states, 3), torch.full_like(states, 2))
 
 
 def build_groups(stats, dev, chunk_info=None) -> List[LaunchGroup]:
@@ -547,7 +550,7 @@ def pack_arcs(
         lgs = torch.ceil(torch.log2(span.to(torch.float64))).to(torch.int64).clamp_(0, 31)
         cum = torch.cumsum(torch.bincount(la * 32 + lgs, minlength=B * 32).view(B, 32), 1)
         need = torch.ceil(cum[:, -1:].to(torch.float64) * SELL_WINDOW_QUANTILE).to(torch.int64)
-        sell_win = torch.clamp(torch.ones(B, dtype=torch.int64, device=dev) << (cum < need).sum(1), 32, SELL_WINDOW_MAX)
+        sell_win = torch.clamp(torch.ones(B, dtype=torch.int64, device=dev) << (cum < need).sum(1), min=32)
         # ... and a whole level: two states of one level must never share a ring slot
         slot_lat0 = torch.repeat_interleave(torch.arange(B, device=dev), n_levels + 1)
         lvl_width = torch.zeros(B, dtype=torch.int64, device=dev).scatter_reduce(0, slot_lat0, counts, reduce="amax")

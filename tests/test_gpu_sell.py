@@ -15,6 +15,13 @@ from tests.test_gpu_parity import DEV, check_fwd_bwd, gpu_state_to_orig, oracle_
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(autouse=True)
+def narrow_lattices_too(monkeypatch):
+    """The packer only sends lattices of >= 256 states per level down the sliced-column path (below that the
+    CSR kernels are faster); the tests want small lattices there too."""
+    monkeypatch.setattr(nb.pack, "SELL_MIN_WIDTH", 32)
+
+
 def viterbi_matches(ab, p, sc):
     score, off, arcs, labels = nb.lattice_viterbi(p, arc_scores=sc)
     o_score, o_paths, o_labels = c_oracle.viterbi(oracle_batch(ab))
@@ -25,7 +32,7 @@ def viterbi_matches(ab, p, sc):
         np.testing.assert_array_equal(lab[offc[b]:offc[b + 1]], o_labels[b])
 
 
-@pytest.mark.parametrize("arcs,levels,B", [(3_000, 8, 5), (10_000, 64, 6), (100_000, 64, 4), (400_000, 32, 2)])
+@pytest.mark.parametrize("arcs,levels,B", [(3_000, 8, 5), (10_000, 64, 6), (100_000, 64, 4), (400_000, 64, 2)])
 def test_sell_forward_backward_and_viterbi(arcs, levels, B):
     ab = synth.random_dag_batch(B, arcs, levels=levels, seed=7)
     # strict: sums and differences run in float64 inside the kernel, 1e-5 holds without depth scaling
