@@ -23,6 +23,12 @@
  *                           src/decode/decoder.py:77-79.
  *   nfst_beta_hat_level_f32 the same recurrence with Wh != 0 (the beta-hat messages,
  *                           scorers.py:732-747), one topological level per call.
+ *   nfst_walk_step_f32      one time step of Sampler.stateful_sample (src/modules/samplers.py:243-297):
+ *                           update_fsa_state (scorers.py:683-690), mask_out_invalid (:1037-1054), the
+ *                           beta look-ahead (:583-592) and the Categorical sample / log_prob, fused.
+ *   nfst_sell_pull_f32 / nfst_sell_flow_f32
+ *                           the beta recurrence and the arc posteriors for wide lattices stored as
+ *                           column-major 32-state slices (same reference functions as nfst_bwd_fused_f32).
  *   nfst_beta_to_dense      layout of compute_beta()'s return value, real-space
  *                           beta[B*k, S] (scorers.py:854, :858-875).
  *   nfst_dense_count_arcs / nfst_dense_extract_arcs
@@ -281,6 +287,37 @@ int nfst_sell_pull_f32(const nfst_packed_lattices_t* lat, const nfst_launch_t* l
 int nfst_sell_flow_f32(const nfst_packed_lattices_t* lat, const nfst_launch_t* launch, const float* cond,
                        const float* grad_logz, float* post, const void* beta, const void* logz, void* alpha,
                        float* dtheta, float* gamma_far, void* cuda_stream);
+
+/*
+ * One time step of the lattice-constrained sampling / scoring loop (Sampler.stateful_sample,
+ * src/modules/samplers.py:243-297) for n_rows = B * rows_per_lattice rows; replaces, in one launch over the
+ * out-arcs of each row's current state, the dense-row gathers of FSAGRUScorer.update_fsa_state
+ * (scorers.py:683-690) and mask_out_invalid (:1037-1054), the beta look-ahead of
+ * GRUScorer.actual_left_to_right_score (:583-592), pad_masking (:182-187) and the Categorical
+ * log_prob / sample / logsumexp of the loop body (samplers.py:251-283).
+ *   state[n_rows]       packed id of each row's current state (CSR lattices only, no sliced-column groups)
+ *   look_state[n_rows]  NULL: beta look-ahead = beta of each arc's own destination.  Otherwise the reference's
+ *                       behaviour (quirk: scorers.py:584 reads the state before :679 advances it): beta of the
+ *                       label's successor from look_state (the state BEFORE the previous symbol), or beta of
+ *                       the start state where look_state has no arc with that label (transition = 0)
+ *   prefix[n_rows, V]   the network's score of every label (beta_scorer output)
+ *   base_mask[n_rows,V] vocabulary mask of the scorer base class (scorers.py:314-338), or NULL
+ *   beta_real[S]        REAL-space beta per packed state (the reference adds beta itself, not its log)
+ *   arc_static[A]       log-weights of weighted emission tables, or NULL (boolean tables)
+ *   masked logit of label l at state s = ((l == pad ? 0 : beta[dst] + prefix[l]) + base_mask[l] + static) / T
+ *   for the labels on an arc out of s, -inf for all others; a state without arcs is the absorbing sink and
+ *   emits pad with probability 1.
+ *   given_sym[n_rows]   score these symbols (evaluate_only), or
+ *   uniform[n_rows]     sample by inverse CDF over the arcs in label order -- exactly one of the two.
+ * Outputs: sym_out, logp_out = log softmax at the symbol (-inf: symbol not allowed; the state then stays),
+ * next_state (packed), logz_out = logsumexp of the masked logits (optional).
+ */
+int nfst_walk_step_f32(const nfst_packed_lattices_t* lat, int32_t n_rows, int32_t rows_per_lattice,
+                       const int32_t* state, const int32_t* look_state, const float* prefix, const float* base_mask,
+                       const float* beta_real,
+                       const float* arc_static, float temperature, int32_t pad_id, const int32_t* given_sym,
+                       const float* uniform, int32_t* sym_out, float* logp_out, int32_t* next_state, float* logz_out,
+                       void* cuda_stream);
 
 /* One level of the beta-hat recurrence (FSAGRUScorer.compute_beta_per_sample with Wh != 0,
  * scorers.py:732-747), for the `n_states` packed state ids in `states` (all of one topological

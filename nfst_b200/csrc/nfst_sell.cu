@@ -49,6 +49,9 @@ namespace {
     if (_e != cudaSuccess) return nfst_fail_msg(NFST_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString(_e)); \
   } while (0)
 
+#ifndef SELL_FLOW_MIN_BLOCKS
+#define SELL_FLOW_MIN_BLOCKS 4
+#endif
 constexpr int KU = 8;  // arc columns held in registers per slice; deeper columns take the tail loops
 constexpr int TW = 4;  // columns per tail window (loads issued together)
 constexpr float kLog2e = 1.4426950408889634f;
@@ -505,7 +508,7 @@ __global__ void __launch_bounds__(NT_MAX, NT_MAX == 256 ? 4 : 1)
 // flow pass
 // =====================================================================================
 template <bool DTH, bool ALPHA, typename OT, int NT_MAX>
-__global__ void __launch_bounds__(NT_MAX, NT_MAX == 256 ? 4 : 1)
+__global__ void __launch_bounds__(NT_MAX, NT_MAX == 256 ? SELL_FLOW_MIN_BLOCKS : 1)
     sell_flow_kernel(const nfst_packed_lattices_t L, const int32_t* __restrict__ ids, int W, int max_levels,
                      int dtheta_smem, int far, const float* cond, const float* __restrict__ grad_logz, float* post,
                      const OT* __restrict__ beta, const OT* __restrict__ logz, OT* __restrict__ alpha,

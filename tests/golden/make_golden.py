@@ -122,9 +122,72 @@ def gen_iwae():
     print("iwae.npz:", len(sizes), "cases")
 
 
+class _Fixed(torch.nn.Module):
+    """stands in for the scorer's beta_scorer MLP: returns a recorded tensor"""
+
+    def __init__(self, value):
+        super().__init__()
+        self.value = value
+
+    def forward(self, h):
+        return self.value
+
+
+def gen_walk():
+    """A few time steps of the reference's own sampling loop (samplers.py:243-297) through
+    FSAGRUScorer.left_to_right_score (scorers.py:340-366): masked logits, sampled symbols, log_prob, zs and
+    the FSA states before / after.  The network's beta_scorer output is replaced by a recorded random tensor
+    (an attribute of the module instance; no reference source is touched), everything else is the reference."""
+    from torch.distributions import Categorical
+
+    from oracle.lattice_oracle import collate_pad
+
+    ns = rh.load()
+    rng = np.random.default_rng(20260404)
+    k, T, steps = 3, 0.8, 7
+    m = rh.make_scorer(H, V, seed=41, zero_wh=True, double=False)
+    tabs = [random_mark_lattice(rng, n, V, parallel_arcs=False)[1] for n in (4, 7, 5)]
+    tr = collate_pad(tabs, PAD)
+    em = collate_pad([t != 0 for t in tabs], PAD)
+    out = {"vocab": np.int64(V), "k": np.int64(k), "temperature": np.float64(T), "steps": np.int64(steps),
+           "pad": np.int64(ns.pad), "bos": np.int64(ns.bos), "tr": tr, "em": em,
+           "n_states": np.array([t.shape[0] for t in tabs], dtype=np.int64)}
+    torch.manual_seed(4242)
+    with torch.no_grad():
+        m.set_masks(emission=torch.from_numpy(em), transition=torch.from_numpy(tr))
+        m.set_k(k)
+        beta = m.compute_beta()  # [B*k, S] real space
+        out["beta"] = beta.numpy()
+        N = beta.shape[0]
+        hx, inp, metadata = m.get_init_states(N, device=torch.device("cpu"))
+        for t in range(steps):
+            out[f"state_old_{t}"] = metadata["state"].numpy().copy()
+            out[f"inp_{t}"] = inp.numpy().copy()
+            base = super(ns.FSAGRUScorer, m).mask_out_invalid(inp, metadata)  # vocabulary mask, scorers.py:314-338
+            prefix = torch.randn(N, V)
+            m.beta_scorer = _Fixed(prefix)
+            new_h, masked, upd = m.left_to_right_score(left_h=hx, left_inp=inp, metadata=metadata, beta=beta)
+            masked = masked / T
+            dist = Categorical(logits=masked)
+            sym = dist.sample()
+            out[f"state_new_{t}"] = upd["state"].numpy().copy()
+            out[f"prefix_{t}"] = prefix.numpy()
+            out[f"base_{t}"] = base.numpy().copy()
+            out[f"masked_{t}"] = masked.numpy().copy()
+            out[f"sym_{t}"] = sym.numpy().copy()
+            out[f"logp_{t}"] = dist.log_prob(sym).numpy().copy()
+            out[f"zs_{t}"] = torch.logsumexp(masked, dim=1).numpy().copy()
+            out[f"next_{t}"] = m.update_fsa_state(sym, upd["state"]).numpy().copy()
+            metadata = m.metadata_callback(new_h, sym, upd)
+            inp, hx = sym, new_h
+    np.savez_compressed(os.path.join(OUT, "walk_step.npz"), **out)
+    print("walk_step.npz:", steps, "steps,", N, "rows")
+
+
 if __name__ == "__main__":
     if not rh.available():
         raise SystemExit("reference not mounted; golden vectors can only be regenerated in the build container")
     gen_per_sample()
     gen_parallel()
     gen_iwae()
+    gen_walk()

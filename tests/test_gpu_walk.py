@@ -1,0 +1,152 @@
+"""GPU parity of the fused sampling-loop step (nfst_walk_step_f32) against the reference's own loop (golden
+vectors) and against the numpy restatement on larger random cases, in both look-ahead modes, for boolean and
+weighted tables, scoring and sampling."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import nfst_b200 as nb
+from nfst_b200.sampler import LatticeWalker, walk_step
+from oracle import lattice_oracle as lo
+from oracle import walk_oracle as wo
+from tests.lattice_gen import PAD, random_mark_lattice
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+G = os.path.join(os.path.dirname(__file__), "golden", "walk_step.npz")
+
+
+def to_packed_states(p, k, dense_state):
+    """dense (reference) state ids of the rows -> packed ids"""
+    B, S = p.dense_shape[0], p.dense_shape[1]
+    inv = torch.full((B, S), -1, dtype=torch.int64)
+    so = p.state_off.cpu().long()
+    orig = p.orig_state.cpu().long()
+    for b in range(B):
+        inv[b, orig[so[b]:so[b + 1]]] = torch.arange(so[b], so[b + 1])
+    rows = torch.arange(B * k) // k
+    out = inv[rows, torch.as_tensor(dense_state).long()]
+    assert (out >= 0).all()
+    return out.to(torch.int32).to(DEV)
+
+
+def packed_beta(p, k, beta_dense):
+    """beta[B*k, S] (reference layout, real space) -> one value per packed state"""
+    so = p.state_off.cpu().numpy()
+    lat = np.repeat(np.arange(p.n_lattices), np.diff(so))
+    return torch.from_numpy(beta_dense[lat * k, p.orig_state.cpu().numpy()].astype(np.float32)).to(DEV)
+
+
+def test_walk_step_matches_the_reference_loop():
+    g = np.load(G)
+    k, T, pad = int(g["k"]), float(g["temperature"]), int(g["pad"])
+    tr = torch.from_numpy(g["tr"]).to(DEV)
+    p = nb.pack_dense(tr != 0, tr, weighted=False)
+    beta = packed_beta(p, k, g["beta"])
+    # (1) every recorded step on its own
+    for t in range(int(g["steps"])):
+        sym, logp, nxt, logz = walk_step(
+            p, k, to_packed_states(p, k, g[f"state_new_{t}"]), torch.from_numpy(g[f"prefix_{t}"]).to(DEV), beta, pad,
+            base_mask=torch.from_numpy(g[f"base_{t}"]).to(DEV), symbols=torch.from_numpy(g[f"sym_{t}"]).to(DEV),
+            temperature=T, look_state=to_packed_states(p, k, g[f"state_old_{t}"]))
+        np.testing.assert_array_equal(sym.cpu().numpy(), g[f"sym_{t}"])
+        np.testing.assert_allclose(logp.cpu().numpy(), g[f"logp_{t}"], rtol=1e-5, atol=2e-6)
+        np.testing.assert_allclose(logz.cpu().numpy(), g[f"zs_{t}"], rtol=1e-5, atol=2e-6)
+        np.testing.assert_array_equal(p.orig_state[nxt.long()].cpu().numpy(), g[f"next_{t}"])
+    # (2) the walker object replays the whole loop: bos is consumed first (scorers.py:230-231), then one
+    # scored symbol per step; its states are the reference's metadata["state"]
+    w = LatticeWalker(p, k, beta, pad, temperature=T, faithful=True)
+    w.consume(torch.full((w.n_rows,), int(g["bos"]), dtype=torch.int32, device=DEV))
+    total = torch.zeros(w.n_rows, device=DEV)
+    for t in range(int(g["steps"])):
+        np.testing.assert_array_equal(w.dense_state().cpu().numpy(), g[f"state_new_{t}"])
+        sym, logp, logz = w.step(torch.from_numpy(g[f"prefix_{t}"]).to(DEV), base_mask=torch.from_numpy(g[f"base_{t}"]).to(DEV),
+                                 symbols=torch.from_numpy(g[f"sym_{t}"]).to(DEV))
+        np.testing.assert_allclose(logp.cpu().numpy(), g[f"logp_{t}"], rtol=1e-5, atol=2e-6)
+        total += logp
+    ref_total = sum(g[f"logp_{t}"] for t in range(int(g["steps"])))
+    np.testing.assert_allclose(total.cpu().numpy(), ref_total, rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.parametrize("weighted", [False, True])
+@pytest.mark.parametrize("faithful", [True, False])
+def test_walk_step_matches_oracle_on_random_walks(weighted, faithful):
+    rng = np.random.default_rng(7 + weighted)
+    V, k, T = 40, 4, 1.3
+    tabs = [random_mark_lattice(rng, n, V, parallel_arcs=False) for n in (12, 30, 21, 5)]
+    tr = lo.collate_pad([t[1] for t in tabs], PAD)
+    em_bool = lo.collate_pad([t[1] != 0 for t in tabs], PAD)
+    if weighted:  # float log-weights, -inf = no arc (scorers.py:1011-1013,1026-1027)
+        em = np.where(tr != 0, rng.normal(size=tr.shape), -np.inf)
+        for b, t in enumerate(tabs):  # the sink's pad loop carries weight 0 (scorers.py:1013-1016)
+            em[b, t[1].shape[0] - 1, PAD] = 0.0
+    else:
+        em = em_bool
+    B, S, _ = tr.shape
+    N = B * k
+    trt = torch.from_numpy(tr).to(DEV)
+    p = nb.pack_dense(torch.from_numpy(em).to(DEV), trt, weighted=weighted)
+    beta_dense = np.abs(rng.normal(size=(N, S))).astype(np.float32) + 0.1  # any positive numbers will do
+    beta_dense = np.repeat(beta_dense[::k], k, axis=0)  # rows of one lattice share beta
+    beta = packed_beta(p, k, beta_dense)
+    state_old = np.zeros(N, dtype=np.int64)
+    state_new = tr[np.arange(N) // k, 0, 1].astype(np.int64)  # after bos
+    for step in range(10):
+        prefix = rng.normal(size=(N, V)).astype(np.float32)
+        base = np.where(rng.random((N, V)) < 0.1, -1.5, 0.0).astype(np.float32)
+        # pick a valid symbol per row (pad at the sink, whose pad loop the edge rule drops)
+        syms = np.empty(N, dtype=np.int64)
+        for n in range(N):
+            valid = np.nonzero(tr[n // k, state_new[n]] != 0)[0]
+            syms[n] = rng.choice(valid)
+        look_old = state_old if faithful else None
+        st_old_for_oracle = state_old if faithful else state_new  # aligned: the row of the state itself
+        masked, o_logp, o_logz, o_next = wo.walk_step_dense(em, tr, k, beta_dense, st_old_for_oracle, state_new, prefix, base,
+                                                            PAD, T, syms)
+        kw = dict(base_mask=torch.from_numpy(base).to(DEV), temperature=T,
+                  look_state=None if look_old is None else to_packed_states(p, k, look_old))
+        sym, logp, nxt, logz = walk_step(p, k, to_packed_states(p, k, state_new), torch.from_numpy(prefix).to(DEV), beta, PAD,
+                                         symbols=torch.from_numpy(syms).to(DEV), **kw)
+        np.testing.assert_allclose(logp.cpu().numpy(), o_logp, rtol=1e-5, atol=1e-5)
+        np.testing.assert_allclose(logz.cpu().numpy(), o_logz, rtol=1e-5, atol=1e-5)
+        np.testing.assert_array_equal(p.orig_state[nxt.long()].cpu().numpy(), o_next)
+        # sampling: inverse CDF over the arcs in label order == over the dense row in label order
+        u = rng.random(N).astype(np.float32)
+        s_sym, s_logp, s_nxt, _ = walk_step(p, k, to_packed_states(p, k, state_new), torch.from_numpy(prefix).to(DEV), beta, PAD,
+                                            uniform=torch.from_numpy(u).to(DEV), **kw)
+        probs = np.exp(masked - o_logz[:, None])
+        cdf = np.cumsum(probs, axis=1)
+        s_sym = s_sym.cpu().numpy()
+        for n in range(N):
+            want = int(np.searchsorted(cdf[n], u[n], side="right"))
+            if want != s_sym[n]:  # only at a boundary of the CDF (float32 vs float64 round-off)
+                assert abs(cdf[n, min(want, V - 1)] - u[n]) < 1e-5 or abs(cdf[n, s_sym[n]] - u[n]) < 1e-5
+            assert probs[n, s_sym[n]] > 0
+            assert abs(s_logp[n].item() - np.log(probs[n, s_sym[n]])) < 1e-4
+        state_old, state_new = state_new, o_next
+
+
+def test_walk_sampling_frequencies_and_misuse():
+    rng = np.random.default_rng(3)
+    V, k = 24, 4096
+    _, tr = random_mark_lattice(rng, 6, V, parallel_arcs=False)
+    trt = torch.from_numpy(tr)[None].to(DEV)
+    p = nb.pack_dense(trt != 0, trt, weighted=False)
+    beta = torch.ones(p.n_states, device=DEV)
+    w = LatticeWalker(p, k, beta, PAD, faithful=False)
+    w.consume(torch.full((k,), 1, dtype=torch.int32, device=DEV))
+    prefix = torch.randn(V, device=DEV).expand(k, V).contiguous()
+    s0 = int(w.dense_state()[0])
+    sym, logp, logz = w.step(prefix)
+    valid = np.nonzero(tr[s0] != 0)[0]
+    pr = torch.softmax(prefix[0, valid] + 1.0, 0).cpu().numpy()
+    freq = np.array([(sym == int(l)).float().mean().item() for l in valid])
+    assert np.all(np.abs(freq - pr) < 4 * np.sqrt(pr * (1 - pr) / k) + 1e-3)
+    with pytest.raises(ValueError):
+        walk_step(p, k, w.state, prefix, beta, PAD)  # neither symbols nor uniform
+    lib = nb._lib.load()
+    rc = lib.nfst_walk_step_f32(p.c_struct(), k, k, w.state.data_ptr(), None, prefix.data_ptr(), None, beta.data_ptr(), None,
+                                0.0, PAD, None, prefix.data_ptr(), sym.data_ptr(), logp.data_ptr(), sym.data_ptr(), None, None)
+    assert rc < 0 and b"temperature" in lib.nfst_last_error_string()
