@@ -161,6 +161,61 @@ def training_step_report():
           f"d theta vs C oracle rel {err:.1e} (first {B} lattices)", flush=True)
 
 
+def walk_step_report(B=32, k=16):
+    """one time step of the sampling loop on config-1 lattices (B*k rows, V = 256): the fused
+    kernel next to the reference's own sequence of eager torch ops on the same GPU (dense [B*k, S, V] tables,
+    scorers.py:577-593, :683-690, :1037-1054, samplers.py:251-283)."""
+    from nfst_b200.sampler import walk_step
+    from torch.distributions import Categorical
+
+    ab = synth.transliteration_batch(B, seed=0)
+    p, _ = ab.to(DEV).pack()
+    V, N = ab.vocab, B * k
+    S = int(ab.n_states.max()) + 1
+    # dense tables as the reference holds them (k-fold expanded, scorers.py:887-918)
+    tr = torch.zeros(B, S, V, dtype=torch.int64)
+    tr[ab.arc_lattice, ab.src, ab.label] = ab.dst
+    tr_k = tr.to(DEV).repeat_interleave(k, 0)
+    em_k = tr_k != 0
+    beta_dense = torch.rand(N, S, device=DEV) + 0.1
+    zero_v, ninf_v = torch.zeros(V, device=DEV), torch.full((V,), float("-inf"), device=DEV)
+    prefix = torch.randn(N, V, device=DEV)
+    base = torch.zeros(N, V, device=DEV)
+    rows = torch.arange(N, device=DEV)
+    state_dense = tr_k[rows, 0, synth.BOS]  # after bos
+    look_dense = torch.zeros(N, dtype=torch.int64, device=DEV)
+
+    def reference_ops():
+        trans = tr_k[rows, look_dense]                       # scorers.py:586-589
+        final = torch.gather(beta_dense, 1, trans) + prefix  # :590-592
+        mask = torch.where(em_k[rows, state_dense], zero_v, ninf_v)  # :1042-1049
+        masked = (final + base + mask) / 1.0
+        dist = Categorical(logits=masked)
+        sym = dist.sample()
+        lp = dist.log_prob(sym)
+        nxt = tr_k[rows, state_dense][rows, sym]             # :683-690
+        return sym, lp, nxt
+
+    # packed equivalents of the same states
+    so = p.state_off.long()
+    inv = torch.full((B, S), 0, dtype=torch.int64, device=DEV)
+    lat = torch.repeat_interleave(torch.arange(B, device=DEV), (so[1:] - so[:-1]))
+    inv[lat, p.orig_state.long()] = torch.arange(p.n_states, device=DEV)
+    st = inv[rows // k, state_dense].to(torch.int32)
+    lk = inv[rows // k, look_dense].to(torch.int32)
+    beta_packed = beta_dense[lat * k, p.orig_state.long()].contiguous()
+    u = torch.rand(N, device=DEV)
+
+    def fused():
+        return walk_step(p, k, st, prefix, beta_packed, synth.PAD, base_mask=base, uniform=u, look_state=lk)
+
+    ms_ref = timed(reference_ops, args.steps * 5, False)
+    ms_new = timed(fused, args.steps * 5, False)
+    print(f"{'config1 sampling-loop step B=32 k=16':44s} rows {N}, V {V}: fused kernel {ms_new * 1e3:.1f} us/step, the reference's eager "
+          f"torch ops on the same GPU {ms_ref * 1e3:.1f} us/step ({ms_ref / ms_new:.1f}x); dense tables {tr_k.numel() * 9 / 1e6:.0f} MB "
+          f"vs packed arcs {p.n_arcs * 8 / 1e6:.2f} MB", flush=True)
+
+
 q = args.quick
 CONFIGS = [
     ("config1 transliteration B=32", lambda n, o: synth.transliteration_batch(n, seed=o), 32, 32),
@@ -182,9 +237,12 @@ for name, gen, B, per_chunk in CONFIGS:
     A, S = packed.n_arcs, packed.n_states
     flush = 20 * A < 2 * 126e6
 
-    def fb():
-        al, lz = nb.lattice_forward(packed, arc_scores=sc)
-        nb.lattice_backward(packed, arc_scores=sc, alpha=al, logz=lz, want_beta=True, want_post=True)
+    all_sell = all(g.sell for g in packed.groups)
+    beta_buf = torch.empty(S, dtype=nb.ops.resolve_state_dtype(packed), device=DEV) if packed.has_sell else None
+
+    def fb():  # first pass: logZ (+ beta / alpha), second pass: posteriors (+ beta for CSR groups) -- bench.py's step
+        lz, al, cond = nb.ops.lattice_pull(packed, arc_scores=sc, beta_out=beta_buf)
+        nb.lattice_backward(packed, arc_scores=sc, alpha=al, logz=lz, cond=cond, want_beta=not all_sell, want_post=True)
 
     def vit():
         nb.lattice_viterbi(packed, arc_scores=sc)
@@ -192,6 +250,7 @@ for name, gen, B, per_chunk in CONFIGS:
     ms_fb = timed(fb, args.steps, flush)
     ms_v = timed(vit, args.steps, flush)
     par = parity(sample)
+    name = name + (" [sell]" if all_sell else "")
     print(f"{name:44s} {A:11d} {S:10d} {packed.max_levels:5d} {t_pack:7.2f} {ms_fb:8.3f} {A / ms_fb / 1e6:10.2f} "
           f"{(20 * A + 20 * S) / ms_fb / 1e6:8.0f} {ms_v:8.3f} {A / ms_v / 1e6:10.2f} | {par['cpu_arcs_per_s'] / 1e6:10.1f} {par['cpu_threads']:3d} | "
           f"state {par['state']} logZ rel {par['logz_rel']:.1e} post rel {par['post_rel']:.1e} "
@@ -200,3 +259,4 @@ for name, gen, B, per_chunk in CONFIGS:
     torch.cuda.empty_cache()
 recurrent_beta_report()
 training_step_report()
+walk_step_report()
