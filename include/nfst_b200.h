@@ -319,6 +319,21 @@ int nfst_walk_step_f32(const nfst_packed_lattices_t* lat, int32_t n_rows, int32_
                        const float* uniform, int32_t* sym_out, float* logp_out, int32_t* next_state, float* logz_out,
                        void* cuda_stream);
 
+/*
+ * The whole sampling loop for an arc-factored proposal (WFSTScorer, scorers.py:1663-1687): n_rows =
+ * B * rows_per_lattice walks from the start state, next arc drawn with probability
+ * exp(w_a + beta[dst_a] - beta[s]) (inverse CDF over the state's arcs in label order, uniform[n_rows, max_len]),
+ * until a state without arcs.  beta[S]: log-space beta of the same scores (nfst_bwd_fused_f32), float32 or
+ * float64 per beta_f64.  The paths are exact posterior samples: log_q[r] = score(path) - logZ, so every
+ * importance weight of Estimators.iwae (estimatros.py:10-44) equals logZ.  labels[n_rows, max_len] (padded
+ * with pad_id), arcs[n_rows, max_len] canonical arc ids (-1 padded; may be NULL), length[n_rows], log_q[n_rows].
+ * CSR lattices only; max_len >= the deepest lattice's level count - 1.
+ */
+int nfst_sample_paths_f32(const nfst_packed_lattices_t* lat, int32_t n_rows, int32_t rows_per_lattice, int32_t max_len,
+                          const nfst_scores_t* scores, const void* beta, int beta_f64, const float* uniform,
+                          int32_t pad_id, int32_t* labels, int32_t* arcs, int32_t* length, float* log_q,
+                          void* cuda_stream);
+
 /* One level of the beta-hat recurrence (FSAGRUScorer.compute_beta_per_sample with Wh != 0,
  * scorers.py:732-747), for the `n_states` packed state ids in `states` (all of one topological
  * level, any lattices; call for the deepest level first -- every arc's destination must be done):

@@ -19,6 +19,6 @@ from .ops import (  # noqa: F401
     lattice_viterbi,
 )
 
-from .sampler import LatticeWalker, walk_step  # noqa: F401
+from .sampler import LatticeWalker, sample_paths, walk_step  # noqa: F401
 
 __version__ = "0.1.0"

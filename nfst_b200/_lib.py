@@ -101,6 +101,8 @@ SYMBOLS = {
     "nfst_sell_flow_f32": (C.c_int, [C.POINTER(PackedLatticesC), C.POINTER(LaunchC)] + [_P] * 9),
     "nfst_walk_step_f32": (C.c_int, [C.POINTER(PackedLatticesC), C.c_int32, C.c_int32, _P, _P, _P, _P, _P, _P, C.c_float, C.c_int32,
                                      _P, _P, _P, _P, _P, _P, _P]),
+    "nfst_sample_paths_f32": (C.c_int, [C.POINTER(PackedLatticesC), C.c_int32, C.c_int32, C.c_int32, C.POINTER(ScoresC), _P,
+                                        C.c_int, _P, C.c_int32, _P, _P, _P, _P, _P]),
     "nfst_beta_hat_level_f32": (C.c_int, [C.POINTER(PackedLatticesC), _P, C.c_int32, C.c_int32, _P, _P, _P, _P, _P, _P, _P]),
     "nfst_beta_to_dense": (C.c_int, [C.POINTER(PackedLatticesC), _P, C.c_int, _P, C.c_int32, C.c_int32, _P, _P]),
     "nfst_dense_count_arcs": (C.c_int, [_P, C.c_int64, C.c_int32, C.c_int32, _P, _P]),

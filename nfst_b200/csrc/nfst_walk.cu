@@ -131,3 +131,90 @@ extern "C" int nfst_walk_step_f32(const nfst_packed_lattices_t* lat, int32_t n_r
   if (e != cudaSuccess) return nfst_fail_msg(NFST_ERR_CUDA, "walk_step_kernel: %s", cudaGetErrorString(e));
   return 0;
 }
+
+// =====================================================================================
+// Whole sampling loop for an ARC-FACTORED proposal (second half).
+//
+// When the proposal's score of a path is the sum of its arc scores (the reference's WFSTScorer,
+// scorers.py:1663-1687), the look-ahead beta is exact and the loop of Sampler.stateful_sample
+// (samplers.py:243-297) needs no network between steps: from state s the next arc is drawn with
+// probability exp(w_a + beta[dst_a] - beta[s]), and the walk ends at a state without arcs.  The
+// paths are then EXACT samples of the posterior over paths, log q(z) = score(z) - logZ, so every
+// importance weight log p~(z) - log q(z) of Estimators.iwae (estimatros.py:10-44) equals logZ: the
+// k-sample estimate has zero variance.  One thread per row (lattice, sample) walks the whole path in one
+// launch; inverse CDF over the arcs of a state in label order, one uniform number per step.
+// =====================================================================================
+namespace {
+
+template <typename ST>
+__global__ void sample_paths_kernel(const nfst_packed_lattices_t L, int n_rows, int rows_per_lattice, int max_len,
+                                    const float* __restrict__ arc_scores, const float* __restrict__ theta,
+                                    const ST* __restrict__ beta, const float* __restrict__ uniform, int pad_id,
+                                    int32_t* __restrict__ labels, int32_t* __restrict__ arcs,
+                                    int32_t* __restrict__ length, float* __restrict__ log_q) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n_rows) return;
+  int s = L.start_state[r / rows_per_lattice];
+  double lq = 0.0;
+  int t = 0;
+  for (; t < max_len; ++t) {
+    const int a0 = L.out_ptr[s], a1 = L.out_ptr[s + 1];
+    if (a1 == a0) break;  // the sink (its pad loop is not an arc)
+    const double bs = static_cast<double>(beta[s]);
+    const float u = uniform[static_cast<size_t>(r) * max_len + t];
+    auto logc = [&](int a) -> double {  // log P(arc | state)
+      float w = arc_scores ? arc_scores[a] : 0.0f;
+      if (theta) w += theta[L.label_out[a]];
+      return static_cast<double>(w) + static_cast<double>(beta[L.dst_out[a]]) - bs;
+    };
+    int pick = -1;
+    double cum = 0.0, lp = 0.0;
+    for (int a = a0; a < a1; ++a) {
+      const double lc = logc(a);
+      const double c = exp(lc);
+      if (c > 0.0) {  // the last arc with mass catches round-off at the top of the CDF
+        pick = a;
+        lp = lc;
+      }
+      cum += c;
+      if (cum > static_cast<double>(u) && c > 0.0) break;
+    }
+    if (pick < 0) break;  // every arc has probability 0 (scores -inf): the walk cannot continue
+    lq += lp;
+    labels[static_cast<size_t>(r) * max_len + t] = L.label_out[pick];
+    if (arcs) arcs[static_cast<size_t>(r) * max_len + t] = pick;
+    s = L.dst_out[pick];
+  }
+  length[r] = t;
+  log_q[r] = static_cast<float>(lq);
+  for (int i = t; i < max_len; ++i) {
+    labels[static_cast<size_t>(r) * max_len + i] = pad_id;
+    if (arcs) arcs[static_cast<size_t>(r) * max_len + i] = -1;
+  }
+}
+
+}  // namespace
+
+extern "C" int nfst_sample_paths_f32(const nfst_packed_lattices_t* lat, int32_t n_rows, int32_t rows_per_lattice,
+                                     int32_t max_len, const nfst_scores_t* scores, const void* beta, int beta_f64,
+                                     const float* uniform, int32_t pad_id, int32_t* labels, int32_t* arcs,
+                                     int32_t* length, float* log_q, void* cuda_stream) {
+  if (!lat || !scores || !beta || !uniform || !labels || !length || !log_q)
+    return nfst_fail_msg(NFST_ERR_BAD_ARG, "nfst_sample_paths_f32: null argument");
+  if (!scores->arc_scores && !scores->theta) return nfst_fail_msg(NFST_ERR_BAD_ARG, "arc_scores or theta is required");
+  if (n_rows < 0 || rows_per_lattice <= 0 || max_len <= 0) return nfst_fail_msg(NFST_ERR_BAD_ARG, "bad row counts");
+  if (n_rows == 0) return 0;
+  const int threads = 128;
+  cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+  if (beta_f64)
+    sample_paths_kernel<double><<<(n_rows + threads - 1) / threads, threads, 0, st>>>(
+        *lat, n_rows, rows_per_lattice, max_len, scores->arc_scores, scores->theta, static_cast<const double*>(beta),
+        uniform, pad_id, labels, arcs, length, log_q);
+  else
+    sample_paths_kernel<float><<<(n_rows + threads - 1) / threads, threads, 0, st>>>(
+        *lat, n_rows, rows_per_lattice, max_len, scores->arc_scores, scores->theta, static_cast<const float*>(beta),
+        uniform, pad_id, labels, arcs, length, log_q);
+  const cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return nfst_fail_msg(NFST_ERR_CUDA, "sample_paths_kernel: %s", cudaGetErrorString(e));
+  return 0;
+}

@@ -111,3 +111,42 @@ def walk_step(packed: PackedLattices, k: int, state: torch.Tensor, prefix: torch
                                           p(logz), ops._stream(dev)))
         ops.launch_count += 1
     return sym, logp, nxt, logz
+
+
+def sample_paths(packed: PackedLattices, k: int, arc_scores=None, theta=None, *, pad_id: int = 3,
+                 uniform: Optional[torch.Tensor] = None, beta: Optional[torch.Tensor] = None):
+    """k exact posterior samples per lattice for an arc-factored model (``WFSTScorer``, ``scorers.py:1663-1687``):
+    the whole loop of ``Sampler.stateful_sample`` in one launch (``nfst_sample_paths_f32``).
+
+    Returns ``(labels int32 [B*k, T] padded with pad_id, lengths int32 [B*k], log_q float32 [B*k],
+    arcs int32 [B*k, T] canonical arc ids, logz [B])``.  ``log_q = score(path) - logZ``: with these samples
+    every importance weight of ``Estimators.iwae`` (``estimatros.py:10-44``) is ``logZ`` itself."""
+    lib = _lib.load()
+    dev = packed.device
+    if dev.type != "cuda":
+        raise RuntimeError("nfst_b200 kernels need the packed lattices on a CUDA device (no CPU fallback)")
+    if packed.has_sell:
+        raise ValueError("the walk reads CSR arcs: pack with sell=False")
+    sc, keep = ops._scores(packed, arc_scores, theta)
+    if beta is None:
+        r = ops.lattice_backward(packed, arc_scores, theta, want_beta=True)
+        beta, logz = r["beta"], r["logz_bwd"]
+    else:
+        logz = beta[packed.start_state.long()]
+    N, T = packed.n_lattices * k, max(packed.max_levels - 1, 1)
+    if uniform is None:
+        uniform = torch.rand(N, T, device=dev)
+    uniform = uniform.detach().to(device=dev, dtype=torch.float32).contiguous()
+    if tuple(uniform.shape) != (N, T):
+        raise ValueError(f"uniform must be [{N}, {T}]")
+    labels = torch.empty(N, T, dtype=torch.int32, device=dev)
+    arcs = torch.empty(N, T, dtype=torch.int32, device=dev)
+    length = torch.empty(N, dtype=torch.int32, device=dev)
+    log_q = torch.empty(N, dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.nfst_sample_paths_f32(packed.c_struct(), N, k, T, sc, beta.data_ptr(), int(beta.dtype == torch.float64),
+                                             uniform.data_ptr(), int(pad_id), labels.data_ptr(), arcs.data_ptr(),
+                                             length.data_ptr(), log_q.data_ptr(), ops._stream(dev)))
+        ops.launch_count += 1
+    del keep
+    return labels, length, log_q, arcs, logz

@@ -150,3 +150,63 @@ def test_walk_sampling_frequencies_and_misuse():
     rc = lib.nfst_walk_step_f32(p.c_struct(), k, k, w.state.data_ptr(), None, prefix.data_ptr(), None, beta.data_ptr(), None,
                                 0.0, PAD, None, prefix.data_ptr(), sym.data_ptr(), logp.data_ptr(), sym.data_ptr(), None, None)
     assert rc < 0 and b"temperature" in lib.nfst_last_error_string()
+
+
+def test_sample_paths_are_exact_posterior_samples():
+    """The whole loop in one launch for an arc-factored model: every sampled path is a start->sink path, its
+    log q is score(path) - logZ (so every IWAE weight, estimatros.py:10-44, equals logZ), arc frequencies match
+    the posteriors, and the walk is the inverse-CDF walk of the float64 restatement on the same uniforms."""
+    from nfst_b200 import synth
+    from nfst_b200.sampler import sample_paths
+    from oracle import c_oracle
+
+    ab = synth.transliteration_batch(6, seed=9)
+    p, sc = ab.to(DEV).pack()
+    k = 2048
+    T = p.max_levels - 1
+    g = torch.Generator(device=DEV).manual_seed(5)
+    u = torch.rand(p.n_lattices * k, T, device=DEV, generator=g)
+    labels, length, log_q, arcs, logz = sample_paths(p, k, arc_scores=sc, uniform=u, pad_id=PAD)
+    ob = c_oracle.Batch(ab.arc_lattice.numpy(), ab.src.numpy(), ab.dst.numpy(), ab.label.numpy(), ab.scores.numpy(),
+                        ab.n_states.numpy())
+    o_logz, _, o_beta, o_post = c_oracle.forward_backward(ob)
+    np.testing.assert_allclose(logz.cpu().numpy(), o_logz, rtol=1e-5)
+    arcs_c, len_c, lq = arcs.cpu().numpy(), length.cpu().numpy(), log_q.cpu().numpy()
+    w, dst, src = sc.cpu().numpy().astype(np.float64), p.dst_out.cpu().numpy(), p.src_out.cpu().numpy()
+    out_ptr, start = p.out_ptr.cpu().numpy(), p.start_state.cpu().numpy()
+    lab = labels.cpu().numpy()
+    for r in range(0, p.n_lattices * k, 97):  # a sample of the rows, path by path
+        b, path = r // k, arcs_c[r, :len_c[r]]
+        assert src[path[0]] == start[b] and np.array_equal(dst[path[:-1]], src[path[1:]])
+        assert out_ptr[dst[path[-1]] + 1] == out_ptr[dst[path[-1]]]  # ends at a state without arcs
+        assert np.all(arcs_c[r, len_c[r]:] == -1) and np.all(lab[r, len_c[r]:] == PAD)
+        np.testing.assert_array_equal(lab[r, :len_c[r]], p.label_out.cpu().numpy()[path])
+        assert abs(lq[r] - (w[path].sum() - o_logz[b])) < 2e-4  # log q = score - logZ: the IWAE weight is logZ
+    # zero-variance estimate: logsumexp_k(score - log q) - log k == logZ for every lattice
+    score = torch.zeros_like(log_q)
+    valid = arcs >= 0
+    score = (sc[arcs.clamp(min=0).long()] * valid).sum(1)
+    est = torch.logsumexp((score - log_q).view(p.n_lattices, k), 1) - np.log(k)
+    np.testing.assert_allclose(est.cpu().numpy(), o_logz, rtol=1e-5, atol=1e-4)
+    # arc frequencies ~ posteriors
+    counts = torch.bincount(arcs[valid].long(), minlength=p.n_arcs).cpu().numpy() / k
+    ref = o_post[p.arc_origin.cpu().numpy()]
+    assert np.all(np.abs(counts - ref) < 5 * np.sqrt(np.maximum(ref * (1 - ref), 1e-9) / k) + 2e-3)
+    # inverse-CDF walk of the float64 restatement on the same uniforms (first rows of lattice 0)
+    so = np.concatenate([[0], np.cumsum(ab.n_states.numpy())])
+    state_off = p.state_off.cpu().numpy()
+    lat = np.repeat(np.arange(p.n_lattices), np.diff(state_off))
+    beta = o_beta[so[lat] + p.orig_state.cpu().numpy()]
+    uu = u.cpu().numpy()
+    mism = 0
+    for r in range(64):
+        s, t = start[0], 0
+        while out_ptr[s + 1] > out_ptr[s]:
+            a = np.arange(out_ptr[s], out_ptr[s + 1])
+            c = np.exp(w[a] + beta[dst[a]] - beta[s])
+            j = min(int(np.searchsorted(np.cumsum(c), uu[r, t], side="right")), len(a) - 1)
+            if a[j] != arcs_c[r, t]:
+                mism += 1
+                break
+            s, t = dst[a[j]], t + 1
+    assert mism <= 1  # a uniform number can fall on a CDF boundary (fp32 beta on the GPU side)
