@@ -72,11 +72,19 @@ __device__ __forceinline__ float lg2_approx(float x) {
 
 extern __shared__ __align__(16) unsigned char sell_smem[];
 
-// position of a slice in a lattice: level l, slice j of that level
+// position of a warp in a lattice: level l, round j of that level.  The slices of a level are dealt to the warps
+// in rounds of nw, in SERPENTINE order (round 0 to warps 0..nw-1, round 1 to warps nw-1..0, ...): degrees
+// descend along a level, so the slices of a round get lighter from first to last; the warp that takes the
+// heaviest slice of the level (the one with the many-arc states, whose arcs beyond the register window cost
+// extra memory round trips) takes the lightest of the next round, and the leftover round -- the lightest slices
+// -- never lands on that warp when the level has a multiple of nw slices plus one.
 struct Pos {
   int l, j;
   bool ok;
 };
+__device__ __forceinline__ int slice_of(const Pos& p, int warp, int nw) {
+  return p.j * nw + ((p.j & 1) ? nw - 1 - warp : warp);
+}
 // degree byte + descriptor of a slice (loaded two slices ahead; nothing here waits for a load)
 struct StA {
   int s;     // this lane's state (global packed id); 0x7fffffff for idle lanes
@@ -95,28 +103,26 @@ __device__ __forceinline__ int slice_dmax8(const int4& d) { return static_cast<u
 // lsl[l] = index of the first slice of level l (lsl[n_levels] closes the last level)
 template <bool DESC>
 __device__ __forceinline__ void advance(Pos& p, const int* lsl, int n_levels, int warp, int nw) {
-  p.j += nw;
+  p.j += 1;
   while (DESC ? p.l >= 0 : p.l < n_levels) {
-    if (p.j < lsl[p.l + 1] - lsl[p.l]) {
+    if (slice_of(p, warp, nw) < lsl[p.l + 1] - lsl[p.l]) {
       p.ok = true;
       return;
     }
     p.l += DESC ? -1 : 1;
-    p.j = warp;
+    p.j = 0;
   }
   p.ok = false;
 }
 
-__device__ __forceinline__ StA load_a(const Pos& p, const int* lvl, const int* lsl, int lane,
+__device__ __forceinline__ StA load_a(const Pos& p, const int* lvl, const int* lsl, int lane, int warp, int nw,
                                       const uint8_t* __restrict__ deg8, const int4* __restrict__ desc) {
   StA a;
   a.s = 0x7fffffff;
   a.degb = 0;
   a.d = make_int4(0, 0, 0, 0);
   if (p.ok) {
-    // p.j counts from the END of the level: degrees descend along a level, so the warp that gets one slice
-    // more than the others (warp 0) gets the lightest ones
-    const int jj = lsl[p.l + 1] - lsl[p.l] - 1 - p.j;
+    const int jj = slice_of(p, warp, nw);
     const int first = lvl[p.l] + 32 * jj;
     if (first + lane < lvl[p.l + 1]) {
       a.s = first + lane;
@@ -143,6 +149,49 @@ __device__ __forceinline__ void for_columns(const int4& d, int deg, int lane, F&
     for_columns<K + 1>(d, deg, lane, f);
   }
 }
+// ---- per-warp staging of a slice's arc columns (cp.async, 16 bytes per lane) ----
+// The columns 0..KU-1 of a slice lie inside its first 32*KU arcs.  Each warp owns one stage of SA elements per
+// streamed array; the copy of the NEXT slice's arcs is issued as soon as the current slice's columns have been
+// read out into registers, so it travels while the current slice is computed: one slice of every warp is
+// always in flight and no warp waits a full memory latency per slice.  Copies are 16-byte chunks of the
+// aligned superset of the range (the arrays are 16-byte aligned; the last chunk of the last slice of the batch
+// is copied by element).
+constexpr int SA = 32 * KU + 8;
+__device__ __forceinline__ void cp_async_16(void* smem, const void* gmem) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(static_cast<unsigned>(__cvta_generic_to_shared(smem))), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_4(void* smem, const void* gmem) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(static_cast<unsigned>(__cvta_generic_to_shared(smem))), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+template <bool A1, bool A2>
+__device__ __forceinline__ void stage_issue(const int4& d, int lane, int n_arcs, int32_t* stage, const int32_t* g0,
+                                            const void* g1, const void* g2) {
+  const int base = d.x & ~3;
+  const int n16 = (min(d.y, d.x + 32 * KU) - base + 3) >> 2;  // <= 65
+  const int32_t* h1 = static_cast<const int32_t*>(g1);
+  const int32_t* h2 = static_cast<const int32_t*>(g2);
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    const int c = lane + 32 * r;
+    if (c < n16) {
+      const int e0 = base + 4 * c;
+      if (e0 + 4 <= n_arcs) {
+        cp_async_16(stage + 4 * c, g0 + e0);
+        if (A1) cp_async_16(stage + SA + 4 * c, h1 + e0);
+        if (A2) cp_async_16(stage + 2 * SA + 4 * c, h2 + e0);
+      } else {
+        for (int j = 0; j < 4; ++j)
+          if (e0 + j < n_arcs) {
+            cp_async_4(stage + 4 * c + j, g0 + e0 + j);
+            if (A1) cp_async_4(stage + SA + 4 * c + j, h1 + e0 + j);
+            if (A2) cp_async_4(stage + 2 * SA + 4 * c + j, h2 + e0 + j);
+          }
+      }
+    }
+  }
+}
+
 // rare path: an arc longer than the shared-memory ring (kept out of line: no 64-bit address arithmetic in
 // the hot loops).  The value was written by this block before an earlier level barrier.
 #ifdef SELL_FAR_INLINE
@@ -204,10 +253,11 @@ __device__ __forceinline__ void lse_join(RT& m, float& s, RT m2, float s2) {
 // =====================================================================================
 // pull pass
 // =====================================================================================
-// NT_MAX: largest block the instantiation may be launched with; both variants are held to 64 registers
-// (8 blocks of 128 threads per SM: 1024 lattices fit the 148 SMs in ONE wave)
+// NT_MAX: largest block the instantiation may be launched with.  128: 72 registers (7 blocks per SM: 1024 lattices
+// fit the 148 SMs in ONE wave; at 64 registers ptxas spills the loop-carried slice descriptors and every reload
+// is a local-memory round trip on the slice's critical path -- measured 1.39 vs 0.65 ms); 256: 80 registers
 template <bool TROP, bool SC, bool TH, bool COND, typename OT, int NT_MAX>
-__global__ void __launch_bounds__(NT_MAX, NT_MAX == 256 ? 4 : 1)
+__global__ void __launch_bounds__(NT_MAX, NT_MAX == 128 ? 7 : NT_MAX == 256 ? 3 : 1)
     sell_pull_kernel(const nfst_packed_lattices_t L, const int32_t* __restrict__ ids, int W, int max_levels,
                      int theta_smem, int far, const float* __restrict__ arc_scores, const float* __restrict__ theta,
                      OT* beta, OT* __restrict__ logz, float* __restrict__ cond, float* delta,
@@ -232,6 +282,14 @@ __global__ void __launch_bounds__(NT_MAX, NT_MAX == 256 ? 4 : 1)
     float* sth = reinterpret_cast<float*>(lsl + lvl_words);
     for (int i = tid; i < L.vocab; i += blockDim.x) sth[i] = theta[i];
     th = sth;
+  }
+  // per-warp stage: [dst | scores (SC) | labels (TH)], SA elements each
+  int32_t* stage;
+  {
+    size_t o = static_cast<size_t>(W) * sizeof(RingT) + 2 * static_cast<size_t>(lvl_words) * 4;
+    if (TH && theta_smem) o += static_cast<size_t>(L.vocab) * 4;
+    o = (o + 15) & ~static_cast<size_t>(15);
+    stage = reinterpret_cast<int32_t*>(sell_smem + o) + warp * ((1 + SC + TH) * SA);
   }
   __syncthreads();
   const int mask = W - 1;
@@ -278,16 +336,21 @@ __global__ void __launch_bounds__(NT_MAX, NT_MAX == 256 ? 4 : 1)
                                               : fill;
   };
 
-  // ---- pipeline state: the slice being computed and the next one (descriptor + degree byte in flight).
-  // The arc columns themselves are not prefetched: with 8 warps per scheduler the kernel is bound by
-  // instruction issue, the other warps cover a slice's one exposed load latency, and every prefetch
-  // scheme tried (register double buffering, L2 prefetch) cost more instructions than it saved.
+  // ---- pipeline state: the slice being computed (its arc columns staged in shared memory), the next one
+  // (descriptor + degree byte in registers, its stage copy issued once the current columns are read out) and
+  // the one after that (descriptor + degree byte in flight).  None of these addresses depends on a DP value.
+  auto issue = [&](const int4& d) {
+    stage_issue<true, SC && TH>(d, lane, L.n_arcs, stage, dst_out, SC ? static_cast<const void*>(arc_scores) : static_cast<const void*>(label_out),
+                        SC ? static_cast<const void*>(label_out) : nullptr);
+  };
   Pos pc, pn;
-  pc.l = n_levels - 1; pc.j = warp - nw; pc.ok = false;
+  pc.l = n_levels - 1; pc.j = -1; pc.ok = false;
   advance<true>(pc, lsl, n_levels, warp, nw);
   pn = pc;
   if (pn.ok) advance<true>(pn, lsl, n_levels, warp, nw);
-  StA ac = load_a(pc, lvl, lsl, lane, deg8, desc);
+  StA ac = load_a(pc, lvl, lsl, lane, warp, nw, deg8, desc);
+  StA an = load_a(pn, lvl, lsl, lane, warp, nw, deg8, desc);
+  if (pc.ok) issue(ac.d);
   const int lim_cap = last0;  // ring reads need dst < min(lim, last0)
 
 #pragma unroll 1
@@ -298,22 +361,33 @@ __global__ void __launch_bounds__(NT_MAX, NT_MAX == 256 ? 4 : 1)
     }
 #pragma unroll 1
     while (pc.ok && pc.l == l) {
-      const StA an = load_a(pn, lvl, lsl, lane, deg8, desc);  // consumed in the next iteration
+      Pos pa = pn;
+      if (pa.ok) advance<true>(pa, lsl, n_levels, warp, nw);
+      const StA aa2 = load_a(pa, lvl, lsl, lane, warp, nw, deg8, desc);  // consumed two iterations from now
 
-      // ---- the current slice's register window: all loads first ----
+      // ---- the current slice's register window, out of the warp's stage ----
       const int deg = slice_degree(ac, L.out_ptr), s = ac.s;
       const int dmax = slice_dmax8(ac.d);  // 255 = "255 or more"
       int dstc[KU];
       float wc[KU];
-      // branch-free: lanes without a k-th arc re-read the slice's first arc (a valid, cached address) and
-      // ignore the value -- cheaper than a reconvergence point per column
-      for_columns<0>(ac.d, deg, lane, [&](auto kc, bool on, int a) {
-        constexpr int k = decltype(kc)::value;
-        const int aa = on ? a : ac.d.x;
-        dstc[k] = __ldg(dst_out + aa);
-        wc[k] = SC ? __ldg(arc_scores + aa) : 0.0f;
-        if (TH) wc[k] += th[__ldg(label_out + aa)];
-      });
+      cp_async_wait_all();
+      __syncwarp();
+      {
+        // branch-free: lanes without a k-th arc re-read the slice's first arc and ignore the value --
+        // cheaper than a reconvergence point per column
+        const int32_t* const sd = stage + (ac.d.x & 3);
+        const float* const sw = reinterpret_cast<const float*>(sd + SA);
+        const int32_t* const sl = sd + (SC ? 2 : 1) * SA;
+        for_columns<0>(ac.d, deg, lane, [&](auto kc, bool on, int) {
+          constexpr int k = decltype(kc)::value;
+          const int o = on ? col_start<k>(ac.d) + lane : 0;
+          dstc[k] = sd[o];
+          wc[k] = SC ? sw[o] : 0.0f;
+          if (TH) wc[k] += th[on ? sl[o] : 0];  // an empty slice stages nothing: no stale label may index theta
+        });
+      }
+      __syncwarp();  // every lane has its columns: the stage is free for the next slice
+      if (pn.ok) issue(an.d);
       // destinations' DP values: from the ring, straight-line; the rare ones beyond it are patched afterwards
       RingT rv[KU];
       bool any_slow = false;
@@ -497,8 +571,9 @@ __global__ void __launch_bounds__(NT_MAX, NT_MAX == 256 ? 4 : 1)
 
       // ---- rotate the pipeline ----
       pc = pn;
-      if (pn.ok) advance<true>(pn, lsl, n_levels, warp, nw);
+      pn = pa;
       ac = an;
+      an = aa2;
     }
     __syncthreads();
   }
@@ -508,7 +583,7 @@ __global__ void __launch_bounds__(NT_MAX, NT_MAX == 256 ? 4 : 1)
 // flow pass
 // =====================================================================================
 template <bool DTH, bool ALPHA, typename OT, int NT_MAX>
-__global__ void __launch_bounds__(NT_MAX, NT_MAX == 256 ? SELL_FLOW_MIN_BLOCKS : 1)
+__global__ void __launch_bounds__(NT_MAX, NT_MAX == 128 ? 7 : NT_MAX == 256 ? SELL_FLOW_MIN_BLOCKS : 1)
     sell_flow_kernel(const nfst_packed_lattices_t L, const int32_t* __restrict__ ids, int W, int max_levels,
                      int dtheta_smem, int far, const float* cond, const float* __restrict__ grad_logz, float* post,
                      const OT* __restrict__ beta, const OT* __restrict__ logz, OT* __restrict__ alpha,
@@ -531,6 +606,14 @@ __global__ void __launch_bounds__(NT_MAX, NT_MAX == 256 ? SELL_FLOW_MIN_BLOCKS :
   if (DTH && dtheta_smem) {
     hist = reinterpret_cast<float*>(lsl + lvl_words);
     for (int i = tid; i < L.vocab; i += blockDim.x) hist[i] = 0.0f;
+  }
+  // per-warp stage: [dst | cond | labels (DTH)], SA elements each
+  int32_t* stage;
+  {
+    size_t o = static_cast<size_t>(W) * 4 + 2 * static_cast<size_t>(lvl_words) * 4;
+    if (DTH && dtheta_smem) o += static_cast<size_t>(L.vocab) * 4;
+    o = (o + 15) & ~static_cast<size_t>(15);
+    stage = reinterpret_cast<int32_t*>(sell_smem + o) + warp * ((2 + DTH) * SA);
   }
   __syncthreads();
   const int mask = W - 1;
@@ -560,12 +643,20 @@ __global__ void __launch_bounds__(NT_MAX, NT_MAX == 256 ? SELL_FLOW_MIN_BLOCKS :
   };
   const bool read_far = far || ALPHA;
 
+  // pipeline as in the pull pass: current slice staged, next slice's copy in flight, descriptors two ahead.
+  // cond may be the same buffer as post: an arc's conditional is staged before its own posterior is written
+  // (the 16-byte superset may re-read a neighbour slice's arcs, whose values are ignored).
+  auto issue = [&](const int4& d) {
+    stage_issue<true, DTH>(d, lane, L.n_arcs, stage, dst_out, cond, label_out);
+  };
   Pos pc, pn;
-  pc.l = 0; pc.j = warp - nw; pc.ok = false;
+  pc.l = 0; pc.j = -1; pc.ok = false;
   advance<false>(pc, lsl, n_levels, warp, nw);
   pn = pc;
   if (pn.ok) advance<false>(pn, lsl, n_levels, warp, nw);
-  StA ac = load_a(pc, lvl, lsl, lane, deg8, desc);
+  StA ac = load_a(pc, lvl, lsl, lane, warp, nw, deg8, desc);
+  StA an = load_a(pn, lvl, lsl, lane, warp, nw, deg8, desc);
+  if (pc.ok) issue(ac.d);
 
 #pragma unroll 1
   for (int l = 0; l < n_levels; ++l) {
@@ -573,23 +664,33 @@ __global__ void __launch_bounds__(NT_MAX, NT_MAX == 256 ? SELL_FLOW_MIN_BLOCKS :
     const int lim2 = min(lim, last0);  // ring pushes need dst < lim2
 #pragma unroll 1
     while (pc.ok && pc.l == l) {
-      const StA an = load_a(pn, lvl, lsl, lane, deg8, desc);  // consumed in the next iteration
+      Pos pa = pn;
+      if (pa.ok) advance<false>(pa, lsl, n_levels, warp, nw);
+      const StA aa2 = load_a(pa, lvl, lsl, lane, warp, nw, deg8, desc);  // consumed two iterations from now
 
       const int deg = slice_degree(ac, L.out_ptr), s = ac.s;
       const int dmax = slice_dmax8(ac.d);
-      // flow that reached s through global memory (complete: earlier levels are done); issued with the
-      // column loads so that it costs no latency of its own
+      // flow that reached s through global memory (complete: earlier levels are done)
       float g_far = 0.0f;
       if (read_far && s != 0x7fffffff) g_far = *reinterpret_cast<volatile float*>(gamma_far + s);
       int dstc[KU], labc[KU];
       float cc[KU];
-      for_columns<0>(ac.d, deg, lane, [&](auto kc, bool on, int a) {  // branch-free, see the pull pass
-        constexpr int k = decltype(kc)::value;
-        const int aa = on ? a : ac.d.x;
-        dstc[k] = __ldg(dst_out + aa);
-        cc[k] = cond[aa];
-        labc[k] = DTH ? __ldg(label_out + aa) : 0;
-      });
+      cp_async_wait_all();
+      __syncwarp();
+      {
+        const int32_t* const sd = stage + (ac.d.x & 3);
+        const float* const sc = reinterpret_cast<const float*>(sd + SA);
+        const int32_t* const sl = sd + 2 * SA;
+        for_columns<0>(ac.d, deg, lane, [&](auto kc, bool on, int) {  // branch-free, see the pull pass
+          constexpr int k = decltype(kc)::value;
+          const int o = on ? col_start<k>(ac.d) + lane : 0;
+          dstc[k] = sd[o];
+          cc[k] = sc[o];
+          labc[k] = DTH ? sl[o] : 0;
+        });
+      }
+      __syncwarp();  // the stage is free for the next slice
+      if (pn.ok) issue(an.d);
       float gs = 0.0f;
       if (s != 0x7fffffff) {
         // every arc into s comes from a shallower level: gamma[s] is final; free the slot
@@ -660,8 +761,9 @@ __global__ void __launch_bounds__(NT_MAX, NT_MAX == 256 ? SELL_FLOW_MIN_BLOCKS :
       }
 
       pc = pn;
-      if (pn.ok) advance<false>(pn, lsl, n_levels, warp, nw);
+      pn = pa;
       ac = an;
+      an = aa2;
     }
     __syncthreads();
   }
@@ -673,18 +775,22 @@ __global__ void __launch_bounds__(NT_MAX, NT_MAX == 256 ? SELL_FLOW_MIN_BLOCKS :
   }
 }
 
-size_t pull_smem(int W, int max_levels, int vocab, int ring_bytes, bool theta_smem) {
+size_t pull_smem(int W, int max_levels, int vocab, int ring_bytes, bool theta_smem, int threads, int n_staged) {
   size_t o = static_cast<size_t>(W) * ring_bytes;
   o += 2 * static_cast<size_t>((max_levels + 2 + 3) & ~3) * 4;
   if (theta_smem) o += static_cast<size_t>(vocab) * 4;
-  return (o + 15) & ~static_cast<size_t>(15);
+  o = (o + 15) & ~static_cast<size_t>(15);
+  return o + static_cast<size_t>(threads / 32) * n_staged * SA * 4;  // per-warp stages
 }
-size_t flow_smem(int W, int max_levels, int vocab, bool dtheta_smem) {
+size_t flow_smem(int W, int max_levels, int vocab, bool dtheta_smem, int threads, int n_staged) {
   size_t o = static_cast<size_t>(W) * 4;
   o += 2 * static_cast<size_t>((max_levels + 2 + 3) & ~3) * 4;
   if (dtheta_smem) o += static_cast<size_t>(vocab) * 4;
-  return (o + 15) & ~static_cast<size_t>(15);
+  o = (o + 15) & ~static_cast<size_t>(15);
+  return o + static_cast<size_t>(threads / 32) * n_staged * SA * 4;
 }
+
+bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 template <typename K>
 int prepare(K kernel, size_t smem) {
@@ -719,7 +825,10 @@ int launch_pull(const nfst_packed_lattices_t* lat, const nfst_launch_t* launch, 
                 OT* logz, float* cond, float* delta, int32_t* backptr, float* vit, cudaStream_t stream) {
   const bool has_sc = sc->arc_scores != nullptr, has_th = sc->theta != nullptr;
   const bool th_smem = has_th && lat->vocab <= NFST_THETA_SMEM_MAX;
-  const size_t smem = pull_smem(launch->window_states, launch->n_levels, lat->vocab, TROP ? 4 : static_cast<int>(sizeof(OT)), th_smem);
+  const size_t smem = pull_smem(launch->window_states, launch->n_levels, lat->vocab, TROP ? 4 : static_cast<int>(sizeof(OT)), th_smem,
+                                launch->block_threads, 1 + (has_sc ? 1 : 0) + (has_th ? 1 : 0));
+  if (!aligned16(lat->dst_out) || !aligned16(sc->arc_scores) || (has_th && !aligned16(lat->label_out)))
+    return nfst_fail_msg(NFST_ERR_BAD_ARG, "dst_out, label_out and arc_scores must be 16-byte aligned (they are staged with 16-byte copies)");
   if (smem > 227 * 1024) return nfst_fail_msg(NFST_ERR_TOO_LARGE, "sliced-column window needs %zu bytes of shared memory", smem);
 #define SELL_PULL_NT(SCv, THv, NTv)                                                                               \
   do {                                                                                                            \
@@ -732,6 +841,7 @@ int launch_pull(const nfst_packed_lattices_t* lat, const nfst_launch_t* launch, 
 #define SELL_PULL(SCv, THv)                                                                                       \
   do {                                                                                                            \
     if (big_blocks(launch)) SELL_PULL_NT(SCv, THv, 1024);                                                         \
+    else if (launch->block_threads <= 128) SELL_PULL_NT(SCv, THv, 128);                                           \
     else SELL_PULL_NT(SCv, THv, 256);                                                                             \
   } while (0)
   if (has_sc && has_th) SELL_PULL(true, true);
@@ -750,8 +860,10 @@ extern "C" {
 size_t nfst_sell_smem_bytes(const nfst_launch_t* launch, int32_t vocab, int pass, int with_trop, int with_table) {
   if (!launch) return 0;
   const bool tab = with_table && vocab <= NFST_THETA_SMEM_MAX;
-  return pass == 0 ? pull_smem(launch->window_states, launch->n_levels, vocab, (with_trop || !launch->state_f64) ? 4 : 8, tab)
-                   : flow_smem(launch->window_states, launch->n_levels, vocab, tab);
+  // upper bound: three staged arrays per warp (dst, scores or conditionals, labels)
+  return pass == 0 ? pull_smem(launch->window_states, launch->n_levels, vocab, (with_trop || !launch->state_f64) ? 4 : 8, tab,
+                               launch->block_threads, 3)
+                   : flow_smem(launch->window_states, launch->n_levels, vocab, tab, launch->block_threads, 3);
 }
 
 int nfst_sell_pull_f32(const nfst_packed_lattices_t* lat, const nfst_launch_t* launch, const nfst_scores_t* scores,
@@ -802,11 +914,14 @@ int nfst_sell_flow_f32(const nfst_packed_lattices_t* lat, const nfst_launch_t* l
   if (launch->n_ids == 0) return 0;
   cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
   const bool dth_smem = dtheta && lat->vocab <= NFST_THETA_SMEM_MAX;
-  const size_t smem = flow_smem(launch->window_states, launch->n_levels, lat->vocab, dth_smem);
+  const size_t smem = flow_smem(launch->window_states, launch->n_levels, lat->vocab, dth_smem, launch->block_threads, dtheta ? 3 : 2);
+  if (!aligned16(lat->dst_out) || !aligned16(cond) || (dtheta && !aligned16(lat->label_out)))
+    return nfst_fail_msg(NFST_ERR_BAD_ARG, "dst_out, label_out and cond must be 16-byte aligned (they are staged with 16-byte copies)");
   if (smem > 227 * 1024) return nfst_fail_msg(NFST_ERR_TOO_LARGE, "sliced-column window needs %zu bytes of shared memory", smem);
 #define SELL_FLOW(DTHv, ALv, OT)                                                                                  \
   do {                                                                                                            \
     if (big_blocks(launch)) SELL_FLOW_NT(DTHv, ALv, OT, 1024);                                                    \
+    else if (launch->block_threads <= 128) SELL_FLOW_NT(DTHv, ALv, OT, 128);                                      \
     else SELL_FLOW_NT(DTHv, ALv, OT, 256);                                                                        \
   } while (0)
 #define SELL_FLOW_NT(DTHv, ALv, OT, NTv)                                                                          \
