@@ -52,6 +52,13 @@ namespace {
 #ifndef SELL_FLOW_MIN_BLOCKS
 #define SELL_FLOW_MIN_BLOCKS 4
 #endif
+// resident blocks the pull kernels are compiled for (register budget): 128-thread / 256-thread instantiations
+#ifndef SELL_PULL_MIN_BLOCKS_128
+#define SELL_PULL_MIN_BLOCKS_128 7
+#endif
+#ifndef SELL_PULL_MIN_BLOCKS_256
+#define SELL_PULL_MIN_BLOCKS_256 4
+#endif
 constexpr int KU = 8;  // arc columns held in registers per slice; deeper columns take the tail loops
 constexpr int TW = 4;  // columns per tail window (loads issued together)
 constexpr float kLog2e = 1.4426950408889634f;
@@ -115,20 +122,24 @@ __device__ __forceinline__ void advance(Pos& p, const int* lsl, int n_levels, in
   p.ok = false;
 }
 
-__device__ __forceinline__ StA load_a(const Pos& p, const int* lvl, const int* lsl, int lane, int warp, int nw,
-                                      const uint8_t* __restrict__ deg8, const int4* __restrict__ desc) {
+// ---- slice meta data through shared memory ----
+// The descriptor and the degree bytes of a slice travel like its arc columns: cp.async into a per-warp buffer two
+// slices ahead (two buffers, by the parity of the warp's slice counter), read when the slice is reached.
+// Nothing about the slices ahead is carried in registers: at 64 registers ptxas spilled exactly those
+// loop-carried values, and a local-memory reload sits on every slice's critical path.
+constexpr int META = 16;  // ints: descriptor (4) + the word-aligned superset of 32 degree bytes (<= 9 words)
+__device__ __forceinline__ void meta_issue(const Pos& p, const int* lvl, const int* lsl, int lane, int warp, int nw,
+                                           int n_states, const uint8_t* __restrict__ deg8,
+                                           const int4* __restrict__ desc, int32_t* buf);
+__device__ __forceinline__ StA meta_read(const Pos& p, const int* lvl, int lane, int warp, int nw, const int32_t* buf) {
   StA a;
+  const int first = lvl[p.l] + 32 * slice_of(p, warp, nw);
+  a.d = *reinterpret_cast<const int4*>(buf);
   a.s = 0x7fffffff;
   a.degb = 0;
-  a.d = make_int4(0, 0, 0, 0);
-  if (p.ok) {
-    const int jj = slice_of(p, warp, nw);
-    const int first = lvl[p.l] + 32 * jj;
-    if (first + lane < lvl[p.l + 1]) {
-      a.s = first + lane;
-      a.degb = __ldg(deg8 + a.s);
-    }
-    a.d = __ldg(desc + lsl[p.l] + jj);
+  if (first + lane < lvl[p.l + 1]) {
+    a.s = first + lane;
+    a.degb = reinterpret_cast<const uint8_t*>(buf + 4)[(first & 3) + lane];
   }
   return a;
 }
@@ -142,12 +153,21 @@ __device__ __forceinline__ int slice_degree(const StA& a, const int32_t* __restr
 // arrays.  Straight-line and predicated per lane (on = the lane's state has a k-th arc): no warp vote, no
 // branch on the slice's largest degree -- the branches cost more in reconvergence and register moves than the
 // idle columns do.
-template <int K, typename F>
+template <int K, int N, typename F>
 __device__ __forceinline__ void for_columns(const int4& d, int deg, int lane, F&& f) {
-  if constexpr (K < KU) {
+  if constexpr (K < N) {
     f(std::integral_constant<int, K>{}, deg > K, d.x + col_start<K>(d) + lane);
-    for_columns<K + 1>(d, deg, lane, f);
+    for_columns<K + 1, N>(d, deg, lane, f);
   }
+}
+// The per-slice code exists twice: for slices whose states have at most KL arcs (degrees descend along a level:
+// most slices of a level) and for the others.  One warp-uniform branch per phase picks the instantiation; inside
+// it the columns stay straight-line, so their loads and arithmetic interleave.
+constexpr int KL = 4;
+template <typename F>
+__device__ __forceinline__ void by_width(int dmax, F&& f) {
+  if (dmax <= KL) f(std::integral_constant<int, KL>{});
+  else f(std::integral_constant<int, KU>{});
 }
 // ---- per-warp staging of a slice's arc columns (cp.async, 16 bytes per lane) ----
 // The columns 0..KU-1 of a slice lie inside its first 32*KU arcs.  Each warp owns one stage of SA elements per
@@ -168,28 +188,53 @@ template <bool A1, bool A2>
 __device__ __forceinline__ void stage_issue(const int4& d, int lane, int n_arcs, int32_t* stage, const int32_t* g0,
                                             const void* g1, const void* g2) {
   const int base = d.x & ~3;
-  const int n16 = (min(d.y, d.x + 32 * KU) - base + 3) >> 2;  // <= 65
+  const int n16 = (min(d.y, d.x + 32 * KU) - base + 3) >> 2;  // <= 65, the same for the whole warp
   const int32_t* h1 = static_cast<const int32_t*>(g1);
   const int32_t* h2 = static_cast<const int32_t*>(g2);
-#pragma unroll
-  for (int r = 0; r < 3; ++r) {
-    const int c = lane + 32 * r;
-    if (c < n16) {
-      const int e0 = base + 4 * c;
-      if (e0 + 4 <= n_arcs) {
-        cp_async_16(stage + 4 * c, g0 + e0);
-        if (A1) cp_async_16(stage + SA + 4 * c, h1 + e0);
-        if (A2) cp_async_16(stage + 2 * SA + 4 * c, h2 + e0);
-      } else {
-        for (int j = 0; j < 4; ++j)
-          if (e0 + j < n_arcs) {
-            cp_async_4(stage + 4 * c + j, g0 + e0 + j);
-            if (A1) cp_async_4(stage + SA + 4 * c + j, h1 + e0 + j);
-            if (A2) cp_async_4(stage + 2 * SA + 4 * c + j, h2 + e0 + j);
-          }
+  if (base + 4 * n16 <= n_arcs) {
+    // every slice but the very last of the batch: whole 16-byte chunks; a slice of average size needs one
+    // round, the second and third run under warp-uniform branches
+    const int e0 = base + 4 * lane;
+    int32_t* const st = stage + 4 * lane;
+    if (lane < n16) {
+      cp_async_16(st, g0 + e0);
+      if (A1) cp_async_16(st + SA, h1 + e0);
+      if (A2) cp_async_16(st + 2 * SA, h2 + e0);
+    }
+    if (n16 > 32) {
+      if (lane + 32 < n16) {
+        cp_async_16(st + 128, g0 + e0 + 128);
+        if (A1) cp_async_16(st + SA + 128, h1 + e0 + 128);
+        if (A2) cp_async_16(st + 2 * SA + 128, h2 + e0 + 128);
+      }
+      if (lane + 64 < n16) {
+        cp_async_16(st + 256, g0 + e0 + 256);
+        if (A1) cp_async_16(st + SA + 256, h1 + e0 + 256);
+        if (A2) cp_async_16(st + 2 * SA + 256, h2 + e0 + 256);
+      }
+    }
+  } else {
+    for (int j = lane; j < 4 * n16; j += 32) {
+      const int e = base + j;
+      if (e < n_arcs) {
+        cp_async_4(stage + j, g0 + e);
+        if (A1) cp_async_4(stage + SA + j, h1 + e);
+        if (A2) cp_async_4(stage + 2 * SA + j, h2 + e);
       }
     }
   }
+}
+
+__device__ __forceinline__ void meta_issue(const Pos& p, const int* lvl, const int* lsl, int lane, int warp, int nw,
+                                           int n_states, const uint8_t* __restrict__ deg8,
+                                           const int4* __restrict__ desc, int32_t* buf) {
+  // one 4-byte copy per lane, no divergent branch: lanes 0..3 the descriptor, lanes 4..12 the degree words
+  const int jj = slice_of(p, warp, nw);
+  const int first = lvl[p.l] + 32 * jj;
+  const int w = (first >> 2) + lane - 4;  // out_deg8 is 4-byte aligned and padded to a whole word
+  const int32_t* const src = lane < 4 ? reinterpret_cast<const int32_t*>(desc + lsl[p.l] + jj) + lane
+                                      : reinterpret_cast<const int32_t*>(deg8) + w;
+  if (lane < 4 || (lane < 13 && 4 * w < n_states)) cp_async_4(buf + lane, src);
 }
 
 // rare path: an arc longer than the shared-memory ring (kept out of line: no 64-bit address arithmetic in
@@ -257,7 +302,7 @@ __device__ __forceinline__ void lse_join(RT& m, float& s, RT m2, float s2) {
 // fit the 148 SMs in ONE wave; at 64 registers ptxas spills the loop-carried slice descriptors and every reload
 // is a local-memory round trip on the slice's critical path -- measured 1.39 vs 0.65 ms); 256: 80 registers
 template <bool TROP, bool SC, bool TH, bool COND, typename OT, int NT_MAX>
-__global__ void __launch_bounds__(NT_MAX, NT_MAX == 128 ? 7 : NT_MAX == 256 ? 3 : 1)
+__global__ void __launch_bounds__(NT_MAX, NT_MAX == 128 ? SELL_PULL_MIN_BLOCKS_128 : NT_MAX == 256 ? SELL_PULL_MIN_BLOCKS_256 : 1)
     sell_pull_kernel(const nfst_packed_lattices_t L, const int32_t* __restrict__ ids, int W, int max_levels,
                      int theta_smem, int far, const float* __restrict__ arc_scores, const float* __restrict__ theta,
                      OT* beta, OT* __restrict__ logz, float* __restrict__ cond, float* delta,
@@ -289,7 +334,7 @@ __global__ void __launch_bounds__(NT_MAX, NT_MAX == 128 ? 7 : NT_MAX == 256 ? 3 
     size_t o = static_cast<size_t>(W) * sizeof(RingT) + 2 * static_cast<size_t>(lvl_words) * 4;
     if (TH && theta_smem) o += static_cast<size_t>(L.vocab) * 4;
     o = (o + 15) & ~static_cast<size_t>(15);
-    stage = reinterpret_cast<int32_t*>(sell_smem + o) + warp * ((1 + SC + TH) * SA);
+    stage = reinterpret_cast<int32_t*>(sell_smem + o) + warp * ((1 + SC + TH) * SA + 2 * META) + 2 * META;
   }
   __syncthreads();
   const int mask = W - 1;
@@ -348,9 +393,13 @@ __global__ void __launch_bounds__(NT_MAX, NT_MAX == 128 ? 7 : NT_MAX == 256 ? 3 
   advance<true>(pc, lsl, n_levels, warp, nw);
   pn = pc;
   if (pn.ok) advance<true>(pn, lsl, n_levels, warp, nw);
-  StA ac = load_a(pc, lvl, lsl, lane, warp, nw, deg8, desc);
-  StA an = load_a(pn, lvl, lsl, lane, warp, nw, deg8, desc);
-  if (pc.ok) issue(ac.d);
+  int32_t* const meta = stage - 2 * META;  // two meta buffers in front of the warp's arc stage
+  int par = 0;                             // parity of the warp's slice counter: meta buffer of the current slice
+  if (pc.ok) meta_issue(pc, lvl, lsl, lane, warp, nw, L.n_states, deg8, desc, meta);
+  if (pn.ok) meta_issue(pn, lvl, lsl, lane, warp, nw, L.n_states, deg8, desc, meta + META);
+  cp_async_wait_all();
+  __syncwarp();
+  if (pc.ok) issue(*reinterpret_cast<const int4*>(meta));
   const int lim_cap = last0;  // ring reads need dst < min(lim, last0)
 
 #pragma unroll 1
@@ -363,41 +412,46 @@ __global__ void __launch_bounds__(NT_MAX, NT_MAX == 128 ? 7 : NT_MAX == 256 ? 3 
     while (pc.ok && pc.l == l) {
       Pos pa = pn;
       if (pa.ok) advance<true>(pa, lsl, n_levels, warp, nw);
-      const StA aa2 = load_a(pa, lvl, lsl, lane, warp, nw, deg8, desc);  // consumed two iterations from now
+      // everything issued in the previous iteration has landed: this slice's arcs, the next slice's meta data
+      cp_async_wait_all();
+      __syncwarp();
+      const StA ac = meta_read(pc, lvl, lane, warp, nw, meta + par * META);
 
       // ---- the current slice's register window, out of the warp's stage ----
       const int deg = slice_degree(ac, L.out_ptr), s = ac.s;
       const int dmax = slice_dmax8(ac.d);  // 255 = "255 or more"
       int dstc[KU];
       float wc[KU];
-      cp_async_wait_all();
-      __syncwarp();
-      {
+      by_width(dmax, [&](auto nc) {
+        constexpr int NC = decltype(nc)::value;
         // branch-free: lanes without a k-th arc re-read the slice's first arc and ignore the value --
         // cheaper than a reconvergence point per column
         const int32_t* const sd = stage + (ac.d.x & 3);
         const float* const sw = reinterpret_cast<const float*>(sd + SA);
         const int32_t* const sl = sd + (SC ? 2 : 1) * SA;
-        for_columns<0>(ac.d, deg, lane, [&](auto kc, bool on, int) {
+        for_columns<0, NC>(ac.d, deg, lane, [&](auto kc, bool on, int) {
           constexpr int k = decltype(kc)::value;
           const int o = on ? col_start<k>(ac.d) + lane : 0;
           dstc[k] = sd[o];
           wc[k] = SC ? sw[o] : 0.0f;
           if (TH) wc[k] += th[on ? sl[o] : 0];  // an empty slice stages nothing: no stale label may index theta
         });
-      }
-      __syncwarp();  // every lane has its columns: the stage is free for the next slice
-      if (pn.ok) issue(an.d);
+      });
+      __syncwarp();  // every lane has its columns and meta data: both buffers are free
+      if (pn.ok) issue(*reinterpret_cast<const int4*>(meta + (par ^ 1) * META));
+      if (pa.ok) meta_issue(pa, lvl, lsl, lane, warp, nw, L.n_states, deg8, desc, meta + par * META);
+      by_width(dmax, [&](auto nc) {
+      constexpr int NC = decltype(nc)::value;
       // destinations' DP values: from the ring, straight-line; the rare ones beyond it are patched afterwards
       RingT rv[KU];
       bool any_slow = false;
-      for_columns<0>(ac.d, deg, lane, [&](auto kc, bool on, int) {
+      for_columns<0, NC>(ac.d, deg, lane, [&](auto kc, bool on, int) {
         constexpr int k = decltype(kc)::value;
         rv[k] = ring[dstc[k] & mask];
         any_slow |= on && dstc[k] >= lim2;
       });
       if (any_slow) {
-        for_columns<0>(ac.d, deg, lane, [&](auto kc, bool on, int) {
+        for_columns<0, NC>(ac.d, deg, lane, [&](auto kc, bool on, int) {
           constexpr int k = decltype(kc)::value;
           if (on && dstc[k] >= lim2) rv[k] = static_cast<RingT>(nbr_slow(dstc[k]));
         });
@@ -411,24 +465,24 @@ __global__ void __launch_bounds__(NT_MAX, NT_MAX == 128 ? 7 : NT_MAX == 256 ? 3 
         RT t0 = static_cast<RT>(wc[0]) + static_cast<RT>(rv[0]);
         if (deg > 0 && !(t0 > static_cast<RT>(kFloor))) {  // rare: the first arc scores -inf -- take the largest
           t0 = static_cast<RT>(kFloor);
-          for_columns<0>(ac.d, deg, lane, [&](auto kc, bool on, int) {
+          for_columns<0, NC>(ac.d, deg, lane, [&](auto kc, bool on, int) {
             constexpr int k = decltype(kc)::value;
             const RT t = static_cast<RT>(wc[k]) + static_cast<RT>(rv[k]);
             if (on && t > t0) t0 = t;
           });
         }
         float tf[KU];
-        for_columns<0>(ac.d, deg, lane, [&](auto kc, bool on, int) {
+        for_columns<0, NC>(ac.d, deg, lane, [&](auto kc, bool on, int) {
           constexpr int k = decltype(kc)::value;
           const float off = static_cast<float>(static_cast<RT>(wc[k]) + static_cast<RT>(rv[k]) - t0);
           tf[k] = on ? off : kFloor;
         });
         float mf = kFloor;
 #pragma unroll
-        for (int k = 0; k < KU; ++k) mf = fmaxf(mf, tf[k]);
+        for (int k = 0; k < NC; ++k) mf = fmaxf(mf, tf[k]);
         float e[KU];
         float sum = 0.0f;
-        for_columns<0>(ac.d, deg, lane, [&](auto kc, bool, int) {
+        for_columns<0, NC>(ac.d, deg, lane, [&](auto kc, bool, int) {
           constexpr int k = decltype(kc)::value;
           e[k] = ex2_approx((tf[k] - mf) * kLog2e);  // idle lanes / -inf arcs: exp(-huge) = 0
           sum += e[k];
@@ -438,7 +492,7 @@ __global__ void __launch_bounds__(NT_MAX, NT_MAX == 128 ? 7 : NT_MAX == 256 ? 3 
         // further columns: merged online into (m, sum); the window's exponentials are rescaled at the end
         const RT m_reg = m;
         int col_tail = 0;
-        if (dmax > KU) {
+        if (NC == KU && dmax > KU) {
           int col = ac.d.x + col_start<KU - 1>(ac.d) + __popc(__ballot_sync(0xffffffffu, deg > KU - 1));
           col_tail = col;
           int k = KU;
@@ -478,11 +532,11 @@ __global__ void __launch_bounds__(NT_MAX, NT_MAX == 128 ? 7 : NT_MAX == 256 ? 3 
         if (COND) {
           const float inv = sum > 0.0f ? __frcp_rn(sum) : 0.0f;
           const float inv_reg = inv * ex2_approx(static_cast<float>(m_reg - m) * kLog2e);
-          for_columns<0>(ac.d, deg, lane, [&](auto kc, bool on, int a) {
+          for_columns<0, NC>(ac.d, deg, lane, [&](auto kc, bool on, int a) {
             constexpr int k = decltype(kc)::value;
             if (on) cond[a] = e[k] * inv_reg;
           });
-          if (dmax > KU) {
+          if (NC == KU && dmax > KU) {
             int col = col_tail, k = KU;
             tail_windows(deg, col, k, lane, [&](const int (&a)[TW], const bool (&on)[TW]) {
               RT v[TW];
@@ -513,7 +567,7 @@ __global__ void __launch_bounds__(NT_MAX, NT_MAX == 128 ? 7 : NT_MAX == 256 ? 3 
       } else {
         float best = 0.0f;
         int arg = -1;
-        for_columns<0>(ac.d, deg, lane, [&](auto kc, bool on, int a) {
+        for_columns<0, NC>(ac.d, deg, lane, [&](auto kc, bool on, int a) {
           constexpr int k = decltype(kc)::value;
           const float c = __fadd_rn(wc[k], rv[k]);
           if (on && (arg < 0 || c > best)) {  // strict: arcs of a state come in label order
@@ -521,7 +575,7 @@ __global__ void __launch_bounds__(NT_MAX, NT_MAX == 128 ? 7 : NT_MAX == 256 ? 3 
             arg = a;
           }
         });
-        if (dmax > KU) {
+        if (NC == KU && dmax > KU) {
           int col = ac.d.x + col_start<KU - 1>(ac.d) + __popc(__ballot_sync(0xffffffffu, deg > KU - 1)), k = KU;
           tail_windows(deg, col, k, lane, [&](const int (&a)[TW], const bool (&on)[TW]) {
             RT v[TW];
@@ -569,11 +623,12 @@ __global__ void __launch_bounds__(NT_MAX, NT_MAX == 128 ? 7 : NT_MAX == 256 ? 3 
         }
       }
 
+      });  // by_width
+
       // ---- rotate the pipeline ----
       pc = pn;
       pn = pa;
-      ac = an;
-      an = aa2;
+      par ^= 1;
     }
     __syncthreads();
   }
@@ -613,7 +668,7 @@ __global__ void __launch_bounds__(NT_MAX, NT_MAX == 128 ? 7 : NT_MAX == 256 ? SE
     size_t o = static_cast<size_t>(W) * 4 + 2 * static_cast<size_t>(lvl_words) * 4;
     if (DTH && dtheta_smem) o += static_cast<size_t>(L.vocab) * 4;
     o = (o + 15) & ~static_cast<size_t>(15);
-    stage = reinterpret_cast<int32_t*>(sell_smem + o) + warp * ((2 + DTH) * SA);
+    stage = reinterpret_cast<int32_t*>(sell_smem + o) + warp * ((2 + DTH) * SA + 2 * META) + 2 * META;
   }
   __syncthreads();
   const int mask = W - 1;
@@ -654,9 +709,13 @@ __global__ void __launch_bounds__(NT_MAX, NT_MAX == 128 ? 7 : NT_MAX == 256 ? SE
   advance<false>(pc, lsl, n_levels, warp, nw);
   pn = pc;
   if (pn.ok) advance<false>(pn, lsl, n_levels, warp, nw);
-  StA ac = load_a(pc, lvl, lsl, lane, warp, nw, deg8, desc);
-  StA an = load_a(pn, lvl, lsl, lane, warp, nw, deg8, desc);
-  if (pc.ok) issue(ac.d);
+  int32_t* const meta = stage - 2 * META;  // two meta buffers in front of the warp's arc stage
+  int par = 0;                             // parity of the warp's slice counter: meta buffer of the current slice
+  if (pc.ok) meta_issue(pc, lvl, lsl, lane, warp, nw, L.n_states, deg8, desc, meta);
+  if (pn.ok) meta_issue(pn, lvl, lsl, lane, warp, nw, L.n_states, deg8, desc, meta + META);
+  cp_async_wait_all();
+  __syncwarp();
+  if (pc.ok) issue(*reinterpret_cast<const int4*>(meta));
 
 #pragma unroll 1
   for (int l = 0; l < n_levels; ++l) {
@@ -666,7 +725,10 @@ __global__ void __launch_bounds__(NT_MAX, NT_MAX == 128 ? 7 : NT_MAX == 256 ? SE
     while (pc.ok && pc.l == l) {
       Pos pa = pn;
       if (pa.ok) advance<false>(pa, lsl, n_levels, warp, nw);
-      const StA aa2 = load_a(pa, lvl, lsl, lane, warp, nw, deg8, desc);  // consumed two iterations from now
+      // everything issued in the previous iteration has landed: this slice's arcs, the next slice's meta data
+      cp_async_wait_all();
+      __syncwarp();
+      const StA ac = meta_read(pc, lvl, lane, warp, nw, meta + par * META);
 
       const int deg = slice_degree(ac, L.out_ptr), s = ac.s;
       const int dmax = slice_dmax8(ac.d);
@@ -675,22 +737,22 @@ __global__ void __launch_bounds__(NT_MAX, NT_MAX == 128 ? 7 : NT_MAX == 256 ? SE
       if (read_far && s != 0x7fffffff) g_far = *reinterpret_cast<volatile float*>(gamma_far + s);
       int dstc[KU], labc[KU];
       float cc[KU];
-      cp_async_wait_all();
-      __syncwarp();
-      {
+      by_width(dmax, [&](auto nc) {
+        constexpr int NC = decltype(nc)::value;
         const int32_t* const sd = stage + (ac.d.x & 3);
         const float* const sc = reinterpret_cast<const float*>(sd + SA);
         const int32_t* const sl = sd + 2 * SA;
-        for_columns<0>(ac.d, deg, lane, [&](auto kc, bool on, int) {  // branch-free, see the pull pass
+        for_columns<0, NC>(ac.d, deg, lane, [&](auto kc, bool on, int) {  // branch-free, see the pull pass
           constexpr int k = decltype(kc)::value;
           const int o = on ? col_start<k>(ac.d) + lane : 0;
           dstc[k] = sd[o];
           cc[k] = sc[o];
           labc[k] = DTH ? sl[o] : 0;
         });
-      }
-      __syncwarp();  // the stage is free for the next slice
-      if (pn.ok) issue(an.d);
+      });
+      __syncwarp();  // every lane has its columns and meta data: both buffers are free
+      if (pn.ok) issue(*reinterpret_cast<const int4*>(meta + (par ^ 1) * META));
+      if (pa.ok) meta_issue(pa, lvl, lsl, lane, warp, nw, L.n_states, deg8, desc, meta + par * META);
       float gs = 0.0f;
       if (s != 0x7fffffff) {
         // every arc into s comes from a shallower level: gamma[s] is final; free the slot
@@ -703,8 +765,10 @@ __global__ void __launch_bounds__(NT_MAX, NT_MAX == 128 ? 7 : NT_MAX == 256 ? SE
                               : static_cast<OT>(kNegInf);
         }
       }
+      by_width(dmax, [&](auto nc) {
+      constexpr int NC = decltype(nc)::value;
       bool any_slow = false;
-      for_columns<0>(ac.d, deg, lane, [&](auto kc, bool on, int a) {
+      for_columns<0, NC>(ac.d, deg, lane, [&](auto kc, bool on, int a) {
         constexpr int k = decltype(kc)::value;
         const float p = gs * cc[k];
         if (on) {
@@ -715,11 +779,12 @@ __global__ void __launch_bounds__(NT_MAX, NT_MAX == 128 ? 7 : NT_MAX == 256 ? SE
         }
       });
       if (any_slow) {  // rare: flow into the last level (alpha only) or beyond the ring
-        for_columns<0>(ac.d, deg, lane, [&](auto kc, bool on, int) {
+        for_columns<0, NC>(ac.d, deg, lane, [&](auto kc, bool on, int) {
           constexpr int k = decltype(kc)::value;
           if (on && dstc[k] >= lim2) push(dstc[k], gs * cc[k]);
         });
       }
+      });  // by_width
       if (dmax > KU) {
         int col = ac.d.x + col_start<KU - 1>(ac.d) + __popc(__ballot_sync(0xffffffffu, deg > KU - 1)), k = KU;
         tail_windows(deg, col, k, lane, [&](const int (&a)[TW], const bool (&on)[TW]) {
@@ -762,8 +827,7 @@ __global__ void __launch_bounds__(NT_MAX, NT_MAX == 128 ? 7 : NT_MAX == 256 ? SE
 
       pc = pn;
       pn = pa;
-      ac = an;
-      an = aa2;
+      par ^= 1;
     }
     __syncthreads();
   }
@@ -780,14 +844,14 @@ size_t pull_smem(int W, int max_levels, int vocab, int ring_bytes, bool theta_sm
   o += 2 * static_cast<size_t>((max_levels + 2 + 3) & ~3) * 4;
   if (theta_smem) o += static_cast<size_t>(vocab) * 4;
   o = (o + 15) & ~static_cast<size_t>(15);
-  return o + static_cast<size_t>(threads / 32) * n_staged * SA * 4;  // per-warp stages
+  return o + static_cast<size_t>(threads / 32) * (n_staged * SA + 2 * META) * 4;  // per-warp stages
 }
 size_t flow_smem(int W, int max_levels, int vocab, bool dtheta_smem, int threads, int n_staged) {
   size_t o = static_cast<size_t>(W) * 4;
   o += 2 * static_cast<size_t>((max_levels + 2 + 3) & ~3) * 4;
   if (dtheta_smem) o += static_cast<size_t>(vocab) * 4;
   o = (o + 15) & ~static_cast<size_t>(15);
-  return o + static_cast<size_t>(threads / 32) * n_staged * SA * 4;
+  return o + static_cast<size_t>(threads / 32) * (n_staged * SA + 2 * META) * 4;
 }
 
 bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }

@@ -122,7 +122,7 @@ class PackedLattices:
     )
 
     # arrays the kernels stage with 16-byte copies: kept zero-padded by PAD elements
-    _ARC_FIELDS = ("src_in", "label_in", "in2out", "dst_out", "label_out", "in_ptr", "out_ptr")
+    _ARC_FIELDS = ("src_in", "label_in", "in2out", "dst_out", "label_out", "in_ptr", "out_ptr", "out_deg8")
     PAD = 4
 
     @staticmethod
