@@ -460,21 +460,33 @@ __global__ void __launch_bounds__(NT_MAX, NT_MAX == 128 ? SELL_PULL_MIN_BLOCKS_1
       // ---- DP of the current slice ----
       if (!TROP) {
         // register window: two passes over registers (max, then exponentials)
-        // t_k = w_k + beta[dst_k] in float64; kept as float32 offsets from the first finite one (t0): the
-        // offsets are small numbers, so nothing is lost, and 8 registers hold the window instead of 16
-        RT t0 = static_cast<RT>(wc[0]) + static_cast<RT>(rv[0]);
-        if (deg > 0 && !(t0 > static_cast<RT>(kFloor))) {  // rare: the first arc scores -inf -- take the largest
-          t0 = static_cast<RT>(kFloor);
+        // t_k = w_k + beta[dst_k] is only needed as an offset from a reference arc's t0 (the first arc; every
+        // state with arcs has one).  float32 state: the offset is formed as (beta_k - beta_0) + (w_k - w_0) --
+        // two differences of float32 numbers, each rounded at its own small size (6e-8 relative), so nothing is
+        // lost against the float64 sum, and the per-arc float64 converts and adds (the busiest pipe of this
+        // kernel in ncu) are gone; t0 itself stays float64, once per slice.  float64 state: float64 throughout.
+        float rw = wc[0];
+        RingT rb = rv[0];
+        if (deg > 0 && !(rw + static_cast<float>(rb) > kFloor)) {  // rare: the first arc scores -inf -- take the largest
+          float tbest = kFloor;
+          rw = kFloor;
+          rb = static_cast<RingT>(0);
           for_columns<0, NC>(ac.d, deg, lane, [&](auto kc, bool on, int) {
             constexpr int k = decltype(kc)::value;
-            const RT t = static_cast<RT>(wc[k]) + static_cast<RT>(rv[k]);
-            if (on && t > t0) t0 = t;
+            const float t = wc[k] + static_cast<float>(rv[k]);
+            if (on && t > tbest) {
+              tbest = t;
+              rw = wc[k];
+              rb = rv[k];
+            }
           });
         }
         float tf[KU];
         for_columns<0, NC>(ac.d, deg, lane, [&](auto kc, bool on, int) {
           constexpr int k = decltype(kc)::value;
-          const float off = static_cast<float>(static_cast<RT>(wc[k]) + static_cast<RT>(rv[k]) - t0);
+          float off;
+          if constexpr (sizeof(RingT) == 4) off = (static_cast<float>(rv[k]) - static_cast<float>(rb)) + (wc[k] - rw);
+          else off = static_cast<float>(static_cast<RT>(wc[k]) + static_cast<RT>(rv[k]) - (static_cast<RT>(rw) + static_cast<RT>(rb)));
           tf[k] = on ? off : kFloor;
         });
         float mf = kFloor;
@@ -487,12 +499,23 @@ __global__ void __launch_bounds__(NT_MAX, NT_MAX == 128 ? SELL_PULL_MIN_BLOCKS_1
           e[k] = ex2_approx((tf[k] - mf) * kLog2e);  // idle lanes / -inf arcs: exp(-huge) = 0
           sum += e[k];
         });
-        RT m = mf > kFloor ? t0 + static_cast<RT>(mf) : static_cast<RT>(kFloor);
         if (!(mf > kFloor)) sum = 0.0f;  // no finite arc: every term above was exp(0)
-        // further columns: merged online into (m, sum); the window's exponentials are rescaled at the end
-        const RT m_reg = m;
-        int col_tail = 0;
+        // sinks: beta = 1 (scorers.py:720); a state whose arcs all score -inf: beta = -inf.
+        // beta[s] = beta_0 + (w_0 + max offset + log sum): one rounding at beta's magnitude
+        RingT bv = static_cast<RingT>(0);
+        float inv_reg = sum > 0.0f ? __frcp_rn(sum) : 0.0f;  // scale of the window's exponentials in cond[]
+        if (deg > 0) {
+          const float lg = lg2_approx(sum) * kLn2;
+          if (!(sum > 0.0f)) bv = static_cast<RingT>(kNegInf);
+          else if constexpr (sizeof(RingT) == 4) bv = rb + (rw + (mf + lg));
+          else bv = rb + (static_cast<RT>(rw) + (static_cast<RT>(mf) + static_cast<RT>(lg)));
+        }
+        // further columns (warp-uniform branch, rare): merged online into (m, sum) in float64; what depends on
+        // them is redone inside the branch, so that no float64 value lives outside it
         if (NC == KU && dmax > KU) {
+          RT m = mf > kFloor ? (static_cast<RT>(rw) + static_cast<RT>(rb)) + static_cast<RT>(mf) : static_cast<RT>(kFloor);
+          const RT m_reg = m;
+          int col_tail = 0;
           int col = ac.d.x + col_start<KU - 1>(ac.d) + __popc(__ballot_sync(0xffffffffu, deg > KU - 1));
           col_tail = col;
           int k = KU;
@@ -525,18 +548,10 @@ __global__ void __launch_bounds__(NT_MAX, NT_MAX == 128 ? SELL_PULL_MIN_BLOCKS_1
             }
             if (lane == 0) lse_join(m, sum, hm, hs);
           }
-        }
-        // sinks: beta = 1 (scorers.py:720); a state whose arcs all score -inf: beta = -inf
-        RT bv = static_cast<RT>(0);
-        if (deg > 0) bv = sum > 0.0f ? m + static_cast<RT>(lg2_approx(sum) * kLn2) : static_cast<RT>(kNegInf);
-        if (COND) {
+          if (deg > 0) bv = sum > 0.0f ? static_cast<RingT>(m + static_cast<RT>(lg2_approx(sum) * kLn2)) : static_cast<RingT>(kNegInf);
           const float inv = sum > 0.0f ? __frcp_rn(sum) : 0.0f;
-          const float inv_reg = inv * ex2_approx(static_cast<float>(m_reg - m) * kLog2e);
-          for_columns<0, NC>(ac.d, deg, lane, [&](auto kc, bool on, int a) {
-            constexpr int k = decltype(kc)::value;
-            if (on) cond[a] = e[k] * inv_reg;
-          });
-          if (NC == KU && dmax > KU) {
+          inv_reg = inv * ex2_approx(static_cast<float>(m_reg - m) * kLog2e);
+          if (COND) {
             int col = col_tail, k = KU;
             tail_windows(deg, col, k, lane, [&](const int (&a)[TW], const bool (&on)[TW]) {
               RT v[TW];
@@ -557,6 +572,12 @@ __global__ void __launch_bounds__(NT_MAX, NT_MAX == 128 ? SELL_PULL_MIN_BLOCKS_1
               }
             }
           }
+        }
+        if (COND) {
+          for_columns<0, NC>(ac.d, deg, lane, [&](auto kc, bool on, int a) {
+            constexpr int k = decltype(kc)::value;
+            if (on) cond[a] = e[k] * inv_reg;
+          });
         }
         if (s != 0x7fffffff) {
           // the ring slot of s is only read by shallower levels, i.e. after the level barrier
