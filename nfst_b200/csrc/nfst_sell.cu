@@ -160,14 +160,26 @@ __device__ __forceinline__ void for_columns(const int4& d, int deg, int lane, F&
     for_columns<K + 1, N>(d, deg, lane, f);
   }
 }
-// The per-slice code exists twice: for slices whose states have at most KL arcs (degrees descend along a level:
-// most slices of a level) and for the others.  One warp-uniform branch per phase picks the instantiation; inside
-// it the columns stay straight-line, so their loads and arithmetic interleave.
+// The per-slice code exists in several widths: for slices whose states have at most 2 / 4 / 6 arcs (degrees descend
+// along a level: most slices of a level are narrow) and for the others.  One warp-uniform branch tree per phase
+// picks the instantiation; inside it the columns stay straight-line, so their loads and arithmetic interleave.
+// Four widths for the flow and the tropical pass; two (<= KL, KU) for the log-semiring pull pass, whose per-column
+// code is the longest: with four its loop outgrows the instruction cache (measured 0.563 vs 0.541 ms).
 constexpr int KL = 4;
-template <typename F>
+template <int WIDTHS, typename F>
 __device__ __forceinline__ void by_width(int dmax, F&& f) {
-  if (dmax <= KL) f(std::integral_constant<int, KL>{});
-  else f(std::integral_constant<int, KU>{});
+  if constexpr (WIDTHS == 4) {
+    if (dmax <= 4) {
+      if (dmax <= 2) f(std::integral_constant<int, 2>{});
+      else f(std::integral_constant<int, 4>{});
+    } else {
+      if (dmax <= 6) f(std::integral_constant<int, 6>{});
+      else f(std::integral_constant<int, KU>{});
+    }
+  } else {
+    if (dmax <= KL) f(std::integral_constant<int, KL>{});
+    else f(std::integral_constant<int, KU>{});
+  }
 }
 // ---- per-warp staging of a slice's arc columns (cp.async, 16 bytes per lane) ----
 // The columns 0..KU-1 of a slice lie inside its first 32*KU arcs.  Each warp owns one stage of SA elements per
@@ -422,7 +434,7 @@ __global__ void __launch_bounds__(NT_MAX, NT_MAX == 128 ? SELL_PULL_MIN_BLOCKS_1
       const int dmax = slice_dmax8(ac.d);  // 255 = "255 or more"
       int dstc[KU];
       float wc[KU];
-      by_width(dmax, [&](auto nc) {
+      by_width<(TROP ? 4 : 2)>(dmax, [&](auto nc) {
         constexpr int NC = decltype(nc)::value;
         // branch-free: lanes without a k-th arc re-read the slice's first arc and ignore the value --
         // cheaper than a reconvergence point per column
@@ -440,7 +452,7 @@ __global__ void __launch_bounds__(NT_MAX, NT_MAX == 128 ? SELL_PULL_MIN_BLOCKS_1
       __syncwarp();  // every lane has its columns and meta data: both buffers are free
       if (pn.ok) issue(*reinterpret_cast<const int4*>(meta + (par ^ 1) * META));
       if (pa.ok) meta_issue(pa, lvl, lsl, lane, warp, nw, L.n_states, deg8, desc, meta + par * META);
-      by_width(dmax, [&](auto nc) {
+      by_width<(TROP ? 4 : 2)>(dmax, [&](auto nc) {
       constexpr int NC = decltype(nc)::value;
       // destinations' DP values: from the ring, straight-line; the rare ones beyond it are patched afterwards
       RingT rv[KU];
@@ -758,7 +770,7 @@ __global__ void __launch_bounds__(NT_MAX, NT_MAX == 128 ? 7 : NT_MAX == 256 ? SE
       if (read_far && s != 0x7fffffff) g_far = *reinterpret_cast<volatile float*>(gamma_far + s);
       int dstc[KU], labc[KU];
       float cc[KU];
-      by_width(dmax, [&](auto nc) {
+      by_width<4>(dmax, [&](auto nc) {
         constexpr int NC = decltype(nc)::value;
         const int32_t* const sd = stage + (ac.d.x & 3);
         const float* const sc = reinterpret_cast<const float*>(sd + SA);
@@ -786,7 +798,7 @@ __global__ void __launch_bounds__(NT_MAX, NT_MAX == 128 ? 7 : NT_MAX == 256 ? SE
                               : static_cast<OT>(kNegInf);
         }
       }
-      by_width(dmax, [&](auto nc) {
+      by_width<4>(dmax, [&](auto nc) {
       constexpr int NC = decltype(nc)::value;
       bool any_slow = false;
       for_columns<0, NC>(ac.d, deg, lane, [&](auto kc, bool on, int a) {
