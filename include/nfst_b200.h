@@ -265,8 +265,8 @@ int nfst_dense_extract_arcs(const int64_t* transition, int64_t n_rows, int32_t s
  * Sliced-column passes (launch->sell != 0).
  *
  * nfst_sell_pull_f32 -- deepest level first.  Log semiring when beta, logz_bwd or cond is given:
- *   beta[S] / logz_bwd[B] (float32, or float64 when launch->state_f64; the recurrence itself always runs
- *   in float64 with fp32 exponentials), and cond[A] (float32, real space):
+ *   beta[S] / logz_bwd[B] (float32, or float64 when launch->state_f64; per-arc terms are float32 offsets from
+ *   a reference arc of the state, float64 with a float64 state), and cond[A] (float32, real space):
  *   cond[a] = exp(w_a + beta[dst_a] - beta[src_a]), the probability of arc a given its source state.
  *   Tropical semiring when backptr is given: delta[S] (optional), backptr[S], vit_score[B] (optional),
  *   same rule as nfst_bwd_fused_f32.  Groups with sell_far need beta (resp. delta): arcs longer than the
@@ -279,6 +279,9 @@ int nfst_dense_extract_arcs(const int64_t* transition, int64_t n_rows, int32_t s
  *   atomics: posteriors are reproducible to rounding (~1e-7 relative), not bit for bit.
  *   gamma_far[S] (float32, zero-filled by the caller) is required for groups with sell_far and whenever alpha
  *   is requested: it receives the flow of arcs longer than the ring (and, for alpha, into the last level).
+ * Both passes stage the arc arrays of every slice in shared memory with 16-byte cp.async copies:
+ *   dst_out, label_out, scores->arc_scores and cond must be 16-byte aligned (NFST_ERR_BAD_ARG otherwise; their
+ *   lengths need no padding), out_deg8 4-byte aligned and readable up to the next multiple of 4 bytes.
  */
 size_t nfst_sell_smem_bytes(const nfst_launch_t* launch, int32_t vocab, int pass, int with_trop, int with_table);
 int nfst_sell_pull_f32(const nfst_packed_lattices_t* lat, const nfst_launch_t* launch, const nfst_scores_t* scores,

@@ -53,11 +53,12 @@ DEGREE_SORT = int(os.environ.get("NFST_DEGREE_SORT", "1"))
 # Sliced-column execution (nfst_sell.cu): lattices whose levels average at least SELL_MIN_WIDTH states and
 # whose DP ring (SELL_WINDOW_QUANTILE of the arc spans, and the widest level) fits SELL_WINDOW_MAX states; the
 # few longer arcs go through global memory.  Measured on B200 against the CSR kernels (config 4, B = 1024,
-# fwd+bwd): narrower lattices are latency-bound and the CSR kernels' cp.async staging wins (10k arcs: 0.49 vs
-# 0.26 ms, 30k: 1.03 vs 0.55 ms); from ~250 states per level the sliced columns win (100k: 1.29 vs 1.42 ms,
-# 300k: 4.10 vs 5.12 ms); lattices whose ring would not fit stay CSR (1M arcs per lattice).
+# fwd+bwd, sliced columns vs CSR): 10k arcs (40 states per level: two slices for four warps) 0.33 vs 0.25 ms;
+# 30k arcs (119 per level) 0.45 vs 0.57 ms, Viterbi 0.16 vs 0.26 ms; 100k: 1.05 vs 1.42 ms; 300k: 3.68 vs
+# 5.12 ms; lattices whose ring would not fit stay CSR (1M arcs per lattice).  The threshold sits where a level
+# fills the four warps of a block (three full slices and a partial one).
 SELL = int(os.environ.get("NFST_SELL", "1"))
-SELL_MIN_WIDTH = int(os.environ.get("NFST_SELL_MIN_WIDTH", "256"))
+SELL_MIN_WIDTH = int(os.environ.get("NFST_SELL_MIN_WIDTH", "96"))
 SELL_WINDOW_MAX = int(os.environ.get("NFST_SELL_WINDOW_MAX", "16384"))
 SELL_WINDOW_QUANTILE = float(os.environ.get("NFST_SELL_WINDOW_QUANTILE", "0.995"))
 SELL_THREADS = int(os.environ.get("NFST_SELL_THREADS", "0"))  # 0 = from the level width (128, or 256 from 1024 states per level)

@@ -17,7 +17,7 @@ pytestmark = pytest.mark.gpu
 
 @pytest.fixture(autouse=True)
 def narrow_lattices_too(monkeypatch):
-    """The packer only sends lattices of >= 256 states per level down the sliced-column path (below that the
+    """The packer only sends lattices of >= 96 states per level down the sliced-column path (below that the
     CSR kernels are faster); the tests want small lattices there too."""
     monkeypatch.setattr(nb.pack, "SELL_MIN_WIDTH", 32)
 

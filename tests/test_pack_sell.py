@@ -14,7 +14,7 @@ from oracle import lattice_oracle as lo
 
 @pytest.fixture(autouse=True)
 def narrow_lattices_too(monkeypatch):
-    """The packer only sends lattices of >= 256 states per level down the sliced-column path (below that the
+    """The packer only sends lattices of >= 96 states per level down the sliced-column path (below that the
     CSR kernels are faster); the tests want small lattices there too."""
     monkeypatch.setattr(nb.pack, "SELL_MIN_WIDTH", 32)
 
@@ -174,7 +174,7 @@ def test_sell_heavy_state_and_narrow_lattices():
 
 def test_sell_default_thresholds(monkeypatch):
     monkeypatch.undo()  # the packer's own defaults
-    assert not layered(2, 4000, 10, 1).pack()[0].has_sell  # 100 states per level: CSR kernels
+    assert not layered(2, 2000, 10, 1).pack()[0].has_sell  # 50 states per level: CSR kernels
     p, _ = layered(1, 40_000, 16, 1).pack()  # 625 states per level
     assert p.has_sell and p.groups[0].block_threads == 128
     monkeypatch.setattr(nb.pack, "SELL_WINDOW_MAX", 1024)  # ring would not fit: stays CSR
