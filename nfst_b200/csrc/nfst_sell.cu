@@ -6,23 +6,26 @@
 // 32 consecutive states of one topological level (sorted by out-degree, descending), and the
 // slice's arcs are laid out column-major without padding -- column k holds the k-th arc of every
 // state of the slice that has more than k arcs, in lane order.  Lane i of a warp owns state i of
-// the slice, so the k-th arcs of 32 states are ONE coalesced 128-byte load, straight from global
-// memory into registers: no shared-memory staging, no row pointers (one base offset per slice
-// and one degree byte per state), ~10 thread-instructions per arc.
+// the slice, so the k-th arcs of 32 states are 128 consecutive bytes: no row pointers (one 16-byte
+// descriptor per slice and one degree byte per state).
 //
-// A thread block owns one lattice and walks its levels with one barrier per level; a warp takes
-// every nw-th slice of a level.  Per slice: one 16-byte descriptor (arc range, column starts,
-// largest degree -- loaded one slice ahead), one degree byte per lane, then all columns of the
-// register window are loaded together, branch-free.  At 64 registers eight 128-thread blocks fit
-// an SM, so 1024 lattices run in ONE wave and the other warps of a scheduler cover the exposed
-// load latency; the kernels are bound by instruction issue, which is why the hot path carries no
-// warp votes, no per-column branches and no prefetch code (measured: register double buffering
-// spilled, and a spilled load result stalls on its own load; L2 prefetch cost ~120 instructions
-// per slice).  The only data that crosses levels, the per-state DP value, lives in a
-// shared-memory ring.
+// A thread block owns one lattice and walks its levels with one barrier per level; the slices of a
+// level are dealt to the warps in serpentine rounds (see Pos).  Every warp owns a small stage in shared
+// memory and keeps it filled with cp.async: the descriptor and degree bytes of the slice two ahead,
+// the arc columns (dst, score or conditional, label) of the next slice -- issued the moment the
+// current slice's columns have been read out into registers, so the copy travels while the current
+// slice is computed and no warp waits a memory latency per slice.  Nothing about the slices ahead is
+// carried in registers (ptxas spills loop-carried descriptors at 64 registers, and a local-memory
+// reload on every slice's critical path doubled the kernel time).  The per-slice code exists in
+// several widths (slices whose states have at most 2 / 4 / 6 arcs, and the rest), chosen by a
+// warp-uniform branch; inside a width the columns are straight-line and predicated per lane: no warp
+// votes, no per-column branches.  128-thread blocks are compiled for 7 resident blocks per SM
+// (72 registers: 1024 lattices run in ONE wave), 256-thread blocks for 4 (64 registers).  The only
+// data that crosses levels, the per-state DP value, lives in a shared-memory ring.
 //
-//   pull pass (deepest level first): beta[s] = logsumexp_k (w_k + beta[dst_k]) in float64
-//       (exp in fp32), and the arc's conditional probability cond[a] = exp(w + beta[dst] - beta[s])
+//   pull pass (deepest level first): beta[s] = logsumexp_k (w_k + beta[dst_k]) -- per-arc terms as float32
+//       offsets from a reference arc of the state (float64 with a float64 state) -- and the arc's
+//       conditional probability cond[a] = exp(w + beta[dst] - beta[s])
 //       written in real space next to it; or the tropical recursion delta / backpointer
 //       (one fp32 add per arc, first maximum in label order wins -- bit-exact rule).
 //   flow pass (start level first): gamma[start] = g_b; post[a] = gamma[src] * cond[a];

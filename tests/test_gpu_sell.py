@@ -161,3 +161,30 @@ def test_sell_rejects_misuse():
     assert rc < 0
     with pytest.raises(ValueError):
         nb.ops.lattice_beta_hat(p, torch.zeros(p.vocab, 8, device=DEV), torch.zeros(8, 8, device=DEV), torch.zeros(8, device=DEV))
+
+
+def test_sell_staging_edges():
+    """The 16-byte staging copies: an arc count that is not a multiple of 4 (the last slice of the batch is copied
+    by element), a misaligned view of the scores (the operator copies it once), and the C ABI's refusal of a
+    misaligned conditional buffer."""
+    for seed in range(20, 40):
+        ab = synth.random_dag_batch(3, 9_000, levels=12, seed=seed)
+        p, sc = ab.to(DEV).pack()
+        if p.n_arcs % 4:
+            break
+    assert p.has_sell and p.n_arcs % 4
+    o_logz, _, _, o_post = c_oracle.forward_backward(oracle_batch(ab))
+    ref = o_post[p.arc_origin.cpu().numpy()]
+    buf = torch.empty(p.n_arcs + 1, device=DEV)
+    view = buf[1:]  # 4 bytes off a 16-byte boundary
+    view.copy_(sc)
+    assert view.data_ptr() % 16
+    for w in (sc, view):
+        logz, _, _, post = nb.lattice_forward_backward(p, arc_scores=w)
+        np.testing.assert_allclose(logz.cpu().numpy(), o_logz, rtol=1e-6)
+        assert np.all(np.abs(post.cpu().numpy() - ref) <= 1e-5 * ref + 1e-7)
+    logz, _, cond = nb.ops.lattice_pull(p, arc_scores=sc)
+    bad = torch.empty(p.n_arcs + 1, device=DEV)[1:]
+    bad.copy_(cond)
+    with pytest.raises(RuntimeError, match="16-byte aligned"):
+        nb.lattice_backward(p, arc_scores=sc, logz=logz, cond=bad, want_beta=False, want_post=True)
