@@ -133,7 +133,7 @@ __device__ __forceinline__ void advance(Pos& p, const int* lsl, int n_levels, in
 constexpr int META = 16;  // ints: descriptor (4) + the word-aligned superset of 32 degree bytes (<= 9 words)
 __device__ __forceinline__ void meta_issue(const Pos& p, const int* lvl, const int* lsl, int lane, int warp, int nw,
                                            int n_states, const uint8_t* __restrict__ deg8,
-                                           const int4* __restrict__ desc, int32_t* buf);
+                                           const int4* __restrict__ desc, unsigned buf);
 __device__ __forceinline__ StA meta_read(const Pos& p, const int* lvl, int lane, int warp, int nw, const int32_t* buf) {
   StA a;
   const int first = lvl[p.l] + 32 * slice_of(p, warp, nw);
@@ -192,49 +192,52 @@ __device__ __forceinline__ void by_width(int dmax, F&& f) {
 // aligned superset of the range (the arrays are 16-byte aligned; the last chunk of the last slice of the batch
 // is copied by element).
 constexpr int SA = 32 * KU + 8;
-__device__ __forceinline__ void cp_async_16(void* smem, const void* gmem) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(static_cast<unsigned>(__cvta_generic_to_shared(smem))), "l"(gmem) : "memory");
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return static_cast<unsigned>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void cp_async_16(unsigned smem, const void* gmem) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem), "l"(gmem) : "memory");
 }
-__device__ __forceinline__ void cp_async_4(void* smem, const void* gmem) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(static_cast<unsigned>(__cvta_generic_to_shared(smem))), "l"(gmem) : "memory");
+__device__ __forceinline__ void cp_async_4(unsigned smem, const void* gmem) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem), "l"(gmem) : "memory");
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 template <bool A1, bool A2>
-__device__ __forceinline__ void stage_issue(const int4& d, int lane, int n_arcs, int32_t* stage, const int32_t* g0,
+__device__ __forceinline__ void stage_issue(const int4& d, int lane, int n_arcs, unsigned stage, const int32_t* g0,
                                             const void* g1, const void* g2) {
+  // stage: 32-bit shared-memory address of the warp's stage (arrays SA * 4 bytes apart)
   const int base = d.x & ~3;
   const int n16 = (min(d.y, d.x + 32 * KU) - base + 3) >> 2;  // <= 65, the same for the whole warp
   const int32_t* h1 = static_cast<const int32_t*>(g1);
   const int32_t* h2 = static_cast<const int32_t*>(g2);
+  constexpr unsigned AB = SA * 4;
   if (base + 4 * n16 <= n_arcs) {
     // every slice but the very last of the batch: whole 16-byte chunks; a slice of average size needs one
     // round, the second and third run under warp-uniform branches
     const int e0 = base + 4 * lane;
-    int32_t* const st = stage + 4 * lane;
+    const unsigned st = stage + 16 * lane;
     if (lane < n16) {
       cp_async_16(st, g0 + e0);
-      if (A1) cp_async_16(st + SA, h1 + e0);
-      if (A2) cp_async_16(st + 2 * SA, h2 + e0);
+      if (A1) cp_async_16(st + AB, h1 + e0);
+      if (A2) cp_async_16(st + 2 * AB, h2 + e0);
     }
     if (n16 > 32) {
       if (lane + 32 < n16) {
-        cp_async_16(st + 128, g0 + e0 + 128);
-        if (A1) cp_async_16(st + SA + 128, h1 + e0 + 128);
-        if (A2) cp_async_16(st + 2 * SA + 128, h2 + e0 + 128);
+        cp_async_16(st + 512, g0 + e0 + 128);
+        if (A1) cp_async_16(st + AB + 512, h1 + e0 + 128);
+        if (A2) cp_async_16(st + 2 * AB + 512, h2 + e0 + 128);
       }
       if (lane + 64 < n16) {
-        cp_async_16(st + 256, g0 + e0 + 256);
-        if (A1) cp_async_16(st + SA + 256, h1 + e0 + 256);
-        if (A2) cp_async_16(st + 2 * SA + 256, h2 + e0 + 256);
+        cp_async_16(st + 1024, g0 + e0 + 256);
+        if (A1) cp_async_16(st + AB + 1024, h1 + e0 + 256);
+        if (A2) cp_async_16(st + 2 * AB + 1024, h2 + e0 + 256);
       }
     }
   } else {
     for (int j = lane; j < 4 * n16; j += 32) {
       const int e = base + j;
       if (e < n_arcs) {
-        cp_async_4(stage + j, g0 + e);
-        if (A1) cp_async_4(stage + SA + j, h1 + e);
-        if (A2) cp_async_4(stage + 2 * SA + j, h2 + e);
+        cp_async_4(stage + 4 * j, g0 + e);
+        if (A1) cp_async_4(stage + AB + 4 * j, h1 + e);
+        if (A2) cp_async_4(stage + 2 * AB + 4 * j, h2 + e);
       }
     }
   }
@@ -242,14 +245,14 @@ __device__ __forceinline__ void stage_issue(const int4& d, int lane, int n_arcs,
 
 __device__ __forceinline__ void meta_issue(const Pos& p, const int* lvl, const int* lsl, int lane, int warp, int nw,
                                            int n_states, const uint8_t* __restrict__ deg8,
-                                           const int4* __restrict__ desc, int32_t* buf) {
+                                           const int4* __restrict__ desc, unsigned buf) {
   // one 4-byte copy per lane, no divergent branch: lanes 0..3 the descriptor, lanes 4..12 the degree words
   const int jj = slice_of(p, warp, nw);
   const int first = lvl[p.l] + 32 * jj;
   const int w = (first >> 2) + lane - 4;  // out_deg8 is 4-byte aligned and padded to a whole word
   const int32_t* const src = lane < 4 ? reinterpret_cast<const int32_t*>(desc + lsl[p.l] + jj) + lane
                                       : reinterpret_cast<const int32_t*>(deg8) + w;
-  if (lane < 4 || (lane < 13 && 4 * w < n_states)) cp_async_4(buf + lane, src);
+  if (lane < 4 || (lane < 13 && 4 * w < n_states)) cp_async_4(buf + 4 * lane, src);
 }
 
 // rare path: an arc longer than the shared-memory ring (kept out of line: no 64-bit address arithmetic in
@@ -319,7 +322,7 @@ __device__ __forceinline__ void lse_join(RT& m, float& s, RT m2, float s2) {
 template <bool TROP, bool SC, bool TH, bool COND, typename OT, int NT_MAX>
 __global__ void __launch_bounds__(NT_MAX, NT_MAX == 128 ? SELL_PULL_MIN_BLOCKS_128 : NT_MAX == 256 ? SELL_PULL_MIN_BLOCKS_256 : 1)
     sell_pull_kernel(const nfst_packed_lattices_t L, const int32_t* __restrict__ ids, int W, int max_levels,
-                     int theta_smem, int far, const float* __restrict__ arc_scores, const float* __restrict__ theta,
+                     int theta_smem, int far, int stage_off, const float* __restrict__ arc_scores, const float* __restrict__ theta,
                      OT* beta, OT* __restrict__ logz, float* __restrict__ cond, float* delta,
                      int32_t* __restrict__ backptr, float* __restrict__ vit_score) {
   using RT = typename std::conditional<TROP, float, double>::type;
@@ -343,14 +346,9 @@ __global__ void __launch_bounds__(NT_MAX, NT_MAX == 128 ? SELL_PULL_MIN_BLOCKS_1
     for (int i = tid; i < L.vocab; i += blockDim.x) sth[i] = theta[i];
     th = sth;
   }
-  // per-warp stage: [dst | scores (SC) | labels (TH)], SA elements each
-  int32_t* stage;
-  {
-    size_t o = static_cast<size_t>(W) * sizeof(RingT) + 2 * static_cast<size_t>(lvl_words) * 4;
-    if (TH && theta_smem) o += static_cast<size_t>(L.vocab) * 4;
-    o = (o + 15) & ~static_cast<size_t>(15);
-    stage = reinterpret_cast<int32_t*>(sell_smem + o) + warp * ((1 + SC + TH) * SA + 2 * META) + 2 * META;
-  }
+  // per-warp stage at byte offset stage_off (computed by the host: the compiler would re-derive it from W, the
+  // level count and the vocabulary on every slice): two meta buffers, then [dst | scores (SC) | labels (TH)]
+  int32_t* const stage = reinterpret_cast<int32_t*>(sell_smem + stage_off) + warp * ((1 + SC + TH) * SA + 2 * META) + 2 * META;
   __syncthreads();
   const int mask = W - 1;
   const int start = L.start_state[b];
@@ -399,8 +397,9 @@ __global__ void __launch_bounds__(NT_MAX, NT_MAX == 128 ? SELL_PULL_MIN_BLOCKS_1
   // ---- pipeline state: the slice being computed (its arc columns staged in shared memory), the next one
   // (descriptor + degree byte in registers, its stage copy issued once the current columns are read out) and
   // the one after that (descriptor + degree byte in flight).  None of these addresses depends on a DP value.
+  const unsigned stage_s = smem_u32(stage);
   auto issue = [&](const int4& d) {
-    stage_issue<true, SC && TH>(d, lane, L.n_arcs, stage, dst_out, SC ? static_cast<const void*>(arc_scores) : static_cast<const void*>(label_out),
+    stage_issue<true, SC && TH>(d, lane, L.n_arcs, stage_s, dst_out, SC ? static_cast<const void*>(arc_scores) : static_cast<const void*>(label_out),
                         SC ? static_cast<const void*>(label_out) : nullptr);
   };
   Pos pc, pn;
@@ -409,9 +408,10 @@ __global__ void __launch_bounds__(NT_MAX, NT_MAX == 128 ? SELL_PULL_MIN_BLOCKS_1
   pn = pc;
   if (pn.ok) advance<true>(pn, lsl, n_levels, warp, nw);
   int32_t* const meta = stage - 2 * META;  // two meta buffers in front of the warp's arc stage
+  const unsigned meta_s = smem_u32(meta);
   int par = 0;                             // parity of the warp's slice counter: meta buffer of the current slice
-  if (pc.ok) meta_issue(pc, lvl, lsl, lane, warp, nw, L.n_states, deg8, desc, meta);
-  if (pn.ok) meta_issue(pn, lvl, lsl, lane, warp, nw, L.n_states, deg8, desc, meta + META);
+  if (pc.ok) meta_issue(pc, lvl, lsl, lane, warp, nw, L.n_states, deg8, desc, meta_s);
+  if (pn.ok) meta_issue(pn, lvl, lsl, lane, warp, nw, L.n_states, deg8, desc, meta_s + META * 4);
   cp_async_wait_all();
   __syncwarp();
   if (pc.ok) issue(*reinterpret_cast<const int4*>(meta));
@@ -454,7 +454,7 @@ __global__ void __launch_bounds__(NT_MAX, NT_MAX == 128 ? SELL_PULL_MIN_BLOCKS_1
       });
       __syncwarp();  // every lane has its columns and meta data: both buffers are free
       if (pn.ok) issue(*reinterpret_cast<const int4*>(meta + (par ^ 1) * META));
-      if (pa.ok) meta_issue(pa, lvl, lsl, lane, warp, nw, L.n_states, deg8, desc, meta + par * META);
+      if (pa.ok) meta_issue(pa, lvl, lsl, lane, warp, nw, L.n_states, deg8, desc, meta_s + par * (META * 4));
       by_width<(TROP ? 4 : 2)>(dmax, [&](auto nc) {
       constexpr int NC = decltype(nc)::value;
       // destinations' DP values: from the ring, straight-line; the rare ones beyond it are patched afterwards
@@ -676,7 +676,7 @@ __global__ void __launch_bounds__(NT_MAX, NT_MAX == 128 ? SELL_PULL_MIN_BLOCKS_1
 template <bool DTH, bool ALPHA, typename OT, int NT_MAX>
 __global__ void __launch_bounds__(NT_MAX, NT_MAX == 128 ? 7 : NT_MAX == 256 ? SELL_FLOW_MIN_BLOCKS : 1)
     sell_flow_kernel(const nfst_packed_lattices_t L, const int32_t* __restrict__ ids, int W, int max_levels,
-                     int dtheta_smem, int far, const float* cond, const float* __restrict__ grad_logz, float* post,
+                     int dtheta_smem, int far, int stage_off, const float* cond, const float* __restrict__ grad_logz, float* post,
                      const OT* __restrict__ beta, const OT* __restrict__ logz, OT* __restrict__ alpha,
                      float* __restrict__ dtheta, float* gamma_far) {
   float* const ring = reinterpret_cast<float*>(sell_smem);
@@ -698,14 +698,8 @@ __global__ void __launch_bounds__(NT_MAX, NT_MAX == 128 ? 7 : NT_MAX == 256 ? SE
     hist = reinterpret_cast<float*>(lsl + lvl_words);
     for (int i = tid; i < L.vocab; i += blockDim.x) hist[i] = 0.0f;
   }
-  // per-warp stage: [dst | cond | labels (DTH)], SA elements each
-  int32_t* stage;
-  {
-    size_t o = static_cast<size_t>(W) * 4 + 2 * static_cast<size_t>(lvl_words) * 4;
-    if (DTH && dtheta_smem) o += static_cast<size_t>(L.vocab) * 4;
-    o = (o + 15) & ~static_cast<size_t>(15);
-    stage = reinterpret_cast<int32_t*>(sell_smem + o) + warp * ((2 + DTH) * SA + 2 * META) + 2 * META;
-  }
+  // per-warp stage at byte offset stage_off: two meta buffers, then [dst | cond | labels (DTH)]
+  int32_t* const stage = reinterpret_cast<int32_t*>(sell_smem + stage_off) + warp * ((2 + DTH) * SA + 2 * META) + 2 * META;
   __syncthreads();
   const int mask = W - 1;
   const int start = L.start_state[b];
@@ -737,8 +731,9 @@ __global__ void __launch_bounds__(NT_MAX, NT_MAX == 128 ? 7 : NT_MAX == 256 ? SE
   // pipeline as in the pull pass: current slice staged, next slice's copy in flight, descriptors two ahead.
   // cond may be the same buffer as post: an arc's conditional is staged before its own posterior is written
   // (the 16-byte superset may re-read a neighbour slice's arcs, whose values are ignored).
+  const unsigned stage_s = smem_u32(stage);
   auto issue = [&](const int4& d) {
-    stage_issue<true, DTH>(d, lane, L.n_arcs, stage, dst_out, cond, label_out);
+    stage_issue<true, DTH>(d, lane, L.n_arcs, stage_s, dst_out, cond, label_out);
   };
   Pos pc, pn;
   pc.l = 0; pc.j = -1; pc.ok = false;
@@ -746,9 +741,10 @@ __global__ void __launch_bounds__(NT_MAX, NT_MAX == 128 ? 7 : NT_MAX == 256 ? SE
   pn = pc;
   if (pn.ok) advance<false>(pn, lsl, n_levels, warp, nw);
   int32_t* const meta = stage - 2 * META;  // two meta buffers in front of the warp's arc stage
+  const unsigned meta_s = smem_u32(meta);
   int par = 0;                             // parity of the warp's slice counter: meta buffer of the current slice
-  if (pc.ok) meta_issue(pc, lvl, lsl, lane, warp, nw, L.n_states, deg8, desc, meta);
-  if (pn.ok) meta_issue(pn, lvl, lsl, lane, warp, nw, L.n_states, deg8, desc, meta + META);
+  if (pc.ok) meta_issue(pc, lvl, lsl, lane, warp, nw, L.n_states, deg8, desc, meta_s);
+  if (pn.ok) meta_issue(pn, lvl, lsl, lane, warp, nw, L.n_states, deg8, desc, meta_s + META * 4);
   cp_async_wait_all();
   __syncwarp();
   if (pc.ok) issue(*reinterpret_cast<const int4*>(meta));
@@ -788,7 +784,7 @@ __global__ void __launch_bounds__(NT_MAX, NT_MAX == 128 ? 7 : NT_MAX == 256 ? SE
       });
       __syncwarp();  // every lane has its columns and meta data: both buffers are free
       if (pn.ok) issue(*reinterpret_cast<const int4*>(meta + (par ^ 1) * META));
-      if (pa.ok) meta_issue(pa, lvl, lsl, lane, warp, nw, L.n_states, deg8, desc, meta + par * META);
+      if (pa.ok) meta_issue(pa, lvl, lsl, lane, warp, nw, L.n_states, deg8, desc, meta_s + par * (META * 4));
       float gs = 0.0f;
       if (s != 0x7fffffff) {
         // every arc into s comes from a shallower level: gamma[s] is final; free the slot
@@ -875,19 +871,20 @@ __global__ void __launch_bounds__(NT_MAX, NT_MAX == 128 ? 7 : NT_MAX == 256 ? SE
   }
 }
 
-size_t pull_smem(int W, int max_levels, int vocab, int ring_bytes, bool theta_smem, int threads, int n_staged) {
+// byte offset of the per-warp stages (ring, level tables, theta / dtheta table in front of them)
+size_t pull_stage_off(int W, int max_levels, int vocab, int ring_bytes, bool theta_smem) {
   size_t o = static_cast<size_t>(W) * ring_bytes;
   o += 2 * static_cast<size_t>((max_levels + 2 + 3) & ~3) * 4;
   if (theta_smem) o += static_cast<size_t>(vocab) * 4;
-  o = (o + 15) & ~static_cast<size_t>(15);
-  return o + static_cast<size_t>(threads / 32) * (n_staged * SA + 2 * META) * 4;  // per-warp stages
+  return (o + 15) & ~static_cast<size_t>(15);
+}
+size_t flow_stage_off(int W, int max_levels, int vocab, bool dtheta_smem) { return pull_stage_off(W, max_levels, vocab, 4, dtheta_smem); }
+size_t stage_bytes(int threads, int n_staged) { return static_cast<size_t>(threads / 32) * (n_staged * SA + 2 * META) * 4; }
+size_t pull_smem(int W, int max_levels, int vocab, int ring_bytes, bool theta_smem, int threads, int n_staged) {
+  return pull_stage_off(W, max_levels, vocab, ring_bytes, theta_smem) + stage_bytes(threads, n_staged);
 }
 size_t flow_smem(int W, int max_levels, int vocab, bool dtheta_smem, int threads, int n_staged) {
-  size_t o = static_cast<size_t>(W) * 4;
-  o += 2 * static_cast<size_t>((max_levels + 2 + 3) & ~3) * 4;
-  if (dtheta_smem) o += static_cast<size_t>(vocab) * 4;
-  o = (o + 15) & ~static_cast<size_t>(15);
-  return o + static_cast<size_t>(threads / 32) * (n_staged * SA + 2 * META) * 4;
+  return flow_stage_off(W, max_levels, vocab, dtheta_smem) + stage_bytes(threads, n_staged);
 }
 
 bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
@@ -936,6 +933,8 @@ int launch_pull(const nfst_packed_lattices_t* lat, const nfst_launch_t* launch, 
     if (int rc = prepare(k, smem)) return rc;                                                                     \
     k<<<launch->n_ids, launch->block_threads, smem, stream>>>(                                                    \
         *lat, launch->lattice_ids, launch->window_states, launch->n_levels, th_smem ? 1 : 0, launch->sell_far,    \
+        static_cast<int>(pull_stage_off(launch->window_states, launch->n_levels, lat->vocab,                      \
+                                        TROP ? 4 : static_cast<int>(sizeof(OT)), th_smem)),                       \
         sc->arc_scores, sc->theta, beta, logz, cond, delta, backptr, vit);                                        \
   } while (0)
 #define SELL_PULL(SCv, THv)                                                                                       \
@@ -1030,6 +1029,7 @@ int nfst_sell_flow_f32(const nfst_packed_lattices_t* lat, const nfst_launch_t* l
     if (int rc = prepare(k, smem)) return rc;                                                                     \
     k<<<launch->n_ids, launch->block_threads, smem, stream>>>(                                                    \
         *lat, launch->lattice_ids, launch->window_states, launch->n_levels, dth_smem ? 1 : 0, launch->sell_far,   \
+        static_cast<int>(flow_stage_off(launch->window_states, launch->n_levels, lat->vocab, dth_smem)),          \
         cond, grad_logz,                                                                                          \
         post, static_cast<const OT*>(beta), static_cast<const OT*>(logz), static_cast<OT*>(alpha), dtheta,        \
         gamma_far);                                                                                               \
