@@ -74,6 +74,11 @@ __device__ __forceinline__ float ex2_approx(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+__device__ __forceinline__ float rcp_approx(float x) {  // 1 ulp; __frcp_rn costs a Newton step and a range branch
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ float lg2_approx(float x) {
   float y;
   asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -509,16 +514,22 @@ __global__ void __launch_bounds__(NT_MAX, NT_MAX == 128 ? SELL_PULL_MIN_BLOCKS_1
         for (int k = 0; k < NC; ++k) mf = fmaxf(mf, tf[k]);
         float e[KU];
         float sum = 0.0f;
+        const float mfl = -mf * kLog2e;
         for_columns<0, NC>(ac.d, deg, lane, [&](auto kc, bool, int) {
           constexpr int k = decltype(kc)::value;
-          e[k] = ex2_approx((tf[k] - mf) * kLog2e);  // idle lanes / -inf arcs: exp(-huge) = 0
+          // idle lanes / -inf arcs: exp(-huge) = 0.  float32 state: one fused multiply-add per arc; the rounding of
+          // mf * log2(e) then scales every term of the state alike (cancels in cond, shifts beta by < 1e-7, far
+          // below the float32 state's own rounding).  float64 state: exact difference first -- the shift would
+          // add up over hundreds of levels.
+          if constexpr (sizeof(RingT) == 4) e[k] = ex2_approx(fmaf(tf[k], kLog2e, mfl));
+          else e[k] = ex2_approx((tf[k] - mf) * kLog2e);
           sum += e[k];
         });
         if (!(mf > kFloor)) sum = 0.0f;  // no finite arc: every term above was exp(0)
         // sinks: beta = 1 (scorers.py:720); a state whose arcs all score -inf: beta = -inf.
         // beta[s] = beta_0 + (w_0 + max offset + log sum): one rounding at beta's magnitude
         RingT bv = static_cast<RingT>(0);
-        float inv_reg = sum > 0.0f ? __frcp_rn(sum) : 0.0f;  // scale of the window's exponentials in cond[]
+        float inv_reg = sum > 0.0f ? rcp_approx(sum) : 0.0f;  // scale of the window's exponentials in cond[]
         if (deg > 0) {
           const float lg = lg2_approx(sum) * kLn2;
           if (!(sum > 0.0f)) bv = static_cast<RingT>(kNegInf);
