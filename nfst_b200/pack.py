@@ -54,7 +54,7 @@ DEGREE_SORT = int(os.environ.get("NFST_DEGREE_SORT", "1"))
 # whose DP ring (SELL_WINDOW_QUANTILE of the arc spans, and the widest level) fits SELL_WINDOW_MAX states; the
 # few longer arcs go through global memory.  Measured on B200 against the CSR kernels (config 4, B = 1024,
 # fwd+bwd, sliced columns vs CSR): 10k arcs (40 states per level: two slices for four warps) 0.33 vs 0.25 ms;
-# 30k arcs (119 per level) 0.45 vs 0.57 ms, Viterbi 0.16 vs 0.26 ms; 100k: 1.05 vs 1.42 ms; 300k: 3.68 vs
+# 30k arcs (119 per level) 0.45 vs 0.57 ms, Viterbi 0.16 vs 0.26 ms; 100k: 1.02 vs 1.42 ms; 300k: 3.60 vs
 # 5.12 ms; lattices whose ring would not fit stay CSR (1M arcs per lattice).  The threshold sits where a level
 # fills the four warps of a block (three full slices and a partial one).
 SELL = int(os.environ.get("NFST_SELL", "1"))
