@@ -255,8 +255,10 @@ __device__ __forceinline__ void meta_issue(const Pos& p, const int* lvl, const i
   const int jj = slice_of(p, warp, nw);
   const int first = lvl[p.l] + 32 * jj;
   const int w = (first >> 2) + lane - 4;  // out_deg8 is 4-byte aligned and padded to a whole word
-  const int32_t* const src = lane < 4 ? reinterpret_cast<const int32_t*>(desc + lsl[p.l] + jj) + lane
-                                      : reinterpret_cast<const int32_t*>(deg8) + w;
+  const int32_t* const dsrc = reinterpret_cast<const int32_t*>(desc + lsl[p.l] + jj) + lane;
+  const int32_t* const gsrc = reinterpret_cast<const int32_t*>(deg8) + w;
+  const int32_t* src;  // a select, not a branch: both addresses are a handful of instructions
+  asm("{\n\t.reg .pred p;\n\tsetp.lt.s32 p, %3, 4;\n\tselp.b64 %0, %1, %2, p;\n\t}" : "=l"(src) : "l"(dsrc), "l"(gsrc), "r"(lane));
   if (lane < 4 || (lane < 13 && 4 * w < n_states)) cp_async_4(buf + 4 * lane, src);
 }
 
@@ -444,14 +446,14 @@ __global__ void __launch_bounds__(NT_MAX, NT_MAX == 128 ? SELL_PULL_MIN_BLOCKS_1
       float wc[KU];
       by_width<(TROP ? 4 : 2)>(dmax, [&](auto nc) {
         constexpr int NC = decltype(nc)::value;
-        // branch-free: lanes without a k-th arc re-read the slice's first arc and ignore the value --
-        // cheaper than a reconvergence point per column
+        // branch-free: lanes without a k-th arc read whatever the stage holds at their position (always inside
+        // the stage) and ignore the value -- cheaper than a reconvergence point, or even a select, per column
         const int32_t* const sd = stage + (ac.d.x & 3);
         const float* const sw = reinterpret_cast<const float*>(sd + SA);
         const int32_t* const sl = sd + (SC ? 2 : 1) * SA;
         for_columns<0, NC>(ac.d, deg, lane, [&](auto kc, bool on, int) {
           constexpr int k = decltype(kc)::value;
-          const int o = on ? col_start<k>(ac.d) + lane : 0;
+          const int o = col_start<k>(ac.d) + lane;  // lanes without a k-th arc read a neighbour's (ignored)
           dstc[k] = sd[o];
           wc[k] = SC ? sw[o] : 0.0f;
           if (TH) wc[k] += th[on ? sl[o] : 0];  // an empty slice stages nothing: no stale label may index theta
@@ -787,7 +789,7 @@ __global__ void __launch_bounds__(NT_MAX, NT_MAX == 128 ? 7 : NT_MAX == 256 ? SE
         const int32_t* const sl = sd + 2 * SA;
         for_columns<0, NC>(ac.d, deg, lane, [&](auto kc, bool on, int) {  // branch-free, see the pull pass
           constexpr int k = decltype(kc)::value;
-          const int o = on ? col_start<k>(ac.d) + lane : 0;
+          const int o = col_start<k>(ac.d) + lane;  // lanes without a k-th arc read a neighbour's (ignored)
           dstc[k] = sd[o];
           cc[k] = sc[o];
           labc[k] = DTH ? sl[o] : 0;
