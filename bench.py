@@ -337,13 +337,30 @@ def main():
         if i is not None:
             ev[3 * i + 2].record()
         if world > 1:
-            # the path's only collective: the loss all-reduce (posteriors feed the scorer's own backward)
-            loss.copy_(logz.sum().reshape(1))
-            dist.all_reduce(loss)
+            # the path's only collective: the loss all-reduce (posteriors feed the scorer's own backward).  It runs
+            # asynchronously on NCCL's stream, a ring of buffers deep, so that a step's kernels never queue behind
+            # the slowest rank's previous step; every all-reduce is waited for before the timed region ends.
+            k = step.count % len(loss_ring)
+            step.count += 1
+            if pending[k] is not None:
+                pending[k].wait()
+            loss_ring[k].copy_(logz.sum().reshape(1))
+            pending[k] = dist.all_reduce(loss_ring[k], async_op=True)
         return r
+
+    step.count = 0
+    loss_ring = [torch.zeros(1, device=dev, dtype=torch.float32) for _ in range(4)] if world > 1 else []
+    pending = [None] * len(loss_ring)
+
+    def drain():
+        for k, w in enumerate(pending):
+            if w is not None:
+                w.wait()
+                pending[k] = None
 
     for _ in range(max(a.warmup, 3)):
         step()
+    drain()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -356,6 +373,7 @@ def main():
     t_start.record()
     for i in range(a.steps):
         step(i)
+    drain()  # the timed region ends when the last loss all-reduce has completed
     t_end.record()
     torch.cuda.synchronize()
     if world > 1:
