@@ -49,7 +49,7 @@
 extern "C" {
 #endif
 
-#define NFST_ABI_VERSION 10
+#define NFST_ABI_VERSION 11
 
 typedef enum nfst_status {
   NFST_OK = 0,
@@ -125,6 +125,33 @@ typedef struct nfst_packed_lattices {
    * of lattice b (the spare entry of each lattice closes its last level); CSR lattices own no slices. */
   const int32_t* sell_desc;         /* [n_slices][4] */
   const int32_t* sell_lvl_slice;    /* [sum_b (L_b+1)] */
+  /* Tile-stream lattices (launch groups with nfst_launch_t.tiles != 0; see nfst_tile_pull_f32).  The lattice is
+   * dealt to the nw warps of its block at pack time: the states of a level are sorted by out-degree
+   * (descending), cut into slices of 32 (a state with more than 32 arcs is a slice of its own: "heavy"), the
+   * slices are dealt to the warps in serpentine rounds, and states and arcs are numbered so that what one warp
+   * does in one level is a contiguous run of both.  The arcs of a slice are column-major without padding;
+   * consecutive slices of one (level, warp) form TILES, the unit a warp fetches with one bulk copy per array.
+   *   tile_tab     one int32[4] per tile, per (lattice, warp) in level order:
+   *                  [0] canonical id of the tile's first arc, [1] offset of the tile in tile_stream / 16,
+   *                  [2] arcs | segments << 16 | extension blocks << 24, [3] level | (stream bytes / 16) << 16
+   *   tile_lw_off  [n_(lattice,warp) + 1] offsets into tile_tab
+   *   tile_lat_info one int32[4] per lattice: [0] index of its warp 0 in tile_lw_off, [1] W = slots of its DP
+   *                ring (a multiple of 32), [2] first state of its last level (lattice-relative),
+   *                [3] != 0: some arc's destination has left the ring when its source is processed
+   *   tile_stream  per tile, 16-byte aligned: a 16-byte tile header {first state and first arc (both
+   *                lattice-relative), ring slot of the first slice | offset of the slot region << 16,
+   *                level | segments << 16}; one 16-byte header per segment {bytes n_0..n_7 = states with more
+   *                than k arcs, arc offset in the tile (16 bit), states (8), largest degree (8), offset of the
+   *                extension block (16), flags (16)}; 32-byte extension blocks {n_8..n_39}; the arcs'
+   *                destinations as 16-bit ring slots (slot W = "a constant": the last level, or a far arc of a
+   *                segment flagged 1 -- resolved through dst_out); 64 bytes of slot W.  Heavy segments: header
+   *                words {arcs of the state, arcs before this piece}, extension field = arcs of the piece,
+   *                flags 4 (heavy) | 8 (first piece) | 16 (last piece).  Flag 2: a state of the segment
+   *                receives flow from a far arc (nfst_tile_flow_f32 reads gamma_far for it). */
+  const uint8_t* tile_stream;
+  const int32_t* tile_tab;
+  const int32_t* tile_lw_off;
+  const int32_t* tile_lat_info;
 } nfst_packed_lattices_t;
 
 /*
@@ -168,6 +195,18 @@ typedef struct nfst_launch {
    * n_levels = largest level count of the group. */
   int32_t sell;
   int32_t sell_far;
+  /* Tile-stream execution (tiles != 0): one block of block_threads = 32 * nw threads per lattice (nw = the
+   * warps the lattices were dealt to), every warp streams its own tiles through a tile_stages-deep ring of
+   * shared-memory stages filled by bulk copies (TMA) that complete on per-stage mbarriers.  tile_ring = largest
+   * DP ring of the group in slots, tile_cap_arcs / tile_cap_bytes = largest tile of the group (arcs / stream
+   * bytes), tile_far != 0: some lattice has far arcs (the passes then need beta / delta / gamma_far in global
+   * memory), tile_stages: 0 = chosen by the library from the shared memory the launch leaves per block. */
+  int32_t tiles;
+  int32_t tile_ring;
+  int32_t tile_far;
+  int32_t tile_cap_arcs;
+  int32_t tile_cap_bytes;
+  int32_t tile_stages;
 } nfst_launch_t;
 
 /* Arc scores: w(a) = (arc_scores ? arc_scores[a] : 0) + (theta ? theta[label(a)] : 0);
@@ -290,6 +329,30 @@ int nfst_sell_pull_f32(const nfst_packed_lattices_t* lat, const nfst_launch_t* l
 int nfst_sell_flow_f32(const nfst_packed_lattices_t* lat, const nfst_launch_t* launch, const float* cond,
                        const float* grad_logz, float* post, const void* beta, const void* logz, void* alpha,
                        float* dtheta, float* gamma_far, void* cuda_stream);
+
+/*
+ * Tile-stream passes (launch->tiles != 0); same mathematics as the sliced-column passes above.
+ *
+ * nfst_tile_pull_f32 -- deepest level first.  Log semiring when beta, logz_bwd or cond is given: beta[S] /
+ *   logz_bwd[B] (float32, or float64 when launch->state_f64) and cond[A] = exp(w_a + beta[dst_a] - beta[src_a]);
+ *   tropical semiring when backptr is given: delta[S] (optional), backptr[S] (canonical arc id, -1 at sinks),
+ *   vit_score[B] (optional); first maximum in label order wins.  Groups with tile_far need beta (resp. delta).
+ * nfst_tile_flow_f32 -- start level first: post[a] = grad_logz[b] * gamma[src_a] * cond[a] with gamma[start] = 1,
+ *   gamma[dst_a] += gamma[src_a] * cond[a] accumulated in 32-bit FIXED POINT (2^-31 units) with native integer
+ *   shared-memory atomics: the state posteriors carry an absolute error below 1e-9 and the result is bit
+ *   reproducible (integer addition commutes).  post may alias cond.  dtheta[V] += post by label (caller
+ *   zero-fills; accumulated per lattice in fixed point, then added with one float atomic per label).
+ *   gamma_far[S] (float32, zero-filled by the caller) is required for groups with tile_far.
+ * Arc arrays are fetched with bulk copies of the 16-byte-aligned superset of a tile's range: arc_scores, cond
+ *   and label_out must be 16-byte aligned and readable up to the next multiple of 4 elements.
+ */
+size_t nfst_tile_smem_bytes(const nfst_launch_t* launch, int32_t vocab, int pass, int n_f32_arrays, int with_table,
+                            int stages);
+int nfst_tile_pull_f32(const nfst_packed_lattices_t* lat, const nfst_launch_t* launch, const nfst_scores_t* scores,
+                       void* beta, void* logz_bwd, float* cond, float* delta, int32_t* backptr, float* vit_score,
+                       void* cuda_stream);
+int nfst_tile_flow_f32(const nfst_packed_lattices_t* lat, const nfst_launch_t* launch, const float* cond,
+                       const float* grad_logz, float* post, float* dtheta, float* gamma_far, void* cuda_stream);
 
 /*
  * One time step of the lattice-constrained sampling / scoring loop (Sampler.stateful_sample,

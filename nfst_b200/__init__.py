@@ -5,6 +5,7 @@ One hot path of steventan0110/nFST, rebuilt from scratch: log-semiring forward/b
 Viterbi over batched, topologically levelled, CSR-packed lattices.  Hand-written CUDA
 behind a C ABI (``include/nfst_b200.h``); no Triton, no CPU fallback.
 """
+from . import tiles  # noqa: F401
 from .pack import PackedLattices, pack_arcs, pack_dense, dense_arcs  # noqa: F401
 from .ops import (  # noqa: F401
     CapturedForwardBackward,

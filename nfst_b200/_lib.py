@@ -46,6 +46,10 @@ class PackedLatticesC(C.Structure):
         ("out_deg8", C.c_void_p),
         ("sell_desc", C.c_void_p),
         ("sell_lvl_slice", C.c_void_p),
+        ("tile_stream", C.c_void_p),
+        ("tile_tab", C.c_void_p),
+        ("tile_lw_off", C.c_void_p),
+        ("tile_lat_info", C.c_void_p),
     ]
 
 
@@ -70,6 +74,12 @@ class LaunchC(C.Structure):
         ("small_max_levels", C.c_int32),
         ("sell", C.c_int32),
         ("sell_far", C.c_int32),
+        ("tiles", C.c_int32),
+        ("tile_ring", C.c_int32),
+        ("tile_far", C.c_int32),
+        ("tile_cap_arcs", C.c_int32),
+        ("tile_cap_bytes", C.c_int32),
+        ("tile_stages", C.c_int32),
     ]
 
 
@@ -99,6 +109,9 @@ SYMBOLS = {
     "nfst_sell_smem_bytes": (C.c_size_t, [C.POINTER(LaunchC), C.c_int32, C.c_int, C.c_int, C.c_int]),
     "nfst_sell_pull_f32": (C.c_int, [C.POINTER(PackedLatticesC), C.POINTER(LaunchC), C.POINTER(ScoresC)] + [_P] * 7),
     "nfst_sell_flow_f32": (C.c_int, [C.POINTER(PackedLatticesC), C.POINTER(LaunchC)] + [_P] * 9),
+    "nfst_tile_smem_bytes": (C.c_size_t, [C.POINTER(LaunchC), C.c_int32, C.c_int, C.c_int, C.c_int, C.c_int]),
+    "nfst_tile_pull_f32": (C.c_int, [C.POINTER(PackedLatticesC), C.POINTER(LaunchC), C.POINTER(ScoresC)] + [_P] * 7),
+    "nfst_tile_flow_f32": (C.c_int, [C.POINTER(PackedLatticesC), C.POINTER(LaunchC)] + [_P] * 6),
     "nfst_walk_step_f32": (C.c_int, [C.POINTER(PackedLatticesC), C.c_int32, C.c_int32, _P, _P, _P, _P, _P, _P, C.c_float, C.c_int32,
                                      _P, _P, _P, _P, _P, _P, _P]),
     "nfst_sample_paths_f32": (C.c_int, [C.POINTER(PackedLatticesC), C.c_int32, C.c_int32, C.c_int32, C.POINTER(ScoresC), _P,
@@ -132,7 +145,7 @@ def load() -> C.CDLL:
         fn = getattr(lib, name)  # AttributeError if the header and the library disagree
         fn.restype = res
         fn.argtypes = args
-    if lib.nfst_abi_version() != 10:
+    if lib.nfst_abi_version() != 11:
         raise RuntimeError("libnfst_b200.so ABI version mismatch")
     _lib = lib
     return lib

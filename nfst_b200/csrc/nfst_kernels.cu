@@ -1628,6 +1628,8 @@ int check_launch(const nfst_packed_lattices_t* lat, const nfst_launch_t* launch)
   if (!lat || !launch) return fail(NFST_ERR_BAD_ARG, "null lattice or launch descriptor");
   if (launch->sell)
     return fail(NFST_ERR_BAD_ARG, "sliced-column launch group: its arcs are not CSR, use nfst_sell_pull_f32 / nfst_sell_flow_f32");
+  if (launch->tiles)
+    return fail(NFST_ERR_BAD_ARG, "tile-stream launch group: its arcs are not CSR, use nfst_tile_pull_f32 / nfst_tile_flow_f32");
   if (launch->n_ids < 0 || launch->n_ids > lat->n_lattices)
     return fail(NFST_ERR_BAD_ARG, "n_ids=%d out of range (B=%d)", launch->n_ids, lat->n_lattices);
   const int bt = launch->block_threads;
@@ -1948,7 +1950,7 @@ int nfst_backtrace(const nfst_packed_lattices_t* lat, const int32_t* backptr, co
 int nfst_viterbi_paths_f32(const nfst_packed_lattices_t* lat, const nfst_launch_t* launch, const nfst_scores_t* scores,
                            float* delta, int32_t* backptr, float* vit_score, const int32_t* path_off,
                            int32_t* path_arcs, int32_t* path_len, void* cuda_stream) {
-  if (!launch || !launch->sell) {
+  if (!launch || !(launch->sell || launch->tiles)) {
     if (int rc = check_launch(lat, launch)) return rc;
   }
   if (!scores || (!scores->arc_scores && !scores->theta)) return fail(NFST_ERR_BAD_ARG, "need arc_scores and/or theta");
@@ -1960,7 +1962,10 @@ int nfst_viterbi_paths_f32(const nfst_packed_lattices_t* lat, const nfst_launch_
     return launch_small_sc<float, false, true, false, true, false>(lat, launch, scores, nullptr, nullptr, nullptr, nullptr,
                                                                    nullptr, nullptr, nullptr, delta, backptr, vit_score, st,
                                                                    PathOut{path_off, path_arcs, path_len});
-  if (launch->sell) {  // sliced-column group: tropical pull pass (nfst_sell.cu), then the same read-out
+  if (launch->tiles) {  // tile-stream group: tropical pull pass (nfst_tiles.cu), then the same read-out
+    if (int rc = nfst_tile_pull_f32(lat, launch, scores, nullptr, nullptr, nullptr, delta, backptr, vit_score, cuda_stream))
+      return rc;
+  } else if (launch->sell) {  // sliced-column group: tropical pull pass (nfst_sell.cu), then the same read-out
     if (int rc = nfst_sell_pull_f32(lat, launch, scores, nullptr, nullptr, nullptr, delta, backptr, vit_score, cuda_stream))
       return rc;
   } else if (int rc = nfst_bwd_fused_f32(lat, launch, scores, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr,

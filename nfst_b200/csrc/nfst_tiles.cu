@@ -1,0 +1,921 @@
+// nfst_tiles.cu -- "tile stream" execution model of the lattice DP (sm_100a).
+//
+// Same recurrence as nfst_kernels.cu / nfst_sell.cu (the reference's FSAGRUScorer.compute_beta_per_sample,
+// src/modules/scorers.py:692-751, with Wh = 0, in log space; arc scores as in WFSTScorer, scorers.py:1663-1687).
+// What is different is who decides the order of work: the PACKER (nfst_b200/tiles.py) deals every lattice to the
+// nw warps of its block, level by level, and lays states and arcs out so that what one warp does in one level is
+// a contiguous run of both.  A warp therefore walks a private list of TILES (about 384 arcs: a few 32-state
+// slices, column-major without padding) and fetches each with ONE bulk copy per array -- cp.async.bulk (TMA,
+// SASS UBLKCP) issued by lane 0, completing on a per-stage mbarrier (SYNCS) -- into a ring of shared-memory stages
+// that runs several tiles ahead.  No lane computes an address for staging, no warp derives its position in the
+// lattice: the tile's header (which arrives with the tile) says which states and ring slots it covers.
+//
+//   * destinations are 16-bit RING SLOTS computed at pack time: beta[dst] is ring[code], no masking, no range
+//     test; slot W holds the constant of the last level (beta = 0 / delta = 0); an arc whose destination has
+//     left the ring is flagged per slice and resolved through dst_out and global memory (rare);
+//   * slices are processed from registers by a code path specialised for the slice's column count (1..8);
+//     deeper columns (states with 9..32 arcs) loop over the staged tile, states with more arcs are HEAVY:
+//     a slice of their own, possibly cut into several tiles, the whole warp striding over the arcs;
+//   * pull pass (deepest level first): beta[s] = logsumexp_k(w_k + beta[dst_k]) with per-arc terms as float32
+//     offsets from a reference arc, cond[a] = exp(w + beta[dst] - beta[s]); or delta / backpointer with one fp32
+//     add per arc and first-maximum-in-label-order ties (bit exact);
+//   * flow pass (start level first): post[a] = g * gamma[src] * cond[a]; gamma[dst] += gamma[src] * cond[a] in
+//     32-bit fixed point with native integer shared-memory atomics (ATOMS.ADD; a float add there is a
+//     compare-and-swap loop, measured 2.3-5x slower, tools/microbench): deterministic, absolute error < 1e-9;
+//   * one block barrier per level when nw > 1, none when a warp owns the whole lattice (nw = 1).
+#include "nfst_b200.h"
+
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <type_traits>
+
+int nfst_fail_msg(int code, const char* fmt, ...);  // nfst_kernels.cu (sets the thread's last error)
+
+namespace {
+
+#define TILE_CUDA_OK(expr)                                                                                  \
+  do {                                                                                                      \
+    cudaError_t _e = (expr);                                                                                \
+    if (_e != cudaSuccess) return nfst_fail_msg(NFST_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString(_e)); \
+  } while (0)
+
+constexpr int KU = 8;  // arc columns of a slice held in registers
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kLn2 = 0.6931471805599453f;
+constexpr float kFloor = -1.0e30f;
+constexpr float kNegInf = -__builtin_huge_valf();
+constexpr float kFix = 2147483648.0f;  // 2^31: fixed-point unit of the flow pass
+constexpr int FLAG_FAR_OUT = 1, FLAG_FAR_IN = 2, FLAG_HEAVY = 4, FLAG_HEAVY_FIRST = 8, FLAG_HEAVY_LAST = 16;
+
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float lg2_approx(float x) {
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return static_cast<unsigned>(__cvta_generic_to_shared(p)); }
+
+// ---- mbarrier + bulk copy (TMA) ----
+__device__ __forceinline__ void mbar_init(unsigned bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(unsigned dst, const void* src, unsigned bytes, unsigned bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+               "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tWAIT_%=:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void block_bar() { asm volatile("bar.sync 0;" ::: "memory"); }
+
+extern __shared__ __align__(128) unsigned char tile_smem[];
+
+// launch geometry (host-computed; byte offsets into dynamic shared memory)
+struct TP {
+  int stages;       // depth of every warp's stage ring
+  int cap_bytes;    // stream part of a stage (largest tile of the group, 16-byte multiple)
+  int arr_bytes;    // one staged 4-byte-per-arc array (scores / conditionals / labels), 16-byte multiple
+  int stage_bytes;  // cap_bytes + staged arrays
+  int bar_off, table_off, stage_off;
+  int table;        // theta / dtheta table lives in shared memory
+  float hist_scale, hist_inv;  // fixed-point unit of the dtheta histogram
+};
+
+// rare path: the destination has left the ring; its value was written by this block before an earlier level barrier
+template <typename T>
+__device__ __noinline__ T far_load(const T* p, int i) {
+  return *reinterpret_cast<const volatile T*>(p + i);
+}
+
+// online logsumexp pair (m, s): value = m + log(s); branch-free, finite floor instead of -inf
+__device__ __forceinline__ void lse_push(float& m, float& s, float v) {
+  const float d = v - m;
+  const float e = ex2_approx(-fabsf(d) * kLog2e);
+  const bool up = d > 0.0f;
+  s = up ? fmaf(s, e, 1.0f) : s + e;
+  m = up ? v : m;
+}
+__device__ __forceinline__ void lse_join(float& m, float& s, float m2, float s2) {
+  const float d = m2 - m;
+  const float e = ex2_approx(-fabsf(d) * kLog2e);
+  const bool up = d > 0.0f;
+  s = up ? fmaf(s, e, s2) : fmaf(s2, e, s);
+  m = up ? m2 : m;
+}
+
+// states with n_k..: byte k of the two header words
+__device__ __forceinline__ int col_count(const int4& h, int k) {
+  return (static_cast<unsigned>(k < 4 ? h.x : h.y) >> (8 * (k & 3))) & 0xff;
+}
+
+// everything a segment needs to find its data in the landed stage
+struct Seg {
+  const uint16_t* codes;  // ring slots of the tile's arcs (tile-relative arc index)
+  const float* vals;      // staged scores (pull) / conditionals (flow), tile-relative
+  const int32_t* labs;    // staged labels, tile-relative
+  const unsigned char* st;  // the stage (tile header at 0)
+  int arc0;               // canonical id of the tile's first arc
+};
+
+// offset of x from the reference, in float32: (beta - beta_ref) + (w - w_ref), each difference rounded at its own
+// small size (float64 ring: the exact float64 sum first)
+template <typename RingT>
+__device__ __forceinline__ float rel_term(float w, RingT v, float rw, RingT rb) {
+  if constexpr (sizeof(RingT) == 4) return (static_cast<float>(v) - static_cast<float>(rb)) + (w - rw);
+  else return static_cast<float>((static_cast<double>(w) + static_cast<double>(v)) - (static_cast<double>(rw) + static_cast<double>(rb)));
+}
+
+// =====================================================================================
+// pull pass
+// =====================================================================================
+template <bool TROP, bool SC, bool TH, typename OT>
+struct PullCtx {
+  using RingT = typename std::conditional<TROP, float, OT>::type;
+  RingT* ring;
+  const float* th;
+  const int32_t* __restrict__ dst_out;
+  OT* beta;
+  OT* __restrict__ logz;
+  float* cond;
+  float* delta;
+  int32_t* __restrict__ backptr;
+  float* __restrict__ vit;
+  int W, last0, start, b, lane;
+
+  __device__ __forceinline__ float score(const Seg& g, int e, bool on) const {
+    float w = SC ? g.vals[e] : 0.0f;
+    if (TH) w += th[on ? g.labs[e] : 0];  // lanes without an arc read a neighbour's entry: no stale label may index theta
+    return w;
+  }
+  // DP value of the destination of the arc at tile-relative position e (code = its staged ring slot)
+  __device__ __forceinline__ RingT far_value(const Seg& g, int e) const {
+    const int d = dst_out[g.arc0 + e];
+    if (d >= last0) return static_cast<RingT>(0);
+    return TROP ? static_cast<RingT>(far_load(delta, d)) : static_cast<RingT>(far_load(beta, d));
+  }
+  __device__ __forceinline__ void store_state(int s, int slot, RingT v, int arg) const {
+    ring[slot] = v;
+    if (!TROP) {
+      if (beta) beta[s] = static_cast<OT>(v);
+      if (s == start && logz) logz[b] = static_cast<OT>(v);
+    } else {
+      if (delta) delta[s] = static_cast<float>(v);
+      backptr[s] = arg;
+      if (s == start && vit) vit[b] = static_cast<float>(v);
+    }
+  }
+
+  // ---- a regular segment with NC register columns (NC = min(largest degree, KU)) ----
+  template <int NC>
+  __device__ __forceinline__ void regular(const Seg& g, const int4 h, int s0, int vslot) const {
+    const int arc_rel = h.z & 0xffff, nst = (h.z >> 16) & 0xff, dmax = static_cast<unsigned>(h.z) >> 24;
+    const int flags = static_cast<unsigned>(h.w) >> 16;
+    const bool far = flags & FLAG_FAR_OUT;
+    float wc[NC];
+    RingT rv[NC];
+    bool on[NC];
+    int e = arc_rel + lane;
+#pragma unroll
+    for (int k = 0; k < NC; ++k) {
+      const int n = col_count(h, k);
+      on[k] = lane < n;
+      wc[k] = score(g, e, on[k]);
+      rv[k] = ring[g.codes[e]];
+      e += n;
+    }
+    const int e_tail = e;  // this lane's entry in column KU (when the slice has one)
+    if (far) {             // warp-uniform, rare
+      int e2 = arc_rel + lane;
+#pragma unroll
+      for (int k = 0; k < NC; ++k) {
+        if (on[k] && g.codes[e2] == W) rv[k] = far_value(g, e2);
+        e2 += col_count(h, k);
+      }
+    }
+    const unsigned char* nk_ext = g.st + (h.w & 0xffff);  // n_8, n_9, ... (only read when dmax > KU)
+    // f(on, e, w, v) over the columns k >= KU of this lane
+    auto tail = [&](auto&& f) {
+      int et = e_tail;
+      for (int k = KU; k < dmax; ++k) {
+        const int n = nk_ext[k - KU];
+        const bool o = lane < n;
+        const float w = score(g, et, o);
+        RingT v = ring[g.codes[et]];
+        if (far && o && g.codes[et] == W) v = far_value(g, et);
+        f(o, et, w, v);
+        et += n;
+      }
+    };
+    const int s = s0 + lane;
+    if constexpr (!TROP) {
+      // reference arc: the first one (every state with arcs has it); if it scores -inf, the largest
+      float rw = wc[0];
+      RingT rb = rv[0];
+      if (on[0] && !(rw + static_cast<float>(rb) > kFloor)) {
+        float tbest = kFloor;
+        rw = 0.0f;
+        rb = static_cast<RingT>(0);
+#pragma unroll
+        for (int k = 0; k < NC; ++k) {
+          const float t = wc[k] + static_cast<float>(rv[k]);
+          if (on[k] && t > tbest) {
+            tbest = t;
+            rw = wc[k];
+            rb = rv[k];
+          }
+        }
+      }
+      float tf[NC];
+      float mf = kFloor;
+#pragma unroll
+      for (int k = 0; k < NC; ++k) {
+        tf[k] = on[k] ? rel_term<RingT>(wc[k], rv[k], rw, rb) : kFloor;
+        mf = fmaxf(mf, tf[k]);
+      }
+      if (NC == KU && dmax > KU) tail([&](bool o, int, float w, RingT v) { if (o) mf = fmaxf(mf, rel_term<RingT>(w, v, rw, rb)); });
+      mf = fmaxf(mf, kFloor);  // a NaN-free floor
+      float ex[NC];
+      float sum = 0.0f;
+      const float mfl = -mf * kLog2e;
+#pragma unroll
+      for (int k = 0; k < NC; ++k) {
+        // idle lanes / -inf arcs: exp(-huge) = 0
+        if constexpr (sizeof(RingT) == 4) ex[k] = ex2_approx(fmaf(tf[k], kLog2e, mfl));
+        else ex[k] = ex2_approx((tf[k] - mf) * kLog2e);
+        sum += ex[k];
+      }
+      if (NC == KU && dmax > KU)
+        tail([&](bool o, int, float w, RingT v) { if (o) sum += ex2_approx((fmaxf(rel_term<RingT>(w, v, rw, rb), kFloor) - mf) * kLog2e); });
+      if (!(mf > kFloor)) sum = 0.0f;  // no finite arc: every term above was exp(0)
+      // sinks: beta = 1 (scorers.py:720); a state whose arcs all score -inf: beta = -inf
+      RingT bv = static_cast<RingT>(0);
+      const float inv = sum > 0.0f ? rcp_approx(sum) : 0.0f;
+      if (on[0]) {
+        const float lg = lg2_approx(sum) * kLn2;
+        if (!(sum > 0.0f)) bv = static_cast<RingT>(kNegInf);
+        else if constexpr (sizeof(RingT) == 4) bv = rb + (rw + (mf + lg));
+        else bv = rb + (static_cast<double>(rw) + (static_cast<double>(mf) + static_cast<double>(lg)));
+      }
+      if (cond) {
+        int e2 = arc_rel + lane;
+#pragma unroll
+        for (int k = 0; k < NC; ++k) {
+          if (on[k]) cond[g.arc0 + e2] = ex[k] * inv;
+          e2 += col_count(h, k);
+        }
+        if (NC == KU && dmax > KU)
+          tail([&](bool o, int et, float w, RingT v) {
+            if (o) cond[g.arc0 + et] = ex2_approx((fmaxf(rel_term<RingT>(w, v, rw, rb), kFloor) - mf) * kLog2e) * inv;
+          });
+      }
+      if (lane < nst) store_state(s, vslot + lane, bv, 0);
+    } else {
+      float best = 0.0f;
+      int arg = -1;
+      int e2 = arc_rel + lane;
+#pragma unroll
+      for (int k = 0; k < NC; ++k) {
+        const float c = __fadd_rn(wc[k], rv[k]);
+        if (on[k] && (arg < 0 || c > best)) {  // strict: the columns of a state follow its labels
+          best = c;
+          arg = g.arc0 + e2;
+        }
+        e2 += col_count(h, k);
+      }
+      if (NC == KU && dmax > KU)
+        tail([&](bool o, int et, float w, RingT v) {
+          const float c = __fadd_rn(w, v);
+          if (o && c > best) {
+            best = c;
+            arg = g.arc0 + et;
+          }
+        });
+      if (lane < nst) store_state(s, vslot + lane, best, arg);  // sinks: delta = 0, backpointer -1
+    }
+  }
+};
+
+// heavy state carried across the pieces (tiles) of one warp
+struct HeavyLog {
+  float m, s, rw;
+  double rb;  // reference arc (holds either ring precision)
+  int a_first;
+};
+struct HeavyTrop {
+  float best;
+  int arg;
+};
+
+template <bool TROP, bool SC, bool TH, typename OT, int NT_MAX, int MINB>
+__global__ void __launch_bounds__(NT_MAX, MINB)
+    tile_pull_kernel(const nfst_packed_lattices_t L, const int32_t* __restrict__ ids, const TP P,
+                     const float* __restrict__ arc_scores, const float* __restrict__ theta, OT* beta, OT* __restrict__ logz,
+                     float* cond, float* delta, int32_t* __restrict__ backptr, float* __restrict__ vit_score) {
+  using Ctx = PullCtx<TROP, SC, TH, OT>;
+  using RingT = typename Ctx::RingT;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
+  const int b = ids ? ids[blockIdx.x] : blockIdx.x;
+  const int4 info = __ldg(reinterpret_cast<const int4*>(L.tile_lat_info) + b);
+  const int s_base = L.state_off[b];
+  const int a_base = L.out_ptr[s_base];
+  const int n_levels = L.level_off[b + 1] - L.level_off[b] - 1;
+  Ctx c;
+  c.ring = reinterpret_cast<RingT*>(tile_smem);
+  c.th = theta;
+  c.dst_out = L.dst_out;
+  c.beta = beta; c.logz = logz; c.cond = cond; c.delta = delta; c.backptr = backptr; c.vit = vit_score;
+  c.W = info.y;
+  c.last0 = s_base + info.z;
+  c.start = L.start_state[b];
+  c.b = b;
+  c.lane = lane;
+  if (TH && P.table) {
+    float* sth = reinterpret_cast<float*>(tile_smem + P.table_off);
+    for (int i = tid; i < L.vocab; i += blockDim.x) sth[i] = theta[i];
+    c.th = sth;
+  }
+  if (tid == 0) c.ring[c.W] = static_cast<RingT>(0);  // the last level: beta = 1 (scorers.py:720), delta = 0
+  const int D = P.stages;
+  uint64_t* const bars = reinterpret_cast<uint64_t*>(tile_smem + P.bar_off) + warp * D;
+  const unsigned bars_s = smem_u32(bars);
+  if (lane == 0)
+    for (int d = 0; d < D; ++d) mbar_init(bars_s + 8 * d, 1);
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  __syncthreads();
+
+  unsigned char* const my_stage = tile_smem + P.stage_off + static_cast<size_t>(warp) * D * P.stage_bytes;
+  const unsigned stage_s = smem_u32(my_stage);
+  const int lw = info.x + warp;
+  const int t_lo = L.tile_lw_off[lw], t_hi = L.tile_lw_off[lw + 1];
+  const int n_t = t_hi - t_lo;
+  const int4* __restrict__ tab = reinterpret_cast<const int4*>(L.tile_tab);
+  const unsigned char* __restrict__ stream = L.tile_stream;
+  const int32_t* __restrict__ label_out = L.label_out;
+  // lane 0: one expect_tx + one bulk copy per array; the tile's scores / labels are the 16-byte-aligned superset
+  auto issue = [&](int d, const int4 e) {
+    const unsigned st = stage_s + d * P.stage_bytes, bar = bars_s + 8 * d;
+    const int arc0 = e.x, n_arcs = e.z & 0xffff;
+    const unsigned sbytes = (static_cast<unsigned>(e.w) >> 16) << 4;
+    const int a_lo = arc0 & ~3;
+    const unsigned abytes = n_arcs ? static_cast<unsigned>(((arc0 + n_arcs + 3) & ~3) - a_lo) << 2 : 0u;
+    mbar_expect_tx(bar, sbytes + (SC ? abytes : 0u) + (TH ? abytes : 0u));
+    bulk_g2s(st, stream + static_cast<size_t>(e.y) * 16, sbytes, bar);
+    if (abytes) {
+      if (SC) bulk_g2s(st + P.cap_bytes, arc_scores + a_lo, abytes, bar);
+      if (TH) bulk_g2s(st + P.cap_bytes + (SC ? P.arr_bytes : 0), label_out + a_lo, abytes, bar);
+    }
+  };
+  // the pull pass walks the warp's tiles from the deepest level up: i-th tile = t_hi - 1 - i
+  int4 nxt = make_int4(0, 0, 0, 0);
+  if (lane == 0) {
+    for (int i = 0; i < D && i < n_t; ++i) issue(i, __ldg(tab + (t_hi - 1 - i)));
+    if (D < n_t) nxt = __ldg(tab + (t_hi - 1 - D));
+  }
+  HeavyLog hl = {kFloor, 0.0f, 0.0f, 0.0, 0};
+  HeavyTrop ht = {0.0f, -1};
+  int cur = n_levels - 1;
+  int d = 0;
+  unsigned phase = 0;
+#pragma unroll 1
+  for (int i = 0; i < n_t; ++i) {
+    mbar_wait(bars_s + 8 * d, phase);
+    const unsigned char* const st = my_stage + d * P.stage_bytes;
+    const int4 hd = *reinterpret_cast<const int4*>(st);
+    const int level = hd.w & 0xffff, nseg = static_cast<unsigned>(hd.w) >> 16;
+    // every deeper level is complete before this tile reads the ring (one block barrier per level)
+    while (cur > level) {
+      if (nw > 1) block_bar();
+      else __syncwarp();
+      --cur;
+    }
+    Seg g;
+    g.st = st;
+    g.arc0 = hd.y + a_base;
+    g.codes = reinterpret_cast<const uint16_t*>(st + (static_cast<unsigned>(hd.z) >> 16));
+    const int shift = g.arc0 & 3;
+    g.vals = reinterpret_cast<const float*>(st + P.cap_bytes) + shift;
+    g.labs = reinterpret_cast<const int32_t*>(st + P.cap_bytes + (SC ? P.arr_bytes : 0)) + shift;
+    int s0 = hd.x + s_base;
+    int vslot = hd.z & 0xffff;
+#pragma unroll 1
+    for (int sg = 0; sg < nseg; ++sg) {
+      const int4 h = *reinterpret_cast<const int4*>(st + 16 + 16 * sg);
+      const int flags = static_cast<unsigned>(h.w) >> 16;
+      if (flags & FLAG_HEAVY) {
+        // ---- a piece of a heavy state: the warp strides over its arcs ----
+        const int n = h.w & 0xffff;  // arcs of this piece
+        const bool far = flags & FLAG_FAR_OUT;
+        if (!TROP) {
+          if (flags & FLAG_HEAVY_FIRST) {
+            float w0 = c.score(g, 0, true);
+            RingT v0 = c.ring[g.codes[0]];
+            if (far && g.codes[0] == c.W) v0 = c.far_value(g, 0);
+            if (!(w0 + static_cast<float>(v0) > kFloor)) { w0 = 0.0f; v0 = static_cast<RingT>(0); }
+            hl.m = kFloor; hl.s = 0.0f; hl.rw = w0; hl.rb = static_cast<double>(v0);
+            hl.a_first = g.arc0;
+          }
+          const RingT rb = static_cast<RingT>(hl.rb);
+#pragma unroll 2
+          for (int e = lane; e < n; e += 32) {
+            const float w = c.score(g, e, true);
+            RingT v = c.ring[g.codes[e]];
+            if (far && g.codes[e] == c.W) v = c.far_value(g, e);
+            const float t = fmaxf(rel_term<RingT>(w, v, hl.rw, rb), kFloor);
+            lse_push(hl.m, hl.s, t);
+            if (cond) cond[g.arc0 + e] = t;  // provisional: the offset; rescaled below once beta is known
+          }
+          if (flags & FLAG_HEAVY_LAST) {
+            float m = hl.m, s = hl.s;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+              const float m2 = __shfl_xor_sync(0xffffffffu, m, o);
+              const float s2 = __shfl_xor_sync(0xffffffffu, s, o);
+              lse_join(m, s, m2, s2);
+            }
+            const bool finite = m > kFloor && s > 0.0f;
+            RingT bv = static_cast<RingT>(kNegInf);
+            if (finite) {
+              const float lg = lg2_approx(s) * kLn2;
+              if constexpr (sizeof(RingT) == 4) bv = rb + (hl.rw + (m + lg));
+              else bv = rb + (static_cast<double>(hl.rw) + (static_cast<double>(m) + static_cast<double>(lg)));
+            }
+            if (lane == 0) c.store_state(s0, vslot, bv, 0);
+            if (cond) {
+              const int total = h.x;  // arcs of the whole state; every lane re-reads what it wrote itself
+              const float inv = finite ? rcp_approx(s) : 0.0f;
+              for (int e = lane; e < total; e += 32) {
+                const float t = cond[hl.a_first + e];
+                cond[hl.a_first + e] = finite ? ex2_approx((t - m) * kLog2e) * inv : 0.0f;
+              }
+            }
+          }
+        } else {
+          if (flags & FLAG_HEAVY_FIRST) { ht.best = 0.0f; ht.arg = -1; }
+#pragma unroll 2
+          for (int e = lane; e < n; e += 32) {
+            const float w = c.score(g, e, true);
+            RingT v = c.ring[g.codes[e]];
+            if (far && g.codes[e] == c.W) v = c.far_value(g, e);
+            const float cnd = __fadd_rn(w, v);
+            if (ht.arg < 0 || cnd > ht.best) {  // a lane's arcs ascend: its first maximum stays
+              ht.best = cnd;
+              ht.arg = g.arc0 + e;
+            }
+          }
+          if (flags & FLAG_HEAVY_LAST) {
+            float best = ht.best;
+            int arg = ht.arg;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+              const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+              const int oa = __shfl_xor_sync(0xffffffffu, arg, o);
+              if (oa >= 0 && (arg < 0 || ob > best || (ob == best && oa < arg))) {
+                best = ob;
+                arg = oa;
+              }
+            }
+            if (lane == 0) c.store_state(s0, vslot, best, arg);
+          }
+        }
+      } else {
+        const int dmax = static_cast<unsigned>(h.z) >> 24;
+        switch (dmax < KU ? dmax : KU) {
+          case 0: if (lane < ((h.z >> 16) & 0xff)) c.store_state(s0 + lane, vslot + lane, static_cast<RingT>(0), -1); break;
+          case 1: c.template regular<1>(g, h, s0, vslot); break;
+          case 2: c.template regular<2>(g, h, s0, vslot); break;
+          case 3: c.template regular<3>(g, h, s0, vslot); break;
+          case 4: c.template regular<4>(g, h, s0, vslot); break;
+          case 5: c.template regular<5>(g, h, s0, vslot); break;
+          case 6: c.template regular<6>(g, h, s0, vslot); break;
+          case 7: c.template regular<7>(g, h, s0, vslot); break;
+          default: c.template regular<8>(g, h, s0, vslot); break;
+        }
+      }
+      s0 += 32;
+      vslot += 32;
+      if (vslot >= c.W) vslot -= c.W;
+    }
+    __syncwarp();  // every lane is done with the stage: refill it
+    if (lane == 0 && i + D < n_t) {
+      issue(d, nxt);
+      if (i + D + 1 < n_t) nxt = __ldg(tab + (t_hi - 1 - (i + D + 1)));
+    }
+    if (++d == D) {
+      d = 0;
+      phase ^= 1;
+    }
+  }
+  // warps that run out of tiles keep the level barriers company
+  if (nw > 1)
+    while (cur > 0) {
+      block_bar();
+      --cur;
+    }
+}
+
+// =====================================================================================
+// flow pass
+// =====================================================================================
+template <bool DTH, int NT_MAX, int MINB>
+__global__ void __launch_bounds__(NT_MAX, MINB)
+    tile_flow_kernel(const nfst_packed_lattices_t L, const int32_t* __restrict__ ids, const TP P, const float* cond,
+                     const float* __restrict__ grad_logz, float* post, float* __restrict__ dtheta, float* gamma_far) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
+  const int b = ids ? ids[blockIdx.x] : blockIdx.x;
+  const int4 info = __ldg(reinterpret_cast<const int4*>(L.tile_lat_info) + b);
+  const int s_base = L.state_off[b];
+  const int a_base = L.out_ptr[s_base];
+  const int n_levels = L.level_off[b + 1] - L.level_off[b] - 1;
+  const int W = info.y, last0 = s_base + info.z;
+  unsigned* const ring = reinterpret_cast<unsigned*>(tile_smem);
+  unsigned* hist = nullptr;
+  for (int i = tid; i <= W; i += blockDim.x) ring[i] = 0u;
+  if (DTH && P.table) {
+    hist = reinterpret_cast<unsigned*>(tile_smem + P.table_off);
+    for (int i = tid; i < L.vocab; i += blockDim.x) hist[i] = 0u;
+  }
+  const int D = P.stages;
+  uint64_t* const bars = reinterpret_cast<uint64_t*>(tile_smem + P.bar_off) + warp * D;
+  const unsigned bars_s = smem_u32(bars);
+  if (lane == 0)
+    for (int d = 0; d < D; ++d) mbar_init(bars_s + 8 * d, 1);
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  __syncthreads();
+  if (tid == 0) ring[0] = 0x80000000u;  // gamma[start] = 1: the start state is state 0 / slot 0 of its lattice
+  __syncthreads();
+  const float gl = grad_logz ? grad_logz[b] : 1.0f;
+  const float unfix = gl * (1.0f / kFix);  // fixed-point gamma -> gradient-scaled posterior mass
+  const int32_t* __restrict__ dst_out = L.dst_out;
+
+  unsigned char* const my_stage = tile_smem + P.stage_off + static_cast<size_t>(warp) * D * P.stage_bytes;
+  const unsigned stage_s = smem_u32(my_stage);
+  const int lw = info.x + warp;
+  const int t_lo = L.tile_lw_off[lw], t_hi = L.tile_lw_off[lw + 1];
+  const int n_t = t_hi - t_lo;
+  const int4* __restrict__ tab = reinterpret_cast<const int4*>(L.tile_tab);
+  const unsigned char* __restrict__ stream = L.tile_stream;
+  const int32_t* __restrict__ label_out = L.label_out;
+  auto issue = [&](int d, const int4 e) {
+    const unsigned st = stage_s + d * P.stage_bytes, bar = bars_s + 8 * d;
+    const int arc0 = e.x, n_arcs = e.z & 0xffff;
+    const unsigned sbytes = (static_cast<unsigned>(e.w) >> 16) << 4;
+    const int a_lo = arc0 & ~3;
+    const unsigned abytes = n_arcs ? static_cast<unsigned>(((arc0 + n_arcs + 3) & ~3) - a_lo) << 2 : 0u;
+    mbar_expect_tx(bar, sbytes + abytes + (DTH ? abytes : 0u));
+    bulk_g2s(st, stream + static_cast<size_t>(e.y) * 16, sbytes, bar);
+    if (abytes) {
+      bulk_g2s(st + P.cap_bytes, cond + a_lo, abytes, bar);
+      if (DTH) bulk_g2s(st + P.cap_bytes + P.arr_bytes, label_out + a_lo, abytes, bar);
+    }
+  };
+  int4 nxt = make_int4(0, 0, 0, 0);
+  if (lane == 0) {
+    for (int i = 0; i < D && i < n_t; ++i) issue(i, __ldg(tab + t_lo + i));
+    if (D < n_t) nxt = __ldg(tab + t_lo + D);
+  }
+  // one arc: posterior out, flow into the destination's ring slot (or, for a far arc, global memory)
+  auto push = [&](const Seg& g, int e, float gam, bool far) {
+    const float cd = g.vals[e];
+    const unsigned code = g.codes[e];
+    const float pf = gam * cd;  // in fixed-point units (gam = gamma * 2^31)
+    post[g.arc0 + e] = pf * unfix;
+    atomicAdd(&ring[code], __float2uint_rn(pf));
+    if (far && code == static_cast<unsigned>(W)) {
+      const int dd = dst_out[g.arc0 + e];
+      if (dd < last0) atomicAdd(gamma_far + dd, pf * (1.0f / kFix));
+    }
+    if (DTH) {
+      const float pr = pf * (1.0f / kFix);
+      if (hist) atomicAdd(&hist[g.labs[e]], __float2uint_rn(pr * P.hist_scale));
+      else atomicAdd(dtheta + g.labs[e], pr * gl);
+    }
+  };
+  float heavy_gam = 0.0f;
+  int cur = 0;
+  int d = 0;
+  unsigned phase = 0;
+#pragma unroll 1
+  for (int i = 0; i < n_t; ++i) {
+    mbar_wait(bars_s + 8 * d, phase);
+    const unsigned char* const st = my_stage + d * P.stage_bytes;
+    const int4 hd = *reinterpret_cast<const int4*>(st);
+    const int level = hd.w & 0xffff, nseg = static_cast<unsigned>(hd.w) >> 16;
+    while (cur < level) {
+      if (nw > 1) block_bar();
+      else __syncwarp();
+      ++cur;
+    }
+    Seg g;
+    g.st = st;
+    g.arc0 = hd.y + a_base;
+    g.codes = reinterpret_cast<const uint16_t*>(st + (static_cast<unsigned>(hd.z) >> 16));
+    const int shift = g.arc0 & 3;
+    g.vals = reinterpret_cast<const float*>(st + P.cap_bytes) + shift;
+    g.labs = reinterpret_cast<const int32_t*>(st + P.cap_bytes + P.arr_bytes) + shift;
+    int s0 = hd.x + s_base;
+    int vslot = hd.z & 0xffff;
+#pragma unroll 1
+    for (int sg = 0; sg < nseg; ++sg) {
+      const int4 h = *reinterpret_cast<const int4*>(st + 16 + 16 * sg);
+      const int flags = static_cast<unsigned>(h.w) >> 16;
+      const bool far = flags & FLAG_FAR_OUT;
+      if (flags & FLAG_HEAVY) {
+        if (flags & FLAG_HEAVY_FIRST) {
+          // every arc into the state comes from a shallower level: gamma is final; free the slot
+          heavy_gam = static_cast<float>(ring[vslot]);
+          if (flags & FLAG_FAR_IN) heavy_gam += *reinterpret_cast<volatile float*>(gamma_far + s0) * kFix;
+          __syncwarp();
+          if (lane == 0) ring[vslot] = 0u;
+        }
+        const int n = h.w & 0xffff;
+#pragma unroll 2
+        for (int e = lane; e < n; e += 32) push(g, e, heavy_gam, far);
+      } else {
+        const int arc_rel = h.z & 0xffff, nst = (h.z >> 16) & 0xff, dmax = static_cast<unsigned>(h.z) >> 24;
+        float gam = 0.0f;
+        if (lane < nst) {
+          gam = static_cast<float>(ring[vslot + lane]);
+          ring[vslot + lane] = 0u;
+          if (flags & FLAG_FAR_IN) gam += *reinterpret_cast<volatile float*>(gamma_far + s0 + lane) * kFix;
+        }
+        int e = arc_rel + lane;
+        auto cols = [&](auto nc) {
+          constexpr int NC = decltype(nc)::value;
+#pragma unroll
+          for (int k = 0; k < NC; ++k) {
+            const int n = col_count(h, k);
+            if (lane < n) push(g, e, gam, far);
+            e += n;
+          }
+        };
+        switch (dmax < KU ? dmax : KU) {
+          case 0: break;
+          case 1: cols(std::integral_constant<int, 1>{}); break;
+          case 2: cols(std::integral_constant<int, 2>{}); break;
+          case 3: cols(std::integral_constant<int, 3>{}); break;
+          case 4: cols(std::integral_constant<int, 4>{}); break;
+          case 5: cols(std::integral_constant<int, 5>{}); break;
+          case 6: cols(std::integral_constant<int, 6>{}); break;
+          case 7: cols(std::integral_constant<int, 7>{}); break;
+          default: cols(std::integral_constant<int, 8>{}); break;
+        }
+        if (dmax > KU) {
+          const unsigned char* nk_ext = st + (h.w & 0xffff);
+          for (int k = KU; k < dmax; ++k) {
+            const int n = nk_ext[k - KU];
+            if (lane < n) push(g, e, gam, far);
+            e += n;
+          }
+        }
+      }
+      s0 += 32;
+      vslot += 32;
+      if (vslot >= W) vslot -= W;
+    }
+    __syncwarp();
+    if (lane == 0 && i + D < n_t) {
+      issue(d, nxt);
+      if (i + D + 1 < n_t) nxt = __ldg(tab + t_lo + i + D + 1);
+    }
+    if (++d == D) {
+      d = 0;
+      phase ^= 1;
+    }
+  }
+  if (nw > 1)
+    while (cur < n_levels - 1) {
+      block_bar();
+      ++cur;
+    }
+  if (DTH && hist) {
+    __syncthreads();
+    const float sc = P.hist_inv * gl;
+    for (int i = tid; i < L.vocab; i += blockDim.x) {
+      const unsigned v = hist[i];
+      if (v) atomicAdd(dtheta + i, static_cast<float>(v) * sc);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------------
+size_t round_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+struct Geometry {
+  TP p;
+  size_t smem;
+};
+
+// shared memory of a launch: ring (+ constant slot), mbarriers, theta / dtheta table, the warps' stage rings
+Geometry geometry(const nfst_launch_t* launch, int vocab, int ring_elem_bytes, int n_arrays, bool table, int stages) {
+  Geometry g;
+  const int nw = launch->block_threads / 32;
+  size_t o = round_up(static_cast<size_t>(launch->tile_ring + 32) * ring_elem_bytes, 16);
+  g.p.bar_off = static_cast<int>(o);
+  o += round_up(static_cast<size_t>(nw) * stages * 8, 16);
+  g.p.table = table ? 1 : 0;
+  g.p.table_off = static_cast<int>(o);
+  if (table) o += round_up(static_cast<size_t>(vocab) * 4, 16);
+  o = round_up(o, 128);
+  g.p.stage_off = static_cast<int>(o);
+  g.p.stages = stages;
+  g.p.cap_bytes = static_cast<int>(round_up(launch->tile_cap_bytes, 16));
+  g.p.arr_bytes = static_cast<int>(round_up(static_cast<size_t>(launch->tile_cap_arcs + 8) * 4, 16));
+  g.p.stage_bytes = g.p.cap_bytes + n_arrays * g.p.arr_bytes;
+  g.p.hist_scale = g.p.hist_inv = 1.0f;
+  g.smem = o + static_cast<size_t>(nw) * stages * g.p.stage_bytes;
+  return g;
+}
+
+int sm_count() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+  }
+  return n;
+}
+
+// stage depth: as deep as the shared memory left per block allows when every lattice of the launch is to be
+// resident at once (1024 lattices on 148 SMs: 7 blocks per SM), between 2 and 4 (NFST_TILE_STAGES overrides)
+Geometry pick_geometry(const nfst_launch_t* launch, int vocab, int ring_elem_bytes, int n_arrays, bool table) {
+  static const int forced = getenv("NFST_TILE_STAGES") ? atoi(getenv("NFST_TILE_STAGES")) : 0;
+  int stages = launch->tile_stages > 0 ? launch->tile_stages : forced;
+  if (stages > 0) return geometry(launch, vocab, ring_elem_bytes, n_arrays, table, stages < 2 ? 2 : stages > 8 ? 8 : stages);
+  int want = (launch->n_ids + sm_count() - 1) / sm_count();
+  const int by_threads = 2048 / launch->block_threads;
+  if (want > by_threads) want = by_threads;
+  if (want > 32) want = 32;
+  if (want < 1) want = 1;
+  const size_t budget = (228u * 1024u) / want - 1024u;
+  for (int s = 4; s > 2; --s) {
+    Geometry g = geometry(launch, vocab, ring_elem_bytes, n_arrays, table, s);
+    if (g.smem <= budget) return g;
+  }
+  return geometry(launch, vocab, ring_elem_bytes, n_arrays, table, 2);
+}
+
+bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+template <typename K>
+int prepare(K kernel, size_t smem) {
+  if (smem > 48 * 1024) {
+    TILE_CUDA_OK(cudaFuncSetAttribute(reinterpret_cast<const void*>(kernel), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      static_cast<int>(smem)));
+  }
+  return 0;
+}
+
+int check_launch(const nfst_packed_lattices_t* lat, const nfst_launch_t* launch) {
+  if (!lat || !launch) return nfst_fail_msg(NFST_ERR_BAD_ARG, "null argument");
+  if (!launch->tiles) return nfst_fail_msg(NFST_ERR_BAD_ARG, "launch group is not a tile-stream group");
+  if (!lat->tile_stream || !lat->tile_tab || !lat->tile_lw_off || !lat->tile_lat_info)
+    return nfst_fail_msg(NFST_ERR_BAD_ARG, "packed lattices carry no tile-stream arrays");
+  const int nt = launch->block_threads;
+  if (nt < 32 || nt > 1024 || (nt & (nt - 1))) return nfst_fail_msg(NFST_ERR_BAD_ARG, "block_threads must be a power of two in 32..1024");
+  if (launch->tile_ring < 32 || (launch->tile_ring & 31)) return nfst_fail_msg(NFST_ERR_BAD_ARG, "tile_ring must be a positive multiple of 32");
+  if (launch->tile_cap_bytes <= 0 || launch->tile_cap_arcs < 0) return nfst_fail_msg(NFST_ERR_BAD_ARG, "tile_cap_bytes / tile_cap_arcs are required");
+  if (!aligned16(lat->tile_stream) || !aligned16(lat->tile_tab) || !aligned16(lat->tile_lat_info))
+    return nfst_fail_msg(NFST_ERR_BAD_ARG, "tile_stream, tile_tab and tile_lat_info must be 16-byte aligned");
+  return 0;
+}
+
+// register budgets: blocks of up to 64 threads may use 128 registers, 128-thread blocks 72 (7 blocks per SM),
+// 256-thread blocks 64 (4 per SM), larger blocks 64
+#define TILE_BY_BLOCK(CALL)                         \
+  do {                                              \
+    if (launch->block_threads <= 64) CALL(64, 7);   \
+    else if (launch->block_threads <= 128) CALL(128, 7); \
+    else if (launch->block_threads <= 256) CALL(256, 4); \
+    else CALL(1024, 1);                             \
+  } while (0)
+
+template <bool TROP, typename OT>
+int launch_pull(const nfst_packed_lattices_t* lat, const nfst_launch_t* launch, const nfst_scores_t* sc, OT* beta, OT* logz,
+                float* cond, float* delta, int32_t* backptr, float* vit, cudaStream_t stream) {
+  const bool has_sc = sc->arc_scores != nullptr, has_th = sc->theta != nullptr;
+  const bool table = has_th && lat->vocab <= NFST_THETA_SMEM_MAX;
+  const Geometry g = pick_geometry(launch, lat->vocab, TROP ? 4 : static_cast<int>(sizeof(OT)), (has_sc ? 1 : 0) + (has_th ? 1 : 0), table);
+  if (g.smem > 227 * 1024) return nfst_fail_msg(NFST_ERR_TOO_LARGE, "tile-stream launch needs %zu bytes of shared memory", g.smem);
+  if ((has_sc && !aligned16(sc->arc_scores)) || (has_th && !aligned16(lat->label_out)))
+    return nfst_fail_msg(NFST_ERR_BAD_ARG, "arc_scores and label_out must be 16-byte aligned (they are fetched with bulk copies)");
+#define PULL_NT(NTv, MINBv)                                                                                     \
+  do {                                                                                                          \
+    if (has_sc && has_th) {                                                                                     \
+      auto k = tile_pull_kernel<TROP, true, true, OT, NTv, MINBv>;                                              \
+      if (int rc = prepare(k, g.smem)) return rc;                                                               \
+      k<<<launch->n_ids, launch->block_threads, g.smem, stream>>>(*lat, launch->lattice_ids, g.p, sc->arc_scores, sc->theta, \
+                                                                  beta, logz, cond, delta, backptr, vit);       \
+    } else if (has_th) {                                                                                        \
+      auto k = tile_pull_kernel<TROP, false, true, OT, NTv, MINBv>;                                             \
+      if (int rc = prepare(k, g.smem)) return rc;                                                               \
+      k<<<launch->n_ids, launch->block_threads, g.smem, stream>>>(*lat, launch->lattice_ids, g.p, sc->arc_scores, sc->theta, \
+                                                                  beta, logz, cond, delta, backptr, vit);       \
+    } else {                                                                                                    \
+      auto k = tile_pull_kernel<TROP, true, false, OT, NTv, MINBv>;                                             \
+      if (int rc = prepare(k, g.smem)) return rc;                                                               \
+      k<<<launch->n_ids, launch->block_threads, g.smem, stream>>>(*lat, launch->lattice_ids, g.p, sc->arc_scores, sc->theta, \
+                                                                  beta, logz, cond, delta, backptr, vit);       \
+    }                                                                                                           \
+  } while (0)
+  TILE_BY_BLOCK(PULL_NT);
+#undef PULL_NT
+  TILE_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+size_t nfst_tile_smem_bytes(const nfst_launch_t* launch, int32_t vocab, int pass, int n_f32_arrays, int with_table, int stages) {
+  if (!launch || !launch->tiles) return 0;
+  const bool table = with_table && vocab <= NFST_THETA_SMEM_MAX;
+  const int elem = pass == 0 && launch->state_f64 ? 8 : 4;
+  if (stages > 0) return geometry(launch, vocab, elem, n_f32_arrays, table, stages).smem;
+  return pick_geometry(launch, vocab, elem, n_f32_arrays, table).smem;
+}
+
+int nfst_tile_pull_f32(const nfst_packed_lattices_t* lat, const nfst_launch_t* launch, const nfst_scores_t* scores, void* beta,
+                       void* logz_bwd, float* cond, float* delta, int32_t* backptr, float* vit_score, void* cuda_stream) {
+  if (int rc = check_launch(lat, launch)) return rc;
+  if (!scores || (!scores->arc_scores && !scores->theta)) return nfst_fail_msg(NFST_ERR_BAD_ARG, "arc_scores or theta is required");
+  if (launch->n_ids == 0) return 0;
+  cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
+  const bool logs = beta || logz_bwd || cond;
+  const bool trop = delta || backptr || vit_score;
+  if (trop && !backptr) return nfst_fail_msg(NFST_ERR_BAD_ARG, "the tropical pass needs backptr[S]");
+  if (launch->tile_far && ((logs && !beta) || (trop && !delta)))
+    return nfst_fail_msg(NFST_ERR_BAD_ARG, "a group with far arcs (tile_far) needs beta[S] / delta[S]");
+  if (logs) {
+    const int rc = launch->state_f64
+                       ? launch_pull<false, double>(lat, launch, scores, static_cast<double*>(beta), static_cast<double*>(logz_bwd), cond,
+                                                    nullptr, nullptr, nullptr, stream)
+                       : launch_pull<false, float>(lat, launch, scores, static_cast<float*>(beta), static_cast<float*>(logz_bwd), cond,
+                                                   nullptr, nullptr, nullptr, stream);
+    if (rc) return rc;
+  }
+  if (trop) {
+    if (int rc = launch_pull<true, float>(lat, launch, scores, nullptr, nullptr, nullptr, delta, backptr, vit_score, stream)) return rc;
+  }
+  return 0;
+}
+
+int nfst_tile_flow_f32(const nfst_packed_lattices_t* lat, const nfst_launch_t* launch, const float* cond, const float* grad_logz,
+                       float* post, float* dtheta, float* gamma_far, void* cuda_stream) {
+  if (int rc = check_launch(lat, launch)) return rc;
+  if (!cond || !post) return nfst_fail_msg(NFST_ERR_BAD_ARG, "cond[A] and post[A] are required");
+  if (launch->tile_far && !gamma_far) return nfst_fail_msg(NFST_ERR_BAD_ARG, "gamma_far[S] is required for groups with far arcs (tile_far)");
+  if (launch->n_ids == 0) return 0;
+  cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
+  const bool table = dtheta && lat->vocab <= NFST_THETA_SMEM_MAX;
+  Geometry g = pick_geometry(launch, lat->vocab, 4, dtheta ? 2 : 1, table);
+  // dtheta histogram unit: an expected label count is at most the number of levels
+  int lv = 1;
+  while (lv < launch->n_levels) lv <<= 1;
+  g.p.hist_scale = kFix / static_cast<float>(lv);
+  g.p.hist_inv = static_cast<float>(lv) / kFix;
+  if (g.smem > 227 * 1024) return nfst_fail_msg(NFST_ERR_TOO_LARGE, "tile-stream launch needs %zu bytes of shared memory", g.smem);
+  if (!aligned16(cond) || (dtheta && !aligned16(lat->label_out)))
+    return nfst_fail_msg(NFST_ERR_BAD_ARG, "cond and label_out must be 16-byte aligned (they are fetched with bulk copies)");
+#define FLOW_NT(NTv, MINBv)                                                                                               \
+  do {                                                                                                                    \
+    if (dtheta) {                                                                                                         \
+      auto k = tile_flow_kernel<true, NTv, MINBv>;                                                                        \
+      if (int rc = prepare(k, g.smem)) return rc;                                                                         \
+      k<<<launch->n_ids, launch->block_threads, g.smem, stream>>>(*lat, launch->lattice_ids, g.p, cond, grad_logz, post, dtheta, \
+                                                                  gamma_far);                                             \
+    } else {                                                                                                              \
+      auto k = tile_flow_kernel<false, NTv, MINBv>;                                                                       \
+      if (int rc = prepare(k, g.smem)) return rc;                                                                         \
+      k<<<launch->n_ids, launch->block_threads, g.smem, stream>>>(*lat, launch->lattice_ids, g.p, cond, grad_logz, post, dtheta, \
+                                                                  gamma_far);                                             \
+    }                                                                                                                     \
+  } while (0)
+  TILE_BY_BLOCK(FLOW_NT);
+#undef FLOW_NT
+  TILE_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+}  // extern "C"

@@ -39,6 +39,8 @@ def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
 WINDOW_BYTES_MAX = pack_mod.WINDOW_BYTES_MAX
 # lattices deeper than this default to float64 state vectors (see resolve_state_dtype)
 F64_DEPTH = 96
+# depth of the tile-stream kernels' stage rings; 0 = chosen by the library from the shared memory per block
+TILE_STAGES = int(os.environ.get("NFST_TILE_STAGES", "0"))
 
 
 def resolve_state_dtype(packed: PackedLattices, state_dtype="auto") -> torch.dtype:
@@ -85,6 +87,12 @@ def _launch(g: LaunchGroup, st_dtype: torch.dtype) -> "_lib.LaunchC":
         c.sell_far = int(g.sell_far)
         c.window_states = g.sell_window
         c.n_levels = g.n_levels
+    if g.tiles:  # tile-stream group: ring slots and tile sizes were fixed at pack time
+        c.tiles = 1
+        c.tile_ring, c.tile_far = g.tile_ring, int(g.tile_far)
+        c.tile_cap_arcs, c.tile_cap_bytes = g.tile_cap_arcs, g.tile_cap_bytes
+        c.tile_stages = TILE_STAGES
+        c.n_levels = g.n_levels
     if g.fwd_level_chunks is not None:  # level-major group: one launch per topological level
         c.n_levels = g.n_levels
         c.fwd_level_chunks = g.fwd_level_chunks.data_ptr()
@@ -128,7 +136,7 @@ def _scores(packed: PackedLattices, arc_scores, theta):
 def _gamma_far(packed: PackedLattices, alpha: bool = False) -> Optional[torch.Tensor]:
     """zero-filled float32 [S] for the flow pass of groups whose ring does not cover every arc (and of every
     sliced-column group when alpha is wanted: the flow into the last level is only needed for it)"""
-    if any(g.sell and (g.sell_far or alpha) for g in packed.groups):
+    if any((g.sell and (g.sell_far or alpha)) or (g.tiles and g.tile_far) for g in packed.groups):
         return torch.zeros(packed.n_states, dtype=torch.float32, device=packed.device)
     return None
 
@@ -178,7 +186,7 @@ def lattice_forward(packed: PackedLattices, arc_scores=None, theta=None, *, stat
         streams = _GroupStreams(dev, len(packed.groups))
         for i, g in enumerate(packed.groups):
             # sliced-column groups: their in-order arrays are plain CSR by destination, the forward kernel runs on them
-            lc = _launch_csr_forward(g, st) if g.sell else _launch(g, st)
+            lc = _launch_csr_forward(g, st) if (g.sell or g.tiles) else _launch(g, st)
             _lib.check(lib.nfst_fwd_f32(packed.c_struct(), lc, sc, alpha.data_ptr(), logz.data_ptr(), streams[i]))
             launch_count += 1
         streams.join()
@@ -199,19 +207,22 @@ def lattice_pull(packed: PackedLattices, arc_scores=None, theta=None, *, state_d
     dev = packed.device
     sc, keep = _scores(packed, arc_scores, theta)
     st = resolve_state_dtype(packed, state_dtype)
-    any_csr = any(not g.sell for g in packed.groups)
+    any_csr = any(not (g.sell or g.tiles) for g in packed.groups)
     alpha = torch.empty(packed.n_states, dtype=st, device=dev) if any_csr else None
-    cond = torch.empty(packed.n_arcs, dtype=torch.float32, device=dev) if packed.has_sell else None
+    cond = torch.empty(packed.n_arcs, dtype=torch.float32, device=dev) if packed.has_columns else None
     logz = torch.empty(packed.n_lattices, dtype=st, device=dev)
     if beta_out is not None and (beta_out.dtype != st or beta_out.numel() != packed.n_states or beta_out.device != dev):
         raise ValueError("beta_out must be [S] in the state dtype on the lattices' device")
-    if beta_out is None and any(g.sell and g.sell_far for g in packed.groups):
+    if beta_out is None and any((g.sell and g.sell_far) or (g.tiles and g.tile_far) for g in packed.groups):
         beta_out = torch.empty(packed.n_states, dtype=st, device=dev)  # arcs longer than the ring re-read beta
     with torch.cuda.device(dev):
         streams = _GroupStreams(dev, len(packed.groups))
         for i, g in enumerate(packed.groups):
             lc = _launch(g, st)
-            if g.sell:
+            if g.tiles:
+                _lib.check(lib.nfst_tile_pull_f32(packed.c_struct(), lc, sc, _ptr(beta_out), logz.data_ptr(),
+                                                  cond.data_ptr(), None, None, None, streams[i]))
+            elif g.sell:
                 _lib.check(lib.nfst_sell_pull_f32(packed.c_struct(), lc, sc, _ptr(beta_out), logz.data_ptr(),
                                                   cond.data_ptr(), None, None, None, streams[i]))
             else:
@@ -249,23 +260,27 @@ def lattice_backward(
     sc, keep = _scores(packed, arc_scores, theta)
     S, A, B, V = packed.n_states, packed.n_arcs, packed.n_lattices, packed.vocab
     logs = want_beta or want_post or want_dtheta
-    any_csr = any(not g.sell for g in packed.groups)
+    any_csr = any(not (g.sell or g.tiles) for g in packed.groups)
     if (want_post or want_dtheta) and any_csr and (alpha is None or logz is None):
         raise ValueError("posteriors need alpha and logz from lattice_forward")
+    if alpha is not None and logz is None:
+        raise ValueError("alpha needs the logz of the same lattice_forward / lattice_pull call")
     st = alpha.dtype if alpha is not None else (logz.dtype if logz is not None else resolve_state_dtype(packed, state_dtype))
     if alpha is not None and (logz.dtype != st or alpha.numel() != S or logz.numel() != B):
         raise ValueError("alpha / logz must come from lattice_forward on the same packed batch")
     out = {}
     f32 = dict(dtype=torch.float32, device=dev)
     beta = torch.empty(S, dtype=st, device=dev) if logs else None
-    logz_bwd = torch.empty(B, dtype=st, device=dev) if logs else None
+    # column-major groups only run their log-semiring pull pass when beta or the conditionals are missing: their
+    # entries of logz_bwd then come from the caller's logz
+    logz_bwd = (logz.to(st).clone() if logz is not None else torch.empty(B, dtype=st, device=dev)) if logs else None
     post = torch.empty(A, **f32) if want_post else None
     dtheta = torch.zeros(V, **f32) if want_dtheta else None
     delta = torch.empty(S, **f32) if want_viterbi else None
     backptr = torch.empty(S, dtype=torch.int32, device=dev) if want_viterbi else None
     vit = torch.empty(B, **f32) if want_viterbi else None
     g32 = _check_f32("grad_logz", grad_logz, B, dev)
-    flow = (want_post or want_dtheta) and packed.has_sell
+    flow = (want_post or want_dtheta) and packed.has_columns
     have_cond = cond is not None
     gfar = _gamma_far(packed) if flow else None
     if flow and not have_cond:
@@ -273,19 +288,26 @@ def lattice_backward(
     with torch.cuda.device(dev):
         streams = _GroupStreams(dev, len(packed.groups))
         for i, g in enumerate(packed.groups):
-            if g.sell:
+            if g.sell or g.tiles:
                 lc = _launch(g, st)
-                need_pull = want_beta or want_viterbi or (flow and not have_cond)
-                if need_pull:
-                    _lib.check(lib.nfst_sell_pull_f32(
-                        packed.c_struct(), lc, sc, _ptr(beta) if (want_beta or (g.sell_far and flow and not have_cond)) else None,
-                        _ptr(logz_bwd) if logs else None,
+                far = g.tile_far if g.tiles else g.sell_far
+                # the log-semiring pull pass runs for beta / logZ, and for the conditionals when the caller has none
+                log_pull = want_beta or (flow and not have_cond)
+                if log_pull or want_viterbi:
+                    pull = lib.nfst_tile_pull_f32 if g.tiles else lib.nfst_sell_pull_f32
+                    _lib.check(pull(
+                        packed.c_struct(), lc, sc, _ptr(beta) if log_pull and (want_beta or far) else None,
+                        _ptr(logz_bwd) if log_pull else None,
                         _ptr(cond) if (flow and not have_cond) else None, _ptr(delta), _ptr(backptr), _ptr(vit), streams[i]))
-                    launch_count += int(logs) + int(want_viterbi)
+                    launch_count += int(log_pull) + int(want_viterbi)
                 if flow:
                     dst = post if want_post else (torch.empty(A, **f32) if have_cond else cond)
-                    _lib.check(lib.nfst_sell_flow_f32(packed.c_struct(), lc, cond.data_ptr(), _ptr(g32), dst.data_ptr(),
-                                                      None, None, None, _ptr(dtheta), _ptr(gfar), streams[i]))
+                    if g.tiles:
+                        _lib.check(lib.nfst_tile_flow_f32(packed.c_struct(), lc, cond.data_ptr(), _ptr(g32), dst.data_ptr(),
+                                                          _ptr(dtheta), _ptr(gfar), streams[i]))
+                    else:
+                        _lib.check(lib.nfst_sell_flow_f32(packed.c_struct(), lc, cond.data_ptr(), _ptr(g32), dst.data_ptr(),
+                                                          None, None, None, _ptr(dtheta), _ptr(gfar), streams[i]))
                     launch_count += 1
                 continue
             _lib.check(
@@ -331,7 +353,15 @@ def lattice_forward_backward(packed: PackedLattices, arc_scores=None, theta=None
         for i, g in enumerate(packed.groups):
             lc = _launch(g, st)
             stream = streams[i]
-            if g.sell:  # beta pass (cond written into post), then the flow pass in place; alpha by the CSR forward kernel
+            if g.tiles:  # as below, through the tile-stream kernels
+                _lib.check(lib.nfst_tile_pull_f32(packed.c_struct(), lc, sc, beta.data_ptr(), logz_bwd.data_ptr(),
+                                                  post.data_ptr(), None, None, None, stream))
+                _lib.check(lib.nfst_tile_flow_f32(packed.c_struct(), lc, post.data_ptr(), None, post.data_ptr(),
+                                                  _ptr(dtheta), _ptr(gfar), stream))
+                _lib.check(lib.nfst_fwd_f32(packed.c_struct(), _launch_csr_forward(g, st), sc, alpha.data_ptr(),
+                                            logz.data_ptr(), stream))
+                launch_count += 3
+            elif g.sell:  # beta pass (cond written into post), then the flow pass in place; alpha by the CSR forward kernel
                 _lib.check(lib.nfst_sell_pull_f32(packed.c_struct(), lc, sc, beta.data_ptr(), logz_bwd.data_ptr(),
                                                   post.data_ptr(), None, None, None, stream))
                 _lib.check(lib.nfst_sell_flow_f32(packed.c_struct(), lc, post.data_ptr(), None, post.data_ptr(),
@@ -512,8 +542,8 @@ def lattice_beta_hat(packed: PackedLattices, label_proj: torch.Tensor, Wh: torch
     dev = packed.device
     if dev.type != "cuda":
         raise RuntimeError("nfst_b200 kernels need the packed lattices on a CUDA device (no CPU fallback)")
-    if packed.has_sell:
-        raise ValueError("the beta-hat recurrence reads CSR arcs: pack with sell=False")
+    if packed.has_columns:
+        raise ValueError("the beta-hat recurrence reads CSR arcs: pack with sell=False, tiles=False")
     V, H = label_proj.shape
     if V != packed.vocab or tuple(Wh.shape) != (H, H) or W.numel() != H:
         raise ValueError("label_proj must be [vocab, H], Wh [H, H], W [H]")

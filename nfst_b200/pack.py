@@ -29,6 +29,7 @@ from typing import List, Optional
 import torch
 
 from . import _lib
+from . import tiles as tiles_mod
 
 # shared-memory window of the most recent per-state DP values, in bytes per state vector
 WINDOW_BYTES_MAX = int(os.environ.get("NFST_WINDOW_BYTES", str(64 * 1024)))
@@ -99,6 +100,12 @@ class LaunchGroup:
     sell_window: int = 0  # states in the shared-memory DP ring (a power of two)
     sell_far: bool = False  # some arc spans more than the ring: (end of dst's level - start of src's level) > window
     csr_block_threads: int = 0  # sliced-column groups: block size their in-order (CSR by destination) chunks were cut for
+    # tile-stream execution (nfst_tiles.cu): block_threads = 32 * warps the lattices were dealt to
+    tiles: bool = False
+    tile_ring: int = 0  # largest DP ring of the group, in slots (a multiple of 32)
+    tile_far: bool = False  # some arc's destination has left the ring when its source is processed
+    tile_cap_arcs: int = 0  # largest tile, in arcs
+    tile_cap_bytes: int = 0  # largest tile, in stream bytes
 
     def to(self, device, non_blocking: bool = False) -> "LaunchGroup":
         mv = lambda t: None if t is None else t.to(device, non_blocking=non_blocking)  # noqa: E731
@@ -120,6 +127,7 @@ class PackedLattices:
         "in_ptr", "src_in", "label_in", "in2out", "out_ptr", "dst_out", "label_out",
         "fwd_chunk_off", "fwd_chunks", "bwd_chunk_off", "bwd_chunks", "fwd_gather",
         "fwd_chunk_level", "bwd_chunk_level", "bwd_order", "sell_desc", "sell_lvl_slice",
+        "tile_tab", "tile_lw_off", "tile_lat_info",
     )
 
     # arrays the kernels stage with 16-byte copies: kept zero-padded by PAD elements
@@ -161,6 +169,7 @@ class PackedLattices:
         self.lanes_in_log2: torch.Tensor = kw["lanes_in_log2"]
         self.lanes_out_log2: torch.Tensor = kw["lanes_out_log2"]
         self.out_deg8: torch.Tensor = kw["out_deg8"]  # uint8 [S] min(out-degree, 255)
+        self.tile_stream: torch.Tensor = kw["tile_stream"]  # uint8: tile headers, slice headers, 16-bit ring slots
         self.src_out: torch.Tensor = kw["src_out"]  # int32 [A] source state of each canonical arc (host-side view)
         self.orig_state: torch.Tensor = kw["orig_state"]  # int32 [S] original local state id
         self.arc_origin: torch.Tensor = kw["arc_origin"]  # int64 [A] index into the caller's arc list / dense cells
@@ -182,9 +191,18 @@ class PackedLattices:
     def has_sell(self) -> bool:
         return any(g.sell for g in self.groups)
 
+    @property
+    def has_tiles(self) -> bool:
+        return any(g.tiles for g in self.groups)
+
+    @property
+    def has_columns(self) -> bool:
+        """some lattices are stored column-major (sliced-column or tile-stream groups): their arcs are not CSR"""
+        return any(g.sell or g.tiles for g in self.groups)
+
     def tensors(self):
-        names = list(self._INT_FIELDS) + ["lanes_in_log2", "lanes_out_log2", "out_deg8", "src_out", "orig_state",
-                                          "arc_origin", "arc_off", "n_levels"]
+        names = list(self._INT_FIELDS) + ["lanes_in_log2", "lanes_out_log2", "out_deg8", "tile_stream", "src_out",
+                                          "orig_state", "arc_origin", "arc_off", "n_levels"]
         if self.static_scores is not None:
             names.append("static_scores")
         return names
@@ -224,6 +242,8 @@ class PackedLattices:
             c.lanes_in_log2 = self.lanes_in_log2.data_ptr()
             c.lanes_out_log2 = self.lanes_out_log2.data_ptr()
             c.out_deg8 = self.out_deg8.data_ptr()
+            assert self.tile_stream.dtype == torch.uint8 and self.tile_stream.data_ptr() % 16 == 0
+            c.tile_stream = self.tile_stream.data_ptr()
             self._c = c
         return self._c
 
@@ -305,14 +325,26 @@ def build_groups(stats, dev, chunk_info=None) -> List[LaunchGroup]:
     foot = small_footprint_bytes(stats["states"], stats["arcs"], stats["levels"], int(stats["vocab"][0]))
     small = ((foot <= SMALL_SMEM_BYTES) & (stats["states"] < 65536) & (stats["arcs"] < 65536)).to(torch.int64) * (1 - wide)
     sell = stats["sell"].to(torch.int64)
-    wide, small = wide * (1 - sell), small * (1 - sell)
-    # sliced-column lattices: one group per block size (a power of two of warps)
+    tile = stats["tile"].to(torch.int64)
+    wide, small = wide * (1 - sell) * (1 - tile), small * (1 - sell) * (1 - tile)
+    # sliced-column lattices: one group per block size (a power of two of warps); tile-stream lattices likewise
     gkey = torch.where(sell > 0, (stats["sell_block"] * 2) * 2 + 4096, (stats["block_class"] * 2 + wide) * 2 + small)
+    gkey = torch.where(tile > 0, stats["tile_warps_log2"] + 8192, gkey)
     groups: List[LaunchGroup] = []
     B = int(gkey.numel())
     for key in sorted(set(gkey.tolist()), reverse=True):
         members = torch.nonzero(gkey == key).squeeze(1)
         members = members[torch.argsort(stats["arcs"][members], descending=True, stable=True)]
+        if key >= 8192:
+            groups.append(LaunchGroup(
+                ids=members.to(torch.int32).to(dev), n=int(members.numel()), block_threads=32 << (key - 8192),
+                max_states=int(stats["states"][members].max()), max_reach=int(stats["reach"][members].max()),
+                n_arcs=int(stats["arcs"][members].sum()), n_levels=int(stats["levels"][members].max()),
+                chunk_cap=int(stats["chunk_cap"][members].max()), csr_block_threads=1 << int(stats["block_class"][members].max()),
+                tiles=True, tile_ring=int(stats["tile_ring"][members].max()), tile_far=bool(stats["tile_far"][members].any()),
+                tile_cap_arcs=int(stats["tile_cap_arcs"][members].max()), tile_cap_bytes=int(stats["tile_cap_bytes"][members].max()),
+            ))
+            continue
         if key >= 4096:
             groups.append(LaunchGroup(
                 ids=members.to(torch.int32).to(dev), n=int(members.numel()),
@@ -381,6 +413,9 @@ def concat_packed(parts: List["PackedLattices"]) -> "PackedLattices":
     n_fc = [int(p.fwd_chunks.shape[0]) for p in parts]
     n_bc = [int(p.bwd_chunks.shape[0]) for p in parts]
     n_sl = [int(p.sell_desc.shape[0]) for p in parts]
+    n_tt = [int(p.tile_tab.shape[0]) for p in parts]
+    n_lw = [int(p.tile_lw_off.numel()) - 1 for p in parts]
+    n_ts = [int(p.tile_stream.numel()) for p in parts]  # multiples of 16 bytes
 
     def starts(counts):
         out, t = [], 0
@@ -443,6 +478,23 @@ def concat_packed(parts: List["PackedLattices"]) -> "PackedLattices":
     for name, space, off_c in (("fwd_chunks", by_fc, offF), ("bwd_chunks", by_bc, offC)):
         shift = torch.stack([offA[space], offA[space], offS[space], offS[space]], dim=1)
         kw[name] = cat(name) + shift
+    # tile-stream arrays: the stream is lattice-relative, only the tables shift
+    oT, oW, oY = starts(n_tt)[0], starts(n_lw)[0], starts(n_ts)[0]
+    tabs, lws, infos = [], [], []
+    for i, p in enumerate(parts):
+        t = p.tile_tab.clone()
+        if t.shape[0]:
+            t[:, 0] += oA[i]
+            t[:, 1] += oY[i] // 16
+        tabs.append(t)
+        lws.append(p.tile_lw_off[:-1] + oT[i])
+        inf = p.tile_lat_info.clone()
+        inf[:, 0] += oW[i]
+        infos.append(inf)
+    kw["tile_tab"] = torch.cat(tabs)
+    kw["tile_lw_off"] = torch.cat(lws + [torch.tensor([sum(n_tt)], dtype=torch.int32, device=dev)])
+    kw["tile_lat_info"] = torch.cat(infos)
+    kw["tile_stream"] = torch.cat([p.tile_stream for p in parts])
     sd = cat("sell_desc")
     kw["sell_desc"] = sd + torch.stack([offA[by_sl], offA[by_sl], torch.zeros_like(offA[by_sl]), torch.zeros_like(offA[by_sl])], dim=1)
     fg = cat("fwd_gather")
@@ -473,11 +525,13 @@ def pack_arcs(
     static_scores: Optional[torch.Tensor] = None,
     dense_shape=None,
     sell: Optional[bool] = None,
+    tiles: Optional[bool] = None,
 ) -> PackedLattices:
     """Pack an arc list.  ``arc_lattice/src/dst/label`` are [A0] integer tensors (local
     state ids), ``n_states`` is [B].  Raises ``ValueError`` for cyclic lattices (the
     reference's denominator / base machines, which it never feeds to the DP either).
-    ``sell``: allow the sliced-column layout for wide lattices (default: the NFST_SELL knob)."""
+    ``sell`` / ``tiles``: allow the sliced-column / tile-stream layouts for wide lattices (defaults: the NFST_SELL
+    and NFST_TILES knobs; tiles win where both apply)."""
     dev = src.device
     n_states = n_states.to(device=dev, dtype=torch.int64)
     B = int(n_states.numel())
@@ -559,15 +613,31 @@ def pack_arcs(
             torch.log2(torch.clamp(lvl_width, min=1).to(torch.float64))).to(torch.int64)
         sell_win = torch.maximum(sell_win, pow2_width)
         sell_lat = sell_lat & (sell_win <= SELL_WINDOW_MAX)
+    # tile-stream eligibility (nfst_tiles.cu): levels at least a slice wide; every level must fit the largest ring
+    tile_lat = torch.zeros(B, dtype=torch.bool, device=dev)
+    tile_nw = torch.ones(B, dtype=torch.int64, device=dev)
+    if (tiles_mod.TILES if tiles is None else tiles) and kept.numel():
+        slot_lat1 = torch.repeat_interleave(torch.arange(B, device=dev), n_levels + 1)
+        lvl_width1 = torch.zeros(B, dtype=torch.int64, device=dev).scatter_reduce(0, slot_lat1, counts, reduce="amax")
+        tile_lat = (S_b0 >= tiles_mod.TILE_MIN_WIDTH * n_levels) & (lvl_width1 + 32 * tiles_mod.NW_MAX <= tiles_mod.RING_MAX)
+        tile_nw = tiles_mod.warps_per_lattice(S_b0, n_levels)
+        sell_lat = sell_lat & ~tile_lat
+    col_lat = sell_lat | tile_lat
     # inside a level states are ordered by (in-degree, out-degree): the 32 states a warp reduces then
-    # have (nearly) equal segment lengths in both passes; sliced-column lattices by out-degree,
+    # have (nearly) equal segment lengths in both passes; column-major lattices by out-degree,
     # descending, so that the states of a slice that own a k-th arc are a prefix of the slice
     if DEGREE_SORT and lmax * dmax * dmax < 2**62 // max(B, 1):
-        dkey = torch.where(sell_lat[lt], (dmax - 1 - deg_out) * dmax, deg_in * dmax + deg_out)
+        dkey = torch.where(col_lat[lt], (dmax - 1 - deg_out) * dmax, deg_in * dmax + deg_out)
         order = torch.argsort((lt * lmax + lv) * dmax * dmax + dkey, stable=True)
     else:  # pathological degrees: fall back to level order only
         sell_lat = torch.zeros_like(sell_lat)
+        tile_lat = torch.zeros_like(tile_lat)
+        col_lat = sell_lat
         order = torch.argsort(lt * lmax + lv, stable=True)
+    st_w = st_j = st_lane = None
+    if bool(tile_lat.any()):
+        # tile-stream lattices: the slices of a level are dealt to the block's warps; (level, warp, slice, lane) order
+        order, st_w, st_j, st_lane = tiles_mod.deal_order(order, lt, deg_out, slot_kept, level_ptr, tile_lat, tile_nw)
     kept_sorted = kept[order]
     lt_s, lv_s = lt[order], lv[order]
     S = int(kept_sorted.numel())
@@ -586,13 +656,15 @@ def pack_arcs(
     A = int(src_out.numel())
     out_deg = torch.bincount(src_out, minlength=S)
     out_ptr = _excl_cumsum(out_deg)
-    if bool(sell_lat.any()) and A:
-        # column-major inside every 32-state slice: key (first arc of the slice, k, lane)
+    if bool(col_lat.any()) and A:
+        # column-major inside every slice: key (first arc of the slice, k, lane)
         pos = torch.arange(A, device=dev)
         k_in_state = pos - out_ptr[src_out]
         rel = src_out - level_ptr[slot[src_out]]
         lane = rel % 32
-        is_sell = sell_lat[lt_s[src_out]]
+        if st_lane is not None:  # tile-stream lattices: slices are per (level, warp); heavy states are slices of their own
+            lane = torch.where(tile_lat[lt_s[src_out]], st_lane[src_out], lane)
+        is_sell = col_lat[lt_s[src_out]]
         zero = torch.zeros_like(pos)
         kmul = int(k_in_state[is_sell].max()) + 1 if bool(is_sell.any()) else 1
         if A * kmul * 32 >= 2**62:
@@ -630,6 +702,13 @@ def pack_arcs(
         sell_desc[:, 2] = cs[:, 0] | (cs[:, 1] << 8) | (cs[:, 2] << 16) | (cs[:, 3] << 24)
         sell_desc[:, 3] = cs[:, 4] | (cs[:, 5] << 8) | (cs[:, 6] << 16) | (dmax8 << 24)
         sell_desc = torch.where(sell_desc >= 2**31, sell_desc - 2**32, sell_desc)  # bit pattern as int32
+
+    # ---- tile-stream lattices: slices, ring slots, tiles, byte stream ----
+    if st_w is None:
+        st_w = st_j = torch.zeros(S, dtype=torch.int64, device=dev)
+    tile_data = tiles_mod.build(lt_s=lt_s, slot=slot, level_off=level_off, level_ptr=level_ptr, n_levels=n_levels, st_w=st_w,
+                                st_j=st_j, out_ptr=out_ptr, out_deg=out_deg, src_out=src_out, dst_out=dst_out,
+                                tile_lat=tile_lat, tile_nw=tile_nw, state_off=state_off, n_lattices=B)
 
     # ---- per-lattice shape statistics -> lanes per state, block size, launch groups ----
     A_b = (arc_off[1:] - arc_off[:-1]).to(torch.float64)
@@ -694,6 +773,9 @@ def pack_arcs(
         "sell_bound": sell_bound.cpu(),
         "sell_window": sell_win.cpu(),
         "sell_block": _sell_block_log2(S_b.cpu(), n_levels.cpu()),
+        "tile": tile_lat.cpu(),
+        "tile_warps_log2": torch.round(torch.log2(tile_nw.to(torch.float64))).to(torch.int64).cpu(),
+        **tile_data["stats"],
     }
     groups = build_groups(stats, dev, {"fwd": (fwd_chunk_off, fwd_chunks, fwd_chunk_level),
                                        "bwd": (bwd_chunk_off, bwd_chunks, bwd_chunk_level)})
@@ -707,6 +789,8 @@ def pack_arcs(
         fwd_chunk_off=i32(fwd_chunk_off), fwd_chunks=fwd_chunks, bwd_chunk_off=i32(bwd_chunk_off), bwd_chunks=bwd_chunks,
         fwd_gather=i32(fwd_gather), fwd_chunk_level=i32(fwd_chunk_level), bwd_chunk_level=i32(bwd_chunk_level),
         bwd_order=bwd_order, sell_desc=i32(sell_desc), sell_lvl_slice=i32(sell_lvl_slice),
+        tile_stream=tile_data["tile_stream"], tile_tab=tile_data["tile_tab"], tile_lw_off=tile_data["tile_lw_off"],
+        tile_lat_info=tile_data["tile_lat_info"],
         lanes_in_log2=lg_in.to(torch.uint8).contiguous(), lanes_out_log2=lg_out.to(torch.uint8).contiguous(),
         out_deg8=torch.clamp(out_deg, max=255).to(torch.uint8).contiguous(), src_out=i32(src_out),
         orig_state=i32(orig_state), arc_origin=origin.contiguous(), arc_off=i32(arc_off), n_levels=i32(n_levels),

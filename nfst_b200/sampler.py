@@ -34,7 +34,7 @@ class LatticeWalker:
                  temperature: float = 1.0, faithful: bool = True):
         if packed.device.type != "cuda":
             raise RuntimeError("nfst_b200 kernels need the packed lattices on a CUDA device (no CPU fallback)")
-        if packed.has_sell:
+        if packed.has_columns:
             raise ValueError("the walk reads CSR arcs: pack with sell=False")
         if beta_real.numel() != packed.n_states:
             raise ValueError("beta_real must hold one value per packed state")
@@ -86,7 +86,7 @@ def walk_step(packed: PackedLattices, k: int, state: torch.Tensor, prefix: torch
     dev = packed.device
     if dev.type != "cuda":
         raise RuntimeError("nfst_b200 kernels need the packed lattices on a CUDA device (no CPU fallback)")
-    if packed.has_sell:
+    if packed.has_columns:
         raise ValueError("the walk reads CSR arcs: pack with sell=False")
     N = packed.n_lattices * k
     V = packed.vocab
@@ -125,7 +125,7 @@ def sample_paths(packed: PackedLattices, k: int, arc_scores=None, theta=None, *,
     dev = packed.device
     if dev.type != "cuda":
         raise RuntimeError("nfst_b200 kernels need the packed lattices on a CUDA device (no CPU fallback)")
-    if packed.has_sell:
+    if packed.has_columns:
         raise ValueError("the walk reads CSR arcs: pack with sell=False")
     sc, keep = ops._scores(packed, arc_scores, theta)
     if beta is None:

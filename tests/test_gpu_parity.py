@@ -51,7 +51,8 @@ def tiny_window(monkeypatch):
     """Shrink the shared-memory window to 32 states so that most neighbour reads take the
     global-memory path behind it."""
     monkeypatch.setattr(nb.ops, "WINDOW_BYTES_MAX", 128)
-    monkeypatch.setattr(nb.pack, "SELL", 0)  # the sliced-column path has no window fallback to exercise
+    monkeypatch.setattr(nb.pack, "SELL", 0)
+    monkeypatch.setattr(nb.tiles, "TILES", 0)
 
 
 @pytest.fixture(params=["auto", "block", "level"])
@@ -62,10 +63,12 @@ def exec_mode(request, monkeypatch):
     if request.param == "block":
         monkeypatch.setattr(nb.pack, "SMALL_SMEM_BYTES", 0)
         monkeypatch.setattr(nb.pack, "SELL", 0)
+        monkeypatch.setattr(nb.tiles, "TILES", 0)
     elif request.param == "level":
         monkeypatch.setattr(nb.pack, "SMALL_SMEM_BYTES", 0)
         monkeypatch.setattr(nb.pack, "LEVEL_MODE_MIN_ARCS", 1)
         monkeypatch.setattr(nb.pack, "SELL", 0)
+        monkeypatch.setattr(nb.tiles, "TILES", 0)
     return request.param
 
 
@@ -73,6 +76,7 @@ def exec_mode(request, monkeypatch):
 def block_mode(monkeypatch):
     monkeypatch.setattr(nb.pack, "SMALL_SMEM_BYTES", 0)
     monkeypatch.setattr(nb.pack, "SELL", 0)
+    monkeypatch.setattr(nb.tiles, "TILES", 0)
 
 
 @pytest.fixture
@@ -81,6 +85,7 @@ def level_major(monkeypatch):
     monkeypatch.setattr(nb.pack, "SMALL_SMEM_BYTES", 0)
     monkeypatch.setattr(nb.pack, "LEVEL_MODE_MIN_ARCS", 1)
     monkeypatch.setattr(nb.pack, "SELL", 0)
+    monkeypatch.setattr(nb.tiles, "TILES", 0)
 
 
 def check_fwd_bwd(ab: synth.ArcBatch, *, state_dtype="auto", strict=False):

@@ -20,6 +20,7 @@ def narrow_lattices_too(monkeypatch):
     """The packer only sends lattices of >= 96 states per level down the sliced-column path (below that the
     CSR kernels are faster); the tests want small lattices there too."""
     monkeypatch.setattr(nb.pack, "SELL_MIN_WIDTH", 32)
+    monkeypatch.setattr(nb.tiles, "TILES", 0)  # these tests are about the sliced-column layout (tiles win by default)
 
 
 def viterbi_matches(ab, p, sc):

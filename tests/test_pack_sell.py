@@ -17,6 +17,7 @@ def narrow_lattices_too(monkeypatch):
     """The packer only sends lattices of >= 96 states per level down the sliced-column path (below that the
     CSR kernels are faster); the tests want small lattices there too."""
     monkeypatch.setattr(nb.pack, "SELL_MIN_WIDTH", 32)
+    monkeypatch.setattr(nb.tiles, "TILES", 0)  # these tests are about the sliced-column layout (tiles win by default)
 
 
 def _np(t):
@@ -173,7 +174,8 @@ def test_sell_heavy_state_and_narrow_lattices():
 
 
 def test_sell_default_thresholds(monkeypatch):
-    monkeypatch.undo()  # the packer's own defaults
+    monkeypatch.undo()  # the packer's own defaults ...
+    monkeypatch.setattr(nb.tiles, "TILES", 0)  # ... of the sliced-column path
     assert not layered(2, 2000, 10, 1).pack()[0].has_sell  # 50 states per level: CSR kernels
     p, _ = layered(1, 40_000, 16, 1).pack()  # 625 states per level
     assert p.has_sell and p.groups[0].block_threads == 128
