@@ -311,13 +311,14 @@ def main():
 
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(3 * a.steps + 2)]
 
-    all_sell = all(g.sell for g in packed.groups)
-    beta_buf = torch.empty(S, dtype=ops.resolve_state_dtype(packed), device=dev) if packed.has_sell else None
+    all_sell = all(g.sell or g.tiles for g in packed.groups)  # column-major groups only: two passes, no alpha
+    all_tiles = all(g.tiles for g in packed.groups)
+    beta_buf = torch.empty(S, dtype=ops.resolve_state_dtype(packed), device=dev) if packed.has_columns else None
 
     def sweep_step(pk, sc_):
         """the same two passes on another batch (the --sweep points)"""
-        bb = torch.empty(pk.n_states, dtype=ops.resolve_state_dtype(pk), device=dev) if pk.has_sell else None
-        sell_only = all(g.sell for g in pk.groups)
+        bb = torch.empty(pk.n_states, dtype=ops.resolve_state_dtype(pk), device=dev) if pk.has_columns else None
+        sell_only = all(g.sell or g.tiles for g in pk.groups)
 
         def run():
             lz, al, cd = ops.lattice_pull(pk, arc_scores=sc_, beta_out=bb)
@@ -396,7 +397,9 @@ def main():
     # ---- e2e: host (pinned) buffers -> H2D -> fwd+bwd -> D2H logZ ----
     e2e = None
     if not a.no_e2e:
-        if all_sell:  # the sliced-column kernels read nothing else (no in-order arrays, no chunk lists)
+        if all_tiles:  # the tile-stream kernels read the byte stream (16-bit ring slots + headers) and three small tables
+            fields = ("state_off", "start_state", "level_off", "tile_stream", "tile_tab", "tile_lw_off", "tile_lat_info")
+        elif all_sell:  # the sliced-column kernels read nothing else (no in-order arrays, no chunk lists)
             fields = ("state_off", "start_state", "level_off", "level_ptr", "out_ptr", "dst_out", "out_deg8",
                       "sell_desc", "sell_lvl_slice")
         else:
@@ -429,7 +432,7 @@ def main():
             # bookkeeping, and for sliced-column batches the in-order arrays and chunk lists) stay resident
             kw = {f: getattr(packed, f) for f in PackedLattices._INT_FIELDS}
             kw.update(lanes_in_log2=packed.lanes_in_log2, lanes_out_log2=packed.lanes_out_log2, out_deg8=packed.out_deg8,
-                      src_out=packed.src_out, orig_state=packed.orig_state, arc_origin=packed.arc_origin,
+                      tile_stream=packed.tile_stream, src_out=packed.src_out, orig_state=packed.orig_state, arc_origin=packed.arc_origin,
                       arc_off=packed.arc_off, n_levels=packed.n_levels)
             kw.update(land)
             groups = [dataclasses.replace(g, ids=d_) for g, d_ in zip(packed.groups, land_ids)]
@@ -468,10 +471,12 @@ def main():
 
     peak, peak_src = measured_peak_gbs()
     if all_sell:
-        # sliced-column passes: pull = dst + score read, cond write per arc, beta write per
+        # column-major passes: pull = dst + score read, cond write per arc, beta write per
         # state; flow = dst + cond read, post write per arc.  Their sum, 24 A + 4 S, equals SURVEY 8(d)'s
-        # 20 A + 20 S at S = A/4.
-        names = ("sell_pull_kernel (beta + logZ + arc conditionals)", "sell_flow_kernel (arc posteriors)")
+        # 20 A + 20 S at S = A/4.  (The tile-stream kernels read destinations as 16-bit ring slots: they move
+        # fewer bytes than this algorithmic count.)
+        names = (("tile_pull_kernel (beta + logZ + arc conditionals)", "tile_flow_kernel (arc posteriors)") if all_tiles else
+                 ("sell_pull_kernel (beta + logZ + arc conditionals)", "sell_flow_kernel (arc posteriors)"))
         fwd_bytes, bwd_bytes = 12 * A + 4 * S, 12 * A
     else:
         names = ("nfst_fwd_kernel", "nfst_bwd_kernel (fused beta + posteriors)")
@@ -490,7 +495,9 @@ def main():
                    "levels": packed.max_levels, "global_batch": B * world, "parallelism": f"dp{world} (lattices sharded, loss all-reduce only)",
                    "l2": "inputs larger than L2 (no flush)" if 20 * A > 2 * 126e6 else "inputs fit in L2 (no flush; latency-bound config)",
                    "scores": "per-arc fp32, canonical order",
-                   "execution": "sliced-column (nfst_sell.cu)" if all_sell else "CSR kernels (nfst_kernels.cu)"},
+                   "execution": ("tile-stream (nfst_tiles.cu): " + ", ".join(f"{g.n} lattices x {g.block_threads // 32} warps, ring {g.tile_ring}"
+                                                                              for g in packed.groups)) if all_tiles
+                   else "sliced-column (nfst_sell.cu)" if all_sell else "CSR kernels (nfst_kernels.cu)"},
         "gpu_launches": launches,
         "clocks": clk,
         "roofline": {"bound": "hbm", "kernel": dom["kernel"], "achieved": dom["achieved"],
@@ -524,7 +531,8 @@ def main():
             torch.cuda.synchronize()
             ms = s0.elapsed_time(s1) / a.steps
             sweep.append({"arcs_per_lattice": arcs, "arcs": packed.n_arcs, "ms_per_step": ms,
-                          "execution": "sliced-column" if all(g.sell for g in packed.groups) else "CSR",
+                          "execution": "tile-stream" if all(g.tiles for g in packed.groups) else
+                          "sliced-column" if all(g.sell for g in packed.groups) else "CSR/mixed",
                           "arcs_per_s": packed.n_arcs / (ms * 1e-3),
                           "gbs": (20 * packed.n_arcs + 20 * packed.n_states) / (ms * 1e-3) / 1e9})
         out["sweep"] = sweep

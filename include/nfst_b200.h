@@ -137,7 +137,7 @@ typedef struct nfst_packed_lattices {
    *   tile_lw_off  [n_(lattice,warp) + 1] offsets into tile_tab
    *   tile_lat_info one int32[4] per lattice: [0] index of its warp 0 in tile_lw_off, [1] W = slots of its DP
    *                ring (a multiple of 32), [2] first state of its last level (lattice-relative),
-   *                [3] != 0: some arc's destination has left the ring when its source is processed
+   *                [3] canonical id of its first arc
    *   tile_stream  per tile, 16-byte aligned: a 16-byte tile header {first state and first arc (both
    *                lattice-relative), ring slot of the first slice | offset of the slot region << 16,
    *                level | segments << 16}; one 16-byte header per segment {bytes n_0..n_7 = states with more
@@ -353,6 +353,10 @@ int nfst_tile_pull_f32(const nfst_packed_lattices_t* lat, const nfst_launch_t* l
                        void* cuda_stream);
 int nfst_tile_flow_f32(const nfst_packed_lattices_t* lat, const nfst_launch_t* launch, const float* cond,
                        const float* grad_logz, float* post, float* dtheta, float* gamma_far, void* cuda_stream);
+/* Diagnostic: builds with -DNFST_TILE_DEBUG range-check every data-dependent index of the tile-stream kernels;
+ * this synchronises the device and returns the first violation {code, a, b, c, block, thread, 0, 0} (and clears
+ * it).  Regular builds return zeros. */
+int nfst_tile_debug_read(int32_t* out8);
 
 /*
  * One time step of the lattice-constrained sampling / scoring loop (Sampler.stateful_sample,

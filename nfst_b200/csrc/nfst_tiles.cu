@@ -89,6 +89,21 @@ __device__ __forceinline__ void block_bar() { asm volatile("bar.sync 0;" ::: "me
 
 extern __shared__ __align__(128) unsigned char tile_smem[];
 
+// -DNFST_TILE_DEBUG: range checks on the data-dependent indices; the first violation is recorded (code, three
+// values, block, thread) and the access is made harmless.  Read back with nfst_tile_debug_read.
+#ifdef NFST_TILE_DEBUG
+__device__ int tile_dbg[8];
+#define TILE_CHECK(ok, code, a, b, c)                                                        \
+  do {                                                                                        \
+    if (!(ok) && atomicCAS(&tile_dbg[0], 0, (code)) == 0) {                                   \
+      tile_dbg[1] = (a); tile_dbg[2] = (b); tile_dbg[3] = (c);                                \
+      tile_dbg[4] = blockIdx.x; tile_dbg[5] = threadIdx.x;                                    \
+    }                                                                                         \
+  } while (0)
+#else
+#define TILE_CHECK(ok, code, a, b, c) do { } while (0)
+#endif
+
 // launch geometry (host-computed; byte offsets into dynamic shared memory)
 struct TP {
   int stages;       // depth of every warp's stage ring
@@ -160,6 +175,22 @@ struct PullCtx {
   int32_t* __restrict__ backptr;
   float* __restrict__ vit;
   int W, last0, start, b, lane;
+  int a_lo, a_hi, s_lo, s_hi;  // the lattice's arc / state ranges (range checks of the debug build)
+
+  __device__ __forceinline__ RingT ring_at(int code, int where) const {
+    TILE_CHECK(code >= 0 && code <= W, 1, code, W, where);
+#ifdef NFST_TILE_DEBUG
+    if (code < 0 || code > W) code = W;
+#endif
+    return ring[code];
+  }
+  __device__ __forceinline__ void cond_store(int a, float v, int where) const {
+    TILE_CHECK(a >= a_lo && a < a_hi, 2, a, a_hi, where);
+#ifdef NFST_TILE_DEBUG
+    if (a < a_lo || a >= a_hi) return;
+#endif
+    cond[a] = v;
+  }
 
   __device__ __forceinline__ float score(const Seg& g, int e, bool on) const {
     float w = SC ? g.vals[e] : 0.0f;
@@ -173,6 +204,10 @@ struct PullCtx {
     return TROP ? static_cast<RingT>(far_load(delta, d)) : static_cast<RingT>(far_load(beta, d));
   }
   __device__ __forceinline__ void store_state(int s, int slot, RingT v, int arg) const {
+    TILE_CHECK(s >= s_lo && s < s_hi && slot >= 0 && slot < W, 3, s, slot, W);
+#ifdef NFST_TILE_DEBUG
+    if (!(s >= s_lo && s < s_hi && slot >= 0 && slot < W)) return;
+#endif
     ring[slot] = v;
     if (!TROP) {
       if (beta) beta[s] = static_cast<OT>(v);
@@ -199,7 +234,7 @@ struct PullCtx {
       const int n = col_count(h, k);
       on[k] = lane < n;
       wc[k] = score(g, e, on[k]);
-      rv[k] = ring[g.codes[e]];
+      rv[k] = ring_at(g.codes[e], 10 + k);
       e += n;
     }
     const int e_tail = e;  // this lane's entry in column KU (when the slice has one)
@@ -219,7 +254,7 @@ struct PullCtx {
         const int n = nk_ext[k - KU];
         const bool o = lane < n;
         const float w = score(g, et, o);
-        RingT v = ring[g.codes[et]];
+        RingT v = ring_at(g.codes[et], 30 + k);
         if (far && o && g.codes[et] == W) v = far_value(g, et);
         f(o, et, w, v);
         et += n;
@@ -279,12 +314,12 @@ struct PullCtx {
         int e2 = arc_rel + lane;
 #pragma unroll
         for (int k = 0; k < NC; ++k) {
-          if (on[k]) cond[g.arc0 + e2] = ex[k] * inv;
+          if (on[k]) cond_store(g.arc0 + e2, ex[k] * inv, 100 + k);
           e2 += col_count(h, k);
         }
         if (NC == KU && dmax > KU)
           tail([&](bool o, int et, float w, RingT v) {
-            if (o) cond[g.arc0 + et] = ex2_approx((fmaxf(rel_term<RingT>(w, v, rw, rb), kFloor) - mf) * kLog2e) * inv;
+            if (o) cond_store(g.arc0 + et, ex2_approx((fmaxf(rel_term<RingT>(w, v, rw, rb), kFloor) - mf) * kLog2e) * inv, 200);
           });
       }
       if (lane < nst) store_state(s, vslot + lane, bv, 0);
@@ -318,7 +353,6 @@ struct PullCtx {
 struct HeavyLog {
   float m, s, rw;
   double rb;  // reference arc (holds either ring precision)
-  int a_first;
 };
 struct HeavyTrop {
   float best;
@@ -336,7 +370,7 @@ __global__ void __launch_bounds__(NT_MAX, MINB)
   const int b = ids ? ids[blockIdx.x] : blockIdx.x;
   const int4 info = __ldg(reinterpret_cast<const int4*>(L.tile_lat_info) + b);
   const int s_base = L.state_off[b];
-  const int a_base = L.out_ptr[s_base];
+  const int a_base = info.w;
   const int n_levels = L.level_off[b + 1] - L.level_off[b] - 1;
   Ctx c;
   c.ring = reinterpret_cast<RingT*>(tile_smem);
@@ -348,6 +382,10 @@ __global__ void __launch_bounds__(NT_MAX, MINB)
   c.start = L.start_state[b];
   c.b = b;
   c.lane = lane;
+  c.a_lo = a_base;
+  c.a_hi = L.n_arcs;
+  c.s_lo = s_base;
+  c.s_hi = L.state_off[b + 1];
   if (TH && P.table) {
     float* sth = reinterpret_cast<float*>(tile_smem + P.table_off);
     for (int i = tid; i < L.vocab; i += blockDim.x) sth[i] = theta[i];
@@ -390,7 +428,7 @@ __global__ void __launch_bounds__(NT_MAX, MINB)
     for (int i = 0; i < D && i < n_t; ++i) issue(i, __ldg(tab + (t_hi - 1 - i)));
     if (D < n_t) nxt = __ldg(tab + (t_hi - 1 - D));
   }
-  HeavyLog hl = {kFloor, 0.0f, 0.0f, 0.0, 0};
+  HeavyLog hl = {kFloor, 0.0f, 0.0f, 0.0};
   HeavyTrop ht = {0.0f, -1};
   int cur = n_levels - 1;
   int d = 0;
@@ -401,6 +439,7 @@ __global__ void __launch_bounds__(NT_MAX, MINB)
     const unsigned char* const st = my_stage + d * P.stage_bytes;
     const int4 hd = *reinterpret_cast<const int4*>(st);
     const int level = hd.w & 0xffff, nseg = static_cast<unsigned>(hd.w) >> 16;
+    TILE_CHECK(level <= cur && nseg >= 1 && nseg <= 64 && 16 + 16 * nseg <= P.cap_bytes, 5, level, cur, nseg);
     // every deeper level is complete before this tile reads the ring (one block barrier per level)
     while (cur > level) {
       if (nw > 1) block_bar();
@@ -424,26 +463,26 @@ __global__ void __launch_bounds__(NT_MAX, MINB)
         // ---- a piece of a heavy state: the warp strides over its arcs ----
         const int n = h.w & 0xffff;  // arcs of this piece
         const bool far = flags & FLAG_FAR_OUT;
+        // the pull pass walks a warp's tiles backwards: the LAST piece of the state comes first, the FIRST one ends it
         if (!TROP) {
-          if (flags & FLAG_HEAVY_FIRST) {
+          if (flags & FLAG_HEAVY_LAST) {
             float w0 = c.score(g, 0, true);
-            RingT v0 = c.ring[g.codes[0]];
+            RingT v0 = c.ring_at(g.codes[0], 50);
             if (far && g.codes[0] == c.W) v0 = c.far_value(g, 0);
             if (!(w0 + static_cast<float>(v0) > kFloor)) { w0 = 0.0f; v0 = static_cast<RingT>(0); }
             hl.m = kFloor; hl.s = 0.0f; hl.rw = w0; hl.rb = static_cast<double>(v0);
-            hl.a_first = g.arc0;
           }
           const RingT rb = static_cast<RingT>(hl.rb);
 #pragma unroll 2
           for (int e = lane; e < n; e += 32) {
             const float w = c.score(g, e, true);
-            RingT v = c.ring[g.codes[e]];
+            RingT v = c.ring_at(g.codes[e], 51);
             if (far && g.codes[e] == c.W) v = c.far_value(g, e);
             const float t = fmaxf(rel_term<RingT>(w, v, hl.rw, rb), kFloor);
             lse_push(hl.m, hl.s, t);
-            if (cond) cond[g.arc0 + e] = t;  // provisional: the offset; rescaled below once beta is known
+            if (cond) c.cond_store(g.arc0 + e, t, 300);  // provisional: the offset; rescaled below once beta is known
           }
-          if (flags & FLAG_HEAVY_LAST) {
+          if (flags & FLAG_HEAVY_FIRST) {
             float m = hl.m, s = hl.s;
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) {
@@ -460,28 +499,32 @@ __global__ void __launch_bounds__(NT_MAX, MINB)
             }
             if (lane == 0) c.store_state(s0, vslot, bv, 0);
             if (cond) {
-              const int total = h.x;  // arcs of the whole state; every lane re-reads what it wrote itself
+              // the state's arcs start with this piece; pieces are multiples of 32 arcs, so every lane re-reads
+              // exactly what it wrote itself
+              const int total = h.x;
               const float inv = finite ? rcp_approx(s) : 0.0f;
+              TILE_CHECK(g.arc0 >= c.a_lo && g.arc0 + total <= c.a_hi, 4, g.arc0, total, c.a_hi);
               for (int e = lane; e < total; e += 32) {
-                const float t = cond[hl.a_first + e];
-                cond[hl.a_first + e] = finite ? ex2_approx((t - m) * kLog2e) * inv : 0.0f;
+                const float t = cond[g.arc0 + e];
+                c.cond_store(g.arc0 + e, finite ? ex2_approx((t - m) * kLog2e) * inv : 0.0f, 400);
               }
             }
           }
         } else {
-          if (flags & FLAG_HEAVY_FIRST) { ht.best = 0.0f; ht.arg = -1; }
+          if (flags & FLAG_HEAVY_LAST) { ht.best = 0.0f; ht.arg = -1; }
 #pragma unroll 2
           for (int e = lane; e < n; e += 32) {
             const float w = c.score(g, e, true);
-            RingT v = c.ring[g.codes[e]];
+            RingT v = c.ring_at(g.codes[e], 52);
             if (far && g.codes[e] == c.W) v = c.far_value(g, e);
             const float cnd = __fadd_rn(w, v);
-            if (ht.arg < 0 || cnd > ht.best) {  // a lane's arcs ascend: its first maximum stays
+            // later pieces come first: among equal candidates the smaller arc id (= smaller label) wins
+            if (ht.arg < 0 || cnd > ht.best || (cnd == ht.best && g.arc0 + e < ht.arg)) {
               ht.best = cnd;
               ht.arg = g.arc0 + e;
             }
           }
-          if (flags & FLAG_HEAVY_LAST) {
+          if (flags & FLAG_HEAVY_FIRST) {
             float best = ht.best;
             int arg = ht.arg;
 #pragma unroll
@@ -543,7 +586,7 @@ __global__ void __launch_bounds__(NT_MAX, MINB)
   const int b = ids ? ids[blockIdx.x] : blockIdx.x;
   const int4 info = __ldg(reinterpret_cast<const int4*>(L.tile_lat_info) + b);
   const int s_base = L.state_off[b];
-  const int a_base = L.out_ptr[s_base];
+  const int a_base = info.w;
   const int n_levels = L.level_off[b + 1] - L.level_off[b] - 1;
   const int W = info.y, last0 = s_base + info.z;
   unsigned* const ring = reinterpret_cast<unsigned*>(tile_smem);
@@ -740,7 +783,9 @@ Geometry geometry(const nfst_launch_t* launch, int vocab, int ring_elem_bytes, i
   g.p.stage_off = static_cast<int>(o);
   g.p.stages = stages;
   g.p.cap_bytes = static_cast<int>(round_up(launch->tile_cap_bytes, 16));
-  g.p.arr_bytes = static_cast<int>(round_up(static_cast<size_t>(launch->tile_cap_arcs + 8) * 4, 16));
+  // a staged array holds the 16-byte-aligned superset of the tile's range (up to 6 more elements), and lanes without
+  // an arc in a column read up to 31 elements past the tile's last arc (their values are ignored)
+  g.p.arr_bytes = static_cast<int>(round_up(static_cast<size_t>(launch->tile_cap_arcs + 8 + 32) * 4, 16));
   g.p.stage_bytes = g.p.cap_bytes + n_arrays * g.p.arr_bytes;
   g.p.hist_scale = g.p.hist_inv = 1.0f;
   g.smem = o + static_cast<size_t>(nw) * stages * g.p.stage_bytes;
@@ -847,6 +892,18 @@ int launch_pull(const nfst_packed_lattices_t* lat, const nfst_launch_t* launch, 
 }  // namespace
 
 extern "C" {
+
+/* debug builds (-DNFST_TILE_DEBUG): the first range-check violation {code, a, b, c, block, thread, 0, 0}; else zeros */
+int nfst_tile_debug_read(int32_t* out8) {
+  for (int i = 0; i < 8; ++i) out8[i] = 0;
+#ifdef NFST_TILE_DEBUG
+  int zero[8] = {0};
+  if (cudaDeviceSynchronize() != cudaSuccess) return -1;
+  if (cudaMemcpyFromSymbol(out8, tile_dbg, sizeof(int) * 8) != cudaSuccess) return -1;
+  cudaMemcpyToSymbol(tile_dbg, zero, sizeof(zero));
+#endif
+  return 0;
+}
 
 size_t nfst_tile_smem_bytes(const nfst_launch_t* launch, int32_t vocab, int pass, int n_f32_arrays, int with_table, int stages) {
   if (!launch || !launch->tiles) return 0;

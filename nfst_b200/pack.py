@@ -490,6 +490,7 @@ def concat_packed(parts: List["PackedLattices"]) -> "PackedLattices":
         lws.append(p.tile_lw_off[:-1] + oT[i])
         inf = p.tile_lat_info.clone()
         inf[:, 0] += oW[i]
+        inf[:, 3] += oA[i]
         infos.append(inf)
     kw["tile_tab"] = torch.cat(tabs)
     kw["tile_lw_off"] = torch.cat(lws + [torch.tensor([sum(n_tt)], dtype=torch.int32, device=dev)])

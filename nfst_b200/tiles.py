@@ -62,6 +62,14 @@ def warps_per_lattice(states: torch.Tensor, levels: torch.Tensor) -> torch.Tenso
     return torch.ones_like(states) << torch.clamp(lg, 0, 5)
 
 
+def tile_arcs_for(nw: torch.Tensor) -> torch.Tensor:
+    """Target arcs per tile for lattices dealt to ``nw`` warps: TILE_ARCS for narrow blocks (few warps per SM: each
+    bulk copy must be a kilobyte or two to keep HBM busy), smaller for wide blocks (many warps in flight, and
+    nw x stages x tile bytes must fit shared memory next to the ring); a multiple of 32, at least 96."""
+    t = torch.clamp(torch.div(4 * TILE_ARCS, torch.clamp(nw, min=1), rounding_mode="floor"), min=min(96, TILE_ARCS), max=TILE_ARCS)
+    return torch.div(t, 32, rounding_mode="floor") * 32
+
+
 def deal_order(order, lt, deg_out, slot_kept, level_start, tile_lat, tile_nw):
     """Refine the state order of tile-stream lattices.
 
@@ -97,8 +105,8 @@ def build(*, lt_s, slot, level_off, level_ptr, n_levels, st_w, st_j, out_ptr, ou
     dev = lt_s.device
     B = n_lattices
     i64 = dict(dtype=torch.int64, device=dev)
-    T = TILE_ARCS
-    assert T % 32 == 0 and T <= 4096
+    assert TILE_ARCS % 32 == 0 and 32 <= TILE_ARCS <= 4096
+    T_lat = tile_arcs_for(tile_nw)  # [B] target arcs per tile
     ts = torch.nonzero(tile_lat[lt_s]).squeeze(1)  # tile states, ascending
     empty = {
         "tile_stream": torch.zeros(16, dtype=torch.uint8, device=dev), "tile_tab": torch.zeros((0, 4), dtype=torch.int32, device=dev),
@@ -173,13 +181,15 @@ def build(*, lt_s, slot, level_off, level_ptr, n_levels, st_w, st_j, out_ptr, ou
     sl_vslot = (32 * sl_ord) % W[sl_lat]
 
     # ---- segments (one header each): regular slices, heavy slices cut into pieces of T arcs ----
+    T = T_lat[sl_lat]  # per slice
     n_seg = torch.where(sl_heavy, torch.clamp((sl_arcs + T - 1) // T, min=1), torch.ones_like(sl_arcs))
     seg_start = _excl_cumsum(n_seg)
     NSEG = int(seg_start[-1])
     seg_slice = torch.repeat_interleave(torch.arange(NSL, device=dev), n_seg, output_size=NSEG)
     seg_piece = torch.arange(NSEG, device=dev) - seg_start[seg_slice]
     seg_heavy = sl_heavy[seg_slice]
-    seg_arcs = torch.where(seg_heavy, torch.clamp(sl_arcs[seg_slice] - seg_piece * T, max=T), sl_arcs[seg_slice])
+    T = T[seg_slice]  # per segment from here on
+    seg_arcs = torch.where(seg_heavy, torch.minimum(sl_arcs[seg_slice] - seg_piece * T, T), sl_arcs[seg_slice])
     seg_arc0 = sl_arc0[seg_slice] + seg_piece * T
     seg_flags = sl_flags[seg_slice] + seg_heavy.to(torch.int64) * (
         FLAG_HEAVY + (seg_piece == 0).to(torch.int64) * FLAG_HEAVY_FIRST
@@ -250,7 +260,7 @@ def build(*, lt_s, slot, level_off, level_ptr, n_levels, st_w, st_j, out_ptr, ou
     hv = torch.nonzero(seg_heavy).squeeze(1)
     if hv.numel():
         put32(hdr[hv], sl_arcs[seg_slice[hv]])
-        put32(hdr[hv] + 4, seg_piece[hv] * T)
+        put32(hdr[hv] + 4, seg_piece[hv] * T[hv])
     put16(hdr + 8, seg_arc0 - t_arc0[seg_tile])
     put16(hdr + 10, sl_nst[seg_slice] | (torch.clamp(sl_dmax[seg_slice], max=255) << 8))
     ext_rank = torch.cumsum(seg_ext.to(torch.int64), 0) - seg_ext.to(torch.int64)  # global rank among extension blocks
@@ -266,7 +276,7 @@ def build(*, lt_s, slot, level_off, level_ptr, n_levels, st_w, st_j, out_ptr, ou
     # ring slots of the arcs
     a_tile = tile_of_seg[seg_start[slice_of_state[a_src]]
                          + torch.where(sl_heavy[slice_of_state[a_src]],
-                                       torch.div(at - sl_arc0[slice_of_state[a_src]], T, rounding_mode="floor"),
+                                       torch.div(at - sl_arc0[slice_of_state[a_src]], T_lat[a_lat], rounding_mode="floor"),
                                        torch.zeros_like(at))]
     put16(t_off[a_tile] + t_dst_off[a_tile] + 2 * (at - t_arc0[a_tile]), code)
     tile_stream = stream.to(torch.int16).view(torch.uint8)  # little-endian 16-bit words
@@ -283,7 +293,7 @@ def build(*, lt_s, slot, level_off, level_ptr, n_levels, st_w, st_j, out_ptr, ou
     tab = torch.where(tab >= 2**31, tab - 2**32, tab).to(torch.int32).contiguous()
     # first state of the last level, lattice-relative (its states are final: beta = 0; the far path needs to know them)
     last0 = level_ptr[level_off[:-1] + torch.clamp(n_levels - 1, min=0)] - state_off[:-1]
-    info = torch.stack([lw_base[:-1], W, last0, lat_far.to(torch.int64)], dim=1).to(torch.int32).contiguous()
+    info = torch.stack([lw_base[:-1], W, last0, out_ptr[state_off[:-1]]], dim=1).to(torch.int32).contiguous()
 
     cap_arcs = torch.zeros(B, **i64).scatter_reduce(0, t_lat, t_arcs, reduce="amax")
     cap_bytes = torch.zeros(B, **i64).scatter_reduce(0, t_lat, t_bytes, reduce="amax")

@@ -177,7 +177,7 @@ def test_tile_autograd_arc_scores_and_theta():
 
 
 def test_tile_mixed_batch_and_lattice_backward_outputs():
-    parts = [synth.transliteration_batch(5, seed=2), synth.random_dag_batch(3, 30_000, levels=32, seed=4),
+    parts = [synth.transliteration_batch(5, seed=2), synth.random_dag_batch(3, 60_000, levels=16, seed=4),
              synth.snips_batch(4, seed=1), synth.random_dag_batch(2, 6_000, levels=48, seed=6)]
     packs, scores = zip(*[ab.to(DEV).pack() for ab in parts])
     p = concat_packed(list(packs))

@@ -26,7 +26,8 @@ class Tile:
         h, h16 = raw[:16].view(np.int32), raw[:16].view(np.uint16)
         s_base = int(_np(p.state_off)[b])
         self.state0 = int(h[0]) + s_base
-        assert int(h[1]) + int(_np(p.out_ptr)[s_base]) == self.arc0
+        assert int(_np(p.tile_lat_info)[b, 3]) == int(_np(p.out_ptr)[s_base])
+        assert int(h[1]) + int(_np(p.tile_lat_info)[b, 3]) == self.arc0
         self.vslot0, self.dst_off = int(h16[4]), int(h16[5])
         assert int(h16[6]) == self.level and int(h16[7]) == self.n_seg
         assert self.dst_off == 16 + 16 * self.n_seg + 32 * self.n_ext
