@@ -136,18 +136,21 @@ typedef struct nfst_packed_lattices {
    *                  [2] arcs | segments << 16 | extension blocks << 24, [3] level | (stream bytes / 16) << 16
    *   tile_lw_off  [n_(lattice,warp) + 1] offsets into tile_tab
    *   tile_lat_info one int32[4] per lattice: [0] index of its warp 0 in tile_lw_off, [1] W = slots of its DP
-   *                ring (a multiple of 32), [2] first state of its last level (lattice-relative),
+   *                ring (a multiple of 32), [2] slots in all: ring, the constant slot W, the far table,
    *                [3] canonical id of its first arc
    *   tile_stream  per tile, 16-byte aligned: a 16-byte tile header {first state and first arc (both
    *                lattice-relative), ring slot of the first slice | offset of the slot region << 16,
    *                level | segments << 16}; one 16-byte header per segment {bytes n_0..n_7 = states with more
    *                than k arcs, arc offset in the tile (16 bit), states (8), largest degree (8), offset of the
-   *                extension block (16), flags (16)}; 32-byte extension blocks {n_8..n_39}; the arcs'
-   *                destinations as 16-bit ring slots (slot W = "a constant": the last level, or a far arc of a
-   *                segment flagged 1 -- resolved through dst_out); 64 bytes of slot W.  Heavy segments: header
-   *                words {arcs of the state, arcs before this piece}, extension field = arcs of the piece,
-   *                flags 4 (heavy) | 8 (first piece) | 16 (last piece).  Flag 2: a state of the segment
-   *                receives flow from a far arc (nfst_tile_flow_f32 reads gamma_far for it). */
+   *                segment's extension region (16), flags (16)}; extension regions {32 bytes n_8..n_39 when the
+   *                largest degree exceeds 8; 64 bytes = the 32 lanes' far-table slots (0 = none) when flag 2 is
+   *                set}; the arcs' destinations as 16-bit slots: the ring slot of the destination while it is
+   *                resident, W = "a constant" for the last level (beta = 0), or the destination's slot in the FAR
+   *                TABLE (W+1 ...) -- states that outlive their ring slot are additionally kept there, written
+   *                once and never recycled, so every arc reads ring[slot]; 64 bytes of slot W close the region.
+   *                Heavy segments: header words {arcs of the state, arcs before this piece}, arc-offset field =
+   *                the state's far-table slot, extension field = arcs of the piece, flags 4 (heavy) | 8 (first
+   *                piece) | 16 (last piece). */
   const uint8_t* tile_stream;
   const int32_t* tile_tab;
   const int32_t* tile_lw_off;
@@ -198,9 +201,9 @@ typedef struct nfst_launch {
   /* Tile-stream execution (tiles != 0): one block of block_threads = 32 * nw threads per lattice (nw = the
    * warps the lattices were dealt to), every warp streams its own tiles through a tile_stages-deep ring of
    * shared-memory stages filled by bulk copies (TMA) that complete on per-stage mbarriers.  tile_ring = largest
-   * DP ring of the group in slots, tile_cap_arcs / tile_cap_bytes = largest tile of the group (arcs / stream
-   * bytes), tile_far != 0: some lattice has far arcs (the passes then need beta / delta / gamma_far in global
-   * memory), tile_stages: 0 = chosen by the library from the shared memory the launch leaves per block. */
+   * DP ring of the group in slots (ring + constant slot + far table), tile_cap_arcs / tile_cap_bytes = largest
+   * tile of the group (arcs / stream bytes), tile_far = largest far table of the group (informational),
+   * tile_stages: 0 = chosen by the library from the shared memory the launch leaves per block. */
   int32_t tiles;
   int32_t tile_ring;
   int32_t tile_far;
@@ -336,13 +339,12 @@ int nfst_sell_flow_f32(const nfst_packed_lattices_t* lat, const nfst_launch_t* l
  * nfst_tile_pull_f32 -- deepest level first.  Log semiring when beta, logz_bwd or cond is given: beta[S] /
  *   logz_bwd[B] (float32, or float64 when launch->state_f64) and cond[A] = exp(w_a + beta[dst_a] - beta[src_a]);
  *   tropical semiring when backptr is given: delta[S] (optional), backptr[S] (canonical arc id, -1 at sinks),
- *   vit_score[B] (optional); first maximum in label order wins.  Groups with tile_far need beta (resp. delta).
+ *   vit_score[B] (optional); first maximum in label order wins.
  * nfst_tile_flow_f32 -- start level first: post[a] = grad_logz[b] * gamma[src_a] * cond[a] with gamma[start] = 1,
  *   gamma[dst_a] += gamma[src_a] * cond[a] accumulated in 32-bit FIXED POINT (2^-31 units) with native integer
  *   shared-memory atomics: the state posteriors carry an absolute error below 1e-9 and the result is bit
  *   reproducible (integer addition commutes).  post may alias cond.  dtheta[V] += post by label (caller
  *   zero-fills; accumulated per lattice in fixed point, then added with one float atomic per label).
- *   gamma_far[S] (float32, zero-filled by the caller) is required for groups with tile_far.
  * Arc arrays are fetched with bulk copies of the 16-byte-aligned superset of a tile's range: arc_scores, cond
  *   and label_out must be 16-byte aligned and readable up to the next multiple of 4 elements.
  */
@@ -352,7 +354,7 @@ int nfst_tile_pull_f32(const nfst_packed_lattices_t* lat, const nfst_launch_t* l
                        void* beta, void* logz_bwd, float* cond, float* delta, int32_t* backptr, float* vit_score,
                        void* cuda_stream);
 int nfst_tile_flow_f32(const nfst_packed_lattices_t* lat, const nfst_launch_t* launch, const float* cond,
-                       const float* grad_logz, float* post, float* dtheta, float* gamma_far, void* cuda_stream);
+                       const float* grad_logz, float* post, float* dtheta, void* cuda_stream);
 /* Diagnostic: builds with -DNFST_TILE_DEBUG range-check every data-dependent index of the tile-stream kernels;
  * this synchronises the device and returns the first violation {code, a, b, c, block, thread, 0, 0} (and clears
  * it).  Regular builds return zeros. */

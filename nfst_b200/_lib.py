@@ -111,7 +111,7 @@ SYMBOLS = {
     "nfst_sell_flow_f32": (C.c_int, [C.POINTER(PackedLatticesC), C.POINTER(LaunchC)] + [_P] * 9),
     "nfst_tile_smem_bytes": (C.c_size_t, [C.POINTER(LaunchC), C.c_int32, C.c_int, C.c_int, C.c_int, C.c_int]),
     "nfst_tile_pull_f32": (C.c_int, [C.POINTER(PackedLatticesC), C.POINTER(LaunchC), C.POINTER(ScoresC)] + [_P] * 7),
-    "nfst_tile_flow_f32": (C.c_int, [C.POINTER(PackedLatticesC), C.POINTER(LaunchC)] + [_P] * 6),
+    "nfst_tile_flow_f32": (C.c_int, [C.POINTER(PackedLatticesC), C.POINTER(LaunchC)] + [_P] * 5),
     "nfst_tile_debug_read": (C.c_int, [_P]),
     "nfst_walk_step_f32": (C.c_int, [C.POINTER(PackedLatticesC), C.c_int32, C.c_int32, _P, _P, _P, _P, _P, _P, C.c_float, C.c_int32,
                                      _P, _P, _P, _P, _P, _P, _P]),

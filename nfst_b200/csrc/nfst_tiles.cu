@@ -11,8 +11,9 @@
 // lattice: the tile's header (which arrives with the tile) says which states and ring slots it covers.
 //
 //   * destinations are 16-bit RING SLOTS computed at pack time: beta[dst] is ring[code], no masking, no range
-//     test; slot W holds the constant of the last level (beta = 0 / delta = 0); an arc whose destination has
-//     left the ring is flagged per slice and resolved through dst_out and global memory (rare);
+//     test; slot W holds the constant of the last level (beta = 0 / delta = 0); a destination that has left the
+//     ring when one of its sources is processed also owns a slot of a small far table behind the ring (W+1 ...,
+//     written once, never recycled), so its arcs read ring[code] like all others;
 //   * slices are processed from registers by a code path specialised for the slice's column count (1..8);
 //     deeper columns (states with 9..32 arcs) loop over the staged tile, states with more arcs are HEAVY:
 //     a slice of their own, possibly cut into several tiles, the whole warp striding over the arcs;
@@ -48,7 +49,7 @@ constexpr float kLn2 = 0.6931471805599453f;
 constexpr float kFloor = -1.0e30f;
 constexpr float kNegInf = -__builtin_huge_valf();
 constexpr float kFix = 2147483648.0f;  // 2^31: fixed-point unit of the flow pass
-constexpr int FLAG_FAR_OUT = 1, FLAG_FAR_IN = 2, FLAG_HEAVY = 4, FLAG_HEAVY_FIRST = 8, FLAG_HEAVY_LAST = 16;
+constexpr int FLAG_FAR_IN = 2, FLAG_HEAVY = 4, FLAG_HEAVY_FIRST = 8, FLAG_HEAVY_LAST = 16;
 
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
@@ -115,12 +116,6 @@ struct TP {
   float hist_scale, hist_inv;  // fixed-point unit of the dtheta histogram
 };
 
-// rare path: the destination has left the ring; its value was written by this block before an earlier level barrier
-template <typename T>
-__device__ __noinline__ T far_load(const T* p, int i) {
-  return *reinterpret_cast<const volatile T*>(p + i);
-}
-
 // online logsumexp pair (m, s): value = m + log(s); branch-free, finite floor instead of -inf
 __device__ __forceinline__ void lse_push(float& m, float& s, float v) {
   const float d = v - m;
@@ -167,20 +162,19 @@ struct PullCtx {
   using RingT = typename std::conditional<TROP, float, OT>::type;
   RingT* ring;
   const float* th;
-  const int32_t* __restrict__ dst_out;
   OT* beta;
   OT* __restrict__ logz;
   float* cond;
   float* delta;
   int32_t* __restrict__ backptr;
   float* __restrict__ vit;
-  int W, last0, start, b, lane;
+  int W, ring_total, start, b, lane;
   int a_lo, a_hi, s_lo, s_hi;  // the lattice's arc / state ranges (range checks of the debug build)
 
   __device__ __forceinline__ RingT ring_at(int code, int where) const {
-    TILE_CHECK(code >= 0 && code <= W, 1, code, W, where);
+    TILE_CHECK(code >= 0 && code < ring_total, 1, code, ring_total, where);
 #ifdef NFST_TILE_DEBUG
-    if (code < 0 || code > W) code = W;
+    if (code < 0 || code >= ring_total) code = W;
 #endif
     return ring[code];
   }
@@ -197,18 +191,14 @@ struct PullCtx {
     if (TH) w += th[on ? g.labs[e] : 0];  // lanes without an arc read a neighbour's entry: no stale label may index theta
     return w;
   }
-  // DP value of the destination of the arc at tile-relative position e (code = its staged ring slot)
-  __device__ __forceinline__ RingT far_value(const Seg& g, int e) const {
-    const int d = dst_out[g.arc0 + e];
-    if (d >= last0) return static_cast<RingT>(0);
-    return TROP ? static_cast<RingT>(far_load(delta, d)) : static_cast<RingT>(far_load(beta, d));
-  }
-  __device__ __forceinline__ void store_state(int s, int slot, RingT v, int arg) const {
-    TILE_CHECK(s >= s_lo && s < s_hi && slot >= 0 && slot < W, 3, s, slot, W);
+  // far = the state's slot in the far table (0: none)
+  __device__ __forceinline__ void store_state(int s, int slot, int far, RingT v, int arg) const {
+    TILE_CHECK(s >= s_lo && s < s_hi && slot >= 0 && slot < W && (far == 0 || (far > W && far < ring_total)), 3, s, slot, far);
 #ifdef NFST_TILE_DEBUG
-    if (!(s >= s_lo && s < s_hi && slot >= 0 && slot < W)) return;
+    if (!(s >= s_lo && s < s_hi && slot >= 0 && slot < W && (far == 0 || (far > W && far < ring_total)))) return;
 #endif
     ring[slot] = v;
+    if (far) ring[far] = v;
     if (!TROP) {
       if (beta) beta[s] = static_cast<OT>(v);
       if (s == start && logz) logz[b] = static_cast<OT>(v);
@@ -224,7 +214,6 @@ struct PullCtx {
   __device__ __forceinline__ void regular(const Seg& g, const int4 h, int s0, int vslot) const {
     const int arc_rel = h.z & 0xffff, nst = (h.z >> 16) & 0xff, dmax = static_cast<unsigned>(h.z) >> 24;
     const int flags = static_cast<unsigned>(h.w) >> 16;
-    const bool far = flags & FLAG_FAR_OUT;
     float wc[NC];
     RingT rv[NC];
     bool on[NC];
@@ -238,14 +227,6 @@ struct PullCtx {
       e += n;
     }
     const int e_tail = e;  // this lane's entry in column KU (when the slice has one)
-    if (far) {             // warp-uniform, rare
-      int e2 = arc_rel + lane;
-#pragma unroll
-      for (int k = 0; k < NC; ++k) {
-        if (on[k] && g.codes[e2] == W) rv[k] = far_value(g, e2);
-        e2 += col_count(h, k);
-      }
-    }
     const unsigned char* nk_ext = g.st + (h.w & 0xffff);  // n_8, n_9, ... (only read when dmax > KU)
     // f(on, e, w, v) over the columns k >= KU of this lane
     auto tail = [&](auto&& f) {
@@ -254,13 +235,14 @@ struct PullCtx {
         const int n = nk_ext[k - KU];
         const bool o = lane < n;
         const float w = score(g, et, o);
-        RingT v = ring_at(g.codes[et], 30 + k);
-        if (far && o && g.codes[et] == W) v = far_value(g, et);
+        const RingT v = ring_at(g.codes[et], 30 + k);
         f(o, et, w, v);
         et += n;
       }
     };
     const int s = s0 + lane;
+    int far = 0;  // warp-uniform branch, rare: some state of the segment is a far destination
+    if (flags & FLAG_FAR_IN) far = reinterpret_cast<const uint16_t*>(nk_ext + (dmax > KU ? 32 : 0))[lane];
     if constexpr (!TROP) {
       // reference arc: the first one (every state with arcs has it); if it scores -inf, the largest
       float rw = wc[0];
@@ -322,7 +304,7 @@ struct PullCtx {
             if (o) cond_store(g.arc0 + et, ex2_approx((fmaxf(rel_term<RingT>(w, v, rw, rb), kFloor) - mf) * kLog2e) * inv, 200);
           });
       }
-      if (lane < nst) store_state(s, vslot + lane, bv, 0);
+      if (lane < nst) store_state(s, vslot + lane, far, bv, 0);
     } else {
       float best = 0.0f;
       int arg = -1;
@@ -344,7 +326,7 @@ struct PullCtx {
             arg = g.arc0 + et;
           }
         });
-      if (lane < nst) store_state(s, vslot + lane, best, arg);  // sinks: delta = 0, backpointer -1
+      if (lane < nst) store_state(s, vslot + lane, far, best, arg);  // sinks: delta = 0, backpointer -1
     }
   }
 };
@@ -375,10 +357,9 @@ __global__ void __launch_bounds__(NT_MAX, MINB)
   Ctx c;
   c.ring = reinterpret_cast<RingT*>(tile_smem);
   c.th = theta;
-  c.dst_out = L.dst_out;
   c.beta = beta; c.logz = logz; c.cond = cond; c.delta = delta; c.backptr = backptr; c.vit = vit_score;
   c.W = info.y;
-  c.last0 = s_base + info.z;
+  c.ring_total = info.z;
   c.start = L.start_state[b];
   c.b = b;
   c.lane = lane;
@@ -461,14 +442,13 @@ __global__ void __launch_bounds__(NT_MAX, MINB)
       const int flags = static_cast<unsigned>(h.w) >> 16;
       if (flags & FLAG_HEAVY) {
         // ---- a piece of a heavy state: the warp strides over its arcs ----
-        const int n = h.w & 0xffff;  // arcs of this piece
-        const bool far = flags & FLAG_FAR_OUT;
+        const int n = h.w & 0xffff;        // arcs of this piece
+        const int far_slot = h.z & 0xffff;  // the state's slot in the far table (0: none)
         // the pull pass walks a warp's tiles backwards: the LAST piece of the state comes first, the FIRST one ends it
         if (!TROP) {
           if (flags & FLAG_HEAVY_LAST) {
             float w0 = c.score(g, 0, true);
             RingT v0 = c.ring_at(g.codes[0], 50);
-            if (far && g.codes[0] == c.W) v0 = c.far_value(g, 0);
             if (!(w0 + static_cast<float>(v0) > kFloor)) { w0 = 0.0f; v0 = static_cast<RingT>(0); }
             hl.m = kFloor; hl.s = 0.0f; hl.rw = w0; hl.rb = static_cast<double>(v0);
           }
@@ -476,8 +456,7 @@ __global__ void __launch_bounds__(NT_MAX, MINB)
 #pragma unroll 2
           for (int e = lane; e < n; e += 32) {
             const float w = c.score(g, e, true);
-            RingT v = c.ring_at(g.codes[e], 51);
-            if (far && g.codes[e] == c.W) v = c.far_value(g, e);
+            const RingT v = c.ring_at(g.codes[e], 51);
             const float t = fmaxf(rel_term<RingT>(w, v, hl.rw, rb), kFloor);
             lse_push(hl.m, hl.s, t);
             if (cond) c.cond_store(g.arc0 + e, t, 300);  // provisional: the offset; rescaled below once beta is known
@@ -497,7 +476,7 @@ __global__ void __launch_bounds__(NT_MAX, MINB)
               if constexpr (sizeof(RingT) == 4) bv = rb + (hl.rw + (m + lg));
               else bv = rb + (static_cast<double>(hl.rw) + (static_cast<double>(m) + static_cast<double>(lg)));
             }
-            if (lane == 0) c.store_state(s0, vslot, bv, 0);
+            if (lane == 0) c.store_state(s0, vslot, far_slot, bv, 0);
             if (cond) {
               // the state's arcs start with this piece; pieces are multiples of 32 arcs, so every lane re-reads
               // exactly what it wrote itself
@@ -515,8 +494,7 @@ __global__ void __launch_bounds__(NT_MAX, MINB)
 #pragma unroll 2
           for (int e = lane; e < n; e += 32) {
             const float w = c.score(g, e, true);
-            RingT v = c.ring_at(g.codes[e], 52);
-            if (far && g.codes[e] == c.W) v = c.far_value(g, e);
+            const RingT v = c.ring_at(g.codes[e], 52);
             const float cnd = __fadd_rn(w, v);
             // later pieces come first: among equal candidates the smaller arc id (= smaller label) wins
             if (ht.arg < 0 || cnd > ht.best || (cnd == ht.best && g.arc0 + e < ht.arg)) {
@@ -536,13 +514,18 @@ __global__ void __launch_bounds__(NT_MAX, MINB)
                 arg = oa;
               }
             }
-            if (lane == 0) c.store_state(s0, vslot, best, arg);
+            if (lane == 0) c.store_state(s0, vslot, far_slot, best, arg);
           }
         }
       } else {
         const int dmax = static_cast<unsigned>(h.z) >> 24;
         switch (dmax < KU ? dmax : KU) {
-          case 0: if (lane < ((h.z >> 16) & 0xff)) c.store_state(s0 + lane, vslot + lane, static_cast<RingT>(0), -1); break;
+          case 0: {  // a slice of arc-less states (dead ends; the last level)
+            int far = 0;
+            if (flags & FLAG_FAR_IN) far = reinterpret_cast<const uint16_t*>(st + (h.w & 0xffff))[lane];
+            if (lane < ((h.z >> 16) & 0xff)) c.store_state(s0 + lane, vslot + lane, far, static_cast<RingT>(0), -1);
+            break;
+          }
           case 1: c.template regular<1>(g, h, s0, vslot); break;
           case 2: c.template regular<2>(g, h, s0, vslot); break;
           case 3: c.template regular<3>(g, h, s0, vslot); break;
@@ -581,17 +564,17 @@ __global__ void __launch_bounds__(NT_MAX, MINB)
 template <bool DTH, int NT_MAX, int MINB>
 __global__ void __launch_bounds__(NT_MAX, MINB)
     tile_flow_kernel(const nfst_packed_lattices_t L, const int32_t* __restrict__ ids, const TP P, const float* cond,
-                     const float* __restrict__ grad_logz, float* post, float* __restrict__ dtheta, float* gamma_far) {
+                     const float* __restrict__ grad_logz, float* post, float* __restrict__ dtheta) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
   const int b = ids ? ids[blockIdx.x] : blockIdx.x;
   const int4 info = __ldg(reinterpret_cast<const int4*>(L.tile_lat_info) + b);
   const int s_base = L.state_off[b];
   const int a_base = info.w;
   const int n_levels = L.level_off[b + 1] - L.level_off[b] - 1;
-  const int W = info.y, last0 = s_base + info.z;
+  const int W = info.y, ring_total = info.z;  // ring, the dump slot W (arcs into the last level), the far table
   unsigned* const ring = reinterpret_cast<unsigned*>(tile_smem);
   unsigned* hist = nullptr;
-  for (int i = tid; i <= W; i += blockDim.x) ring[i] = 0u;
+  for (int i = tid; i < ring_total; i += blockDim.x) ring[i] = 0u;
   if (DTH && P.table) {
     hist = reinterpret_cast<unsigned*>(tile_smem + P.table_off);
     for (int i = tid; i < L.vocab; i += blockDim.x) hist[i] = 0u;
@@ -607,7 +590,6 @@ __global__ void __launch_bounds__(NT_MAX, MINB)
   __syncthreads();
   const float gl = grad_logz ? grad_logz[b] : 1.0f;
   const float unfix = gl * (1.0f / kFix);  // fixed-point gamma -> gradient-scaled posterior mass
-  const int32_t* __restrict__ dst_out = L.dst_out;
 
   unsigned char* const my_stage = tile_smem + P.stage_off + static_cast<size_t>(warp) * D * P.stage_bytes;
   const unsigned stage_s = smem_u32(my_stage);
@@ -635,17 +617,14 @@ __global__ void __launch_bounds__(NT_MAX, MINB)
     for (int i = 0; i < D && i < n_t; ++i) issue(i, __ldg(tab + t_lo + i));
     if (D < n_t) nxt = __ldg(tab + t_lo + D);
   }
-  // one arc: posterior out, flow into the destination's ring slot (or, for a far arc, global memory)
-  auto push = [&](const Seg& g, int e, float gam, bool far) {
+  // one arc: posterior out, flow into the destination's slot (ring, far table, or the dump slot of the last level)
+  auto push = [&](const Seg& g, int e, float gam) {
     const float cd = g.vals[e];
     const unsigned code = g.codes[e];
     const float pf = gam * cd;  // in fixed-point units (gam = gamma * 2^31)
     post[g.arc0 + e] = pf * unfix;
+    TILE_CHECK(static_cast<int>(code) < ring_total, 6, static_cast<int>(code), ring_total, e);
     atomicAdd(&ring[code], __float2uint_rn(pf));
-    if (far && code == static_cast<unsigned>(W)) {
-      const int dd = dst_out[g.arc0 + e];
-      if (dd < last0) atomicAdd(gamma_far + dd, pf * (1.0f / kFix));
-    }
     if (DTH) {
       const float pr = pf * (1.0f / kFix);
       if (hist) atomicAdd(&hist[g.labs[e]], __float2uint_rn(pr * P.hist_scale));
@@ -680,25 +659,28 @@ __global__ void __launch_bounds__(NT_MAX, MINB)
     for (int sg = 0; sg < nseg; ++sg) {
       const int4 h = *reinterpret_cast<const int4*>(st + 16 + 16 * sg);
       const int flags = static_cast<unsigned>(h.w) >> 16;
-      const bool far = flags & FLAG_FAR_OUT;
       if (flags & FLAG_HEAVY) {
         if (flags & FLAG_HEAVY_FIRST) {
-          // every arc into the state comes from a shallower level: gamma is final; free the slot
-          heavy_gam = static_cast<float>(ring[vslot]);
-          if (flags & FLAG_FAR_IN) heavy_gam += *reinterpret_cast<volatile float*>(gamma_far + s0) * kFix;
+          // every arc into the state comes from a shallower level: gamma is final; free the ring slot
+          const int far_slot = h.z & 0xffff;
+          heavy_gam = static_cast<float>(ring[vslot] + (far_slot ? ring[far_slot] : 0u));
           __syncwarp();
           if (lane == 0) ring[vslot] = 0u;
         }
         const int n = h.w & 0xffff;
 #pragma unroll 2
-        for (int e = lane; e < n; e += 32) push(g, e, heavy_gam, far);
+        for (int e = lane; e < n; e += 32) push(g, e, heavy_gam);
       } else {
         const int arc_rel = h.z & 0xffff, nst = (h.z >> 16) & 0xff, dmax = static_cast<unsigned>(h.z) >> 24;
         float gam = 0.0f;
         if (lane < nst) {
-          gam = static_cast<float>(ring[vslot + lane]);
+          unsigned gfix = ring[vslot + lane];
           ring[vslot + lane] = 0u;
-          if (flags & FLAG_FAR_IN) gam += *reinterpret_cast<volatile float*>(gamma_far + s0 + lane) * kFix;
+          if (flags & FLAG_FAR_IN) {  // flow that arrived through the far table
+            const int far_slot = reinterpret_cast<const uint16_t*>(st + (h.w & 0xffff) + (dmax > KU ? 32 : 0))[lane];
+            if (far_slot) gfix += ring[far_slot];
+          }
+          gam = static_cast<float>(gfix);
         }
         int e = arc_rel + lane;
         auto cols = [&](auto nc) {
@@ -706,7 +688,7 @@ __global__ void __launch_bounds__(NT_MAX, MINB)
 #pragma unroll
           for (int k = 0; k < NC; ++k) {
             const int n = col_count(h, k);
-            if (lane < n) push(g, e, gam, far);
+            if (lane < n) push(g, e, gam);
             e += n;
           }
         };
@@ -725,7 +707,7 @@ __global__ void __launch_bounds__(NT_MAX, MINB)
           const unsigned char* nk_ext = st + (h.w & 0xffff);
           for (int k = KU; k < dmax; ++k) {
             const int n = nk_ext[k - KU];
-            if (lane < n) push(g, e, gam, far);
+            if (lane < n) push(g, e, gam);
             e += n;
           }
         }
@@ -922,8 +904,6 @@ int nfst_tile_pull_f32(const nfst_packed_lattices_t* lat, const nfst_launch_t* l
   const bool logs = beta || logz_bwd || cond;
   const bool trop = delta || backptr || vit_score;
   if (trop && !backptr) return nfst_fail_msg(NFST_ERR_BAD_ARG, "the tropical pass needs backptr[S]");
-  if (launch->tile_far && ((logs && !beta) || (trop && !delta)))
-    return nfst_fail_msg(NFST_ERR_BAD_ARG, "a group with far arcs (tile_far) needs beta[S] / delta[S]");
   if (logs) {
     const int rc = launch->state_f64
                        ? launch_pull<false, double>(lat, launch, scores, static_cast<double*>(beta), static_cast<double*>(logz_bwd), cond,
@@ -939,10 +919,9 @@ int nfst_tile_pull_f32(const nfst_packed_lattices_t* lat, const nfst_launch_t* l
 }
 
 int nfst_tile_flow_f32(const nfst_packed_lattices_t* lat, const nfst_launch_t* launch, const float* cond, const float* grad_logz,
-                       float* post, float* dtheta, float* gamma_far, void* cuda_stream) {
+                       float* post, float* dtheta, void* cuda_stream) {
   if (int rc = check_launch(lat, launch)) return rc;
   if (!cond || !post) return nfst_fail_msg(NFST_ERR_BAD_ARG, "cond[A] and post[A] are required");
-  if (launch->tile_far && !gamma_far) return nfst_fail_msg(NFST_ERR_BAD_ARG, "gamma_far[S] is required for groups with far arcs (tile_far)");
   if (launch->n_ids == 0) return 0;
   cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
   const bool table = dtheta && lat->vocab <= NFST_THETA_SMEM_MAX;
@@ -960,13 +939,11 @@ int nfst_tile_flow_f32(const nfst_packed_lattices_t* lat, const nfst_launch_t* l
     if (dtheta) {                                                                                                         \
       auto k = tile_flow_kernel<true, NTv, MINBv>;                                                                        \
       if (int rc = prepare(k, g.smem)) return rc;                                                                         \
-      k<<<launch->n_ids, launch->block_threads, g.smem, stream>>>(*lat, launch->lattice_ids, g.p, cond, grad_logz, post, dtheta, \
-                                                                  gamma_far);                                             \
+      k<<<launch->n_ids, launch->block_threads, g.smem, stream>>>(*lat, launch->lattice_ids, g.p, cond, grad_logz, post, dtheta); \
     } else {                                                                                                              \
       auto k = tile_flow_kernel<false, NTv, MINBv>;                                                                       \
       if (int rc = prepare(k, g.smem)) return rc;                                                                         \
-      k<<<launch->n_ids, launch->block_threads, g.smem, stream>>>(*lat, launch->lattice_ids, g.p, cond, grad_logz, post, dtheta, \
-                                                                  gamma_far);                                             \
+      k<<<launch->n_ids, launch->block_threads, g.smem, stream>>>(*lat, launch->lattice_ids, g.p, cond, grad_logz, post, dtheta); \
     }                                                                                                                     \
   } while (0)
   TILE_BY_BLOCK(FLOW_NT);

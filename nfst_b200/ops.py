@@ -136,7 +136,7 @@ def _scores(packed: PackedLattices, arc_scores, theta):
 def _gamma_far(packed: PackedLattices, alpha: bool = False) -> Optional[torch.Tensor]:
     """zero-filled float32 [S] for the flow pass of groups whose ring does not cover every arc (and of every
     sliced-column group when alpha is wanted: the flow into the last level is only needed for it)"""
-    if any((g.sell and (g.sell_far or alpha)) or (g.tiles and g.tile_far) for g in packed.groups):
+    if any(g.sell and (g.sell_far or alpha) for g in packed.groups):
         return torch.zeros(packed.n_states, dtype=torch.float32, device=packed.device)
     return None
 
@@ -213,7 +213,7 @@ def lattice_pull(packed: PackedLattices, arc_scores=None, theta=None, *, state_d
     logz = torch.empty(packed.n_lattices, dtype=st, device=dev)
     if beta_out is not None and (beta_out.dtype != st or beta_out.numel() != packed.n_states or beta_out.device != dev):
         raise ValueError("beta_out must be [S] in the state dtype on the lattices' device")
-    if beta_out is None and any((g.sell and g.sell_far) or (g.tiles and g.tile_far) for g in packed.groups):
+    if beta_out is None and any(g.sell and g.sell_far for g in packed.groups):
         beta_out = torch.empty(packed.n_states, dtype=st, device=dev)  # arcs longer than the ring re-read beta
     with torch.cuda.device(dev):
         streams = _GroupStreams(dev, len(packed.groups))
@@ -290,7 +290,7 @@ def lattice_backward(
         for i, g in enumerate(packed.groups):
             if g.sell or g.tiles:
                 lc = _launch(g, st)
-                far = g.tile_far if g.tiles else g.sell_far
+                far = g.sell and g.sell_far  # tile-stream groups keep far destinations in shared memory
                 # the log-semiring pull pass runs for beta / logZ, and for the conditionals when the caller has none
                 log_pull = want_beta or (flow and not have_cond)
                 if log_pull or want_viterbi:
@@ -304,7 +304,7 @@ def lattice_backward(
                     dst = post if want_post else (torch.empty(A, **f32) if have_cond else cond)
                     if g.tiles:
                         _lib.check(lib.nfst_tile_flow_f32(packed.c_struct(), lc, cond.data_ptr(), _ptr(g32), dst.data_ptr(),
-                                                          _ptr(dtheta), _ptr(gfar), streams[i]))
+                                                          _ptr(dtheta), streams[i]))
                     else:
                         _lib.check(lib.nfst_sell_flow_f32(packed.c_struct(), lc, cond.data_ptr(), _ptr(g32), dst.data_ptr(),
                                                           None, None, None, _ptr(dtheta), _ptr(gfar), streams[i]))
@@ -357,7 +357,7 @@ def lattice_forward_backward(packed: PackedLattices, arc_scores=None, theta=None
                 _lib.check(lib.nfst_tile_pull_f32(packed.c_struct(), lc, sc, beta.data_ptr(), logz_bwd.data_ptr(),
                                                   post.data_ptr(), None, None, None, stream))
                 _lib.check(lib.nfst_tile_flow_f32(packed.c_struct(), lc, post.data_ptr(), None, post.data_ptr(),
-                                                  _ptr(dtheta), _ptr(gfar), stream))
+                                                  _ptr(dtheta), stream))
                 _lib.check(lib.nfst_fwd_f32(packed.c_struct(), _launch_csr_forward(g, st), sc, alpha.data_ptr(),
                                             logz.data_ptr(), stream))
                 launch_count += 3

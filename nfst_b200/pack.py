@@ -102,8 +102,8 @@ class LaunchGroup:
     csr_block_threads: int = 0  # sliced-column groups: block size their in-order (CSR by destination) chunks were cut for
     # tile-stream execution (nfst_tiles.cu): block_threads = 32 * warps the lattices were dealt to
     tiles: bool = False
-    tile_ring: int = 0  # largest DP ring of the group, in slots (a multiple of 32)
-    tile_far: bool = False  # some arc's destination has left the ring when its source is processed
+    tile_ring: int = 0  # largest DP ring of the group in slots: ring + constant slot + far table
+    tile_far: int = 0  # largest far table of the group (destinations that outlive their ring slot)
     tile_cap_arcs: int = 0  # largest tile, in arcs
     tile_cap_bytes: int = 0  # largest tile, in stream bytes
 
@@ -341,7 +341,7 @@ def build_groups(stats, dev, chunk_info=None) -> List[LaunchGroup]:
                 max_states=int(stats["states"][members].max()), max_reach=int(stats["reach"][members].max()),
                 n_arcs=int(stats["arcs"][members].sum()), n_levels=int(stats["levels"][members].max()),
                 chunk_cap=int(stats["chunk_cap"][members].max()), csr_block_threads=1 << int(stats["block_class"][members].max()),
-                tiles=True, tile_ring=int(stats["tile_ring"][members].max()), tile_far=bool(stats["tile_far"][members].any()),
+                tiles=True, tile_ring=int(stats["tile_ring"][members].max()), tile_far=int(stats["tile_far"][members].max()),
                 tile_cap_arcs=int(stats["tile_cap_arcs"][members].max()), tile_cap_bytes=int(stats["tile_cap_bytes"][members].max()),
             ))
             continue

@@ -17,8 +17,9 @@ thread block walks them.  A lattice is dealt to the ``nw`` warps of its block AT
   counts, offsets, flags), 32-byte extension blocks for slices with more than 8 columns, and the arcs'
   destinations as 16-bit RING SLOTS: the DP values of recent states live in a shared-memory ring of ``W``
   slots (32 per slice, in slice order), slot ``W`` is a constant (beta = 0 / a dump for flow that nobody
-  reads) used for arcs into the last level, and the rare arc whose destination has already left the ring is
-  flagged per slice and resolved through ``dst_out`` / global memory.
+  reads) used for arcs into the last level, and a destination that has already left the ring when one of its
+  sources is processed additionally owns a slot of a small FAR TABLE behind the ring (``W+1 ...``: written once,
+  never recycled) -- so every arc reads ``ring[code]``, whatever its length.
 
 ``tile_tab`` lists, per (lattice, warp), the warp's tiles in level order: {first canonical arc, stream offset,
 sizes, level}.  Everything in the stream is lattice-relative, so independently packed batches concatenate
@@ -43,7 +44,7 @@ TAILMAX = 32  # states with more arcs than this are heavy
 RING_MAX = int(os.environ.get("NFST_TILE_RING_MAX", "49152"))  # ring slots (float32: 192 KB)
 NW_MAX = 32
 
-FLAG_FAR_OUT, FLAG_FAR_IN, FLAG_HEAVY, FLAG_HEAVY_FIRST, FLAG_HEAVY_LAST = 1, 2, 4, 8, 16
+FLAG_FAR_IN, FLAG_HEAVY, FLAG_HEAVY_FIRST, FLAG_HEAVY_LAST = 2, 4, 8, 16
 
 
 def _excl_cumsum(x: torch.Tensor) -> torch.Tensor:
@@ -111,7 +112,7 @@ def build(*, lt_s, slot, level_off, level_ptr, n_levels, st_w, st_j, out_ptr, ou
     empty = {
         "tile_stream": torch.zeros(16, dtype=torch.uint8, device=dev), "tile_tab": torch.zeros((0, 4), dtype=torch.int32, device=dev),
         "tile_lw_off": torch.zeros(1, dtype=torch.int32, device=dev), "tile_lat_info": torch.zeros((B, 4), dtype=torch.int32, device=dev),
-        "stats": {"tile_ring": torch.zeros(B, dtype=torch.int64), "tile_far": torch.zeros(B, dtype=torch.bool),
+        "stats": {"tile_ring": torch.zeros(B, dtype=torch.int64), "tile_far": torch.zeros(B, dtype=torch.int64),
                   "tile_cap_arcs": torch.zeros(B, dtype=torch.int64), "tile_cap_bytes": torch.zeros(B, dtype=torch.int64)},
     }
     if ts.numel() == 0:
@@ -159,25 +160,44 @@ def build(*, lt_s, slot, level_off, level_ptr, n_levels, st_w, st_j, out_ptr, ou
     a_last = slot[a_dst] == last_slot  # destination in the last level: a constant, never the ring
     od = sl_ord[slice_of_state[a_dst]]
     need = od - slot_first_ord[slot[a_src]] + 1  # slices the ring must span for this arc
-    need_in = torch.where(a_last, torch.zeros_like(need), need)
-    full = torch.zeros(B, **i64).scatter_reduce(0, a_lat, need_in, reduce="amax")
-    ring_slices = torch.clamp(torch.maximum(full, lvl_slices_max), min=1, max=RING_MAX // 32)
+    need = torch.where(a_last, torch.zeros_like(need), need)
     if bool((lvl_slices_max[tile_lat] * 32 > RING_MAX).any()):
         raise ValueError("a level is wider than the largest DP ring; raise NFST_TILE_RING_MAX or disable tiles")
+    # Ring size per lattice.  A destination that has left the ring when its source is processed is kept in a
+    # small FAR TABLE behind the ring instead (slots W+1, W+2, ...: written once, never recycled), so the arc
+    # reads it like any other slot.  n slices of ring cost 32 n slots plus one table slot per far destination:
+    # take the n that minimises the sum (far arcs as a bound on far destinations), from a histogram of `need`.
+    nmax = int(need.max()) + 1 if need.numel() else 1
+    hist_need = torch.bincount(a_lat * (nmax + 1) + need, minlength=B * (nmax + 1)).view(B, nmax + 1)
+    far_arcs_if = hist_need.sum(1, keepdim=True) - torch.cumsum(hist_need, 1)  # [B, n]: arcs with need > n
+    cand = torch.arange(nmax + 1, device=dev).unsqueeze(0)
+    cost = 32 * cand + far_arcs_if
+    floor_n = torch.clamp(lvl_slices_max, min=1).unsqueeze(1)
+    cost = torch.where((cand >= floor_n) & (cand <= RING_MAX // 32), cost, torch.full_like(cost, 2**40))
+    ring_slices = torch.maximum(torch.argmin(cost, 1), floor_n.squeeze(1))
+    ring_slices = torch.clamp(ring_slices, max=RING_MAX // 32)
     W = ring_slices * 32  # [B]
     Wa = W[a_lat]
     resident = (~a_last) & (need <= ring_slices[a_lat])
     far = (~a_last) & (~resident)
-    code = torch.where(resident, (32 * od + (a_dst - sl_first[slice_of_state[a_dst]])) % Wa, Wa)
-    lat_far = torch.zeros(B, dtype=torch.bool, device=dev)
-    lat_far[a_lat[far]] = True
+    # far table: one slot per far destination, numbered per lattice in state order
+    far_slot = torch.zeros(S, **i64)  # 0 = none
+    n_far = torch.zeros(B, **i64)
     sl_flags = torch.zeros(NSL, **i64)
     if bool(far.any()):
-        f_out = torch.zeros(NSL, dtype=torch.bool, device=dev)
-        f_out[slice_of_state[a_src[far]]] = True
+        fd = torch.unique(a_dst[far])  # sorted global state ids
+        fd_lat = lt_s[fd]
+        n_far = torch.bincount(fd_lat, minlength=B)
+        rank = torch.arange(fd.numel(), device=dev) - _excl_cumsum(n_far)[:-1][fd_lat]
+        far_slot[fd] = W[fd_lat] + 1 + rank
         f_in = torch.zeros(NSL, dtype=torch.bool, device=dev)
-        f_in[slice_of_state[a_dst[far]]] = True
-        sl_flags = f_out.to(torch.int64) * FLAG_FAR_OUT + f_in.to(torch.int64) * FLAG_FAR_IN
+        f_in[slice_of_state[fd]] = True
+        sl_flags = f_in.to(torch.int64) * FLAG_FAR_IN
+    ring_total = W + 1 + n_far  # ring, the constant slot, the far table
+    if bool((ring_total[tile_lat] > 65535).any()):
+        raise ValueError("DP ring + far table exceed 16-bit slot numbers; lower NFST_TILE_RING_MAX")
+    code = torch.where(resident, (32 * od + (a_dst - sl_first[slice_of_state[a_dst]])) % Wa,
+                       torch.where(far, far_slot[a_dst], Wa))
     sl_vslot = (32 * sl_ord) % W[sl_lat]
 
     # ---- segments (one header each): regular slices, heavy slices cut into pieces of T arcs ----
@@ -194,7 +214,9 @@ def build(*, lt_s, slot, level_off, level_ptr, n_levels, st_w, st_j, out_ptr, ou
     seg_flags = sl_flags[seg_slice] + seg_heavy.to(torch.int64) * (
         FLAG_HEAVY + (seg_piece == 0).to(torch.int64) * FLAG_HEAVY_FIRST
         + (seg_piece == n_seg[seg_slice] - 1).to(torch.int64) * FLAG_HEAVY_LAST)
-    seg_ext = (~seg_heavy) & (sl_dmax[seg_slice] > KU)
+    seg_ext = (~seg_heavy) & (sl_dmax[seg_slice] > KU)  # 32-byte block: n_8 .. n_39
+    seg_farb = (~seg_heavy) & ((sl_flags[seg_slice] & FLAG_FAR_IN) > 0)  # 64-byte block: far-table slot per lane
+    seg_ext_units = seg_ext.to(torch.int64) + 2 * seg_farb.to(torch.int64)  # in 32-byte units
 
     # ---- tiles: consecutive segments of one (level, warp); heavy pieces stand alone ----
     g = (sl_slot * NW_MAX + sl_w)[seg_slice]
@@ -215,12 +237,12 @@ def build(*, lt_s, slot, level_off, level_ptr, n_levels, st_w, st_j, out_ptr, ou
     t_nseg = torch.bincount(tile_of_seg, minlength=NT)
     t_arc0 = seg_arc0[t_first_seg]
     t_arcs = torch.zeros(NT, **i64).index_add_(0, tile_of_seg, seg_arcs)
-    t_next = torch.zeros(NT, **i64).index_add_(0, tile_of_seg, seg_ext.to(torch.int64))
+    t_next = torch.zeros(NT, **i64).index_add_(0, tile_of_seg, seg_ext_units)
     t_slice0 = seg_slice[t_first_seg]
     t_lat, t_w, t_level = sl_lat[t_slice0], sl_w[t_slice0], sl_level[t_slice0]
     t_dst_off = 16 + 16 * t_nseg + 32 * t_next
     t_bytes = (t_dst_off + 2 * t_arcs + 64 + 15) // 16 * 16
-    if int(t_arcs.max()) >= 65536 or int(t_bytes.max()) >= 65536 or int(t_level.max()) >= 65536:
+    if int(t_arcs.max()) >= 65536 or int(t_bytes.max()) >= 65536 or int(t_level.max()) >= 65536 or int(t_next.max()) >= 256:
         raise ValueError("a tile is too large for its 16-bit size fields")
     t_off = _excl_cumsum(t_bytes)
     n_bytes = int(t_off[-1])
@@ -261,11 +283,12 @@ def build(*, lt_s, slot, level_off, level_ptr, n_levels, st_w, st_j, out_ptr, ou
     if hv.numel():
         put32(hdr[hv], sl_arcs[seg_slice[hv]])
         put32(hdr[hv] + 4, seg_piece[hv] * T[hv])
-    put16(hdr + 8, seg_arc0 - t_arc0[seg_tile])
+    # arc offset in the tile; heavy pieces (always offset 0): the state's far-table slot instead
+    put16(hdr + 8, torch.where(seg_heavy, far_slot[sl_first[seg_slice]], seg_arc0 - t_arc0[seg_tile]))
     put16(hdr + 10, sl_nst[seg_slice] | (torch.clamp(sl_dmax[seg_slice], max=255) << 8))
-    ext_rank = torch.cumsum(seg_ext.to(torch.int64), 0) - seg_ext.to(torch.int64)  # global rank among extension blocks
+    ext_rank = torch.cumsum(seg_ext_units, 0) - seg_ext_units  # 32-byte units before this segment's region
     ext_idx = ext_rank - ext_rank[t_first_seg][seg_tile]
-    ext_off = torch.where(seg_ext, 16 + 16 * t_nseg[seg_tile] + 32 * ext_idx, torch.zeros_like(ext_idx))
+    ext_off = torch.where(seg_ext_units > 0, 16 + 16 * t_nseg[seg_tile] + 32 * ext_idx, torch.zeros_like(ext_idx))
     put16(hdr + 12, torch.where(seg_heavy, seg_arcs, ext_off))  # heavy pieces: arcs of the piece
     put16(hdr + 14, seg_flags)
     ex = torch.nonzero(seg_ext).squeeze(1)
@@ -273,6 +296,13 @@ def build(*, lt_s, slot, level_off, level_ptr, n_levels, st_w, st_j, out_ptr, ou
         base = t_off[seg_tile[ex]] + ext_off[ex]
         for q in range(16):
             put16(base + 2 * q, nk_seg[ex, KU + 2 * q] | (nk_seg[ex, KU + 2 * q + 1] << 8))
+    fb = torch.nonzero(seg_farb).squeeze(1)
+    if fb.numel():  # far-table slots of the segment's 32 lanes (0 = none), behind the n_k block if there is one
+        base = t_off[seg_tile[fb]] + ext_off[fb] + 32 * seg_ext[fb].to(torch.int64)
+        st0 = sl_first[seg_slice[fb]]
+        nst = sl_nst[seg_slice[fb]]
+        for ln in range(32):
+            put16(base + 2 * ln, torch.where(ln < nst, far_slot[torch.clamp(st0 + ln, max=S - 1)], torch.zeros_like(st0)))
     # ring slots of the arcs
     a_tile = tile_of_seg[seg_start[slice_of_state[a_src]]
                          + torch.where(sl_heavy[slice_of_state[a_src]],
@@ -291,9 +321,7 @@ def build(*, lt_s, slot, level_off, level_ptr, n_levels, st_w, st_j, out_ptr, ou
     tab = torch.stack([t_arc0, torch.div(t_off, 16, rounding_mode="floor"), t_arcs | (t_nseg << 16) | (t_next << 24),
                        t_level | (torch.div(t_bytes, 16, rounding_mode="floor") << 16)], dim=1)[t_order]
     tab = torch.where(tab >= 2**31, tab - 2**32, tab).to(torch.int32).contiguous()
-    # first state of the last level, lattice-relative (its states are final: beta = 0; the far path needs to know them)
-    last0 = level_ptr[level_off[:-1] + torch.clamp(n_levels - 1, min=0)] - state_off[:-1]
-    info = torch.stack([lw_base[:-1], W, last0, out_ptr[state_off[:-1]]], dim=1).to(torch.int32).contiguous()
+    info = torch.stack([lw_base[:-1], W, ring_total, out_ptr[state_off[:-1]]], dim=1).to(torch.int32).contiguous()
 
     cap_arcs = torch.zeros(B, **i64).scatter_reduce(0, t_lat, t_arcs, reduce="amax")
     cap_bytes = torch.zeros(B, **i64).scatter_reduce(0, t_lat, t_bytes, reduce="amax")
@@ -306,6 +334,6 @@ def build(*, lt_s, slot, level_off, level_ptr, n_levels, st_w, st_j, out_ptr, ou
     del lane_ts
     return {
         "tile_stream": tile_stream, "tile_tab": tab, "tile_lw_off": lw_off.to(torch.int32).contiguous(), "tile_lat_info": info,
-        "stats": {"tile_ring": W.cpu() * tile_lat.cpu(), "tile_far": lat_far.cpu(), "tile_cap_arcs": cap_arcs.cpu(),
+        "stats": {"tile_ring": (ring_total * tile_lat).cpu(), "tile_far": (n_far * tile_lat).cpu(), "tile_cap_arcs": cap_arcs.cpu(),
                   "tile_cap_bytes": cap_bytes.cpu()},
     }

@@ -54,7 +54,7 @@ def test_tile_small_ring_far_arcs(monkeypatch):
     p, sc, _ = check_fwd_bwd(ab, strict=True)
     assert p.has_tiles and any(g.tile_far for g in p.groups)
     viterbi_matches(ab, p, sc)
-    # autograd through the far path (gamma_far)
+    # autograd through the far table
     w = sc.clone().requires_grad_(True)
     nb.lattice_log_partition(p, arc_scores=w).sum().backward()
     _, _, _, o_post = c_oracle.forward_backward(oracle_batch(ab))
@@ -214,7 +214,7 @@ def test_tile_rejects_misuse_and_misalignment():
     z = torch.empty(p.n_lattices, device=DEV)
     rc = lib.nfst_fwd_f32(p.c_struct(), lc, scs, a.data_ptr(), z.data_ptr(), None)
     assert rc < 0 and b"tile-stream" in lib.nfst_last_error_string()
-    rc = lib.nfst_tile_flow_f32(p.c_struct(), lc, None, None, None, None, None, None)
+    rc = lib.nfst_tile_flow_f32(p.c_struct(), lc, None, None, None, None, None)
     assert rc < 0
     logz, _, cond = nb.ops.lattice_pull(p, arc_scores=sc)
     bad = torch.empty(p.n_arcs + 1, device=DEV)[1:]

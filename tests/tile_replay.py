@@ -43,11 +43,18 @@ class Tile:
             if seg["flags"] & T.FLAG_HEAVY:
                 seg["state_arcs"], seg["before"] = int(s[:4].view(np.uint32)[0]), int(s[4:8].view(np.uint32)[0])
                 seg["n_k"] = None
+                seg["far_slots"] = [seg["arc_rel"]]  # heavy pieces: the arc-offset field holds the state's far-table slot
+                seg["arc_rel"] = 0
             else:
                 nk = list(s[:8])
-                if seg["ext"]:
-                    nk += list(raw[seg["ext"]: seg["ext"] + 32])
+                pos = seg["ext"]
+                if seg["dmax"] > T.KU:
+                    nk += list(raw[pos: pos + 32])
+                    pos += 32
                 seg["n_k"] = [int(x) for x in nk]
+                seg["far_slots"] = [0] * 32
+                if seg["flags"] & T.FLAG_FAR_IN:
+                    seg["far_slots"] = [int(x) for x in raw[pos: pos + 64].view(np.uint16)]
             self.segs.append(seg)
             # the next segment of the tile: the next 32 states / ring slots (heavy pieces stand alone in their tile)
             state += 32
@@ -82,9 +89,9 @@ def seg_arcs(tile, seg):
 
 
 def replay(p, w, b, nw):
-    """(beta, cond, post, delta, backptr) of lattice b computed by walking the tile stream like the kernels do."""
+    """(beta, cond, post, delta, backptr, visits) of lattice b computed by walking the tile stream like the kernels do."""
     info = _np(p.tile_lat_info)[b]
-    W, last0 = int(info[1]), int(info[2]) + int(_np(p.state_off)[b])
+    W, total = int(info[1]), int(info[2])
     dst = _np(p.dst_out).astype(np.int64)
     S, A = p.n_states, p.n_arcs
     tl = tiles_of(p, b, nw)
@@ -94,17 +101,9 @@ def replay(p, w, b, nw):
     bp = np.full(S, -2, dtype=np.int64)
     cond = np.zeros(A)
     seen = np.zeros(A, dtype=np.int64)
-    ring = np.full(W + 1, np.nan)
-    ringd = np.full(W + 1, np.nan, dtype=np.float32)
-    ring[W], ringd[W] = 0.0, 0.0
-
-    def nbr(code, a, far_flag, vals, glob):
-        if code < W:
-            return vals[code]
-        if far_flag and dst[a] < last0:
-            return glob[dst[a]]  # far arc: through global memory
-        assert dst[a] >= last0 or far_flag
-        return vals[W]
+    ring = np.full(total, np.nan)
+    ringd = np.full(total, np.nan, dtype=np.float32)
+    ring[W], ringd[W] = 0.0, 0.0  # the constant slot: the last level
 
     for l in range(L - 1, -1, -1):
         writes = []
@@ -114,7 +113,6 @@ def replay(p, w, b, nw):
                 if t.level != l:
                     continue
                 for seg in t.segs:
-                    far = bool(seg["flags"] & T.FLAG_FAR_OUT)
                     arcs = seg_arcs(t, seg)
                     for (_, _, a, _) in arcs:
                         seen[a] += 1
@@ -133,30 +131,33 @@ def replay(p, w, b, nw):
                             rows[lane].append((a, c))
                     for lane, ac in rows.items():
                         s = seg["state0"] + lane
-                        slot = seg["vslot"] + lane
+                        slots = [seg["vslot"] + lane] + ([seg["far_slots"][lane]] if seg["far_slots"][lane] else [])
                         if not ac:
-                            writes.append((s, slot, 0.0, np.float32(0.0), -1))
+                            writes.append((s, slots, 0.0, np.float32(0.0), -1))
                             continue
                         ids = [a for a, _ in ac]
-                        tt = np.array([w[a].astype(np.float64) + nbr(c, a, far, ring, beta) for a, c in ac])
+                        assert all(c < total for _, c in ac)
+                        tt = np.array([w[a].astype(np.float64) + ring[c] for a, c in ac])
+                        assert not np.isnan(tt).any(), "an arc read a ring slot its destination does not own (any more)"
                         m = tt.max()
                         bs = m + np.log(np.exp(tt - m).sum()) if np.isfinite(m) else -np.inf
                         cond[ids] = np.exp(tt - bs) if np.isfinite(bs) else 0.0
-                        cc = np.array([np.float32(w[a]) + np.float32(nbr(c, a, far, ringd, delta)) for a, c in ac], dtype=np.float32)
+                        cc = np.array([np.float32(w[a]) + ringd[c] for a, c in ac], dtype=np.float32)
                         j = int(np.argmax(cc))
-                        writes.append((s, slot, bs, cc[j], ids[j]))
-        for (s, slot, bv, dv, arg) in writes:  # the level barrier: values become visible to the next level
+                        writes.append((s, slots, bs, cc[j], ids[j]))
+        for (s, slots, bv, dv, arg) in writes:  # the level barrier: values become visible to the next level
             beta[s], delta[s], bp[s] = bv, dv, arg
-            assert slot < W
-            ring[slot], ringd[slot] = bv, dv
+            assert slots[0] < W and all(W < x < total for x in slots[1:])
+            for x in slots:
+                ring[x], ringd[x] = bv, dv
+    # every ring read must have hit the slot of its true destination: recompute beta from dst_out
     # flow: start level first; ring slots are zeroed when their owner is consumed
-    gring = np.zeros(W + 1)
-    gfar = np.zeros(S)
+    gring = np.zeros(total)
     post = np.zeros(A)
     start = int(_np(p.start_state)[b])
     first_seg = tl[0][0].segs[0] if tl[0] else None
-    assert first_seg is not None and first_seg["state0"] == start
-    gring[first_seg["vslot"]] = 1.0
+    assert first_seg is not None and first_seg["state0"] == start and first_seg["vslot"] == 0
+    gring[0] = 1.0
     for l in range(L):
         pushes = []
         for wi in range(nw):
@@ -164,27 +165,20 @@ def replay(p, w, b, nw):
                 if t.level != l:
                     continue
                 for seg in t.segs:
-                    far = bool(seg["flags"] & T.FLAG_FAR_OUT)
                     heavy = bool(seg["flags"] & T.FLAG_HEAVY)
                     n_st = 1 if heavy else seg["n_states"]
                     if not heavy or seg["flags"] & T.FLAG_HEAVY_FIRST:
                         gam = {}
                         for lane in range(n_st):
-                            s, slot = seg["state0"] + lane, seg["vslot"] + lane
-                            gam[lane] = gring[slot] + (gfar[s] if seg["flags"] & T.FLAG_FAR_IN else 0.0)
+                            slot, fs = seg["vslot"] + lane, seg["far_slots"][lane]
+                            gam[lane] = gring[slot] + (gring[fs] if fs else 0.0)
                             gring[slot] = 0.0
                         if heavy:
                             hv_g = gam[0]
                     for (lane, _, a, c) in seg_arcs(t, seg):
                         pr = (hv_g if heavy else gam[lane]) * cond[a]
                         post[a] = pr
-                        if c < W:
-                            pushes.append((c, pr, None))
-                        elif far and dst[a] < last0:
-                            pushes.append((None, pr, dst[a]))
-        for (c, pr, d) in pushes:
-            if c is not None:
-                gring[c] += pr
-            else:
-                gfar[d] += pr
+                        pushes.append((c, pr))
+        for (c, pr) in pushes:
+            gring[c] += pr
     return beta, cond, post, delta, bp, seen
