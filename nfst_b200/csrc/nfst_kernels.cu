@@ -552,7 +552,9 @@ __global__ void __launch_bounds__(256, NFST_MIN_BLOCKS)
       }
       if (TROP) {
         const float t = __fadd_rn(w, delta_of(d));
-        if (t > bt) { bt = t; bi = i; }  // strict: within a lane arcs come in label order
+        // strict: within a lane arcs come in label order; the first candidate is taken whatever its score, so a
+        // state whose arcs all score -inf (or NaN) still gets a valid backpointer
+        if (t > bt || bi == 0x7fffffff) { bt = t; bi = i; }
       }
     };
     // four consecutive arcs of one state: independent loads and exps (see lse_push4)
@@ -568,7 +570,7 @@ __global__ void __launch_bounds__(256, NFST_MIN_BLOCKS)
         if (LOGS) u[k] = static_cast<ST>(w) + beta_of(d);
         if (TROP) {
           const float t = __fadd_rn(w, delta_of(d));
-          if (t > bt) { bt = t; bi = i + k; }
+          if (t > bt || bi == 0x7fffffff) { bt = t; bi = i + k; }
         }
       }
       if (LOGS) {
@@ -1003,7 +1005,7 @@ __global__ void __launch_bounds__(256, 4)
         }
         if (TROP) {
           const float t = __fadd_rn(w, sD[d]);
-          if (t > bt) { bt = t; bi = i; }
+          if (t > bt || bi == 0x7fffffff) { bt = t; bi = i; }
         }
         return u;
       };
@@ -1073,7 +1075,7 @@ __global__ void __launch_bounds__(256, 4)
             }
             if (TROP) {
               const float t = __fadd_rn(w, sD[d]);
-              if (t > bt) { bt = t; bi = i; }
+              if (t > bt || bi == 0x7fffffff) { bt = t; bi = i; }
             }
             return u;
           };
@@ -1293,7 +1295,7 @@ __global__ void __launch_bounds__(256, 4)
     }
     if (TROP) {
       const float t = __fadd_rn(w, delta[d]);
-      if (t > bt) { bt = t; bi = a; }
+      if (t > bt || bi == 0x7fffffff) { bt = t; bi = a; }
     }
   };
   auto visit4 = [&](int a, ST am, ST& m, float& sum, float& bt, int& bi) {
@@ -1308,7 +1310,7 @@ __global__ void __launch_bounds__(256, 4)
       if (LOGS) u[q] = static_cast<ST>(w) + beta[d];
       if (TROP) {
         const float t = __fadd_rn(w, delta[d]);
-        if (t > bt) { bt = t; bi = a + q; }
+        if (t > bt || bi == 0x7fffffff) { bt = t; bi = a + q; }
       }
     }
     if (LOGS) {

@@ -90,6 +90,30 @@ __device__ __forceinline__ void block_bar() { asm volatile("bar.sync 0;" ::: "me
 
 extern __shared__ __align__(128) unsigned char tile_smem[];
 
+// loads / stores on 32-bit shared-window addresses: the hot loops keep addresses, not generic pointers
+template <typename T>
+__device__ __forceinline__ T lds(unsigned a) {
+  T v;
+  if constexpr (sizeof(T) == 8) asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a));
+  else asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ unsigned lds_u16(unsigned a) {
+  unsigned short v;
+  asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ int lds_s32(unsigned a) {
+  int v;
+  asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(a));
+  return v;
+}
+template <typename T>
+__device__ __forceinline__ void sts(unsigned a, T v) {
+  if constexpr (sizeof(T) == 8) asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory");
+  else asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory");
+}
+
 // -DNFST_TILE_DEBUG: range checks on the data-dependent indices; the first violation is recorded (code, three
 // values, block, thread) and the access is made harmless.  Read back with nfst_tile_debug_read.
 #ifdef NFST_TILE_DEBUG
@@ -137,13 +161,18 @@ __device__ __forceinline__ int col_count(const int4& h, int k) {
   return (static_cast<unsigned>(k < 4 ? h.x : h.y) >> (8 * (k & 3))) & 0xff;
 }
 
-// everything a segment needs to find its data in the landed stage
+// everything a segment needs to find its data in the landed stage (flow pass: pointers)
 struct Seg {
   const uint16_t* codes;  // ring slots of the tile's arcs (tile-relative arc index)
   const float* vals;      // staged scores (pull) / conditionals (flow), tile-relative
   const int32_t* labs;    // staged labels, tile-relative
   const unsigned char* st;  // the stage (tile header at 0)
   int arc0;               // canonical id of the tile's first arc
+};
+// the same as 32-bit shared-window addresses (pull pass)
+struct SegA {
+  unsigned codes, vals, labs, st;
+  int arc0;
 };
 
 // offset of x from the reference, in float32: (beta - beta_ref) + (w - w_ref), each difference rounded at its own
@@ -157,119 +186,120 @@ __device__ __forceinline__ float rel_term(float w, RingT v, float rw, RingT rb) 
 // =====================================================================================
 // pull pass
 // =====================================================================================
+// byte k (0..7) of a segment header's column counts: one PRMT
+__device__ __forceinline__ int nk_byte(const int4& h, int k) {
+  return static_cast<int>(__byte_perm(static_cast<unsigned>(k < 4 ? h.x : h.y), 0u, 0x4440u | static_cast<unsigned>(k & 3)));
+}
+// block barriers, `n` of them (n > 0), in a loop the compiler cannot mistake for divergent
+__device__ __forceinline__ void block_bars(int n) {
+  asm volatile("{\n\t.reg .pred p;\n\tLB_%=:\n\tbar.sync 0;\n\tadd.s32 %0, %0, -1;\n\tsetp.gt.s32 p, %0, 0;\n\t@p bra.uni LB_%=;\n\t}" : "+r"(n)::"memory");
+}
+
 template <bool TROP, bool SC, bool TH, typename OT>
 struct PullCtx {
   using RingT = typename std::conditional<TROP, float, OT>::type;
-  RingT* ring;
+  unsigned ring_s;  // shared-window address of the ring
   const float* th;
   OT* beta;
-  OT* __restrict__ logz;
   float* cond;
   float* delta;
   int32_t* __restrict__ backptr;
-  float* __restrict__ vit;
-  int W, ring_total, start, b, lane;
-  int a_lo, a_hi, s_lo, s_hi;  // the lattice's arc / state ranges (range checks of the debug build)
-
-  __device__ __forceinline__ RingT ring_at(int code, int where) const {
-    TILE_CHECK(code >= 0 && code < ring_total, 1, code, ring_total, where);
+  int lane;
 #ifdef NFST_TILE_DEBUG
-    if (code < 0 || code >= ring_total) code = W;
+  int W, ring_total, a_lo, a_hi, s_lo, s_hi;  // the lattice's slot / arc / state ranges
 #endif
-    return ring[code];
-  }
-  __device__ __forceinline__ void cond_store(int a, float v, int where) const {
-    TILE_CHECK(a >= a_lo && a < a_hi, 2, a, a_hi, where);
+
+  __device__ __forceinline__ RingT ring_at(unsigned code, int where) const {
 #ifdef NFST_TILE_DEBUG
+    TILE_CHECK(static_cast<int>(code) < ring_total, 1, static_cast<int>(code), ring_total, where);
+    if (static_cast<int>(code) >= ring_total) code = W;
+#endif
+    return lds<RingT>(ring_s + code * static_cast<unsigned>(sizeof(RingT)));
+  }
+  __device__ __forceinline__ void cond_store(float* p, float v, int where) const {
+#ifdef NFST_TILE_DEBUG
+    const long long a = p - cond;
+    TILE_CHECK(a >= a_lo && a < a_hi, 2, static_cast<int>(a), a_hi, where);
     if (a < a_lo || a >= a_hi) return;
 #endif
-    cond[a] = v;
+    *p = v;
   }
-
-  __device__ __forceinline__ float score(const Seg& g, int e, bool on) const {
-    float w = SC ? g.vals[e] : 0.0f;
-    if (TH) w += th[on ? g.labs[e] : 0];  // lanes without an arc read a neighbour's entry: no stale label may index theta
+  // score of the arc at tile-relative position e
+  __device__ __forceinline__ float score(const SegA& g, int e, bool on) const {
+    float w = SC ? lds<float>(g.vals + 4u * e) : 0.0f;
+    if (TH) w += th[on ? lds_s32(g.labs + 4u * e) : 0];  // lanes without an arc read a neighbour's entry: no stale label may index theta
     return w;
   }
-  // far = the state's slot in the far table (0: none)
+  __device__ __forceinline__ RingT value(const SegA& g, int e, int where) const { return ring_at(lds_u16(g.codes + 2u * e), where); }
+  // the DP value of state s: ring slot, the far table (far = its slot there, 0: none), global memory
   __device__ __forceinline__ void store_state(int s, int slot, int far, RingT v, int arg) const {
-    TILE_CHECK(s >= s_lo && s < s_hi && slot >= 0 && slot < W && (far == 0 || (far > W && far < ring_total)), 3, s, slot, far);
 #ifdef NFST_TILE_DEBUG
-    if (!(s >= s_lo && s < s_hi && slot >= 0 && slot < W && (far == 0 || (far > W && far < ring_total)))) return;
+    const bool ok = s >= s_lo && s < s_hi && slot >= 0 && slot < W && (far == 0 || (far > W && far < ring_total));
+    TILE_CHECK(ok, 3, s, slot, far);
+    if (!ok) return;
 #endif
-    ring[slot] = v;
-    if (far) ring[far] = v;
+    sts<RingT>(ring_s + slot * static_cast<unsigned>(sizeof(RingT)), v);
+    if (far) sts<RingT>(ring_s + far * static_cast<unsigned>(sizeof(RingT)), v);
     if (!TROP) {
       if (beta) beta[s] = static_cast<OT>(v);
-      if (s == start && logz) logz[b] = static_cast<OT>(v);
     } else {
       if (delta) delta[s] = static_cast<float>(v);
       backptr[s] = arg;
-      if (s == start && vit) vit[b] = static_cast<float>(v);
     }
   }
 
-  // ---- a regular segment with NC register columns (NC = min(largest degree, KU)) ----
+  // ---- a regular segment with NC register columns (NC = min(largest degree, KU) >= 1) ----
+  // The columns are read through three running addresses (ring slots, scores, labels) that advance by the
+  // column's entry count; lanes without an arc in a column read a neighbour's entry (always inside the stage: the
+  // slot region ends with 32 constant slots, the staged arrays with 32 spare elements) and ignore it.
   template <int NC>
-  __device__ __forceinline__ void regular(const Seg& g, const int4 h, int s0, int vslot) const {
+  __device__ __forceinline__ void regular(const SegA& g, const int4 h, int s0, int vslot) const {
     const int arc_rel = h.z & 0xffff, nst = (h.z >> 16) & 0xff, dmax = static_cast<unsigned>(h.z) >> 24;
     const int flags = static_cast<unsigned>(h.w) >> 16;
+    const int e0 = arc_rel + lane;
+    unsigned pc = g.codes + 2u * e0, pv = g.vals + 4u * e0, pl = g.labs + 4u * e0;
     float wc[NC];
     RingT rv[NC];
     bool on[NC];
-    int e = arc_rel + lane;
 #pragma unroll
     for (int k = 0; k < NC; ++k) {
-      const int n = col_count(h, k);
+      const int n = nk_byte(h, k);
       on[k] = lane < n;
-      wc[k] = score(g, e, on[k]);
-      rv[k] = ring_at(g.codes[e], 10 + k);
-      e += n;
+      float w = SC ? lds<float>(pv) : 0.0f;
+      if (TH) w += th[on[k] ? lds_s32(pl) : 0];
+      wc[k] = w;
+      rv[k] = ring_at(lds_u16(pc), 10 + k);
+      pc += 2u * n;
+      if (SC) pv += 4u * n;
+      if (TH) pl += 4u * n;
     }
-    const int e_tail = e;  // this lane's entry in column KU (when the slice has one)
-    const unsigned char* nk_ext = g.st + (h.w & 0xffff);  // n_8, n_9, ... (only read when dmax > KU)
-    // f(on, e, w, v) over the columns k >= KU of this lane
+    const int e_tail = static_cast<int>(pc - g.codes) >> 1;  // this lane's entry in column KU (when the slice has one)
+    const unsigned nk_ext = g.st + (h.w & 0xffff);            // n_8, n_9, ... (only read when dmax > KU)
+    // f(on, e, w, v) over the columns k >= KU of this lane (states with 9..32 arcs: a few per level)
     auto tail = [&](auto&& f) {
       int et = e_tail;
       for (int k = KU; k < dmax; ++k) {
-        const int n = nk_ext[k - KU];
+        const int n = (lds_s32((nk_ext + k - KU) & ~3u) >> (8 * ((nk_ext + k - KU) & 3u))) & 0xff;
         const bool o = lane < n;
-        const float w = score(g, et, o);
-        const RingT v = ring_at(g.codes[et], 30 + k);
-        f(o, et, w, v);
+        f(o, et, score(g, et, o), value(g, et, 30 + k));
         et += n;
       }
     };
-    const int s = s0 + lane;
-    int far = 0;  // warp-uniform branch, rare: some state of the segment is a far destination
-    if (flags & FLAG_FAR_IN) far = reinterpret_cast<const uint16_t*>(nk_ext + (dmax > KU ? 32 : 0))[lane];
     if constexpr (!TROP) {
-      // reference arc: the first one (every state with arcs has it); if it scores -inf, the largest
+      // reference arc: the state's first (every state with arcs has one); (0, 0) if that one scores -inf
       float rw = wc[0];
       RingT rb = rv[0];
-      if (on[0] && !(rw + static_cast<float>(rb) > kFloor)) {
-        float tbest = kFloor;
-        rw = 0.0f;
-        rb = static_cast<RingT>(0);
-#pragma unroll
-        for (int k = 0; k < NC; ++k) {
-          const float t = wc[k] + static_cast<float>(rv[k]);
-          if (on[k] && t > tbest) {
-            tbest = t;
-            rw = wc[k];
-            rb = rv[k];
-          }
-        }
-      }
+      const bool fin = rw + static_cast<float>(rb) > kFloor;
+      rw = fin ? rw : 0.0f;
+      rb = fin ? rb : static_cast<RingT>(0);
       float tf[NC];
       float mf = kFloor;
 #pragma unroll
       for (int k = 0; k < NC; ++k) {
         tf[k] = on[k] ? rel_term<RingT>(wc[k], rv[k], rw, rb) : kFloor;
-        mf = fmaxf(mf, tf[k]);
+        mf = fmaxf(mf, tf[k]);  // never NaN: fmaxf drops it
       }
       if (NC == KU && dmax > KU) tail([&](bool o, int, float w, RingT v) { if (o) mf = fmaxf(mf, rel_term<RingT>(w, v, rw, rb)); });
-      mf = fmaxf(mf, kFloor);  // a NaN-free floor
       float ex[NC];
       float sum = 0.0f;
       const float mfl = -mf * kLog2e;
@@ -282,41 +312,44 @@ struct PullCtx {
       }
       if (NC == KU && dmax > KU)
         tail([&](bool o, int, float w, RingT v) { if (o) sum += ex2_approx((fmaxf(rel_term<RingT>(w, v, rw, rb), kFloor) - mf) * kLog2e); });
-      if (!(mf > kFloor)) sum = 0.0f;  // no finite arc: every term above was exp(0)
-      // sinks: beta = 1 (scorers.py:720); a state whose arcs all score -inf: beta = -inf
-      RingT bv = static_cast<RingT>(0);
-      const float inv = sum > 0.0f ? rcp_approx(sum) : 0.0f;
-      if (on[0]) {
-        const float lg = lg2_approx(sum) * kLn2;
-        if (!(sum > 0.0f)) bv = static_cast<RingT>(kNegInf);
-        else if constexpr (sizeof(RingT) == 4) bv = rb + (rw + (mf + lg));
-        else bv = rb + (static_cast<double>(rw) + (static_cast<double>(mf) + static_cast<double>(lg)));
-      }
+      const bool any = mf > kFloor;  // some finite arc (else every term above was exp(0))
+      const float inv = any ? rcp_approx(sum) : 0.0f;
+      // states without arcs: beta = 1 (scorers.py:720); all arcs -inf: beta = -inf.  Branch-free.
+      const float lg = lg2_approx(sum) * kLn2;
+      RingT bv;
+      if constexpr (sizeof(RingT) == 4) bv = rb + (rw + (mf + lg));
+      else bv = rb + (static_cast<double>(rw) + (static_cast<double>(mf) + static_cast<double>(lg)));
+      bv = any ? bv : static_cast<RingT>(kNegInf);
+      bv = on[0] ? bv : static_cast<RingT>(0);
       if (cond) {
-        int e2 = arc_rel + lane;
+        float* pq = cond + g.arc0 + e0;
 #pragma unroll
         for (int k = 0; k < NC; ++k) {
-          if (on[k]) cond_store(g.arc0 + e2, ex[k] * inv, 100 + k);
-          e2 += col_count(h, k);
+          if (on[k]) cond_store(pq, ex[k] * inv, 100 + k);
+          pq += nk_byte(h, k);
         }
         if (NC == KU && dmax > KU)
           tail([&](bool o, int et, float w, RingT v) {
-            if (o) cond_store(g.arc0 + et, ex2_approx((fmaxf(rel_term<RingT>(w, v, rw, rb), kFloor) - mf) * kLog2e) * inv, 200);
+            if (o) cond_store(cond + g.arc0 + et, ex2_approx((fmaxf(rel_term<RingT>(w, v, rw, rb), kFloor) - mf) * kLog2e) * inv, 200);
           });
       }
-      if (lane < nst) store_state(s, vslot + lane, far, bv, 0);
+      if (lane < nst) store_state(s0 + lane, vslot + lane, 0, bv, 0);
+      if (flags & FLAG_FAR_IN) {  // warp-uniform, rare: some state of the segment also lives in the far table
+        const unsigned far = lds_u16(nk_ext + (dmax > KU ? 32u : 0u) + 2u * lane);
+        if (far) sts<RingT>(ring_s + far * static_cast<unsigned>(sizeof(RingT)), bv);
+      }
     } else {
       float best = 0.0f;
       int arg = -1;
-      int e2 = arc_rel + lane;
+      int a = g.arc0 + e0;
 #pragma unroll
       for (int k = 0; k < NC; ++k) {
         const float c = __fadd_rn(wc[k], rv[k]);
         if (on[k] && (arg < 0 || c > best)) {  // strict: the columns of a state follow its labels
           best = c;
-          arg = g.arc0 + e2;
+          arg = a;
         }
-        e2 += col_count(h, k);
+        a += nk_byte(h, k);
       }
       if (NC == KU && dmax > KU)
         tail([&](bool o, int et, float w, RingT v) {
@@ -326,7 +359,11 @@ struct PullCtx {
             arg = g.arc0 + et;
           }
         });
-      if (lane < nst) store_state(s, vslot + lane, far, best, arg);  // sinks: delta = 0, backpointer -1
+      if (lane < nst) store_state(s0 + lane, vslot + lane, 0, best, arg);  // states without arcs: delta = 0, backpointer -1
+      if (flags & FLAG_FAR_IN) {
+        const unsigned far = lds_u16(nk_ext + (dmax > KU ? 32u : 0u) + 2u * lane);
+        if (far) sts<float>(ring_s + far * 4u, best);
+      }
     }
   }
 };
@@ -353,26 +390,22 @@ __global__ void __launch_bounds__(NT_MAX, MINB)
   const int4 info = __ldg(reinterpret_cast<const int4*>(L.tile_lat_info) + b);
   const int s_base = L.state_off[b];
   const int a_base = info.w;
+  const int W = info.y;
   const int n_levels = L.level_off[b + 1] - L.level_off[b] - 1;
   Ctx c;
-  c.ring = reinterpret_cast<RingT*>(tile_smem);
+  c.ring_s = smem_u32(tile_smem);
   c.th = theta;
-  c.beta = beta; c.logz = logz; c.cond = cond; c.delta = delta; c.backptr = backptr; c.vit = vit_score;
-  c.W = info.y;
-  c.ring_total = info.z;
-  c.start = L.start_state[b];
-  c.b = b;
+  c.beta = beta; c.cond = cond; c.delta = delta; c.backptr = backptr;
   c.lane = lane;
-  c.a_lo = a_base;
-  c.a_hi = L.n_arcs;
-  c.s_lo = s_base;
-  c.s_hi = L.state_off[b + 1];
+#ifdef NFST_TILE_DEBUG
+  c.W = W; c.ring_total = info.z; c.a_lo = a_base; c.a_hi = L.n_arcs; c.s_lo = s_base; c.s_hi = L.state_off[b + 1];
+#endif
   if (TH && P.table) {
     float* sth = reinterpret_cast<float*>(tile_smem + P.table_off);
     for (int i = tid; i < L.vocab; i += blockDim.x) sth[i] = theta[i];
     c.th = sth;
   }
-  if (tid == 0) c.ring[c.W] = static_cast<RingT>(0);  // the last level: beta = 1 (scorers.py:720), delta = 0
+  if (tid == 0) reinterpret_cast<RingT*>(tile_smem)[W] = static_cast<RingT>(0);  // the last level: beta = 1 (scorers.py:720), delta = 0
   const int D = P.stages;
   uint64_t* const bars = reinterpret_cast<uint64_t*>(tile_smem + P.bar_off) + warp * D;
   const unsigned bars_s = smem_u32(bars);
@@ -422,33 +455,35 @@ __global__ void __launch_bounds__(NT_MAX, MINB)
     const int level = hd.w & 0xffff, nseg = static_cast<unsigned>(hd.w) >> 16;
     TILE_CHECK(level <= cur && nseg >= 1 && nseg <= 64 && 16 + 16 * nseg <= P.cap_bytes, 5, level, cur, nseg);
     // every deeper level is complete before this tile reads the ring (one block barrier per level)
-    while (cur > level) {
-      if (nw > 1) block_bar();
+    if (cur > level) {
+      if (nw > 1) block_bars(cur - level);
       else __syncwarp();
-      --cur;
+      cur = level;
     }
-    Seg g;
-    g.st = st;
+    SegA g;
+    g.st = stage_s + d * P.stage_bytes;
     g.arc0 = hd.y + a_base;
-    g.codes = reinterpret_cast<const uint16_t*>(st + (static_cast<unsigned>(hd.z) >> 16));
-    const int shift = g.arc0 & 3;
-    g.vals = reinterpret_cast<const float*>(st + P.cap_bytes) + shift;
-    g.labs = reinterpret_cast<const int32_t*>(st + P.cap_bytes + (SC ? P.arr_bytes : 0)) + shift;
+    g.codes = g.st + (static_cast<unsigned>(hd.z) >> 16);
+    const unsigned shift = 4u * (g.arc0 & 3);
+    g.vals = g.st + P.cap_bytes + shift;
+    g.labs = g.st + P.cap_bytes + (SC ? P.arr_bytes : 0) + shift;
     int s0 = hd.x + s_base;
     int vslot = hd.z & 0xffff;
+    int4 h = *reinterpret_cast<const int4*>(st + 16);
 #pragma unroll 1
     for (int sg = 0; sg < nseg; ++sg) {
-      const int4 h = *reinterpret_cast<const int4*>(st + 16 + 16 * sg);
+      const int4 hn = *reinterpret_cast<const int4*>(st + 32 + 16 * sg);  // next header (or whatever follows the last)
       const int flags = static_cast<unsigned>(h.w) >> 16;
+      const int dmax = static_cast<unsigned>(h.z) >> 24;
       if (flags & FLAG_HEAVY) {
-        // ---- a piece of a heavy state: the warp strides over its arcs ----
+        // ---- a piece of a heavy state: the warp strides over its arcs.  The pull pass walks a warp's tiles
+        // backwards: the LAST piece of the state comes first, the FIRST one ends it ----
         const int n = h.w & 0xffff;        // arcs of this piece
         const int far_slot = h.z & 0xffff;  // the state's slot in the far table (0: none)
-        // the pull pass walks a warp's tiles backwards: the LAST piece of the state comes first, the FIRST one ends it
         if (!TROP) {
           if (flags & FLAG_HEAVY_LAST) {
             float w0 = c.score(g, 0, true);
-            RingT v0 = c.ring_at(g.codes[0], 50);
+            RingT v0 = c.value(g, 0, 50);
             if (!(w0 + static_cast<float>(v0) > kFloor)) { w0 = 0.0f; v0 = static_cast<RingT>(0); }
             hl.m = kFloor; hl.s = 0.0f; hl.rw = w0; hl.rb = static_cast<double>(v0);
           }
@@ -456,10 +491,10 @@ __global__ void __launch_bounds__(NT_MAX, MINB)
 #pragma unroll 2
           for (int e = lane; e < n; e += 32) {
             const float w = c.score(g, e, true);
-            const RingT v = c.ring_at(g.codes[e], 51);
+            const RingT v = c.value(g, e, 51);
             const float t = fmaxf(rel_term<RingT>(w, v, hl.rw, rb), kFloor);
             lse_push(hl.m, hl.s, t);
-            if (cond) c.cond_store(g.arc0 + e, t, 300);  // provisional: the offset; rescaled below once beta is known
+            if (cond) c.cond_store(cond + g.arc0 + e, t, 300);  // provisional: the offset; rescaled below once beta is known
           }
           if (flags & FLAG_HEAVY_FIRST) {
             float m = hl.m, s = hl.s;
@@ -482,10 +517,9 @@ __global__ void __launch_bounds__(NT_MAX, MINB)
               // exactly what it wrote itself
               const int total = h.x;
               const float inv = finite ? rcp_approx(s) : 0.0f;
-              TILE_CHECK(g.arc0 >= c.a_lo && g.arc0 + total <= c.a_hi, 4, g.arc0, total, c.a_hi);
               for (int e = lane; e < total; e += 32) {
                 const float t = cond[g.arc0 + e];
-                c.cond_store(g.arc0 + e, finite ? ex2_approx((t - m) * kLog2e) * inv : 0.0f, 400);
+                c.cond_store(cond + g.arc0 + e, finite ? ex2_approx((t - m) * kLog2e) * inv : 0.0f, 400);
               }
             }
           }
@@ -494,7 +528,7 @@ __global__ void __launch_bounds__(NT_MAX, MINB)
 #pragma unroll 2
           for (int e = lane; e < n; e += 32) {
             const float w = c.score(g, e, true);
-            const RingT v = c.ring_at(g.codes[e], 52);
+            const RingT v = c.value(g, e, 52);
             const float cnd = __fadd_rn(w, v);
             // later pieces come first: among equal candidates the smaller arc id (= smaller label) wins
             if (ht.arg < 0 || cnd > ht.best || (cnd == ht.best && g.arc0 + e < ht.arg)) {
@@ -517,30 +551,32 @@ __global__ void __launch_bounds__(NT_MAX, MINB)
             if (lane == 0) c.store_state(s0, vslot, far_slot, best, arg);
           }
         }
-      } else {
-        const int dmax = static_cast<unsigned>(h.z) >> 24;
-        switch (dmax < KU ? dmax : KU) {
-          case 0: {  // a slice of arc-less states (dead ends; the last level)
+      } else if (dmax <= 4) {
+        if (dmax <= 2) {
+          if (dmax == 2) c.template regular<2>(g, h, s0, vslot);
+          else if (dmax == 1) c.template regular<1>(g, h, s0, vslot);
+          else {  // a slice of arc-less states (dead ends; the last level)
             int far = 0;
-            if (flags & FLAG_FAR_IN) far = reinterpret_cast<const uint16_t*>(st + (h.w & 0xffff))[lane];
+            if (flags & FLAG_FAR_IN) far = static_cast<int>(lds_u16(g.st + (h.w & 0xffff) + 2u * lane));
             if (lane < ((h.z >> 16) & 0xff)) c.store_state(s0 + lane, vslot + lane, far, static_cast<RingT>(0), -1);
-            break;
           }
-          case 1: c.template regular<1>(g, h, s0, vslot); break;
-          case 2: c.template regular<2>(g, h, s0, vslot); break;
-          case 3: c.template regular<3>(g, h, s0, vslot); break;
-          case 4: c.template regular<4>(g, h, s0, vslot); break;
-          case 5: c.template regular<5>(g, h, s0, vslot); break;
-          case 6: c.template regular<6>(g, h, s0, vslot); break;
-          case 7: c.template regular<7>(g, h, s0, vslot); break;
-          default: c.template regular<8>(g, h, s0, vslot); break;
-        }
-      }
+        } else if (dmax == 3) c.template regular<3>(g, h, s0, vslot);
+        else c.template regular<4>(g, h, s0, vslot);
+      } else if (dmax <= 6) {
+        if (dmax == 5) c.template regular<5>(g, h, s0, vslot);
+        else c.template regular<6>(g, h, s0, vslot);
+      } else if (dmax == 7) c.template regular<7>(g, h, s0, vslot);
+      else c.template regular<8>(g, h, s0, vslot);
+      h = hn;
       s0 += 32;
       vslot += 32;
-      if (vslot >= c.W) vslot -= c.W;
+      if (vslot >= W) vslot -= W;
     }
     __syncwarp();  // every lane is done with the stage: refill it
+    if (level == 0 && lane == 0) {  // the start state is the lattice's first: level 0, ring slot 0
+      if (!TROP && logz) logz[b] = static_cast<OT>(lds<RingT>(c.ring_s));
+      if (TROP && vit_score) vit_score[b] = static_cast<float>(lds<RingT>(c.ring_s));
+    }
     if (lane == 0 && i + D < n_t) {
       issue(d, nxt);
       if (i + D + 1 < n_t) nxt = __ldg(tab + (t_hi - 1 - (i + D + 1)));
@@ -551,11 +587,7 @@ __global__ void __launch_bounds__(NT_MAX, MINB)
     }
   }
   // warps that run out of tiles keep the level barriers company
-  if (nw > 1)
-    while (cur > 0) {
-      block_bar();
-      --cur;
-    }
+  if (nw > 1 && cur > 0) block_bars(cur);
 }
 
 // =====================================================================================
@@ -820,7 +852,7 @@ int check_launch(const nfst_packed_lattices_t* lat, const nfst_launch_t* launch)
     return nfst_fail_msg(NFST_ERR_BAD_ARG, "packed lattices carry no tile-stream arrays");
   const int nt = launch->block_threads;
   if (nt < 32 || nt > 1024 || (nt & (nt - 1))) return nfst_fail_msg(NFST_ERR_BAD_ARG, "block_threads must be a power of two in 32..1024");
-  if (launch->tile_ring < 32 || (launch->tile_ring & 31)) return nfst_fail_msg(NFST_ERR_BAD_ARG, "tile_ring must be a positive multiple of 32");
+  if (launch->tile_ring < 33 || launch->tile_ring > 65535) return nfst_fail_msg(NFST_ERR_BAD_ARG, "tile_ring must be in 33..65535 slots");
   if (launch->tile_cap_bytes <= 0 || launch->tile_cap_arcs < 0) return nfst_fail_msg(NFST_ERR_BAD_ARG, "tile_cap_bytes / tile_cap_arcs are required");
   if (!aligned16(lat->tile_stream) || !aligned16(lat->tile_tab) || !aligned16(lat->tile_lat_info))
     return nfst_fail_msg(NFST_ERR_BAD_ARG, "tile_stream, tile_tab and tile_lat_info must be 16-byte aligned");

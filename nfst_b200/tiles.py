@@ -67,7 +67,7 @@ def tile_arcs_for(nw: torch.Tensor) -> torch.Tensor:
     """Target arcs per tile for lattices dealt to ``nw`` warps: TILE_ARCS for narrow blocks (few warps per SM: each
     bulk copy must be a kilobyte or two to keep HBM busy), smaller for wide blocks (many warps in flight, and
     nw x stages x tile bytes must fit shared memory next to the ring); a multiple of 32, at least 96."""
-    t = torch.clamp(torch.div(4 * TILE_ARCS, torch.clamp(nw, min=1), rounding_mode="floor"), min=min(96, TILE_ARCS), max=TILE_ARCS)
+    t = torch.clamp(torch.div(2 * TILE_ARCS, torch.clamp(nw, min=1), rounding_mode="floor"), min=min(96, TILE_ARCS), max=TILE_ARCS)
     return torch.div(t, 32, rounding_mode="floor") * 32
 
 

@@ -302,6 +302,46 @@ def test_viterbi_bit_exact_config5_sample(integer_scores, exec_mode):
         assert labels[sl][-1] == synth.EOS and labels[sl][0] == synth.BOS
 
 
+@pytest.mark.parametrize("layout", ["small", "block", "level", "sell", "tiles"])
+def test_viterbi_and_logz_when_every_path_is_blocked(layout, monkeypatch):
+    """-inf scores (a theta mask) that leave lattice 0 -- the first of the batch -- without a finite path: Viterbi
+    score and logZ are -inf, every backpointer still names an arc of its own lattice (the path read-out stays in
+    range), the other lattices are untouched.  Every execution model."""
+    if layout in ("block", "level"):
+        monkeypatch.setattr(nb.pack, "SMALL_SMEM_BYTES", 0)
+    if layout == "level":
+        monkeypatch.setattr(nb.pack, "LEVEL_MODE_MIN_ARCS", 1)
+    monkeypatch.setattr(nb.pack, "SELL_MIN_WIDTH", 32)
+    monkeypatch.setattr(nb.pack, "SELL", int(layout == "sell"))
+    monkeypatch.setattr(nb.tiles, "TILES", int(layout == "tiles"))
+    ab = synth.random_dag_batch(4, 6_000, levels=10, seed=31) if layout in ("sell", "tiles") else synth.transliteration_batch(6, seed=3)
+    p, sc = ab.to(DEV).pack()
+    assert p.has_sell == (layout == "sell") and p.has_tiles == (layout == "tiles")
+    w = sc.clone()
+    a0, a1 = int(p.arc_off[0]), int(p.arc_off[1])
+    blocked = torch.zeros(p.n_arcs, dtype=torch.bool, device=DEV)
+    blocked[a0:a1] = p.src_out[a0:a1] == p.start_state[0]  # every arc out of lattice 0's start state
+    w[blocked] = float("-inf")
+    score, off, arcs, labels = nb.lattice_viterbi(p, arc_scores=w)
+    torch.cuda.synchronize()
+    assert torch.isinf(score[0]) and score[0] < 0 and torch.isfinite(score[1:]).all()
+    if arcs.numel():
+        assert int(arcs.min()) >= 0 and int(arcs.max()) < p.n_arcs
+    first = arcs[int(off[0]):int(off[1])]
+    assert bool(((first >= a0) & (first < a1)).all())
+    r = nb.ops.lattice_backward(p, w, want_beta=True, want_viterbi=True)
+    assert torch.isinf(r["logz_bwd"][0]) and r["logz_bwd"][0] < 0 and torch.isfinite(r["logz_bwd"][1:]).all()
+    in0 = torch.arange(int(p.state_off[0]), int(p.state_off[1]), device=DEV)
+    bp = r["backptr"][in0]
+    assert bool(((bp == -1) | ((bp >= a0) & (bp < a1))).all()), "backpointers stay inside their lattice"
+    # the other lattices: bit-exact against the oracle as usual
+    o_score, _, o_labels = c_oracle.viterbi(oracle_batch(ab))
+    assert np.array_equal(score[1:].cpu().numpy().view(np.uint32), o_score[1:].view(np.uint32))
+    offc, lab = off.cpu().numpy(), labels.cpu().numpy()
+    for b in range(1, p.n_lattices):
+        assert list(lab[offc[b]:offc[b + 1]]) == list(o_labels[b])
+
+
 def test_viterbi_dense_golden_lattices_with_ties_and_theta():
     g = np.load(os.path.join(G, "beta_per_sample.npz"))
     rng = np.random.default_rng(7)
