@@ -155,6 +155,11 @@ typedef struct nfst_packed_lattices {
   const int32_t* tile_tab;
   const int32_t* tile_lw_off;
   const int32_t* tile_lat_info;
+  /* Column-major lattices (sliced-column and tile-stream groups) do not keep a state's arcs together.  out_arc
+   * [A] lists them: out_arc[out_ptr[s] + k] = canonical id of the k-th arc of state s in label order (for CSR
+   * lattices that is the identity).  NULL when the batch has no column-major lattice.  Read by the consumers that
+   * visit the arcs of ONE state: the sampling-loop kernels and the beta-hat recurrence. */
+  const int32_t* out_arc;
 } nfst_packed_lattices_t;
 
 /*
@@ -367,7 +372,7 @@ int nfst_tile_debug_read(int32_t* out8);
  * (scorers.py:683-690) and mask_out_invalid (:1037-1054), the beta look-ahead of
  * GRUScorer.actual_left_to_right_score (:583-592), pad_masking (:182-187) and the Categorical
  * log_prob / sample / logsumexp of the loop body (samplers.py:251-283).
- *   state[n_rows]       packed id of each row's current state (CSR lattices only, no sliced-column groups)
+ *   state[n_rows]       packed id of each row's current state
  *   look_state[n_rows]  NULL: beta look-ahead = beta of each arc's own destination.  Otherwise the reference's
  *                       behaviour (quirk: scorers.py:584 reads the state before :679 advances it): beta of the
  *                       label's successor from look_state (the state BEFORE the previous symbol), or beta of
@@ -392,6 +397,16 @@ int nfst_walk_step_f32(const nfst_packed_lattices_t* lat, int32_t n_rows, int32_
                        void* cuda_stream);
 
 /*
+ * Sampler.stripping_pad (src/modules/samplers.py:162-180): left-compacts every row of sequences[n_rows, seq_len]
+ * (int64), dropping symbol id 0, exactly as the reference's column loop does -- including its stop at the first
+ * column that holds pad in every row and the zero it leaves behind a row's last symbol when the row ends in zeros.
+ * out[n_rows, seq_len] (int64; columns >= *width_out are not written), col_flags[seq_len] (int32 scratch),
+ * width_out[1] (int32, device): the width of the reference's result.
+ */
+int nfst_strip_pad(const int64_t* sequences, int32_t n_rows, int32_t seq_len, int64_t pad_id, int64_t* out,
+                   int32_t* col_flags, int32_t* width_out, void* cuda_stream);
+
+/*
  * The whole sampling loop for an arc-factored proposal (WFSTScorer, scorers.py:1663-1687): n_rows =
  * B * rows_per_lattice walks from the start state, next arc drawn with probability
  * exp(w_a + beta[dst_a] - beta[s]) (inverse CDF over the state's arcs in label order, uniform[n_rows, max_len]),
@@ -399,7 +414,7 @@ int nfst_walk_step_f32(const nfst_packed_lattices_t* lat, int32_t n_rows, int32_
  * float64 per beta_f64.  The paths are exact posterior samples: log_q[r] = score(path) - logZ, so every
  * importance weight of Estimators.iwae (estimatros.py:10-44) equals logZ.  labels[n_rows, max_len] (padded
  * with pad_id), arcs[n_rows, max_len] canonical arc ids (-1 padded; may be NULL), length[n_rows], log_q[n_rows].
- * CSR lattices only; max_len >= the deepest lattice's level count - 1.
+ * max_len >= the deepest lattice's level count - 1.
  */
 int nfst_sample_paths_f32(const nfst_packed_lattices_t* lat, int32_t n_rows, int32_t rows_per_lattice, int32_t max_len,
                           const nfst_scores_t* scores, const void* beta, int beta_f64, const float* uniform,

@@ -20,6 +20,8 @@ from .ops import (  # noqa: F401
     lattice_viterbi,
 )
 
-from .sampler import LatticeWalker, sample_paths, walk_step  # noqa: F401
+from .sampler import LatticeWalker, sample_paths, stripping_pad, walk_step  # noqa: F401
+from .joint import ExactJointProb  # noqa: F401
+from . import data  # noqa: F401
 
 __version__ = "0.1.0"

@@ -50,6 +50,7 @@ class PackedLatticesC(C.Structure):
         ("tile_tab", C.c_void_p),
         ("tile_lw_off", C.c_void_p),
         ("tile_lat_info", C.c_void_p),
+        ("out_arc", C.c_void_p),
     ]
 
 
@@ -115,6 +116,7 @@ SYMBOLS = {
     "nfst_tile_debug_read": (C.c_int, [_P]),
     "nfst_walk_step_f32": (C.c_int, [C.POINTER(PackedLatticesC), C.c_int32, C.c_int32, _P, _P, _P, _P, _P, _P, C.c_float, C.c_int32,
                                      _P, _P, _P, _P, _P, _P, _P]),
+    "nfst_strip_pad": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int64, _P, _P, _P, _P]),
     "nfst_sample_paths_f32": (C.c_int, [C.POINTER(PackedLatticesC), C.c_int32, C.c_int32, C.c_int32, C.POINTER(ScoresC), _P,
                                         C.c_int, _P, C.c_int32, _P, _P, _P, _P, _P]),
     "nfst_beta_hat_level_f32": (C.c_int, [C.POINTER(PackedLatticesC), _P, C.c_int32, C.c_int32, _P, _P, _P, _P, _P, _P, _P]),

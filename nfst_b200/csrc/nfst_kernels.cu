@@ -1530,7 +1530,8 @@ __global__ void nfst_beta_hat_level_kernel(const nfst_packed_lattices_t L, const
   }
   const float wi = act ? w[i] : 0.0f;
   float mx = kNegInf, sum = 0.0f, acc = 0.0f;
-  for (int a = b0; a < b1; ++a) {
+  for (int ai = b0; ai < b1; ++ai) {
+    const int a = L.out_arc ? L.out_arc[ai] : ai;  // column-major lattices list a state's arcs through out_arc
     const int n = L.dst_out[a], lab = L.label_out[a];
     const float mh = act ? tanhf(label_proj[static_cast<size_t>(lab) * H + i] + h_proj[static_cast<size_t>(n) * H + i]) : 0.0f;
     float part = wi * mh;

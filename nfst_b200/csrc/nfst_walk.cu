@@ -29,6 +29,11 @@ namespace {
 
 constexpr float kNegInf = -__builtin_huge_valf();
 
+// canonical id of the arc at CSR position i (= out_ptr[s] + k: the k-th arc of state s in label order).  CSR
+// lattices: the identity.  Column-major lattices (sliced-column / tile-stream groups) store a state's arcs apart;
+// nfst_packed_lattices_t.out_arc lists them.
+__device__ __forceinline__ int arc_at(const nfst_packed_lattices_t& L, int i) { return L.out_arc ? __ldg(L.out_arc + i) : i; }
+
 __global__ void walk_step_kernel(const nfst_packed_lattices_t L, int n_rows, int rows_per_lattice,
                                  const int32_t* __restrict__ state, const int32_t* __restrict__ look_state,
                                  const float* __restrict__ prefix,
@@ -55,8 +60,10 @@ __global__ void walk_step_kernel(const nfst_packed_lattices_t L, int n_rows, int
   const float beta_none = look_state ? beta_real[L.start_state[r / rows_per_lattice]] : 0.0f;
   auto look = [&](int a, int l) -> float {
     if (!look_state) return beta_real[L.dst_out[a]];
-    for (int b = b0; b < b1; ++b)
+    for (int i = b0; i < b1; ++i) {
+      const int b = arc_at(L, i);
       if (L.label_out[b] == l) return beta_real[L.dst_out[b]];
+    }
     return beta_none;
   };
   auto logit = [&](int a) -> float {
@@ -75,19 +82,22 @@ __global__ void walk_step_kernel(const nfst_packed_lattices_t L, int n_rows, int
     return;
   }
   float m = kNegInf;
-  for (int a = a0; a < a1; ++a) m = fmaxf(m, logit(a));
+  for (int i = a0; i < a1; ++i) m = fmaxf(m, logit(arc_at(L, i)));
   float sum = 0.0f;
-  for (int a = a0; a < a1; ++a) sum += (m > kNegInf) ? expf(logit(a) - m) : 0.0f;
+  for (int i = a0; i < a1; ++i) sum += (m > kNegInf) ? expf(logit(arc_at(L, i)) - m) : 0.0f;
   const float lz = (m > kNegInf) ? m + logf(sum) : kNegInf;
   int pick = -1;
   if (given_sym) {  // evaluate_only: score the given symbol (samplers.py:258-259)
     const int want = given_sym[r];
-    for (int a = a0; a < a1; ++a)
+    for (int i = a0; i < a1; ++i) {
+      const int a = arc_at(L, i);
       if (L.label_out[a] == want) pick = a;
+    }
   } else {  // inverse CDF over the arcs in label order
     const float target = uniform[r] * sum;
     float cum = 0.0f;
-    for (int a = a0; a < a1; ++a) {
+    for (int i = a0; i < a1; ++i) {
+      const int a = arc_at(L, i);
       const float e = expf(logit(a) - m);
       cum += e;
       if (e > 0.0f) pick = a;  // the last arc with mass catches round-off at the top
@@ -169,7 +179,8 @@ __global__ void sample_paths_kernel(const nfst_packed_lattices_t L, int n_rows, 
     };
     int pick = -1;
     double cum = 0.0, lp = 0.0;
-    for (int a = a0; a < a1; ++a) {
+    for (int i = a0; i < a1; ++i) {
+      const int a = arc_at(L, i);
       const double lc = logc(a);
       const double c = exp(lc);
       if (c > 0.0) {  // the last arc with mass catches round-off at the top of the CDF
@@ -193,7 +204,69 @@ __global__ void sample_paths_kernel(const nfst_packed_lattices_t L, int n_rows, 
   }
 }
 
+// ---- Sampler.stripping_pad (src/modules/samplers.py:162-180) ----
+// Pass 1: which columns hold `pad` in EVERY row (the reference stops at the first such column).
+__global__ void strip_pad_columns_kernel(const int64_t* __restrict__ seq, int n_rows, int T, int64_t pad_id,
+                                         int32_t* __restrict__ col_not_pad) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= n_rows) return;
+  const int64_t* row = seq + static_cast<size_t>(warp) * T;
+  for (int i = lane; i < T; i += 32)
+    if (row[i] != pad_id) col_not_pad[i] = 1;  // benign race: every writer stores 1
+}
+// Pass 2: one warp per row left-compacts the symbols != 0 of columns 0..last (last = the first all-pad column, or
+// T - 1), exactly as the reference's loop does: a symbol is written at the row's cursor, the cursor advances unless
+// the symbol is 0 -- so a 0 is overwritten by whatever follows, and survives only behind the last non-zero symbol.
+__global__ void strip_pad_compact_kernel(const int64_t* __restrict__ seq, int n_rows, int T, int64_t pad_id,
+                                         const int32_t* __restrict__ col_not_pad, int64_t* __restrict__ out,
+                                         int32_t* __restrict__ width_out) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= n_rows) return;
+  int last = T - 1;  // every lane scans the flags: T is a few hundred
+  for (int i0 = 0; i0 < T; i0 += 32) {
+    const int i = i0 + lane;
+    const unsigned all_pad = __ballot_sync(0xffffffffu, i < T && col_not_pad[i] == 0);
+    if (all_pad) {
+      last = i0 + __ffs(all_pad) - 1;
+      break;
+    }
+  }
+  if (warp == 0 && lane == 0) *width_out = last + 1;
+  const int64_t* row = seq + static_cast<size_t>(warp) * T;
+  int64_t* dst = out + static_cast<size_t>(warp) * T;
+  int cursor = 0;
+  bool trailing_zero = false;
+  for (int i0 = 0; i0 <= last; i0 += 32) {
+    const int i = i0 + lane;
+    const bool in = i <= last;
+    const int64_t v = in ? row[i] : 0;
+    const unsigned nz = __ballot_sync(0xffffffffu, in && v != 0);
+    const unsigned zr = __ballot_sync(0xffffffffu, in && v == 0);
+    if (in && v != 0) dst[cursor + __popc(nz & ((1u << lane) - 1u))] = v;
+    cursor += __popc(nz);
+    // a zero behind the last non-zero symbol seen so far stays at the cursor
+    if (zr) trailing_zero = nz == 0u ? true : (31 - __clz(zr)) > (31 - __clz(nz));
+    else if (nz) trailing_zero = false;
+  }
+  for (int i = cursor + lane; i <= last; i += 32) dst[i] = (i == cursor && trailing_zero) ? 0 : pad_id;
+}
+
 }  // namespace
+
+extern "C" int nfst_strip_pad(const int64_t* sequences, int32_t n_rows, int32_t seq_len, int64_t pad_id, int64_t* out,
+                              int32_t* col_flags, int32_t* width_out, void* cuda_stream) {
+  if (!sequences || !out || !col_flags || !width_out) return nfst_fail_msg(NFST_ERR_BAD_ARG, "nfst_strip_pad: null argument");
+  if (n_rows <= 0 || seq_len <= 0) return nfst_fail_msg(NFST_ERR_BAD_ARG, "nfst_strip_pad: empty input");
+  cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+  cudaError_t e = cudaMemsetAsync(col_flags, 0, sizeof(int32_t) * seq_len, st);
+  if (e != cudaSuccess) return nfst_fail_msg(NFST_ERR_CUDA, "nfst_strip_pad: %s", cudaGetErrorString(e));
+  const int threads = 128, blocks = (n_rows * 32 + threads - 1) / threads;
+  strip_pad_columns_kernel<<<blocks, threads, 0, st>>>(sequences, n_rows, seq_len, pad_id, col_flags);
+  strip_pad_compact_kernel<<<blocks, threads, 0, st>>>(sequences, n_rows, seq_len, pad_id, col_flags, out, width_out);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return nfst_fail_msg(NFST_ERR_CUDA, "strip_pad kernels: %s", cudaGetErrorString(e));
+  return 0;
+}
 
 extern "C" int nfst_sample_paths_f32(const nfst_packed_lattices_t* lat, int32_t n_rows, int32_t rows_per_lattice,
                                      int32_t max_len, const nfst_scores_t* scores, const void* beta, int beta_f64,

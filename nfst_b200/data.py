@@ -1,0 +1,137 @@
+"""Lattice files: the reference's dense ``.npz`` examples and a packed cache beside them.
+
+The reference stores one example per ``<name>.npz`` with six arrays -- ``num_emission``, ``num_transition``,
+``denom_emission``, ``denom_transition``, ``gs``, ``ps`` (``src/preprocess/tr.py:182-190``) -- and re-reads,
+inflates and pads the dense ``[S, V]`` tables on every epoch (``Utils.load_fsa_from_npz``,
+``src/util/preprocess_util.py:293-323``; ``FSADataset.__getitem__``, ``src/util/dataset_reader.py:30-40``;
+``collate``, ``:175-186``) although fewer than 1 % of the cells are arcs.  Here an example is packed ONCE
+(``pack_dense``: the reference's edge rule, levels, CSR / column layouts) and the packed arrays are written next
+to the dense file (``<name>.packed.npz``); later epochs load that file -- a few kilobytes per example -- and
+``collate`` concatenates the cached packs (``concat_packed``: a fixed number of tensor ops, no re-packing).
+"""
+from __future__ import annotations
+
+import os
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from .pack import LaunchGroup, PackedLattices, build_groups, concat_packed, pack_dense
+
+DENSE_KEYS = ("num_emission", "num_transition", "denom_emission", "denom_transition", "gs", "ps")
+PACKED_FORMAT = 2  # bump when the packed layout changes: stale caches are rebuilt
+
+
+def load_fsa_from_npz(npz_fname: str, wfst_name=None, vocab_size=None, pad=None) -> Tuple[np.ndarray, ...]:
+    """The six arrays of a reference example, in the reference's order and with its error for a missing file
+    (``preprocess_util.py:293-310``).  ``wfst_name`` (a weighted proposal FST read through pynini,
+    ``:314-322``) is outside this package's scope."""
+    assert os.path.exists(npz_fname), f"{npz_fname} does not exist! Please run preprocess_npz.py first."
+    if wfst_name is not None:
+        raise NotImplementedError("weighted proposal FSTs are read with pynini by the reference; pass the dense tables instead")
+    with np.load(npz_fname) as l:
+        return tuple(l[k] for k in DENSE_KEYS)
+
+
+def _group_fields(g: LaunchGroup):
+    return {k: v for k, v in g.__dict__.items() if not isinstance(v, torch.Tensor) and v is not None}
+
+
+def save_packed(path: str, packed: PackedLattices) -> None:
+    """Write a packed batch (usually one example) as an ``.npz``: every array of ``PackedLattices`` plus the
+    per-lattice statistics the launch groups are rebuilt from."""
+    arrays = {"__format__": np.array([PACKED_FORMAT]), "__scalars__": np.array(
+        [packed.n_lattices, packed.n_states, packed.n_arcs, packed.vocab, packed.max_levels], dtype=np.int64)}
+    for name in packed.tensors():
+        arrays[name] = getattr(packed, name).cpu().numpy()
+    for k, v in packed.stats.items():
+        arrays["stat__" + k] = v.cpu().numpy()
+    if packed.dense_shape is not None:
+        arrays["__dense_shape__"] = np.array(packed.dense_shape, dtype=np.int64)
+    tmp = path + ".tmp.npz"
+    np.savez(tmp, **arrays)
+    os.replace(tmp, path)
+
+
+def load_packed(path: str, device="cpu") -> PackedLattices:
+    """Inverse of ``save_packed``.  Raises ``ValueError`` for a cache written by another layout version."""
+    with np.load(path) as l:
+        if "__format__" not in l.files or int(l["__format__"][0]) != PACKED_FORMAT:
+            raise ValueError(f"{path}: packed-lattice cache of another format; re-pack it")
+        B, S, A, V, max_levels = (int(x) for x in l["__scalars__"])
+        stats = {k[6:]: torch.from_numpy(l[k]) for k in l.files if k.startswith("stat__")}
+        kw = {k: torch.from_numpy(l[k]) for k in l.files if not k.startswith("__") and not k.startswith("stat__")}
+        dense_shape = tuple(int(x) for x in l["__dense_shape__"]) if "__dense_shape__" in l.files else None
+    kw = {k: v.to(device) for k, v in kw.items()}
+    kw.setdefault("static_scores", None)
+    ci = {d: (kw[f"{d}_chunk_off"].to(torch.int64), kw[f"{d}_chunks"], kw[f"{d}_chunk_level"]) for d in ("fwd", "bwd")}
+    groups = build_groups(stats, torch.device(device), ci)
+    return PackedLattices(n_lattices=B, n_states=S, n_arcs=A, vocab=V, dense_shape=dense_shape, groups=groups,
+                          max_levels=max_levels, stats=stats, **kw)
+
+
+class PackedExample:
+    """What ``LatticeDataset.__getitem__`` returns: the numerator lattice packed, and ``gs`` / ``ps`` as read."""
+
+    def __init__(self, packed: PackedLattices, gs: np.ndarray, ps: np.ndarray, name: str):
+        self.packed, self.gs, self.ps, self.name = packed, gs, ps, name
+
+
+class LatticeDataset(torch.utils.data.Dataset):
+    """Counterpart of ``FSADataset`` (``dataset_reader.py:16-43``) over the same list of example names.
+
+    ``__getitem__`` returns the numerator lattice of ``<name>.npz`` packed (the denominator tables are cyclic
+    and never fed to the DP: ``denom_prob`` is hard-wired to zero, ``lightning.py:473``).  The first access packs
+    the dense tables and writes ``<name>.packed.npz`` (in ``cache_dir`` if given); later accesses read that."""
+
+    def __init__(self, list_of_machines: Sequence[str], vocab_size: Optional[int] = None, pad: Optional[int] = None,
+                 cache_dir: Optional[str] = None, weighted: Optional[bool] = None):
+        self.l = list(list_of_machines)
+        self.vocab_size, self.pad = vocab_size, pad
+        self.cache_dir, self.weighted = cache_dir, weighted
+
+    def __len__(self) -> int:
+        return len(self.l)
+
+    def cache_path(self, name: str) -> str:
+        if self.cache_dir is None:
+            return f"{name}.packed.npz"
+        return os.path.join(self.cache_dir, name.strip(os.sep).replace(os.sep, "__") + ".packed.npz")
+
+    def __getitem__(self, index: int) -> PackedExample:
+        name = self.l[index]
+        dense, cache = f"{name}.npz", self.cache_path(name)
+        if os.path.exists(cache) and (not os.path.exists(dense) or os.path.getmtime(cache) >= os.path.getmtime(dense)):
+            try:
+                with np.load(dense) as l:
+                    gs, ps = l["gs"], l["ps"]
+                return PackedExample(load_packed(cache), gs, ps, name)
+            except (ValueError, OSError, KeyError):
+                pass  # stale or unreadable cache: rebuild it (the reference re-serialises unreadable files too, tr.py:135-141)
+        ne, nt, _, _, gs, ps = load_fsa_from_npz(dense, None, self.vocab_size, self.pad)
+        em = torch.from_numpy(np.ascontiguousarray(ne))[None]
+        tr = torch.from_numpy(np.ascontiguousarray(nt).astype(np.int64))[None]
+        packed = pack_dense(em, tr, weighted=self.weighted)
+        if self.cache_dir is not None:
+            os.makedirs(self.cache_dir, exist_ok=True)
+        save_packed(cache, packed)
+        return PackedExample(packed, gs, ps, name)
+
+
+def pad_sequence_1d(seqs: List[np.ndarray], padding_value: int) -> torch.Tensor:
+    """``Utils.pad_sequence`` (``preprocess_util.py:368-392``) for the 1-D ``gs`` / ``ps`` arrays."""
+    n = max(len(s) for s in seqs)
+    out = torch.full((len(seqs), n), int(padding_value), dtype=torch.int64)
+    for i, s in enumerate(seqs):
+        out[i, : len(s)] = torch.from_numpy(np.asarray(s).astype(np.int64))
+    return out
+
+
+def collate(batch: List[PackedExample], pad: int, device=None):
+    """Counterpart of ``T9FSADataModule.collate`` (``dataset_reader.py:175-186``): (packed batch, gs[B, Lx],
+    ps[B, Ly]).  No dense table is padded or copied; the per-example packs are concatenated."""
+    packed = concat_packed([b.packed for b in batch]) if len(batch) > 1 else batch[0].packed
+    if device is not None:
+        packed = packed.to(device)
+    return packed, pad_sequence_1d([b.gs for b in batch], pad), pad_sequence_1d([b.ps for b in batch], pad)

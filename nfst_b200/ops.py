@@ -542,8 +542,6 @@ def lattice_beta_hat(packed: PackedLattices, label_proj: torch.Tensor, Wh: torch
     dev = packed.device
     if dev.type != "cuda":
         raise RuntimeError("nfst_b200 kernels need the packed lattices on a CUDA device (no CPU fallback)")
-    if packed.has_columns:
-        raise ValueError("the beta-hat recurrence reads CSR arcs: pack with sell=False, tiles=False")
     V, H = label_proj.shape
     if V != packed.vocab or tuple(Wh.shape) != (H, H) or W.numel() != H:
         raise ValueError("label_proj must be [vocab, H], Wh [H, H], W [H]")

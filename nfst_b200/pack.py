@@ -127,7 +127,7 @@ class PackedLattices:
         "in_ptr", "src_in", "label_in", "in2out", "out_ptr", "dst_out", "label_out",
         "fwd_chunk_off", "fwd_chunks", "bwd_chunk_off", "bwd_chunks", "fwd_gather",
         "fwd_chunk_level", "bwd_chunk_level", "bwd_order", "sell_desc", "sell_lvl_slice",
-        "tile_tab", "tile_lw_off", "tile_lat_info",
+        "tile_tab", "tile_lw_off", "tile_lat_info", "out_arc",
     )
 
     # arrays the kernels stage with 16-byte copies: kept zero-padded by PAD elements
@@ -238,7 +238,7 @@ class PackedLattices:
                     continue  # host-side bookkeeping, not part of nfst_packed_lattices_t
                 t = getattr(self, f)
                 assert t.dtype == torch.int32 and t.is_contiguous() and t.data_ptr() % 16 == 0
-                setattr(c, f, t.data_ptr())
+                setattr(c, f, t.data_ptr() if t.numel() else None)
             c.lanes_in_log2 = self.lanes_in_log2.data_ptr()
             c.lanes_out_log2 = self.lanes_out_log2.data_ptr()
             c.out_deg8 = self.out_deg8.data_ptr()
@@ -489,13 +489,19 @@ def concat_packed(parts: List["PackedLattices"]) -> "PackedLattices":
         tabs.append(t)
         lws.append(p.tile_lw_off[:-1] + oT[i])
         inf = p.tile_lat_info.clone()
-        inf[:, 0] += oW[i]
-        inf[:, 3] += oA[i]
+        is_tile = (inf[:, 1] > 0).to(inf.dtype)  # rows of other lattices stay zero
+        inf[:, 0] += oW[i] * is_tile
+        inf[:, 3] += oA[i] * is_tile
         infos.append(inf)
     kw["tile_tab"] = torch.cat(tabs)
     kw["tile_lw_off"] = torch.cat(lws + [torch.tensor([sum(n_tt)], dtype=torch.int32, device=dev)])
     kw["tile_lat_info"] = torch.cat(infos)
     kw["tile_stream"] = torch.cat([p.tile_stream for p in parts])
+    if any(p.out_arc.numel() for p in parts):  # identity for the parts without column-major lattices
+        kw["out_arc"] = torch.cat([(p.out_arc if p.out_arc.numel() else torch.arange(p.n_arcs, dtype=torch.int32, device=dev)) + oA[i]
+                                   for i, p in enumerate(parts)])
+    else:
+        kw["out_arc"] = torch.zeros(0, dtype=torch.int32, device=dev)
     sd = cat("sell_desc")
     kw["sell_desc"] = sd + torch.stack([offA[by_sl], offA[by_sl], torch.zeros_like(offA[by_sl]), torch.zeros_like(offA[by_sl])], dim=1)
     fg = cat("fwd_gather")
@@ -657,6 +663,7 @@ def pack_arcs(
     A = int(src_out.numel())
     out_deg = torch.bincount(src_out, minlength=S)
     out_ptr = _excl_cumsum(out_deg)
+    out_arc = torch.zeros(0, dtype=torch.int64, device=dev)  # empty = identity (no column-major lattice)
     if bool(col_lat.any()) and A:
         # column-major inside every slice: key (first arc of the slice, k, lane)
         pos = torch.arange(A, device=dev)
@@ -674,6 +681,10 @@ def pack_arcs(
             + torch.where(is_sell, lane, zero)
         perm2 = torch.argsort(key, stable=True)
         src_out, dst_out, label_out, origin = src_out[perm2], dst_out[perm2], label_out[perm2], origin[perm2]
+        # the arcs of ONE state in label order, for the consumers that walk a single state (sampler, beta-hat):
+        # CSR position out_ptr[s] + k -> canonical id
+        out_arc = torch.empty(A, dtype=torch.int64, device=dev)
+        out_arc[perm2] = pos
     in2out = torch.argsort(dst_out, stable=True)
     src_in, label_in = src_out[in2out], label_out[in2out]
     in_ptr = _excl_cumsum(torch.bincount(dst_out, minlength=S))
@@ -791,7 +802,7 @@ def pack_arcs(
         fwd_gather=i32(fwd_gather), fwd_chunk_level=i32(fwd_chunk_level), bwd_chunk_level=i32(bwd_chunk_level),
         bwd_order=bwd_order, sell_desc=i32(sell_desc), sell_lvl_slice=i32(sell_lvl_slice),
         tile_stream=tile_data["tile_stream"], tile_tab=tile_data["tile_tab"], tile_lw_off=tile_data["tile_lw_off"],
-        tile_lat_info=tile_data["tile_lat_info"],
+        tile_lat_info=tile_data["tile_lat_info"], out_arc=i32(out_arc),
         lanes_in_log2=lg_in.to(torch.uint8).contiguous(), lanes_out_log2=lg_out.to(torch.uint8).contiguous(),
         out_deg8=torch.clamp(out_deg, max=255).to(torch.uint8).contiguous(), src_out=i32(src_out),
         orig_state=i32(orig_state), arc_origin=origin.contiguous(), arc_off=i32(arc_off), n_levels=i32(n_levels),
@@ -833,11 +844,11 @@ def dense_arcs(transition: torch.Tensor):
 
 
 def pack_dense(emission: Optional[torch.Tensor], transition: torch.Tensor, *,
-               weighted: Optional[bool] = None) -> PackedLattices:
+               weighted: Optional[bool] = None, sell: Optional[bool] = None, tiles: Optional[bool] = None) -> PackedLattices:
     """Pack collate()-style dense tables ``emission[B, S, V]`` / ``transition[B, S, V]``.
 
     ``weighted``: treat ``emission`` as float log-weights (``scorers.py:1011-1013,1026-1027``)
-    that become static arc scores; default = emission is a floating tensor.
+    that become static arc scores; default = emission is a floating tensor.  ``sell`` / ``tiles``: as in ``pack_arcs``.
     """
     if transition.dim() != 3 or (emission is not None and emission.shape != transition.shape):
         raise ValueError("emission and transition must both be [B, S, V]")
@@ -851,7 +862,8 @@ def pack_dense(emission: Optional[torch.Tensor], transition: torch.Tensor, *,
     if weighted:
         static = emission.reshape(-1)[row * V + lab].to(torch.float32)
     n_states = torch.full((B,), S, dtype=torch.int64, device=transition.device)
-    packed = pack_arcs(row // S, row % S, dst, lab, n_states, V, static_scores=static, dense_shape=(B, S, V))
+    packed = pack_arcs(row // S, row % S, dst, lab, n_states, V, static_scores=static, dense_shape=(B, S, V), sell=sell,
+                       tiles=tiles)
     # arc_origin indexes the arc list; turn it into the dense cell index (b*S+s)*V+l
     packed.arc_origin = (row * V + lab)[packed.arc_origin].contiguous()
     return packed

@@ -34,8 +34,6 @@ class LatticeWalker:
                  temperature: float = 1.0, faithful: bool = True):
         if packed.device.type != "cuda":
             raise RuntimeError("nfst_b200 kernels need the packed lattices on a CUDA device (no CPU fallback)")
-        if packed.has_columns:
-            raise ValueError("the walk reads CSR arcs: pack with sell=False")
         if beta_real.numel() != packed.n_states:
             raise ValueError("beta_real must hold one value per packed state")
         self.packed, self.k, self.pad_id = packed, int(k), int(pad_id)
@@ -86,8 +84,6 @@ def walk_step(packed: PackedLattices, k: int, state: torch.Tensor, prefix: torch
     dev = packed.device
     if dev.type != "cuda":
         raise RuntimeError("nfst_b200 kernels need the packed lattices on a CUDA device (no CPU fallback)")
-    if packed.has_columns:
-        raise ValueError("the walk reads CSR arcs: pack with sell=False")
     N = packed.n_lattices * k
     V = packed.vocab
     if state.numel() != N or tuple(prefix.shape) != (N, V):
@@ -125,8 +121,6 @@ def sample_paths(packed: PackedLattices, k: int, arc_scores=None, theta=None, *,
     dev = packed.device
     if dev.type != "cuda":
         raise RuntimeError("nfst_b200 kernels need the packed lattices on a CUDA device (no CPU fallback)")
-    if packed.has_columns:
-        raise ValueError("the walk reads CSR arcs: pack with sell=False")
     sc, keep = ops._scores(packed, arc_scores, theta)
     if beta is None:
         r = ops.lattice_backward(packed, arc_scores, theta, want_beta=True)
@@ -150,3 +144,27 @@ def sample_paths(packed: PackedLattices, k: int, arc_scores=None, theta=None, *,
         ops.launch_count += 1
     del keep
     return labels, length, log_q, arcs, logz
+
+
+def stripping_pad(sequences: torch.Tensor, pad_id: int) -> torch.Tensor:
+    """``Sampler.stripping_pad`` (``src/modules/samplers.py:162-180``): every row of ``sequences[N, T]`` (int64)
+    left-compacted, symbol id 0 dropped, padded with ``pad_id``; the result is as wide as the reference's (it stops
+    at the first column that is ``pad`` in every row).  Two launches instead of T dependent scatter steps."""
+    if sequences.dim() != 2:
+        raise AssertionError("sequences must be [N, T]")  # samplers.py:163
+    dev = sequences.device
+    if dev.type != "cuda":
+        raise RuntimeError("nfst_b200 kernels need CUDA tensors (no CPU fallback)")
+    lib = _lib.load()
+    seq = sequences.detach().to(torch.int64).contiguous()
+    N, T = seq.shape
+    if N == 0 or T == 0:
+        return seq.clone()
+    out = torch.empty_like(seq)
+    flags = torch.empty(T, dtype=torch.int32, device=dev)
+    width = torch.empty(1, dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.nfst_strip_pad(seq.data_ptr(), N, T, int(pad_id), out.data_ptr(), flags.data_ptr(), width.data_ptr(),
+                                      ops._stream(dev)))
+        ops.launch_count += 2
+    return out[:, : int(width.item())].contiguous()

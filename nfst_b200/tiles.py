@@ -321,7 +321,8 @@ def build(*, lt_s, slot, level_off, level_ptr, n_levels, st_w, st_j, out_ptr, ou
     tab = torch.stack([t_arc0, torch.div(t_off, 16, rounding_mode="floor"), t_arcs | (t_nseg << 16) | (t_next << 24),
                        t_level | (torch.div(t_bytes, 16, rounding_mode="floor") << 16)], dim=1)[t_order]
     tab = torch.where(tab >= 2**31, tab - 2**32, tab).to(torch.int32).contiguous()
-    info = torch.stack([lw_base[:-1], W, ring_total, out_ptr[state_off[:-1]]], dim=1).to(torch.int32).contiguous()
+    info = torch.stack([lw_base[:-1], W, ring_total, out_ptr[state_off[:-1]]], dim=1) * tile_lat.to(torch.int64).unsqueeze(1)
+    info = info.to(torch.int32).contiguous()  # rows of other lattices stay zero
 
     cap_arcs = torch.zeros(B, **i64).scatter_reduce(0, t_lat, t_arcs, reduce="amax")
     cap_bytes = torch.zeros(B, **i64).scatter_reduce(0, t_lat, t_bytes, reduce="amax")
