@@ -626,8 +626,9 @@ def pack_arcs(
     if (tiles_mod.TILES if tiles is None else tiles) and kept.numel():
         slot_lat1 = torch.repeat_interleave(torch.arange(B, device=dev), n_levels + 1)
         lvl_width1 = torch.zeros(B, dtype=torch.int64, device=dev).scatter_reduce(0, slot_lat1, counts, reduce="amax")
-        tile_lat = (S_b0 >= tiles_mod.TILE_MIN_WIDTH * n_levels) & (lvl_width1 + 32 * tiles_mod.NW_MAX <= tiles_mod.RING_MAX)
         tile_nw = tiles_mod.warps_per_lattice(S_b0, n_levels)
+        # the ring must hold the widest level (every warp's share rounded up to whole slices) with room to spare
+        tile_lat = (S_b0 >= tiles_mod.TILE_MIN_WIDTH * n_levels) & (lvl_width1 + 32 * tile_nw + 512 <= tiles_mod.ring_cap_slots(tile_nw))
         sell_lat = sell_lat & ~tile_lat
     col_lat = sell_lat | tile_lat
     # inside a level states are ordered by (in-degree, out-degree): the 32 states a warp reduces then

@@ -38,7 +38,8 @@ TILE_MIN_WIDTH = int(os.environ.get("NFST_TILE_MIN_WIDTH", "32"))
 TILE_ARCS = int(os.environ.get("NFST_TILE_ARCS", "384"))  # target arcs per tile (a multiple of 32)
 TILE_SLICES = int(os.environ.get("NFST_TILE_SLICES", "6"))  # slices per tile, at most
 TILE_WARPS = int(os.environ.get("NFST_TILE_WARPS", "0"))  # 0 = from the level width
-SLICES_PER_WARP = float(os.environ.get("NFST_TILE_SLICES_PER_WARP", "4"))
+SLICES_PER_WARP = float(os.environ.get("NFST_TILE_SLICES_PER_WARP", "2.5"))
+TILE_BLOCK_ARCS = int(os.environ.get("NFST_TILE_BLOCK_ARCS", "1024"))  # arcs in the tiles that a block's warps hold at a time
 KU = 8  # columns of a slice the kernels hold in registers
 TAILMAX = 32  # states with more arcs than this are heavy
 RING_MAX = int(os.environ.get("NFST_TILE_RING_MAX", "49152"))  # ring slots (float32: 192 KB)
@@ -53,13 +54,26 @@ def _excl_cumsum(x: torch.Tensor) -> torch.Tensor:
     return out
 
 
+# shared memory of one block: the DP ring (4 bytes per slot; 8 with float64 state) and two stages per warp
+SMEM_BUDGET = int(os.environ.get("NFST_TILE_SMEM_BUDGET", str(216 * 1024)))
+STAGE_EST = 3 * 1024  # bytes of one stage (stream part + one staged array), roughly
+
+
+def ring_cap_slots(nw: torch.Tensor) -> torch.Tensor:
+    """Largest DP ring (slots, far table included) that fits beside the stages of an nw-warp block."""
+    return torch.clamp(torch.div(SMEM_BUDGET - 2 * STAGE_EST * nw, 4, rounding_mode="floor"), min=64, max=min(RING_MAX, 65000))
+
+
 def warps_per_lattice(states: torch.Tensor, levels: torch.Tensor) -> torch.Tensor:
     """Warps per block of a tile-stream lattice (a power of two, 1..32): about SLICES_PER_WARP slices per warp
-    and level."""
+    and level -- fewer where the ring of a very wide lattice (its arcs reach across some eight levels) needs the
+    shared memory the stages of more warps would take."""
     if TILE_WARPS:
         return torch.full_like(states, TILE_WARPS)
-    slices = states.to(torch.float64) / torch.clamp(levels, min=1).to(torch.float64) / 32.0
-    lg = torch.floor(torch.log2(torch.clamp(slices / SLICES_PER_WARP, min=1.0))).to(torch.int64)
+    width = states.to(torch.float64) / torch.clamp(levels, min=1).to(torch.float64)
+    lg = torch.floor(torch.log2(torch.clamp(width / 32.0 / SLICES_PER_WARP, min=1.0))).to(torch.int64)
+    room = torch.clamp((SMEM_BUDGET - 4 * 8 * width) / (2 * STAGE_EST), min=1.0)
+    lg = torch.minimum(lg, torch.floor(torch.log2(room)).to(torch.int64))
     return torch.ones_like(states) << torch.clamp(lg, 0, 5)
 
 
@@ -67,7 +81,7 @@ def tile_arcs_for(nw: torch.Tensor) -> torch.Tensor:
     """Target arcs per tile for lattices dealt to ``nw`` warps: TILE_ARCS for narrow blocks (few warps per SM: each
     bulk copy must be a kilobyte or two to keep HBM busy), smaller for wide blocks (many warps in flight, and
     nw x stages x tile bytes must fit shared memory next to the ring); a multiple of 32, at least 96."""
-    t = torch.clamp(torch.div(2 * TILE_ARCS, torch.clamp(nw, min=1), rounding_mode="floor"), min=min(96, TILE_ARCS), max=TILE_ARCS)
+    t = torch.clamp(torch.div(TILE_BLOCK_ARCS, torch.clamp(nw, min=1), rounding_mode="floor"), min=min(96, TILE_ARCS), max=TILE_ARCS)
     return torch.div(t, 32, rounding_mode="floor") * 32
 
 
@@ -161,7 +175,8 @@ def build(*, lt_s, slot, level_off, level_ptr, n_levels, st_w, st_j, out_ptr, ou
     od = sl_ord[slice_of_state[a_dst]]
     need = od - slot_first_ord[slot[a_src]] + 1  # slices the ring must span for this arc
     need = torch.where(a_last, torch.zeros_like(need), need)
-    if bool((lvl_slices_max[tile_lat] * 32 > RING_MAX).any()):
+    ring_cap = torch.div(ring_cap_slots(tile_nw), 32, rounding_mode="floor") - 8  # slices; 256 slots stay free for the far table
+    if bool((lvl_slices_max[tile_lat] > ring_cap[tile_lat]).any()):
         raise ValueError("a level is wider than the largest DP ring; raise NFST_TILE_RING_MAX or disable tiles")
     # Ring size per lattice.  A destination that has left the ring when its source is processed is kept in a
     # small FAR TABLE behind the ring instead (slots W+1, W+2, ...: written once, never recycled), so the arc
@@ -173,9 +188,8 @@ def build(*, lt_s, slot, level_off, level_ptr, n_levels, st_w, st_j, out_ptr, ou
     cand = torch.arange(nmax + 1, device=dev).unsqueeze(0)
     cost = 32 * cand + far_arcs_if
     floor_n = torch.clamp(lvl_slices_max, min=1).unsqueeze(1)
-    cost = torch.where((cand >= floor_n) & (cand <= RING_MAX // 32), cost, torch.full_like(cost, 2**40))
-    ring_slices = torch.maximum(torch.argmin(cost, 1), floor_n.squeeze(1))
-    ring_slices = torch.clamp(ring_slices, max=RING_MAX // 32)
+    cost = torch.where((cand >= floor_n) & (cand <= ring_cap.unsqueeze(1)), cost, torch.full_like(cost, 2**40))
+    ring_slices = torch.minimum(torch.maximum(torch.argmin(cost, 1), floor_n.squeeze(1)), torch.clamp(ring_cap, min=1))
     W = ring_slices * 32  # [B]
     Wa = W[a_lat]
     resident = (~a_last) & (need <= ring_slices[a_lat])
@@ -220,17 +234,31 @@ def build(*, lt_s, slot, level_off, level_ptr, n_levels, st_w, st_j, out_ptr, ou
 
     # ---- tiles: consecutive segments of one (level, warp); heavy pieces stand alone ----
     g = (sl_slot * NW_MAX + sl_w)[seg_slice]
-    cum = _excl_cumsum(seg_arcs)[:-1]
     g_new = torch.ones(NSEG, dtype=torch.bool, device=dev)
     g_new[1:] = g[1:] != g[:-1]
     g_id = torch.cumsum(g_new.to(torch.int64), 0) - 1
-    g_cum0 = cum[g_new][g_id]
-    tbin = torch.div(cum - g_cum0, T, rounding_mode="floor")
-    run_new = g_new.clone()
-    run_new[1:] |= (tbin[1:] != tbin[:-1]) | seg_heavy[1:] | seg_heavy[:-1]
-    run_id = torch.cumsum(run_new.to(torch.int64), 0) - 1
-    idx_in_run = torch.arange(NSEG, device=dev) - torch.nonzero(run_new).squeeze(1)[run_id]
-    tile_new = run_new | (idx_in_run % TILE_SLICES == 0)
+    g_first = torch.nonzero(g_new).squeeze(1)
+    idx_in_g = torch.arange(NSEG, device=dev) - g_first[g_id]
+    # greedy, in segment order: a segment joins the open tile unless that would exceed T arcs or TILE_SLICES
+    # segments (so a tile holds at most max(T, its largest segment) arcs); heavy pieces stand alone.  One
+    # vectorised step per position in the group (a group = what one warp does in one level: a handful of segments).
+    NG = int(g_first.numel())
+    acc = torch.zeros(NG, **i64)
+    cnt = torch.zeros(NG, **i64)
+    prev_heavy = torch.zeros(NG, dtype=torch.bool, device=dev)
+    tile_new = torch.zeros(NSEG, dtype=torch.bool, device=dev)
+    order_g = torch.argsort(idx_in_g, stable=True)  # segments by position in their group
+    pos_counts = torch.bincount(idx_in_g)
+    pos_off = _excl_cumsum(pos_counts)
+    for j in range(int(pos_counts.numel())):
+        sel = order_g[int(pos_off[j]): int(pos_off[j + 1])]  # the j-th segment of every group that has one
+        gi = g_id[sel]
+        a, hv, Tj = seg_arcs[sel], seg_heavy[sel], T[sel]
+        start = (cnt[gi] == 0) | hv | prev_heavy[gi] | (acc[gi] + a > Tj) | (cnt[gi] >= TILE_SLICES)
+        tile_new[sel] = start
+        acc[gi] = torch.where(start, a, acc[gi] + a)
+        cnt[gi] = torch.where(start, torch.ones_like(a), cnt[gi] + 1)
+        prev_heavy[gi] = hv
     tile_of_seg = torch.cumsum(tile_new.to(torch.int64), 0) - 1
     NT = int(tile_of_seg[-1]) + 1
     t_first_seg = torch.nonzero(tile_new).squeeze(1)

@@ -182,7 +182,7 @@ def test_tile_mixed_batch_and_lattice_backward_outputs():
     packs, scores = zip(*[ab.to(DEV).pack() for ab in parts])
     p = concat_packed(list(packs))
     sc = torch.cat(scores)
-    assert {g.tiles for g in p.groups} == {True, False} and len({g.block_threads for g in p.groups if g.tiles}) == 2
+    assert {g.tiles for g in p.groups} == {True, False}
     logz, alpha, beta, post = nb.lattice_forward_backward(p, arc_scores=sc)
     off_a = off_b = 0
     for ab, pk in zip(parts, packs):

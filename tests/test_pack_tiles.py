@@ -77,7 +77,7 @@ def test_tile_layout_replays_to_the_oracle(arcs, levels, seed, warps, monkeypatc
 
 def test_tile_small_ring_keeps_far_destinations_in_the_far_table(monkeypatch):
     ab = synth.random_dag_batch(2, 5000, levels=20, seed=5)
-    monkeypatch.setattr(T, "RING_MAX", 32 * 12)  # a ring of 12 slices: wider than any level, shorter than the longest arcs
+    monkeypatch.setattr(T, "RING_MAX", 32 * 20)  # a ring of 12 slices (+ room for the far table): wider than any level, shorter than the longest arcs
     monkeypatch.setattr(T, "NW_MAX", 1)
     monkeypatch.setattr(T, "TILE_WARPS", 1)
     p, w = ab.pack(tiles=True)
@@ -135,6 +135,8 @@ def test_tiles_are_per_lattice_and_survive_concat(monkeypatch):
 def test_tile_default_thresholds():
     assert not synth.transliteration_batch(2, seed=3).pack()[0].has_tiles  # the reference's own narrow lattices
     p, _ = synth.random_dag_batch(1, 40_000, levels=16, seed=1).pack()  # 625 states per level: 19 slices
+    assert p.has_tiles and p.groups[0].block_threads == 128
+    p, _ = synth.random_dag_batch(1, 100_000, levels=64, seed=1).pack()  # the bench lattices: 13 slices per level
     assert p.has_tiles and p.groups[0].block_threads == 128
     p, _ = synth.random_dag_batch(1, 10_000, levels=64, seed=1).pack()  # 40 states per level
     assert p.has_tiles and p.groups[0].block_threads == 32
