@@ -626,9 +626,22 @@ def pack_arcs(
     if (tiles_mod.TILES if tiles is None else tiles) and kept.numel():
         slot_lat1 = torch.repeat_interleave(torch.arange(B, device=dev), n_levels + 1)
         lvl_width1 = torch.zeros(B, dtype=torch.int64, device=dev).scatter_reduce(0, slot_lat1, counts, reduce="amax")
-        tile_nw = tiles_mod.warps_per_lattice(S_b0, n_levels)
-        # the ring must hold the widest level (every warp's share rounded up to whole slices) with room to spare
-        tile_lat = (S_b0 >= tiles_mod.TILE_MIN_WIDTH * n_levels) & (lvl_width1 + 32 * tile_nw + 512 <= tiles_mod.ring_cap_slots(tile_nw))
+        # how far the arcs reach, in states (arcs into the last level read a constant): sizes the DP ring, and
+        # with it the number of warps whose stages fit beside it
+        slot_of1 = torch.zeros(S0, dtype=torch.int64, device=dev)
+        slot_of1[kept] = slot_kept
+        inner1 = live & (level[gdst] < n_levels[arc_lattice] - 1)
+        la1 = arc_lattice[inner1]
+        sd1, ss1 = slot_of1[gdst[inner1]], slot_of1[gsrc[inner1]]
+        span1 = level_ptr[sd1] + counts[sd1] - level_ptr[ss1]
+        tile_nw = tiles_mod.warps_per_lattice(S_b0, n_levels, tiles_mod.span_quantile(la1, span1, B))
+        cap1 = tiles_mod.ring_cap_slots(tile_nw)
+        # slices are per (level, warp): every level an arc crosses may add a partial slice per warp
+        est1 = span1 + 32 * tile_nw[la1] * (sd1 - ss1 + 1)
+        far1 = torch.bincount(la1[est1 > (cap1[la1] * 3) // 4], minlength=B)
+        # the ring must hold the widest level (every warp's share rounded up to whole slices) with room to spare, and
+        # the destinations that outlive it must fit the far table
+        tile_lat = (S_b0 >= tiles_mod.TILE_MIN_WIDTH * n_levels) & (lvl_width1 + 32 * tile_nw + 512 <= cap1) & (far1 <= cap1 // 8)
         sell_lat = sell_lat & ~tile_lat
     col_lat = sell_lat | tile_lat
     # inside a level states are ordered by (in-degree, out-degree): the 32 states a warp reduces then

@@ -44,6 +44,7 @@ KU = 8  # columns of a slice the kernels hold in registers
 TAILMAX = 32  # states with more arcs than this are heavy
 RING_MAX = int(os.environ.get("NFST_TILE_RING_MAX", "49152"))  # ring slots (float32: 192 KB)
 NW_MAX = 32
+FORCE_RING_SLICES = int(os.environ.get("NFST_TILE_FORCE_RING_SLICES", "0"))  # tests: a ring this short (more far destinations)
 
 FLAG_FAR_IN, FLAG_HEAVY, FLAG_HEAVY_FIRST, FLAG_HEAVY_LAST = 2, 4, 8, 16
 
@@ -64,17 +65,26 @@ def ring_cap_slots(nw: torch.Tensor) -> torch.Tensor:
     return torch.clamp(torch.div(SMEM_BUDGET - 2 * STAGE_EST * nw, 4, rounding_mode="floor"), min=64, max=min(RING_MAX, 65000))
 
 
-def warps_per_lattice(states: torch.Tensor, levels: torch.Tensor) -> torch.Tensor:
+def warps_per_lattice(states: torch.Tensor, levels: torch.Tensor, span: torch.Tensor = None) -> torch.Tensor:
     """Warps per block of a tile-stream lattice (a power of two, 1..32): about SLICES_PER_WARP slices per warp
-    and level -- fewer where the ring of a very wide lattice (its arcs reach across some eight levels) needs the
-    shared memory the stages of more warps would take."""
+    and level -- fewer where the DP ring needs the shared memory the stages of more warps would take.  ``span``:
+    how many states nearly all arcs of the lattice reach across (default: eight levels)."""
     if TILE_WARPS:
         return torch.full_like(states, TILE_WARPS)
     width = states.to(torch.float64) / torch.clamp(levels, min=1).to(torch.float64)
     lg = torch.floor(torch.log2(torch.clamp(width / 32.0 / SLICES_PER_WARP, min=1.0))).to(torch.int64)
-    room = torch.clamp((SMEM_BUDGET - 4 * 8 * width) / (2 * STAGE_EST), min=1.0)
+    ring = 8 * width if span is None else 1.5 * span.to(torch.float64)
+    room = torch.clamp((SMEM_BUDGET - 4 * ring) / (2 * STAGE_EST), min=1.0)
     lg = torch.minimum(lg, torch.floor(torch.log2(room)).to(torch.int64))
     return torch.ones_like(states) << torch.clamp(lg, 0, 5)
+
+
+def span_quantile(lat: torch.Tensor, span: torch.Tensor, n_lattices: int, q: float = 0.995) -> torch.Tensor:
+    """Per-lattice q-quantile of the arcs' reach (in states), from a histogram of quarter octaves (at most 19 % high)."""
+    bucket = torch.clamp(torch.ceil(4.0 * torch.log2(torch.clamp(span, min=1).to(torch.float64))).to(torch.int64), 0, 127)
+    cum = torch.cumsum(torch.bincount(lat * 128 + bucket, minlength=n_lattices * 128).view(n_lattices, 128), 1)
+    need = torch.ceil(cum[:, -1:].to(torch.float64) * q).to(torch.int64)
+    return torch.pow(2.0, (cum < need).sum(1).to(torch.float64) / 4.0).to(torch.int64)
 
 
 def tile_arcs_for(nw: torch.Tensor) -> torch.Tensor:
@@ -175,9 +185,10 @@ def build(*, lt_s, slot, level_off, level_ptr, n_levels, st_w, st_j, out_ptr, ou
     od = sl_ord[slice_of_state[a_dst]]
     need = od - slot_first_ord[slot[a_src]] + 1  # slices the ring must span for this arc
     need = torch.where(a_last, torch.zeros_like(need), need)
-    ring_cap = torch.div(ring_cap_slots(tile_nw), 32, rounding_mode="floor") - 8  # slices; 256 slots stay free for the far table
+    cap_slots = ring_cap_slots(tile_nw)  # ring + constant slot + far table, per lattice
+    ring_cap = torch.div(cap_slots, 32, rounding_mode="floor") - 1  # slices
     if bool((lvl_slices_max[tile_lat] > ring_cap[tile_lat]).any()):
-        raise ValueError("a level is wider than the largest DP ring; raise NFST_TILE_RING_MAX or disable tiles")
+        raise ValueError("a level is wider than the largest DP ring; pack with tiles=False or fewer warps (NFST_TILE_WARPS)")
     # Ring size per lattice.  A destination that has left the ring when its source is processed is kept in a
     # small FAR TABLE behind the ring instead (slots W+1, W+2, ...: written once, never recycled), so the arc
     # reads it like any other slot.  n slices of ring cost 32 n slots plus one table slot per far destination:
@@ -190,6 +201,12 @@ def build(*, lt_s, slot, level_off, level_ptr, n_levels, st_w, st_j, out_ptr, ou
     floor_n = torch.clamp(lvl_slices_max, min=1).unsqueeze(1)
     cost = torch.where((cand >= floor_n) & (cand <= ring_cap.unsqueeze(1)), cost, torch.full_like(cost, 2**40))
     ring_slices = torch.minimum(torch.maximum(torch.argmin(cost, 1), floor_n.squeeze(1)), torch.clamp(ring_cap, min=1))
+    if FORCE_RING_SLICES:
+        ring_slices = torch.maximum(torch.clamp(ring_slices, max=FORCE_RING_SLICES), floor_n.squeeze(1))
+    best = torch.gather(cost, 1, ring_slices.unsqueeze(1)).squeeze(1)
+    if bool((tile_lat & (best + 1 > cap_slots)).any()):
+        raise ValueError("DP ring and far table of a lattice exceed shared memory (its arcs reach too far for its width); "
+                         "pack with tiles=False or fewer warps (NFST_TILE_WARPS)")
     W = ring_slices * 32  # [B]
     Wa = W[a_lat]
     resident = (~a_last) & (need <= ring_slices[a_lat])

@@ -77,8 +77,7 @@ def test_tile_layout_replays_to_the_oracle(arcs, levels, seed, warps, monkeypatc
 
 def test_tile_small_ring_keeps_far_destinations_in_the_far_table(monkeypatch):
     ab = synth.random_dag_batch(2, 5000, levels=20, seed=5)
-    monkeypatch.setattr(T, "RING_MAX", 32 * 20)  # a ring of 12 slices (+ room for the far table): wider than any level, shorter than the longest arcs
-    monkeypatch.setattr(T, "NW_MAX", 1)
+    monkeypatch.setattr(T, "FORCE_RING_SLICES", 12)  # wider than any level, shorter than most arcs
     monkeypatch.setattr(T, "TILE_WARPS", 1)
     p, w = ab.pack(tiles=True)
     assert p.has_tiles and any(g.tile_far for g in p.groups)
