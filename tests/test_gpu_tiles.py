@@ -265,7 +265,7 @@ def test_single_state_consumers_read_column_layouts(layout, monkeypatch):
     assert torch.equal(pcol.src_out[oa].long(), src)
     lab = pcol.label_out[oa]
     same_state = src[1:] == src[:-1]
-    assert bool((lab[1:][same_state] > lab[:-1][same_state]).all())
+    assert bool((lab[1:][same_state] >= lab[:-1][same_state]).all())  # random DAGs repeat labels
     # states are numbered differently in the two packs: compare through original ids
     g = torch.Generator(device=DEV).manual_seed(5)
     k = 4
@@ -281,10 +281,16 @@ def test_single_state_consumers_read_column_layouts(layout, monkeypatch):
     # one walk step from the start states with a random prefix, sampling and scoring
     V = pcol.vocab
     prefix = torch.randn(N, V, device=DEV, generator=g)
-    ra = nb.ops.lattice_backward(pcol, sccol, want_beta=True)
     rb = nb.ops.lattice_backward(pcsr, sccsr, want_beta=True)
-    wa = nb.LatticeWalker(pcol, k, ra["beta"].float().exp(), pad_id=3, faithful=False)
-    wb = nb.LatticeWalker(pcsr, k, rb["beta"].float().exp(), pad_id=3, faithful=False)
+    # the same look-ahead values for both walks (real-space beta amplifies the kernels' rounding differences): the CSR
+    # pack's beta carried over to the column-major pack's state numbering through the original state ids
+    ia = torch.argsort(pcol.state_off[:-1].long().repeat_interleave((pcol.state_off[1:] - pcol.state_off[:-1]).long()) * 10**7 + pcol.orig_state.long())
+    ib = torch.argsort(pcsr.state_off[:-1].long().repeat_interleave((pcsr.state_off[1:] - pcsr.state_off[:-1]).long()) * 10**7 + pcsr.orig_state.long())
+    beta_b = rb["beta"].float().exp()
+    beta_a = torch.empty_like(beta_b)
+    beta_a[ia] = beta_b[ib]
+    wa = nb.LatticeWalker(pcol, k, beta_a, pad_id=3, faithful=False)
+    wb = nb.LatticeWalker(pcsr, k, beta_b, pad_id=3, faithful=False)
     uu = torch.rand(N, device=DEV, generator=g)
     for _ in range(3):
         sa, pa, za = wa.step(prefix, uniform=uu)
@@ -298,8 +304,6 @@ def test_single_state_consumers_read_column_layouts(layout, monkeypatch):
     W = torch.randn(H, device=DEV, generator=g) * 0.3
     lba, bha = nb.lattice_beta_hat(pcol, proj, Wh, W)
     lbb, bhb = nb.lattice_beta_hat(pcsr, proj, Wh, W)
-    ia = torch.argsort(pcol.state_off[:-1].long().repeat_interleave((pcol.state_off[1:] - pcol.state_off[:-1]).long()) * 10**7 + pcol.orig_state.long())
-    ib = torch.argsort(pcsr.state_off[:-1].long().repeat_interleave((pcsr.state_off[1:] - pcsr.state_off[:-1]).long()) * 10**7 + pcsr.orig_state.long())
     assert torch.allclose(lba[ia], lbb[ib], rtol=1e-5, atol=1e-5) and torch.allclose(bha[ia], bhb[ib], rtol=0, atol=1e-5)
 
 
