@@ -46,7 +46,7 @@ def parse_args():
     ap.add_argument("--levels", type=int, default=64)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--sweep", action="store_true", help="also time the other sweep points (N=1 only)")
+    ap.add_argument("--no-sweep", action="store_true", help="skip the other points of the config-4 sweep (N=1 only)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     return ap.parse_args()
 
@@ -513,9 +513,31 @@ def main():
     if not a.no_cpu and world == 1:  # CPU baseline: rank 0 at N=1 only
         cb, _, _ = cpu_baseline(a, a.cpu_seconds)
         out["cpu_baseline"] = cb
-    if a.sweep and world == 1 and a.workload == "dag":
+    # ---- Viterbi + backtrace on the same batch (BASELINE metric's second half; bit-exact paths) ----
+    if world == 1:
+        for _ in range(3):
+            nb.lattice_viterbi(packed, arc_scores=scores)
+        torch.cuda.synchronize()
+        v0, v1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        v0.record()
+        for _ in range(a.steps):
+            vit = nb.lattice_viterbi(packed, arc_scores=scores)
+        v1.record()
+        torch.cuda.synchronize()
+        vms = v0.elapsed_time(v1) / a.steps
+        vbytes = packed.algorithmic_bytes_viterbi(int(vit[1][-1]))
+        out["viterbi"] = {"arcs_per_s": A / (vms * 1e-3), "ms_per_step": vms, "algorithmic_bytes": vbytes,
+                          "gbs": vbytes / (vms * 1e-3) / 1e9, "frac": vbytes / (vms * 1e-3) / 1e9 / peak,
+                          "note": "tropical pull pass + backtrace + ragged path read-out (one host read of the total length)"}
+        del vit
+    if not a.no_sweep and world == 1 and a.workload == "dag":
         sweep = []
         for arcs in (10_000, 30_000, 100_000, 300_000, 1_000_000):
+            if arcs == a.arcs:  # the bench point itself
+                sweep.append({"arcs_per_lattice": arcs, "arcs": A, "ms_per_step": ms_step,
+                              "execution": out["config"]["execution"].split(" (")[0], "arcs_per_s": value,
+                              "gbs": (20 * A + 20 * S) / (ms_step * 1e-3) / 1e9, "frac": (20 * A + 20 * S) / (ms_step * 1e-3) / 1e9 / peak})
+                continue
             del packed, scores
             torch.cuda.empty_cache()
             packed, scores = build_packed(a, dev, arcs=arcs)
@@ -534,7 +556,8 @@ def main():
                           "execution": "tile-stream" if all(g.tiles for g in packed.groups) else
                           "sliced-column" if all(g.sell for g in packed.groups) else "CSR/mixed",
                           "arcs_per_s": packed.n_arcs / (ms * 1e-3),
-                          "gbs": (20 * packed.n_arcs + 20 * packed.n_states) / (ms * 1e-3) / 1e9})
+                          "gbs": (20 * packed.n_arcs + 20 * packed.n_states) / (ms * 1e-3) / 1e9,
+                          "frac": (20 * packed.n_arcs + 20 * packed.n_states) / (ms * 1e-3) / 1e9 / peak})
         out["sweep"] = sweep
     print(json.dumps(out))
     if world > 1:

@@ -48,8 +48,8 @@ def val(r, name):
 
 
 bench = json.loads(open(a.bench).read().strip().splitlines()[-1])
-out = {"source": f"ncu --set full --clock-control none --import-source on -k regex:sell_|nfst_ -s 6 -c 2 python bench.py "
-                 f"--steps 3 --warmup 3 --no-e2e --no-cpu ({tag})",
+out = {"source": f"ncu --set full --clock-control none --import-source on -k regex:tile_pull|tile_flow -s 6 -c 2 python bench.py "
+                 f"--steps 3 --warmup 3 --no-e2e --no-cpu --no-sweep ({tag})",
        "workload_arcs_per_gpu": bench["config"]["arcs_per_gpu"], "kernels": {}}
 for r in rows[2:]:
     key = short(r[hdr.index("Kernel Name")])
@@ -78,8 +78,8 @@ for r in lrows[st:]:
     v = float(r[h.index("Metric Value")].replace(",", "")) * {"ns": 1e-3, "us": 1, "ms": 1e3}.get(r[h.index("Metric Unit")], 1)
     agg.setdefault(n, []).append(v)
 tot = sum(sum(v) for v in agg.values())
-L = ["ncu launch list: ncu --metrics gpu__time_duration.sum --clock-control none -k regex:sell_|nfst_ -c 12 python bench.py "
-     "--steps 3 --warmup 3 --no-e2e --no-cpu",
+L = ["ncu launch list: ncu --metrics gpu__time_duration.sum --clock-control none -k regex:tile_|sell_|nfst_ -c 12 python bench.py "
+     "--steps 3 --warmup 3 --no-e2e --no-cpu --no-sweep",
      "(a bench step launches exactly these kernels; per-launch times under ncu are cold-cache and serialised: compare SHARES)", ""]
 for k, v in agg.items():
     L.append(f"{k:24s} launches {len(v):3d}  mean {sum(v) / len(v):8.1f} us  share of step {100 * sum(v) / tot:5.1f}%")
