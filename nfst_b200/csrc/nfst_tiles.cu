@@ -825,13 +825,17 @@ Geometry pick_geometry(const nfst_launch_t* launch, int vocab, int ring_elem_byt
   const int by_threads = 2048 / launch->block_threads;
   if (want > by_threads) want = by_threads;
   if (want > 32) want = 32;
+  // ... but no more blocks than fit an SM with the shallowest ring of stages (a large DP ring: one or two blocks)
+  const Geometry g2 = geometry(launch, vocab, ring_elem_bytes, n_arrays, table, 2);
+  const int fit = static_cast<int>((227u * 1024u) / (g2.smem + 1024u));
+  if (want > fit) want = fit;
   if (want < 1) want = 1;
-  const size_t budget = (228u * 1024u) / want - 1024u;
+  const size_t budget = (227u * 1024u) / want - 1024u;
   for (int s = 4; s > 2; --s) {
     Geometry g = geometry(launch, vocab, ring_elem_bytes, n_arrays, table, s);
     if (g.smem <= budget) return g;
   }
-  return geometry(launch, vocab, ring_elem_bytes, n_arrays, table, 2);
+  return g2;
 }
 
 bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
@@ -860,13 +864,15 @@ int check_launch(const nfst_packed_lattices_t* lat, const nfst_launch_t* launch)
 }
 
 // register budgets: blocks of up to 64 threads may use 128 registers, 128-thread blocks 72 (7 blocks per SM),
-// 256-thread blocks 64 (4 per SM), larger blocks 64
-#define TILE_BY_BLOCK(CALL)                         \
-  do {                                              \
-    if (launch->block_threads <= 64) CALL(64, 7);   \
+// 256-thread blocks 80 (3 per SM; at 64 the log pull pass spills), 512-thread blocks 128 (one per SM: lattices
+// whose DP ring fills most of the shared memory), 1024-thread blocks 64
+#define TILE_BY_BLOCK(CALL)                              \
+  do {                                                   \
+    if (launch->block_threads <= 64) CALL(64, 7);        \
     else if (launch->block_threads <= 128) CALL(128, 7); \
-    else if (launch->block_threads <= 256) CALL(256, 4); \
-    else CALL(1024, 1);                             \
+    else if (launch->block_threads <= 256) CALL(256, 3); \
+    else if (launch->block_threads <= 512) CALL(512, 1); \
+    else CALL(1024, 1);                                  \
   } while (0)
 
 template <bool TROP, typename OT>

@@ -38,7 +38,6 @@ TILE_MIN_WIDTH = int(os.environ.get("NFST_TILE_MIN_WIDTH", "32"))
 TILE_ARCS = int(os.environ.get("NFST_TILE_ARCS", "384"))  # target arcs per tile (a multiple of 32)
 TILE_SLICES = int(os.environ.get("NFST_TILE_SLICES", "6"))  # slices per tile, at most
 TILE_WARPS = int(os.environ.get("NFST_TILE_WARPS", "0"))  # 0 = from the level width
-SLICES_PER_WARP = float(os.environ.get("NFST_TILE_SLICES_PER_WARP", "2.5"))
 TILE_BLOCK_ARCS = int(os.environ.get("NFST_TILE_BLOCK_ARCS", "1024"))  # arcs in the tiles that a block's warps hold at a time
 KU = 8  # columns of a slice the kernels hold in registers
 TAILMAX = 32  # states with more arcs than this are heavy
@@ -55,28 +54,47 @@ def _excl_cumsum(x: torch.Tensor) -> torch.Tensor:
     return out
 
 
-# shared memory of one block: the DP ring (4 bytes per slot; 8 with float64 state) and two stages per warp
+# shared memory of one block: the DP ring (4 bytes per slot; 8 with float64 state) and at least two stages per warp
 SMEM_BUDGET = int(os.environ.get("NFST_TILE_SMEM_BUDGET", str(216 * 1024)))
-STAGE_EST = 3 * 1024  # bytes of one stage (stream part + one staged array), roughly
+NW_BASE = int(os.environ.get("NFST_TILE_WARPS_BASE", "4"))  # warps of a block when several blocks fit an SM
+MIN_SM_WARPS = int(os.environ.get("NFST_TILE_MIN_SM_WARPS", "12"))  # wanted resident warps per SM (blocks x warps)
+
+
+def stage_est(nw: torch.Tensor) -> torch.Tensor:
+    """Bytes of one stage of an nw-warp block, roughly: the stream part of a tile (headers + 2 bytes per arc) and one
+    staged 4-byte array (plus its alignment and over-read slack)."""
+    return 7 * tile_arcs_for(nw) + 512
 
 
 def ring_cap_slots(nw: torch.Tensor) -> torch.Tensor:
     """Largest DP ring (slots, far table included) that fits beside the stages of an nw-warp block."""
-    return torch.clamp(torch.div(SMEM_BUDGET - 2 * STAGE_EST * nw, 4, rounding_mode="floor"), min=64, max=min(RING_MAX, 65000))
+    return torch.clamp(torch.div(SMEM_BUDGET - 2 * stage_est(nw) * nw, 4, rounding_mode="floor"), min=64, max=min(RING_MAX, 65000))
 
 
 def warps_per_lattice(states: torch.Tensor, levels: torch.Tensor, span: torch.Tensor = None) -> torch.Tensor:
-    """Warps per block of a tile-stream lattice (a power of two, 1..32): about SLICES_PER_WARP slices per warp
-    and level -- fewer where the DP ring needs the shared memory the stages of more warps would take.  ``span``:
-    how many states nearly all arcs of the lattice reach across (default: eight levels)."""
+    """Warps per block of a tile-stream lattice (a power of two, 1..32).  Measured on B200 (tools/tile_tune.py): four
+    warps per lattice win whenever several blocks fit an SM -- from 4 to 40 slices per level; what keeps HBM busy is
+    the depth of the warps' bulk-copy rings, not the warp count -- so the default is NW_BASE, fewer only where a
+    level has fewer slices than that.  A lattice whose DP ring leaves room for just one or two blocks per SM gets
+    more warps (with smaller tiles: tile_arcs_for) until MIN_SM_WARPS warps are resident.  ``span``: how many states
+    nearly all arcs of the lattice reach across (default: eight levels)."""
     if TILE_WARPS:
         return torch.full_like(states, TILE_WARPS)
     width = states.to(torch.float64) / torch.clamp(levels, min=1).to(torch.float64)
-    lg = torch.floor(torch.log2(torch.clamp(width / 32.0 / SLICES_PER_WARP, min=1.0))).to(torch.int64)
-    ring = 8 * width if span is None else 1.5 * span.to(torch.float64)
-    room = torch.clamp((SMEM_BUDGET - 4 * ring) / (2 * STAGE_EST), min=1.0)
-    lg = torch.minimum(lg, torch.floor(torch.log2(room)).to(torch.int64))
-    return torch.ones_like(states) << torch.clamp(lg, 0, 5)
+    slices = torch.clamp(torch.ceil(width / 32.0), min=1.0)
+    base = torch.ones_like(states) << torch.clamp(torch.ceil(torch.log2(slices)).to(torch.int64), 0, int(NW_BASE).bit_length() - 1)
+    ring = 4.0 * (8 * width if span is None else 1.5 * span.to(torch.float64))  # bytes
+    best = base
+    done = torch.zeros_like(states, dtype=torch.bool)
+    for lg in range(0, 6):
+        nw = torch.full_like(states, 1 << lg)
+        smem = ring + (2 * stage_est(nw) * nw).to(torch.float64)
+        blocks = torch.clamp(torch.floor(SMEM_BUDGET / smem), max=float(2048 // (32 << lg)))
+        blocks = torch.minimum(blocks, torch.full_like(blocks, 7.0))
+        ok = (nw >= base) & (blocks >= 1) & ~done
+        best = torch.where(ok, nw, best)  # the largest block that still fits, until one meets the target
+        done = done | (ok & (blocks * nw.to(torch.float64) >= MIN_SM_WARPS))
+    return best
 
 
 def span_quantile(lat: torch.Tensor, span: torch.Tensor, n_lattices: int, q: float = 0.995) -> torch.Tensor:
@@ -90,8 +108,10 @@ def span_quantile(lat: torch.Tensor, span: torch.Tensor, n_lattices: int, q: flo
 def tile_arcs_for(nw: torch.Tensor) -> torch.Tensor:
     """Target arcs per tile for lattices dealt to ``nw`` warps: TILE_ARCS for narrow blocks (few warps per SM: each
     bulk copy must be a kilobyte or two to keep HBM busy), smaller for wide blocks (many warps in flight, and
-    nw x stages x tile bytes must fit shared memory next to the ring); a multiple of 32, at least 96."""
-    t = torch.clamp(torch.div(TILE_BLOCK_ARCS, torch.clamp(nw, min=1), rounding_mode="floor"), min=min(96, TILE_ARCS), max=TILE_ARCS)
+    nw x stages x tile bytes must fit shared memory next to the ring); a multiple of 32, at least 96.  Blocks of
+    8 warps and more exist for lattices with a large DP ring (one block per SM): they get twice the budget."""
+    budget = torch.where(nw >= 8, torch.full_like(nw, 2 * TILE_BLOCK_ARCS), torch.full_like(nw, TILE_BLOCK_ARCS))
+    t = torch.clamp(torch.div(budget, torch.clamp(nw, min=1), rounding_mode="floor"), min=min(96, TILE_ARCS), max=TILE_ARCS)
     return torch.div(t, 32, rounding_mode="floor") * 32
 
 

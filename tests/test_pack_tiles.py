@@ -137,5 +137,9 @@ def test_tile_default_thresholds():
     assert p.has_tiles and p.groups[0].block_threads == 128
     p, _ = synth.random_dag_batch(1, 100_000, levels=64, seed=1).pack()  # the bench lattices: 13 slices per level
     assert p.has_tiles and p.groups[0].block_threads == 128
-    p, _ = synth.random_dag_batch(1, 10_000, levels=64, seed=1).pack()  # 40 states per level
-    assert p.has_tiles and p.groups[0].block_threads == 32
+    p, _ = synth.random_dag_batch(1, 10_000, levels=64, seed=1).pack()  # 40 states per level: two slices
+    assert p.has_tiles and p.groups[0].block_threads == 64
+    p, _ = synth.random_dag_batch(1, 300_000, levels=64, seed=1).pack()  # 37 slices per level, ring of 35 KB: still 4 warps
+    assert p.has_tiles and p.groups[0].block_threads == 128
+    p, _ = synth.random_dag_batch(1, 1_000_000, levels=64, seed=1).pack()  # ring > 100 KB: one block per SM, 16 warps
+    assert p.has_tiles and p.groups[0].block_threads == 512
