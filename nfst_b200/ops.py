@@ -37,8 +37,10 @@ def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
 # per-state-vector shared-memory window (bytes); tests shrink it to exercise the
 # global-memory path behind the window
 WINDOW_BYTES_MAX = pack_mod.WINDOW_BYTES_MAX
-# lattices deeper than this default to float64 state vectors (see resolve_state_dtype)
+# lattices deeper than this default to float64 state vectors (see resolve_state_dtype): column-major lattices
+# (their kernels form every arc term as a float32 OFFSET from a reference arc) / all others (plain float32 log-values)
 F64_DEPTH = 96
+F64_DEPTH_PLAIN = 64
 # depth of the tile-stream kernels' stage rings; 0 = chosen by the library from the shared memory per block
 TILE_STAGES = int(os.environ.get("NFST_TILE_STAGES", "0"))
 
@@ -49,11 +51,21 @@ def resolve_state_dtype(packed: PackedLattices, state_dtype="auto") -> torch.dty
     An fp32 log-value x is only known to ulp(|x|)/2 ~ 6e-8*|x| and that rounding is
     committed at every level, so posteriors of deep lattices (|alpha| in the hundreds or
     thousands) cannot be 1e-5-accurate with fp32 state.  "auto" therefore uses float64 for
-    lattices deeper than F64_DEPTH levels -- they are latency-bound, the wider state costs
-    nothing measurable -- and float32 otherwise.
+    batches with a lattice deeper than F64_DEPTH levels (F64_DEPTH_PLAIN for lattices outside the column-major
+    layouts: measured 1.3e-5 on 70-level edit lattices with float32 state) -- they are latency-bound, the wider
+    state costs nothing measurable -- and float32 otherwise.
     """
     if state_dtype == "auto" or state_dtype is None:
-        return torch.float64 if packed.max_levels > F64_DEPTH else torch.float32
+        if packed.max_levels > F64_DEPTH:
+            return torch.float64
+        if packed.max_levels > F64_DEPTH_PLAIN:
+            lv, st = packed.stats.get("levels"), packed.stats
+            if lv is None or "tile" not in st or "sell" not in st:
+                return torch.float64
+            plain = ~(st["tile"].bool() | st["sell"].bool())
+            if bool((plain & (lv > F64_DEPTH_PLAIN)).any()):
+                return torch.float64
+        return torch.float32
     if state_dtype in (torch.float32, torch.float64):
         return state_dtype
     raise ValueError("state_dtype must be 'auto', torch.float32 or torch.float64")

@@ -10,6 +10,9 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+    # no test may hang the GPU box: pytest-timeout's per-test limit unless the command line or a marker sets one
+    if config.pluginmanager.hasplugin("timeout") and not getattr(config.option, "timeout", None):
+        config.option.timeout = float(os.environ.get("NFST_TEST_TIMEOUT", "600"))
 
 
 def pytest_collection_modifyitems(config, items):

@@ -190,7 +190,7 @@ def test_tile_mixed_batch_and_lattice_backward_outputs():
         ref = o_post[pk.arc_origin.cpu().numpy()]
         got = post[off_a:off_a + pk.n_arcs].cpu().numpy().astype(np.float64)
         rt = 1e-5 if pk.has_tiles else post_rtol(float(np.abs(o_alpha).max() + np.abs(o_beta).max()))
-        assert np.all(np.abs(got - ref) <= rt * ref + 1e-7)
+        assert np.all(np.abs(got - ref) <= rt * ref + 1e-7), (rt, float(np.max(np.abs(got - ref) / (ref + 1e-7))), pk.n_arcs)
         off_a += pk.n_arcs
         off_b += pk.n_lattices
     alpha2, logz2 = nb.lattice_forward(p, arc_scores=sc)
