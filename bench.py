@@ -46,6 +46,7 @@ def parse_args():
     ap.add_argument("--levels", type=int, default=64)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-theta", action="store_true", help="skip the theta-mode training-step leg")
     ap.add_argument("--no-sweep", action="store_true", help="skip the other points of the config-4 sweep (N=1 only)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     return ap.parse_args()
@@ -77,26 +78,42 @@ def make_arcs(a, device, seed_offset=0, batch=None, arcs=None):
     return synth.cipher_batch(B, T=1000, bigram=a.workload == "cipher-bi", seed=2 + seed_offset, device=device)
 
 
-def build_packed(a, device, seed_offset=0, arcs=None):
-    """Generate + pack on the device in chunks of lattices (bounds the packer's temporaries)
-    and collate the chunks."""
+def build_packed(a, device, arcs=None, rank=0, world=1):
+    """This rank's share of the GLOBAL batch (a.batch x world lattices), generated + packed on the device in
+    chunks of lattices (bounds the packer's temporaries) and collated.  At world > 1 every rank draws the same
+    global batch (chunk c has the seed of its first lattice), counts the arcs of every lattice and keeps the
+    lattices `nfst_b200.dist.shard_by_arcs` assigns to it (LPT bins by arc count)."""
     import torch
 
+    from nfst_b200 import dist as nd
     from nfst_b200.pack import concat_packed
 
     per_lat = (a.arcs if arcs is None else arcs) if a.workload == "dag" else 700_000
     chunk = max(1, min(a.batch, 60_000_000 // max(per_lat, 1)))
+    total = a.batch * world
+    spans = [(d, min(chunk, total - d)) for d in range(0, total, chunk)]
+    mine = None
+    if world > 1:
+        counts = []
+        for d, n in spans:
+            ab = make_arcs(a, device, seed_offset=d, batch=n, arcs=arcs)
+            counts.append(torch.bincount(ab.arc_lattice, minlength=n).cpu())
+            del ab
+        mine = torch.zeros(total, dtype=torch.bool)
+        mine[torch.tensor(nd.shard_by_arcs(torch.cat(counts).tolist(), world)[rank], dtype=torch.int64)] = True
     parts, scores = [], []
-    done = 0
-    while done < a.batch:
-        n = min(chunk, a.batch - done)
-        ab = make_arcs(a, device, seed_offset=seed_offset * 1000 + done, batch=n, arcs=arcs)
+    for d, n in spans:
+        ab = make_arcs(a, device, seed_offset=d, batch=n, arcs=arcs)
+        if mine is not None:
+            sel = torch.nonzero(mine[d:d + n]).squeeze(1)
+            if sel.numel() == 0:
+                continue
+            ab = ab.select(sel.to(device))
         p, sc = ab.pack()
         p.arc_origin = torch.empty(0, dtype=torch.int64, device=device)  # not needed here; frees 8 B/arc
         parts.append(p)
         scores.append(sc)
         del ab
-        done += n
     packed = concat_packed(parts) if len(parts) > 1 else parts[0]
     return packed, torch.cat(scores)
 
@@ -293,6 +310,7 @@ def main():
 
     import nfst_b200 as nb
     from nfst_b200 import _lib, ops
+    from nfst_b200 import dist as nd
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -305,8 +323,9 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     _lib.check(_lib.load().nfst_device_info(local, None, None, None, None))
 
-    packed, scores = build_packed(a, dev, seed_offset=rank)
+    packed, scores = build_packed(a, dev, rank=rank, world=world)
     A, S, B = packed.n_arcs, packed.n_states, packed.n_lattices
+    B_global = a.batch * world
     loss = torch.zeros(1, device=dev)
 
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(3 * a.steps + 2)]
@@ -338,20 +357,18 @@ def main():
         if i is not None:
             ev[3 * i + 2].record()
         if world > 1:
-            # the path's only collective: the loss all-reduce (posteriors feed the scorer's own backward).  It runs
-            # asynchronously on NCCL's stream, a ring of buffers deep, so that a step's kernels never queue behind
-            # the slowest rank's previous step; every all-reduce is waited for before the timed region ends.
-            k = step.count % len(loss_ring)
+            # the path's only collective: nfst_b200.dist.all_reduce_loss_and_grad (here the loss; the theta-mode leg
+            # below adds dtheta[V]).  Asynchronous, a ring of buffers deep, so that a step's kernels never queue
+            # behind the slowest rank's previous step; every all-reduce is waited for before the timed region ends.
+            k = step.count % len(pending)
             step.count += 1
             if pending[k] is not None:
                 pending[k].wait()
-            loss_ring[k].copy_(logz.sum().reshape(1))
-            pending[k] = dist.all_reduce(loss_ring[k], async_op=True)
+            pending[k] = nd.all_reduce_loss_and_grad(logz.sum(), None, async_op=True)
         return r
 
     step.count = 0
-    loss_ring = [torch.zeros(1, device=dev, dtype=torch.float32) for _ in range(4)] if world > 1 else []
-    pending = [None] * len(loss_ring)
+    pending = [None] * (4 if world > 1 else 0)
 
     def drain():
         for k, w in enumerate(pending):
@@ -363,36 +380,44 @@ def main():
         step()
     drain()
     torch.cuda.synchronize()
+    launches0 = ops.launch_count
+    clocks = ClockSampler(local)  # every rank samples its own GPU
+    clocks.start()
+    # all ranks enter the timed region together: the barrier is the LAST thing before it (anything rank-local in
+    # between -- NVML start-up took milliseconds on some ranks -- becomes waiting time at the first all-reduce)
     if world > 1:
         dist.barrier()
-    launches0 = ops.launch_count
-    clocks = ClockSampler(local)
-    if rank == 0:
-        clocks.start()
     torch.cuda.synchronize()
     t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    h0 = time.perf_counter()
     t_start.record()
     for i in range(a.steps):
         step(i)
     drain()  # the timed region ends when the last loss all-reduce has completed
     t_end.record()
+    host_ms = 1e3 * (time.perf_counter() - h0) / a.steps  # host time to ENQUEUE a step (the device must not starve)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-    clk = clocks.stop() if rank == 0 else None
+    clk = clocks.stop()
     ms_total = t_start.elapsed_time(t_end)
     launches = (ops.launch_count - launches0) // a.steps
     fwd_ms = sum(ev[3 * i].elapsed_time(ev[3 * i + 1]) for i in range(a.steps)) / a.steps
     bwd_ms = sum(ev[3 * i + 1].elapsed_time(ev[3 * i + 2]) for i in range(a.steps)) / a.steps
-    t = torch.tensor([ms_total, float(A)], device=dev, dtype=torch.float64)
+    mine = torch.tensor([ms_total / a.steps, fwd_ms, bwd_ms, host_ms, float(A), float(B), float(clk.get("sm_mhz") or 0.0),
+                         float(len(clk.get("reasons") or []))], device=dev, dtype=torch.float64)
     if world > 1:
-        tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-        tsum = t.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
-        ms_total, arcs_all = float(tmax[0]), float(tsum[1])
+        allr = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        per_rank = torch.stack(allr).cpu()
     else:
-        arcs_all = float(A)
-    ms_step = ms_total / a.steps
+        per_rank = mine.cpu().unsqueeze(0)
+    ms_step = float(per_rank[:, 0].max())  # the slowest rank
+    arcs_all = float(per_rank[:, 4].sum())
     value = arcs_all / (ms_step * 1e-3)
+    ranks = [{"rank": r, "ms_per_step": float(v[0]), "first_kernel_ms": float(v[1]), "second_kernel_ms": float(v[2]),
+              "between_kernels_ms": float(v[0] - v[1] - v[2]), "host_enqueue_ms": float(v[3]), "arcs": int(v[4]),
+              "lattices": int(v[5]), "sm_mhz": float(v[6]), "throttle_reasons": int(v[7])} for r, v in enumerate(per_rank)]
 
     # ---- e2e: host (pinned) buffers -> H2D -> fwd+bwd -> D2H logZ ----
     e2e = None
@@ -464,6 +489,59 @@ def main():
                "d2h_bytes_per_step": int(d2h), "steps": n_e2e, "ms_per_step": 1e3 * float(te[0]) / n_e2e}
         del host, host_scores
 
+    # ---- theta mode: arc score = theta[label], the parametrisation of nFST's WFSTScorer (scorers.py:1663-1687).
+    # A training step = logZ (pull pass), d loss / d theta[V] (flow pass with the label histogram, no per-arc output)
+    # and the path's collective, nfst_b200.dist.all_reduce_loss_and_grad({sum logZ, dtheta[V]}), every step.  The
+    # structure stays resident; end to end only theta[V] travels up and {loss, dtheta[V]} down.
+    theta_leg = None
+    if not a.no_theta:
+        V = packed.vocab
+        theta_host = (-torch.rand(V)).pin_memory()
+        theta_dev = theta_host.to(dev)
+        res_host = torch.empty(1 + V, dtype=torch.float32).pin_memory()
+
+        def theta_step(end_to_end=False):
+            if end_to_end:
+                theta_dev.copy_(theta_host, non_blocking=True)
+            logz, alpha, cond = ops.lattice_pull(packed, theta=theta_dev, beta_out=beta_buf)
+            r = nb.lattice_backward(packed, theta=theta_dev, alpha=alpha, logz=logz, cond=cond, want_beta=not all_sell,
+                                    want_post=False, want_dtheta=True)
+            loss, dth = nd.all_reduce_loss_and_grad(logz.sum(), r["dtheta"])
+            if end_to_end:
+                res_host[:1].copy_(loss.reshape(1), non_blocking=True)
+                res_host[1:].copy_(dth, non_blocking=True)
+                torch.cuda.current_stream().synchronize()
+            return loss
+
+        for _ in range(3):
+            theta_step()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        q0, q1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        q0.record()
+        for _ in range(a.steps):
+            theta_step()
+        q1.record()
+        torch.cuda.synchronize()
+        for _ in range(2):
+            theta_step(True)
+        if world > 1:
+            dist.barrier()
+        n_t = max(3, min(a.steps, 10))
+        t0 = time.perf_counter()
+        for _ in range(n_t):
+            theta_step(True)
+        dt = time.perf_counter() - t0
+        tt = torch.tensor([q0.elapsed_time(q1) / a.steps, 1e3 * dt / n_t], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        theta_leg = {"ms_per_step": float(tt[0]), "arcs_per_s": arcs_all / (float(tt[0]) * 1e-3),
+                     "collective": "nfst_b200.dist.all_reduce_loss_and_grad({sum logZ, dtheta[%d]}) every step" % V,
+                     "e2e": {"value": arcs_all / (float(tt[1]) * 1e-3), "unit": UNIT, "ms_per_step": float(tt[1]),
+                             "h2d_bytes_per_step": 4 * V, "d2h_bytes_per_step": 4 * (V + 1),
+                             "note": "structure resident in HBM; theta[V] up, {loss, dtheta[V]} down (pinned host buffers)"}}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -492,14 +570,15 @@ def main():
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
         "config": {"workload": workload_name(a), "lattices_per_gpu": B, "arcs_per_gpu": A, "states_per_gpu": S,
-                   "levels": packed.max_levels, "global_batch": B * world, "parallelism": f"dp{world} (lattices sharded, loss all-reduce only)",
+                   "levels": packed.max_levels, "global_batch": B_global, "parallelism": f"dp{world} (global batch of {B_global} lattices sharded by arc count with nfst_b200.dist.shard_by_arcs; one "
+                                  f"all_reduce_loss_and_grad per step)",
                    "l2": "inputs larger than L2 (no flush)" if 20 * A > 2 * 126e6 else "inputs fit in L2 (no flush; latency-bound config)",
                    "scores": "per-arc fp32, canonical order",
                    "execution": ("tile-stream (nfst_tiles.cu): " + ", ".join(f"{g.n} lattices x {g.block_threads // 32} warps, ring {g.tile_ring}"
                                                                               for g in packed.groups)) if all_tiles
                    else "sliced-column (nfst_sell.cu)" if all_sell else "CSR kernels (nfst_kernels.cu)"},
         "gpu_launches": launches,
-        "clocks": clk,
+        "clocks": dict(clk, min_sm_mhz_over_ranks=min(r["sm_mhz"] for r in ranks), ranks_with_throttle_reasons=sum(1 for r in ranks if r["throttle_reasons"])),
         "roofline": {"bound": "hbm", "kernel": dom["kernel"], "achieved": dom["achieved"],
                      "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": dom["achieved"] / peak,
                      "traffic": traffic, "traffic_source": traffic_src,
@@ -510,6 +589,10 @@ def main():
     }
     if e2e:
         out["e2e"] = e2e
+    if theta_leg:
+        theta_leg["frac"] = (20 * arcs_all / world + 20 * S) / (theta_leg["ms_per_step"] * 1e-3) / 1e9 / peak
+        out["theta_step"] = theta_leg
+    out["ranks"] = ranks
     if not a.no_cpu and world == 1:  # CPU baseline: rank 0 at N=1 only
         cb, _, _ = cpu_baseline(a, a.cpu_seconds)
         out["cpu_baseline"] = cb

@@ -349,7 +349,8 @@ int nfst_sell_flow_f32(const nfst_packed_lattices_t* lat, const nfst_launch_t* l
  *   gamma[dst_a] += gamma[src_a] * cond[a] accumulated in 32-bit FIXED POINT (2^-31 units) with native integer
  *   shared-memory atomics: the state posteriors carry an absolute error below 1e-9 and the result is bit
  *   reproducible (integer addition commutes).  post may alias cond.  dtheta[V] += post by label (caller
- *   zero-fills; accumulated per lattice in fixed point, then added with one float atomic per label).
+ *   zero-fills; accumulated per lattice in fixed point, then added with one float atomic per label).  post may be
+ *   NULL when dtheta is given: the pass then writes nothing per arc (the theta-mode training step).
  * Arc arrays are fetched with bulk copies of the 16-byte-aligned superset of a tile's range: arc_scores, cond
  *   and label_out must be 16-byte aligned and readable up to the next multiple of 4 elements.
  */

@@ -593,7 +593,7 @@ __global__ void __launch_bounds__(NT_MAX, MINB)
 // =====================================================================================
 // flow pass
 // =====================================================================================
-template <bool DTH, int NT_MAX, int MINB>
+template <bool DTH, bool POST, int NT_MAX, int MINB>
 __global__ void __launch_bounds__(NT_MAX, MINB)
     tile_flow_kernel(const nfst_packed_lattices_t L, const int32_t* __restrict__ ids, const TP P, const float* cond,
                      const float* __restrict__ grad_logz, float* post, float* __restrict__ dtheta) {
@@ -654,7 +654,7 @@ __global__ void __launch_bounds__(NT_MAX, MINB)
     const float cd = g.vals[e];
     const unsigned code = g.codes[e];
     const float pf = gam * cd;  // in fixed-point units (gam = gamma * 2^31)
-    post[g.arc0 + e] = pf * unfix;
+    if (POST) post[g.arc0 + e] = pf * unfix;
     TILE_CHECK(static_cast<int>(code) < ring_total, 6, static_cast<int>(code), ring_total, e);
     atomicAdd(&ring[code], __float2uint_rn(pf));
     if (DTH) {
@@ -959,7 +959,7 @@ int nfst_tile_pull_f32(const nfst_packed_lattices_t* lat, const nfst_launch_t* l
 int nfst_tile_flow_f32(const nfst_packed_lattices_t* lat, const nfst_launch_t* launch, const float* cond, const float* grad_logz,
                        float* post, float* dtheta, void* cuda_stream) {
   if (int rc = check_launch(lat, launch)) return rc;
-  if (!cond || !post) return nfst_fail_msg(NFST_ERR_BAD_ARG, "cond[A] and post[A] are required");
+  if (!cond || (!post && !dtheta)) return nfst_fail_msg(NFST_ERR_BAD_ARG, "cond[A] and one of post[A] / dtheta[V] are required");
   if (launch->n_ids == 0) return 0;
   cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
   const bool table = dtheta && lat->vocab <= NFST_THETA_SMEM_MAX;
@@ -974,12 +974,16 @@ int nfst_tile_flow_f32(const nfst_packed_lattices_t* lat, const nfst_launch_t* l
     return nfst_fail_msg(NFST_ERR_BAD_ARG, "cond and label_out must be 16-byte aligned (they are fetched with bulk copies)");
 #define FLOW_NT(NTv, MINBv)                                                                                               \
   do {                                                                                                                    \
-    if (dtheta) {                                                                                                         \
-      auto k = tile_flow_kernel<true, NTv, MINBv>;                                                                        \
+    if (dtheta && post) {                                                                                                 \
+      auto k = tile_flow_kernel<true, true, NTv, MINBv>;                                                                  \
+      if (int rc = prepare(k, g.smem)) return rc;                                                                         \
+      k<<<launch->n_ids, launch->block_threads, g.smem, stream>>>(*lat, launch->lattice_ids, g.p, cond, grad_logz, post, dtheta); \
+    } else if (dtheta) { /* the label histogram only: no per-arc output */                                                \
+      auto k = tile_flow_kernel<true, false, NTv, MINBv>;                                                                 \
       if (int rc = prepare(k, g.smem)) return rc;                                                                         \
       k<<<launch->n_ids, launch->block_threads, g.smem, stream>>>(*lat, launch->lattice_ids, g.p, cond, grad_logz, post, dtheta); \
     } else {                                                                                                              \
-      auto k = tile_flow_kernel<false, NTv, MINBv>;                                                                       \
+      auto k = tile_flow_kernel<false, true, NTv, MINBv>;                                                                 \
       if (int rc = prepare(k, g.smem)) return rc;                                                                         \
       k<<<launch->n_ids, launch->block_threads, g.smem, stream>>>(*lat, launch->lattice_ids, g.p, cond, grad_logz, post, dtheta); \
     }                                                                                                                     \

@@ -37,19 +37,36 @@ def my_shard(arc_counts: Sequence[int]) -> List[int]:
     return shard_by_arcs(arc_counts, dist.get_world_size())[dist.get_rank()]
 
 
-def all_reduce_loss_and_grad(loss_sum: torch.Tensor, dtheta: Optional[torch.Tensor] = None
-                             ) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
+class PendingReduce:
+    """An all-reduce of {loss, dtheta} in flight (``async_op=True``): ``wait()`` makes the current stream wait for
+    it and returns ``(loss, dtheta)``."""
+
+    def __init__(self, flat: torch.Tensor, work, loss_shape, dtheta_shape):
+        self.flat, self.work, self.loss_shape, self.dtheta_shape = flat, work, loss_shape, dtheta_shape
+
+    def wait(self) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
+        if self.work is not None:
+            self.work.wait()
+            self.work = None
+        loss = self.flat[0].reshape(self.loss_shape)
+        return loss, (self.flat[1:].reshape(self.dtheta_shape) if self.dtheta_shape is not None else None)
+
+
+def all_reduce_loss_and_grad(loss_sum: torch.Tensor, dtheta: Optional[torch.Tensor] = None, *, async_op: bool = False):
     """Sum ``loss_sum`` (scalar) and ``dtheta`` ([V]) over ranks with a single all-reduce of
-    one flat buffer, enqueued on the current stream right behind the fused backward."""
-    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
-        return loss_sum, dtheta
+    one flat buffer, enqueued right behind the fused backward.  Returns ``(loss, dtheta)``; with
+    ``async_op=True`` a ``PendingReduce`` instead (the all-reduce runs on the process group's own stream, the
+    caller's stream goes on with the next step and calls ``wait()`` when it needs the sums)."""
+    solo = not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1
     parts = [loss_sum.reshape(1).to(torch.float32)]
     if dtheta is not None:
         parts.append(dtheta.reshape(-1).to(torch.float32))
+    if solo and not async_op:
+        return loss_sum, dtheta
     flat = torch.cat(parts)
-    dist.all_reduce(flat, op=dist.ReduceOp.SUM)
-    loss = flat[0].reshape(loss_sum.shape)
-    return loss, (flat[1:].reshape(dtheta.shape) if dtheta is not None else None)
+    work = None if solo else dist.all_reduce(flat, op=dist.ReduceOp.SUM, async_op=async_op)
+    pending = PendingReduce(flat, work if async_op else None, loss_sum.shape, dtheta.shape if dtheta is not None else None)
+    return pending if async_op else pending.wait()
 
 
 def gather_ragged(local: torch.Tensor, indices: Sequence[int], total: int) -> torch.Tensor:

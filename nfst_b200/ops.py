@@ -313,11 +313,11 @@ def lattice_backward(
                         _ptr(cond) if (flow and not have_cond) else None, _ptr(delta), _ptr(backptr), _ptr(vit), streams[i]))
                     launch_count += int(log_pull) + int(want_viterbi)
                 if flow:
-                    dst = post if want_post else (torch.empty(A, **f32) if have_cond else cond)
-                    if g.tiles:
-                        _lib.check(lib.nfst_tile_flow_f32(packed.c_struct(), lc, cond.data_ptr(), _ptr(g32), dst.data_ptr(),
+                    if g.tiles:  # without want_post the tile-stream flow pass writes nothing per arc (dtheta only)
+                        _lib.check(lib.nfst_tile_flow_f32(packed.c_struct(), lc, cond.data_ptr(), _ptr(g32), _ptr(post),
                                                           _ptr(dtheta), streams[i]))
                     else:
+                        dst = post if want_post else (torch.empty(A, **f32) if have_cond else cond)
                         _lib.check(lib.nfst_sell_flow_f32(packed.c_struct(), lc, cond.data_ptr(), _ptr(g32), dst.data_ptr(),
                                                           None, None, None, _ptr(dtheta), _ptr(gfar), streams[i]))
                     launch_count += 1

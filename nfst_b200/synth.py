@@ -34,6 +34,15 @@ class ArcBatch:
         p = pack_arcs(self.arc_lattice, self.src, self.dst, self.label, self.n_states, self.vocab, **kw)
         return p, self.scores[p.arc_origin].contiguous()
 
+    def select(self, lattice_ids) -> "ArcBatch":
+        """The sub-batch of the given lattices (ascending ids), renumbered 0..n-1; arc order is kept."""
+        ids = torch.as_tensor(lattice_ids, dtype=torch.int64, device=self.src.device)
+        remap = torch.full((int(self.n_states.numel()),), -1, dtype=torch.int64, device=self.src.device)
+        remap[ids] = torch.arange(ids.numel(), device=self.src.device)
+        new_lat = remap[self.arc_lattice]
+        keep = new_lat >= 0
+        return ArcBatch(new_lat[keep], self.src[keep], self.dst[keep], self.label[keep], self.scores[keep], self.n_states[ids], self.vocab)
+
     def to(self, device) -> "ArcBatch":
         return ArcBatch(*(getattr(self, f.name).to(device) if isinstance(getattr(self, f.name), torch.Tensor)
                           else getattr(self, f.name) for f in dataclasses.fields(self)))

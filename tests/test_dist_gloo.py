@@ -40,6 +40,11 @@ def _worker(rank, world, port, q):
         np.add.at(dtheta, ab.label.numpy()[sel], post)
         loss, grad = nd.all_reduce_loss_and_grad(torch.tensor(logz.sum(), dtype=torch.float32),
                                                  torch.from_numpy(dtheta).float())
+        # the same sums through the asynchronous form (what bench.py's step uses)
+        pend = nd.all_reduce_loss_and_grad(torch.tensor(logz.sum(), dtype=torch.float32), torch.from_numpy(dtheta).float(),
+                                           async_op=True)
+        loss2, grad2 = pend.wait()
+        assert float(loss2) == float(loss) and torch.equal(grad2, grad)
         scores = nd.gather_ragged(torch.from_numpy(logz).float(), mine, 9)
         q.put((rank, mine, float(loss), grad.numpy(), scores.numpy()))
     finally:

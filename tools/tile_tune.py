@@ -64,6 +64,22 @@ def main():
     v1.record()
     torch.cuda.synchronize()
     tv = v0.elapsed_time(v1) / n
+    # theta mode (scores = theta[label]): pull with the label lookup, flow with the label histogram and no per-arc output
+    theta = -torch.rand(packed.vocab, device=dev)
+    tev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(n)]
+    for e in [None] * 3 + tev:
+        if e:
+            e[0].record()
+        lz, al, cd = ops.lattice_pull(packed, theta=theta, beta_out=beta)
+        if e:
+            e[1].record()
+        nb.lattice_backward(packed, theta=theta, alpha=al, logz=lz, cond=cd, want_beta=not sell_only, want_post=False, want_dtheta=True)
+        if e:
+            e[2].record()
+    torch.cuda.synchronize()
+    tp = sum(e[0].elapsed_time(e[1]) for e in tev) / n
+    tf = sum(e[1].elapsed_time(e[2]) for e in tev) / n
+    print(f"  theta mode: pull {tp:.3f} ms  flow+dtheta {tf:.3f} ms  step {tp + tf:.3f} ms = {Ar / (tp + tf) / 1e6:.1f} Garc/s", flush=True)
     # the same step replayed from a CUDA graph: device time without the host's per-call work
     g = torch.cuda.CUDAGraph()
     with torch.cuda.graph(g):
