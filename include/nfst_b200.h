@@ -31,6 +31,10 @@
  *                           column-major 32-state slices (same reference functions as nfst_bwd_fused_f32).
  *   nfst_beta_to_dense      layout of compute_beta()'s return value, real-space
  *                           beta[B*k, S] (scorers.py:854, :858-875).
+ *   nfst_pack_small         the per-call graph build at the top of compute_beta_per_sample / compute_beta_parallel
+ *                           (scorers.py:704-716, :764-776: adjacency lists from the dense table) plus the
+ *                           topological ordering the reference does implicitly with its message counters
+ *                           (:741-749); trims the rows collate() padding adds (util/dataset_reader.py:175-186).
  *   nfst_dense_count_arcs / nfst_dense_extract_arcs
  *                           the dense-table edge rule `t != 0 and t != i`
  *                           (scorers.py:704-716, :764-776) over collate()-padded
@@ -49,14 +53,16 @@
 extern "C" {
 #endif
 
-#define NFST_ABI_VERSION 11
+#define NFST_ABI_VERSION 12
 
 typedef enum nfst_status {
   NFST_OK = 0,
   NFST_ERR_BAD_ARG = -1,
   NFST_ERR_CUDA = -2,
   NFST_ERR_UNSUPPORTED_DEVICE = -3,
-  NFST_ERR_TOO_LARGE = -4
+  NFST_ERR_TOO_LARGE = -4,
+  NFST_ERR_CYCLIC = -5,      /* pack: a lattice has a cycle (the DP is defined for acyclic lattices only) */
+  NFST_ERR_BAD_LATTICE = -6  /* pack: arc endpoint or start state out of range */
 } nfst_status;
 
 /* One unit of work of a lattice: a run of consecutive states of ONE topological level
@@ -432,6 +438,38 @@ int nfst_sample_paths_f32(const nfst_packed_lattices_t* lat, int32_t n_rows, int
 int nfst_beta_hat_level_f32(const nfst_packed_lattices_t* lat, const int32_t* states, int32_t n_states, int32_t hidden,
                             const float* label_proj, const float* wh_t, const float* w, float* log_beta,
                             float* beta_hat, float* h_proj, void* cuda_stream);
+
+/*
+ * Device packer for lattices that fit one SM's shared memory (the size nFST's composed mark lattices have).
+ * Input: a raw arc list grouped by lattice and sorted by (source state, label) -- the scan order of the dense
+ * tables, which nfst_dense_extract_arcs produces -- with LOCAL destination ids and either local source ids or
+ * global rows (src_is_global: raw_state_off[b] + local id).  Output: the arrays of nfst_packed_lattices_t that
+ * the small-lattice kernels, the sampling-loop kernels and the best-path read-out use (everything except the
+ * chunk lists, the sliced-column descriptors and the tile stream), written into caller-allocated buffers sized
+ * for the RAW counts (trimming only shrinks): per-state arrays [n_states_raw (+1)], per-arc arrays [n_arcs_raw],
+ * level_ptr [n_states_raw + B], offsets [B + 1].  Three launches on the caller's stream, no host synchronisation:
+ * the caller reads totals[8] = {S, A, level_ptr entries, sinks, error, lattice of the error, largest level count,
+ * 0} (error 4: a lattice keeps more than max_arcs arcs -- max_arcs bounds the KEPT arcs of a lattice, the raw list
+ * may be longer: collate() padding) and lattice_stats[B][8] = {states, arcs, levels, sinks, arcs of the widest level, 0, 0, 0} (zero-filled by the
+ * caller) when it needs the sizes.  error: 0 ok, 1 = cyclic
+ * lattice, 2 = arc endpoint / start state out of range, 3 = batch beyond int32 indices.
+ */
+typedef struct nfst_pack_out {
+  int32_t *state_off, *arc_off, *level_off, *sink_off; /* [B+1] */
+  int32_t *n_levels, *start_state;                     /* [B]   */
+  int32_t *level_ptr, *sinks, *orig_state;             /* per state */
+  int32_t *in_ptr, *out_ptr;                           /* [S+1] */
+  int32_t *src_in, *label_in, *in2out, *dst_out, *label_out, *src_out; /* per arc */
+  int64_t *arc_origin;                                 /* per arc: index into the raw arc list */
+  int32_t *lattice_stats;                              /* [B][8] */
+  int32_t *totals;                                     /* [8] */
+} nfst_pack_out_t;
+size_t nfst_pack_small_smem_bytes(int32_t max_states, int32_t max_arcs);
+size_t nfst_pack_small_workspace_bytes(int64_t n_states_raw, int64_t n_arcs_raw);
+int nfst_pack_small(int32_t n_lattices, const int32_t* raw_state_off, const int32_t* raw_arc_off, const int32_t* raw_src,
+                    const int32_t* raw_dst, const int32_t* raw_label, int32_t src_is_global, int32_t start_state,
+                    int32_t max_states, int32_t max_arcs, const nfst_pack_out_t* out, void* workspace, size_t workspace_bytes,
+                    int64_t n_states_raw, int64_t n_arcs_raw, void* cuda_stream);
 
 #ifdef __cplusplus
 }

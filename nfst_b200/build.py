@@ -8,7 +8,8 @@ import subprocess
 PKG = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(PKG)
 SRC = [os.path.join(PKG, "csrc", "nfst_kernels.cu"), os.path.join(PKG, "csrc", "nfst_sell.cu"),
-       os.path.join(PKG, "csrc", "nfst_tiles.cu"), os.path.join(PKG, "csrc", "nfst_walk.cu")]
+       os.path.join(PKG, "csrc", "nfst_tiles.cu"), os.path.join(PKG, "csrc", "nfst_walk.cu"),
+       os.path.join(PKG, "csrc", "nfst_pack.cu")]
 HDR = [os.path.join(ROOT, "include", "nfst_b200.h")]
 LIB = os.path.join(PKG, "lib", "libnfst_b200.so")
 

@@ -1,0 +1,481 @@
+// nfst_pack.cu -- device packer for the lattices nFST itself builds (sm_100a).
+//
+// What it replaces: the per-call Python graph build at the top of FSAGRUScorer.compute_beta_per_sample /
+// compute_beta_parallel (src/modules/scorers.py:704-716, :764-776: scan the dense transition table, keep cell
+// (i, j) iff t != 0 and t != i, build adjacency lists) and the host-side packer of this repository
+// (nfst_b200/pack.py, ~10^3 eager tensor ops) for the lattices that fit one SM's shared memory -- the size
+// nFST's composed mark lattices have (hundreds to a few thousand states).
+//
+// One thread block per lattice, three launches for the whole batch:
+//   pack_level_kernel   states the start state reaches (sweeps over the raw arcs in global memory); the arcs out of
+//                       those states -> shared memory; longest distance from the start by relaxation sweeps
+//                       (shared-memory atomicMax, until nothing changes; more sweeps than states = a cycle);
+//                       states unreachable from the start -- every row collate() padding adds
+//                       (util/dataset_reader.py:175-186) -- are trimmed; per-lattice counts
+//   pack_scan_kernel    one block: exclusive scans of the counts -> state / arc / level / sink offsets, totals
+//   pack_build_kernel   renumber the states by (level, original id), emit CSR by source in (state, label) order --
+//                       the reference's scan order, which is what Viterbi's first-label tie rule needs -- and CSR
+//                       by destination in (state, canonical id) order, level pointers, sinks, original ids
+// The caller reads the totals once (the only host synchronisation of a pack) to size the views it hands out.
+#include "nfst_b200.h"
+
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+int nfst_fail_msg(int code, const char* fmt, ...);  // nfst_kernels.cu (sets the thread's last error)
+
+namespace {
+
+#define PACK_CUDA_OK(expr)                                                                                  \
+  do {                                                                                                      \
+    cudaError_t _e = (expr);                                                                                \
+    if (_e != cudaSuccess) return nfst_fail_msg(NFST_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString(_e)); \
+  } while (0)
+
+constexpr int kThreads = 256;
+extern __shared__ __align__(16) int pack_smem[];
+
+struct RawArcs {
+  const int32_t* src;    // raw source: local id, or global row (src_global)
+  const int32_t* dst;    // raw destination, local id
+  const int32_t* label;
+  const int32_t* state_off;  // [B+1] raw (untrimmed) state offsets
+  const int32_t* arc_off;    // [B+1] raw arc offsets (arcs grouped by lattice, sorted by (src, label))
+  int src_global;
+  int start;  // local id of the start state (the reference's row 0, scorers.py:1005)
+};
+
+// exclusive scan of v[0..n) in place over the block (n arbitrary); returns the total.  tmp: kThreads ints.
+__device__ int block_excl_scan(int* v, int n, int* tmp) {
+  const int tid = threadIdx.x;
+  const int per = (n + kThreads - 1) / kThreads;
+  const int lo = tid * per, hi = min(lo + per, n);
+  int sum = 0;
+  for (int i = lo; i < hi; ++i) sum += v[i];
+  tmp[tid] = sum;
+  __syncthreads();
+  for (int o = 1; o < kThreads; o <<= 1) {  // Hillis-Steele over the per-thread sums
+    const int add = tid >= o ? tmp[tid - o] : 0;
+    __syncthreads();
+    tmp[tid] += add;
+    __syncthreads();
+  }
+  int run = tid ? tmp[tid - 1] : 0;
+  const int total = tmp[kThreads - 1];
+  for (int i = lo; i < hi; ++i) {
+    const int x = v[i];
+    v[i] = run;
+    run += x;
+  }
+  __syncthreads();
+  return total;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// reachability, kept arcs, levels, counts
+// ---------------------------------------------------------------------------------------------------------
+struct Kept {  // the arcs that survive trimming, per lattice at its raw arc offset (workspace)
+  int32_t* pack;   // src | dst << 16 (raw local ids)
+  int32_t* label;
+  int32_t* raw;    // position in the lattice's raw arc list
+};
+
+__global__ void __launch_bounds__(kThreads)
+    pack_level_kernel(const RawArcs R, int capS, int capA, int32_t* __restrict__ level_g, const Kept K,
+                      int32_t* __restrict__ stats, int32_t* __restrict__ totals) {
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int s0 = R.state_off[b], S0 = R.state_off[b + 1] - s0;
+  const int a0 = R.arc_off[b], A0 = R.arc_off[b + 1] - a0;
+  int* const level = pack_smem;             // [capS]
+  int* const has_out = level + capS;        // [capS]
+  int* const arcs = has_out + capS;         // [capA] kept arcs: src | dst << 16
+  __shared__ int changed, bad, n_states, n_sinks, max_level, kept_base;
+  __shared__ int warp_sum[kThreads / 32];
+  for (int s = tid; s < S0; s += kThreads) {
+    level[s] = -1;
+    has_out[s] = 0;
+  }
+  if (tid == 0) {
+    changed = 0; bad = 0; n_states = 0; n_sinks = 0; max_level = 0; kept_base = 0;
+  }
+  __syncthreads();
+  if (tid == 0 && R.start >= 0 && R.start < S0) level[R.start] = 0;
+  __syncthreads();
+  // 1. which states the start state reaches: sweeps over the RAW arcs in global memory (a collate()-padded table
+  //    carries V arcs per pad row -- far more than the lattice's own -- so they never enter shared memory).
+  //    OpenFst numbers states roughly topologically and the arcs are sorted by source: a sweep or two settles it.
+  for (int sweep = 0;; ++sweep) {
+    for (int i = tid; i < A0; i += kThreads) {
+      const int s = R.src[a0 + i] - (R.src_global ? s0 : 0), d = R.dst[a0 + i];
+      if (s < 0 || s >= S0 || d < 0 || d >= S0) {
+        bad = 2;
+      } else if (level[s] >= 0 && level[d] < 0) {
+        level[d] = 0;
+        changed = 1;
+      }
+    }
+    __syncthreads();
+    const int again = changed, wrong = bad;
+    __syncthreads();
+    if (wrong || R.start < 0 || R.start >= S0) {
+      if (tid == 0 && atomicCAS(&totals[4], 0, 2) == 0) totals[5] = b;
+      return;
+    }
+    if (!again || sweep > S0) break;
+    if (tid == 0) changed = 0;
+    __syncthreads();
+  }
+  // 2. the kept arcs (source reachable), in raw order: shared memory for the level sweeps, workspace for the build
+  for (int base = 0; base < A0; base += kThreads) {
+    const int i = base + tid;
+    int s = 0, d = 0;
+    bool keep = false;
+    if (i < A0) {
+      s = R.src[a0 + i] - (R.src_global ? s0 : 0);
+      d = R.dst[a0 + i];
+      keep = level[s] >= 0;
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, keep);
+    if (lane == 0) warp_sum[warp] = __popc(m);
+    __syncthreads();
+    int before = kept_base;
+    for (int w = 0; w < warp; ++w) before += warp_sum[w];
+    if (keep) {
+      const int j = before + __popc(m & ((1u << lane) - 1u));
+      const int pk = static_cast<int>((static_cast<unsigned>(s) & 0xffffu) | (static_cast<unsigned>(d) << 16));
+      if (j < capA) arcs[j] = pk;
+      K.pack[a0 + j] = pk;
+      K.label[a0 + j] = R.label[a0 + i];
+      K.raw[a0 + j] = i;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      int t = 0;
+      for (int w = 0; w < kThreads / 32; ++w) t += warp_sum[w];
+      kept_base += t;
+    }
+    __syncthreads();
+  }
+  const int Ak = kept_base;
+  if (Ak > capA) {  // more arcs than the shared memory this launch was sized for: the caller packs this batch elsewhere
+    if (tid == 0 && atomicCAS(&totals[4], 0, 4) == 0) totals[5] = b;
+    return;
+  }
+  // 3. longest distance from the start over the kept arcs: sweep until a sweep changes nothing
+  for (int s = tid; s < S0; s += kThreads) level[s] = (level[s] >= 0) ? (s == R.start ? 0 : -2) : -1;  // -2: reachable, not yet placed
+  __syncthreads();
+  for (int sweep = 0;; ++sweep) {
+    for (int i = tid; i < Ak; i += kThreads) {
+      const int a = arcs[i];
+      const int ls = level[a & 0xffff];
+      if (ls >= 0 && atomicMax(&level[static_cast<unsigned>(a) >> 16], ls + 1) < ls + 1) changed = 1;
+    }
+    __syncthreads();
+    const int again = changed;
+    __syncthreads();
+    if (!again) break;
+    if (tid == 0) changed = 0;
+    if (sweep > S0) {  // a path longer than the number of states: a cycle
+      if (tid == 0 && atomicCAS(&totals[4], 0, 1) == 0) totals[5] = b;
+      return;
+    }
+    __syncthreads();
+  }
+  for (int i = tid; i < Ak; i += kThreads) has_out[arcs[i] & 0xffff] = 1;
+  __syncthreads();
+  int cs = 0, ck = 0, ml = 0;
+  for (int s = tid; s < S0; s += kThreads) {
+    const int l = level[s];
+    level_g[s0 + s] = l;
+    if (l >= 0) {
+      ++cs;
+      ck += has_out[s] ? 0 : 1;
+      ml = max(ml, l);
+    }
+  }
+  atomicAdd(&n_states, cs);
+  atomicAdd(&n_sinks, ck);
+  atomicMax(&max_level, ml);
+  __syncthreads();
+  if (tid == 0) {
+    stats[8 * b + 0] = n_states;
+    stats[8 * b + 1] = Ak;
+    stats[8 * b + 2] = max_level + 1;
+    stats[8 * b + 3] = n_sinks;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// offsets (one block)
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads)
+    pack_scan_kernel(int B, const int32_t* __restrict__ stats, int32_t* __restrict__ state_off, int32_t* __restrict__ arc_off,
+                     int32_t* __restrict__ level_off, int32_t* __restrict__ sink_off, int32_t* __restrict__ n_levels,
+                     int32_t* __restrict__ totals) {
+  __shared__ long long carry[4];
+  __shared__ int tmp[4][kThreads];
+  __shared__ int mx[kThreads];
+  const int tid = threadIdx.x;
+  if (tid < 4) carry[tid] = 0;
+  int my_max = 0;
+  __syncthreads();
+  for (int base = 0; base < B; base += kThreads) {
+    const int b = base + tid;
+    int v[4] = {0, 0, 0, 0};
+    if (b < B) {
+      v[0] = stats[8 * b + 0];
+      v[1] = stats[8 * b + 1];
+      v[2] = stats[8 * b + 2] + 1;  // a lattice owns levels + 1 entries of level_ptr
+      v[3] = stats[8 * b + 3];
+      n_levels[b] = stats[8 * b + 2];
+      my_max = max(my_max, stats[8 * b + 2]);
+    }
+    for (int q = 0; q < 4; ++q) tmp[q][tid] = v[q];
+    __syncthreads();
+    for (int o = 1; o < kThreads; o <<= 1) {
+      int add[4];
+      for (int q = 0; q < 4; ++q) add[q] = tid >= o ? tmp[q][tid - o] : 0;
+      __syncthreads();
+      for (int q = 0; q < 4; ++q) tmp[q][tid] += add[q];
+      __syncthreads();
+    }
+    if (b < B) {
+      state_off[b] = static_cast<int32_t>(carry[0] + tmp[0][tid] - v[0]);
+      arc_off[b] = static_cast<int32_t>(carry[1] + tmp[1][tid] - v[1]);
+      level_off[b] = static_cast<int32_t>(carry[2] + tmp[2][tid] - v[2]);
+      sink_off[b] = static_cast<int32_t>(carry[3] + tmp[3][tid] - v[3]);
+    }
+    __syncthreads();
+    if (tid < 4) carry[tid] += tmp[tid][kThreads - 1];
+    __syncthreads();
+  }
+  mx[tid] = my_max;
+  __syncthreads();
+  for (int o = kThreads / 2; o > 0; o >>= 1) {
+    if (tid < o) mx[tid] = max(mx[tid], mx[tid + o]);
+    __syncthreads();
+  }
+  if (tid == 0) {
+    state_off[B] = static_cast<int32_t>(carry[0]);
+    arc_off[B] = static_cast<int32_t>(carry[1]);
+    level_off[B] = static_cast<int32_t>(carry[2]);
+    sink_off[B] = static_cast<int32_t>(carry[3]);
+    if (carry[0] >= 0x7fffffffLL || carry[1] >= 0x7fffffffLL) atomicCAS(&totals[4], 0, 3);
+    totals[0] = static_cast<int32_t>(carry[0]);
+    totals[1] = static_cast<int32_t>(carry[1]);
+    totals[2] = static_cast<int32_t>(carry[2]);
+    totals[3] = static_cast<int32_t>(carry[3]);
+    totals[6] = mx[0];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// build
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads)
+    pack_build_kernel(const RawArcs R, int capS, int capA, const int32_t* __restrict__ level_g, const Kept K,
+                      const nfst_pack_out_t O, const int32_t* __restrict__ totals) {
+  if (totals[4]) return;  // an invalid lattice somewhere: the caller raises, nothing is used
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
+  const int s0 = R.state_off[b], S0 = R.state_off[b + 1] - s0;
+  const int a0 = R.arc_off[b];
+  const int s_lo = O.state_off[b], Sb = O.state_off[b + 1] - s_lo;
+  const int a_lo = O.arc_off[b], Ab = O.arc_off[b + 1] - a_lo;
+  const int A0 = Ab;  // the kept arcs, in raw order (pack_level_kernel left them in the workspace)
+  const int l_lo = O.level_off[b], nlev = O.level_off[b + 1] - l_lo - 1;
+  const int k_lo = O.sink_off[b];
+  int* p = pack_smem;
+  int* const level = p;      p += capS;      // [S0] raw state -> level (-1: trimmed)
+  int* const new_id = p;     p += capS;      // [S0] raw state -> packed local id
+  int* const first_raw = p;  p += capS;      // [S0] raw state -> index of its first raw arc
+  int* const lvl = p;        p += capS + 2;  // [nlev + 1] level start (packed local ids), then a cursor copy
+  int* const cur = p;        p += capS + 2;
+  int* const out_ptr = p;    p += capS + 1;  // [Sb + 1]
+  int* const in_ptr = p;     p += capS + 1;
+  int* const in_cur = p;     p += capS + 1;
+  int* const raw = p;        p += capA;      // [A0] src | dst << 16 (raw local ids)
+  unsigned short* const can_src = reinterpret_cast<unsigned short*>(p);  // [Ab] packed local source of each canonical arc
+  unsigned short* const in_tmp = can_src + capA;                           // [Ab] canonical arc (local) per in-order position
+  __shared__ int tmp[kThreads];
+  __shared__ int sink_cursor, width_arcs;
+
+  for (int s = tid; s < S0; s += kThreads) {
+    level[s] = level_g[s0 + s];
+    first_raw[s] = 0;
+  }
+  for (int i = tid; i <= nlev + 1; i += kThreads) lvl[i] = 0;
+  for (int i = tid; i <= Sb; i += kThreads) {
+    out_ptr[i] = 0;
+    in_ptr[i] = 0;
+    in_cur[i] = 0;
+  }
+  if (tid == 0) {
+    sink_cursor = 0;
+    width_arcs = 0;
+  }
+  for (int i = tid; i < A0; i += kThreads) raw[i] = K.pack[a0 + i];
+  __syncthreads();
+  // states per level -> level starts
+  for (int s = tid; s < S0; s += kThreads)
+    if (level[s] >= 0) atomicAdd(&lvl[level[s]], 1);
+  __syncthreads();
+  block_excl_scan(lvl, nlev + 1, tmp);  // lvl[nlev] = Sb
+  for (int i = tid; i <= nlev; i += kThreads) cur[i] = lvl[i];
+  __syncthreads();
+  // packed id = (level, original id) order: one warp walks the states in original order, 32 at a time; the states
+  // of a batch that share a level take consecutive ids in lane order (match_any), so the numbering is deterministic
+  if (tid < 32) {
+    for (int base = 0; base < S0; base += 32) {
+      const int s = base + lane;
+      const int l = s < S0 ? level[s] : -1;
+      const unsigned same = __match_any_sync(0xffffffffu, l);
+      if (l >= 0) {
+        const int rank = __popc(same & ((1u << lane) - 1u));
+        new_id[s] = cur[l] + rank;
+      } else if (s < S0) {
+        new_id[s] = -1;
+      }
+      __syncwarp();
+      if (l >= 0 && (same & ((1u << lane) - 1u)) == 0) cur[l] += __popc(same);
+      __syncwarp();
+    }
+  }
+  __syncthreads();
+  // degrees of the kept states; first raw arc of every raw state (raw arcs are sorted by source)
+  for (int i = tid; i < A0; i += kThreads) {
+    const int a = raw[i];
+    const int s = a & 0xffff, d = static_cast<unsigned>(a) >> 16;
+    if (i == 0 || (raw[i - 1] & 0xffff) != s) first_raw[s] = i;
+    atomicAdd(&out_ptr[new_id[s]], 1);
+    atomicAdd(&in_ptr[new_id[d]], 1);
+  }
+  __syncthreads();
+  // sinks (kept states without arcs), in packed order: states of the deepest level and dead ends
+  for (int base = 0; base < Sb; base += kThreads) {
+    const int s = base + tid;
+    const bool is_sink = s < Sb && out_ptr[s] == 0;
+    tmp[tid] = is_sink ? 1 : 0;
+    __syncthreads();
+    if (tid == 0) {
+      int run = sink_cursor;
+      for (int i = 0; i < kThreads; ++i) {
+        const int x = tmp[i];
+        tmp[i] = run;
+        run += x;
+      }
+      sink_cursor = run;
+    }
+    __syncthreads();
+    if (is_sink) O.sinks[k_lo + tmp[tid]] = s_lo + s;
+    __syncthreads();
+  }
+  block_excl_scan(out_ptr, Sb + 1, tmp);
+  block_excl_scan(in_ptr, Sb + 1, tmp);
+  // widest level, in arcs (either direction): sizes the thread block of the DP kernels
+  for (int l = tid; l < nlev; l += kThreads)
+    atomicMax(&width_arcs, max(out_ptr[lvl[l + 1]] - out_ptr[lvl[l]], in_ptr[lvl[l + 1]] - in_ptr[lvl[l]]));
+  // canonical (out) order: arcs of one source are contiguous in the raw list and sorted by label already
+  for (int i = tid; i < A0; i += kThreads) {
+    const int a = raw[i];
+    const int s = a & 0xffff, d = static_cast<unsigned>(a) >> 16;
+    const int ns = new_id[s], nd = new_id[d];
+    const int pos = out_ptr[ns] + (i - first_raw[s]);
+    O.dst_out[a_lo + pos] = s_lo + nd;
+    O.label_out[a_lo + pos] = K.label[a0 + i];
+    O.arc_origin[a_lo + pos] = a0 + K.raw[a0 + i];
+    can_src[pos] = static_cast<unsigned short>(ns);
+    in_tmp[in_ptr[nd] + atomicAdd(&in_cur[nd], 1)] = static_cast<unsigned short>(pos);
+  }
+  __syncthreads();
+  // in order: every destination's arcs sorted by canonical id (insertion sort per state: in-degrees are small),
+  // which makes the layout independent of the order the atomics above were served in
+  for (int s = tid; s < Sb; s += kThreads) {
+    const int lo = in_ptr[s], hi = in_ptr[s + 1];
+    for (int i = lo + 1; i < hi; ++i) {
+      const unsigned short x = in_tmp[i];
+      int j = i - 1;
+      while (j >= lo && in_tmp[j] > x) {
+        in_tmp[j + 1] = in_tmp[j];
+        --j;
+      }
+      in_tmp[j + 1] = x;
+    }
+  }
+  __syncthreads();
+  for (int i = tid; i < Ab; i += kThreads) {
+    const int c = in_tmp[i];
+    O.in2out[a_lo + i] = a_lo + c;
+    O.src_in[a_lo + i] = s_lo + can_src[c];
+    O.label_in[a_lo + i] = O.label_out[a_lo + c];  // written above by this block
+    O.src_out[a_lo + i] = s_lo + can_src[i];
+  }
+  for (int s = tid; s < Sb; s += kThreads) {
+    O.out_ptr[s_lo + s] = a_lo + out_ptr[s];
+    O.in_ptr[s_lo + s] = a_lo + in_ptr[s];
+  }
+  for (int s = tid; s < S0; s += kThreads)
+    if (level[s] >= 0) O.orig_state[s_lo + new_id[s]] = s;
+  for (int i = tid; i <= nlev; i += kThreads) O.level_ptr[l_lo + i] = s_lo + lvl[i];
+  if (tid == 0) {
+    O.lattice_stats[8 * b + 4] = width_arcs;  // complete: an atomicMax above, several barriers ago
+    O.start_state[b] = s_lo + new_id[R.start];
+    if (b == gridDim.x - 1) {  // closing entries of the CSR pointers
+      O.out_ptr[s_lo + Sb] = a_lo + Ab;
+      O.in_ptr[s_lo + Sb] = a_lo + Ab;
+    }
+  }
+}
+
+size_t level_smem(int capS, int capA) { return static_cast<size_t>(2 * capS + capA) * 4; }
+size_t build_smem(int capS, int capA) { return static_cast<size_t>(8 * capS + 8 + capA) * 4 + static_cast<size_t>(capA) * 4; }
+
+}  // namespace
+
+extern "C" {
+
+size_t nfst_pack_small_smem_bytes(int32_t max_states, int32_t max_arcs) {
+  const size_t a = level_smem(max_states, max_arcs), b = build_smem(max_states, max_arcs);
+  return a > b ? a : b;
+}
+
+size_t nfst_pack_small_workspace_bytes(int64_t n_states_raw, int64_t n_arcs_raw) {
+  // level of every raw state; the kept arcs {src | dst << 16, label, raw position}
+  return (static_cast<size_t>(n_states_raw) + 3 * static_cast<size_t>(n_arcs_raw) + 16) * 4;
+}
+
+int nfst_pack_small(int32_t n_lattices, const int32_t* raw_state_off, const int32_t* raw_arc_off, const int32_t* raw_src,
+                    const int32_t* raw_dst, const int32_t* raw_label, int32_t src_is_global, int32_t start_state,
+                    int32_t max_states, int32_t max_arcs, const nfst_pack_out_t* out, void* workspace, size_t workspace_bytes,
+                    int64_t n_states_raw, int64_t n_arcs_raw, void* cuda_stream) {
+  if (n_lattices <= 0 || !raw_state_off || !raw_arc_off || !out || !workspace)
+    return nfst_fail_msg(NFST_ERR_BAD_ARG, "nfst_pack_small: null argument or empty batch");
+  if (max_states < 1 || max_states > 65535 || max_arcs < 0 || max_arcs > 65535)
+    return nfst_fail_msg(NFST_ERR_TOO_LARGE, "nfst_pack_small: at most 65535 states and arcs per lattice (got %d, %d)", max_states,
+                         max_arcs);
+  if (workspace_bytes < nfst_pack_small_workspace_bytes(n_states_raw, n_arcs_raw))
+    return nfst_fail_msg(NFST_ERR_BAD_ARG, "nfst_pack_small: workspace too small");
+  const size_t smem = nfst_pack_small_smem_bytes(max_states, max_arcs);
+  if (smem > 227 * 1024)
+    return nfst_fail_msg(NFST_ERR_TOO_LARGE, "nfst_pack_small: a lattice of %d states / %d arcs needs %zu bytes of shared memory",
+                         max_states, max_arcs, smem);
+  cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+  int32_t* level_g = static_cast<int32_t*>(workspace);
+  Kept K{level_g + n_states_raw, level_g + n_states_raw + n_arcs_raw, level_g + n_states_raw + 2 * n_arcs_raw};
+  int32_t* stats = out->lattice_stats;
+  RawArcs R{raw_src, raw_dst, raw_label, raw_state_off, raw_arc_off, src_is_global, start_state};
+  PACK_CUDA_OK(cudaMemsetAsync(out->totals, 0, 8 * sizeof(int32_t), st));
+  if (smem > 48 * 1024) {
+    PACK_CUDA_OK(cudaFuncSetAttribute(pack_level_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    PACK_CUDA_OK(cudaFuncSetAttribute(pack_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  }
+  pack_level_kernel<<<n_lattices, kThreads, level_smem(max_states, max_arcs), st>>>(R, max_states, max_arcs, level_g, K, stats, out->totals);
+  pack_scan_kernel<<<1, kThreads, 0, st>>>(n_lattices, stats, out->state_off, out->arc_off, out->level_off, out->sink_off,
+                                          out->n_levels, out->totals);
+  pack_build_kernel<<<n_lattices, kThreads, build_smem(max_states, max_arcs), st>>>(R, max_states, max_arcs, level_g, K, *out,
+                                                                                  out->totals);
+  PACK_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+}  // extern "C"

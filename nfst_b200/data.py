@@ -38,7 +38,7 @@ def _group_fields(g: LaunchGroup):
     return {k: v for k, v in g.__dict__.items() if not isinstance(v, torch.Tensor) and v is not None}
 
 
-def save_packed(path: str, packed: PackedLattices) -> None:
+def save_packed(path: str, packed: PackedLattices, compress: bool = False) -> None:
     """Write a packed batch (usually one example) as an ``.npz``: every array of ``PackedLattices`` plus the
     per-lattice statistics the launch groups are rebuilt from."""
     arrays = {"__format__": np.array([PACKED_FORMAT]), "__scalars__": np.array(
@@ -50,7 +50,7 @@ def save_packed(path: str, packed: PackedLattices) -> None:
     if packed.dense_shape is not None:
         arrays["__dense_shape__"] = np.array(packed.dense_shape, dtype=np.int64)
     tmp = path + ".tmp.npz"
-    np.savez(tmp, **arrays)
+    (np.savez_compressed if compress else np.savez)(tmp, **arrays)
     os.replace(tmp, path)
 
 

@@ -558,6 +558,23 @@ def pack_arcs(
     if label.numel() and (int(label.min()) < 0 or int(label.max()) >= vocab):
         raise ValueError("label out of range")
 
+    # ---- small lattices on a GPU: the library's device packer (nfst_pack.cu) ----
+    if DEVICE_PACK and dev.type == "cuda" and sell is None and tiles is None and src.numel():
+        cnt = torch.bincount(arc_lattice, minlength=B)
+        head = torch.stack([n_states.max(), cnt.max()]).cpu()
+        smax, amax = int(head[0]), int(head[1])
+        if smax <= 65535 and B * smax * vocab < 2**62:
+            perm = torch.argsort((arc_lattice * smax + src.to(torch.int64)) * vocab + label, stable=True)  # (lattice, source, label)
+            i32c = lambda t: t[perm].to(torch.int32).contiguous()  # noqa: E731
+            packed = pack_small_device(so.to(torch.int32), _excl_cumsum(cnt).to(torch.int32), i32c(src), i32c(dst), i32c(label),
+                                       vocab, src_is_global=False, max_states=smax, max_arcs=amax, start_state=start_state,
+                                       dense_shape=dense_shape)
+            if packed is not None:
+                packed.arc_origin = perm[packed.arc_origin].contiguous()
+                if static_scores is not None:
+                    packed.static_scores = static_scores[packed.arc_origin].to(torch.float32).contiguous()
+                return packed
+
     # ---- levels = longest distance from the start state; -1 = unreachable (trimmed) ----
     level = torch.full((S0,), -1, dtype=torch.int64, device=dev)
     level[so[:-1] + start_state] = 0
@@ -825,6 +842,28 @@ def pack_arcs(
     )
 
 
+def _dense_arcs_cuda(transition: torch.Tensor):
+    """(row, label, dst) int32 in scan order plus row_start int64 [B*S + 1], through the library's kernels."""
+    B, S, V = transition.shape
+    lib = _lib.load()
+    tr = transition.to(torch.int64).contiguous()
+    n_rows = B * S
+    counts = torch.empty(n_rows, dtype=torch.int32, device=tr.device)
+    st = torch.cuda.current_stream(tr.device).cuda_stream
+    with torch.cuda.device(tr.device):
+        _lib.check(lib.nfst_dense_count_arcs(tr.data_ptr(), n_rows, S, V, counts.data_ptr(), st))
+        row_start = _excl_cumsum(counts.to(torch.int64))
+        lat_off = row_start[::S]  # [B + 1]: raw arcs before lattice b
+        head = torch.stack([row_start[-1], (lat_off[1:] - lat_off[:-1]).max()]).cpu()  # the one sync: sizes
+        A0, max_arcs = int(head[0]), int(head[1])
+        row = torch.empty(A0, dtype=torch.int32, device=tr.device)
+        lab = torch.empty(A0, dtype=torch.int32, device=tr.device)
+        dst = torch.empty(A0, dtype=torch.int32, device=tr.device)
+        _lib.check(lib.nfst_dense_extract_arcs(tr.data_ptr(), n_rows, S, V, row_start.data_ptr(), row.data_ptr(),
+                                               lab.data_ptr(), dst.data_ptr(), st))
+    return row, lab, dst, lat_off, max_arcs
+
+
 def dense_arcs(transition: torch.Tensor):
     """Apply the reference's edge rule (``scorers.py:704-716``) to ``transition[B, S, V]``.
 
@@ -836,25 +875,123 @@ def dense_arcs(transition: torch.Tensor):
         raise ValueError("transition must be [B, S, V]")  # scorers.py:878-879
     B, S, V = transition.shape
     if transition.device.type == "cuda":
-        lib = _lib.load()
-        tr = transition.to(torch.int64).contiguous()
-        n_rows = B * S
-        counts = torch.empty(n_rows, dtype=torch.int32, device=tr.device)
-        st = torch.cuda.current_stream(tr.device).cuda_stream
-        with torch.cuda.device(tr.device):
-            _lib.check(lib.nfst_dense_count_arcs(tr.data_ptr(), n_rows, S, V, counts.data_ptr(), st))
-            row_start = _excl_cumsum(counts.to(torch.int64))
-            A0 = int(row_start[-1])
-            row = torch.empty(A0, dtype=torch.int32, device=tr.device)
-            lab = torch.empty(A0, dtype=torch.int32, device=tr.device)
-            dst = torch.empty(A0, dtype=torch.int32, device=tr.device)
-            _lib.check(lib.nfst_dense_extract_arcs(tr.data_ptr(), n_rows, S, V, row_start.data_ptr(), row.data_ptr(),
-                                                   lab.data_ptr(), dst.data_ptr(), st))
+        row, lab, dst, _, _ = _dense_arcs_cuda(transition)
         return row.to(torch.int64), lab.to(torch.int64), dst.to(torch.int64)
     rows = torch.arange(S, device=transition.device).view(1, S, 1)
     keep = (transition != 0) & (transition != rows)
     b, s, l = torch.nonzero(keep, as_tuple=True)
     return b * S + s, l, transition[b, s, l].to(torch.int64)
+
+
+# pack small lattices on the device (nfst_pack.cu) instead of with the tensor-op packer below
+DEVICE_PACK = int(os.environ.get("NFST_DEVICE_PACK", "1"))
+launch_count = 0  # launches of the library's own pack kernels (diagnostics)
+
+
+def pack_small_device(raw_state_off: torch.Tensor, raw_arc_off: torch.Tensor, src: torch.Tensor, dst: torch.Tensor,
+                      label: torch.Tensor, vocab: int, *, src_is_global: bool, max_states: int, max_arcs: int,
+                      start_state: int = 0, dense_shape=None) -> Optional[PackedLattices]:
+    """Pack a batch of small lattices with the library's device packer (``nfst_pack_small``: three launches, one
+    host read of the sizes).  ``src / dst / label``: int32 raw arcs grouped by lattice and sorted by (source,
+    label) -- the scan order of the dense tables; ``dst`` local ids, ``src`` local or (``src_is_global``) global
+    rows.  Returns None when the batch is not one for this packer (a lattice too large for one SM's shared
+    memory, or one that would not run on the small-lattice kernels): the caller then uses the tensor-op packer.
+    ``arc_origin`` of the result indexes the raw arc list.  Raises ``ValueError`` for cyclic lattices and
+    out-of-range arcs, like ``pack_arcs``."""
+    global launch_count
+    lib = _lib.load()
+    dev = src.device
+    B = int(raw_state_off.numel()) - 1
+    if max_states > 65535:
+        return None
+    # max_arcs bounds the arcs a lattice KEEPS (the raw list may be far longer: collate() padding adds V arcs per pad
+    # row, all unreachable); shared memory caps it -- a lattice that keeps more makes the pack return None
+    max_arcs = min(int(max_arcs), 65535, (200 * 1024 - 32 * int(max_states) - 64) // 8)
+    if max_arcs < 256:
+        return None
+    S0, A0 = int(max_states) * B if dense_shape is not None else None, int(src.numel())
+    if S0 is None:
+        S0 = int(raw_state_off[-1])
+    i32 = dict(dtype=torch.int32, device=dev)
+    o = {
+        "state_off": torch.empty(B + 1, **i32), "arc_off": torch.empty(B + 1, **i32), "level_off": torch.empty(B + 1, **i32),
+        "sink_off": torch.empty(B + 1, **i32), "n_levels": torch.empty(B, **i32), "start_state": torch.empty(B, **i32),
+        "level_ptr": torch.empty(S0 + B + 4, **i32), "sinks": torch.empty(S0 + 4, **i32), "orig_state": torch.empty(S0 + 4, **i32),
+        "in_ptr": torch.zeros(S0 + 1 + PackedLattices.PAD, **i32), "out_ptr": torch.zeros(S0 + 1 + PackedLattices.PAD, **i32),
+        "src_in": torch.zeros(A0 + PackedLattices.PAD, **i32), "label_in": torch.zeros(A0 + PackedLattices.PAD, **i32),
+        "in2out": torch.zeros(A0 + PackedLattices.PAD, **i32), "dst_out": torch.zeros(A0 + PackedLattices.PAD, **i32),
+        "label_out": torch.zeros(A0 + PackedLattices.PAD, **i32), "src_out": torch.empty(A0 + 4, **i32),
+        "arc_origin": torch.empty(A0 + 4, dtype=torch.int64, device=dev),
+        "lattice_stats": torch.zeros(B * 8 + 8, **i32),  # ... and the totals behind them: one host read
+    }
+    o["totals"] = o["lattice_stats"][B * 8:]
+    out = _lib.PackOutC()
+    for k, t in o.items():
+        setattr(out, k, t.data_ptr())
+    ws_bytes = int(lib.nfst_pack_small_workspace_bytes(S0, A0))
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    st = torch.cuda.current_stream(dev).cuda_stream
+    with torch.cuda.device(dev):
+        _lib.check(lib.nfst_pack_small(B, raw_state_off.data_ptr(), raw_arc_off.data_ptr(), src.data_ptr(), dst.data_ptr(),
+                                       label.data_ptr(), int(src_is_global), int(start_state), int(max_states), int(max_arcs),
+                                       C.byref(out), ws.data_ptr(), ws_bytes, S0, A0, st))
+    launch_count += 3
+    host = o["lattice_stats"].cpu()  # the pack's host synchronisation
+    totals, per = host[B * 8:].tolist(), host[:B * 8].view(B, 8).to(torch.int64)
+    if totals[4] == 1:
+        raise ValueError(f"lattice is cyclic: the DP is defined for acyclic lattices only (lattice {totals[5]})")
+    if totals[4] == 2:
+        raise ValueError(f"arc endpoint out of range (lattice {totals[5]})")
+    if totals[4] == 4:
+        return None  # a lattice keeps more arcs than one SM's shared memory holds
+    if totals[4]:
+        raise ValueError("batch too large for int32 indices; shard it")
+    S, A, n_lp, n_sink = totals[0], totals[1], totals[2], totals[3]
+    width_arcs = per[:, 4]
+    bmax = int(math.log2(BLOCK_MAX))
+    block_class = torch.clamp(torch.ceil(torch.log2(torch.clamp(width_arcs.to(torch.float64) / ARCS_PER_THREAD, min=32.0))), 5, bmax).to(torch.int64)
+    zeros = torch.zeros(B, dtype=torch.int64)
+    stats = {
+        "width_arcs": width_arcs, "arcs": per[:, 1].clone(), "states": per[:, 0].clone(), "levels": per[:, 2].clone(),
+        "block_class": block_class, "vocab": torch.full((B,), int(vocab), dtype=torch.int64),
+        "chunk_cap": torch.tensor([chunk_geometry(1 << int(k))[2] for k in block_class.tolist()], dtype=torch.int64),
+        "reach": per[:, 0].clone(), "sell": torch.zeros(B, dtype=torch.bool), "sell_bound": zeros, "sell_window": zeros + 32,
+        "sell_block": zeros + 2, "tile": torch.zeros(B, dtype=torch.bool), "tile_warps_log2": zeros, "tile_ring": zeros,
+        "tile_far": zeros, "tile_cap_arcs": zeros, "tile_cap_bytes": zeros,
+    }
+    foot = small_footprint_bytes(stats["states"], stats["arcs"], stats["levels"], int(vocab))
+    other = (foot > SMALL_SMEM_BYTES) | (width_arcs >= LEVEL_MODE_MIN_ARCS)
+    if tiles_mod.TILES:
+        other |= stats["states"] >= tiles_mod.TILE_MIN_WIDTH * stats["levels"]
+    if SELL:
+        other |= stats["states"] >= SELL_MIN_WIDTH * stats["levels"]
+    if bool(other.any()):
+        return None  # some lattice belongs on the chunked / column-major kernels: those layouts come from pack_arcs
+    groups = build_groups(stats, dev)
+
+    def view(name, n):
+        t = o[name][:n]
+        t._nfst_padded = name in PackedLattices._ARC_FIELDS  # allocated with PAD zeroed elements behind the view
+        return t
+
+    e32 = torch.zeros(0, **i32)
+    out_deg = o["out_ptr"][1:S + 1] - o["out_ptr"][:S]
+    return PackedLattices(
+        n_lattices=B, n_states=S, n_arcs=A, vocab=int(vocab),
+        state_off=o["state_off"], level_off=o["level_off"], level_ptr=view("level_ptr", n_lp), start_state=o["start_state"],
+        sink_off=o["sink_off"], sinks=view("sinks", n_sink), in_ptr=view("in_ptr", S + 1), src_in=view("src_in", A),
+        label_in=view("label_in", A), in2out=view("in2out", A), out_ptr=view("out_ptr", S + 1), dst_out=view("dst_out", A),
+        label_out=view("label_out", A),
+        fwd_chunk_off=torch.zeros(B + 1, **i32), fwd_chunks=torch.zeros((0, 4), **i32), bwd_chunk_off=torch.zeros(B + 1, **i32),
+        bwd_chunks=torch.zeros((0, 4), **i32), fwd_gather=torch.zeros((0, 2), **i32), fwd_chunk_level=e32, bwd_chunk_level=e32,
+        bwd_order=e32, sell_desc=torch.zeros((0, 4), **i32), sell_lvl_slice=torch.zeros(n_lp, **i32),
+        tile_stream=torch.zeros(16, dtype=torch.uint8, device=dev), tile_tab=torch.zeros((0, 4), **i32),
+        tile_lw_off=torch.zeros(1, **i32), tile_lat_info=torch.zeros((B, 4), **i32), out_arc=e32,
+        lanes_in_log2=torch.zeros(B, dtype=torch.uint8, device=dev), lanes_out_log2=torch.zeros(B, dtype=torch.uint8, device=dev),
+        out_deg8=torch.clamp(out_deg, max=255).to(torch.uint8), src_out=view("src_out", A), orig_state=view("orig_state", S),
+        arc_origin=view("arc_origin", A), arc_off=o["arc_off"], n_levels=o["n_levels"], static_scores=None,
+        dense_shape=dense_shape, groups=groups, max_levels=int(totals[6]), stats=stats,
+    )
 
 
 def pack_dense(emission: Optional[torch.Tensor], transition: torch.Tensor, *,
@@ -867,11 +1004,29 @@ def pack_dense(emission: Optional[torch.Tensor], transition: torch.Tensor, *,
     if transition.dim() != 3 or (emission is not None and emission.shape != transition.shape):
         raise ValueError("emission and transition must both be [B, S, V]")
     B, S, V = transition.shape
-    row, lab, dst = dense_arcs(transition)
-    if dst.numel() and int(dst.max()) >= S:
-        raise ValueError("transition points outside the table")
     if weighted is None:
         weighted = emission is not None and emission.is_floating_point()
+    if transition.device.type == "cuda" and DEVICE_PACK and B * S < 2**31 and (sell is None and tiles is None):
+        # device packer (nfst_pack.cu): the tables are scanned, levelled and laid out in a handful of launches
+        row32, lab32, dst32, lat_off, max_arcs = _dense_arcs_cuda(transition)
+        if row32.numel() < 2**31:
+            raw_state_off = torch.arange(B + 1, dtype=torch.int32, device=transition.device) * S
+            try:
+                packed = pack_small_device(raw_state_off, lat_off.to(torch.int32), row32, dst32, lab32, V, src_is_global=True,
+                                           max_states=S, max_arcs=max_arcs, dense_shape=(B, S, V))
+            except ValueError as e:
+                raise ValueError("transition points outside the table" if "out of range" in str(e) else str(e)) from None
+            if packed is not None:
+                cell = (row32.to(torch.int64) * V + lab32.to(torch.int64))[packed.arc_origin]  # (b*S+s)*V+l of each arc
+                if weighted:
+                    packed.static_scores = emission.reshape(-1)[cell].to(torch.float32).contiguous()
+                packed.arc_origin = cell.contiguous()
+                return packed
+        row, lab, dst = row32.to(torch.int64), lab32.to(torch.int64), dst32.to(torch.int64)
+    else:
+        row, lab, dst = dense_arcs(transition)
+    if dst.numel() and int(dst.max()) >= S:
+        raise ValueError("transition points outside the table")
     static = None
     if weighted:
         static = emission.reshape(-1)[row * V + lab].to(torch.float32)

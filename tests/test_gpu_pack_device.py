@@ -1,0 +1,159 @@
+"""The device packer (nfst_pack.cu: nfst_pack_small) against the tensor-op packer and the oracle.
+
+Structure: the packed arrays describe the same lattice (arc_origin / orig_state are permutations onto the kept
+arcs / states, CSR by source is in (state, label) order, CSR by destination in (state, canonical id) order, states
+are numbered by level and every arc goes to a deeper level, the rows collate() padding adds are trimmed).
+Results: beta / logZ / posteriors / Viterbi of the device-packed batch meet the same bounds against the C oracle as
+everything else, and equal the tensor-op packer's results in the original numbering.
+"""
+import numpy as np
+import pytest
+import torch
+
+import nfst_b200 as nb
+from nfst_b200 import pack as P
+from nfst_b200 import synth
+from oracle import c_oracle
+from tests.lattice_gen import random_mark_lattice
+
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(300)]
+DEV = "cuda:0"
+
+
+def _np(t):
+    return t.cpu().numpy().astype(np.int64)
+
+
+def check_structure(p: nb.PackedLattices, n_raw_arcs: int):
+    S, A, B = p.n_states, p.n_arcs, p.n_lattices
+    state_off, arc_off, level_off, level_ptr = _np(p.state_off), _np(p.arc_off), _np(p.level_off), _np(p.level_ptr)
+    out_ptr, in_ptr, dst, lab, src_out = _np(p.out_ptr), _np(p.in_ptr), _np(p.dst_out), _np(p.label_out), _np(p.src_out)
+    src_in, lab_in, in2out = _np(p.src_in), _np(p.label_in), _np(p.in2out)
+    assert state_off[0] == 0 and state_off[-1] == S and arc_off[-1] == A and out_ptr[S] == A and in_ptr[S] == A
+    assert len(level_ptr) == level_off[-1]
+    level_of = np.full(S, -1)
+    for b in range(B):
+        lp = level_ptr[level_off[b]:level_off[b + 1]]
+        assert lp[0] == state_off[b] and lp[-1] == state_off[b + 1] and np.all(np.diff(lp) > 0)
+        assert len(lp) - 1 == int(p.n_levels[b])
+        for l in range(len(lp) - 1):
+            level_of[lp[l]:lp[l + 1]] = l
+        assert int(p.start_state[b]) == state_off[b], "the start state is the only state of level 0"
+        assert np.all(out_ptr[state_off[b]:state_off[b + 1] + 1] >= arc_off[b]) and out_ptr[state_off[b + 1]] == arc_off[b + 1]
+    # CSR by source, (state, label) order; every arc goes to a deeper level of the same lattice
+    np.testing.assert_array_equal(src_out, np.repeat(np.arange(S), np.diff(out_ptr)))
+    assert np.all(level_of[dst] > level_of[src_out])
+    same = src_out[1:] == src_out[:-1]
+    assert np.all(lab[1:][same] >= lab[:-1][same])
+    # CSR by destination, (state, canonical id) order
+    np.testing.assert_array_equal(dst[in2out], np.repeat(np.arange(S), np.diff(in_ptr)))
+    np.testing.assert_array_equal(src_in, src_out[in2out])
+    np.testing.assert_array_equal(lab_in, lab[in2out])
+    d_in = dst[in2out]
+    same = d_in[1:] == d_in[:-1]
+    assert np.all(in2out[1:][same] > in2out[:-1][same])
+    assert sorted(in2out.tolist()) == list(range(A))
+    # sinks
+    sinks, sink_off = _np(p.sinks), _np(p.sink_off)
+    np.testing.assert_array_equal(sinks, np.nonzero(np.diff(out_ptr) == 0)[0])
+    assert sink_off[-1] == len(sinks)
+    origin = _np(p.arc_origin)
+    assert len(set(origin.tolist())) == A and origin.min() >= 0 and origin.max() < n_raw_arcs
+
+
+def results_in_original_numbering(ab, p, sc):
+    logz, alpha, beta, post = nb.lattice_forward_backward(p, arc_scores=sc)
+    score, off, arcs, labels = nb.lattice_viterbi(p, arc_scores=sc)
+    torch.cuda.synchronize()
+    so = np.concatenate([[0], np.cumsum(ab.n_states.cpu().numpy())])
+    lat = np.repeat(np.arange(p.n_lattices), np.diff(_np(p.state_off)))
+    g2o = so[lat] + _np(p.orig_state)
+    beta_o = np.full(int(so[-1]), np.nan)
+    beta_o[g2o] = beta.cpu().numpy()
+    post_o = np.zeros(ab.src.numel())
+    post_o[_np(p.arc_origin)] = post.cpu().numpy()
+    offc, lab = _np(off), _np(labels)
+    return logz.cpu().numpy(), beta_o, post_o, score.cpu().numpy(), [lab[offc[b]:offc[b + 1]].tolist() for b in range(p.n_lattices)]
+
+
+@pytest.mark.parametrize("gen", ["translit32", "snips8", "dag_small", "translit_ties"])
+def test_device_packer_matches_tensor_op_packer_and_oracle(gen, monkeypatch):
+    ab = {"translit32": lambda: synth.transliteration_batch(32, seed=0), "snips8": lambda: synth.snips_batch(8, seed=1),
+          "dag_small": lambda: synth.random_dag_batch(5, 3000, levels=40, seed=4),  # 19 states per level: not a tile-stream lattice
+          "translit_ties": lambda: synth.transliteration_batch(16, seed=4, integer_scores=True)}[gen]()
+    abd = ab.to(DEV)
+    before = P.launch_count
+    p_dev, sc_dev = abd.pack()
+    assert P.launch_count == before + 3, "the device packer ran"
+    assert all(g.small_max_arcs > 0 for g in p_dev.groups)
+    check_structure(p_dev, ab.src.numel())
+    monkeypatch.setattr(P, "DEVICE_PACK", 0)
+    p_ref, sc_ref = abd.pack()
+    assert P.launch_count == before + 3
+    assert (p_dev.n_states, p_dev.n_arcs, p_dev.max_levels) == (p_ref.n_states, p_ref.n_arcs, p_ref.max_levels)
+    np.testing.assert_array_equal(_np(p_dev.n_levels), _np(p_ref.n_levels))
+    r_dev = results_in_original_numbering(ab, p_dev, sc_dev)
+    r_ref = results_in_original_numbering(ab, p_ref, sc_ref)
+    np.testing.assert_allclose(r_dev[0], r_ref[0], rtol=2e-6, atol=2e-6)
+    np.testing.assert_allclose(r_dev[1], r_ref[1], rtol=2e-6, atol=2e-6)  # NaN = trimmed, in the same places
+    np.testing.assert_allclose(r_dev[2], r_ref[2], rtol=2e-5, atol=1e-7)
+    assert np.array_equal(r_dev[3].view(np.uint32), r_ref[3].view(np.uint32)) and r_dev[4] == r_ref[4], "Viterbi is bit-exact"
+    ob = c_oracle.Batch(ab.arc_lattice.numpy(), ab.src.numpy(), ab.dst.numpy(), ab.label.numpy(), ab.scores.numpy(), ab.n_states.numpy())
+    o_logz, _, o_beta, o_post = c_oracle.forward_backward(ob)
+    o_score, _, o_labels = c_oracle.viterbi(ob)
+    np.testing.assert_allclose(r_dev[0], o_logz, rtol=1e-5, atol=1e-5)
+    assert np.all(np.abs(r_dev[2] - o_post) <= 1e-5 * o_post + 1e-7)
+    assert np.array_equal(r_dev[3].view(np.uint32), o_score.view(np.uint32))
+    assert r_dev[4] == [list(x) for x in o_labels]
+
+
+def test_device_packer_dense_tables_trim_padding_and_unreachable_rows(monkeypatch):
+    rng = np.random.default_rng(3)
+    tabs, S = [], 0
+    for i in range(6):
+        em, tr = random_mark_lattice(rng, 6 + 5 * i, 24)  # state ids shuffled: not topological
+        tabs.append(tr)
+        S = max(S, tr.shape[0])
+    V = tabs[0].shape[1]
+    from tests.lattice_gen import PAD
+    batch = np.full((len(tabs), S + 2, V), PAD, dtype=np.int64)  # collate(): pad rows hold the pad id everywhere (quirk Q5)
+    for i, t in enumerate(tabs):
+        batch[i, :t.shape[0]] = t
+    tr = torch.from_numpy(batch).to(DEV)
+    before = P.launch_count
+    p = nb.pack_dense(tr != 0, tr)
+    assert P.launch_count == before + 3
+    row, lab, dst = P.dense_arcs(tr)
+    check_structure(p, 10**12)
+    # arc_origin holds dense cell indices of real arcs; the pad rows' arcs are gone
+    cells = _np(p.arc_origin)
+    b, rem = cells // ((S + 2) * V), cells % ((S + 2) * V)
+    s, l = rem // V, rem % V
+    for i, t in enumerate(tabs):
+        assert np.all(s[b == i] < t.shape[0])
+    np.testing.assert_array_equal(batch[b, s, l], _np(p.orig_state)[_np(p.dst_out)])
+    np.testing.assert_array_equal(l, _np(p.label_out))
+    theta = torch.randn(V, device=DEV)
+    beta = nb.compute_beta(tr != 0, tr, theta, k=1)
+    monkeypatch.setattr(P, "DEVICE_PACK", 0)
+    beta_ref = nb.compute_beta(tr != 0, tr, theta, k=1)
+    assert P.launch_count == before + 6
+    torch.testing.assert_close(beta, beta_ref, rtol=2e-6, atol=0)
+
+
+def test_device_packer_rejects_cycles_and_bad_endpoints():
+    lat = torch.zeros(3, dtype=torch.int64, device=DEV)
+    src, dst = torch.tensor([0, 1, 2], device=DEV), torch.tensor([1, 2, 1], device=DEV)
+    lab = torch.tensor([4, 5, 6], device=DEV)
+    with pytest.raises(ValueError, match="cyclic"):
+        nb.pack_arcs(lat, src, dst, lab, torch.tensor([3]), 16)
+    tr = torch.zeros((1, 3, 8), dtype=torch.int64, device=DEV)
+    tr[0, 0, 4] = 7  # points outside the table
+    with pytest.raises(ValueError, match="outside the table|out of range"):
+        nb.pack_dense(tr != 0, tr)
+
+
+def test_device_packer_falls_back_for_wide_lattices():
+    before = P.launch_count
+    p, _ = synth.random_dag_batch(2, 60_000, levels=16, seed=1, device=DEV).pack()
+    assert p.has_tiles and P.launch_count == before, "wide lattices keep the column-major layouts of the tensor-op packer"
