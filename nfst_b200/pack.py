@@ -984,7 +984,7 @@ def pack_small_device(raw_state_off: torch.Tensor, raw_arc_off: torch.Tensor, sr
         label_out=view("label_out", A),
         fwd_chunk_off=torch.zeros(B + 1, **i32), fwd_chunks=torch.zeros((0, 4), **i32), bwd_chunk_off=torch.zeros(B + 1, **i32),
         bwd_chunks=torch.zeros((0, 4), **i32), fwd_gather=torch.zeros((0, 2), **i32), fwd_chunk_level=e32, bwd_chunk_level=e32,
-        bwd_order=e32, sell_desc=torch.zeros((0, 4), **i32), sell_lvl_slice=torch.zeros(n_lp, **i32),
+        bwd_order=torch.arange(S, **i32), sell_desc=torch.zeros((0, 4), **i32), sell_lvl_slice=torch.zeros(n_lp, **i32),
         tile_stream=torch.zeros(16, dtype=torch.uint8, device=dev), tile_tab=torch.zeros((0, 4), **i32),
         tile_lw_off=torch.zeros(1, **i32), tile_lat_info=torch.zeros((B, 4), **i32), out_arc=e32,
         lanes_in_log2=torch.zeros(B, dtype=torch.uint8, device=dev), lanes_out_log2=torch.zeros(B, dtype=torch.uint8, device=dev),
