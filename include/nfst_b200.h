@@ -35,6 +35,9 @@
  *                           (scorers.py:704-716, :764-776: adjacency lists from the dense table) plus the
  *                           topological ordering the reference does implicitly with its message counters
  *                           (:741-749); trims the rows collate() padding adds (util/dataset_reader.py:175-186).
+ *   nfst_edit_lattice_arcs  the offline lattice construction x o T o y + mark expansion for the transliteration edit
+ *                           machine (src/preprocess/tr.py:142-190, src/fsm/tr.py:321-390,
+ *                           src/modules/path_semiring.py:120-180), emitted on the device from id strings.
  *   nfst_dense_count_arcs / nfst_dense_extract_arcs
  *                           the dense-table edge rule `t != 0 and t != i`
  *                           (scorers.py:704-716, :764-776) over collate()-padded
@@ -470,6 +473,22 @@ int nfst_pack_small(int32_t n_lattices, const int32_t* raw_state_off, const int3
                     const int32_t* raw_dst, const int32_t* raw_label, int32_t src_is_global, int32_t start_state,
                     int32_t max_states, int32_t max_arcs, const nfst_pack_out_t* out, void* workspace, size_t workspace_bytes,
                     int64_t n_states_raw, int64_t n_arcs_raw, void* cuda_stream);
+
+/*
+ * On-device construction of the transliteration lattices (what src/preprocess/tr.py:142-190 builds offline with
+ * OpenFst: x o T o y for the one-state edit machine of src/fsm/tr.py:321-390, every arc expanded into the chain
+ * of its marks, src/modules/path_semiring.py:120-180, bos in front and eos behind).  Writes the arc list of B
+ * lattices from the id strings x[B][x_stride] / y[B][y_stride] (lengths x_len / y_len): grouped by lattice at
+ * raw_arc_off[b], sorted by (source, label) -- the input nfst_pack_small takes (local source ids).  State
+ * numbering: 0 = start, then the (|x|+1) x (|y|+1) grid row-major, the intermediate states of the deletion /
+ * insertion / substitution chains, the sink last.  Marks: deletion [input_mark, x_i], insertion
+ * [output_mark, y_j], substitution (add_sub) [sub_mark, input_mark, x_i, output_mark, y_j].
+ */
+void nfst_edit_lattice_size(int32_t n, int32_t m, int32_t add_sub, int64_t* n_states, int64_t* n_arcs);
+int nfst_edit_lattice_arcs(int32_t n_lattices, const int32_t* x, const int32_t* x_len, int32_t x_stride, const int32_t* y,
+                           const int32_t* y_len, int32_t y_stride, int32_t bos, int32_t eos, int32_t input_mark,
+                           int32_t output_mark, int32_t sub_mark, int32_t add_sub, const int32_t* raw_arc_off, int32_t* src,
+                           int32_t* dst, int32_t* label, void* cuda_stream);
 
 #ifdef __cplusplus
 }

@@ -23,5 +23,7 @@ from .ops import (  # noqa: F401
 from .sampler import LatticeWalker, sample_paths, stripping_pad, walk_step  # noqa: F401
 from .joint import ExactJointProb  # noqa: F401
 from . import data  # noqa: F401
+from . import construct  # noqa: F401
+from .construct import edit_lattices  # noqa: F401
 
 __version__ = "0.1.0"

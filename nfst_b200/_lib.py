@@ -134,6 +134,8 @@ SYMBOLS = {
     "nfst_pack_small_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int64]),
     "nfst_pack_small": (C.c_int, [C.c_int32, _P, _P, _P, _P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(PackOutC), _P,
                                   C.c_size_t, C.c_int64, C.c_int64, _P]),
+    "nfst_edit_lattice_size": (None, [C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "nfst_edit_lattice_arcs": (C.c_int, [C.c_int32, _P, _P, C.c_int32, _P, _P, C.c_int32] + [C.c_int32] * 6 + [_P, _P, _P, _P, _P]),
     "nfst_dense_count_arcs": (C.c_int, [_P, C.c_int64, C.c_int32, C.c_int32, _P, _P]),
     "nfst_dense_extract_arcs": (C.c_int, [_P, C.c_int64, C.c_int32, C.c_int32, _P, _P, _P, _P, _P]),
 }

@@ -479,3 +479,108 @@ int nfst_pack_small(int32_t n_lattices, const int32_t* raw_state_off, const int3
 }
 
 }  // extern "C"
+
+// =========================================================================================================
+// On-device construction of the transliteration lattices
+// =========================================================================================================
+// What the reference does offline with OpenFst for every training pair (src/preprocess/tr.py:142-190:
+// x o T o y, then OwnAST.mfst_weight_projection, src/modules/path_semiring.py:120-180, which replaces every arc
+// by the chain of its marks): T is the one-state edit machine of src/fsm/tr.py:321-390 --
+//   insertion of y_j        marks [output-mark, y_j]
+//   deletion of x_i         marks [input-mark, x_i]
+//   substitution x_i : y_j  marks [insertion-mark, input-mark, x_i, output-mark, y_j]   (add_sub)
+// -- so x o T o y is the (|x|+1) x (|y|+1) edit grid and the mark lattice is that grid with every arc expanded
+// into a chain, plus the bos arc in front and the eos arc behind (Preprocess.composed_to_matrices,
+// src/preprocess/preprocess.py:51-174).  This kernel writes that lattice's arc list straight from the id
+// strings, grouped by lattice and sorted by (source, label) -- the input format of nfst_pack_small.
+// (The reference additionally runs pynini's optimize(); that renumbers and may merge states but keeps the set
+// of mark strings, which is all the dynamic programme sees.)
+namespace {
+
+struct EditMarks {
+  int bos, eos, input_mark, output_mark, sub_mark;
+  int rank_del, rank_ins, rank_sub;  // position of each edit's first arc among a grid state's arcs (label order)
+  int add_sub;
+};
+
+__global__ void __launch_bounds__(kThreads)
+    edit_arcs_kernel(const int32_t* __restrict__ x, const int32_t* __restrict__ x_len, int x_stride,
+                     const int32_t* __restrict__ y, const int32_t* __restrict__ y_len, int y_stride, const EditMarks M,
+                     const int32_t* __restrict__ arc_off, int32_t* __restrict__ src, int32_t* __restrict__ dst,
+                     int32_t* __restrict__ label) {
+  const int b = blockIdx.x;
+  const int n = x_len[b], m = y_len[b];
+  const int32_t* xs = x + static_cast<size_t>(b) * x_stride;
+  const int32_t* ys = y + static_cast<size_t>(b) * y_stride;
+  const int c = 2 + (M.add_sub ? 1 : 0);  // arcs of an interior grid state
+  const int G = (n + 1) * (m + 1);
+  const int id_del = 1 + G, id_ins = id_del + n * (m + 1), id_sub = id_ins + (n + 1) * m;
+  const int sink = id_sub + (M.add_sub ? 4 * n * m : 0);
+  const int a_grid = 1, a_del = a_grid + n * (c * m + 1) + m + 1, a_ins = a_del + n * (m + 1), a_sub = a_ins + (n + 1) * m;
+  const int a0 = arc_off[b];
+  auto put = [&](int pos, int s, int l, int d) {
+    src[a0 + pos] = s;
+    label[a0 + pos] = l;
+    dst[a0 + pos] = d;
+  };
+  auto grid = [&](int i, int j) { return 1 + i * (m + 1) + j; };
+  if (threadIdx.x == 0) put(0, 0, M.bos, grid(0, 0));
+  for (int cell = threadIdx.x; cell < G; cell += kThreads) {
+    const int i = cell / (m + 1), j = cell % (m + 1);
+    const int g = grid(i, j);
+    const bool can_del = i < n, can_ins = j < m, can_sub = M.add_sub && can_del && can_ins;
+    const int base = a_grid + (i < n ? i * (c * m + 1) + c * j : n * (c * m + 1) + j);
+    if (can_del && can_ins) {  // interior: all edits, in label order
+      put(base + M.rank_del, g, M.input_mark, id_del + i * (m + 1) + j);
+      put(base + M.rank_ins, g, M.output_mark, id_ins + i * m + j);
+      if (can_sub) put(base + M.rank_sub, g, M.sub_mark, id_sub + 4 * (i * m + j));
+    } else if (can_del) {
+      put(base, g, M.input_mark, id_del + i * (m + 1) + j);
+    } else if (can_ins) {
+      put(base, g, M.output_mark, id_ins + i * m + j);
+    } else {
+      put(base, g, M.eos, sink);
+    }
+    if (can_del) put(a_del + i * (m + 1) + j, id_del + i * (m + 1) + j, xs[i], grid(i + 1, j));
+    if (can_ins) put(a_ins + i * m + j, id_ins + i * m + j, ys[j], grid(i, j + 1));
+    if (can_sub) {
+      const int k = id_sub + 4 * (i * m + j), a = a_sub + 4 * (i * m + j);
+      put(a, k, M.input_mark, k + 1);
+      put(a + 1, k + 1, xs[i], k + 2);
+      put(a + 2, k + 2, M.output_mark, k + 3);
+      put(a + 3, k + 3, ys[j], grid(i + 1, j + 1));
+    }
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
+/* states and arcs of the lattice of one (|x|, |y|) pair */
+void nfst_edit_lattice_size(int32_t n, int32_t m, int32_t add_sub, int64_t* n_states, int64_t* n_arcs) {
+  const int64_t c = 2 + (add_sub ? 1 : 0), N = n, Mm = m;
+  if (n_states) *n_states = 1 + (N + 1) * (Mm + 1) + N * (Mm + 1) + (N + 1) * Mm + (add_sub ? 4 * N * Mm : 0) + 1;
+  if (n_arcs) *n_arcs = 1 + N * (c * Mm + 1) + Mm + 1 + N * (Mm + 1) + (N + 1) * Mm + (add_sub ? 4 * N * Mm : 0);
+}
+
+int nfst_edit_lattice_arcs(int32_t n_lattices, const int32_t* x, const int32_t* x_len, int32_t x_stride, const int32_t* y,
+                           const int32_t* y_len, int32_t y_stride, int32_t bos, int32_t eos, int32_t input_mark,
+                           int32_t output_mark, int32_t sub_mark, int32_t add_sub, const int32_t* raw_arc_off, int32_t* src,
+                           int32_t* dst, int32_t* label, void* cuda_stream) {
+  if (n_lattices <= 0 || !x || !x_len || !y || !y_len || !raw_arc_off || !src || !dst || !label)
+    return nfst_fail_msg(NFST_ERR_BAD_ARG, "nfst_edit_lattice_arcs: null argument or empty batch");
+  if (input_mark == output_mark || (add_sub && (sub_mark == input_mark || sub_mark == output_mark)))
+    return nfst_fail_msg(NFST_ERR_BAD_ARG, "nfst_edit_lattice_arcs: the edit marks must be distinct labels");
+  EditMarks M{bos, eos, input_mark, output_mark, sub_mark, 0, 0, 0, add_sub};
+  // order of a grid state's arcs = order of their labels (the scan order of the reference's dense tables)
+  M.rank_del = (output_mark < input_mark) + (add_sub && sub_mark < input_mark);
+  M.rank_ins = (input_mark < output_mark) + (add_sub && sub_mark < output_mark);
+  M.rank_sub = (input_mark < sub_mark) + (output_mark < sub_mark);
+  edit_arcs_kernel<<<n_lattices, kThreads, 0, static_cast<cudaStream_t>(cuda_stream)>>>(x, x_len, x_stride, y, y_len, y_stride, M,
+                                                                                     raw_arc_off, src, dst, label);
+  PACK_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+}  // extern "C"

@@ -906,9 +906,10 @@ def pack_small_device(raw_state_off: torch.Tensor, raw_arc_off: torch.Tensor, sr
         return None
     # max_arcs bounds the arcs a lattice KEEPS (the raw list may be far longer: collate() padding adds V arcs per pad
     # row, all unreachable); shared memory caps it -- a lattice that keeps more makes the pack return None
-    max_arcs = min(int(max_arcs), 65535, (200 * 1024 - 32 * int(max_states) - 64) // 8)
-    if max_arcs < 256:
+    room = (200 * 1024 - 32 * int(max_states) - 64) // 8
+    if room < 256:
         return None
+    max_arcs = max(min(int(max_arcs), 65535, room), 1)
     S0, A0 = int(max_states) * B if dense_shape is not None else None, int(src.numel())
     if S0 is None:
         S0 = int(raw_state_off[-1])
