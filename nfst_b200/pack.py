@@ -13,10 +13,17 @@ reference's scan order: state, then label) and by incoming state ("in" order), w
 states of each lattice renumbered by topological level so that a level is a contiguous
 range.  States that are unreachable from the start state (row 0, ``scorers.py:1005``) --
 which includes every row added by ``collate`` padding (quirk Q5) -- are trimmed; their
-beta is reported as 0, which is also what the batched reference leaves there.
+beta is reported as 0.  That equals the batched reference for the padding rows (no path to
+the sink: it leaves 0 there).  A REAL state that the start cannot reach but that can reach
+the sink is a documented difference: ``compute_beta_parallel`` runs its recurrence on every
+row and leaves a non-zero beta there, this package reports 0.  The sampler never reads such
+a state (it only gathers beta at successors of reachable states) and OpenFst's ``connect``
+removes them from the machines the reference builds, so the golden lattices have none.
 
-All work is torch tensor ops on whatever device the inputs live on (the dense-table scan
-uses the library's CUDA kernels for CUDA inputs); nothing here is on the per-step path.
+Two packers produce this layout: ``pack_small_device`` (the library's device packer,
+``nfst_pack.cu``: three launches, for lattices that fit one SM's shared memory -- the size
+nFST builds) and the tensor-op packer below (any size, any device; it also builds the chunk
+lists, the sliced-column descriptors and the tile stream of wide lattices).
 """
 from __future__ import annotations
 

@@ -471,6 +471,23 @@ def test_empty_and_ragged_batches():
     assert off.tolist()[1] == 0 and off.tolist()[3] - off.tolist()[2] == 2
 
 
+def test_state_unreachable_from_the_start_is_trimmed_documented_difference():
+    # a real state (row 4) that the start cannot reach but that reaches the sink: the reference's recurrence runs on
+    # every row and gives it a beta; this package trims what row 0 cannot reach and reports 0 (pack.py docstring).
+    # The reachable states are unaffected.
+    V = 16
+    tr = np.zeros((1, 6, V), dtype=np.int64)
+    tr[0, 0, 1] = 1; tr[0, 1, 7] = 2; tr[0, 1, 8] = 3; tr[0, 2, 9] = 3; tr[0, 3, 2] = 5
+    tr[0, 4, 10] = 3  # unreachable, co-reachable
+    tr[0, 5, 3] = 5  # sink: pad self-loop (no arc under the edge rule)
+    theta = torch.randn(V, generator=torch.Generator().manual_seed(0))
+    beta = nb.compute_beta(torch.from_numpy(tr != 0).to(DEV), torch.from_numpy(tr).to(DEV), theta.to(DEV), k=1)[0].cpu().numpy()
+    src, lab, dst, _ = lo.arcs_from_dense(tr[0])
+    ref = np.exp(lo.beta_log(6, src, dst, theta.numpy().astype(np.float64)[lab]))  # the recurrence on every row
+    np.testing.assert_allclose(beta[[0, 1, 2, 3, 5]], ref[[0, 1, 2, 3, 5]], rtol=1e-5)
+    assert ref[4] > 0 and beta[4] == 0.0
+
+
 # --------------------------------------------------------------------------------------
 # drop-in surface of the reference module (set_masks / set_k / compute_beta)
 # --------------------------------------------------------------------------------------
