@@ -56,7 +56,7 @@
 extern "C" {
 #endif
 
-#define NFST_ABI_VERSION 12
+#define NFST_ABI_VERSION 13
 
 typedef enum nfst_status {
   NFST_OK = 0,
@@ -217,13 +217,17 @@ typedef struct nfst_launch {
    * shared-memory stages filled by bulk copies (TMA) that complete on per-stage mbarriers.  tile_ring = largest
    * DP ring of the group in slots (ring + constant slot + far table), tile_cap_arcs / tile_cap_bytes = largest
    * tile of the group (arcs / stream bytes), tile_far = largest far table of the group (informational),
-   * tile_stages: 0 = chosen by the library from the shared memory the launch leaves per block. */
+   * tile_stages: 0 = chosen by the library from the shared memory the launch leaves per block.
+   * tile_flow_bits: width of the flow pass's fixed-point gamma accumulator -- 32 (or 0): 2^-31 units, posteriors
+   * carry an ABSOLUTE error below 1e-9 (relative 1e-5 down to posteriors of 1e-4); 64: 2^-62 units, the error is
+   * the float32 rounding of each contribution (relative ~1e-6 at any size), twice the ring's shared memory. */
   int32_t tiles;
   int32_t tile_ring;
   int32_t tile_far;
   int32_t tile_cap_arcs;
   int32_t tile_cap_bytes;
   int32_t tile_stages;
+  int32_t tile_flow_bits;
 } nfst_launch_t;
 
 /* Arc scores: w(a) = (arc_scores ? arc_scores[a] : 0) + (theta ? theta[label(a)] : 0);

@@ -81,6 +81,7 @@ class LaunchC(C.Structure):
         ("tile_cap_arcs", C.c_int32),
         ("tile_cap_bytes", C.c_int32),
         ("tile_stages", C.c_int32),
+        ("tile_flow_bits", C.c_int32),
     ]
 
 
@@ -163,7 +164,7 @@ def load() -> C.CDLL:
         fn = getattr(lib, name)  # AttributeError if the header and the library disagree
         fn.restype = res
         fn.argtypes = args
-    if lib.nfst_abi_version() != 12:
+    if lib.nfst_abi_version() != 13:
         raise RuntimeError("libnfst_b200.so ABI version mismatch")
     _lib = lib
     return lib

@@ -593,7 +593,9 @@ __global__ void __launch_bounds__(NT_MAX, MINB)
 // =====================================================================================
 // flow pass
 // =====================================================================================
-template <bool DTH, bool POST, int NT_MAX, int MINB>
+// GT: the fixed-point accumulator of gamma -- unsigned (2^-31 units: absolute error of a posterior < 1e-9) or
+// unsigned long long (2^-62 units: what is left is the float32 rounding of every contribution, ~6e-8 relative)
+template <bool DTH, bool POST, typename GT, int NT_MAX, int MINB>
 __global__ void __launch_bounds__(NT_MAX, MINB)
     tile_flow_kernel(const nfst_packed_lattices_t L, const int32_t* __restrict__ ids, const TP P, const float* cond,
                      const float* __restrict__ grad_logz, float* post, float* __restrict__ dtheta) {
@@ -604,9 +606,11 @@ __global__ void __launch_bounds__(NT_MAX, MINB)
   const int a_base = info.w;
   const int n_levels = L.level_off[b + 1] - L.level_off[b] - 1;
   const int W = info.y, ring_total = info.z;  // ring, the dump slot W (arcs into the last level), the far table
-  unsigned* const ring = reinterpret_cast<unsigned*>(tile_smem);
+  constexpr bool WIDE = sizeof(GT) == 8;
+  constexpr float kUnit = WIDE ? 4611686018427387904.0f : kFix;  // 2^62 : 2^31
+  GT* const ring = reinterpret_cast<GT*>(tile_smem);
   unsigned* hist = nullptr;
-  for (int i = tid; i < ring_total; i += blockDim.x) ring[i] = 0u;
+  for (int i = tid; i < ring_total; i += blockDim.x) ring[i] = 0;
   if (DTH && P.table) {
     hist = reinterpret_cast<unsigned*>(tile_smem + P.table_off);
     for (int i = tid; i < L.vocab; i += blockDim.x) hist[i] = 0u;
@@ -618,10 +622,10 @@ __global__ void __launch_bounds__(NT_MAX, MINB)
     for (int d = 0; d < D; ++d) mbar_init(bars_s + 8 * d, 1);
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   __syncthreads();
-  if (tid == 0) ring[0] = 0x80000000u;  // gamma[start] = 1: the start state is state 0 / slot 0 of its lattice
+  if (tid == 0) ring[0] = static_cast<GT>(1) << (WIDE ? 62 : 31);  // gamma[start] = 1: the start state is state 0 / slot 0 of its lattice
   __syncthreads();
   const float gl = grad_logz ? grad_logz[b] : 1.0f;
-  const float unfix = gl * (1.0f / kFix);  // fixed-point gamma -> gradient-scaled posterior mass
+  const float unfix = gl * (1.0f / kUnit);  // fixed-point gamma -> gradient-scaled posterior mass
 
   unsigned char* const my_stage = tile_smem + P.stage_off + static_cast<size_t>(warp) * D * P.stage_bytes;
   const unsigned stage_s = smem_u32(my_stage);
@@ -653,12 +657,23 @@ __global__ void __launch_bounds__(NT_MAX, MINB)
   auto push = [&](const Seg& g, int e, float gam) {
     const float cd = g.vals[e];
     const unsigned code = g.codes[e];
-    const float pf = gam * cd;  // in fixed-point units (gam = gamma * 2^31)
+    const float pf = gam * cd;  // in fixed-point units (gam = gamma * 2^31 or 2^62)
     if (POST) post[g.arc0 + e] = pf * unfix;
     TILE_CHECK(static_cast<int>(code) < ring_total, 6, static_cast<int>(code), ring_total, e);
-    atomicAdd(&ring[code], __float2uint_rn(pf));
+    if constexpr (WIDE) {
+      // 64-bit add as two native 32-bit shared-memory atomics (a 64-bit atomicAdd there is a compare-and-swap
+      // loop): exactly the adds whose low word wraps carry one into the high word, so the sum is exact whatever
+      // the order; the words are read together only after the level barrier
+      const unsigned long long x = __float2ull_rn(pf);
+      const unsigned xl = static_cast<unsigned>(x);
+      unsigned* const w = reinterpret_cast<unsigned*>(&ring[code]);
+      const unsigned old = atomicAdd(w, xl);
+      atomicAdd(w + 1, static_cast<unsigned>(x >> 32) + (old + xl < old ? 1u : 0u));
+    } else {
+      atomicAdd(&ring[code], __float2uint_rn(pf));
+    }
     if (DTH) {
-      const float pr = pf * (1.0f / kFix);
+      const float pr = pf * (1.0f / kUnit);
       if (hist) atomicAdd(&hist[g.labs[e]], __float2uint_rn(pr * P.hist_scale));
       else atomicAdd(dtheta + g.labs[e], pr * gl);
     }
@@ -695,9 +710,9 @@ __global__ void __launch_bounds__(NT_MAX, MINB)
         if (flags & FLAG_HEAVY_FIRST) {
           // every arc into the state comes from a shallower level: gamma is final; free the ring slot
           const int far_slot = h.z & 0xffff;
-          heavy_gam = static_cast<float>(ring[vslot] + (far_slot ? ring[far_slot] : 0u));
+          heavy_gam = static_cast<float>(ring[vslot] + (far_slot ? ring[far_slot] : static_cast<GT>(0)));
           __syncwarp();
-          if (lane == 0) ring[vslot] = 0u;
+          if (lane == 0) ring[vslot] = 0;
         }
         const int n = h.w & 0xffff;
 #pragma unroll 2
@@ -706,8 +721,8 @@ __global__ void __launch_bounds__(NT_MAX, MINB)
         const int arc_rel = h.z & 0xffff, nst = (h.z >> 16) & 0xff, dmax = static_cast<unsigned>(h.z) >> 24;
         float gam = 0.0f;
         if (lane < nst) {
-          unsigned gfix = ring[vslot + lane];
-          ring[vslot + lane] = 0u;
+          GT gfix = ring[vslot + lane];
+          ring[vslot + lane] = 0;
           if (flags & FLAG_FAR_IN) {  // flow that arrived through the far table
             const int far_slot = reinterpret_cast<const uint16_t*>(st + (h.w & 0xffff) + (dmax > KU ? 32 : 0))[lane];
             if (far_slot) gfix += ring[far_slot];
@@ -928,7 +943,7 @@ int nfst_tile_debug_read(int32_t* out8) {
 size_t nfst_tile_smem_bytes(const nfst_launch_t* launch, int32_t vocab, int pass, int n_f32_arrays, int with_table, int stages) {
   if (!launch || !launch->tiles) return 0;
   const bool table = with_table && vocab <= NFST_THETA_SMEM_MAX;
-  const int elem = pass == 0 && launch->state_f64 ? 8 : 4;
+  const int elem = (pass == 0 && launch->state_f64) || (pass == 1 && launch->tile_flow_bits == 64) ? 8 : 4;
   if (stages > 0) return geometry(launch, vocab, elem, n_f32_arrays, table, stages).smem;
   return pick_geometry(launch, vocab, elem, n_f32_arrays, table).smem;
 }
@@ -963,7 +978,10 @@ int nfst_tile_flow_f32(const nfst_packed_lattices_t* lat, const nfst_launch_t* l
   if (launch->n_ids == 0) return 0;
   cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
   const bool table = dtheta && lat->vocab <= NFST_THETA_SMEM_MAX;
-  Geometry g = pick_geometry(launch, lat->vocab, 4, dtheta ? 2 : 1, table);
+  const bool wide = launch->tile_flow_bits == 64;
+  if (launch->tile_flow_bits != 0 && launch->tile_flow_bits != 32 && !wide)
+    return nfst_fail_msg(NFST_ERR_BAD_ARG, "tile_flow_bits must be 0, 32 or 64");
+  Geometry g = pick_geometry(launch, lat->vocab, wide ? 8 : 4, dtheta ? 2 : 1, table);
   // dtheta histogram unit: an expected label count is at most the number of levels
   int lv = 1;
   while (lv < launch->n_levels) lv <<= 1;
@@ -972,24 +990,27 @@ int nfst_tile_flow_f32(const nfst_packed_lattices_t* lat, const nfst_launch_t* l
   if (g.smem > 227 * 1024) return nfst_fail_msg(NFST_ERR_TOO_LARGE, "tile-stream launch needs %zu bytes of shared memory", g.smem);
   if (!aligned16(cond) || (dtheta && !aligned16(lat->label_out)))
     return nfst_fail_msg(NFST_ERR_BAD_ARG, "cond and label_out must be 16-byte aligned (they are fetched with bulk copies)");
-#define FLOW_NT(NTv, MINBv)                                                                                               \
+#define FLOW_GO(DTHv, POSTv, GTv, NTv, MINBv)                                                                             \
   do {                                                                                                                    \
-    if (dtheta && post) {                                                                                                 \
-      auto k = tile_flow_kernel<true, true, NTv, MINBv>;                                                                  \
-      if (int rc = prepare(k, g.smem)) return rc;                                                                         \
-      k<<<launch->n_ids, launch->block_threads, g.smem, stream>>>(*lat, launch->lattice_ids, g.p, cond, grad_logz, post, dtheta); \
-    } else if (dtheta) { /* the label histogram only: no per-arc output */                                                \
-      auto k = tile_flow_kernel<true, false, NTv, MINBv>;                                                                 \
-      if (int rc = prepare(k, g.smem)) return rc;                                                                         \
-      k<<<launch->n_ids, launch->block_threads, g.smem, stream>>>(*lat, launch->lattice_ids, g.p, cond, grad_logz, post, dtheta); \
-    } else {                                                                                                              \
-      auto k = tile_flow_kernel<false, true, NTv, MINBv>;                                                                 \
-      if (int rc = prepare(k, g.smem)) return rc;                                                                         \
-      k<<<launch->n_ids, launch->block_threads, g.smem, stream>>>(*lat, launch->lattice_ids, g.p, cond, grad_logz, post, dtheta); \
-    }                                                                                                                     \
+    auto k = tile_flow_kernel<DTHv, POSTv, GTv, NTv, MINBv>;                                                              \
+    if (int rc = prepare(k, g.smem)) return rc;                                                                           \
+    k<<<launch->n_ids, launch->block_threads, g.smem, stream>>>(*lat, launch->lattice_ids, g.p, cond, grad_logz, post, dtheta); \
+  } while (0)
+#define FLOW_NT(NTv, MINBv)                                                                  \
+  do {                                                                                       \
+    if (wide) {                                                                              \
+      if (dtheta && post) FLOW_GO(true, true, unsigned long long, NTv, MINBv);               \
+      else if (dtheta) FLOW_GO(true, false, unsigned long long, NTv, MINBv);                 \
+      else FLOW_GO(false, true, unsigned long long, NTv, MINBv);                             \
+    } else {                                                                                 \
+      if (dtheta && post) FLOW_GO(true, true, unsigned, NTv, MINBv);                         \
+      else if (dtheta) FLOW_GO(true, false, unsigned, NTv, MINBv); /* no per-arc output */   \
+      else FLOW_GO(false, true, unsigned, NTv, MINBv);                                       \
+    }                                                                                        \
   } while (0)
   TILE_BY_BLOCK(FLOW_NT);
 #undef FLOW_NT
+#undef FLOW_GO
   TILE_CUDA_OK(cudaGetLastError());
   return 0;
 }

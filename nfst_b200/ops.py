@@ -43,6 +43,8 @@ F64_DEPTH = 96
 F64_DEPTH_PLAIN = 64
 # depth of the tile-stream kernels' stage rings; 0 = chosen by the library from the shared memory per block
 TILE_STAGES = int(os.environ.get("NFST_TILE_STAGES", "0"))
+# width of the tile-stream flow pass's fixed-point accumulator (see nfst_launch_t.tile_flow_bits): 32 or 64
+FLOW_BITS = int(os.environ.get("NFST_FLOW_BITS", "32"))
 
 
 def resolve_state_dtype(packed: PackedLattices, state_dtype="auto") -> torch.dtype:
@@ -104,6 +106,7 @@ def _launch(g: LaunchGroup, st_dtype: torch.dtype) -> "_lib.LaunchC":
         c.tile_ring, c.tile_far = g.tile_ring, int(g.tile_far)
         c.tile_cap_arcs, c.tile_cap_bytes = g.tile_cap_arcs, g.tile_cap_bytes
         c.tile_stages = TILE_STAGES
+        c.tile_flow_bits = FLOW_BITS
         c.n_levels = g.n_levels
     if g.fwd_level_chunks is not None:  # level-major group: one launch per topological level
         c.n_levels = g.n_levels

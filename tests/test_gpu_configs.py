@@ -7,7 +7,7 @@ against the C oracle (oracle/lattice_oracle.c, float64):
   * logZ of EVERY lattice against a float64 restatement of the recurrence in plain torch ops on the ORIGINAL arc
     list (Bellman sweeps until nothing changes; independent of the packer and of the kernels), which is itself
     held to the C oracle on the sample;
-  * arc posteriors (|p - ref| <= 1e-5 ref + 1e-7), Viterbi scores (bit-exact) and best-path label sequences
+  * arc posteriors (|p - ref| <= 1e-5 ref + 2e-9), Viterbi scores (bit-exact) and best-path label sequences
     (equal) on a seeded random sample of 16 lattices taken out of the full-batch results;
   * size-independent identities on all lattices: the posterior mass leaving the start state is 1, logZ is finite.
 
@@ -26,6 +26,10 @@ from oracle import c_oracle
 pytestmark = [pytest.mark.gpu, pytest.mark.timeout(300)]
 DEV = torch.device("cuda", 0)
 N_SAMPLE = 16
+# posteriors: 1e-5 relative plus an ABSOLUTE 2e-9 -- the tile-stream flow pass accumulates state posteriors in 2^-31
+# fixed point (native integer shared-memory atomics, bit-reproducible), so a posterior carries an absolute error of a
+# few 5e-10 units: 1e-5 relative down to posteriors of ~1e-4, absolute below (NFST_FLOW_BITS=64 is relative at any size)
+ATOL_POST = 2e-9
 
 
 def logz_by_sweeps(ab: synth.ArcBatch) -> torch.Tensor:
@@ -125,7 +129,7 @@ def check_config(gen, B, per_chunk, *, seed=0, expect=None):
         np.testing.assert_allclose(logz_c[b], o_logz[j], rtol=1e-5, atol=1e-5)
         got = post[s["a0"]:s["a1"]].cpu().numpy().astype(np.float64)
         ref = o_post[off[j] + s["pos"]]
-        err = np.abs(got - ref) - (1e-5 * ref + 1e-7)
+        err = np.abs(got - ref) - (1e-5 * ref + ATOL_POST)
         worst = max(worst, float(np.max(np.abs(got - ref) / (ref + 1e-7))))
         assert np.all(err <= 0), (b, float(np.max(np.abs(got - ref) / (ref + 1e-7))))
         assert vs_c[b:b + 1].view(np.uint32)[0] == o_vs[j:j + 1].view(np.uint32)[0], "Viterbi score bit-exact"
