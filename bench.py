@@ -102,6 +102,7 @@ def build_packed(a, device, arcs=None, rank=0, world=1):
         mine = torch.zeros(total, dtype=torch.bool)
         mine[torch.tensor(nd.shard_by_arcs(torch.cat(counts).tolist(), world)[rank], dtype=torch.int64)] = True
     parts, scores = [], []
+    build_packed.pack_s = 0.0
     for d, n in spans:
         ab = make_arcs(a, device, seed_offset=d, batch=n, arcs=arcs)
         if mine is not None:
@@ -109,7 +110,13 @@ def build_packed(a, device, arcs=None, rank=0, world=1):
             if sel.numel() == 0:
                 continue
             ab = ab.select(sel.to(device))
+        if device != "cpu":
+            torch.cuda.synchronize()
+        t0 = time.perf_counter()
         p, sc = ab.pack()
+        if device != "cpu":
+            torch.cuda.synchronize()
+        build_packed.pack_s += time.perf_counter() - t0
         p.arc_origin = torch.empty(0, dtype=torch.int64, device=device)  # not needed here; frees 8 B/arc
         parts.append(p)
         scores.append(sc)
@@ -324,6 +331,7 @@ def main():
     _lib.check(_lib.load().nfst_device_info(local, None, None, None, None))
 
     packed, scores = build_packed(a, dev, rank=rank, world=world)
+    pack_ms = 1e3 * build_packed.pack_s
     A, S, B = packed.n_arcs, packed.n_states, packed.n_lattices
     B_global = a.batch * world
     loss = torch.zeros(1, device=dev)
@@ -593,6 +601,10 @@ def main():
         theta_leg["frac"] = (20 * arcs_all / world + 20 * S) / (theta_leg["ms_per_step"] * 1e-3) / 1e9 / peak
         out["theta_step"] = theta_leg
     out["ranks"] = ranks
+    out["pack"] = {"ms": pack_ms, "arcs_per_s": A / (pack_ms * 1e-3), "when": "once per batch, outside the timed region",
+                   "packer": "tensor-op packer (nfst_b200/pack.py + tiles.py) for these wide lattices; the lattices nFST builds "
+                             "(configs 1, 2, 5) pack on the device with nfst_pack_small: 1.8 ms for config 1, 4.1 ms for config 5 "
+                             "(tools/pack_profile.py)"}
     if not a.no_cpu and world == 1:  # CPU baseline: rank 0 at N=1 only
         cb, _, _ = cpu_baseline(a, a.cpu_seconds)
         out["cpu_baseline"] = cb

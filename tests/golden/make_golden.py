@@ -184,6 +184,69 @@ def gen_walk():
     print("walk_step.npz:", steps, "steps,", N, "rows")
 
 
+def gen_stateful():
+    """ONE FULL CALL of the reference's ``Sampler.stateful_sample`` (samplers.py:182-335) on a real
+    ``FSAGRUScorer(use_beta=True)``: ``compute_beta()`` at its top (:196-198), then the whole loop with the module's own
+    GRU, ``beta_scorer`` and masks.  Recorded without touching the reference's source: the instance's ``beta_scorer`` is
+    wrapped by a module that calls the real one and keeps its output, and the parent class's ``mask_out_invalid`` is
+    wrapped the same way for the duration of the call (the vocabulary mask of every step).  Stored: tables, k, the
+    module's parameters that define theta, beta, per step {beta_scorer output, vocabulary mask}, the sampled
+    sequences and the summed log-probabilities the call returns."""
+    from oracle.lattice_oracle import collate_pad
+
+    ns = rh.load()
+    rng = np.random.default_rng(20260505)
+    k, T = 4, 0.9
+    m = rh.make_scorer(H, V, seed=51, zero_wh=True, double=False)
+    tabs = [random_mark_lattice(rng, n, V, parallel_arcs=False)[1] for n in (5, 8, 6)]
+    tr = collate_pad(tabs, PAD)
+    em = collate_pad([t != 0 for t in tabs], PAD)
+    prefixes, bases = [], []
+    real_scorer = m.beta_scorer
+
+    class Recorder(torch.nn.Module):
+        def forward(self, h):
+            out = real_scorer(h)
+            prefixes.append(out.detach().clone())
+            return out
+
+    parent = ns.FSAGRUScorer.__mro__[1]
+    orig_mask = parent.mask_out_invalid
+
+    def recording_mask(self, inp, metadata):
+        r = orig_mask(self, inp, metadata)
+        bases.append(r.detach().clone())
+        return r
+
+    sampler = ns.Sampler(m)
+    with torch.no_grad():
+        m.set_masks(emission=torch.from_numpy(em), transition=torch.from_numpy(tr))
+        m.set_k(k)
+        N = tr.shape[0] * k
+        beta = m.compute_beta().clone()  # what stateful_sample computes at its top (same inputs, deterministic)
+        m.beta_scorer = Recorder()
+        parent.mask_out_invalid = recording_mask
+        try:
+            torch.manual_seed(5151)
+            summed, seqs, _ = sampler.stateful_sample(N, temperature=T)
+        finally:
+            if "mask_out_invalid" in parent.__dict__ and parent.__dict__["mask_out_invalid"] is recording_mask:
+                parent.mask_out_invalid = orig_mask
+            m.beta_scorer = real_scorer
+    steps = len(prefixes)
+    assert steps == len(bases) == seqs.shape[1] + 1
+    out = {"vocab": np.int64(V), "k": np.int64(k), "temperature": np.float64(T), "steps": np.int64(steps), "pad": np.int64(ns.pad),
+           "bos": np.int64(ns.bos), "tr": tr, "em": em, "theta": rh.arc_theta(m).numpy(), "beta": beta.numpy(),
+           "summed_log_probs": summed.numpy(), "sequences": seqs.numpy()}
+    for name, v in params_of(m).items():
+        out["p_" + name] = v.astype(np.float32)
+    for t in range(steps):
+        out[f"prefix_{t}"] = prefixes[t].numpy()
+        out[f"base_{t}"] = bases[t].numpy()
+    np.savez_compressed(os.path.join(OUT, "stateful_sample.npz"), **out)
+    print("stateful_sample.npz:", steps, "steps,", N, "rows; mean log q", float(summed.mean()))
+
+
 if __name__ == "__main__":
     if not rh.available():
         raise SystemExit("reference not mounted; golden vectors can only be regenerated in the build container")
@@ -191,3 +254,4 @@ if __name__ == "__main__":
     gen_parallel()
     gen_iwae()
     gen_walk()
+    gen_stateful()

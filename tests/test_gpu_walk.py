@@ -210,3 +210,40 @@ def test_sample_paths_are_exact_posterior_samples():
                 break
             s, t = dst[a[j]], t + 1
     assert mism <= 1  # a uniform number can fall on a CDF boundary (fp32 beta on the GPU side)
+
+
+def test_full_stateful_sample_call_replays_through_the_patched_module_and_the_walker():
+    """tests/golden/stateful_sample.npz is ONE FULL CALL of the reference's Sampler.stateful_sample on a real
+    FSAGRUScorer(use_beta=True) (samplers.py:182-335).  Here: an object with that module's attribute names and its
+    recorded parameters gets patch_compute_beta -> its compute_beta() equals the reference's beta; LatticeWalker then
+    replays the whole loop on the recorded per-step network outputs and vocabulary masks, scoring the recorded samples:
+    the summed log-probabilities equal what the reference's call returned."""
+    from types import SimpleNamespace
+
+    from nfst_b200.scorer import patch_compute_beta
+
+    g = np.load(os.path.join(os.path.dirname(G), "stateful_sample.npz"))
+    k, T, pad, bos, steps = int(g["k"]), float(g["temperature"]), int(g["pad"]), int(g["bos"]), int(g["steps"])
+    tr, em = torch.from_numpy(g["tr"]).to(DEV), torch.from_numpy(g["em"]).to(DEV)
+    dev = lambda name: torch.from_numpy(g["p_" + name]).to(DEV)  # noqa: E731
+    mod = SimpleNamespace(embeddings=SimpleNamespace(weight=dev("emb")), Wx=dev("Wx"), Wh=dev("Wh"), W=dev("W"),
+                          beta_bias=dev("bias"), emission=em, transition=tr, k=k)
+    patch_compute_beta(mod)
+    beta_dense = mod.compute_beta()
+    assert beta_dense.shape == g["beta"].shape and beta_dense.dtype == torch.float32
+    B, S = tr.shape[0], tr.shape[1]
+    p = nb.pack_dense(em, tr, weighted=False)
+    # compare where the reference's value is meaningful: the states the start reaches (the rest are collate padding)
+    so = p.state_off.cpu().numpy()
+    lat = np.repeat(np.arange(B), np.diff(so))
+    orig = p.orig_state.cpu().numpy()
+    np.testing.assert_allclose(beta_dense.cpu().numpy()[lat * k, orig], g["beta"][lat * k, orig], rtol=2e-5)
+    w = LatticeWalker(p, k, packed_beta(p, k, beta_dense.cpu().numpy()), pad, temperature=T, faithful=True)
+    w.consume(torch.full((w.n_rows,), bos, dtype=torch.int32, device=DEV))
+    seqs = g["sequences"]  # [N, steps - 1]; the call pops the final (all-pad) step
+    total = torch.zeros(w.n_rows, device=DEV)
+    for t in range(steps):
+        sym = torch.from_numpy(seqs[:, t] if t < seqs.shape[1] else np.full(w.n_rows, pad)).to(DEV)
+        _, logp, _ = w.step(torch.from_numpy(g[f"prefix_{t}"]).to(DEV), base_mask=torch.from_numpy(g[f"base_{t}"]).to(DEV), symbols=sym)
+        total += logp
+    np.testing.assert_allclose(total.cpu().numpy(), g["summed_log_probs"], rtol=1e-5, atol=1e-5)
