@@ -56,7 +56,7 @@
 extern "C" {
 #endif
 
-#define NFST_ABI_VERSION 13
+#define NFST_ABI_VERSION 15
 
 typedef enum nfst_status {
   NFST_OK = 0,
@@ -454,10 +454,13 @@ int nfst_beta_hat_level_f32(const nfst_packed_lattices_t* lat, const int32_t* st
  * the small-lattice kernels, the sampling-loop kernels and the best-path read-out use (everything except the
  * chunk lists, the sliced-column descriptors and the tile stream), written into caller-allocated buffers sized
  * for the RAW counts (trimming only shrinks): per-state arrays [n_states_raw (+1)], per-arc arrays [n_arcs_raw],
- * level_ptr [n_states_raw + B], offsets [B + 1].  Three launches on the caller's stream, no host synchronisation:
+ * level_ptr [n_states_raw + B], offsets [B + 1].  phases: 1 = count (levels, trimming, per-lattice counts, offsets,
+ * totals: two launches; only the per-lattice outputs are touched), 2 = build (one launch; same workspace, same
+ * inputs; max_arcs may shrink to the largest kept count), 3 = both -- a caller that reads the totals between the
+ * phases can allocate the per-state / per-arc outputs at their exact sizes.  On the caller's stream, no host synchronisation:
  * the caller reads totals[8] = {S, A, level_ptr entries, sinks, error, lattice of the error, largest level count,
- * 0} (error 4: a lattice keeps more than max_arcs arcs -- max_arcs bounds the KEPT arcs of a lattice, the raw list
- * may be longer: collate() padding) and lattice_stats[B][8] = {states, arcs, levels, sinks, arcs of the widest level, 0, 0, 0} (zero-filled by the
+ * 0} (error 4: a lattice keeps more than max_arcs arcs -- max_arcs bounds the KEPT arcs of a lattice, max_raw_arcs
+ * its raw list, which may be far longer: collate() padding) and lattice_stats[B][8] = {states, arcs, levels, sinks, arcs of the widest level, 0, 0, 0} (zero-filled by the
  * caller) when it needs the sizes.  error: 0 ok, 1 = cyclic
  * lattice, 2 = arc endpoint / start state out of range, 3 = batch beyond int32 indices.
  */
@@ -468,6 +471,7 @@ typedef struct nfst_pack_out {
   int32_t *in_ptr, *out_ptr;                           /* [S+1] */
   int32_t *src_in, *label_in, *in2out, *dst_out, *label_out, *src_out; /* per arc */
   int64_t *arc_origin;                                 /* per arc: index into the raw arc list */
+  uint8_t *out_deg8;                                   /* per state: min(out-degree, 255); may be NULL */
   int32_t *lattice_stats;                              /* [B][8] */
   int32_t *totals;                                     /* [8] */
 } nfst_pack_out_t;
@@ -475,8 +479,8 @@ size_t nfst_pack_small_smem_bytes(int32_t max_states, int32_t max_arcs);
 size_t nfst_pack_small_workspace_bytes(int64_t n_states_raw, int64_t n_arcs_raw);
 int nfst_pack_small(int32_t n_lattices, const int32_t* raw_state_off, const int32_t* raw_arc_off, const int32_t* raw_src,
                     const int32_t* raw_dst, const int32_t* raw_label, int32_t src_is_global, int32_t start_state,
-                    int32_t max_states, int32_t max_arcs, const nfst_pack_out_t* out, void* workspace, size_t workspace_bytes,
-                    int64_t n_states_raw, int64_t n_arcs_raw, void* cuda_stream);
+                    int32_t max_states, int32_t max_arcs, int32_t max_raw_arcs, const nfst_pack_out_t* out, void* workspace,
+                    size_t workspace_bytes, int64_t n_states_raw, int64_t n_arcs_raw, int32_t phases, void* cuda_stream);
 
 /*
  * On-device construction of the transliteration lattices (what src/preprocess/tr.py:142-190 builds offline with

@@ -90,7 +90,7 @@ class PackOutC(C.Structure):
 
     _fields_ = [(n, C.c_void_p) for n in (
         "state_off", "arc_off", "level_off", "sink_off", "n_levels", "start_state", "level_ptr", "sinks", "orig_state",
-        "in_ptr", "out_ptr", "src_in", "label_in", "in2out", "dst_out", "label_out", "src_out", "arc_origin",
+        "in_ptr", "out_ptr", "src_in", "label_in", "in2out", "dst_out", "label_out", "src_out", "arc_origin", "out_deg8",
         "lattice_stats", "totals")]
 
 
@@ -133,8 +133,8 @@ SYMBOLS = {
     "nfst_beta_to_dense": (C.c_int, [C.POINTER(PackedLatticesC), _P, C.c_int, _P, C.c_int32, C.c_int32, _P, _P]),
     "nfst_pack_small_smem_bytes": (C.c_size_t, [C.c_int32, C.c_int32]),
     "nfst_pack_small_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int64]),
-    "nfst_pack_small": (C.c_int, [C.c_int32, _P, _P, _P, _P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(PackOutC), _P,
-                                  C.c_size_t, C.c_int64, C.c_int64, _P]),
+    "nfst_pack_small": (C.c_int, [C.c_int32, _P, _P, _P, _P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(PackOutC), _P,
+                                  C.c_size_t, C.c_int64, C.c_int64, C.c_int32, _P]),
     "nfst_edit_lattice_size": (None, [C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "nfst_edit_lattice_arcs": (C.c_int, [C.c_int32, _P, _P, C.c_int32, _P, _P, C.c_int32] + [C.c_int32] * 6 + [_P, _P, _P, _P, _P]),
     "nfst_dense_count_arcs": (C.c_int, [_P, C.c_int64, C.c_int32, C.c_int32, _P, _P]),
@@ -164,7 +164,7 @@ def load() -> C.CDLL:
         fn = getattr(lib, name)  # AttributeError if the header and the library disagree
         fn.restype = res
         fn.argtypes = args
-    if lib.nfst_abi_version() != 13:
+    if lib.nfst_abi_version() != 15:
         raise RuntimeError("libnfst_b200.so ABI version mismatch")
     _lib = lib
     return lib

@@ -77,7 +77,7 @@ def edit_lattices(x, y, *, vocab: int, bos: int, eos: int, input_mark: int, outp
                                               int(sub_mark) if add_sub else -1, int(add_sub), arc_off32.data_ptr(), src.data_ptr(),
                                               dst.data_ptr(), lab.data_ptr(), torch.cuda.current_stream(dev).cuda_stream))
     packed = pack_small_device(state_off32, arc_off32, src, dst, lab, vocab, src_is_global=False, max_states=int(smax),
-                               max_arcs=int(amax))
+                               max_arcs=int(amax), n_states_raw=int(S0))
     if packed is None:  # pairs too long for one SM's shared memory: the general packer
         lat = torch.repeat_interleave(torch.arange(B, device=dev), n_arcs)
         packed = pack_arcs(lat, src.to(torch.int64), dst.to(torch.int64), lab.to(torch.int64), n_states, vocab)

@@ -7,8 +7,9 @@
 // nFST's composed mark lattices have (hundreds to a few thousand states).
 //
 // One thread block per lattice, three launches for the whole batch:
-//   pack_level_kernel   states the start state reaches (sweeps over the raw arcs in global memory); the arcs out of
-//                       those states -> shared memory; longest distance from the start by relaxation sweeps
+//   pack_level_kernel   states the start state reaches (one pass over the raw arcs for every state's arc range, then a
+//                       breadth-first search over the reachable states' arcs); the arcs out of those states -> shared
+//                       memory; longest distance from the start by relaxation sweeps
 //                       (shared-memory atomicMax, until nothing changes; more sweeps than states = a cycle);
 //                       states unreachable from the start -- every row collate() padding adds
 //                       (util/dataset_reader.py:175-186) -- are trimmed; per-lattice counts
@@ -75,6 +76,28 @@ __device__ int block_excl_scan(int* v, int n, int* tmp) {
 // ---------------------------------------------------------------------------------------------------------
 // reachability, kept arcs, levels, counts
 // ---------------------------------------------------------------------------------------------------------
+// every state's range in the raw arc list (sorted by source) + endpoint validation: grid (chunks, lattices)
+__global__ void __launch_bounds__(kThreads)
+    pack_ranges_kernel(const RawArcs R, int32_t* __restrict__ first_g, int32_t* __restrict__ end_g, int32_t* __restrict__ totals) {
+  const int b = blockIdx.y;
+  const int s0 = R.state_off[b], S0 = R.state_off[b + 1] - s0;
+  const int a0 = R.arc_off[b], A0 = R.arc_off[b + 1] - a0;
+  const int i = blockIdx.x * kThreads + threadIdx.x;
+  if (i >= A0) return;
+  const int base = R.src_global ? s0 : 0;
+  const int s = R.src[a0 + i] - base, d = R.dst[a0 + i];
+  if (s < 0 || s >= S0 || d < 0 || d >= S0) {
+    if (atomicCAS(&totals[4], 0, 2) == 0) totals[5] = b;
+    return;
+  }
+  const int sp = i ? R.src[a0 + i - 1] - base : -1;
+  if (sp != s) {
+    first_g[s0 + s] = i;
+    if (sp >= 0 && sp < S0) end_g[s0 + sp] = i;
+  }
+  if (i == A0 - 1) end_g[s0 + s] = A0;
+}
+
 struct Kept {  // the arcs that survive trimming, per lattice at its raw arc offset (workspace)
   int32_t* pack;   // src | dst << 16 (raw local ids)
   int32_t* label;
@@ -82,86 +105,97 @@ struct Kept {  // the arcs that survive trimming, per lattice at its raw arc off
 };
 
 __global__ void __launch_bounds__(kThreads)
-    pack_level_kernel(const RawArcs R, int capS, int capA, int32_t* __restrict__ level_g, const Kept K,
-                      int32_t* __restrict__ stats, int32_t* __restrict__ totals) {
+    pack_level_kernel(const RawArcs R, int capS, int capA, int32_t* __restrict__ level_g, const int32_t* __restrict__ first_g,
+                      const int32_t* __restrict__ end_g, const Kept K, int32_t* __restrict__ stats,
+                      int32_t* __restrict__ totals) {
+  if (totals[4]) return;  // pack_ranges_kernel met an arc that points outside its lattice
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int s0 = R.state_off[b], S0 = R.state_off[b + 1] - s0;
   const int a0 = R.arc_off[b], A0 = R.arc_off[b + 1] - a0;
   int* const level = pack_smem;             // [capS]
   int* const has_out = level + capS;        // [capS]
-  int* const arcs = has_out + capS;         // [capA] kept arcs: src | dst << 16
-  __shared__ int changed, bad, n_states, n_sinks, max_level, kept_base;
-  __shared__ int warp_sum[kThreads / 32];
+  int* const lvl_out = has_out + capS;      // [capS] arcs out of / into every level
+  int* const lvl_in = lvl_out + capS;
+  int* const arcs = lvl_in + capS;          // [capA] kept arcs: src | dst << 16
+  __shared__ int changed, n_states, n_sinks, max_level, width_arcs;
   for (int s = tid; s < S0; s += kThreads) {
     level[s] = -1;
     has_out[s] = 0;
+    lvl_out[s] = 0;
+    lvl_in[s] = 0;
   }
   if (tid == 0) {
-    changed = 0; bad = 0; n_states = 0; n_sinks = 0; max_level = 0; kept_base = 0;
+    changed = 0; n_states = 0; n_sinks = 0; max_level = 0; width_arcs = 0;
   }
   __syncthreads();
   if (tid == 0 && R.start >= 0 && R.start < S0) level[R.start] = 0;
   __syncthreads();
-  // 1. which states the start state reaches: sweeps over the RAW arcs in global memory (a collate()-padded table
-  //    carries V arcs per pad row -- far more than the lattice's own -- so they never enter shared memory).
-  //    OpenFst numbers states roughly topologically and the arcs are sorted by source: a sweep or two settles it.
-  for (int sweep = 0;; ++sweep) {
-    for (int i = tid; i < A0; i += kThreads) {
-      const int s = R.src[a0 + i] - (R.src_global ? s0 : 0), d = R.dst[a0 + i];
-      if (s < 0 || s >= S0 || d < 0 || d >= S0) {
-        bad = 2;
-      } else if (level[s] >= 0 && level[d] < 0) {
-        level[d] = 0;
-        changed = 1;
+  // 1. which states the start state reaches.  A collate()-padded table carries V arcs per pad row -- far more than
+  //    the lattice's own -- so the raw arcs never enter shared memory: pack_ranges_kernel found every state's arc
+  //    range (they are sorted by source) and validated the endpoints; a breadth-first search from the start
+  //    touches the arcs of reachable states only (a queue in shared memory, one thread per newly reached state).
+  int* const raw_first = lvl_out;  // [S0] first raw arc of a state / one past its last (aliases: re-zeroed below)
+  int* const raw_end = lvl_in;
+  int* const queue = has_out;
+  __shared__ int q_tail;
+  for (int s = tid; s < S0; s += kThreads) {
+    raw_first[s] = first_g[s0 + s];
+    raw_end[s] = end_g[s0 + s];
+  }
+  __syncthreads();
+  if (R.start < 0 || R.start >= S0) {
+    if (tid == 0 && atomicCAS(&totals[4], 0, 2) == 0) totals[5] = b;
+    return;
+  }
+  if (tid == 0) {
+    queue[0] = R.start;
+    q_tail = 1;
+  }
+  __syncthreads();
+  for (int head = 0;;) {
+    const int tail = q_tail;  // everything below [head, tail) was reached in the previous round
+    __syncthreads();
+    if (head >= tail) break;
+    for (int q = head + tid; q < tail; q += kThreads) {
+      const int s = queue[q];
+      for (int i = raw_first[s]; i < raw_end[s]; ++i) {
+        const int d = R.dst[a0 + i];
+        if (atomicCAS(&level[d], -1, 0) == -1) queue[atomicAdd(&q_tail, 1)] = d;
       }
     }
-    __syncthreads();
-    const int again = changed, wrong = bad;
-    __syncthreads();
-    if (wrong || R.start < 0 || R.start >= S0) {
-      if (tid == 0 && atomicCAS(&totals[4], 0, 2) == 0) totals[5] = b;
-      return;
-    }
-    if (!again || sweep > S0) break;
-    if (tid == 0) changed = 0;
+    head = tail;
     __syncthreads();
   }
-  // 2. the kept arcs (source reachable), in raw order: shared memory for the level sweeps, workspace for the build
-  for (int base = 0; base < A0; base += kThreads) {
-    const int i = base + tid;
-    int s = 0, d = 0;
-    bool keep = false;
-    if (i < A0) {
-      s = R.src[a0 + i] - (R.src_global ? s0 : 0);
-      d = R.dst[a0 + i];
-      keep = level[s] >= 0;
-    }
-    const unsigned m = __ballot_sync(0xffffffffu, keep);
-    if (lane == 0) warp_sum[warp] = __popc(m);
-    __syncthreads();
-    int before = kept_base;
-    for (int w = 0; w < warp; ++w) before += warp_sum[w];
-    if (keep) {
-      const int j = before + __popc(m & ((1u << lane) - 1u));
-      const int pk = static_cast<int>((static_cast<unsigned>(s) & 0xffffu) | (static_cast<unsigned>(d) << 16));
-      if (j < capA) arcs[j] = pk;
-      K.pack[a0 + j] = pk;
-      K.label[a0 + j] = R.label[a0 + i];
-      K.raw[a0 + j] = i;
-    }
-    __syncthreads();
-    if (tid == 0) {
-      int t = 0;
-      for (int w = 0; w < kThreads / 32; ++w) t += warp_sum[w];
-      kept_base += t;
-    }
-    __syncthreads();
-  }
-  const int Ak = kept_base;
+  // 2. the kept arcs (source reachable), in raw order: every reachable state's raw range, placed by an exclusive scan
+  //    over the states (the raw list is sorted by source) -- shared memory for the level sweeps, workspace for the build
+  int* const koff = queue;  // the search is over
+  __shared__ int scan_tmp[kThreads];
+  for (int s = tid; s < S0; s += kThreads) koff[s] = level[s] >= 0 ? raw_end[s] - raw_first[s] : 0;
+  __syncthreads();
+  const int Ak = block_excl_scan(koff, S0, scan_tmp);
   if (Ak > capA) {  // more arcs than the shared memory this launch was sized for: the caller packs this batch elsewhere
     if (tid == 0 && atomicCAS(&totals[4], 0, 4) == 0) totals[5] = b;
     return;
   }
+  for (int s = tid; s < S0; s += kThreads) {
+    if (level[s] < 0) continue;
+    const int first = raw_first[s], n = raw_end[s] - first, at = koff[s];
+    for (int q = 0; q < n; ++q) {
+      const int d = R.dst[a0 + first + q];
+      const int pk = static_cast<int>((static_cast<unsigned>(s) & 0xffffu) | (static_cast<unsigned>(d) << 16));
+      arcs[at + q] = pk;
+      K.pack[a0 + at + q] = pk;
+      K.label[a0 + at + q] = R.label[a0 + first + q];
+      K.raw[a0 + at + q] = first + q;
+    }
+  }
+  __syncthreads();
+  for (int s = tid; s < S0; s += kThreads) {  // give the aliased arrays back
+    has_out[s] = 0;
+    lvl_out[s] = 0;
+    lvl_in[s] = 0;
+  }
+  __syncthreads();
   // 3. longest distance from the start over the kept arcs: sweep until a sweep changes nothing
   for (int s = tid; s < S0; s += kThreads) level[s] = (level[s] >= 0) ? (s == R.start ? 0 : -2) : -1;  // -2: reachable, not yet placed
   __syncthreads();
@@ -182,8 +216,15 @@ __global__ void __launch_bounds__(kThreads)
     }
     __syncthreads();
   }
-  for (int i = tid; i < Ak; i += kThreads) has_out[arcs[i] & 0xffff] = 1;
+  for (int i = tid; i < Ak; i += kThreads) {
+    const int a = arcs[i];
+    has_out[a & 0xffff] = 1;
+    atomicAdd(&lvl_out[level[a & 0xffff]], 1);
+    atomicAdd(&lvl_in[level[static_cast<unsigned>(a) >> 16]], 1);
+  }
   __syncthreads();
+  // widest level, in arcs (either direction): sizes the thread block of the DP kernels
+  for (int l = tid; l < S0; l += kThreads) atomicMax(&width_arcs, max(lvl_out[l], lvl_in[l]));
   int cs = 0, ck = 0, ml = 0;
   for (int s = tid; s < S0; s += kThreads) {
     const int l = level[s];
@@ -203,6 +244,7 @@ __global__ void __launch_bounds__(kThreads)
     stats[8 * b + 1] = Ak;
     stats[8 * b + 2] = max_level + 1;
     stats[8 * b + 3] = n_sinks;
+    stats[8 * b + 4] = width_arcs;
   }
 }
 
@@ -298,7 +340,7 @@ __global__ void __launch_bounds__(kThreads)
   unsigned short* const can_src = reinterpret_cast<unsigned short*>(p);  // [Ab] packed local source of each canonical arc
   unsigned short* const in_tmp = can_src + capA;                           // [Ab] canonical arc (local) per in-order position
   __shared__ int tmp[kThreads];
-  __shared__ int sink_cursor, width_arcs;
+  __shared__ int sink_cursor;
 
   for (int s = tid; s < S0; s += kThreads) {
     level[s] = level_g[s0 + s];
@@ -310,10 +352,7 @@ __global__ void __launch_bounds__(kThreads)
     in_ptr[i] = 0;
     in_cur[i] = 0;
   }
-  if (tid == 0) {
-    sink_cursor = 0;
-    width_arcs = 0;
-  }
+  if (tid == 0) sink_cursor = 0;
   for (int i = tid; i < A0; i += kThreads) raw[i] = K.pack[a0 + i];
   __syncthreads();
   // states per level -> level starts
@@ -372,9 +411,6 @@ __global__ void __launch_bounds__(kThreads)
   }
   block_excl_scan(out_ptr, Sb + 1, tmp);
   block_excl_scan(in_ptr, Sb + 1, tmp);
-  // widest level, in arcs (either direction): sizes the thread block of the DP kernels
-  for (int l = tid; l < nlev; l += kThreads)
-    atomicMax(&width_arcs, max(out_ptr[lvl[l + 1]] - out_ptr[lvl[l]], in_ptr[lvl[l + 1]] - in_ptr[lvl[l]]));
   // canonical (out) order: arcs of one source are contiguous in the raw list and sorted by label already
   for (int i = tid; i < A0; i += kThreads) {
     const int a = raw[i];
@@ -413,12 +449,12 @@ __global__ void __launch_bounds__(kThreads)
   for (int s = tid; s < Sb; s += kThreads) {
     O.out_ptr[s_lo + s] = a_lo + out_ptr[s];
     O.in_ptr[s_lo + s] = a_lo + in_ptr[s];
+    if (O.out_deg8) O.out_deg8[s_lo + s] = static_cast<uint8_t>(min(out_ptr[s + 1] - out_ptr[s], 255));
   }
   for (int s = tid; s < S0; s += kThreads)
     if (level[s] >= 0) O.orig_state[s_lo + new_id[s]] = s;
   for (int i = tid; i <= nlev; i += kThreads) O.level_ptr[l_lo + i] = s_lo + lvl[i];
   if (tid == 0) {
-    O.lattice_stats[8 * b + 4] = width_arcs;  // complete: an atomicMax above, several barriers ago
     O.start_state[b] = s_lo + new_id[R.start];
     if (b == gridDim.x - 1) {  // closing entries of the CSR pointers
       O.out_ptr[s_lo + Sb] = a_lo + Ab;
@@ -427,7 +463,7 @@ __global__ void __launch_bounds__(kThreads)
   }
 }
 
-size_t level_smem(int capS, int capA) { return static_cast<size_t>(2 * capS + capA) * 4; }
+size_t level_smem(int capS, int capA) { return static_cast<size_t>(4 * capS + capA) * 4; }
 size_t build_smem(int capS, int capA) { return static_cast<size_t>(8 * capS + 8 + capA) * 4 + static_cast<size_t>(capA) * 4; }
 
 }  // namespace
@@ -440,17 +476,19 @@ size_t nfst_pack_small_smem_bytes(int32_t max_states, int32_t max_arcs) {
 }
 
 size_t nfst_pack_small_workspace_bytes(int64_t n_states_raw, int64_t n_arcs_raw) {
-  // level of every raw state; the kept arcs {src | dst << 16, label, raw position}
-  return (static_cast<size_t>(n_states_raw) + 3 * static_cast<size_t>(n_arcs_raw) + 16) * 4;
+  // level of every raw state, its range in the raw arc list; the kept arcs {src | dst << 16, label, raw position}
+  return (3 * static_cast<size_t>(n_states_raw) + 3 * static_cast<size_t>(n_arcs_raw) + 16) * 4;
 }
 
 int nfst_pack_small(int32_t n_lattices, const int32_t* raw_state_off, const int32_t* raw_arc_off, const int32_t* raw_src,
                     const int32_t* raw_dst, const int32_t* raw_label, int32_t src_is_global, int32_t start_state,
-                    int32_t max_states, int32_t max_arcs, const nfst_pack_out_t* out, void* workspace, size_t workspace_bytes,
-                    int64_t n_states_raw, int64_t n_arcs_raw, void* cuda_stream) {
-  if (n_lattices <= 0 || !raw_state_off || !raw_arc_off || !out || !workspace)
-    return nfst_fail_msg(NFST_ERR_BAD_ARG, "nfst_pack_small: null argument or empty batch");
-  if (max_states < 1 || max_states > 65535 || max_arcs < 0 || max_arcs > 65535)
+                    int32_t max_states, int32_t max_arcs, int32_t max_raw_arcs, const nfst_pack_out_t* out, void* workspace,
+                    size_t workspace_bytes, int64_t n_states_raw, int64_t n_arcs_raw, int32_t phases, void* cuda_stream) {
+  if (n_lattices <= 0 || !raw_state_off || !raw_arc_off || !out || !workspace || !(phases & 3))
+    return nfst_fail_msg(NFST_ERR_BAD_ARG, "nfst_pack_small: null argument, empty batch or no phase");
+  if (n_lattices > 65535)
+    return nfst_fail_msg(NFST_ERR_TOO_LARGE, "nfst_pack_small: at most 65535 lattices per call (got %d)", n_lattices);
+  if (max_states < 1 || max_states > 65535 || max_arcs < 0 || max_arcs > 65535 || max_raw_arcs < 0)
     return nfst_fail_msg(NFST_ERR_TOO_LARGE, "nfst_pack_small: at most 65535 states and arcs per lattice (got %d, %d)", max_states,
                          max_arcs);
   if (workspace_bytes < nfst_pack_small_workspace_bytes(n_states_raw, n_arcs_raw))
@@ -459,21 +497,39 @@ int nfst_pack_small(int32_t n_lattices, const int32_t* raw_state_off, const int3
   if (smem > 227 * 1024)
     return nfst_fail_msg(NFST_ERR_TOO_LARGE, "nfst_pack_small: a lattice of %d states / %d arcs needs %zu bytes of shared memory",
                          max_states, max_arcs, smem);
+  if (!out->state_off || !out->arc_off || !out->level_off || !out->sink_off || !out->n_levels || !out->lattice_stats || !out->totals)
+    return nfst_fail_msg(NFST_ERR_BAD_ARG, "nfst_pack_small: the per-lattice outputs are required in every phase");
+  if ((phases & 2) && (!out->start_state || !out->level_ptr || !out->sinks || !out->orig_state || !out->in_ptr || !out->out_ptr ||
+                       !out->src_in || !out->label_in || !out->in2out || !out->dst_out || !out->label_out || !out->src_out ||
+                       !out->arc_origin))
+    return nfst_fail_msg(NFST_ERR_BAD_ARG, "nfst_pack_small: the build phase needs every per-state / per-arc output");
   cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
   int32_t* level_g = static_cast<int32_t*>(workspace);
-  Kept K{level_g + n_states_raw, level_g + n_states_raw + n_arcs_raw, level_g + n_states_raw + 2 * n_arcs_raw};
+  int32_t* first_g = level_g + n_states_raw;
+  int32_t* end_g = first_g + n_states_raw;
+  int32_t* kept0 = end_g + n_states_raw;
+  Kept K{kept0, kept0 + n_arcs_raw, kept0 + 2 * n_arcs_raw};
   int32_t* stats = out->lattice_stats;
   RawArcs R{raw_src, raw_dst, raw_label, raw_state_off, raw_arc_off, src_is_global, start_state};
-  PACK_CUDA_OK(cudaMemsetAsync(out->totals, 0, 8 * sizeof(int32_t), st));
   if (smem > 48 * 1024) {
     PACK_CUDA_OK(cudaFuncSetAttribute(pack_level_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     PACK_CUDA_OK(cudaFuncSetAttribute(pack_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   }
-  pack_level_kernel<<<n_lattices, kThreads, level_smem(max_states, max_arcs), st>>>(R, max_states, max_arcs, level_g, K, stats, out->totals);
-  pack_scan_kernel<<<1, kThreads, 0, st>>>(n_lattices, stats, out->state_off, out->arc_off, out->level_off, out->sink_off,
-                                          out->n_levels, out->totals);
-  pack_build_kernel<<<n_lattices, kThreads, build_smem(max_states, max_arcs), st>>>(R, max_states, max_arcs, level_g, K, *out,
-                                                                                  out->totals);
+  if (phases & 1) {
+    PACK_CUDA_OK(cudaMemsetAsync(out->totals, 0, 8 * sizeof(int32_t), st));
+    PACK_CUDA_OK(cudaMemsetAsync(first_g, 0, 2 * static_cast<size_t>(n_states_raw) * sizeof(int32_t), st));
+    if (max_raw_arcs > 0) {
+      const dim3 grid((max_raw_arcs + kThreads - 1) / kThreads, n_lattices);
+      pack_ranges_kernel<<<grid, kThreads, 0, st>>>(R, first_g, end_g, out->totals);
+    }
+    pack_level_kernel<<<n_lattices, kThreads, level_smem(max_states, max_arcs), st>>>(R, max_states, max_arcs, level_g, first_g,
+                                                                                    end_g, K, stats, out->totals);
+    pack_scan_kernel<<<1, kThreads, 0, st>>>(n_lattices, stats, out->state_off, out->arc_off, out->level_off, out->sink_off,
+                                            out->n_levels, out->totals);
+  }
+  if (phases & 2)
+    pack_build_kernel<<<n_lattices, kThreads, build_smem(max_states, max_arcs), st>>>(R, max_states, max_arcs, level_g, K, *out,
+                                                                                    out->totals);
   PACK_CUDA_OK(cudaGetLastError());
   return 0;
 }

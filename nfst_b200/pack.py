@@ -552,35 +552,38 @@ def pack_arcs(
     if B == 0:
         raise ValueError("empty batch")
     arc_lattice = arc_lattice.to(torch.int64)
+    label = label.to(torch.int64)
     so = _excl_cumsum(n_states)  # original global state offsets
+    # ---- small lattices on a GPU: the library's device packer (nfst_pack.cu); it checks the arc endpoints itself ----
+    if DEVICE_PACK and dev.type == "cuda" and sell is None and tiles is None and src.numel():
+        cnt = torch.bincount(arc_lattice, minlength=B)
+        head = torch.stack([so[-1], n_states.max(), cnt.max(), label.min(), label.max()]).cpu().tolist()  # one host read
+        S0, smax, amax = head[0], head[1], head[2]
+        if S0 >= 2**31 or src.numel() >= 2**31:
+            raise ValueError("batch too large for int32 indices; shard it")
+        if head[3] < 0 or head[4] >= vocab:
+            raise ValueError("label out of range")
+        if smax <= 65535 and B * smax * vocab < 2**62:
+            perm = torch.argsort((arc_lattice * smax + src.to(torch.int64)) * vocab + label, stable=True)  # (lattice, source, label)
+            i32c = lambda t: t[perm].to(torch.int32)  # noqa: E731
+            packed = pack_small_device(so.to(torch.int32), _excl_cumsum(cnt).to(torch.int32), i32c(src), i32c(dst), i32c(label),
+                                       vocab, src_is_global=False, max_states=smax, max_arcs=amax, n_states_raw=S0,
+                                       start_state=start_state, dense_shape=dense_shape)
+            if packed is not None:
+                packed.arc_origin = perm[packed.arc_origin]
+                if static_scores is not None:
+                    packed.static_scores = static_scores[packed.arc_origin].to(torch.float32).contiguous()
+                return packed
     S0 = int(so[-1])
     if S0 >= 2**31 or src.numel() >= 2**31:
         raise ValueError("batch too large for int32 indices; shard it")
     gsrc = so[arc_lattice] + src.to(torch.int64)
     gdst = so[arc_lattice] + dst.to(torch.int64)
-    label = label.to(torch.int64)
     if src.numel() and (int(src.min()) < 0 or int(dst.min()) < 0 or bool((src >= n_states[arc_lattice]).any())
                         or bool((dst >= n_states[arc_lattice]).any())):
         raise ValueError("arc endpoint out of range")
     if label.numel() and (int(label.min()) < 0 or int(label.max()) >= vocab):
         raise ValueError("label out of range")
-
-    # ---- small lattices on a GPU: the library's device packer (nfst_pack.cu) ----
-    if DEVICE_PACK and dev.type == "cuda" and sell is None and tiles is None and src.numel():
-        cnt = torch.bincount(arc_lattice, minlength=B)
-        head = torch.stack([n_states.max(), cnt.max()]).cpu()
-        smax, amax = int(head[0]), int(head[1])
-        if smax <= 65535 and B * smax * vocab < 2**62:
-            perm = torch.argsort((arc_lattice * smax + src.to(torch.int64)) * vocab + label, stable=True)  # (lattice, source, label)
-            i32c = lambda t: t[perm].to(torch.int32).contiguous()  # noqa: E731
-            packed = pack_small_device(so.to(torch.int32), _excl_cumsum(cnt).to(torch.int32), i32c(src), i32c(dst), i32c(label),
-                                       vocab, src_is_global=False, max_states=smax, max_arcs=amax, start_state=start_state,
-                                       dense_shape=dense_shape)
-            if packed is not None:
-                packed.arc_origin = perm[packed.arc_origin].contiguous()
-                if static_scores is not None:
-                    packed.static_scores = static_scores[packed.arc_origin].to(torch.float32).contiguous()
-                return packed
 
     # ---- levels = longest distance from the start state; -1 = unreachable (trimmed) ----
     level = torch.full((S0,), -1, dtype=torch.int64, device=dev)
@@ -895,16 +898,29 @@ DEVICE_PACK = int(os.environ.get("NFST_DEVICE_PACK", "1"))
 launch_count = 0  # launches of the library's own pack kernels (diagnostics)
 
 
+def _carve(pool: torch.Tensor, sizes):
+    """Views into ``pool`` (int32 words), each starting on a 16-byte boundary; ``sizes`` = [(name, words)]."""
+    out, at = {}, 0
+    for name, n in sizes:
+        out[name] = pool[at: at + n]
+        at += (n + 3) & ~3
+    return out, at
+
+
+def _pool_words(sizes) -> int:
+    return sum((n + 3) & ~3 for _, n in sizes)
+
+
 def pack_small_device(raw_state_off: torch.Tensor, raw_arc_off: torch.Tensor, src: torch.Tensor, dst: torch.Tensor,
                       label: torch.Tensor, vocab: int, *, src_is_global: bool, max_states: int, max_arcs: int,
-                      start_state: int = 0, dense_shape=None) -> Optional[PackedLattices]:
+                      n_states_raw: int, start_state: int = 0, dense_shape=None) -> Optional[PackedLattices]:
     """Pack a batch of small lattices with the library's device packer (``nfst_pack_small``: three launches, one
-    host read of the sizes).  ``src / dst / label``: int32 raw arcs grouped by lattice and sorted by (source,
-    label) -- the scan order of the dense tables; ``dst`` local ids, ``src`` local or (``src_is_global``) global
-    rows.  Returns None when the batch is not one for this packer (a lattice too large for one SM's shared
-    memory, or one that would not run on the small-lattice kernels): the caller then uses the tensor-op packer.
-    ``arc_origin`` of the result indexes the raw arc list.  Raises ``ValueError`` for cyclic lattices and
-    out-of-range arcs, like ``pack_arcs``."""
+    host read of the sizes between the count and the build phase, so every output has its exact size).
+    ``src / dst / label``: int32 raw arcs grouped by lattice and sorted by (source, label) -- the scan order of the
+    dense tables; ``dst`` local ids, ``src`` local or (``src_is_global``) global rows.  Returns None when the batch
+    is not one for this packer (a lattice too large for one SM's shared memory, or one that would not run on the
+    small-lattice kernels): the caller then uses the tensor-op packer.  ``arc_origin`` of the result indexes the raw
+    arc list.  Raises ``ValueError`` for cyclic lattices and out-of-range arcs, like ``pack_arcs``."""
     global launch_count
     lib = _lib.load()
     dev = src.device
@@ -916,33 +932,27 @@ def pack_small_device(raw_state_off: torch.Tensor, raw_arc_off: torch.Tensor, sr
     room = (200 * 1024 - 32 * int(max_states) - 64) // 8
     if room < 256:
         return None
-    max_arcs = max(min(int(max_arcs), 65535, room), 1)
-    S0, A0 = int(max_states) * B if dense_shape is not None else None, int(src.numel())
-    if S0 is None:
-        S0 = int(raw_state_off[-1])
-    i32 = dict(dtype=torch.int32, device=dev)
-    o = {
-        "state_off": torch.empty(B + 1, **i32), "arc_off": torch.empty(B + 1, **i32), "level_off": torch.empty(B + 1, **i32),
-        "sink_off": torch.empty(B + 1, **i32), "n_levels": torch.empty(B, **i32), "start_state": torch.empty(B, **i32),
-        "level_ptr": torch.empty(S0 + B + 4, **i32), "sinks": torch.empty(S0 + 4, **i32), "orig_state": torch.empty(S0 + 4, **i32),
-        "in_ptr": torch.zeros(S0 + 1 + PackedLattices.PAD, **i32), "out_ptr": torch.zeros(S0 + 1 + PackedLattices.PAD, **i32),
-        "src_in": torch.zeros(A0 + PackedLattices.PAD, **i32), "label_in": torch.zeros(A0 + PackedLattices.PAD, **i32),
-        "in2out": torch.zeros(A0 + PackedLattices.PAD, **i32), "dst_out": torch.zeros(A0 + PackedLattices.PAD, **i32),
-        "label_out": torch.zeros(A0 + PackedLattices.PAD, **i32), "src_out": torch.empty(A0 + 4, **i32),
-        "arc_origin": torch.empty(A0 + 4, dtype=torch.int64, device=dev),
-        "lattice_stats": torch.zeros(B * 8 + 8, **i32),  # ... and the totals behind them: one host read
-    }
-    o["totals"] = o["lattice_stats"][B * 8:]
+    max_raw = int(max_arcs)
+    max_arcs = max(min(max_raw, 65535, room), 1)
+    if B > 65535:
+        return None
+    S0, A0 = int(n_states_raw), int(src.numel())
+    PAD = PackedLattices.PAD
+    # ---- phase 1: levels, trimming, per-lattice counts and offsets (two launches) ----
+    small = [("state_off", B + 1), ("arc_off", B + 1), ("level_off", B + 1), ("sink_off", B + 1), ("n_levels", B),
+             ("start_state", B), ("lanes", (2 * B + 3) // 4), ("lattice_stats", 8 * B + 8)]
+    o, _ = _carve(torch.zeros(_pool_words(small), dtype=torch.int32, device=dev), small)
+    o["totals"] = o["lattice_stats"][8 * B:]
     out = _lib.PackOutC()
-    for k, t in o.items():
-        setattr(out, k, t.data_ptr())
+    for k in ("state_off", "arc_off", "level_off", "sink_off", "n_levels", "start_state", "lattice_stats", "totals"):
+        setattr(out, k, o[k].data_ptr())
     ws_bytes = int(lib.nfst_pack_small_workspace_bytes(S0, A0))
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
     st = torch.cuda.current_stream(dev).cuda_stream
+    args = (B, raw_state_off.data_ptr(), raw_arc_off.data_ptr(), src.data_ptr(), dst.data_ptr(), label.data_ptr(),
+            int(src_is_global), int(start_state), int(max_states))
     with torch.cuda.device(dev):
-        _lib.check(lib.nfst_pack_small(B, raw_state_off.data_ptr(), raw_arc_off.data_ptr(), src.data_ptr(), dst.data_ptr(),
-                                       label.data_ptr(), int(src_is_global), int(start_state), int(max_states), int(max_arcs),
-                                       C.byref(out), ws.data_ptr(), ws_bytes, S0, A0, st))
+        _lib.check(lib.nfst_pack_small(*args, int(max_arcs), max_raw, C.byref(out), ws.data_ptr(), ws_bytes, S0, A0, 1, st))
     launch_count += 3
     host = o["lattice_stats"].cpu()  # the pack's host synchronisation
     totals, per = host[B * 8:].tolist(), host[:B * 8].view(B, 8).to(torch.int64)
@@ -955,50 +965,67 @@ def pack_small_device(raw_state_off: torch.Tensor, raw_arc_off: torch.Tensor, sr
     if totals[4]:
         raise ValueError("batch too large for int32 indices; shard it")
     S, A, n_lp, n_sink = totals[0], totals[1], totals[2], totals[3]
-    width_arcs = per[:, 4]
+    st_b, ar_b, lv_b = per[:, 0], per[:, 1], per[:, 2]
+    # do these lattices belong on the small-lattice kernels?
+    foot = small_footprint_bytes(st_b, ar_b, lv_b, int(vocab))
+    other = (foot > SMALL_SMEM_BYTES) | (per[:, 4] >= LEVEL_MODE_MIN_ARCS)
+    if tiles_mod.TILES:
+        other |= st_b >= tiles_mod.TILE_MIN_WIDTH * lv_b
+    if SELL:
+        other |= st_b >= SELL_MIN_WIDTH * lv_b
+    if bool(other.any()):
+        return None  # some lattice belongs on the chunked / column-major kernels: those layouts come from pack_arcs
+    # ---- phase 2: the packed arrays at their exact sizes (one launch) ----
+    big = [("level_ptr", n_lp), ("sinks", n_sink), ("orig_state", S), ("in_ptr", S + 1 + PAD), ("out_ptr", S + 1 + PAD),
+           ("src_in", A + PAD), ("label_in", A + PAD), ("in2out", A + PAD), ("dst_out", A + PAD), ("label_out", A + PAD),
+           ("src_out", A), ("out_deg8", (S + PAD + 3) // 4), ("sell_lvl_slice", n_lp)]
+    ob, _ = _carve(torch.zeros(_pool_words(big), dtype=torch.int32, device=dev), big)
+    arc_origin = torch.empty(A, dtype=torch.int64, device=dev)
+    deg8 = ob["out_deg8"].view(torch.uint8)
+    for k in ("level_ptr", "sinks", "orig_state", "in_ptr", "out_ptr", "src_in", "label_in", "in2out", "dst_out", "label_out",
+              "src_out"):
+        setattr(out, k, ob[k].data_ptr())
+    out.arc_origin, out.out_deg8 = arc_origin.data_ptr(), deg8.data_ptr()
+    kept_max = max(int(ar_b.max()), 1)
+    with torch.cuda.device(dev):
+        _lib.check(lib.nfst_pack_small(*args, kept_max, max_raw, C.byref(out), ws.data_ptr(), ws_bytes, S0, A0, 2, st))
+    launch_count += 1
+    width_arcs = per[:, 4]  # arcs of the widest level: sizes the thread block of the DP kernels
     bmax = int(math.log2(BLOCK_MAX))
     block_class = torch.clamp(torch.ceil(torch.log2(torch.clamp(width_arcs.to(torch.float64) / ARCS_PER_THREAD, min=32.0))), 5, bmax).to(torch.int64)
     zeros = torch.zeros(B, dtype=torch.int64)
     stats = {
-        "width_arcs": width_arcs, "arcs": per[:, 1].clone(), "states": per[:, 0].clone(), "levels": per[:, 2].clone(),
+        "width_arcs": width_arcs, "arcs": ar_b.clone(), "states": st_b.clone(), "levels": lv_b.clone(),
         "block_class": block_class, "vocab": torch.full((B,), int(vocab), dtype=torch.int64),
         "chunk_cap": torch.tensor([chunk_geometry(1 << int(k))[2] for k in block_class.tolist()], dtype=torch.int64),
-        "reach": per[:, 0].clone(), "sell": torch.zeros(B, dtype=torch.bool), "sell_bound": zeros, "sell_window": zeros + 32,
+        "reach": st_b.clone(), "sell": torch.zeros(B, dtype=torch.bool), "sell_bound": zeros, "sell_window": zeros + 32,
         "sell_block": zeros + 2, "tile": torch.zeros(B, dtype=torch.bool), "tile_warps_log2": zeros, "tile_ring": zeros,
         "tile_far": zeros, "tile_cap_arcs": zeros, "tile_cap_bytes": zeros,
     }
-    foot = small_footprint_bytes(stats["states"], stats["arcs"], stats["levels"], int(vocab))
-    other = (foot > SMALL_SMEM_BYTES) | (width_arcs >= LEVEL_MODE_MIN_ARCS)
-    if tiles_mod.TILES:
-        other |= stats["states"] >= tiles_mod.TILE_MIN_WIDTH * stats["levels"]
-    if SELL:
-        other |= stats["states"] >= SELL_MIN_WIDTH * stats["levels"]
-    if bool(other.any()):
-        return None  # some lattice belongs on the chunked / column-major kernels: those layouts come from pack_arcs
     groups = build_groups(stats, dev)
 
-    def view(name, n):
-        t = o[name][:n]
-        t._nfst_padded = name in PackedLattices._ARC_FIELDS  # allocated with PAD zeroed elements behind the view
+    def arc_view(name, n):  # allocated with PAD zeroed elements behind the view
+        t = ob[name][:n]
+        t._nfst_padded = True
         return t
 
-    e32 = torch.zeros(0, **i32)
-    out_deg = o["out_ptr"][1:S + 1] - o["out_ptr"][:S]
+    i32 = dict(dtype=torch.int32, device=dev)
+    e32, e4, lanes = torch.zeros(0, **i32), torch.zeros((0, 4), **i32), o["lanes"].view(torch.uint8)
+    d8 = deg8[:S]
+    d8._nfst_padded = True
     return PackedLattices(
         n_lattices=B, n_states=S, n_arcs=A, vocab=int(vocab),
-        state_off=o["state_off"], level_off=o["level_off"], level_ptr=view("level_ptr", n_lp), start_state=o["start_state"],
-        sink_off=o["sink_off"], sinks=view("sinks", n_sink), in_ptr=view("in_ptr", S + 1), src_in=view("src_in", A),
-        label_in=view("label_in", A), in2out=view("in2out", A), out_ptr=view("out_ptr", S + 1), dst_out=view("dst_out", A),
-        label_out=view("label_out", A),
-        fwd_chunk_off=torch.zeros(B + 1, **i32), fwd_chunks=torch.zeros((0, 4), **i32), bwd_chunk_off=torch.zeros(B + 1, **i32),
-        bwd_chunks=torch.zeros((0, 4), **i32), fwd_gather=torch.zeros((0, 2), **i32), fwd_chunk_level=e32, bwd_chunk_level=e32,
-        bwd_order=torch.arange(S, **i32), sell_desc=torch.zeros((0, 4), **i32), sell_lvl_slice=torch.zeros(n_lp, **i32),
-        tile_stream=torch.zeros(16, dtype=torch.uint8, device=dev), tile_tab=torch.zeros((0, 4), **i32),
-        tile_lw_off=torch.zeros(1, **i32), tile_lat_info=torch.zeros((B, 4), **i32), out_arc=e32,
-        lanes_in_log2=torch.zeros(B, dtype=torch.uint8, device=dev), lanes_out_log2=torch.zeros(B, dtype=torch.uint8, device=dev),
-        out_deg8=torch.clamp(out_deg, max=255).to(torch.uint8), src_out=view("src_out", A), orig_state=view("orig_state", S),
-        arc_origin=view("arc_origin", A), arc_off=o["arc_off"], n_levels=o["n_levels"], static_scores=None,
-        dense_shape=dense_shape, groups=groups, max_levels=int(totals[6]), stats=stats,
+        state_off=o["state_off"], level_off=o["level_off"], level_ptr=ob["level_ptr"], start_state=o["start_state"],
+        sink_off=o["sink_off"], sinks=ob["sinks"], in_ptr=arc_view("in_ptr", S + 1), src_in=arc_view("src_in", A),
+        label_in=arc_view("label_in", A), in2out=arc_view("in2out", A), out_ptr=arc_view("out_ptr", S + 1),
+        dst_out=arc_view("dst_out", A), label_out=arc_view("label_out", A),
+        fwd_chunk_off=torch.zeros(B + 1, **i32), fwd_chunks=e4, bwd_chunk_off=torch.zeros(B + 1, **i32), bwd_chunks=e4,
+        fwd_gather=torch.zeros((0, 2), **i32), fwd_chunk_level=e32, bwd_chunk_level=e32,
+        bwd_order=torch.arange(S, **i32), sell_desc=e4, sell_lvl_slice=ob["sell_lvl_slice"],
+        tile_stream=torch.zeros(16, dtype=torch.uint8, device=dev), tile_tab=e4, tile_lw_off=torch.zeros(1, **i32),
+        tile_lat_info=torch.zeros((B, 4), **i32), out_arc=e32, lanes_in_log2=lanes[:B], lanes_out_log2=lanes[B:2 * B],
+        out_deg8=d8, src_out=ob["src_out"], orig_state=ob["orig_state"], arc_origin=arc_origin, arc_off=o["arc_off"],
+        n_levels=o["n_levels"], static_scores=None, dense_shape=dense_shape, groups=groups, max_levels=int(totals[6]), stats=stats,
     )
 
 
@@ -1021,11 +1048,12 @@ def pack_dense(emission: Optional[torch.Tensor], transition: torch.Tensor, *,
             raw_state_off = torch.arange(B + 1, dtype=torch.int32, device=transition.device) * S
             try:
                 packed = pack_small_device(raw_state_off, lat_off.to(torch.int32), row32, dst32, lab32, V, src_is_global=True,
-                                           max_states=S, max_arcs=max_arcs, dense_shape=(B, S, V))
+                                           max_states=S, max_arcs=max_arcs, n_states_raw=B * S, dense_shape=(B, S, V))
             except ValueError as e:
                 raise ValueError("transition points outside the table" if "out of range" in str(e) else str(e)) from None
             if packed is not None:
-                cell = (row32.to(torch.int64) * V + lab32.to(torch.int64))[packed.arc_origin]  # (b*S+s)*V+l of each arc
+                ao = packed.arc_origin  # raw arc index of every kept arc -> its dense cell (b*S+s)*V+l
+                cell = row32[ao].to(torch.int64) * V + lab32[ao].to(torch.int64)
                 if weighted:
                     packed.static_scores = emission.reshape(-1)[cell].to(torch.float32).contiguous()
                 packed.arc_origin = cell.contiguous()

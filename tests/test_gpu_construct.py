@@ -56,7 +56,7 @@ def test_device_built_lattices_equal_the_host_construction(add_sub):
         marks["sub_mark"] = None
     before = P.launch_count
     p = construct.edit_lattices(xs, ys, vocab=V, **marks)
-    assert P.launch_count == before + 3 and all(g.small_max_arcs > 0 for g in p.groups), "packed on the device"
+    assert P.launch_count == before + 4 and all(g.small_max_arcs > 0 for g in p.groups), "packed on the device"
     theta = torch.randn(V, generator=torch.Generator().manual_seed(3))
     logz = nb.lattice_log_partition(p, theta=theta.to(DEV)).cpu().numpy()
     vs, voff, varcs, vlab = nb.lattice_viterbi(p, theta=theta.to(DEV))
