@@ -56,7 +56,7 @@
 extern "C" {
 #endif
 
-#define NFST_ABI_VERSION 15
+#define NFST_ABI_VERSION 16
 
 typedef enum nfst_status {
   NFST_OK = 0,
@@ -497,6 +497,15 @@ int nfst_edit_lattice_arcs(int32_t n_lattices, const int32_t* x, const int32_t* 
                            const int32_t* y_len, int32_t y_stride, int32_t bos, int32_t eos, int32_t input_mark,
                            int32_t output_mark, int32_t sub_mark, int32_t add_sub, const int32_t* raw_arc_off, int32_t* src,
                            int32_t* dst, int32_t* label, void* cuda_stream);
+
+/*
+ * n_sweeps relaxation sweeps of level[dst] = max(level[dst], level[src] + 1) over an arc list with GLOBAL state ids
+ * (int64), in place; level[] = 0 at the start states and -1 elsewhere on entry.  *changed (device, caller-zeroed) is
+ * set when a sweep moved anything: the caller repeats until it stays 0 -- the longest distance from the start states
+ * (the topological levels of the tensor-op packer; more sweeps than states = a cycle).
+ */
+int nfst_level_sweeps(const int64_t* gsrc, const int64_t* gdst, int64_t n_arcs, int32_t* level, int32_t* changed,
+                      int32_t n_sweeps, void* cuda_stream);
 
 #ifdef __cplusplus
 }

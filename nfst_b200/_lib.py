@@ -137,6 +137,7 @@ SYMBOLS = {
                                   C.c_size_t, C.c_int64, C.c_int64, C.c_int32, _P]),
     "nfst_edit_lattice_size": (None, [C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "nfst_edit_lattice_arcs": (C.c_int, [C.c_int32, _P, _P, C.c_int32, _P, _P, C.c_int32] + [C.c_int32] * 6 + [_P, _P, _P, _P, _P]),
+    "nfst_level_sweeps": (C.c_int, [_P, _P, C.c_int64, _P, _P, C.c_int32, _P]),
     "nfst_dense_count_arcs": (C.c_int, [_P, C.c_int64, C.c_int32, C.c_int32, _P, _P]),
     "nfst_dense_extract_arcs": (C.c_int, [_P, C.c_int64, C.c_int32, C.c_int32, _P, _P, _P, _P, _P]),
 }
@@ -164,7 +165,7 @@ def load() -> C.CDLL:
         fn = getattr(lib, name)  # AttributeError if the header and the library disagree
         fn.restype = res
         fn.argtypes = args
-    if lib.nfst_abi_version() != 15:
+    if lib.nfst_abi_version() != 16:
         raise RuntimeError("libnfst_b200.so ABI version mismatch")
     _lib = lib
     return lib

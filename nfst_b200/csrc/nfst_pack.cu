@@ -640,3 +640,36 @@ int nfst_edit_lattice_arcs(int32_t n_lattices, const int32_t* x, const int32_t* 
 }
 
 }  // extern "C"
+
+// =========================================================================================================
+// Level sweeps for the tensor-op packer (lattices too large for nfst_pack_small)
+// =========================================================================================================
+// level[dst] = max(level[dst], level[src] + 1) over all arcs, in place (atomicMax: updates are visible to the rest of
+// the sweep, so a sweep usually settles several levels); *changed is set when anything moved.  The caller repeats
+// until a sweep changes nothing -- the fixed point is the longest distance from the start states, whatever the order.
+namespace {
+__global__ void __launch_bounds__(256)
+    level_sweep_kernel(const int64_t* __restrict__ gsrc, const int64_t* __restrict__ gdst, int64_t n_arcs, int32_t* level,
+                       int32_t* __restrict__ changed) {
+  bool moved = false;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n_arcs;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int ls = level[gsrc[i]];
+    if (ls >= 0 && atomicMax(&level[gdst[i]], ls + 1) < ls + 1) moved = true;
+  }
+  if (__any_sync(0xffffffffu, moved) && (threadIdx.x & 31) == 0) *changed = 1;
+}
+}  // namespace
+
+extern "C" int nfst_level_sweeps(const int64_t* gsrc, const int64_t* gdst, int64_t n_arcs, int32_t* level, int32_t* changed,
+                                 int32_t n_sweeps, void* cuda_stream) {
+  if (!gsrc || !gdst || !level || !changed || n_arcs < 0 || n_sweeps < 1)
+    return nfst_fail_msg(NFST_ERR_BAD_ARG, "nfst_level_sweeps: null argument");
+  if (n_arcs == 0) return 0;
+  const int64_t want = (n_arcs + 255) / 256;
+  const int blocks = static_cast<int>(want < 148 * 16 ? want : 148 * 16);
+  for (int k = 0; k < n_sweeps; ++k)
+    level_sweep_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(cuda_stream)>>>(gsrc, gdst, n_arcs, level, changed);
+  PACK_CUDA_OK(cudaGetLastError());
+  return 0;
+}

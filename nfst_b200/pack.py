@@ -38,6 +38,29 @@ import torch
 from . import _lib
 from . import tiles as tiles_mod
 
+
+PACK_TIMING = int(os.environ.get("NFST_PACK_TIMING", "0"))
+phase_ms = {}  # NFST_PACK_TIMING=1: milliseconds per packer phase (device-synchronised), accumulated
+_phase_state = [None, 0.0]
+
+
+def _phase(name, dev=None):
+    """Timing hook (off by default): closes the running phase and opens ``name``."""
+    if not PACK_TIMING:
+        return
+    import time
+
+    if dev is not None and dev.type == "cuda":
+        torch.cuda.synchronize(dev)
+    now = time.perf_counter()
+    if _phase_state[0] is not None:
+        phase_ms[_phase_state[0]] = phase_ms.get(_phase_state[0], 0.0) + 1e3 * (now - _phase_state[1])
+    if name is None:
+        _phase_state[0] = None
+        return
+    _phase_state[0], _phase_state[1] = name, now
+
+
 # shared-memory window of the most recent per-state DP values, in bytes per state vector
 WINDOW_BYTES_MAX = int(os.environ.get("NFST_WINDOW_BYTES", str(64 * 1024)))
 # chunk geometry (tunable): a chunk targets ARCS_PER_THREAD arcs per thread of a block of at
@@ -585,12 +608,30 @@ def pack_arcs(
     if label.numel() and (int(label.min()) < 0 or int(label.max()) >= vocab):
         raise ValueError("label out of range")
 
+    _phase("pack: levels = longest distance from the start", dev)
     # ---- levels = longest distance from the start state; -1 = unreachable (trimmed) ----
     level = torch.full((S0,), -1, dtype=torch.int64, device=dev)
     level[so[:-1] + start_state] = 0
     max_iter = int(n_states.max()) if B else 0
     it = 0
-    while gsrc.numel():
+    if dev.type == "cuda" and gsrc.numel():
+        # the library's sweep kernel: in place, several levels settle per sweep; one flag read per round of 4 sweeps
+        lib = _lib.load()
+        level32 = level.to(torch.int32)
+        changed = torch.zeros(1, dtype=torch.int32, device=dev)
+        gs, gd = gsrc.contiguous(), gdst.contiguous()
+        st = torch.cuda.current_stream(dev).cuda_stream
+        while True:
+            with torch.cuda.device(dev):
+                _lib.check(lib.nfst_level_sweeps(gs.data_ptr(), gd.data_ptr(), gs.numel(), level32.data_ptr(), changed.data_ptr(), 4, st))
+            if int(changed) == 0:
+                break
+            changed.zero_()
+            it += 4
+            if it > max_iter + 8:
+                raise ValueError("lattice is cyclic: the DP is defined for acyclic lattices only")
+        level = level32.to(torch.int64)
+    while dev.type != "cuda" and gsrc.numel():
         before = level
         for _ in range(8):  # relaxation sweeps between convergence checks (each check is a host sync)
             ls = level[gsrc]
@@ -601,6 +642,7 @@ def pack_arcs(
         if it > max_iter + 8:
             raise ValueError("lattice is cyclic: the DP is defined for acyclic lattices only")
 
+    _phase("pack: state renumbering", dev)
     # ---- state renumbering: (lattice, level, degree key, original id) ----
     lat_of_state = torch.repeat_interleave(torch.arange(B, device=dev), n_states)
     kept = torch.nonzero(level >= 0).squeeze(1)
@@ -620,33 +662,7 @@ def pack_arcs(
     level_ptr = torch.cumsum(counts, 0) - counts  # exclusive; the spare slot of lattice b lands on state_off[b+1]
     S_b0 = torch.bincount(lt, minlength=B)
 
-    # ---- sliced-column eligibility (nfst_sell.cu): wide levels, out-degree <= 255, bounded arc span ----
-    sell_lat = torch.zeros(B, dtype=torch.bool, device=dev)
-    sell_bound = torch.zeros(B, dtype=torch.int64, device=dev)
-    sell_win = torch.full((B,), 32, dtype=torch.int64, device=dev)
-    if (SELL if sell is None else sell) and kept.numel():
-        slot_of = torch.full((S0,), 0, dtype=torch.int64, device=dev)
-        slot_of[kept] = slot_kept
-        # arcs into the LAST level need no ring: its states are final (beta = 0, delta = 0), the kernels
-        # know them by their id
-        inner = live & (level[gdst] < n_levels[arc_lattice] - 1)
-        la = arc_lattice[inner]
-        span = (level_ptr[slot_of[gdst[inner]]] + counts[slot_of[gdst[inner]]]) - level_ptr[slot_of[gsrc[inner]]]
-        sell_bound = sell_bound.scatter_reduce(0, la, span, reduce="amax")
-        sell_lat = S_b0 >= SELL_MIN_WIDTH * n_levels
-        # ring size: covers SELL_WINDOW_QUANTILE of the lattice's arcs (log2 histogram of the spans); the few
-        # longer ones -- e.g. dead ends wired to the sink -- go through global memory
-        lgs = torch.ceil(torch.log2(span.to(torch.float64))).to(torch.int64).clamp_(0, 31)
-        cum = torch.cumsum(torch.bincount(la * 32 + lgs, minlength=B * 32).view(B, 32), 1)
-        need = torch.ceil(cum[:, -1:].to(torch.float64) * SELL_WINDOW_QUANTILE).to(torch.int64)
-        sell_win = torch.clamp(torch.ones(B, dtype=torch.int64, device=dev) << (cum < need).sum(1), min=32)
-        # ... and a whole level: two states of one level must never share a ring slot
-        slot_lat0 = torch.repeat_interleave(torch.arange(B, device=dev), n_levels + 1)
-        lvl_width = torch.zeros(B, dtype=torch.int64, device=dev).scatter_reduce(0, slot_lat0, counts, reduce="amax")
-        pow2_width = torch.ones(B, dtype=torch.int64, device=dev) << torch.ceil(
-            torch.log2(torch.clamp(lvl_width, min=1).to(torch.float64))).to(torch.int64)
-        sell_win = torch.maximum(sell_win, pow2_width)
-        sell_lat = sell_lat & (sell_win <= SELL_WINDOW_MAX)
+    _phase("pack: sliced-column eligibility", dev)
     # tile-stream eligibility (nfst_tiles.cu): levels at least a slice wide; every level must fit the largest ring
     tile_lat = torch.zeros(B, dtype=torch.bool, device=dev)
     tile_nw = torch.ones(B, dtype=torch.int64, device=dev)
@@ -669,7 +685,34 @@ def pack_arcs(
         # the ring must hold the widest level (every warp's share rounded up to whole slices) with room to spare, and
         # the destinations that outlive it must fit the far table
         tile_lat = (S_b0 >= tiles_mod.TILE_MIN_WIDTH * n_levels) & (lvl_width1 + 32 * tile_nw + 512 <= cap1) & (far1 <= cap1 // 8)
-        sell_lat = sell_lat & ~tile_lat
+    # ---- sliced-column eligibility (nfst_sell.cu): wide levels, out-degree <= 255, bounded arc span ----
+    sell_lat = torch.zeros(B, dtype=torch.bool, device=dev)
+    sell_bound = torch.zeros(B, dtype=torch.int64, device=dev)
+    sell_win = torch.full((B,), 32, dtype=torch.int64, device=dev)
+    # (tile-stream lattices win where both layouts apply: when they take the whole batch this block is skipped)
+    if (SELL if sell is None else sell) and kept.numel() and not bool(tile_lat.all()):
+        slot_of = torch.full((S0,), 0, dtype=torch.int64, device=dev)
+        slot_of[kept] = slot_kept
+        # arcs into the LAST level need no ring: its states are final (beta = 0, delta = 0), the kernels
+        # know them by their id
+        inner = live & (level[gdst] < n_levels[arc_lattice] - 1)
+        la = arc_lattice[inner]
+        span = (level_ptr[slot_of[gdst[inner]]] + counts[slot_of[gdst[inner]]]) - level_ptr[slot_of[gsrc[inner]]]
+        sell_bound = sell_bound.scatter_reduce(0, la, span, reduce="amax")
+        sell_lat = S_b0 >= SELL_MIN_WIDTH * n_levels
+        # ring size: covers SELL_WINDOW_QUANTILE of the lattice's arcs (log2 histogram of the spans); the few
+        # longer ones -- e.g. dead ends wired to the sink -- go through global memory
+        lgs = torch.ceil(torch.log2(span.to(torch.float64))).to(torch.int64).clamp_(0, 31)
+        cum = torch.cumsum(torch.bincount(la * 32 + lgs, minlength=B * 32).view(B, 32), 1)
+        need = torch.ceil(cum[:, -1:].to(torch.float64) * SELL_WINDOW_QUANTILE).to(torch.int64)
+        sell_win = torch.clamp(torch.ones(B, dtype=torch.int64, device=dev) << (cum < need).sum(1), min=32)
+        # ... and a whole level: two states of one level must never share a ring slot
+        slot_lat0 = torch.repeat_interleave(torch.arange(B, device=dev), n_levels + 1)
+        lvl_width = torch.zeros(B, dtype=torch.int64, device=dev).scatter_reduce(0, slot_lat0, counts, reduce="amax")
+        pow2_width = torch.ones(B, dtype=torch.int64, device=dev) << torch.ceil(
+            torch.log2(torch.clamp(lvl_width, min=1).to(torch.float64))).to(torch.int64)
+        sell_win = torch.maximum(sell_win, pow2_width)
+        sell_lat = sell_lat & (sell_win <= SELL_WINDOW_MAX) & ~tile_lat
     col_lat = sell_lat | tile_lat
     # inside a level states are ordered by (in-degree, out-degree): the 32 states a warp reduces then
     # have (nearly) equal segment lengths in both passes; column-major lattices by out-degree,
@@ -696,6 +739,7 @@ def pack_arcs(
     orig_state = kept_sorted - so[lt_s]
     start_packed = new_id[so[:-1] + start_state]
 
+    _phase("pack: arcs", dev)
     # ---- arcs: canonical (out) order and in order ----
     origin = torch.nonzero(level[gsrc] >= 0).squeeze(1)
     ns, nd, lb = new_id[gsrc[origin]], new_id[gdst[origin]], label[origin]
@@ -734,6 +778,7 @@ def pack_arcs(
     sink_off = _excl_cumsum(torch.bincount(sink_lat, minlength=B))
     arc_off = out_ptr[state_off]
 
+    _phase("pack: slice descriptors of the sliced-column l", dev)
     # ---- slice descriptors of the sliced-column lattices (nfst_packed_lattices_t.sell_desc) ----
     sell_slot = torch.repeat_interleave(sell_lat, n_levels + 1)
     nsl_slot = torch.where(sell_slot, (counts + 31) // 32, torch.zeros_like(counts))
@@ -756,6 +801,7 @@ def pack_arcs(
         sell_desc[:, 3] = cs[:, 4] | (cs[:, 5] << 8) | (cs[:, 6] << 16) | (dmax8 << 24)
         sell_desc = torch.where(sell_desc >= 2**31, sell_desc - 2**32, sell_desc)  # bit pattern as int32
 
+    _phase("pack: tile-stream lattices", dev)
     # ---- tile-stream lattices: slices, ring slots, tiles, byte stream ----
     if st_w is None:
         st_w = st_j = torch.zeros(S, dtype=torch.int64, device=dev)
@@ -763,6 +809,7 @@ def pack_arcs(
                                 st_j=st_j, out_ptr=out_ptr, out_deg=out_deg, src_out=src_out, dst_out=dst_out,
                                 tile_lat=tile_lat, tile_nw=tile_nw, state_off=state_off, n_lattices=B)
 
+    _phase("pack: per-lattice shape statistics -> lanes pe", dev)
     # ---- per-lattice shape statistics -> lanes per state, block size, launch groups ----
     A_b = (arc_off[1:] - arc_off[:-1]).to(torch.float64)
     S_b = state_off[1:] - state_off[:-1]
@@ -833,8 +880,9 @@ def pack_arcs(
     groups = build_groups(stats, dev, {"fwd": (fwd_chunk_off, fwd_chunks, fwd_chunk_level),
                                        "bwd": (bwd_chunk_off, bwd_chunks, bwd_chunk_level)})
 
+    _phase("pack: final int32 conversion", dev)
     i32 = lambda t: t.to(torch.int32).contiguous()  # noqa: E731
-    return PackedLattices(
+    packed_result = PackedLattices(
         n_lattices=B, n_states=S, n_arcs=A, vocab=int(vocab),
         state_off=i32(state_off), level_off=i32(level_off), level_ptr=i32(level_ptr), start_state=i32(start_packed),
         sink_off=i32(sink_off), sinks=i32(sinks), in_ptr=i32(in_ptr), src_in=i32(src_in), label_in=i32(label_in),
@@ -850,6 +898,8 @@ def pack_arcs(
         static_scores=None if static_scores is None else static_scores[origin].to(torch.float32).contiguous(),
         dense_shape=dense_shape, groups=groups, max_levels=int(n_levels.max()) if B else 0, stats=stats,
     )
+    _phase(None, dev)
+    return packed_result
 
 
 def _dense_arcs_cuda(transition: torch.Tensor):

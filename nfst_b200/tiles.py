@@ -32,6 +32,13 @@ from typing import Dict
 
 import torch
 
+
+def _phase(name, dev=None):
+    from .pack import _phase as p
+
+    p(name, dev)
+
+
 TILES = int(os.environ.get("NFST_TILES", "1"))
 # lattices whose levels average at least this many states take the tile-stream path
 TILE_MIN_WIDTH = int(os.environ.get("NFST_TILE_MIN_WIDTH", "32"))
@@ -163,6 +170,7 @@ def build(*, lt_s, slot, level_off, level_ptr, n_levels, st_w, st_j, out_ptr, ou
         return empty
     S = int(lt_s.numel())
 
+    _phase("tiles: slices", dev)
     # ---- slices ----
     jmax = int(st_j[ts].max()) + 1
     sl_key = (slot[ts] * NW_MAX + st_w[ts]) * jmax + st_j[ts]
@@ -188,6 +196,7 @@ def build(*, lt_s, slot, level_off, level_ptr, n_levels, st_w, st_j, out_ptr, ou
     # degrees must descend inside a regular slice (column k = a prefix of the lanes)
     lane_ts = ts - sl_first[slice_of_ts]
 
+    _phase("tiles: ring", dev)
     # ---- ring: 32 slots per slice, in slice order ----
     lat_slices = torch.bincount(sl_lat, minlength=B)
     lat_first_slice = _excl_cumsum(lat_slices)[:-1]
@@ -251,6 +260,7 @@ def build(*, lt_s, slot, level_off, level_ptr, n_levels, st_w, st_j, out_ptr, ou
                        torch.where(far, far_slot[a_dst], Wa))
     sl_vslot = (32 * sl_ord) % W[sl_lat]
 
+    _phase("tiles: segments", dev)
     # ---- segments (one header each): regular slices, heavy slices cut into pieces of T arcs ----
     T = T_lat[sl_lat]  # per slice
     n_seg = torch.where(sl_heavy, torch.clamp((sl_arcs + T - 1) // T, min=1), torch.ones_like(sl_arcs))
@@ -269,6 +279,7 @@ def build(*, lt_s, slot, level_off, level_ptr, n_levels, st_w, st_j, out_ptr, ou
     seg_farb = (~seg_heavy) & ((sl_flags[seg_slice] & FLAG_FAR_IN) > 0)  # 64-byte block: far-table slot per lane
     seg_ext_units = seg_ext.to(torch.int64) + 2 * seg_farb.to(torch.int64)  # in 32-byte units
 
+    _phase("tiles: tiles", dev)
     # ---- tiles: consecutive segments of one (level, warp); heavy pieces stand alone ----
     g = (sl_slot * NW_MAX + sl_w)[seg_slice]
     g_new = torch.ones(NSEG, dtype=torch.bool, device=dev)
@@ -313,6 +324,7 @@ def build(*, lt_s, slot, level_off, level_ptr, n_levels, st_w, st_j, out_ptr, ou
     n_bytes = int(t_off[-1])
     t_off = t_off[:-1]
 
+    _phase("tiles: the byte stream, written as 16-bit words", dev)
     # ---- the byte stream, written as 16-bit words ----
     stream = torch.zeros(n_bytes // 2, dtype=torch.int32, device=dev)  # values 0..65535, narrowed at the end
 
@@ -376,6 +388,7 @@ def build(*, lt_s, slot, level_off, level_ptr, n_levels, st_w, st_j, out_ptr, ou
     put16(t_off[a_tile] + t_dst_off[a_tile] + 2 * (at - t_arc0[a_tile]), code)
     tile_stream = stream.to(torch.int16).view(torch.uint8)  # little-endian 16-bit words
 
+    _phase("tiles: tile table", dev)
     # ---- tile table: per (lattice, warp) in level order ----
     lmax = int(t_level.max()) + 1
     t_order = torch.argsort((t_lat * NW_MAX + t_w) * lmax + t_level, stable=True)
