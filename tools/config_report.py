@@ -217,6 +217,28 @@ def walk_step_report(B=32, k=16):
           f"vs packed arcs {p.n_arcs * 8 / 1e6:.2f} MB", flush=True)
 
 
+def compute_beta_report(B=32, k=16):
+    """The drop-in call itself on config 1 as the reference holds it: FSAGRUScorer.compute_beta() on collate()-padded
+    dense [B, S, V] tables (scorers.py:753-875) -> nb.compute_beta(emission, transition, theta, k): dense scan + device
+    packer + fused backward kernel + expansion to beta[B*k, S]; and the same with the pack cached."""
+    ab = synth.transliteration_batch(B, seed=0)
+    S, V = int(ab.n_states.max()), ab.vocab
+    tr = torch.full((B, S, V), synth.PAD, dtype=torch.int64)
+    for b in range(B):
+        tr[b, : int(ab.n_states[b])] = 0
+    tr[ab.arc_lattice, ab.src, ab.label] = ab.dst
+    tr = tr.to(DEV)
+    em = tr != 0
+    theta = torch.randn(V, device=DEV)
+    ms_full = timed(lambda: nb.compute_beta(em, tr, theta, k=k), args.steps * 3, False)
+    p = nb.pack_dense(em, tr)
+    ms_dp = timed(lambda: nb.compute_beta(em, tr, theta, k=k, packed=p), args.steps * 3, False)
+    print(f"{'config1 compute_beta(em, tr, theta, k=16) drop-in call':44s} dense tables [{B}, {S}, {V}] ({tr.numel() * 8 / 1e6:.0f} MB), {p.n_arcs} arcs: "
+          f"{ms_full:.3f} ms per call from the dense tables (scan + device pack + DP + beta[{B * k}, {S}]), {ms_dp:.3f} ms with the pack cached; "
+          f"the unmodified reference's compute_beta() on lattices of this batch, timed in the build container (CPU, 1 core): 0.94-1.16 s "
+          f"per lattice = ~600 arcs/s, i.e. ~{p.n_arcs / 600:.0f} s for the batch", flush=True)
+
+
 q = args.quick
 CONFIGS = [
     ("config1 transliteration B=32", lambda n, o: synth.transliteration_batch(n, seed=o), 32, 32),
@@ -259,6 +281,7 @@ for name, gen, B, per_chunk in CONFIGS:
           f"Viterbi scores {par['vit_scores_exact']} paths {par['vit_paths_exact']} (first {par['B']} lattices)", flush=True)
     del packed, sc, sample
     torch.cuda.empty_cache()
+compute_beta_report()
 recurrent_beta_report()
 training_step_report()
 walk_step_report()
