@@ -157,3 +157,21 @@ def test_device_packer_falls_back_for_wide_lattices():
     before = P.launch_count
     p, _ = synth.random_dag_batch(2, 60_000, levels=16, seed=1, device=DEV).pack()
     assert p.has_tiles and P.launch_count == before, "wide lattices keep the column-major layouts of the tensor-op packer"
+
+
+def test_tensor_op_packer_levels_on_the_device_and_rejects_cycles():
+    # tiles=True keeps the batch on the tensor-op packer, whose level sweeps run in the library (nfst_level_sweeps)
+    ab = synth.random_dag_batch(3, 5000, levels=10, seed=2)
+    p_gpu, _ = ab.to(DEV).pack(tiles=True)
+    p_cpu, _ = ab.pack(tiles=True)  # the same packer on the CPU: torch scatter sweeps
+    assert p_gpu.has_tiles
+    np.testing.assert_array_equal(_np(p_gpu.level_ptr), _np(p_cpu.level_ptr))
+    np.testing.assert_array_equal(_np(p_gpu.orig_state), _np(p_cpu.orig_state))
+    np.testing.assert_array_equal(_np(p_gpu.dst_out), _np(p_cpu.dst_out))
+    assert torch.equal(p_gpu.tile_stream.cpu(), p_cpu.tile_stream)
+    n = 200  # a long cycle 1 -> 2 -> ... -> n -> 1 behind the start state
+    src = torch.arange(0, n + 1, device=DEV)
+    dst = torch.cat([torch.arange(1, n + 1, device=DEV), torch.tensor([1], device=DEV)])
+    with pytest.raises(ValueError, match="cyclic"):
+        nb.pack_arcs(torch.zeros(n + 1, dtype=torch.int64, device=DEV), src, dst, torch.full((n + 1,), 5, device=DEV),
+                     torch.tensor([n + 1]), 16, tiles=True)
