@@ -65,7 +65,8 @@ def load_packed(path: str, device="cpu") -> PackedLattices:
         dense_shape = tuple(int(x) for x in l["__dense_shape__"]) if "__dense_shape__" in l.files else None
     kw = {k: v.to(device) for k, v in kw.items()}
     kw.setdefault("static_scores", None)
-    ci = {d: (kw[f"{d}_chunk_off"].to(torch.int64), kw[f"{d}_chunks"], kw[f"{d}_chunk_level"]) for d in ("fwd", "bwd")}
+    lazy = A > 0 and int(kw["in2out"].numel()) != A  # packed without the in-order arrays (column-major lattices)
+    ci = None if lazy else {d: (kw[f"{d}_chunk_off"].to(torch.int64), kw[f"{d}_chunks"], kw[f"{d}_chunk_level"]) for d in ("fwd", "bwd")}
     groups = build_groups(stats, torch.device(device), ci)
     return PackedLattices(n_lattices=B, n_states=S, n_arcs=A, vocab=V, dense_shape=dense_shape, groups=groups,
                           max_levels=max_levels, stats=stats, **kw)

@@ -197,6 +197,7 @@ def lattice_forward(packed: PackedLattices, arc_scores=None, theta=None, *, stat
     st = resolve_state_dtype(packed, state_dtype)
     alpha = torch.empty(packed.n_states, dtype=st, device=dev)
     logz = torch.empty(packed.n_lattices, dtype=st, device=dev)
+    packed.ensure_in_order()  # column-major batches are packed without their arcs-by-destination arrays
     with torch.cuda.device(dev):
         streams = _GroupStreams(dev, len(packed.groups))
         for i, g in enumerate(packed.groups):
@@ -363,6 +364,7 @@ def lattice_forward_backward(packed: PackedLattices, arc_scores=None, theta=None
     post = torch.empty(A, dtype=torch.float32, device=dev)
     dtheta = torch.zeros(V, dtype=torch.float32, device=dev) if want_dtheta else None
     gfar = _gamma_far(packed)
+    packed.ensure_in_order()  # alpha of column-major lattices comes from the CSR forward kernel
     with torch.cuda.device(dev):
         streams = _GroupStreams(dev, len(packed.groups))
         for i, g in enumerate(packed.groups):

@@ -230,6 +230,31 @@ class PackedLattices:
         """some lattices are stored column-major (sliced-column or tile-stream groups): their arcs are not CSR"""
         return any(g.sell or g.tiles for g in self.groups)
 
+    @property
+    def has_in_order(self) -> bool:
+        return self.n_arcs == 0 or int(self.in2out.numel()) == self.n_arcs
+
+    def ensure_in_order(self) -> "PackedLattices":
+        """Build the arcs-by-destination arrays and the chunk lists of a batch that was packed without them (all of
+        its lattices are column-major): what the CSR forward kernel needs to produce alpha for such lattices."""
+        if self.has_in_order:
+            return self
+        dev, B, S = self.device, self.n_lattices, self.n_states
+        state_off, level_ptr, level_off = self.state_off.to(torch.int64), self.level_ptr.to(torch.int64), self.level_off.to(torch.int64)
+        lt_s = torch.repeat_interleave(torch.arange(B, device=dev), state_off[1:] - state_off[:-1])
+        # level slot of every state: the last entry of level_ptr that is <= the state (a lattice's spare entry equals
+        # the first entry of the next lattice; right=True picks the latter)
+        slot = torch.searchsorted(level_ptr, torch.arange(S, device=dev), right=True) - 1
+        csr = _in_order_and_chunks(
+            in_ptr=self.in_ptr.to(torch.int64), out_ptr=self.out_ptr.to(torch.int64), src_out=self.src_out.to(torch.int64),
+            dst_out=self.dst_out.to(torch.int64), label_out=self.label_out.to(torch.int64), slot=slot,
+            lvl_first_state=level_ptr[slot], lt_s=lt_s, level_of_state=slot - level_off[lt_s],
+            block_class=self.stats["block_class"].to(dev), n_lattices=B)
+        for k, v in csr.items():
+            setattr(self, k, self._padded(v) if k in self._ARC_FIELDS else v)
+        self._c = None
+        return self
+
     def tensors(self):
         names = list(self._INT_FIELDS) + ["lanes_in_log2", "lanes_out_log2", "out_deg8", "tile_stream", "src_out",
                                           "orig_state", "arc_origin", "arc_off", "n_levels"]
@@ -338,6 +363,43 @@ def _build_chunks(ptr, slot, level_first, lat_of_state, target, heavy_thr, n_lat
     return chunk_off, chunks.to(torch.int32).contiguous(), order.to(torch.int32).contiguous()
 
 
+def _in_order_and_chunks(*, in_ptr, out_ptr, src_out, dst_out, label_out, slot, lvl_first_state, lt_s, level_of_state,
+                         block_class, n_lattices: int):
+    """The arrays only the CSR kernels read: arcs by destination (``in2out``, ``src_in``, ``label_in``), the forward /
+    backward chunk lists and the score-gather ranges.  Column-major batches build them on demand
+    (``PackedLattices.ensure_in_order``): their own kernels read the out order only."""
+    dev = out_ptr.device
+    B, A = n_lattices, int(src_out.numel())
+    in2out = torch.argsort(dst_out, stable=True)
+    src_in, label_in = src_out[in2out], label_out[in2out]
+    bmax = int(math.log2(BLOCK_MAX))
+    geo_t = torch.tensor([chunk_geometry(1 << k) if k >= 5 else (0, 0, 0) for k in range(bmax + 1)], device=dev)
+    target_state, heavy_state = geo_t[block_class, 0][lt_s], geo_t[block_class, 1][lt_s]
+    fwd_chunk_off, fwd_chunks, _ = _build_chunks(in_ptr, slot, lvl_first_state, lt_s, target_state, heavy_state, B, False)
+    bwd_chunk_off, bwd_chunks, bwd_order = _build_chunks(out_ptr, slot, lvl_first_state, lt_s, target_state, heavy_state, B, True)
+    # canonical-id range [lo, hi) that the arcs of each forward chunk gather their scores from
+    # (the kernel prefetches it into L2 several chunks ahead)
+    nfc = int(fwd_chunks.shape[0])
+    fc = fwd_chunks.to(torch.int64)
+    n_arc_c = fc[:, 1] - fc[:, 0]
+    g_lo = torch.full((nfc,), A, dtype=torch.int64, device=dev)
+    g_hi = torch.zeros(nfc, dtype=torch.int64, device=dev)
+    if A:
+        cid = torch.repeat_interleave(torch.arange(nfc, device=dev), n_arc_c)  # fwd chunks tile the in-order arcs
+        g_lo = g_lo.scatter_reduce(0, cid, in2out, reduce="amin")
+        g_hi = g_hi.scatter_reduce(0, cid, in2out + 1, reduce="amax")
+    g_lo = torch.where(n_arc_c > 0, g_lo, torch.zeros_like(g_lo))
+    fwd_gather = torch.stack([g_lo, torch.maximum(g_hi, g_lo)], dim=1)
+    i32 = lambda t: t.to(torch.int32).contiguous()  # noqa: E731
+    return {
+        "in2out": i32(in2out), "src_in": i32(src_in), "label_in": i32(label_in),
+        "fwd_chunk_off": i32(fwd_chunk_off), "fwd_chunks": fwd_chunks, "bwd_chunk_off": i32(bwd_chunk_off),
+        "bwd_chunks": bwd_chunks, "fwd_gather": i32(fwd_gather), "bwd_order": bwd_order,
+        "fwd_chunk_level": i32(level_of_state[fwd_chunks[:, 2].to(torch.int64)]),
+        "bwd_chunk_level": i32(level_of_state[bwd_chunks[:, 2].to(torch.int64)]),
+    }
+
+
 def _sell_block_log2(states: torch.Tensor, levels: torch.Tensor) -> torch.Tensor:
     """log2 of the warps per block of a sliced-column lattice: 4 warps, 8 from 1024 states per level
     (measured: 128 threads best at 400 states per level, 256 at 1200)."""
@@ -434,6 +496,12 @@ def concat_packed(parts: List["PackedLattices"]) -> "PackedLattices":
     if any(p.vocab != vocab for p in parts):
         raise ValueError("all parts must share one vocabulary")
     P = len(parts)
+    # parts packed without their in-order arrays (column-major lattices): the batch keeps it that way when all parts
+    # agree, otherwise the lazy parts build theirs now
+    lazy = not any(p.has_in_order and p.n_arcs for p in parts)
+    if not lazy:
+        for p in parts:
+            p.ensure_in_order()
     # element counts of every index space, per part (host integers: no device sync)
     n_state = [p.n_states for p in parts]
     n_arc = [p.n_arcs for p in parts]
@@ -484,15 +552,15 @@ def concat_packed(parts: List["PackedLattices"]) -> "PackedLattices":
         "sink_off": closed("sink_off", by_lat, offK, n_sinks),
         "sinks": cat("sinks") + offS[by_sink],
         "in_ptr": closed("in_ptr", by_state, offA, A),
-        "src_in": cat("src_in") + offS[by_arc],
+        "src_in": cat("src_in") + (0 if lazy else offS[by_arc]),
         "label_in": cat("label_in"),
-        "in2out": cat("in2out") + offA[by_arc],
+        "in2out": cat("in2out") + (0 if lazy else offA[by_arc]),
         "out_ptr": closed("out_ptr", by_state, offA, A),
         "dst_out": cat("dst_out") + offS[by_arc],
         "label_out": cat("label_out"),
         "fwd_chunk_off": closed("fwd_chunk_off", by_lat, offF, nfc),
         "bwd_chunk_off": closed("bwd_chunk_off", by_lat, offC, nbc),
-        "bwd_order": cat("bwd_order") + offS[by_state],
+        "bwd_order": cat("bwd_order") + (0 if lazy else offS[by_state]),
         "fwd_chunk_level": cat("fwd_chunk_level"),
         "bwd_chunk_level": cat("bwd_chunk_level"),
         "lanes_in_log2": cat("lanes_in_log2"),
@@ -563,12 +631,15 @@ def pack_arcs(
     dense_shape=None,
     sell: Optional[bool] = None,
     tiles: Optional[bool] = None,
+    in_order: Optional[bool] = None,
 ) -> PackedLattices:
     """Pack an arc list.  ``arc_lattice/src/dst/label`` are [A0] integer tensors (local
     state ids), ``n_states`` is [B].  Raises ``ValueError`` for cyclic lattices (the
     reference's denominator / base machines, which it never feeds to the DP either).
     ``sell`` / ``tiles``: allow the sliced-column / tile-stream layouts for wide lattices (defaults: the NFST_SELL
-    and NFST_TILES knobs; tiles win where both apply)."""
+    and NFST_TILES knobs; tiles win where both apply).  ``in_order``: build the arcs-by-destination arrays and the chunk
+    lists now (default: only when some lattice runs on the CSR kernels; column-major batches build them on the first
+    call that needs alpha, ``PackedLattices.ensure_in_order``)."""
     dev = src.device
     n_states = n_states.to(device=dev, dtype=torch.int64)
     B = int(n_states.numel())
@@ -578,7 +649,7 @@ def pack_arcs(
     label = label.to(torch.int64)
     so = _excl_cumsum(n_states)  # original global state offsets
     # ---- small lattices on a GPU: the library's device packer (nfst_pack.cu); it checks the arc endpoints itself ----
-    if DEVICE_PACK and dev.type == "cuda" and sell is None and tiles is None and src.numel():
+    if DEVICE_PACK and dev.type == "cuda" and sell is None and tiles is None and in_order is not False and src.numel():
         cnt = torch.bincount(arc_lattice, minlength=B)
         head = torch.stack([so[-1], n_states.max(), cnt.max(), label.min(), label.max()]).cpu().tolist()  # one host read
         S0, smax, amax = head[0], head[1], head[2]
@@ -770,8 +841,6 @@ def pack_arcs(
         # CSR position out_ptr[s] + k -> canonical id
         out_arc = torch.empty(A, dtype=torch.int64, device=dev)
         out_arc[perm2] = pos
-    in2out = torch.argsort(dst_out, stable=True)
-    src_in, label_in = src_out[in2out], label_out[in2out]
     in_ptr = _excl_cumsum(torch.bincount(dst_out, minlength=S))
     sinks = torch.nonzero(out_deg == 0).squeeze(1)
     sink_lat = torch.searchsorted(state_off, sinks, right=True) - 1
@@ -831,22 +900,22 @@ def pack_arcs(
     block_class = torch.clamp(torch.ceil(torch.log2(torch.clamp(
         width_arcs.to(torch.float64) / ARCS_PER_THREAD, min=32.0))), 5, bmax).to(torch.int64)
     geo = torch.tensor([chunk_geometry(1 << k) if k >= 5 else (0, 0, 0) for k in range(bmax + 1)], device=dev)
-    target_state, heavy_state = geo[block_class, 0][lt_s], geo[block_class, 1][lt_s]
-    fwd_chunk_off, fwd_chunks, _ = _build_chunks(in_ptr, slot, lvl_first_state, lt_s, target_state, heavy_state, B, False)
-    bwd_chunk_off, bwd_chunks, bwd_order = _build_chunks(out_ptr, slot, lvl_first_state, lt_s, target_state, heavy_state, B, True)
-    # canonical-id range [lo, hi) that the arcs of each forward chunk gather their scores from
-    # (the kernel prefetches it into L2 several chunks ahead)
-    nfc = int(fwd_chunks.shape[0])
-    fc = fwd_chunks.to(torch.int64)
-    n_arc_c = fc[:, 1] - fc[:, 0]
-    g_lo = torch.full((nfc,), A, dtype=torch.int64, device=dev)
-    g_hi = torch.zeros(nfc, dtype=torch.int64, device=dev)
-    if A:
-        cid = torch.repeat_interleave(torch.arange(nfc, device=dev), n_arc_c)  # fwd chunks tile the in-order arcs
-        g_lo = g_lo.scatter_reduce(0, cid, in2out, reduce="amin")
-        g_hi = g_hi.scatter_reduce(0, cid, in2out + 1, reduce="amax")
-    g_lo = torch.where(n_arc_c > 0, g_lo, torch.zeros_like(g_lo))
-    fwd_gather = torch.stack([g_lo, torch.maximum(g_hi, g_lo)], dim=1)
+    # the in-order arrays and the chunk lists: read by the CSR kernels only -- a batch whose lattices are all
+    # column-major leaves them to PackedLattices.ensure_in_order() (alpha of such a batch is asked for rarely)
+    lazy = bool(col_lat.all()) if in_order is None else not in_order
+    if lazy and not bool(col_lat.all()):
+        raise ValueError("in_order=False needs a batch of column-major lattices only (the CSR kernels read the in-order arrays)")
+    e32 = torch.zeros(0, dtype=torch.int32, device=dev)
+    if lazy:
+        csr = {"in2out": e32, "src_in": e32, "label_in": e32, "fwd_chunk_off": torch.zeros(B + 1, dtype=torch.int32, device=dev),
+               "fwd_chunks": torch.zeros((0, 4), dtype=torch.int32, device=dev),
+               "bwd_chunk_off": torch.zeros(B + 1, dtype=torch.int32, device=dev),
+               "bwd_chunks": torch.zeros((0, 4), dtype=torch.int32, device=dev), "fwd_gather": torch.zeros((0, 2), dtype=torch.int32, device=dev),
+               "bwd_order": e32, "fwd_chunk_level": e32, "bwd_chunk_level": e32}
+    else:
+        csr = _in_order_and_chunks(in_ptr=in_ptr, out_ptr=out_ptr, src_out=src_out, dst_out=dst_out, label_out=label_out,
+                                   slot=slot, lvl_first_state=lvl_first_state, lt_s=lt_s, level_of_state=lv_s,
+                                   block_class=block_class, n_lattices=B)
     # how far back (in packed state ids) an arc reaches: sizes the shared-memory window
     arc_lat = torch.repeat_interleave(torch.arange(B, device=dev), (arc_off[1:] - arc_off[:-1]))
     # (99% quantile over the lattice's arcs, rounded up to a power of two, from a log2
@@ -858,8 +927,6 @@ def pack_arcs(
         cum = torch.cumsum(hist, 1)
         need = torch.ceil(cum[:, -1:].to(torch.float64) * 0.99).to(torch.int64)
         reach = torch.ones_like(reach) << (cum < need).sum(1)
-    fwd_chunk_level = lv_s[fwd_chunks[:, 2].to(torch.int64)]
-    bwd_chunk_level = lv_s[bwd_chunks[:, 2].to(torch.int64)]
     stats = {
         "width_arcs": width_arcs.cpu(),
         "arcs": A_b.to(torch.int64).cpu(),
@@ -877,19 +944,21 @@ def pack_arcs(
         "tile_warps_log2": torch.round(torch.log2(tile_nw.to(torch.float64))).to(torch.int64).cpu(),
         **tile_data["stats"],
     }
-    groups = build_groups(stats, dev, {"fwd": (fwd_chunk_off, fwd_chunks, fwd_chunk_level),
-                                       "bwd": (bwd_chunk_off, bwd_chunks, bwd_chunk_level)})
+    groups = build_groups(stats, dev, None if lazy else {
+        "fwd": (csr["fwd_chunk_off"].to(torch.int64), csr["fwd_chunks"], csr["fwd_chunk_level"].to(torch.int64)),
+        "bwd": (csr["bwd_chunk_off"].to(torch.int64), csr["bwd_chunks"], csr["bwd_chunk_level"].to(torch.int64))})
 
     _phase("pack: final int32 conversion", dev)
     i32 = lambda t: t.to(torch.int32).contiguous()  # noqa: E731
     packed_result = PackedLattices(
         n_lattices=B, n_states=S, n_arcs=A, vocab=int(vocab),
         state_off=i32(state_off), level_off=i32(level_off), level_ptr=i32(level_ptr), start_state=i32(start_packed),
-        sink_off=i32(sink_off), sinks=i32(sinks), in_ptr=i32(in_ptr), src_in=i32(src_in), label_in=i32(label_in),
-        in2out=i32(in2out), out_ptr=i32(out_ptr), dst_out=i32(dst_out), label_out=i32(label_out),
-        fwd_chunk_off=i32(fwd_chunk_off), fwd_chunks=fwd_chunks, bwd_chunk_off=i32(bwd_chunk_off), bwd_chunks=bwd_chunks,
-        fwd_gather=i32(fwd_gather), fwd_chunk_level=i32(fwd_chunk_level), bwd_chunk_level=i32(bwd_chunk_level),
-        bwd_order=bwd_order, sell_desc=i32(sell_desc), sell_lvl_slice=i32(sell_lvl_slice),
+        sink_off=i32(sink_off), sinks=i32(sinks), in_ptr=i32(in_ptr), src_in=csr["src_in"], label_in=csr["label_in"],
+        in2out=csr["in2out"], out_ptr=i32(out_ptr), dst_out=i32(dst_out), label_out=i32(label_out),
+        fwd_chunk_off=csr["fwd_chunk_off"], fwd_chunks=csr["fwd_chunks"], bwd_chunk_off=csr["bwd_chunk_off"],
+        bwd_chunks=csr["bwd_chunks"], fwd_gather=csr["fwd_gather"], fwd_chunk_level=csr["fwd_chunk_level"],
+        bwd_chunk_level=csr["bwd_chunk_level"], bwd_order=csr["bwd_order"], sell_desc=i32(sell_desc),
+        sell_lvl_slice=i32(sell_lvl_slice),
         tile_stream=tile_data["tile_stream"], tile_tab=tile_data["tile_tab"], tile_lw_off=tile_data["tile_lw_off"],
         tile_lat_info=tile_data["tile_lat_info"], out_arc=i32(out_arc),
         lanes_in_log2=lg_in.to(torch.uint8).contiguous(), lanes_out_log2=lg_out.to(torch.uint8).contiguous(),

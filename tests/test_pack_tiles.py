@@ -143,3 +143,29 @@ def test_tile_default_thresholds():
     assert p.has_tiles and p.groups[0].block_threads == 128
     p, _ = synth.random_dag_batch(1, 1_000_000, levels=64, seed=1).pack()  # ring > 100 KB: one block per SM, 16 warps
     assert p.has_tiles and p.groups[0].block_threads == 512
+
+
+def test_in_order_arrays_are_built_on_demand_and_equal_the_eager_pack():
+    # a batch of column-major lattices is packed without the arcs-by-destination arrays and the chunk lists (only the
+    # CSR forward kernel reads them: alpha); ensure_in_order() builds exactly what an eager pack would have
+    ab = synth.random_dag_batch(3, 4000, levels=8, seed=2)
+    lazy, _ = ab.pack()
+    assert lazy.has_tiles and not lazy.has_in_order and lazy.in2out.numel() == 0 and lazy.fwd_chunks.shape[0] == 0
+    eager, _ = ab.pack(in_order=True)
+    assert eager.has_in_order
+    two = concat_packed([lazy, ab.pack()[0]])
+    assert not two.has_in_order and two.n_arcs == 2 * lazy.n_arcs  # lazy parts: the batch stays lazy
+    lazy.ensure_in_order()
+    for f in ("in2out", "src_in", "label_in", "in_ptr", "fwd_chunk_off", "fwd_chunks", "bwd_chunk_off", "bwd_chunks", "fwd_gather",
+              "bwd_order", "fwd_chunk_level", "bwd_chunk_level"):
+        assert torch.equal(getattr(lazy, f), getattr(eager, f)), f
+    # next to a CSR lattice the in-order arrays are needed: concat builds them for the lazy part
+    narrow, _ = synth.transliteration_batch(2, seed=1).pack()
+    mixed = concat_packed([narrow, ab.pack()[0]])
+    assert mixed.has_in_order and mixed.in2out.numel() == mixed.n_arcs
+    two.ensure_in_order()
+    ref = concat_packed([eager, eager])
+    for f in ("in2out", "src_in", "fwd_chunks", "bwd_order"):
+        assert torch.equal(getattr(two, f), getattr(ref, f)), f
+    with pytest.raises(ValueError, match="column-major"):
+        synth.transliteration_batch(2, seed=1).pack(in_order=False)
