@@ -56,7 +56,7 @@
 extern "C" {
 #endif
 
-#define NFST_ABI_VERSION 16
+#define NFST_ABI_VERSION 17
 
 typedef enum nfst_status {
   NFST_OK = 0,
@@ -318,8 +318,8 @@ int nfst_beta_to_dense(const nfst_packed_lattices_t* lat, const void* beta, int 
 int nfst_dense_count_arcs(const int64_t* transition, int64_t n_rows, int32_t states_per_lattice, int32_t vocab,
                           int32_t* row_counts, void* cuda_stream);
 int nfst_dense_extract_arcs(const int64_t* transition, int64_t n_rows, int32_t states_per_lattice, int32_t vocab,
-                            const int64_t* row_start, int32_t* arc_row, int32_t* arc_label, int32_t* arc_dst,
-                            void* cuda_stream);
+                            const int64_t* row_start, int64_t arc_capacity, int32_t* arc_row, int32_t* arc_label,
+                            int32_t* arc_dst, void* cuda_stream);
 
 /*
  * Sliced-column passes (launch->sell != 0).
@@ -481,6 +481,20 @@ int nfst_pack_small(int32_t n_lattices, const int32_t* raw_state_off, const int3
                     const int32_t* raw_dst, const int32_t* raw_label, int32_t src_is_global, int32_t start_state,
                     int32_t max_states, int32_t max_arcs, int32_t max_raw_arcs, const nfst_pack_out_t* out, void* workspace,
                     size_t workspace_bytes, int64_t n_states_raw, int64_t n_arcs_raw, int32_t phases, void* cuda_stream);
+
+/*
+ * collate()-padded dense tables -> packed lattices in one call per phase: the edge rule over transition[B, S, V]
+ * (int64, scorers.py:704-716), row offsets, the arc list, then nfst_pack_small (same outputs, same phases, same
+ * totals / lattice_stats; the start state is row 0, scorers.py:1005).  raw_arc_capacity bounds the arc list the
+ * tables produce INCLUDING the arcs of collate() padding rows (V per pad row); more than that sets totals[4] = 5 and
+ * nothing is built.  max_arcs bounds the arcs one lattice keeps (shared memory; see nfst_pack_small_smem_bytes).
+ * arc_origin of the result is the dense cell of every arc, (b * S + s) * V + label.  The workspace must survive
+ * from the count phase to the build phase.
+ */
+size_t nfst_pack_workspace_bytes(int32_t n_lattices, int32_t states_per_lattice, int64_t raw_arc_capacity);
+int nfst_pack_dense(const int64_t* transition, int32_t n_lattices, int32_t states_per_lattice, int32_t vocab,
+                    int64_t raw_arc_capacity, int32_t max_arcs, const nfst_pack_out_t* out, void* workspace, size_t workspace_bytes,
+                    int32_t phases, void* cuda_stream);
 
 /*
  * On-device construction of the transliteration lattices (what src/preprocess/tr.py:142-190 builds offline with

@@ -139,7 +139,10 @@ SYMBOLS = {
     "nfst_edit_lattice_arcs": (C.c_int, [C.c_int32, _P, _P, C.c_int32, _P, _P, C.c_int32] + [C.c_int32] * 6 + [_P, _P, _P, _P, _P]),
     "nfst_level_sweeps": (C.c_int, [_P, _P, C.c_int64, _P, _P, C.c_int32, _P]),
     "nfst_dense_count_arcs": (C.c_int, [_P, C.c_int64, C.c_int32, C.c_int32, _P, _P]),
-    "nfst_dense_extract_arcs": (C.c_int, [_P, C.c_int64, C.c_int32, C.c_int32, _P, _P, _P, _P, _P]),
+    "nfst_dense_extract_arcs": (C.c_int, [_P, C.c_int64, C.c_int32, C.c_int32, _P, C.c_int64, _P, _P, _P, _P]),
+    "nfst_pack_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int64]),
+    "nfst_pack_dense": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, C.c_int64, C.c_int32, C.POINTER(PackOutC), _P, C.c_size_t,
+                                  C.c_int32, _P]),
 }
 
 _lib = None
@@ -165,7 +168,7 @@ def load() -> C.CDLL:
         fn = getattr(lib, name)  # AttributeError if the header and the library disagree
         fn.restype = res
         fn.argtypes = args
-    if lib.nfst_abi_version() != 16:
+    if lib.nfst_abi_version() != 17:
         raise RuntimeError("libnfst_b200.so ABI version mismatch")
     _lib = lib
     return lib

@@ -1602,7 +1602,7 @@ __global__ void nfst_dense_count_kernel(const int64_t* __restrict__ tr, int64_t 
 }
 
 __global__ void nfst_dense_extract_kernel(const int64_t* __restrict__ tr, int64_t n_rows, int S, int V,
-                                          const int64_t* __restrict__ row_start, int32_t* __restrict__ arc_row,
+                                          const int64_t* __restrict__ row_start, int64_t capacity, int32_t* __restrict__ arc_row,
                                           int32_t* __restrict__ arc_label, int32_t* __restrict__ arc_dst) {
   const int64_t row = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
@@ -1616,8 +1616,8 @@ __global__ void nfst_dense_extract_kernel(const int64_t* __restrict__ tr, int64_
     if (j < V) t = p[j];
     const bool keep = (j < V) && t != 0 && t != self;
     const unsigned mask = __ballot_sync(0xffffffffu, keep);
-    if (keep) {
-      const int64_t at = pos + __popc(mask & ((1u << lane) - 1u));
+    const int64_t at = pos + __popc(mask & ((1u << lane) - 1u));
+    if (keep && at < capacity) {  // arcs beyond the caller's capacity are dropped (the caller sees the total in row_start)
       arc_row[at] = static_cast<int32_t>(row);
       arc_label[at] = j;
       arc_dst[at] = static_cast<int32_t>(t);
@@ -2029,17 +2029,17 @@ int nfst_dense_count_arcs(const int64_t* transition, int64_t n_rows, int32_t sta
 }
 
 int nfst_dense_extract_arcs(const int64_t* transition, int64_t n_rows, int32_t states_per_lattice, int32_t vocab,
-                            const int64_t* row_start, int32_t* arc_row, int32_t* arc_label, int32_t* arc_dst,
-                            void* cuda_stream) {
+                            const int64_t* row_start, int64_t arc_capacity, int32_t* arc_row, int32_t* arc_label,
+                            int32_t* arc_dst, void* cuda_stream) {
   if (!transition || !row_start || !arc_row || !arc_label || !arc_dst || n_rows < 0 || states_per_lattice < 1 ||
-      vocab < 1)
+      vocab < 1 || arc_capacity < 0)
     return fail(NFST_ERR_BAD_ARG, "nfst_dense_extract_arcs: bad argument");
   if (n_rows == 0) return NFST_OK;
   const int threads = 256;
   const int64_t blocks = (n_rows * 32 + threads - 1) / threads;
   if (blocks > 0x7fffffffLL) return fail(NFST_ERR_TOO_LARGE, "too many table rows");
   nfst_dense_extract_kernel<<<static_cast<unsigned>(blocks), threads, 0, static_cast<cudaStream_t>(cuda_stream)>>>(
-      transition, n_rows, states_per_lattice, vocab, row_start, arc_row, arc_label, arc_dst);
+      transition, n_rows, states_per_lattice, vocab, row_start, arc_capacity, arc_row, arc_label, arc_dst);
   NFST_CUDA_OK(cudaGetLastError());
   return NFST_OK;
 }

@@ -79,6 +79,7 @@ __device__ int block_excl_scan(int* v, int n, int* tmp) {
 // every state's range in the raw arc list (sorted by source) + endpoint validation: grid (chunks, lattices)
 __global__ void __launch_bounds__(kThreads)
     pack_ranges_kernel(const RawArcs R, int32_t* __restrict__ first_g, int32_t* __restrict__ end_g, int32_t* __restrict__ totals) {
+  if (totals[4]) return;  // e.g. an arc list that overflowed its capacity (nfst_pack_dense)
   const int b = blockIdx.y;
   const int s0 = R.state_off[b], S0 = R.state_off[b + 1] - s0;
   const int a0 = R.arc_off[b], A0 = R.arc_off[b + 1] - a0;
@@ -516,7 +517,7 @@ int nfst_pack_small(int32_t n_lattices, const int32_t* raw_state_off, const int3
     PACK_CUDA_OK(cudaFuncSetAttribute(pack_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   }
   if (phases & 1) {
-    PACK_CUDA_OK(cudaMemsetAsync(out->totals, 0, 8 * sizeof(int32_t), st));
+    if (!(phases & 4)) PACK_CUDA_OK(cudaMemsetAsync(out->totals, 0, 8 * sizeof(int32_t), st));
     PACK_CUDA_OK(cudaMemsetAsync(first_g, 0, 2 * static_cast<size_t>(n_states_raw) * sizeof(int32_t), st));
     if (max_raw_arcs > 0) {
       const dim3 grid((max_raw_arcs + kThreads - 1) / kThreads, n_lattices);
@@ -673,3 +674,122 @@ extern "C" int nfst_level_sweeps(const int64_t* gsrc, const int64_t* gdst, int64
   PACK_CUDA_OK(cudaGetLastError());
   return 0;
 }
+
+// =========================================================================================================
+// nfst_pack_dense: collate()-padded dense tables -> packed lattices through the C ABI alone
+// =========================================================================================================
+// The entry SURVEY.md section 8(b) asks for: everything pack_dense() does on the device, in one call per phase --
+// the edge rule over transition[B, S, V] (nfst_dense_count_arcs), the row offsets (one block scans the B*S row
+// counts), the arc list (nfst_dense_extract_arcs), then nfst_pack_small.  The caller sizes the raw arc list by a
+// capacity; more arcs than that is reported through totals[4] = 5.
+namespace {
+
+__global__ void __launch_bounds__(kThreads)
+    dense_offsets_kernel(const int32_t* __restrict__ row_counts, int64_t n_rows, int S, int B, int64_t capacity,
+                         int64_t* __restrict__ row_start, int32_t* __restrict__ raw_state_off, int32_t* __restrict__ raw_arc_off,
+                         int32_t* __restrict__ totals) {
+  __shared__ long long part[kThreads];
+  const int tid = threadIdx.x;
+  const int64_t per = (n_rows + kThreads - 1) / kThreads;
+  const int64_t lo = tid * per, hi = lo + per < n_rows ? lo + per : n_rows;
+  long long sum = 0;
+  for (int64_t i = lo; i < hi; ++i) sum += row_counts[i];
+  part[tid] = sum;
+  __syncthreads();
+  for (int o = 1; o < kThreads; o <<= 1) {
+    const long long add = tid >= o ? part[tid - o] : 0;
+    __syncthreads();
+    part[tid] += add;
+    __syncthreads();
+  }
+  long long run = tid ? part[tid - 1] : 0;
+  for (int64_t i = lo; i < hi; ++i) {
+    row_start[i] = run;
+    run += row_counts[i];
+  }
+  __syncthreads();
+  const long long total = part[kThreads - 1];
+  if (tid == 0) {
+    row_start[n_rows] = total;
+    if (total > capacity || total >= 0x7fffffffLL) atomicCAS(&totals[4], 0, 5);
+  }
+  __syncthreads();
+  for (int b = tid; b <= B; b += kThreads) {
+    raw_state_off[b] = b * S;
+    const long long at = b < B ? row_start[static_cast<int64_t>(b) * S] : total;
+    raw_arc_off[b] = static_cast<int32_t>(at < 0x7fffffffLL ? at : 0x7fffffffLL);
+  }
+}
+
+// arc_origin: index into the extracted arc list -> dense cell (b * S + s) * V + label
+__global__ void __launch_bounds__(kThreads)
+    origin_to_cell_kernel(int64_t* __restrict__ arc_origin, const int32_t* __restrict__ arc_row, const int32_t* __restrict__ arc_label,
+                          int V, const int32_t* __restrict__ totals) {
+  if (totals[4]) return;
+  const int64_t A = totals[1];
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * kThreads + threadIdx.x; i < A; i += static_cast<int64_t>(gridDim.x) * kThreads) {
+    const int64_t r = arc_origin[i];
+    arc_origin[i] = static_cast<int64_t>(arc_row[r]) * V + arc_label[r];
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
+
+size_t nfst_pack_workspace_bytes(int32_t n_lattices, int32_t states_per_lattice, int64_t raw_arc_capacity) {
+  const size_t rows = static_cast<size_t>(n_lattices) * states_per_lattice;
+  // row counts, row offsets (int64), raw lattice offsets, the raw arc list {row, label, dst}, nfst_pack_small's workspace
+  return rows * 4 + (rows + 1) * 8 + 2 * (static_cast<size_t>(n_lattices) + 1) * 4 + 3 * static_cast<size_t>(raw_arc_capacity) * 4 + 64 +
+         nfst_pack_small_workspace_bytes(static_cast<int64_t>(rows), raw_arc_capacity);
+}
+
+int nfst_pack_dense(const int64_t* transition, int32_t n_lattices, int32_t states_per_lattice, int32_t vocab,
+                    int64_t raw_arc_capacity, int32_t max_arcs, const nfst_pack_out_t* out, void* workspace, size_t workspace_bytes,
+                    int32_t phases, void* cuda_stream) {
+  if (!transition || !out || !workspace || n_lattices <= 0 || states_per_lattice < 1 || vocab < 1 || raw_arc_capacity < 0)
+    return nfst_fail_msg(NFST_ERR_BAD_ARG, "nfst_pack_dense: bad argument");
+  if (workspace_bytes < nfst_pack_workspace_bytes(n_lattices, states_per_lattice, raw_arc_capacity))
+    return nfst_fail_msg(NFST_ERR_BAD_ARG, "nfst_pack_dense: workspace too small");
+  if (raw_arc_capacity >= 0x7fffffffLL || static_cast<int64_t>(n_lattices) * states_per_lattice >= 0x7fffffffLL)
+    return nfst_fail_msg(NFST_ERR_TOO_LARGE, "nfst_pack_dense: batch beyond int32 indices");
+  cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+  const int64_t rows = static_cast<int64_t>(n_lattices) * states_per_lattice;
+  char* w = static_cast<char*>(workspace);
+  int64_t* row_start = reinterpret_cast<int64_t*>(w);                        w += (rows + 1) * 8;
+  int32_t* row_counts = reinterpret_cast<int32_t*>(w);                       w += rows * 4;
+  int32_t* raw_state_off = reinterpret_cast<int32_t*>(w);                    w += (static_cast<size_t>(n_lattices) + 1) * 4;
+  int32_t* raw_arc_off = reinterpret_cast<int32_t*>(w);                      w += (static_cast<size_t>(n_lattices) + 1) * 4;
+  w = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(w) + 15) & ~static_cast<uintptr_t>(15));
+  int32_t* arc_row = reinterpret_cast<int32_t*>(w);                          w += raw_arc_capacity * 4;
+  int32_t* arc_label = reinterpret_cast<int32_t*>(w);                        w += raw_arc_capacity * 4;
+  int32_t* arc_dst = reinterpret_cast<int32_t*>(w);                          w += raw_arc_capacity * 4;
+  w = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(w) + 15) & ~static_cast<uintptr_t>(15));
+  const size_t small_bytes = nfst_pack_small_workspace_bytes(rows, raw_arc_capacity);
+  if (phases & 1) {
+    PACK_CUDA_OK(cudaMemsetAsync(out->totals, 0, 8 * sizeof(int32_t), st));
+    if (int rc = nfst_dense_count_arcs(transition, rows, states_per_lattice, vocab, row_counts, cuda_stream)) return rc;
+    dense_offsets_kernel<<<1, kThreads, 0, st>>>(row_counts, rows, states_per_lattice, n_lattices, raw_arc_capacity, row_start,
+                                                raw_state_off, raw_arc_off, out->totals);
+    PACK_CUDA_OK(cudaGetLastError());
+    // more arcs than the capacity: totals[4] = 5 (set above), the extract drops what does not fit, the pack kernels return
+    if (int rc = nfst_dense_extract_arcs(transition, rows, states_per_lattice, vocab, row_start, raw_arc_capacity, arc_row, arc_label,
+                                         arc_dst, cuda_stream))
+      return rc;
+  }
+  const int64_t cell_cap = static_cast<int64_t>(states_per_lattice) * vocab;
+  const int32_t max_raw = static_cast<int32_t>(cell_cap < raw_arc_capacity ? cell_cap : raw_arc_capacity);
+  // nfst_pack_small's count phase would zero the totals: bit 2 of phases keeps them (the overflow code above)
+  if (int rc = nfst_pack_small(n_lattices, raw_state_off, raw_arc_off, arc_row, arc_dst, arc_label, /*src_is_global=*/1, /*start=*/0,
+                               states_per_lattice, max_arcs, max_raw, out, w, small_bytes, rows, raw_arc_capacity, phases | 4,
+                               cuda_stream))
+    return rc;
+  if (phases & 2) {
+    origin_to_cell_kernel<<<148 * 4, kThreads, 0, st>>>(out->arc_origin, arc_row, arc_label, vocab, out->totals);
+    PACK_CUDA_OK(cudaGetLastError());
+  }
+  return 0;
+}
+
+}  // extern "C"

@@ -988,7 +988,7 @@ def _dense_arcs_cuda(transition: torch.Tensor):
         row = torch.empty(A0, dtype=torch.int32, device=tr.device)
         lab = torch.empty(A0, dtype=torch.int32, device=tr.device)
         dst = torch.empty(A0, dtype=torch.int32, device=tr.device)
-        _lib.check(lib.nfst_dense_extract_arcs(tr.data_ptr(), n_rows, S, V, row_start.data_ptr(), row.data_ptr(),
+        _lib.check(lib.nfst_dense_extract_arcs(tr.data_ptr(), n_rows, S, V, row_start.data_ptr(), A0, row.data_ptr(),
                                                lab.data_ptr(), dst.data_ptr(), st))
     return row, lab, dst, lat_off, max_arcs
 

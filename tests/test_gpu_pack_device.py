@@ -175,3 +175,58 @@ def test_tensor_op_packer_levels_on_the_device_and_rejects_cycles():
     with pytest.raises(ValueError, match="cyclic"):
         nb.pack_arcs(torch.zeros(n + 1, dtype=torch.int64, device=DEV), src, dst, torch.full((n + 1,), 5, device=DEV),
                      torch.tensor([n + 1]), 16, tiles=True)
+
+
+def test_c_abi_pack_dense_equals_the_python_path():
+    """nfst_pack_dense: dense tables -> packed arrays through the C ABI alone, both phases, against
+    nb.pack_dense; an arc list that overflows its capacity is reported through totals[4] = 5."""
+    import ctypes as C
+
+    from nfst_b200 import _lib
+
+    rng = np.random.default_rng(5)
+    tabs = [random_mark_lattice(rng, 4 + 3 * i, 20)[1] for i in range(5)]
+    S, V = max(t.shape[0] for t in tabs) + 1, 20
+    from tests.lattice_gen import PAD
+    batch = np.full((len(tabs), S, V), PAD, dtype=np.int64)
+    for i, t in enumerate(tabs):
+        batch[i, :t.shape[0]] = t
+    tr = torch.from_numpy(batch).to(DEV)
+    ref = nb.pack_dense(tr != 0, tr)
+    lib = _lib.load()
+    B = len(tabs)
+    cap = int(((tr != 0) & (tr != torch.arange(S, device=DEV).view(1, S, 1))).sum())
+
+    def run(capacity):
+        i32 = dict(dtype=torch.int32, device=DEV)
+        o = {k: torch.zeros(n, **i32) for k, n in (("state_off", B + 1), ("arc_off", B + 1), ("level_off", B + 1), ("sink_off", B + 1),
+                                                   ("n_levels", B), ("start_state", B), ("lattice_stats", 8 * B), ("totals", 8))}
+        out = _lib.PackOutC()
+        for k, t in o.items():
+            setattr(out, k, t.data_ptr())
+        nbytes = int(lib.nfst_pack_workspace_bytes(B, S, capacity))
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=DEV)
+        st = torch.cuda.current_stream().cuda_stream
+        _lib.check(lib.nfst_pack_dense(tr.data_ptr(), B, S, V, capacity, 4096, C.byref(out), ws.data_ptr(), nbytes, 1, st))
+        totals = o["totals"].cpu().tolist()
+        if totals[4]:
+            return totals, None
+        Sk, A, n_lp, n_sink = totals[:4]
+        big = {k: torch.zeros(n + 4, **i32) for k, n in (("level_ptr", n_lp), ("sinks", n_sink), ("orig_state", Sk), ("in_ptr", Sk + 1),
+                                                         ("out_ptr", Sk + 1), ("src_in", A), ("label_in", A), ("in2out", A),
+                                                         ("dst_out", A), ("label_out", A), ("src_out", A))}
+        origin = torch.zeros(A, dtype=torch.int64, device=DEV)
+        for k, t in big.items():
+            setattr(out, k, t.data_ptr())
+        out.arc_origin = origin.data_ptr()
+        _lib.check(lib.nfst_pack_dense(tr.data_ptr(), B, S, V, capacity, 4096, C.byref(out), ws.data_ptr(), nbytes, 2, st))
+        torch.cuda.synchronize()
+        return totals, {**{k: v for k, v in o.items()}, **{k: v[:-4] for k, v in big.items()}, "arc_origin": origin}
+
+    totals, got = run(cap)
+    assert totals[4] == 0 and (totals[0], totals[1]) == (ref.n_states, ref.n_arcs)
+    for k in ("state_off", "arc_off", "level_off", "sink_off", "n_levels", "start_state", "level_ptr", "sinks", "orig_state", "in_ptr",
+              "out_ptr", "src_in", "label_in", "in2out", "dst_out", "label_out", "src_out", "arc_origin"):
+        assert torch.equal(got[k].to(torch.int64), getattr(ref, k).to(torch.int64)), k
+    totals, got = run(cap - 1)
+    assert totals[4] == 5 and got is None
