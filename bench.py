@@ -102,7 +102,7 @@ def build_packed(a, device, arcs=None, rank=0, world=1):
         mine = torch.zeros(total, dtype=torch.bool)
         mine[torch.tensor(nd.shard_by_arcs(torch.cat(counts).tolist(), world)[rank], dtype=torch.int64)] = True
     parts, scores = [], []
-    build_packed.pack_s = 0.0
+    build_packed.pack_s, build_packed.chunks = 0.0, []
     for d, n in spans:
         ab = make_arcs(a, device, seed_offset=d, batch=n, arcs=arcs)
         if mine is not None:
@@ -117,6 +117,7 @@ def build_packed(a, device, arcs=None, rank=0, world=1):
         if device != "cpu":
             torch.cuda.synchronize()
         build_packed.pack_s += time.perf_counter() - t0
+        build_packed.chunks.append((p.n_arcs, time.perf_counter() - t0))
         p.arc_origin = torch.empty(0, dtype=torch.int64, device=device)  # not needed here; frees 8 B/arc
         parts.append(p)
         scores.append(sc)
@@ -332,6 +333,7 @@ def main():
 
     packed, scores = build_packed(a, dev, rank=rank, world=world)
     pack_ms = 1e3 * build_packed.pack_s
+    pack_chunks = list(build_packed.chunks)
     A, S, B = packed.n_arcs, packed.n_states, packed.n_lattices
     B_global = a.batch * world
     loss = torch.zeros(1, device=dev)
@@ -602,9 +604,12 @@ def main():
         out["theta_step"] = theta_leg
     out["ranks"] = ranks
     out["pack"] = {"ms": pack_ms, "arcs_per_s": A / (pack_ms * 1e-3), "when": "once per batch, outside the timed region",
+                   "chunks_ms": [round(1e3 * t, 1) for _, t in pack_chunks],
+                   "warm_arcs_per_s": (pack_chunks[-1][0] / pack_chunks[-1][1]) if len(pack_chunks) > 1 else None,
+                   "note": "the first chunk includes one-time costs (library and torch kernel loading, allocator growth)",
                    "packer": "tensor-op packer (nfst_b200/pack.py + tiles.py) for these wide lattices; the lattices nFST builds "
-                             "(configs 1, 2, 5) pack on the device with nfst_pack_small: 1.8 ms for config 1, 4.1 ms for config 5 "
-                             "(tools/pack_profile.py)"}
+                             "(configs 1, 2, 5) pack on the device with nfst_pack_small: 1.2 ms for config 1 from its dense tables, 3.5 ms for "
+                             "config 5 (tools/pack_profile.py)"}
     if not a.no_cpu and world == 1:  # CPU baseline: rank 0 at N=1 only
         cb, _, _ = cpu_baseline(a, a.cpu_seconds)
         out["cpu_baseline"] = cb
