@@ -174,6 +174,10 @@ __global__ void __launch_bounds__(kThreads)
   for (int s = tid; s < S0; s += kThreads) koff[s] = level[s] >= 0 ? raw_end[s] - raw_first[s] : 0;
   __syncthreads();
   const int Ak = block_excl_scan(koff, S0, scan_tmp);
+  if (Ak > A0) {  // the ranges overlap: the raw list was not sorted by source
+    if (tid == 0 && atomicCAS(&totals[4], 0, 2) == 0) totals[5] = b;
+    return;
+  }
   if (Ak > capA) {  // more arcs than the shared memory this launch was sized for: the caller packs this batch elsewhere
     if (tid == 0 && atomicCAS(&totals[4], 0, 4) == 0) totals[5] = b;
     return;
