@@ -47,7 +47,9 @@ TILE_SLICES = int(os.environ.get("NFST_TILE_SLICES", "6"))  # slices per tile, a
 TILE_WARPS = int(os.environ.get("NFST_TILE_WARPS", "0"))  # 0 = from the level width
 TILE_BLOCK_ARCS = int(os.environ.get("NFST_TILE_BLOCK_ARCS", "1024"))  # arcs in the tiles that a block's warps hold at a time
 KU = 8  # columns of a slice the kernels hold in registers
-TAILMAX = 32  # states with more arcs than this are heavy
+# states with more arcs than this are heavy (a slice of their own).  Measured at 8 / 12 / 16 on B200: never faster than
+# 32, and at 8 every 9+-arc state costs 32 ring slots
+TAILMAX = int(os.environ.get("NFST_TILE_TAILMAX", "32"))
 RING_MAX = int(os.environ.get("NFST_TILE_RING_MAX", "49152"))  # ring slots (float32: 192 KB)
 NW_MAX = 32
 FORCE_RING_SLICES = int(os.environ.get("NFST_TILE_FORCE_RING_SLICES", "0"))  # tests: a ring this short (more far destinations)
