@@ -48,6 +48,7 @@ def parse_args():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-theta", action="store_true", help="skip the theta-mode training-step leg")
     ap.add_argument("--no-sweep", action="store_true", help="skip the other points of the config-4 sweep (N=1 only)")
+    ap.add_argument("--no-configs", action="store_true", help="skip BASELINE configs 1, 2, 3 and 5 at their stated batch (N=1 only; --no-sweep skips them too)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     return ap.parse_args()
 
@@ -306,6 +307,73 @@ def run_reference(a):
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
+
+
+def other_configs(dev, steps, peak):
+    """BASELINE.json configs 1, 2, 3 and 5 at their stated batch (config 4 is the sweep): the same two-pass step and
+    Viterbi + backtrace, CUDA events over `steps` back-to-back calls after 3 warm-ups.  These are latency-bound shapes
+    (tens to a thousand dependent levels of a few states each): arcs/s and ms are the figures, the roofline fraction is
+    reported because the metric asks for it."""
+    import torch
+
+    import nfst_b200 as nb
+    from nfst_b200 import ops, synth
+    from nfst_b200.pack import concat_packed
+
+    cases = [
+        ("config1 transliteration B=32", lambda n, o: synth.transliteration_batch(n, seed=o), 32, 32),
+        ("config2 SNIPS B=256", lambda n, o: synth.snips_batch(n, seed=1 + o), 256, 256),
+        ("config3 cipher unigram T=1000 B=64", lambda n, o: synth.cipher_batch(n, T=1000, bigram=False, seed=2 + o, device=dev), 64, 64),
+        ("config3 cipher bigram T=1000 B=64", lambda n, o: synth.cipher_batch(n, T=1000, bigram=True, seed=2 + o, device=dev), 64, 16),
+        ("config5 Viterbi transliteration B=4096", lambda n, o: synth.transliteration_batch(n, seed=4 + o), 4096, 512),
+        ("config5 Viterbi integer scores B=4096", lambda n, o: synth.transliteration_batch(n, seed=4 + o, integer_scores=True), 4096, 512),
+    ]
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > L2: these inputs are smaller than it
+
+    def timed(fn):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        tot = 0.0
+        for _ in range(steps):
+            flush.zero_()
+            e0.record()
+            fn()
+            e1.record()
+            torch.cuda.synchronize()
+            tot += e0.elapsed_time(e1)
+        return tot / steps
+
+    rows = []
+    for name, gen, B, per_chunk in cases:
+        parts, scs = [], []
+        for o in range(0, B, per_chunk):
+            pk, sc = gen(min(per_chunk, B - o), o).to(dev).pack()
+            parts.append(pk)
+            scs.append(sc)
+        pk = concat_packed(parts) if len(parts) > 1 else parts[0]
+        sc = torch.cat(scs)
+        A, S = pk.n_arcs, pk.n_states
+        cols = all(g.sell or g.tiles for g in pk.groups)
+        bb = torch.empty(S, dtype=ops.resolve_state_dtype(pk), device=dev) if pk.has_columns else None
+
+        def fb():
+            lz, al, cd = ops.lattice_pull(pk, arc_scores=sc, beta_out=bb)
+            nb.lattice_backward(pk, arc_scores=sc, alpha=al, logz=lz, cond=cd, want_beta=not cols, want_post=True)
+
+        ms_fb = timed(fb)
+        ms_v = timed(lambda: nb.lattice_viterbi(pk, arc_scores=sc))
+        rows.append({
+            "config": name, "arcs": A, "states": S, "levels": pk.max_levels,
+            "state_dtype": str(ops.resolve_state_dtype(pk)).replace("torch.", ""),
+            "execution": "small-lattice kernel" if all(g.small_max_arcs > 0 for g in pk.groups) else
+                         "tile-stream" if all(g.tiles for g in pk.groups) else "CSR / level-major",
+            "fwd_bwd_ms": ms_fb, "fwd_bwd_arcs_per_s": A / (ms_fb * 1e-3), "fwd_bwd_frac": (20 * A + 20 * S) / (ms_fb * 1e-3) / 1e9 / peak,
+            "viterbi_ms": ms_v, "viterbi_arcs_per_s": A / (ms_v * 1e-3)})
+        del pk, sc, parts, scs, bb
+        torch.cuda.empty_cache()
+    return rows
 
 
 def main():
@@ -659,6 +727,10 @@ def main():
                           "gbs": (20 * packed.n_arcs + 20 * packed.n_states) / (ms * 1e-3) / 1e9,
                           "frac": (20 * packed.n_arcs + 20 * packed.n_states) / (ms * 1e-3) / 1e9 / peak})
         out["sweep"] = sweep
+    if not (a.no_configs or a.no_sweep) and world == 1 and a.workload == "dag":
+        del packed, scores
+        torch.cuda.empty_cache()
+        out["configs"] = other_configs(dev, max(a.steps, 5), peak)
     print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()

@@ -16,3 +16,5 @@ for path in sys.argv[1:]:
           f"({e.get('ms_per_step', 0):.2f} ms, {e.get('h2d_bytes_per_step', 0) / 1e6:.0f} MB) | {d['config'].get('execution')}")
     for s in d.get("sweep", []):
         print("   sweep", s)
+    for c in d.get("configs", []):
+        print(f"   {c['config']:42s} {c['execution']:22s} f+b {c['fwd_bwd_ms']:.3f} ms {c['fwd_bwd_arcs_per_s']:.3e} arcs/s | Viterbi {c['viterbi_ms']:.3f} ms {c['viterbi_arcs_per_s']:.3e}")
