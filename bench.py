@@ -364,13 +364,20 @@ def other_configs(dev, steps, peak):
 
         ms_fb = timed(fb)
         ms_v = timed(lambda: nb.lattice_viterbi(pk, arc_scores=sc))
+        ms_graph = None
+        if not (cols or all(g.small_max_arcs > 0 for g in pk.groups)):
+            # CSR / level-major groups are many launches per step (one per level for wide levels): the same
+            # forward-backward replayed from a CUDA graph (ops.CapturedForwardBackward), scores copied in per step
+            cap = ops.CapturedForwardBackward(pk)
+            ms_graph = timed(lambda: cap.run(sc))
+            del cap
         rows.append({
             "config": name, "arcs": A, "states": S, "levels": pk.max_levels,
             "state_dtype": str(ops.resolve_state_dtype(pk)).replace("torch.", ""),
             "execution": "small-lattice kernel" if all(g.small_max_arcs > 0 for g in pk.groups) else
                          "tile-stream" if all(g.tiles for g in pk.groups) else "CSR / level-major",
             "fwd_bwd_ms": ms_fb, "fwd_bwd_arcs_per_s": A / (ms_fb * 1e-3), "fwd_bwd_frac": (20 * A + 20 * S) / (ms_fb * 1e-3) / 1e9 / peak,
-            "viterbi_ms": ms_v, "viterbi_arcs_per_s": A / (ms_v * 1e-3)})
+            "fwd_bwd_graph_ms": ms_graph, "viterbi_ms": ms_v, "viterbi_arcs_per_s": A / (ms_v * 1e-3)})
         del pk, sc, parts, scs, bb
         torch.cuda.empty_cache()
     return rows
