@@ -56,7 +56,7 @@
 extern "C" {
 #endif
 
-#define NFST_ABI_VERSION 17
+#define NFST_ABI_VERSION 18
 
 typedef enum nfst_status {
   NFST_OK = 0,
@@ -305,6 +305,14 @@ int nfst_viterbi_paths_f32(const nfst_packed_lattices_t* lat, const nfst_launch_
 int nfst_compact_paths(const nfst_packed_lattices_t* lat, const int32_t* path_off, const int32_t* path_len,
                        const int32_t* path_buf, const int64_t* out_off, int32_t* out_arcs, int32_t* out_labels,
                        void* cuda_stream);
+
+/* Padded result, no host read: row b of out_labels[B, row_len] (int64, the reference's sample dtype) = the labels of
+ * lattice b's path -- without a leading skip_label (>= 0: the reference's samples never hold bos, scorers.py:230-231)
+ * -- followed by pad_label; out_len[b] (may be NULL) = labels written.  The best-sample read-out of
+ * lightning.py:474-479 as one [B, T] tensor. */
+int nfst_pad_paths(const nfst_packed_lattices_t* lat, const int32_t* path_off, const int32_t* path_len, const int32_t* path_buf,
+                   int32_t skip_label, int64_t pad_label, int32_t row_len, int64_t* out_labels, int32_t* out_len,
+                   void* cuda_stream);
 
 /* out[(b*k+j)*dense_states + orig_state[s]] = exp(beta[s]) for j < k (float32 out; beta
  * float32 or float64 per beta_f64); `out` must be zero-filled by the caller (states that

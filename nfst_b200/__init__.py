@@ -18,6 +18,7 @@ from .ops import (  # noqa: F401
     lattice_forward_backward,
     lattice_log_partition,
     lattice_viterbi,
+    lattice_viterbi_padded,
 )
 
 from .sampler import LatticeWalker, sample_paths, stripping_pad, walk_step  # noqa: F401

@@ -117,6 +117,7 @@ SYMBOLS = {
     "nfst_backtrace": (C.c_int, [C.POINTER(PackedLatticesC), _P, _P, _P, _P, _P]),
     "nfst_viterbi_paths_f32": (C.c_int, [C.POINTER(PackedLatticesC), C.POINTER(LaunchC), C.POINTER(ScoresC), _P, _P, _P, _P, _P, _P, _P]),
     "nfst_compact_paths": (C.c_int, [C.POINTER(PackedLatticesC), _P, _P, _P, _P, _P, _P, _P]),
+    "nfst_pad_paths": (C.c_int, [C.POINTER(PackedLatticesC), _P, _P, _P, C.c_int32, C.c_int64, C.c_int32, _P, _P, _P]),
     "nfst_sell_smem_bytes": (C.c_size_t, [C.POINTER(LaunchC), C.c_int32, C.c_int, C.c_int, C.c_int]),
     "nfst_sell_pull_f32": (C.c_int, [C.POINTER(PackedLatticesC), C.POINTER(LaunchC), C.POINTER(ScoresC)] + [_P] * 7),
     "nfst_sell_flow_f32": (C.c_int, [C.POINTER(PackedLatticesC), C.POINTER(LaunchC)] + [_P] * 9),
@@ -168,7 +169,7 @@ def load() -> C.CDLL:
         fn = getattr(lib, name)  # AttributeError if the header and the library disagree
         fn.restype = res
         fn.argtypes = args
-    if lib.nfst_abi_version() != 17:
+    if lib.nfst_abi_version() != 18:
         raise RuntimeError("libnfst_b200.so ABI version mismatch")
     _lib = lib
     return lib

@@ -1499,6 +1499,26 @@ __global__ void nfst_compact_paths_kernel(const nfst_packed_lattices_t L, const 
   }
 }
 
+// padded result: row b of out_labels[B, T] = the labels of lattice b's path (without a leading skip_label: the
+// reference's samples never hold bos, scorers.py:230-231), then pad_label; out_len[b] = labels written; one warp
+// per lattice, no host read anywhere (the best-sample read-out of lightning.py:474-479 as a [B, T] tensor)
+__global__ void nfst_pad_paths_kernel(const nfst_packed_lattices_t L, const int32_t* __restrict__ path_off,
+                                      const int32_t* __restrict__ path_len, const int32_t* __restrict__ path_buf,
+                                      int skip_label, int64_t pad_label, int T, int64_t* __restrict__ out_labels,
+                                      int32_t* __restrict__ out_len) {
+  const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (b >= L.n_lattices) return;
+  const int lane = threadIdx.x & 31;
+  const int src0 = path_off[b];
+  int len = path_len[b];
+  int skip = 0;
+  if (len > 0 && skip_label >= 0 && L.label_out[path_buf[src0]] == skip_label) skip = 1;
+  len = min(len - skip, T);
+  int64_t* const row = out_labels + static_cast<int64_t>(b) * T;
+  for (int k = lane; k < T; k += 32) row[k] = k < len ? static_cast<int64_t>(L.label_out[path_buf[src0 + skip + k]]) : pad_label;
+  if (lane == 0 && out_len) out_len[b] = len;
+}
+
 // =====================================================================================
 // beta-hat recurrence (the reference's full compute_beta, Wh != 0; scorers.py:692-751):
 //   message over arc c --j--> n :  m_hat = tanh(Wx e_j + Wh beta_hat[n] + b)     (:732-735)
@@ -1992,6 +2012,20 @@ int nfst_compact_paths(const nfst_packed_lattices_t* lat, const int32_t* path_of
   const int blocks = (lat->n_lattices * 32 + threads - 1) / threads;
   nfst_compact_paths_kernel<<<blocks, threads, 0, static_cast<cudaStream_t>(cuda_stream)>>>(
       *lat, path_off, path_len, path_buf, out_off, out_arcs, out_labels);
+  NFST_CUDA_OK(cudaGetLastError());
+  return NFST_OK;
+}
+
+int nfst_pad_paths(const nfst_packed_lattices_t* lat, const int32_t* path_off, const int32_t* path_len, const int32_t* path_buf,
+                   int32_t skip_label, int64_t pad_label, int32_t row_len, int64_t* out_labels, int32_t* out_len,
+                   void* cuda_stream) {
+  if (!lat || !path_off || !path_len || !path_buf || !out_labels || row_len < 0)
+    return fail(NFST_ERR_BAD_ARG, "nfst_pad_paths: bad argument");
+  if (lat->n_lattices == 0) return NFST_OK;
+  const int threads = 256;
+  const int blocks = (lat->n_lattices * 32 + threads - 1) / threads;
+  nfst_pad_paths_kernel<<<blocks, threads, 0, static_cast<cudaStream_t>(cuda_stream)>>>(
+      *lat, path_off, path_len, path_buf, skip_label, pad_label, row_len, out_labels, out_len);
   NFST_CUDA_OK(cudaGetLastError());
   return NFST_OK;
 }

@@ -21,7 +21,7 @@ import numpy as np
 import torch
 
 from .data import load_fsa_from_npz
-from .ops import lattice_log_partition, lattice_viterbi
+from .ops import lattice_log_partition, lattice_viterbi_padded
 from .pack import PackedLattices, pack_dense
 
 
@@ -70,21 +70,15 @@ class ExactJointProb(torch.nn.Module):
         denom_prob = torch.zeros_like(num_prob)  # lightning.py:473
         if not return_samples:
             return num_prob, denom_prob
-        _, off, _, labels = lattice_viterbi(packed, theta=self._theta().detach().to(packed.device))
-        off_c = off.cpu()
-        rows = []
-        for b in range(packed.n_lattices):
-            lab = labels[int(off_c[b]): int(off_c[b + 1])].to(torch.int64)
-            if lab.numel() and int(lab[0]) == self.__bos__:
-                lab = lab[1:]  # the walk starts one arc in: samples never hold bos
-            rows.append(lab)
+        # the best path's labels after bos, one padded row per lattice, written on the device; ONE host read (the
+        # longest path) fixes T
+        _, labels, lengths = lattice_viterbi_padded(packed, theta=self._theta().detach().to(packed.device),
+                                                    pad_label=self.__pad__, skip_label=self.__bos__)
+        T = int(lengths.max()) if packed.n_lattices else 0
+        best = labels[:, :T]
         if packed.n_lattices == 1:
-            return num_prob, denom_prob, rows[0]
-        T = max((r.numel() for r in rows), default=0)
-        best = torch.full((packed.n_lattices, T), self.__pad__, dtype=torch.int64, device=packed.device)
-        for b, r in enumerate(rows):
-            best[b, : r.numel()] = r
-        return num_prob, denom_prob, best
+            return num_prob, denom_prob, best[0]
+        return num_prob, denom_prob, best.contiguous()
 
     def decode_from_npz(self, npz_path: str, vocab_size: Optional[int] = None, pad: Optional[int] = None):
         """``(prob, mark)`` of one example file, as ``JointProb.decode_from_npz`` (``lightning.py:647-658``)."""

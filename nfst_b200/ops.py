@@ -522,6 +522,41 @@ def lattice_viterbi(packed: PackedLattices, arc_scores=None, theta=None):
     return vit, offsets, path_arcs, path_labels
 
 
+def lattice_viterbi_padded(packed: PackedLattices, arc_scores=None, theta=None, *, pad_label: int, skip_label: int = -1):
+    """``lattice_viterbi`` with the result in the reference's sample layout and NO host synchronisation:
+    ``(score[B], labels[B, T] int64 padded with pad_label, lengths[B] int32)``, ``T = max_levels - 1`` (the longest
+    possible path).  A leading ``skip_label`` (the reference's samples never hold ``bos``, ``scorers.py:230-231``) is
+    dropped.  What ``JointProb.forward(return_samples=True)`` returns as ``best_sample`` (``lightning.py:474-479``)."""
+    global launch_count
+    lib = _lib.load()
+    dev = packed.device
+    sc, keep = _scores(packed, arc_scores, theta)
+    S, B = packed.n_states, packed.n_lattices
+    i32 = dict(dtype=torch.int32, device=dev)
+    delta = torch.empty(S, dtype=torch.float32, device=dev)
+    backptr = torch.empty(S, **i32)
+    vit = torch.empty(B, dtype=torch.float32, device=dev)
+    path_off = _path_slots(packed)
+    path_buf = torch.empty(max(S, 1), **i32)
+    path_len = torch.empty(B, **i32)
+    T = max(packed.max_levels - 1, 0)
+    labels = torch.empty((B, T), dtype=torch.int64, device=dev)
+    lengths = torch.empty(B, **i32)
+    with torch.cuda.device(dev):
+        streams = _GroupStreams(dev, len(packed.groups))
+        for i, g in enumerate(packed.groups):
+            _lib.check(lib.nfst_viterbi_paths_f32(packed.c_struct(), _launch(g, torch.float32), sc, delta.data_ptr(),
+                                                  backptr.data_ptr(), vit.data_ptr(), path_off.data_ptr(),
+                                                  path_buf.data_ptr(), path_len.data_ptr(), streams[i]))
+            launch_count += 1 if g.small_max_arcs > 0 else 2
+        streams.join()
+        _lib.check(lib.nfst_pad_paths(packed.c_struct(), path_off.data_ptr(), path_len.data_ptr(), path_buf.data_ptr(),
+                                      int(skip_label), int(pad_label), T, labels.data_ptr(), lengths.data_ptr(), _stream(dev)))
+        launch_count += 1
+    del keep
+    return vit, labels, lengths
+
+
 def _level_state_lists(packed: PackedLattices):
     """(states[S] int32 sorted by topological level, host offsets[L+1]) -- cached on `packed`."""
     cached = getattr(packed, "_level_lists", None)

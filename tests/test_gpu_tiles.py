@@ -202,6 +202,28 @@ def test_tile_mixed_batch_and_lattice_backward_outputs():
     assert torch.equal(r["vit_score"], vs)
 
 
+def test_viterbi_padded_rows_equal_the_ragged_result():
+    """``lattice_viterbi_padded`` (no host read; the layout of the reference's best sample, lightning.py:474-479) against
+    ``lattice_viterbi`` on a batch that mixes small-lattice, tile-stream and CSR groups; with and without a skipped first label."""
+    parts = [synth.transliteration_batch(6, seed=2), synth.random_dag_batch(2, 6_000, levels=12, seed=4), synth.snips_batch(3, seed=1)]
+    packs, scores = zip(*[ab.to(DEV).pack() for ab in parts])
+    p = concat_packed(list(packs))
+    sc = torch.cat(scores)
+    vs, off, arcs, labels = nb.lattice_viterbi(p, arc_scores=sc)
+    PADL = 3
+    first = int(labels[int(off[0])])
+    for skip in (-1, first):
+        vs2, rows, lens = nb.lattice_viterbi_padded(p, arc_scores=sc, pad_label=PADL, skip_label=skip)
+        assert torch.equal(vs, vs2) and rows.shape == (p.n_lattices, p.max_levels - 1) and rows.dtype == torch.int64
+        offc, lab, rows_c, lens_c = off.cpu().tolist(), labels.cpu(), rows.cpu(), lens.cpu().tolist()
+        for b in range(p.n_lattices):
+            want = lab[offc[b]:offc[b + 1]].to(torch.int64)
+            if skip >= 0 and want.numel() and int(want[0]) == skip:
+                want = want[1:]
+            assert lens_c[b] == want.numel() and torch.equal(rows_c[b, :lens_c[b]], want)
+            assert bool((rows_c[b, lens_c[b]:] == PADL).all())
+
+
 def test_tile_rejects_misuse_and_misalignment():
     ab = synth.random_dag_batch(2, 5_000, levels=8, seed=3).to(DEV)
     p, sc = ab.pack()
