@@ -80,6 +80,9 @@ __device__ __forceinline__ void bulk_g2s(unsigned dst, const void* src, unsigned
                "r"(bytes), "r"(bar)
                : "memory");
 }
+__device__ __forceinline__ void bulk_prefetch_l2(const void* src, unsigned bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
   asm volatile(
       "{\n\t.reg .pred p;\n\tWAIT_%=:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}" ::"r"(bar),
@@ -165,7 +168,7 @@ __device__ __forceinline__ int col_count(const int4& h, int k) {
 struct Seg {
   const uint16_t* codes;  // ring slots of the tile's arcs (tile-relative arc index)
   const float* vals;      // staged scores (pull) / conditionals (flow), tile-relative
-  const int32_t* labs;    // staged labels, tile-relative
+  const int32_t* labs;    // labels of the tile's arcs, tile-relative (staged, or global memory: LG)
   const unsigned char* st;  // the stage (tile header at 0)
   int arc0;               // canonical id of the tile's first arc
 };
@@ -595,7 +598,10 @@ __global__ void __launch_bounds__(NT_MAX, MINB)
 // =====================================================================================
 // GT: the fixed-point accumulator of gamma -- unsigned (2^-31 units: absolute error of a posterior < 1e-9) or
 // unsigned long long (2^-62 units: what is left is the float32 rounding of every contribution, ~6e-8 relative)
-template <bool DTH, bool POST, typename GT, int NT_MAX, int MINB>
+// LG: the labels of the dtheta histogram are not staged but read from global memory (coalesced: canonical arc order
+// is column-major) after a bulk L2 prefetch issued with the tile -- the fallback for launches whose DP ring leaves no
+// room for a second staged array (1M-arc lattices); measured slower than staging wherever both fit
+template <bool DTH, bool POST, typename GT, int NT_MAX, int MINB, bool LG = false>
 __global__ void __launch_bounds__(NT_MAX, MINB)
     tile_flow_kernel(const nfst_packed_lattices_t L, const int32_t* __restrict__ ids, const TP P, const float* cond,
                      const float* __restrict__ grad_logz, float* post, float* __restrict__ dtheta) {
@@ -641,11 +647,12 @@ __global__ void __launch_bounds__(NT_MAX, MINB)
     const unsigned sbytes = (static_cast<unsigned>(e.w) >> 16) << 4;
     const int a_lo = arc0 & ~3;
     const unsigned abytes = n_arcs ? static_cast<unsigned>(((arc0 + n_arcs + 3) & ~3) - a_lo) << 2 : 0u;
-    mbar_expect_tx(bar, sbytes + abytes + (DTH ? abytes : 0u));
+    mbar_expect_tx(bar, sbytes + abytes + (DTH && !LG ? abytes : 0u));
     bulk_g2s(st, stream + static_cast<size_t>(e.y) * 16, sbytes, bar);
     if (abytes) {
       bulk_g2s(st + P.cap_bytes, cond + a_lo, abytes, bar);
-      if (DTH) bulk_g2s(st + P.cap_bytes + P.arr_bytes, label_out + a_lo, abytes, bar);
+      if (DTH && !LG) bulk_g2s(st + P.cap_bytes + P.arr_bytes, label_out + a_lo, abytes, bar);
+      if (DTH && LG) bulk_prefetch_l2(label_out + a_lo, abytes);
     }
   };
   int4 nxt = make_int4(0, 0, 0, 0);
@@ -674,8 +681,9 @@ __global__ void __launch_bounds__(NT_MAX, MINB)
     }
     if (DTH) {
       const float pr = pf * (1.0f / kUnit);
-      if (hist) atomicAdd(&hist[g.labs[e]], __float2uint_rn(pr * P.hist_scale));
-      else atomicAdd(dtheta + g.labs[e], pr * gl);
+      const int lab = LG ? __ldg(g.labs + e) : g.labs[e];
+      if (hist) atomicAdd(&hist[lab], __float2uint_rn(pr * P.hist_scale));
+      else atomicAdd(dtheta + lab, pr * gl);
     }
   };
   float heavy_gam = 0.0f;
@@ -699,7 +707,7 @@ __global__ void __launch_bounds__(NT_MAX, MINB)
     g.codes = reinterpret_cast<const uint16_t*>(st + (static_cast<unsigned>(hd.z) >> 16));
     const int shift = g.arc0 & 3;
     g.vals = reinterpret_cast<const float*>(st + P.cap_bytes) + shift;
-    g.labs = reinterpret_cast<const int32_t*>(st + P.cap_bytes + P.arr_bytes) + shift;
+    g.labs = LG ? label_out + g.arc0 : reinterpret_cast<const int32_t*>(st + P.cap_bytes + P.arr_bytes) + shift;
     int s0 = hd.x + s_base;
     int vslot = hd.z & 0xffff;
 #pragma unroll 1
@@ -945,7 +953,10 @@ size_t nfst_tile_smem_bytes(const nfst_launch_t* launch, int32_t vocab, int pass
   const bool table = with_table && vocab <= NFST_THETA_SMEM_MAX;
   const int elem = (pass == 0 && launch->state_f64) || (pass == 1 && launch->tile_flow_bits == 64) ? 8 : 4;
   if (stages > 0) return geometry(launch, vocab, elem, n_f32_arrays, table, stages).smem;
-  return pick_geometry(launch, vocab, elem, n_f32_arrays, table).smem;
+  const size_t need = pick_geometry(launch, vocab, elem, n_f32_arrays, table).smem;
+  // the flow pass reads its labels from global memory when the second staged array does not fit
+  if (pass == 1 && n_f32_arrays == 2 && need > 227 * 1024) return pick_geometry(launch, vocab, elem, 1, table).smem;
+  return need;
 }
 
 int nfst_tile_pull_f32(const nfst_packed_lattices_t* lat, const nfst_launch_t* launch, const nfst_scores_t* scores, void* beta,
@@ -982,6 +993,9 @@ int nfst_tile_flow_f32(const nfst_packed_lattices_t* lat, const nfst_launch_t* l
   if (launch->tile_flow_bits != 0 && launch->tile_flow_bits != 32 && !wide)
     return nfst_fail_msg(NFST_ERR_BAD_ARG, "tile_flow_bits must be 0, 32 or 64");
   Geometry g = pick_geometry(launch, lat->vocab, wide ? 8 : 4, dtheta ? 2 : 1, table);
+  // no room for the staged labels next to a large DP ring: read them from global memory (LG kernels)
+  const bool lg = dtheta && g.smem > 227 * 1024;
+  if (lg) g = pick_geometry(launch, lat->vocab, wide ? 8 : 4, 1, table);
   // dtheta histogram unit: an expected label count is at most the number of levels
   int lv = 1;
   while (lv < launch->n_levels) lv <<= 1;
@@ -990,26 +1004,32 @@ int nfst_tile_flow_f32(const nfst_packed_lattices_t* lat, const nfst_launch_t* l
   if (g.smem > 227 * 1024) return nfst_fail_msg(NFST_ERR_TOO_LARGE, "tile-stream launch needs %zu bytes of shared memory", g.smem);
   if (!aligned16(cond) || (dtheta && !aligned16(lat->label_out)))
     return nfst_fail_msg(NFST_ERR_BAD_ARG, "cond and label_out must be 16-byte aligned (they are fetched with bulk copies)");
-#define FLOW_GO(DTHv, POSTv, GTv, NTv, MINBv)                                                                             \
+#define FLOW_GO(DTHv, POSTv, GTv, NTv, MINBv, LGv)                                                                        \
   do {                                                                                                                    \
-    auto k = tile_flow_kernel<DTHv, POSTv, GTv, NTv, MINBv>;                                                              \
+    auto k = tile_flow_kernel<DTHv, POSTv, GTv, NTv, MINBv, LGv>;                                                         \
     if (int rc = prepare(k, g.smem)) return rc;                                                                           \
     k<<<launch->n_ids, launch->block_threads, g.smem, stream>>>(*lat, launch->lattice_ids, g.p, cond, grad_logz, post, dtheta); \
+  } while (0)
+#define FLOW_DTH(POSTv, GTv, NTv, MINBv)                      \
+  do {                                                        \
+    if (lg) FLOW_GO(true, POSTv, GTv, NTv, MINBv, true);      \
+    else FLOW_GO(true, POSTv, GTv, NTv, MINBv, false);        \
   } while (0)
 #define FLOW_NT(NTv, MINBv)                                                                  \
   do {                                                                                       \
     if (wide) {                                                                              \
-      if (dtheta && post) FLOW_GO(true, true, unsigned long long, NTv, MINBv);               \
-      else if (dtheta) FLOW_GO(true, false, unsigned long long, NTv, MINBv);                 \
-      else FLOW_GO(false, true, unsigned long long, NTv, MINBv);                             \
+      if (dtheta && post) FLOW_DTH(true, unsigned long long, NTv, MINBv);                    \
+      else if (dtheta) FLOW_DTH(false, unsigned long long, NTv, MINBv);                      \
+      else FLOW_GO(false, true, unsigned long long, NTv, MINBv, false);                      \
     } else {                                                                                 \
-      if (dtheta && post) FLOW_GO(true, true, unsigned, NTv, MINBv);                         \
-      else if (dtheta) FLOW_GO(true, false, unsigned, NTv, MINBv); /* no per-arc output */   \
-      else FLOW_GO(false, true, unsigned, NTv, MINBv);                                       \
+      if (dtheta && post) FLOW_DTH(true, unsigned, NTv, MINBv);                              \
+      else if (dtheta) FLOW_DTH(false, unsigned, NTv, MINBv); /* no per-arc output */        \
+      else FLOW_GO(false, true, unsigned, NTv, MINBv, false);                                \
     }                                                                                        \
   } while (0)
   TILE_BY_BLOCK(FLOW_NT);
 #undef FLOW_NT
+#undef FLOW_DTH
 #undef FLOW_GO
   TILE_CUDA_OK(cudaGetLastError());
   return 0;

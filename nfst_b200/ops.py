@@ -24,6 +24,7 @@ import torch
 
 from . import _lib
 from . import pack as pack_mod
+from . import tiles as tiles_mod
 from .pack import LaunchGroup, PackedLattices, pack_dense
 
 # number of library kernels launched since import (bench.py reports the per-step count)
@@ -39,7 +40,7 @@ def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
 WINDOW_BYTES_MAX = pack_mod.WINDOW_BYTES_MAX
 # lattices deeper than this default to float64 state vectors (see resolve_state_dtype): column-major lattices
 # (their kernels form every arc term as a float32 OFFSET from a reference arc) / all others (plain float32 log-values)
-F64_DEPTH = 96
+F64_DEPTH = tiles_mod.F64_LEVELS  # 96: the tile-stream packer sizes the DP rings of such lattices for 8-byte slots
 F64_DEPTH_PLAIN = 64
 # depth of the tile-stream kernels' stage rings; 0 = chosen by the library from the shared memory per block
 TILE_STAGES = int(os.environ.get("NFST_TILE_STAGES", "0"))
@@ -142,10 +143,31 @@ def _scores(packed: PackedLattices, arc_scores, theta):
     if packed.n_arcs == 0:
         a = None
     t = _check_f32("theta", theta, packed.vocab, dev)
+    if a is not None and t is not None and _two_arrays_do_not_fit(packed):
+        # per-arc scores AND theta: the tile-stream pull pass stages two arrays per tile; next to a DP ring that fills
+        # the shared memory (1M-arc lattices) they do not fit, so the same sum w = score + theta[label] (one float32
+        # add, as in the kernels) is formed once here and the pass runs on per-arc scores alone
+        a = a + t[packed.label_out.long()]
+        t = None
     c = _lib.ScoresC()
     c.arc_scores = _ptr(a)
     c.theta = _ptr(t)
     return c, (a, t)  # keep the tensors alive for the duration of the call
+
+
+def _two_arrays_do_not_fit(packed: PackedLattices) -> bool:
+    """some tile-stream group of the batch has no room for two staged per-arc arrays (cached on the batch)"""
+    cached = getattr(packed, "_two_arrays_overflow", None)
+    if cached is None:
+        lib = _lib.load()
+        cached = False
+        for g in packed.groups:
+            if g.tiles:
+                for dt in (torch.float32, torch.float64):
+                    need = lib.nfst_tile_smem_bytes(_launch(g, dt), packed.vocab, 0, 2, 1, 0)
+                    cached = cached or need > 227 * 1024
+        packed._two_arrays_overflow = cached
+    return cached
 
 
 def _gamma_far(packed: PackedLattices, alpha: bool = False) -> Optional[torch.Tensor]:

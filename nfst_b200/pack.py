@@ -749,7 +749,7 @@ def pack_arcs(
         sd1, ss1 = slot_of1[gdst[inner1]], slot_of1[gsrc[inner1]]
         span1 = level_ptr[sd1] + counts[sd1] - level_ptr[ss1]
         tile_nw = tiles_mod.warps_per_lattice(S_b0, n_levels, tiles_mod.span_quantile(la1, span1, B))
-        cap1 = tiles_mod.ring_cap_slots(tile_nw)
+        cap1 = tiles_mod.ring_cap_slots(tile_nw, n_levels)
         # slices are per (level, warp): every level an arc crosses may add a partial slice per warp
         est1 = span1 + 32 * tile_nw[la1] * (sd1 - ss1 + 1)
         far1 = torch.bincount(la1[est1 > (cap1[la1] * 3) // 4], minlength=B)

@@ -75,9 +75,16 @@ def stage_est(nw: torch.Tensor) -> torch.Tensor:
     return 7 * tile_arcs_for(nw) + 512
 
 
-def ring_cap_slots(nw: torch.Tensor) -> torch.Tensor:
-    """Largest DP ring (slots, far table included) that fits beside the stages of an nw-warp block."""
-    return torch.clamp(torch.div(SMEM_BUDGET - 2 * stage_est(nw) * nw, 4, rounding_mode="floor"), min=64, max=min(RING_MAX, 65000))
+# lattices with more than this many levels run with float64 state vectors by default (ops.resolve_state_dtype): their
+# ring slots are 8 bytes
+F64_LEVELS = 96
+
+
+def ring_cap_slots(nw: torch.Tensor, levels: torch.Tensor = None) -> torch.Tensor:
+    """Largest DP ring (slots, far table included) that fits beside the stages of an nw-warp block; ``levels``: the
+    lattices' level counts (deep lattices keep float64 state: half as many slots fit)."""
+    elem = 4 if levels is None else torch.where(levels > F64_LEVELS, torch.full_like(nw, 8), torch.full_like(nw, 4))
+    return torch.clamp(torch.div(SMEM_BUDGET - 2 * stage_est(nw) * nw, elem, rounding_mode="floor"), min=64, max=min(RING_MAX, 65000))
 
 
 def warps_per_lattice(states: torch.Tensor, levels: torch.Tensor, span: torch.Tensor = None) -> torch.Tensor:
@@ -92,7 +99,8 @@ def warps_per_lattice(states: torch.Tensor, levels: torch.Tensor, span: torch.Te
     width = states.to(torch.float64) / torch.clamp(levels, min=1).to(torch.float64)
     slices = torch.clamp(torch.ceil(width / 32.0), min=1.0)
     base = torch.ones_like(states) << torch.clamp(torch.ceil(torch.log2(slices)).to(torch.int64), 0, int(NW_BASE).bit_length() - 1)
-    ring = 4.0 * (8 * width if span is None else 1.5 * span.to(torch.float64))  # bytes
+    elem = torch.where(levels > F64_LEVELS, 8.0, 4.0).to(torch.float64)  # deep lattices: float64 state
+    ring = elem * (8 * width if span is None else 1.5 * span.to(torch.float64))  # bytes
     best = base
     done = torch.zeros_like(states, dtype=torch.bool)
     for lg in range(0, 6):
@@ -216,7 +224,7 @@ def build(*, lt_s, slot, level_off, level_ptr, n_levels, st_w, st_j, out_ptr, ou
     od = sl_ord[slice_of_state[a_dst]]
     need = od - slot_first_ord[slot[a_src]] + 1  # slices the ring must span for this arc
     need = torch.where(a_last, torch.zeros_like(need), need)
-    cap_slots = ring_cap_slots(tile_nw)  # ring + constant slot + far table, per lattice
+    cap_slots = ring_cap_slots(tile_nw, n_levels.to(torch.int64))  # ring + constant slot + far table, per lattice
     ring_cap = torch.div(cap_slots, 32, rounding_mode="floor") - 1  # slices
     if bool((lvl_slices_max[tile_lat] > ring_cap[tile_lat]).any()):
         raise ValueError("a level is wider than the largest DP ring; pack with tiles=False or fewer warps (NFST_TILE_WARPS)")

@@ -224,6 +224,44 @@ def test_viterbi_padded_rows_equal_the_ragged_result():
             assert bool((rows_c[b, lens_c[b]:] == PADL).all())
 
 
+def test_tile_large_ring_leaves_no_room_for_a_second_staged_array():
+    """1M-arc lattices: the DP ring fills the shared memory, so (a) the flow pass reads the labels of the dtheta
+    histogram from global memory instead of staging them and (b) per-arc scores + theta are summed once before the
+    pull pass.  Both against the C oracle."""
+    ab = synth.random_dag_batch(2, 1_000_000, seed=5)
+    p, sc = ab.to(DEV).pack()
+    assert p.has_tiles and nb.ops._two_arrays_do_not_fit(p)
+    g = torch.Generator().manual_seed(1)
+    theta = torch.randn(p.vocab, generator=g) * 0.3
+    lab = ab.label.numpy()
+    for with_scores in (False, True):
+        w = theta.numpy()[lab] + (ab.scores.numpy() if with_scores else 0.0)
+        ab2 = synth.ArcBatch(ab.arc_lattice, ab.src, ab.dst, ab.label, torch.from_numpy(w.astype(np.float32)), ab.n_states, ab.vocab)
+        o_logz, _, _, o_post = c_oracle.forward_backward(oracle_batch(ab2))
+        logz, _, _, post, dth = nb.lattice_forward_backward(p, arc_scores=sc if with_scores else None, theta=theta.to(DEV),
+                                                            want_dtheta=True)
+        np.testing.assert_allclose(logz.cpu().numpy(), o_logz, rtol=1e-6)
+        ref = o_post[p.arc_origin.cpu().numpy()]
+        assert np.all(np.abs(post.cpu().numpy() - ref) <= 1e-5 * ref + 2e-9)
+        want = np.zeros(p.vocab)
+        np.add.at(want, lab, o_post)
+        np.testing.assert_allclose(dth.cpu().numpy(), want, rtol=1e-5, atol=1e-5)
+        score, off, arcs, labels = nb.lattice_viterbi(p, arc_scores=sc if with_scores else None, theta=theta.to(DEV))
+        o_score, o_paths, _ = c_oracle.viterbi(oracle_batch(ab2))
+        assert np.array_equal(score.cpu().numpy().view(np.uint32), o_score.view(np.uint32))
+
+
+def test_deep_and_wide_lattice_runs_with_float64_state():
+    """More than 96 levels: float64 state by default, i.e. 8-byte ring slots -- the packer sizes the ring for them (or
+    leaves the lattice to the level-major kernels); the call must not be refused for shared memory."""
+    ab = synth.random_dag_batch(1, 2_000_000, levels=128, seed=2)
+    p, sc, _ = check_fwd_bwd(ab)
+    assert nb.ops.resolve_state_dtype(p) == torch.float64
+    for g in p.groups:
+        assert not g.tiles or (g.tile_ring + 32) * 8 < 200 * 1024
+    viterbi_matches(ab, p, sc)
+
+
 def test_tile_rejects_misuse_and_misalignment():
     ab = synth.random_dag_batch(2, 5_000, levels=8, seed=3).to(DEV)
     p, sc = ab.pack()

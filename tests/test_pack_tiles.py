@@ -145,6 +145,15 @@ def test_tile_default_thresholds():
     assert p.has_tiles and p.groups[0].block_threads == 512
 
 
+def test_deep_lattices_get_rings_sized_for_float64_state():
+    # more than 96 levels -> float64 state by default (ops.resolve_state_dtype): 8 bytes per ring slot
+    nw = torch.tensor([4, 16])
+    shallow, deep = T.ring_cap_slots(nw, torch.tensor([64, 64])), T.ring_cap_slots(nw, torch.tensor([128, 400]))
+    assert bool((deep <= shallow).all()) and bool((deep * 8 <= T.SMEM_BUDGET).all()) and bool((deep >= 64).all())
+    p, _ = synth.random_dag_batch(1, 60_000, levels=400, seed=9).pack()  # narrow and deep: still tile-stream
+    assert p.has_tiles and (p.groups[0].tile_ring + 32) * 8 < 200 * 1024
+
+
 def test_in_order_arrays_are_built_on_demand_and_equal_the_eager_pack():
     # a batch of column-major lattices is packed without the arcs-by-destination arrays and the chunk lists (only the
     # CSR forward kernel reads them: alpha); ensure_in_order() builds exactly what an eager pack would have
