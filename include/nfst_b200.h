@@ -182,6 +182,8 @@ typedef struct nfst_packed_lattices {
  * needed for posteriors within 1e-5 on deep lattices, where |alpha| is in the hundreds
  * or thousands and an fp32 ulp is no longer small against 1e-5.
  */
+/* tile-stream groups deeper than this keep float64 DP rings when the state vectors are float64 (see tile_flow_bits) */
+#define NFST_TILE_F64_LEVELS 96
 typedef struct nfst_launch {
   const int32_t* lattice_ids;
   int32_t n_ids;
@@ -220,7 +222,9 @@ typedef struct nfst_launch {
    * tile_stages: 0 = chosen by the library from the shared memory the launch leaves per block.
    * tile_flow_bits: width of the flow pass's fixed-point gamma accumulator -- 32 (or 0): 2^-31 units, posteriors
    * carry an ABSOLUTE error below 1e-9 (relative 1e-5 down to posteriors of 1e-4); 64: 2^-62 units, the error is
-   * the float32 rounding of each contribution (relative ~1e-6 at any size), twice the ring's shared memory. */
+   * the float32 rounding of each contribution (relative ~1e-6 at any size), twice the ring's shared memory.
+   * With state_f64 the DP ring holds doubles only when n_levels > NFST_TILE_F64_LEVELS (the packer sizes such
+   * lattices' rings for 8-byte slots); shallower groups keep the float32 ring and write beta / logZ as doubles. */
   int32_t tiles;
   int32_t tile_ring;
   int32_t tile_far;

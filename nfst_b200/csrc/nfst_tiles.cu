@@ -198,9 +198,11 @@ __device__ __forceinline__ void block_bars(int n) {
   asm volatile("{\n\t.reg .pred p;\n\tLB_%=:\n\tbar.sync 0;\n\tadd.s32 %0, %0, -1;\n\tsetp.gt.s32 p, %0, 0;\n\t@p bra.uni LB_%=;\n\t}" : "+r"(n)::"memory");
 }
 
-template <bool TROP, bool SC, bool TH, typename OT>
+// OT: type of beta[] / logz[] in global memory; RT: type of the DP ring (float32 for lattices of at most 96 levels even
+// when the batch's state vectors are float64: their values are what a float32 launch computes, stored as doubles)
+template <bool TROP, bool SC, bool TH, typename OT, typename RT = OT>
 struct PullCtx {
-  using RingT = typename std::conditional<TROP, float, OT>::type;
+  using RingT = typename std::conditional<TROP, float, RT>::type;
   unsigned ring_s;  // shared-window address of the ring
   const float* th;
   OT* beta;
@@ -381,12 +383,12 @@ struct HeavyTrop {
   int arg;
 };
 
-template <bool TROP, bool SC, bool TH, typename OT, int NT_MAX, int MINB>
+template <bool TROP, bool SC, bool TH, typename OT, int NT_MAX, int MINB, typename RT = OT>
 __global__ void __launch_bounds__(NT_MAX, MINB)
     tile_pull_kernel(const nfst_packed_lattices_t L, const int32_t* __restrict__ ids, const TP P,
                      const float* __restrict__ arc_scores, const float* __restrict__ theta, OT* beta, OT* __restrict__ logz,
                      float* cond, float* delta, int32_t* __restrict__ backptr, float* __restrict__ vit_score) {
-  using Ctx = PullCtx<TROP, SC, TH, OT>;
+  using Ctx = PullCtx<TROP, SC, TH, OT, RT>;
   using RingT = typename Ctx::RingT;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
   const int b = ids ? ids[blockIdx.x] : blockIdx.x;
@@ -898,29 +900,29 @@ int check_launch(const nfst_packed_lattices_t* lat, const nfst_launch_t* launch)
     else CALL(1024, 1);                                  \
   } while (0)
 
-template <bool TROP, typename OT>
+template <bool TROP, typename OT, typename RT = OT>
 int launch_pull(const nfst_packed_lattices_t* lat, const nfst_launch_t* launch, const nfst_scores_t* sc, OT* beta, OT* logz,
                 float* cond, float* delta, int32_t* backptr, float* vit, cudaStream_t stream) {
   const bool has_sc = sc->arc_scores != nullptr, has_th = sc->theta != nullptr;
   const bool table = has_th && lat->vocab <= NFST_THETA_SMEM_MAX;
-  const Geometry g = pick_geometry(launch, lat->vocab, TROP ? 4 : static_cast<int>(sizeof(OT)), (has_sc ? 1 : 0) + (has_th ? 1 : 0), table);
+  const Geometry g = pick_geometry(launch, lat->vocab, TROP ? 4 : static_cast<int>(sizeof(RT)), (has_sc ? 1 : 0) + (has_th ? 1 : 0), table);
   if (g.smem > 227 * 1024) return nfst_fail_msg(NFST_ERR_TOO_LARGE, "tile-stream launch needs %zu bytes of shared memory", g.smem);
   if ((has_sc && !aligned16(sc->arc_scores)) || (has_th && !aligned16(lat->label_out)))
     return nfst_fail_msg(NFST_ERR_BAD_ARG, "arc_scores and label_out must be 16-byte aligned (they are fetched with bulk copies)");
 #define PULL_NT(NTv, MINBv)                                                                                     \
   do {                                                                                                          \
     if (has_sc && has_th) {                                                                                     \
-      auto k = tile_pull_kernel<TROP, true, true, OT, NTv, MINBv>;                                              \
+      auto k = tile_pull_kernel<TROP, true, true, OT, NTv, MINBv, RT>;                                            \
       if (int rc = prepare(k, g.smem)) return rc;                                                               \
       k<<<launch->n_ids, launch->block_threads, g.smem, stream>>>(*lat, launch->lattice_ids, g.p, sc->arc_scores, sc->theta, \
                                                                   beta, logz, cond, delta, backptr, vit);       \
     } else if (has_th) {                                                                                        \
-      auto k = tile_pull_kernel<TROP, false, true, OT, NTv, MINBv>;                                             \
+      auto k = tile_pull_kernel<TROP, false, true, OT, NTv, MINBv, RT>;                                            \
       if (int rc = prepare(k, g.smem)) return rc;                                                               \
       k<<<launch->n_ids, launch->block_threads, g.smem, stream>>>(*lat, launch->lattice_ids, g.p, sc->arc_scores, sc->theta, \
                                                                   beta, logz, cond, delta, backptr, vit);       \
     } else {                                                                                                    \
-      auto k = tile_pull_kernel<TROP, true, false, OT, NTv, MINBv>;                                             \
+      auto k = tile_pull_kernel<TROP, true, false, OT, NTv, MINBv, RT>;                                            \
       if (int rc = prepare(k, g.smem)) return rc;                                                               \
       k<<<launch->n_ids, launch->block_threads, g.smem, stream>>>(*lat, launch->lattice_ids, g.p, sc->arc_scores, sc->theta, \
                                                                   beta, logz, cond, delta, backptr, vit);       \
@@ -951,7 +953,7 @@ int nfst_tile_debug_read(int32_t* out8) {
 size_t nfst_tile_smem_bytes(const nfst_launch_t* launch, int32_t vocab, int pass, int n_f32_arrays, int with_table, int stages) {
   if (!launch || !launch->tiles) return 0;
   const bool table = with_table && vocab <= NFST_THETA_SMEM_MAX;
-  const int elem = (pass == 0 && launch->state_f64) || (pass == 1 && launch->tile_flow_bits == 64) ? 8 : 4;
+  const int elem = (pass == 0 && launch->state_f64 && launch->n_levels > NFST_TILE_F64_LEVELS) || (pass == 1 && launch->tile_flow_bits == 64) ? 8 : 4;
   if (stages > 0) return geometry(launch, vocab, elem, n_f32_arrays, table, stages).smem;
   const size_t need = pick_geometry(launch, vocab, elem, n_f32_arrays, table).smem;
   // the flow pass reads its labels from global memory when the second staged array does not fit
@@ -969,7 +971,13 @@ int nfst_tile_pull_f32(const nfst_packed_lattices_t* lat, const nfst_launch_t* l
   const bool trop = delta || backptr || vit_score;
   if (trop && !backptr) return nfst_fail_msg(NFST_ERR_BAD_ARG, "the tropical pass needs backptr[S]");
   if (logs) {
-    const int rc = launch->state_f64
+    // float64 state vectors, but a group whose lattices have at most NFST_TILE_F64_LEVELS levels keeps the float32 ring
+    // it was packed for: the values a float32 launch computes, written as doubles (a batch is float64 as soon as ONE of
+    // its lattices is deep; its shallow, wide lattices must not pay -- or be refused -- for that)
+    const int rc = launch->state_f64 && launch->n_levels <= NFST_TILE_F64_LEVELS
+                       ? launch_pull<false, double, float>(lat, launch, scores, static_cast<double*>(beta), static_cast<double*>(logz_bwd),
+                                                           cond, nullptr, nullptr, nullptr, stream)
+                   : launch->state_f64
                        ? launch_pull<false, double>(lat, launch, scores, static_cast<double*>(beta), static_cast<double*>(logz_bwd), cond,
                                                     nullptr, nullptr, nullptr, stream)
                        : launch_pull<false, float>(lat, launch, scores, static_cast<float*>(beta), static_cast<float*>(logz_bwd), cond,

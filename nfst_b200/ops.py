@@ -41,7 +41,9 @@ WINDOW_BYTES_MAX = pack_mod.WINDOW_BYTES_MAX
 # lattices deeper than this default to float64 state vectors (see resolve_state_dtype): column-major lattices
 # (their kernels form every arc term as a float32 OFFSET from a reference arc) / all others (plain float32 log-values)
 F64_DEPTH = tiles_mod.F64_LEVELS  # 96: the tile-stream packer sizes the DP rings of such lattices for 8-byte slots
-F64_DEPTH_PLAIN = 64
+# shared memory of all SMs that a small-lattice group's one-launch forward+backward may claim (148 SMs x ~200 KB)
+SMALL_RESIDENT_BYTES = int(os.environ.get("NFST_SMALL_RESIDENT_BYTES", str(148 * 200 * 1024)))
+F64_DEPTH_PLAIN = int(os.environ.get("NFST_F64_DEPTH_PLAIN", "32"))
 # depth of the tile-stream kernels' stage rings; 0 = chosen by the library from the shared memory per block
 TILE_STAGES = int(os.environ.get("NFST_TILE_STAGES", "0"))
 # width of the tile-stream flow pass's fixed-point accumulator (see nfst_launch_t.tile_flow_bits): 32 or 64
@@ -54,9 +56,13 @@ def resolve_state_dtype(packed: PackedLattices, state_dtype="auto") -> torch.dty
     An fp32 log-value x is only known to ulp(|x|)/2 ~ 6e-8*|x| and that rounding is
     committed at every level, so posteriors of deep lattices (|alpha| in the hundreds or
     thousands) cannot be 1e-5-accurate with fp32 state.  "auto" therefore uses float64 for
-    batches with a lattice deeper than F64_DEPTH levels (F64_DEPTH_PLAIN for lattices outside the column-major
-    layouts: measured 1.3e-5 on 70-level edit lattices with float32 state) -- they are latency-bound, the wider
-    state costs nothing measurable -- and float32 otherwise.
+    batches with a lattice deeper than F64_DEPTH = 96 levels -- F64_DEPTH_PLAIN = 32 for lattices outside the
+    column-major layouts, whose kernels form posteriors as exp(alpha + w + beta - logZ) from float32 log-values
+    rounded at every level: random batches measured up to 2e-5 on 40-63-level edit lattices and 3e-5 on 43-level
+    cipher lattices (|alpha| + |beta| = 260) with float32 state (tools/fuzz_gpu.py) -- and float32 otherwise.  The
+    column-major kernels take posteriors from per-state conditionals and a fixed-point flow instead, which does not
+    accumulate that rounding: 5e-6 at 64 levels.  float64 state costs the small-lattice kernel 17 % at B = 32 and
+    50 % at B = 4096 (shared memory per lattice); ``state_dtype=torch.float32`` buys that back where 2e-5 is enough.
     """
     if state_dtype == "auto" or state_dtype is None:
         if packed.max_levels > F64_DEPTH:
@@ -364,6 +370,17 @@ def lattice_backward(
     return out
 
 
+def _small_fused_fits(g: LaunchGroup, vocab: int, st: torch.dtype) -> bool:
+    """The one-launch forward+backward of a small-lattice group keeps both passes' arrays in shared memory: it wins
+    while all the group's lattices are resident at once (config 1, B = 32: 69 vs 84 us for two launches) and loses once
+    they are not (config 5, B = 4096: 206 vs 153 us -- the two kernels each need about half the footprint, so twice as
+    many lattices run per wave)."""
+    foot = pack_mod.small_footprint_bytes(g.small_max_states, g.small_max_arcs, g.small_max_levels, vocab)
+    if st != torch.float64:
+        foot = foot * 3 // 4  # the bound assumes float64 state vectors
+    return g.n * (foot + 1024) <= SMALL_RESIDENT_BYTES
+
+
 def lattice_forward_backward(packed: PackedLattices, arc_scores=None, theta=None, *, want_dtheta: bool = False,
                              state_dtype="auto"):
     """(logZ[B], alpha[S], beta[S], post[A]) -- plus dtheta[V] when ``want_dtheta``.
@@ -408,7 +425,7 @@ def lattice_forward_backward(packed: PackedLattices, arc_scores=None, theta=None
                 _lib.check(lib.nfst_fwd_f32(packed.c_struct(), _launch_csr_forward(g, st), sc, alpha.data_ptr(),
                                             logz.data_ptr(), stream))
                 launch_count += 3
-            elif g.small_max_arcs > 0:
+            elif g.small_max_arcs > 0 and _small_fused_fits(g, packed.vocab, st):
                 _lib.check(lib.nfst_fwd_bwd_small_f32(packed.c_struct(), lc, sc, None, alpha.data_ptr(), logz.data_ptr(),
                                                       beta.data_ptr(), logz_bwd.data_ptr(), post.data_ptr(),
                                                       _ptr(dtheta), stream))

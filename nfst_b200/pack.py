@@ -421,7 +421,9 @@ def build_groups(stats, dev, chunk_info=None) -> List[LaunchGroup]:
     wide, small = wide * (1 - sell) * (1 - tile), small * (1 - sell) * (1 - tile)
     # sliced-column lattices: one group per block size (a power of two of warps); tile-stream lattices likewise
     gkey = torch.where(sell > 0, (stats["sell_block"] * 2) * 2 + 4096, (stats["block_class"] * 2 + wide) * 2 + small)
-    gkey = torch.where(tile > 0, stats["tile_warps_log2"] + 8192, gkey)
+    # (deep tile-stream lattices -- float64 DP rings by default -- do not share a launch with shallow ones)
+    deep = (stats["levels"] > tiles_mod.F64_LEVELS).to(torch.int64)
+    gkey = torch.where(tile > 0, stats["tile_warps_log2"] + 8192 + 64 * deep, gkey)
     groups: List[LaunchGroup] = []
     B = int(gkey.numel())
     for key in sorted(set(gkey.tolist()), reverse=True):
@@ -429,7 +431,7 @@ def build_groups(stats, dev, chunk_info=None) -> List[LaunchGroup]:
         members = members[torch.argsort(stats["arcs"][members], descending=True, stable=True)]
         if key >= 8192:
             groups.append(LaunchGroup(
-                ids=members.to(torch.int32).to(dev), n=int(members.numel()), block_threads=32 << (key - 8192),
+                ids=members.to(torch.int32).to(dev), n=int(members.numel()), block_threads=32 << ((key - 8192) & 63),
                 max_states=int(stats["states"][members].max()), max_reach=int(stats["reach"][members].max()),
                 n_arcs=int(stats["arcs"][members].sum()), n_levels=int(stats["levels"][members].max()),
                 chunk_cap=int(stats["chunk_cap"][members].max()), csr_block_threads=1 << int(stats["block_class"][members].max()),
