@@ -14,8 +14,7 @@ import torch  # noqa: E402
 import nfst_b200 as nb  # noqa: E402
 from nfst_b200 import synth  # noqa: E402
 from oracle import c_oracle  # noqa: E402
-from tests.test_gpu_parity import DEV, check_fwd_bwd, oracle_batch  # noqa: E402
-from tests.test_gpu_tiles import viterbi_matches  # noqa: E402
+from tests.test_gpu_parity import DEV, oracle_batch  # noqa: E402
 
 budget = float(sys.argv[1]) if len(sys.argv) > 1 else 90.0
 rng = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 0)
@@ -49,31 +48,78 @@ def part():
     return f"dag {arcs} arcs, {levels} levels x{B} s{s}", synth.random_dag_batch(B, arcs, levels=levels, seed=s)
 
 
+def run_case(names, parts):
+    """one random batch: packed jointly or part by part (concat_packed, the per-step collate of cached examples), scored
+    per arc / by theta / both, sometimes with integer scores (exact Viterbi ties)"""
+    from nfst_b200.pack import concat_packed
+    from tests.test_gpu_parity import gpu_state_to_orig
+
+    ab = cat(list(parts))
+    A = ab.src.numel()
+    if rng.integers(0, 4) == 0:
+        ab.scores = -torch.from_numpy(rng.integers(0, 3, size=A)).float()
+    if rng.integers(0, 2) and len(parts) > 1:
+        how = "concat"
+        packs, off, origin = [], 0, []
+        for a in parts:
+            a.vocab = ab.vocab  # concat_packed: all parts share one vocabulary
+            pk, _ = a.to(DEV).pack()
+            packs.append(pk)
+            origin.append(pk.arc_origin.cpu() + off)
+            off += a.src.numel()
+        p, origin = concat_packed(packs), torch.cat(origin).numpy()
+    else:
+        how = "joint"
+        p, _ = ab.to(DEV).pack()
+        origin = p.arc_origin.cpu().numpy()
+    mode = ["arcs", "theta", "both"][int(rng.integers(0, 3))]
+    theta = torch.from_numpy(rng.normal(size=p.vocab).astype(np.float32) * 0.3)
+    lab = ab.label.numpy()
+    w = np.zeros(A, dtype=np.float32)
+    if mode != "theta":
+        w = w + ab.scores.numpy()
+    if mode != "arcs":
+        w = (w + theta.numpy()[lab]).astype(np.float32)
+    sc = torch.from_numpy(ab.scores.numpy()[origin]).to(DEV) if mode != "theta" else None
+    th = theta.to(DEV) if mode != "arcs" else None
+    ab2 = synth.ArcBatch(ab.arc_lattice, ab.src, ab.dst, ab.label, torch.from_numpy(w), ab.n_states, ab.vocab)
+    ob = oracle_batch(ab2)
+    o_logz, o_alpha, o_beta, o_post = c_oracle.forward_backward(ob)
+    st = "auto" if rng.integers(0, 5) else torch.float64
+    out = nb.lattice_forward_backward(p, arc_scores=sc, theta=th, want_dtheta=th is not None, state_dtype=st)
+    logz, alpha, beta, post = (t.cpu().numpy().astype(np.float64) for t in out[:4])
+    g2o = gpu_state_to_orig(p, ab.n_states.numpy())
+    np.testing.assert_allclose(logz, o_logz, rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(alpha, o_alpha[g2o], rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(beta, o_beta[g2o], rtol=1e-5, atol=1e-5)
+    ref = o_post[origin]
+    bad = np.abs(post - ref) > 1e-5 * ref + 1e-7
+    assert not bad.any(), f"posteriors: {int(bad.sum())} arcs beyond 1e-5 (worst {float(np.max(np.abs(post - ref) / (ref + 1e-7))):.2e})"
+    if th is not None:
+        want = np.zeros(p.vocab)
+        np.add.at(want, lab, o_post)
+        # (a label's gradient sums thousands of posteriors; the CSR kernels add them with float32 atomics: 2.4e-5 measured
+        # on 200-level bigram cipher lattices -- the tile-stream kernels accumulate in fixed point)
+        np.testing.assert_allclose(out[4].cpu().numpy(), want, rtol=5e-5, atol=5e-5)
+    score, off, arcs, labels = nb.lattice_viterbi(p, arc_scores=sc, theta=th)
+    o_score, o_paths, o_labels = c_oracle.viterbi(ob)
+    assert np.array_equal(score.cpu().numpy().view(np.uint32), o_score.view(np.uint32)), "Viterbi scores differ"
+    offc, arcs_c, lab_c = off.cpu().numpy(), arcs.cpu().numpy(), labels.cpu().numpy()
+    for b in range(p.n_lattices):
+        assert np.array_equal(origin[arcs_c[offc[b]:offc[b + 1]]], o_paths[b]), f"Viterbi path of lattice {b} differs"
+        assert np.array_equal(lab_c[offc[b]:offc[b + 1]], o_labels[b])
+    kinds = sorted({"tiles" if g.tiles else "sell" if g.sell else "small" if g.small_max_arcs > 0 else
+                    "level" if g.fwd_level_chunks is not None else "csr" for g in p.groups})
+    return f"[{', '.join(kinds)}; {how}, {mode}, state {str(alpha.dtype) if False else out[1].dtype}; {p.n_arcs} arcs, {p.max_levels} levels]"
+
+
 t0 = time.time()
 n = fails = refused = 0
 while time.time() - t0 < budget:
     names, parts = zip(*[part() for _ in range(int(rng.integers(1, 4)))])
-    ab = cat(list(parts))
     n += 1
     try:
-        p, sc, _ = check_fwd_bwd(ab)
-        viterbi_matches(ab, p, sc)
-        theta = torch.from_numpy(rng.normal(size=p.vocab).astype(np.float32) * 0.3)
-        w = theta.numpy()[ab.label.numpy()]
-        ab2 = synth.ArcBatch(ab.arc_lattice, ab.src, ab.dst, ab.label, torch.from_numpy(w), ab.n_states, ab.vocab)
-        o_logz, _, _, o_post = c_oracle.forward_backward(oracle_batch(ab2))
-        th = theta.to(DEV).requires_grad_(True)
-        logz = nb.lattice_log_partition(p, theta=th)
-        logz.sum().backward()
-        np.testing.assert_allclose(logz.detach().cpu().numpy(), o_logz, rtol=1e-5, atol=1e-5)
-        want = np.zeros(p.vocab)
-        np.add.at(want, ab.label.numpy(), o_post)
-        # (a label's gradient sums thousands of posteriors; the CSR kernels add them with float32 atomics: 2.4e-5 measured
-        # on 200-level bigram cipher lattices -- the tile-stream kernels accumulate in fixed point)
-        np.testing.assert_allclose(th.grad.cpu().numpy(), want, rtol=5e-5, atol=5e-5)
-        kinds = sorted({"tiles" if g.tiles else "sell" if g.sell else "small" if g.small_max_arcs > 0 else
-                        "level" if g.fwd_level_chunks is not None else "csr" for g in p.groups})
-        print(f"ok   {' + '.join(names)}  [{', '.join(kinds)}; {p.n_arcs} arcs, {p.max_levels} levels]", flush=True)
+        print(f"ok   {' + '.join(names)}  {run_case(names, parts)}", flush=True)
     except RuntimeError as e:
         if "shared memory" in str(e):
             refused += 1
@@ -84,26 +130,5 @@ while time.time() - t0 < budget:
     except Exception:  # noqa: BLE001
         fails += 1
         print(f"FAIL {' + '.join(names)}\n{traceback.format_exc()}", flush=True)
-        try:  # which lattices / launch groups carry the posterior error
-            p, sc = ab.to(DEV).pack()
-            logz, alpha, beta, post = nb.lattice_forward_backward(p, arc_scores=sc)
-            _, o_alpha, o_beta, o_post = c_oracle.forward_backward(oracle_batch(ab))
-            ref = o_post[p.arc_origin.cpu().numpy()]
-            got = post.cpu().numpy().astype(np.float64)
-            bad = np.abs(got - ref) > 1e-5 * ref + 1e-7
-            aoff = p.arc_off.cpu().numpy()
-            kind = {}
-            for g in p.groups:
-                for b in g.ids.cpu().tolist():
-                    kind[b] = "tiles" if g.tiles else "sell" if g.sell else "small" if g.small_max_arcs > 0 else "csr/level"
-            for b in range(p.n_lattices):
-                nb_ = int(bad[aoff[b]:aoff[b + 1]].sum())
-                if nb_:
-                    r = ref[aoff[b]:aoff[b + 1]]; d = np.abs(got[aoff[b]:aoff[b + 1]] - r)
-                    i = int(np.argmax(d / (r + 1e-7)))
-                    print(f"   lattice {b} [{kind[b]}] {aoff[b + 1] - aoff[b]} arcs, levels {int(p.n_levels[b])}, state {alpha.dtype}: {nb_} bad arcs, worst ref {r[i]:.3e} got-ref {d[i]:.3e}; "
-                          f"max|alpha|+|beta| {float(np.abs(o_alpha).max() + np.abs(o_beta).max()):.1f}", flush=True)
-        except Exception as e2:  # noqa: BLE001
-            print("   (diagnosis failed:", e2, ")")
 print(f"{n} batches, {fails} failures, {refused} refused for shared memory, {time.time() - t0:.0f} s")
 sys.exit(1 if fails else 0)
