@@ -448,6 +448,39 @@ __global__ void __launch_bounds__(256, NFST_MIN_BLOCKS)
 // fused backward: beta (+ posteriors, dtheta) and/or Viterbi delta + backpointer
 // =====================================================================================
 // LOGS / TROP: semirings; SC / TH: score sources; POST: posteriors (post and/or dtheta).
+// dtheta histogram of one block (= one lattice's arcs): in shared memory the posteriors are accumulated WITHOUT the
+// lattice's gradient scale, in fixed point with native integer atomics (a float add there is a compare-and-swap loop,
+// and thousands of float adds per label lose ~1e-5: measured 2.4e-5 on 200-level bigram cipher lattices); a label's
+// expected count is at most the lattice's level count, so the unit is 2^31 / (levels rounded up to a power of two).
+// Without the shared-memory table (V > NFST_THETA_SMEM_MAX) the scaled posterior goes to dtheta with a float atomic.
+struct Hist {
+  unsigned* fix;  // shared memory, fixed point (or null)
+  float* glob;    // dtheta itself (or null)
+  float scale, inv;
+};
+__device__ __forceinline__ Hist hist_make(unsigned* fix, float* glob, int levels) {
+  Hist h;
+  h.fix = fix;
+  h.glob = glob;
+  const int lv = levels < 1 ? 1 : levels;
+  const float p2 = static_cast<float>(1u << (32 - __clz(lv - 1 > 0 ? lv - 1 : 0)));  // >= levels, a power of two (1 for lv = 1)
+  h.scale = 2147483648.0f / p2;
+  h.inv = p2 / 2147483648.0f;
+  return h;
+}
+// (callers guard the call with `if (h.fix || h.glob)`: the label expression may read an array that only exists with a histogram)
+__device__ __forceinline__ void hist_add(const Hist& h, int lab, float pu, float gscale) {
+  if (h.fix) atomicAdd(&h.fix[lab], __float2uint_rn(pu * h.scale));
+  else if (h.glob) atomicAdd(&h.glob[lab], pu * gscale);
+}
+__device__ __forceinline__ void hist_flush(const Hist& h, float* dtheta, int vocab, float gscale, int tid, int nt) {
+  const float sc = h.inv * gscale;
+  for (int i = tid; i < vocab; i += nt) {
+    const unsigned v = h.fix[i];
+    if (v) atomicAdd(&dtheta[i], static_cast<float>(v) * sc);
+  }
+}
+
 template <typename ST, bool LOGS, bool TROP, bool SC, bool TH, bool POST>
 __global__ void __launch_bounds__(256, NFST_MIN_BLOCKS)
     nfst_bwd_kernel(const nfst_packed_lattices_t L, const int32_t* __restrict__ ids, int W, int cap,
@@ -478,15 +511,12 @@ __global__ void __launch_bounds__(256, NFST_MIN_BLOCKS)
     for (int i = tid; i < L.vocab; i += NT) sth[i] = theta[i];
     th = sth;
   }
-  float* hist = nullptr;
-  if (want_hist) {
-    if (dtheta_smem) {
-      hist = smem_f + plan.dtheta / 4;
-      for (int i = tid; i < L.vocab; i += NT) hist[i] = 0.0f;
-    } else {
-      hist = dtheta;
-    }
+  unsigned* hist_fix = nullptr;
+  if (want_hist && dtheta_smem) {
+    hist_fix = reinterpret_cast<unsigned*>(smem_f + plan.dtheta / 4);
+    for (int i = tid; i < L.vocab; i += NT) hist_fix[i] = 0u;
   }
+  const Hist H = hist_make(hist_fix, want_hist && !dtheta_smem ? dtheta : nullptr, L.level_off[b + 1] - L.level_off[b] - 1);
   ST lz = 0;
   float gscale = 1.0f;
   if (POST) {
@@ -545,9 +575,10 @@ __global__ void __launch_bounds__(256, NFST_MIN_BLOCKS)
         const ST u = static_cast<ST>(w) + beta_of(d);
         lse_push(m, sum, u, neg_inf);
         if (POST) {
-          const float p = ex2_approx(static_cast<float>(am + u) * kLog2e) * gscale;
+          const float pu = ex2_approx(static_cast<float>(am + u) * kLog2e);
+          const float p = pu * gscale;
           if (post) post[base4 + i] = p;
-          if (hist) atomicAdd(&hist[lab], p);
+          if (H.fix || H.glob) hist_add(H, lab, pu, gscale);
         }
       }
       if (TROP) {
@@ -578,9 +609,10 @@ __global__ void __launch_bounds__(256, NFST_MIN_BLOCKS)
         if (POST) {
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
-            const float p = ex2_approx(static_cast<float>(am + u[k]) * kLog2e) * gscale;
+            const float pu = ex2_approx(static_cast<float>(am + u[k]) * kLog2e);
+          const float p = pu * gscale;
             if (post) post[base4 + i + k] = p;
-            if (hist) atomicAdd(&hist[lab[k]], p);
+            if (H.fix || H.glob) hist_add(H, lab[k], pu, gscale);
           }
         }
       }
@@ -674,9 +706,10 @@ __global__ void __launch_bounds__(256, NFST_MIN_BLOCKS)
             const ST u = static_cast<ST>(w) + beta_of(d);
             lse_add(m, sum, u);
             if (POST) {
-              const float p = ex2_approx(static_cast<float>(am + u) * kLog2e) * gscale;
+              const float pu = ex2_approx(static_cast<float>(am + u) * kLog2e);
+          const float p = pu * gscale;
               if (post) post[a] = p;
-              if (hist) atomicAdd(&hist[lab], p);
+              if (H.fix || H.glob) hist_add(H, lab, pu, gscale);
             }
           }
           if (TROP) {
@@ -727,12 +760,7 @@ __global__ void __launch_bounds__(256, NFST_MIN_BLOCKS)
     if (LOGS && logz_bwd) logz_bwd[b] = beta[start];
     if (TROP && vit_score) vit_score[b] = delta[start];
   }
-  if (want_hist && dtheta_smem) {
-    for (int i = tid; i < L.vocab; i += NT) {
-      const float v = hist[i];
-      if (v != 0.0f) atomicAdd(&dtheta[i], v);
-    }
-  }
+  if (want_hist && dtheta_smem) hist_flush(H, dtheta, L.vocab, gscale, tid, NT);
 }
 
 // =====================================================================================
@@ -809,15 +837,12 @@ __global__ void __launch_bounds__(256, 4)
   const int a_lo = L.out_ptr[s_lo], Ab = L.out_ptr[s_lo + Sb] - a_lo;  // arcs are grouped by lattice in both orders
   const int lvl0 = L.level_off[b], nlev = L.level_off[b + 1] - lvl0 - 1;
   const int start = L.start_state[b] - s_lo;
-  float* hist = nullptr;
-  if (want_hist) {
-    if (dtheta_smem) {
-      hist = smem_f + P.hist;
-      for (int i = tid; i < L.vocab; i += NT) hist[i] = 0.0f;
-    } else {
-      hist = dtheta;
-    }
+  unsigned* hist_fix = nullptr;
+  if (want_hist && dtheta_smem) {
+    hist_fix = reinterpret_cast<unsigned*>(smem_f + P.hist);
+    for (int i = tid; i < L.vocab; i += NT) hist_fix[i] = 0u;
   }
+  const Hist H = hist_make(hist_fix, want_hist && !dtheta_smem ? dtheta : nullptr, L.level_off[b + 1] - L.level_off[b] - 1);
 
   NFST_T(t_start);
   // ---- load the lattice (everything made lattice-local); all global loads are independent
@@ -998,9 +1023,10 @@ __global__ void __launch_bounds__(256, 4)
         if (LOGS) {
           u = static_cast<ST>(w) + sB[d];
           if (POST) {
-            const float pz = ex2_approx(static_cast<float>(am + u) * kLog2e) * gscale;
+            const float pzu = ex2_approx(static_cast<float>(am + u) * kLog2e);
+          const float pz = pzu * gscale;
             if (post) post[a_lo + i] = pz;
-            if (hist) atomicAdd(&hist[s_lab[i]], pz);
+            if (H.fix || H.glob) hist_add(H, s_lab[i], pzu, gscale);
           }
         }
         if (TROP) {
@@ -1068,9 +1094,10 @@ __global__ void __launch_bounds__(256, 4)
             if (LOGS) {
               u = static_cast<ST>(w) + sB[d];
               if (POST) {
-                const float pz = ex2_approx(static_cast<float>(am + u) * kLog2e) * gscale;
+                const float pzu = ex2_approx(static_cast<float>(am + u) * kLog2e);
+          const float pz = pzu * gscale;
                 if (post) post[a_lo + i] = pz;
-                if (hist) atomicAdd(&hist[s_lab[i]], pz);
+                if (H.fix || H.glob) hist_add(H, s_lab[i], pzu, gscale);
               }
             }
             if (TROP) {
@@ -1142,10 +1169,7 @@ __global__ void __launch_bounds__(256, 4)
     }
     if (want_hist && dtheta_smem) {
       __syncthreads();
-      for (int i = tid; i < L.vocab; i += NT) {
-        const float v = hist[i];
-        if (v != 0.0f) atomicAdd(&dtheta[i], v);
-      }
+      hist_flush(H, dtheta, L.vocab, gscale, tid, NT);
     }
   }
 }
@@ -1261,23 +1285,22 @@ __global__ void __launch_bounds__(256, 4)
   const int32_t* __restrict__ out_ptr = L.out_ptr;
   const int32_t* __restrict__ dst_out = L.dst_out;
   const int32_t* __restrict__ label_out = L.label_out;
-  float* hist = nullptr;
-  if (want_hist) {
-    if (dtheta_smem) {
-      hist = smem_f;
-      for (int i = tid; i < L.vocab; i += NT) hist[i] = 0.0f;
-      __syncthreads();
-    } else {
-      hist = dtheta;
-    }
+  unsigned* hist_fix = nullptr;
+  if (want_hist && dtheta_smem) {
+    hist_fix = reinterpret_cast<unsigned*>(smem_f);
+    for (int i = tid; i < L.vocab; i += NT) hist_fix[i] = 0u;
+    __syncthreads();
   }
   ST lz = 0;
   float gscale = 1.0f;
+  int hist_levels = 1;
   if (POST) {
     const int b = __ldg(chunk_lat + blockIdx.x);
     lz = logz[b];
     if (grad_logz) gscale = grad_logz[b];
+    hist_levels = L.level_off[b + 1] - L.level_off[b] - 1;
   }
+  const Hist H = hist_make(hist_fix, want_hist && !dtheta_smem ? dtheta : nullptr, hist_levels);
   auto visit = [&](int a, ST am, ST& m, float& sum, float& bt, int& bi) {
     const int d = __ldg(dst_out + a);
     float w = SC ? __ldg(arc_scores + a) : 0.0f;
@@ -1288,9 +1311,10 @@ __global__ void __launch_bounds__(256, 4)
       const ST u = static_cast<ST>(w) + beta[d];
       lse_push(m, sum, u, neg_inf);
       if (POST) {
-        const float p = ex2_approx(static_cast<float>(am + u) * kLog2e) * gscale;
+        const float pu = ex2_approx(static_cast<float>(am + u) * kLog2e);
+          const float p = pu * gscale;
         if (post) post[a] = p;
-        if (hist) atomicAdd(&hist[lab], p);
+        if (H.fix || H.glob) hist_add(H, lab, pu, gscale);
       }
     }
     if (TROP) {
@@ -1318,9 +1342,10 @@ __global__ void __launch_bounds__(256, 4)
       if (POST) {
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-          const float p = ex2_approx(static_cast<float>(am + u[q]) * kLog2e) * gscale;
+          const float pu = ex2_approx(static_cast<float>(am + u[q]) * kLog2e);
+          const float p = pu * gscale;
           if (post) post[a + q] = p;
-          if (hist) atomicAdd(&hist[lab[q]], p);
+          if (H.fix || H.glob) hist_add(H, lab[q], pu, gscale);
         }
       }
     }
@@ -1401,9 +1426,10 @@ __global__ void __launch_bounds__(256, 4)
           const ST u = static_cast<ST>(w) + beta[d];
           lse_add(m, sum, u);
           if (POST) {
-            const float p = ex2_approx(static_cast<float>(am + u) * kLog2e) * gscale;
+            const float pu = ex2_approx(static_cast<float>(am + u) * kLog2e);
+          const float p = pu * gscale;
             if (post) post[a] = p;
-            if (hist) atomicAdd(&hist[lab], p);
+            if (H.fix || H.glob) hist_add(H, lab, pu, gscale);
           }
         }
         if (TROP) {
@@ -1439,10 +1465,7 @@ __global__ void __launch_bounds__(256, 4)
   }
   if (want_hist && dtheta_smem) {
     __syncthreads();
-    for (int i = tid; i < L.vocab; i += NT) {
-      const float v = hist[i];
-      if (v != 0.0f) atomicAdd(&dtheta[i], v);
-    }
+    hist_flush(H, dtheta, L.vocab, gscale, tid, NT);
   }
 }
 
