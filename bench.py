@@ -474,6 +474,13 @@ def main():
         dist.barrier()
     torch.cuda.synchronize()
     t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if world > 1:
+        # ... and once more on the DEVICE timeline: the hosts leave dist.barrier() up to a millisecond or two apart (one
+        # rank of eight entered 1.6 ms late in a 12 ms region: the other seven then spend that skew waiting at every loss
+        # all-reduce and read 0.09 ms/step "between kernels"); a 4-byte all-reduce that the current stream waits for makes
+        # every rank's start event fire when the LAST rank has arrived, while the early hosts already enqueue their steps
+        gate = torch.zeros(1, device=dev)
+        dist.all_reduce(gate)
     h0 = time.perf_counter()
     t_start.record()
     for i in range(a.steps):
