@@ -610,6 +610,7 @@ def main():
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
+            dist.all_reduce(torch.zeros(1, device=dev))  # the start events aligned on the device timeline, as above
         q0, q1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         q0.record()
         for _ in range(a.steps):
