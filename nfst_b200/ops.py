@@ -59,7 +59,7 @@ def resolve_state_dtype(packed: PackedLattices, state_dtype="auto") -> torch.dty
     batches with a lattice deeper than F64_DEPTH = 96 levels -- F64_DEPTH_PLAIN = 32 for lattices outside the
     column-major layouts, whose kernels form posteriors as exp(alpha + w + beta - logZ) from float32 log-values
     rounded at every level: random batches measured up to 2e-5 on 40-63-level edit lattices and 3e-5 on 43-level
-    cipher lattices (|alpha| + |beta| = 260) with float32 state (tools/fuzz_gpu.py) -- and float32 otherwise.  The
+    cipher lattices (|alpha| + |beta| = 260) with float32 state (tests/fuzz/fuzz_gpu.py) -- and float32 otherwise.  The
     column-major kernels take posteriors from per-state conditionals and a fixed-point flow instead, which does not
     accumulate that rounding: 5e-6 at 64 levels.  float64 state costs the small-lattice kernel 17 % at B = 32 and
     50 % at B = 4096 (shared memory per lattice); ``state_dtype=torch.float32`` buys that back where 2e-5 is enough.

@@ -1,12 +1,12 @@
 """Random (x, y) pairs through the on-device lattice construction (construct.edit_lattices) against the host restatement
 (oracle/edit_lattice_oracle.py) and the C oracle: sizes, chains between grid states, logZ, best path.  Test
-infrastructure (imports oracle/ and tests/).  python tools/fuzz_construct.py [seconds] [seed]"""
+infrastructure (imports oracle/ and tests/).  python tests/fuzz/fuzz_construct.py [seconds] [seed]"""
 import os
 import sys
 import time
 import traceback
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
 

@@ -1,13 +1,13 @@
 """Random batches of the reference's dense [S, V] tables (tests/lattice_gen.py) through the drop-in calls against the
 numpy oracle (test infrastructure: imports oracle/): compute_beta(emission, transition, theta, k) -- dense scan, device
 packer, backward kernel, expansion to beta[B*k, S] in real space -- on collate()-padded batches, ExactJointProb.forward
-with the best path, and the walker's exact samples.  python tools/fuzz_dense.py [seconds] [seed]"""
+with the best path, and the walker's exact samples.  python tests/fuzz/fuzz_dense.py [seconds] [seed]"""
 import os
 import sys
 import time
 import traceback
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
 

@@ -1,13 +1,13 @@
 """Random mixed batches through every execution model against the C oracle (test infrastructure: imports oracle/ and
 the parity helpers of tests/): transliteration / SNIPS / cipher / random-DAG lattices of random sizes concatenated into
 one batch, forward-backward (logZ, alpha, beta, posteriors: the tests' tolerances), Viterbi (bit-exact scores, equal
-paths) and the theta-mode gradient.  python tools/fuzz_gpu.py [seconds] [seed]"""
+paths) and the theta-mode gradient.  python tests/fuzz/fuzz_gpu.py [seconds] [seed]"""
 import os
 import sys
 import time
 import traceback
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
 

@@ -1,13 +1,13 @@
 """Random batches through the sampling-loop kernels and the beta-hat recurrence against their oracles (test
 infrastructure: imports oracle/): sample_paths -- every sampled row is a start->sink path, log q = score - logZ (so the
 k-sample IWAE estimate of estimatros.py:32-44 equals logZ with zero variance) on small-lattice, CSR and column-major
-packs; lattice_beta_hat (scorers.py:732-747, Wh != 0) vs the float64 numpy port.  python tools/fuzz_walk.py [seconds] [seed]"""
+packs; lattice_beta_hat (scorers.py:732-747, Wh != 0) vs the float64 numpy port.  python tests/fuzz/fuzz_walk.py [seconds] [seed]"""
 import os
 import sys
 import time
 import traceback
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
