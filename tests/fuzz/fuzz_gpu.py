@@ -16,8 +16,7 @@ from nfst_b200 import synth  # noqa: E402
 from oracle import c_oracle  # noqa: E402
 from tests.test_gpu_parity import DEV, oracle_batch  # noqa: E402
 
-budget = float(sys.argv[1]) if len(sys.argv) > 1 else 90.0
-rng = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 0)
+rng = np.random.default_rng(0)  # main() / the caller reseeds: fuzz_gpu.rng = np.random.default_rng(seed)
 
 
 def cat(parts):
@@ -113,22 +112,29 @@ def run_case(names, parts):
     return f"[{', '.join(kinds)}; {how}, {mode}, state {str(alpha.dtype) if False else out[1].dtype}; {p.n_arcs} arcs, {p.max_levels} levels]"
 
 
-t0 = time.time()
-n = fails = refused = 0
-while time.time() - t0 < budget:
-    names, parts = zip(*[part() for _ in range(int(rng.integers(1, 4)))])
-    n += 1
-    try:
-        print(f"ok   {' + '.join(names)}  {run_case(names, parts)}", flush=True)
-    except RuntimeError as e:
-        if "shared memory" in str(e):
-            refused += 1
-            print(f"REFUSED {' + '.join(names)}: {e}", flush=True)
-        else:
+def main(budget: float, seed: int) -> int:
+    global rng
+    rng = np.random.default_rng(seed)
+    t0 = time.time()
+    n = fails = refused = 0
+    while time.time() - t0 < budget:
+        names, parts = zip(*[part() for _ in range(int(rng.integers(1, 4)))])
+        n += 1
+        try:
+            print(f"ok   {' + '.join(names)}  {run_case(names, parts)}", flush=True)
+        except RuntimeError as e:
+            if "shared memory" in str(e):
+                refused += 1
+                print(f"REFUSED {' + '.join(names)}: {e}", flush=True)
+            else:
+                fails += 1
+                print(f"FAIL {' + '.join(names)}\n{traceback.format_exc()}", flush=True)
+        except Exception:  # noqa: BLE001
             fails += 1
             print(f"FAIL {' + '.join(names)}\n{traceback.format_exc()}", flush=True)
-    except Exception:  # noqa: BLE001
-        fails += 1
-        print(f"FAIL {' + '.join(names)}\n{traceback.format_exc()}", flush=True)
-print(f"{n} batches, {fails} failures, {refused} refused for shared memory, {time.time() - t0:.0f} s")
-sys.exit(1 if fails else 0)
+    print(f"{n} batches, {fails} failures, {refused} refused for shared memory, {time.time() - t0:.0f} s")
+    return 1 if fails else 0
+
+
+if __name__ == "__main__":
+    sys.exit(main(float(sys.argv[1]) if len(sys.argv) > 1 else 90.0, int(sys.argv[2]) if len(sys.argv) > 2 else 0))
