@@ -660,7 +660,11 @@ __global__ void __launch_bounds__(256)
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n_arcs;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
     const int ls = level[gsrc[i]];
-    if (ls >= 0 && atomicMax(&level[gdst[i]], ls + 1) < ls + 1) moved = true;
+    if (ls < 0) continue;
+    // levels only grow: a plain read that already shows ls + 1 or more settles the arc without an atomic (after the
+    // first sweeps that is nearly every arc); a stale smaller value only costs the atomic it would have cost anyway
+    const int64_t d = gdst[i];
+    if (level[d] <= ls && atomicMax(&level[d], ls + 1) < ls + 1) moved = true;
   }
   if (__any_sync(0xffffffffu, moved) && (threadIdx.x & 31) == 0) *changed = 1;
 }
