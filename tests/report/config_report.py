@@ -1,6 +1,6 @@
 """Throughput + parity over the five BASELINE.json configs on one GPU (not the bench line).
 
-    python tools/config_report.py [--quick] > profiles/rN_configs.txt
+    python tests/report/config_report.py [--quick] > profiles/rN_configs.txt
 
 For every config: pack time, forward+fused-backward (beta + posteriors) and Viterbi+backtrace
 time (CUDA events, 3 warm-ups, L2 flushed between iterations when the inputs fit in L2),
@@ -12,7 +12,7 @@ import os
 import sys
 import time
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
 

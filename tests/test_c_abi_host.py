@@ -157,9 +157,8 @@ def test_device_entry_fails_with_a_status_not_a_crash_when_there_is_no_gpu(lib):
 
 
 def test_product_package_never_imports_the_oracle():
-    """oracle/ is test infrastructure: nothing under nfst_b200/ may import, link or execute it."""
-    pkg = os.path.join(ROOT, "nfst_b200")
-    for dirpath, _, files in os.walk(pkg):
+    """oracle/ is test infrastructure: nothing under nfst_b200/ (or tools/) may import, link or execute it."""
+    for dirpath, _, files in list(os.walk(os.path.join(ROOT, "nfst_b200"))) + list(os.walk(os.path.join(ROOT, "tools"))):
         for fn in files:
             if fn.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
                 with open(os.path.join(dirpath, fn)) as f:
