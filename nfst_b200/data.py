@@ -34,6 +34,81 @@ def load_fsa_from_npz(npz_fname: str, wfst_name=None, vocab_size=None, pad=None)
         return tuple(l[k] for k in DENSE_KEYS)
 
 
+def fst_arc_list(machine, final_zero=None):
+    """Arc list of an OpenFst-style acceptor as ``get_state_mask_pynini`` reads it (``scorers.py:1005-1032``):
+    ``(N, src[A], ilabel[A], nextstate[A], weight[A] float64)`` with every arc into a FINAL state redirected to the
+    sink row ``N = machine.num_states()`` (``:1023-1025``).  ``machine`` needs ``start() / num_states() /
+    arcs(state) / final(state) / weight_type()`` -- a ``pynini.Fst`` or anything shaped like one; ``final_zero`` is the
+    semiring zero that marks non-final states (default: ``pynini.Weight.zero(machine.weight_type())``, as the
+    reference computes it, ``:1002``).  Same assertions as the reference: the start is state 0 (``:1005``), one arc
+    per (state, label) (``:1030``)."""
+    if final_zero is None:
+        from pynini import Weight  # the reference's own dependency for this function (scorers.py:999)
+
+        final_zero = Weight.zero(machine.weight_type())
+    assert machine.start() == 0
+    n = int(machine.num_states())
+    is_final = np.array([machine.final(s) != final_zero for s in range(n)], dtype=bool)
+    src, lab, nxt, wgt = [], [], [], []
+    for state in range(n):
+        for arc in machine.arcs(state):
+            src.append(state)
+            lab.append(int(arc.ilabel))
+            nxt.append(int(arc.nextstate))
+            wgt.append(float(arc.weight))
+    src, lab, nxt = (np.asarray(a, dtype=np.int64) for a in (src, lab, nxt))
+    key = src * (int(lab.max()) + 1 if lab.size else 1) + lab
+    assert np.unique(key).size == key.size  # "assert arc.ilabel not in ilabel_set"
+    nxt = np.where(is_final[nxt], n, nxt) if nxt.size else nxt
+    return n, src, lab, nxt, np.asarray(wgt, dtype=np.float64)
+
+
+def get_state_mask_pynini(machine, vocab_size: int, pad: int, to_numpy: bool = False, weighted: bool = False, final_zero=None):
+    """``FSAGRUScorer.get_state_mask_pynini`` (``scorers.py:995-1035``) -- the function that DEFINES the lattice
+    tables -- without the per-arc Python writes: ``emission[N+1, V]`` (bool, or float64 log-weights ``-arc.weight``
+    with ``-inf`` = no arc when ``weighted``), ``transition[N+1, V]`` int64 next state; row ``N`` is the sink with its
+    ``pad`` self-loop (``:1011-1016``).  (The reference's ``weighted=True`` branch needs ``np.float``, gone from
+    current numpy; the dtype it named is float64.)"""
+    n, src, lab, nxt, wgt = fst_arc_list(machine, final_zero)
+    if weighted:
+        emission = np.full((n + 1, vocab_size), -np.inf, dtype=np.float64)
+        emission[n, pad] = 0.0
+        emission[src, lab] = -wgt
+    else:
+        emission = np.zeros((n + 1, vocab_size), dtype=bool)
+        emission[n, pad] = True
+        emission[src, lab] = True
+    transition = np.zeros((n + 1, vocab_size), dtype=np.int64)
+    transition[n, pad] = n
+    transition[src, lab] = nxt
+    if to_numpy:
+        return emission, transition
+    return torch.from_numpy(emission), torch.from_numpy(transition)
+
+
+def pack_fsts(machines: Sequence, vocab_size: int, weighted: bool = False, device=None, final_zero=None, **pack_kw) -> PackedLattices:
+    """A batch of acceptors straight to the packed layout, skipping the dense tables (fewer than 1 % of their cells
+    are arcs): the arcs ``get_state_mask_pynini`` would write, filtered by the DP's edge rule -- a cell is an arc iff
+    its next state is neither 0 nor the row itself (``scorers.py:704-716``) -- and packed with ``pack_arcs``.  Same
+    lattices, state for state, as ``pack_dense`` of the collated tables; ``weighted`` keeps ``-arc.weight`` as static
+    arc scores (``scorers.py:1026-1027``)."""
+    lat, src, dst, lab, sc, ns = [], [], [], [], [], []
+    for b, m in enumerate(machines):
+        n, s, l, t, w = fst_arc_list(m, final_zero)
+        keep = (t != 0) & (t != s)
+        lat.append(np.full(int(keep.sum()), b, dtype=np.int64))
+        src.append(s[keep]); dst.append(t[keep]); lab.append(l[keep]); sc.append(-w[keep]); ns.append(n + 1)
+    if lab and max((int(l.max()) for l in lab if l.size), default=0) >= vocab_size:
+        raise ValueError("label out of range")
+    dev = torch.device(device) if device is not None else torch.device("cpu")
+    cat = lambda xs: torch.from_numpy(np.concatenate(xs)).to(dev)  # noqa: E731
+    static = cat(sc).to(torch.float32) if weighted else None
+    from .pack import pack_arcs
+
+    return pack_arcs(cat(lat), cat(src), cat(dst), cat(lab), torch.tensor(ns, dtype=torch.int64, device=dev), vocab_size,
+                     static_scores=static, **pack_kw)
+
+
 def _group_fields(g: LaunchGroup):
     return {k: v for k, v in g.__dict__.items() if not isinstance(v, torch.Tensor) and v is not None}
 

@@ -247,6 +247,28 @@ def gen_stateful():
     print("stateful_sample.npz:", steps, "steps,", N, "rows; mean log q", float(summed.mean()))
 
 
+def gen_state_mask():
+    """The reference's table-format function ``FSAGRUScorer.get_state_mask_pynini`` (scorers.py:995-1035), unmodified,
+    on OpenFst-shaped stand-ins (tests/lattice_gen.FakeFst; ``pynini.Weight`` replaced by FakeWeight in the stub
+    module -- pynini itself is absent).  Unweighted only: the weighted branch names ``np.float`` (:1008), which current
+    numpy no longer has."""
+    from tests.lattice_gen import FakeFst, FakeWeight, random_fst_arrays
+
+    ns = rh.load()
+    sys.modules["pynini"].Weight = FakeWeight
+    rng = np.random.default_rng(20260404)
+    out = {"vocab": np.int64(V), "n_cases": np.int64(8)}
+    for i, n in enumerate([3, 4, 5, 7, 10, 16, 25, 40]):
+        arrs = random_fst_arrays(rng, n, V)
+        em, tr = ns.FSAGRUScorer.get_state_mask_pynini(FakeFst(*arrs), V, PAD, to_numpy=True)
+        for k, a in zip(("n", "src", "ilabel", "nextstate", "weight", "is_final"), arrs):
+            out[f"{k}_{i}"] = np.asarray(a)
+        out[f"emission_{i}"] = em
+        out[f"transition_{i}"] = tr
+    np.savez_compressed(os.path.join(OUT, "state_mask.npz"), **out)
+    print("state_mask.npz: 8 machines")
+
+
 if __name__ == "__main__":
     if not rh.available():
         raise SystemExit("reference not mounted; golden vectors can only be regenerated in the build container")
@@ -255,3 +277,4 @@ if __name__ == "__main__":
     gen_iwae()
     gen_walk()
     gen_stateful()
+    gen_state_mask()

@@ -104,3 +104,87 @@ def chain_with_skips(n: int, vocab: int):
     t[n, EOS] = sink
     t[sink, PAD] = sink
     return t != 0, t
+
+
+# ---- OpenFst-shaped acceptors without OpenFst (what get_state_mask_pynini reads, scorers.py:995-1035) ----
+class FakeWeight:
+    """The part of ``pynini.Weight`` that ``get_state_mask_pynini`` touches: ``zero(type)``, ``!=``, ``float()``."""
+
+    def __init__(self, value: float):
+        self.value = float(value)
+
+    @classmethod
+    def zero(cls, weight_type):
+        assert weight_type == "tropical"
+        return cls(float("inf"))
+
+    def __eq__(self, other):
+        return isinstance(other, FakeWeight) and self.value == other.value
+
+    def __ne__(self, other):
+        return not self.__eq__(other)
+
+    def __float__(self):
+        return self.value
+
+
+class FakeArc:
+    def __init__(self, ilabel, nextstate, weight):
+        self.ilabel, self.olabel, self.nextstate, self.weight = int(ilabel), int(ilabel), int(nextstate), FakeWeight(weight)
+
+
+class FakeFst:
+    """``start() / num_states() / arcs(s) / final(s) / weight_type()`` over plain arrays."""
+
+    def __init__(self, n_states, src, ilabel, nextstate, weight, is_final):
+        self.n = int(n_states)
+        self.rows = [[] for _ in range(self.n)]
+        for s, l, t, w in zip(src, ilabel, nextstate, weight):
+            self.rows[int(s)].append(FakeArc(l, t, w))
+        self.is_final = np.asarray(is_final, dtype=bool)
+
+    def start(self):
+        return 0
+
+    def num_states(self):
+        return self.n
+
+    def weight_type(self):
+        return "tropical"
+
+    def arcs(self, state):
+        return iter(self.rows[state])
+
+    def final(self, state):
+        return FakeWeight(0.0 if self.is_final[state] else float("inf"))
+
+
+def random_fst_arrays(rng: np.random.Generator, n_states: int, vocab: int):
+    """Arrays of a random acyclic acceptor the way the offline pipeline leaves them: state 0 the start with one
+    ``bos`` arc, one arc per (state, label), states without outgoing arcs final (reached by ``eos``), a few extra
+    final states that also have outgoing arcs, one arc back into state 0 and one self-loop (both vanish under the
+    DP's edge rule)."""
+    n = max(int(n_states), 3)
+    src, lab, nxt = [0], [BOS], [1]
+    for s in range(1, n - 1):
+        k = int(rng.integers(1, 4))
+        labels = rng.choice(np.arange(FIRST_LABEL, vocab), size=k, replace=False)
+        for l in labels:
+            d = int(rng.integers(s + 1, n))
+            src.append(s); lab.append(EOS if d == n - 1 else int(l)); nxt.append(d)
+    # one arc per (state, label): eos may have been drawn twice for a state
+    seen, keep = set(), []
+    for i, (s, l) in enumerate(zip(src, lab)):
+        if (s, l) not in seen:
+            seen.add((s, l)); keep.append(i)
+    src, lab, nxt = ([a[i] for i in keep] for a in (src, lab, nxt))
+    mid = int(rng.integers(1, n - 1))
+    for extra in ((mid, 4, 0), (mid, 5, mid)):  # into the start / a self-loop
+        if (extra[0], extra[1]) not in seen:
+            src.append(extra[0]); lab.append(extra[1]); nxt.append(extra[2])
+    is_final = np.zeros(n, dtype=bool)
+    is_final[n - 1] = True
+    if n > 4:
+        is_final[int(rng.integers(2, n - 1))] = True  # arcs into it are redirected to the sink row too
+    w = np.round(rng.uniform(0.0, 4.0, size=len(src)), 3)
+    return n, np.asarray(src), np.asarray(lab), np.asarray(nxt), w, is_final
