@@ -230,3 +230,29 @@ def test_c_abi_pack_dense_equals_the_python_path():
         assert torch.equal(got[k].to(torch.int64), getattr(ref, k).to(torch.int64)), k
     totals, got = run(cap - 1)
     assert totals[4] == 5 and got is None
+
+
+def test_pack_fsts_on_the_device_matches_the_oracle():
+    """``data.pack_fsts``: OpenFst-shaped acceptors -> packed batch on the device (row a1 without the dense tables,
+    ``scorers.py:995-1035``): logZ with theta scores and with the machines' own weights against the numpy oracle."""
+    from nfst_b200 import data as nd
+    from oracle import lattice_oracle as lo
+    from tests.lattice_gen import PAD, FakeFst, FakeWeight, random_fst_arrays
+
+    rng = np.random.default_rng(12)
+    V = 24
+    zero = FakeWeight.zero("tropical")
+    machines = [FakeFst(*random_fst_arrays(rng, int(n), V)) for n in rng.integers(3, 40, size=9)]
+    theta = rng.normal(size=V).astype(np.float32)
+    p = nd.pack_fsts(machines, V, device=DEV, final_zero=zero)
+    pw = nd.pack_fsts(machines, V, weighted=True, device=DEV, final_zero=zero)
+    assert p.device.type == "cuda" and pw.static_scores is not None
+    logz = nb.lattice_log_partition(p, theta=torch.from_numpy(theta).to(DEV)).cpu().numpy()
+    logz_w = nb.lattice_log_partition(pw).cpu().numpy()  # the static scores (-arc.weight) are the arc scores
+    for b, m in enumerate(machines):
+        em, tr = nd.get_state_mask_pynini(m, V, PAD, to_numpy=True, weighted=True, final_zero=zero)
+        s, l, d, sc = lo.arcs_from_dense(tr, em)
+        want = lo.forward_backward(tr.shape[0], s, d, theta[l].astype(np.float64))[0]
+        want_w = lo.forward_backward(tr.shape[0], s, d, sc.astype(np.float32).astype(np.float64))[0]
+        assert abs(logz[b] - want) <= 1e-5 * max(1.0, abs(want)), (b, logz[b], want)
+        assert abs(logz_w[b] - want_w) <= 1e-5 * max(1.0, abs(want_w)), (b, logz_w[b], want_w)
