@@ -113,10 +113,11 @@ def test_stale_or_foreign_cache_is_rebuilt(examples, tmp_path):
     assert torch.equal(ds[0].packed.label_out, good.label_out)
     # a dense file newer than its cache wins
     nd.load_packed(path)
-    old = os.path.getmtime(path)
-    os.utime(names[0] + ".npz", (old + 10, old + 10))
+    past = os.path.getmtime(path) - 1000.0
+    os.utime(path, (past, past))
+    os.utime(names[0] + ".npz", (past + 500.0, past + 500.0))
     ds[0]
-    assert os.path.getmtime(path) > old
+    assert os.path.getmtime(path) > past + 500.0  # rewritten
 
 
 def test_collate_of_cached_examples_equals_the_reference_collate_then_pack(examples):
