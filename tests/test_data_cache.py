@@ -147,3 +147,25 @@ def test_collate_of_cached_examples_equals_the_reference_collate_then_pack(examp
     # a batch of one is the example's own pack
     one, g1, p1 = nd.collate(batch[3:4], PAD)
     assert one is batch[3].packed and g1.shape == (1, len(arrays[3][4])) and p1.shape == (1, len(arrays[3][5]))
+
+
+def test_dataset_under_a_multi_worker_dataloader(examples):
+    """As the reference drives its dataset (``dataset_reader.py:148-155``: DataLoader workers + ``collate_fn``): the packed
+    batches cross the process boundary intact, epoch after epoch (the second epoch reads the caches)."""
+    import functools
+
+    names, arrays = examples
+    ds = nd.LatticeDataset(names[:4], V, PAD)
+    dl = torch.utils.data.DataLoader(ds, batch_size=2, num_workers=2, collate_fn=functools.partial(nd.collate, pad=PAD),
+                                     multiprocessing_context="spawn", persistent_workers=True)
+    want = [nd.collate([ds[0], ds[1]], PAD), nd.collate([ds[2], ds[3]], PAD)]
+    for epoch in range(2):
+        got = list(dl)
+        assert len(got) == 2
+        for (p, gs, ps), (q, gs_w, ps_w) in zip(got, want):
+            assert torch.equal(gs, gs_w) and torch.equal(ps, ps_w)
+            assert (p.n_lattices, p.n_states, p.n_arcs) == (q.n_lattices, q.n_states, q.n_arcs)
+            for f in q.tensors():
+                assert torch.equal(getattr(p, f), getattr(q, f)), f
+            assert [nd._group_fields(g) for g in p.groups] == [nd._group_fields(g) for g in q.groups]
+            check_structure(p)
