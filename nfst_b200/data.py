@@ -25,13 +25,19 @@ PACKED_FORMAT = 2  # bump when the packed layout changes: stale caches are rebui
 
 def load_fsa_from_npz(npz_fname: str, wfst_name=None, vocab_size=None, pad=None) -> Tuple[np.ndarray, ...]:
     """The six arrays of a reference example, in the reference's order and with its error for a missing file
-    (``preprocess_util.py:293-310``).  ``wfst_name`` (a weighted proposal FST read through pynini,
-    ``:314-322``) is outside this package's scope."""
+    (``preprocess_util.py:293-310``).  With ``wfst_name`` the weighted proposal FST is read through pynini and its
+    weighted tables are appended, as the reference does (``:314-322``) -- pynini is that branch's own dependency; the
+    tables come from ``get_state_mask_pynini`` below."""
     assert os.path.exists(npz_fname), f"{npz_fname} does not exist! Please run preprocess_npz.py first."
-    if wfst_name is not None:
-        raise NotImplementedError("weighted proposal FSTs are read with pynini by the reference; pass the dense tables instead")
     with np.load(npz_fname) as l:
-        return tuple(l[k] for k in DENSE_KEYS)
+        to_return = tuple(l[k] for k in DENSE_KEYS)
+    if wfst_name is not None:
+        from pynini import Fst
+
+        loaded_fst = Fst.read(wfst_name)
+        matrices = get_state_mask_pynini(loaded_fst, vocab_size, pad, to_numpy=True, weighted=True)
+        to_return = tuple(list(to_return) + list(matrices))
+    return to_return
 
 
 def fst_arc_list(machine, final_zero=None):

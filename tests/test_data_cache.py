@@ -61,8 +61,39 @@ def test_load_fsa_from_npz_returns_the_six_arrays_in_the_reference_order(example
     missing = str(tmp_path / "nope.npz")
     with pytest.raises(AssertionError, match="does not exist! Please run preprocess_npz.py first."):
         nd.load_fsa_from_npz(missing, None, V, PAD)
-    with pytest.raises(NotImplementedError):
+
+
+def test_load_fsa_from_npz_appends_the_weighted_proposal_tables(examples, monkeypatch):
+    """The ``wfst_name`` branch (preprocess_util.py:314-322): ``pynini.Fst.read`` + the weighted tables.  pynini is absent
+    here, so a stand-in module supplies ``Fst.read`` / ``Weight`` (tests/lattice_gen.py); without any pynini the branch
+    fails on its import, as the reference's does."""
+    import sys
+    import types
+
+    from tests.lattice_gen import FakeFst, FakeWeight, random_fst_arrays
+
+    names, arrays = examples
+    monkeypatch.delitem(sys.modules, "pynini", raising=False)
+    with pytest.raises(ImportError):
         nd.load_fsa_from_npz(names[0] + ".npz", "proposal.fst", V, PAD)
+    machine = FakeFst(*random_fst_arrays(np.random.default_rng(2), 9, V))
+    read = []
+
+    class Fst:
+        @staticmethod
+        def read(path):
+            read.append(path)
+            return machine
+
+    fake = types.ModuleType("pynini")
+    fake.Fst, fake.Weight = Fst, FakeWeight
+    monkeypatch.setitem(sys.modules, "pynini", fake)
+    got = nd.load_fsa_from_npz(names[0] + ".npz", "proposal.fst", V, PAD)
+    assert read == ["proposal.fst"] and len(got) == 8
+    for g, w in zip(got[:6], arrays[0]):
+        assert np.array_equal(g, w)
+    em, tr = nd.get_state_mask_pynini(machine, V, PAD, to_numpy=True, weighted=True)
+    assert got[6].dtype == np.float64 and np.array_equal(got[6], em) and np.array_equal(got[7], tr)
 
 
 def test_dataset_packs_once_then_reads_the_cache(examples):
