@@ -156,8 +156,9 @@ def load_packed(path: str, device="cpu") -> PackedLattices:
 class PackedExample:
     """What ``LatticeDataset.__getitem__`` returns: the numerator lattice packed, and ``gs`` / ``ps`` as read."""
 
-    def __init__(self, packed: PackedLattices, gs: np.ndarray, ps: np.ndarray, name: str):
+    def __init__(self, packed: PackedLattices, gs: np.ndarray, ps: np.ndarray, name: str, proposal_tables=None):
         self.packed, self.gs, self.ps, self.name = packed, gs, ps, name
+        self.proposal_tables = proposal_tables  # (emission float64 [N+1, V], transition int64) of the weighted proposal FST, if any
 
 
 class LatticeDataset(torch.utils.data.Dataset):
@@ -168,10 +169,20 @@ class LatticeDataset(torch.utils.data.Dataset):
     the dense tables and writes ``<name>.packed.npz`` (in ``cache_dir`` if given); later accesses read that."""
 
     def __init__(self, list_of_machines: Sequence[str], vocab_size: Optional[int] = None, pad: Optional[int] = None,
-                 cache_dir: Optional[str] = None, weighted: Optional[bool] = None):
+                 cache_dir: Optional[str] = None, weighted: Optional[bool] = None, *,
+                 list_of_wfst_proposals: Optional[Sequence[str]] = None):
         self.l = list(list_of_machines)
+        self.proposals = None if list_of_wfst_proposals is None else list(list_of_wfst_proposals)  # dataset_reader.py:18,23
         self.vocab_size, self.pad = vocab_size, pad
         self.cache_dir, self.weighted = cache_dir, weighted
+
+    def _proposal(self, index: int):
+        """the weighted proposal tables of example ``index`` (``dataset_reader.py:33-36`` -> ``preprocess_util.py:314-322``)"""
+        if self.proposals is None:
+            return None
+        from pynini import Fst
+
+        return get_state_mask_pynini(Fst.read(self.proposals[index]), self.vocab_size, self.pad, to_numpy=True, weighted=True)
 
     def __len__(self) -> int:
         return len(self.l)
@@ -188,7 +199,7 @@ class LatticeDataset(torch.utils.data.Dataset):
             try:
                 with np.load(dense) as l:
                     gs, ps = l["gs"], l["ps"]
-                return PackedExample(load_packed(cache), gs, ps, name)
+                return PackedExample(load_packed(cache), gs, ps, name, self._proposal(index))
             except (ValueError, OSError, KeyError):
                 pass  # stale or unreadable cache: rebuild it (the reference re-serialises unreadable files too, tr.py:135-141)
         ne, nt, _, _, gs, ps = load_fsa_from_npz(dense, None, self.vocab_size, self.pad)
@@ -198,7 +209,7 @@ class LatticeDataset(torch.utils.data.Dataset):
         if self.cache_dir is not None:
             os.makedirs(self.cache_dir, exist_ok=True)
         save_packed(cache, packed)
-        return PackedExample(packed, gs, ps, name)
+        return PackedExample(packed, gs, ps, name, self._proposal(index))
 
 
 def pad_sequence_1d(seqs: List[np.ndarray], padding_value: int) -> torch.Tensor:

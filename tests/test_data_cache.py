@@ -200,3 +200,27 @@ def test_dataset_under_a_multi_worker_dataloader(examples):
                 assert torch.equal(getattr(p, f), getattr(q, f)), f
             assert [nd._group_fields(g) for g in p.groups] == [nd._group_fields(g) for g in q.groups]
             check_structure(p)
+
+
+def test_dataset_is_constructed_the_way_the_reference_constructs_fsadataset(examples, monkeypatch):
+    """``FSADataset(current_split, vocab_size=..., pad=..., list_of_wfst_proposals=...)`` (dataset_reader.py:98-103): the
+    same keywords work; with proposals every example also carries the weighted proposal tables."""
+    import sys
+    import types
+
+    from tests.lattice_gen import FakeFst, FakeWeight, random_fst_arrays
+
+    names, _ = examples
+    ds = nd.LatticeDataset(names[:2], vocab_size=V, pad=PAD, list_of_wfst_proposals=None)
+    assert ds[0].proposal_tables is None
+    machines = {f"p{i}.fst": FakeFst(*random_fst_arrays(np.random.default_rng(30 + i), 7 + i, V)) for i in range(2)}
+    fake = types.ModuleType("pynini")
+    fake.Fst = type("Fst", (), {"read": staticmethod(lambda path: machines[path])})
+    fake.Weight = FakeWeight
+    monkeypatch.setitem(sys.modules, "pynini", fake)
+    ds = nd.LatticeDataset(names[:2], vocab_size=V, pad=PAD, list_of_wfst_proposals=list(machines))
+    for i in range(2):
+        for ex in (ds[i], ds[i]):  # packed now, from the cache next
+            em, tr = ex.proposal_tables
+            want = nd.get_state_mask_pynini(machines[f"p{i}.fst"], V, PAD, to_numpy=True, weighted=True)
+            assert np.array_equal(em, want[0]) and np.array_equal(tr, want[1])
