@@ -223,8 +223,24 @@ def pad_sequence_1d(seqs: List[np.ndarray], padding_value: int) -> torch.Tensor:
 
 def collate(batch: List[PackedExample], pad: int, device=None):
     """Counterpart of ``T9FSADataModule.collate`` (``dataset_reader.py:175-186``): (packed batch, gs[B, Lx],
-    ps[B, Ly]).  No dense table is padded or copied; the per-example packs are concatenated."""
+    ps[B, Ly]) -- plus the padded proposal tables when the examples carry them.  No numerator table is padded or
+    copied; the per-example packs are concatenated."""
     packed = concat_packed([b.packed for b in batch]) if len(batch) > 1 else batch[0].packed
     if device is not None:
         packed = packed.to(device)
-    return packed, pad_sequence_1d([b.gs for b in batch], pad), pad_sequence_1d([b.ps for b in batch], pad)
+    out = (packed, pad_sequence_1d([b.gs for b in batch], pad), pad_sequence_1d([b.ps for b in batch], pad))
+    if batch[0].proposal_tables is not None:
+        # the two weighted proposal tables ride along dense, padded like every array of the reference's batch --
+        # with the pad id, the float emission table included (quirk Q5)
+        out = out + tuple(pad_tables([b.proposal_tables[i] for b in batch], pad) for i in (0, 1))
+    return out
+
+
+def pad_tables(tables: List[np.ndarray], padding_value) -> torch.Tensor:
+    """``Utils.pad_sequence(batch_first=True)`` (``preprocess_util.py:368-392``) for ``[S_b, V]`` tables: ``[B, max S_b, V]``
+    filled with ``padding_value`` in the tables' own dtype."""
+    n = max(t.shape[0] for t in tables)
+    out = np.full((len(tables), n) + tables[0].shape[1:], padding_value, dtype=tables[0].dtype)
+    for i, t in enumerate(tables):
+        out[i, : t.shape[0], ...] = t
+    return torch.from_numpy(out)

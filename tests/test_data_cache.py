@@ -224,3 +224,11 @@ def test_dataset_is_constructed_the_way_the_reference_constructs_fsadataset(exam
             em, tr = ex.proposal_tables
             want = nd.get_state_mask_pynini(machines[f"p{i}.fst"], V, PAD, to_numpy=True, weighted=True)
             assert np.array_equal(em, want[0]) and np.array_equal(tr, want[1])
+    # collate: the proposal tables ride along, padded with the pad id like every array of the reference's batch (Q5)
+    out = nd.collate([ds[0], ds[1]], PAD)
+    assert len(out) == 5
+    tabs = [nd.get_state_mask_pynini(machines[f"p{i}.fst"], V, PAD, to_numpy=True, weighted=True) for i in range(2)]
+    for k, got in ((0, out[3]), (1, out[4])):
+        want = reference_collate([(t[k],) * 6 for t in tabs], PAD)[0]
+        assert got.dtype == torch.from_numpy(want).dtype and np.array_equal(got.numpy(), want)
+    assert out[3].dtype == torch.float64 and float(out[3][0, -1, 0]) == float(PAD)  # the float table too
