@@ -115,6 +115,52 @@ def pack_fsts(machines: Sequence, vocab_size: int, weighted: bool = False, devic
                      static_scores=static, **pack_kw)
 
 
+def packed_to_dense(packed: PackedLattices, pad: int, weighted: bool = False):
+    """The way back: ``(emission[B, S, V], transition[B, S, V])`` in the format ``collate`` hands the reference's modules
+    (``scorers.py:995-1035`` tables, padded with the pad id, ``dataset_reader.py:175-186``) -- for feeding lattices that
+    never had dense tables (``construct.edit_lattices``, ``pack_fsts``, ``pack_arcs``) to the reference's own consumers
+    (``FSAGRUScorer.set_masks``, ``scorers.py:877-885``).  Rows are the PACKED local state ids (level order: the start
+    is row 0, no arc enters it; every state without outgoing arcs gets the sink's ``pad`` self-loop, ``:1013-1016``);
+    ``weighted`` writes the static arc scores as float log-weights with ``-inf`` for "no arc" (``:1011-1013``).  Needs
+    one arc per (state, label), like the tables themselves (``:1030``)."""
+    B, V = packed.n_lattices, packed.vocab
+    state_off = packed.state_off.to(torch.int64)
+    n_b = state_off[1:] - state_off[:-1]
+    S = int(n_b.max())
+    dev = packed.device
+    out_ptr = packed.out_ptr[: packed.n_states + 1].to(torch.int64)
+    deg = out_ptr[1:] - out_ptr[:-1]
+    src = torch.repeat_interleave(torch.arange(packed.n_states, device=dev), deg)
+    lat = torch.bucketize(src, state_off[1:], right=True)
+    dst = packed.dst_out[: packed.n_arcs].to(torch.int64)
+    lab = packed.label_out[: packed.n_arcs].to(torch.int64)
+    cell = (lat * S + (src - state_off[lat])) * V + lab
+    if cell.numel() and int(torch.unique(cell).numel()) != int(cell.numel()):
+        raise ValueError("two arcs of one state share a label: the dense tables hold one arc per (state, label)")
+    transition = torch.zeros(B * S * V, dtype=torch.int64, device=dev)
+    transition[cell] = dst - state_off[lat]
+    if weighted:
+        if packed.static_scores is None:
+            raise ValueError("weighted tables need a batch packed with static arc scores")
+        emission = torch.full((B * S * V,), float("-inf"), dtype=torch.float64, device=dev)
+        emission[cell] = packed.static_scores[: packed.n_arcs].to(torch.float64)
+        on = 0.0
+    else:
+        emission = torch.zeros(B * S * V, dtype=torch.bool, device=dev)
+        emission[cell] = True
+        on = True
+    sinks = torch.nonzero(deg == 0).squeeze(1)
+    sl = torch.bucketize(sinks, state_off[1:], right=True)
+    scell = (sl * S + (sinks - state_off[sl])) * V + int(pad)
+    transition[scell] = sinks - state_off[sl]
+    emission[scell] = on
+    transition, emission = transition.view(B, S, V), emission.view(B, S, V)
+    padded = torch.arange(S, device=dev)[None, :] >= n_b[:, None]  # collate's rows: the pad id everywhere (quirk Q5)
+    transition[padded] = int(pad)
+    emission[padded] = float(pad) if weighted else True
+    return emission, transition
+
+
 def _group_fields(g: LaunchGroup):
     return {k: v for k, v in g.__dict__.items() if not isinstance(v, torch.Tensor) and v is not None}
 

@@ -83,3 +83,43 @@ def test_pack_fsts_equals_pack_dense_of_the_collated_reference_tables():
         s, l, d, sc = lo.arcs_from_dense(tr, em)
         logz = lo.forward_backward(tr.shape[0], s, d, sc.astype(np.float32).astype(np.float64))[0]
         assert abs(beta[_np(wdirect.start_state)[b]] - logz) < 1e-9
+
+
+def test_packed_to_dense_is_the_inverse_of_pack_dense():
+    """``data.packed_to_dense``: a packed batch back to the tables ``collate`` hands the reference's modules -- the same
+    lattices (arc for arc under the DP's edge rule), sinks with their pad self-loop, padding rows full of the pad id."""
+    cases = list(_cases())
+    V = cases[0][0]
+    machines = [FakeFst(*arrs) for _, arrs, _, _ in cases]
+    for weighted in (False, True):
+        p = nd.pack_fsts(machines, V, weighted=weighted, final_zero=ZERO)
+        em, tr = nd.packed_to_dense(p, PAD, weighted=weighted)
+        B, S, _ = tr.shape
+        state_off = _np(p.state_off)
+        assert B == p.n_lattices and S == int(np.diff(state_off).max())
+        assert em.dtype == (torch.float64 if weighted else torch.bool)
+        for b in range(B):
+            n = state_off[b + 1] - state_off[b]
+            t = tr[b, :n].numpy()
+            s, l, d, sc = lo.arcs_from_dense(t, em[b, :n].numpy())
+            a0, a1 = _np(p.arc_off)[b], _np(p.arc_off)[b + 1]
+            out_ptr = _np(p.out_ptr)
+            want_src = np.repeat(np.arange(p.n_states), np.diff(out_ptr[: p.n_states + 1]))[a0:a1] - state_off[b]
+            assert np.array_equal(s, want_src) and np.array_equal(l, _np(p.label_out)[a0:a1])
+            assert np.array_equal(d, _np(p.dst_out)[a0:a1] - state_off[b])
+            if weighted:
+                np.testing.assert_array_equal(sc.astype(np.float32), p.static_scores.numpy()[a0:a1])
+            assert not np.any(d == 0)  # nothing enters the start row
+            sink_rows = np.nonzero(np.diff(out_ptr[state_off[b]: state_off[b + 1] + 1]) == 0)[0]
+            assert np.array_equal(t[sink_rows, PAD], sink_rows)  # the pad self-loop (scorers.py:1013-1016)
+            assert bool((tr[b, n:] == PAD).all()) and bool((em[b, n:] == (float(PAD) if weighted else True)).all())
+        # and back again: the same packed batch
+        q = nb.pack_dense(em, tr, weighted=weighted)
+        for f in ("state_off", "level_off", "level_ptr", "out_ptr", "dst_out", "label_out", "start_state", "sinks"):
+            assert torch.equal(getattr(p, f), getattr(q, f)), f
+        if weighted:
+            assert torch.equal(p.static_scores, q.static_scores)
+    dup = nb.pack_arcs(torch.zeros(2, dtype=torch.int64), torch.tensor([0, 0]), torch.tensor([1, 2]), torch.tensor([5, 5]),
+                       torch.tensor([3]), V)
+    with pytest.raises(ValueError, match="share a label"):
+        nd.packed_to_dense(dup, PAD)
