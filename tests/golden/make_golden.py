@@ -269,6 +269,46 @@ def gen_state_mask():
     print("state_mask.npz: 8 machines")
 
 
+EDIT_PAIRS = [([7, 8, 9], [10, 11]), ([7], [12, 12, 13]), ([8, 9, 7, 7], [10, 13, 11, 12]), ([], [10]), ([9, 8], [])]
+
+
+def edit_tables(x, y, sub):
+    """dense tables of the edit lattice of (x, y) the way the PRODUCT writes them: host construction (the test oracle of
+    nfst_edit_lattice_arcs) -> pack_arcs -> data.packed_to_dense."""
+    import nfst_b200 as nb
+    from nfst_b200 import data as nd
+    from oracle import edit_lattice_oracle as elo
+
+    arcs, n = elo.edit_lattice(x, y, bos=1, eos=2, input_mark=4, output_mark=5, sub_mark=6 if sub else None)
+    src, lab, dst = (torch.tensor([a[i] for a in arcs]) for i in (0, 1, 2))
+    p = nb.pack_arcs(torch.zeros(len(arcs), dtype=torch.int64), src, dst, lab, torch.tensor([n]), V)
+    return nd.packed_to_dense(p, PAD)
+
+
+def gen_edit_tables():
+    """The unmodified reference's compute_beta_per_sample (float64, Wh = 0 and Wh != 0) on edit lattices that THIS repo
+    constructs and writes as dense tables (data.packed_to_dense): the reference accepts them, and its beta pins
+    construction + table format + DP end to end."""
+    m0 = rh.make_scorer(H, V, seed=31, zero_wh=True)
+    m1 = rh.make_scorer(H, V, seed=32, zero_wh=False)
+    out = {"vocab": np.int64(V), "hid": np.int64(H), "n_cases": np.int64(2 * len(EDIT_PAIRS))}
+    for k, v in params_of(m0).items():
+        out[f"p0_{k}"] = v
+    for k, v in params_of(m1).items():
+        out[f"p1_{k}"] = v
+    i = 0
+    with rh.default_dtype(torch.float64), torch.no_grad():
+        for sub in (False, True):
+            for x, y in EDIT_PAIRS:
+                em, tr = edit_tables(x, y, sub)
+                out[f"tr_{i}"] = tr[0].numpy()
+                out[f"beta0_{i}"] = m0.compute_beta_per_sample(tr[0].int()).numpy()
+                out[f"beta1_{i}"] = m1.compute_beta_per_sample(tr[0].int()).numpy()
+                i += 1
+    np.savez_compressed(os.path.join(OUT, "edit_tables.npz"), **out)
+    print("edit_tables.npz:", i, "lattices")
+
+
 if __name__ == "__main__":
     if not rh.available():
         raise SystemExit("reference not mounted; golden vectors can only be regenerated in the build container")
@@ -278,3 +318,4 @@ if __name__ == "__main__":
     gen_walk()
     gen_stateful()
     gen_state_mask()
+    gen_edit_tables()
