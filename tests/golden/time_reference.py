@@ -111,5 +111,38 @@ def main():
               f"log beta[start] vs the float64 oracle: max rel. diff {worst:.1e}", flush=True)
 
 
+def parallel_leg(B: int = 4, hid: int = 8):
+    """``compute_beta()`` -> ``compute_beta_parallel`` (scorers.py:753-875), the batched form the sampler calls, on the
+    first ``B`` lattices of config 1 collate-padded.  At the shipped H = 256 its ``[B, S, S, H]`` work tensors need tens of
+    GB, so this leg runs at H = 8 and says so; one process, torch's own threads."""
+    import torch
+
+    from nfst_b200 import synth
+    from oracle import lattice_oracle as lo
+    from oracle import ref_harness as rh
+
+    tabs = dense_tables(synth.transliteration_batch(32, seed=0))[:B]
+    tr = lo.collate_pad(tabs, synth.PAD)
+    m = rh.make_scorer(hid, V, seed=7, zero_wh=True, double=False)
+    theta = rh.arc_theta(m).double().numpy()
+    arcs = sum(int(np.count_nonzero((t != 0) & (t != np.arange(t.shape[0])[:, None]))) for t in tabs)
+    with torch.no_grad():
+        m.set_masks(emission=torch.from_numpy(tr != 0), transition=torch.from_numpy(tr))
+        m.set_k(1)
+        t0 = time.perf_counter()
+        beta = m.compute_beta()
+        wall = time.perf_counter() - t0
+    worst = 0.0
+    for b, t in enumerate(tabs):
+        s, l, d, _ = lo.arcs_from_dense(t)
+        logz = lo.forward_backward(t.shape[0], s, d, theta[l])[0]
+        worst = max(worst, abs(float(beta[b, 0].log()) - logz) / max(1.0, abs(logz)))
+    assert worst < 1e-3, worst
+    print(f"config1, first {B} lattices through compute_beta() = compute_beta_parallel (H={hid}, not the shipped 256: memory), "
+          f"tables [{B}, {tr.shape[1]}, {V}], {arcs} arcs: {wall:.2f} s = {arcs / wall:.0f} arcs/s "
+          f"({torch.get_num_threads()} torch threads); log beta[start] vs the float64 oracle: max rel. diff {worst:.1e}", flush=True)
+
+
 if __name__ == "__main__":
     main()
+    parallel_leg()
