@@ -43,3 +43,22 @@ def test_small_groups_run_in_one_launch_only_while_resident_at_once():
     many = concat_packed([synth.transliteration_batch(512, seed=4 + o).pack()[0] for o in range(0, 4096, 512)])
     g = many.groups[0]
     assert g.n == 4096 and not ops._small_fused_fits(g, many.vocab, torch.float32)
+
+
+def test_algorithmic_bytes_are_the_survey_figures():
+    """fwd+bwd = 20 B per arc + 20 B per state; Viterbi = 8 A + 12 S + 8 |path| -- the numerators of
+    every roofline fraction bench.py prints."""
+    import numpy as np
+    import torch
+
+    import nfst_b200 as nb
+    from oracle import lattice_oracle as lo
+    from tests.lattice_gen import PAD, random_mark_lattice
+
+    rng = np.random.default_rng(0)
+    tabs = [random_mark_lattice(rng, 7, 24)[1] for _ in range(3)]
+    p = nb.pack_dense(None, torch.from_numpy(lo.collate_pad(tabs, PAD)))
+    A, S = p.n_arcs, p.n_states
+    assert A > 0 and p.algorithmic_bytes_fwd_bwd() == 20 * A + 20 * S
+    assert p.algorithmic_bytes_viterbi() == 8 * A + 12 * S
+    assert p.algorithmic_bytes_viterbi(17) == 8 * A + 12 * S + 8 * 17
