@@ -110,7 +110,7 @@ __global__ void __launch_bounds__(kThreads)
                       const int32_t* __restrict__ end_g, const Kept K, int32_t* __restrict__ stats,
                       int32_t* __restrict__ totals) {
   if (totals[4]) return;  // pack_ranges_kernel met an arc that points outside its lattice
-  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int b = blockIdx.x, tid = threadIdx.x;
   const int s0 = R.state_off[b], S0 = R.state_off[b + 1] - s0;
   const int a0 = R.arc_off[b], A0 = R.arc_off[b + 1] - a0;
   int* const level = pack_smem;             // [capS]
