@@ -516,7 +516,7 @@ __global__ void __launch_bounds__(NT_MAX, NT_MAX == 128 ? SELL_PULL_MIN_BLOCKS_1
         for (int k = 0; k < NC; ++k) mf = fmaxf(mf, tf[k]);
         float e[KU];
         float sum = 0.0f;
-        const float mfl = -mf * kLog2e;
+        [[maybe_unused]] const float mfl = -mf * kLog2e;  // float32 state only
         for_columns<0, NC>(ac.d, deg, lane, [&](auto kc, bool, int) {
           constexpr int k = decltype(kc)::value;
           // idle lanes / -inf arcs: exp(-huge) = 0.  float32 state: one fused multiply-add per arc; the rounding of
