@@ -17,7 +17,7 @@ from typing import List, Optional, Sequence, Tuple
 import numpy as np
 import torch
 
-from .pack import LaunchGroup, PackedLattices, build_groups, concat_packed, pack_dense
+from .pack import LaunchGroup, PackedLattices, build_groups, concat_packed, pack_arcs, pack_dense
 
 DENSE_KEYS = ("num_emission", "num_transition", "denom_emission", "denom_transition", "gs", "ps")
 PACKED_FORMAT = 2  # bump when the packed layout changes: stale caches are rebuilt
@@ -109,8 +109,6 @@ def pack_fsts(machines: Sequence, vocab_size: int, weighted: bool = False, devic
     dev = torch.device(device) if device is not None else torch.device("cpu")
     cat = lambda xs: torch.from_numpy(np.concatenate(xs)).to(dev)  # noqa: E731
     static = cat(sc).to(torch.float32) if weighted else None
-    from .pack import pack_arcs
-
     return pack_arcs(cat(lat), cat(src), cat(dst), cat(lab), torch.tensor(ns, dtype=torch.int64, device=dev), vocab_size,
                      static_scores=static, **pack_kw)
 
