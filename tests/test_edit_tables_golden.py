@@ -51,3 +51,18 @@ def test_reference_beta_on_product_built_tables():
             assert abs(np.exp(z0) - n_paths) < 1e-6 * n_paths
             i += 1
     assert i == int(g["n_cases"])
+
+
+def test_label_scores_is_the_reference_message_weight_at_wh_zero():
+    """``scorer.label_scores`` (what ``patch_compute_beta`` feeds the kernels when ``Wh = 0``): theta[l] = W.tanh(Wx e_l + b),
+    ``scorers.py:732-738`` -- with it the oracle reproduces the reference's beta of the golden above."""
+    from nfst_b200.scorer import label_scores
+
+    g = np.load(G)
+    P0 = {k: torch.from_numpy(g["p0_" + k]) for k in ("emb", "Wx", "W", "bias")}
+    theta = label_scores(P0["emb"], P0["Wx"], P0["W"], P0["bias"])
+    assert theta.dtype == torch.float32 and theta.shape == (int(g["vocab"]),)
+    t = g["tr_0"]
+    src, lab, dst, _ = lo.arcs_from_dense(t)
+    beta = lo.beta_log(t.shape[0], src, dst, theta.double().numpy()[lab])
+    np.testing.assert_allclose(np.exp(beta), g["beta0_0"], rtol=2e-6, atol=0)  # float32 theta
