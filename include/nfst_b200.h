@@ -18,6 +18,21 @@
  *                           the reference cannot produce, quirk Q7), the per-label
  *                           gradient d logZ / d theta (WFSTScorer, scorers.py:1663-1687)
  *                           and the tropical-semiring Viterbi recursion + backpointers.
+ *   nfst_fwd_bwd_small_f32  the same two passes (and Viterbi) for lattices of the size nFST builds, whole lattice
+ *                           in shared memory, one launch (scorers.py:692-751, :753-856 as above).
+ *   nfst_tile_pull_f32 / nfst_tile_flow_f32
+ *                           the same recurrence and the arc posteriors for wide lattices stored as a per-warp tile
+ *                           stream (the bench workload); same reference functions as nfst_bwd_fused_f32.
+ *   nfst_viterbi_f32 / nfst_viterbi_paths_f32
+ *                           tropical-semiring pass (+ backtrace in the same call): the exact counterpart of
+ *                           "the sample with the highest weight" (src/modules/lightning.py:474-479); tie rule =
+ *                           torch.argmax's first index over the dense row, as the reference's consumer gathers it
+ *                           (scorers.py:586-590).
+ *   nfst_compact_paths / nfst_pad_paths
+ *                           the best path in ragged form / in the reference's padded int64 sample layout
+ *                           (what JointProb.forward(return_samples=True) returns, lightning.py:474-479).
+ *   nfst_level_sweeps       topological levels of an arc list: the order the reference gets implicitly from its
+ *                           per-state message counters (scorers.py:741-749, :846-852).
  *   nfst_backtrace          best-path read-out; replaces best-of-k-samples selection
  *                           (src/modules/lightning.py:474-479) reached from
  *                           src/decode/decoder.py:77-79.
@@ -42,6 +57,11 @@
  *                           the dense-table edge rule `t != 0 and t != i`
  *                           (scorers.py:704-716, :764-776) over collate()-padded
  *                           transition[B,S,V] int64 tables (util/dataset_reader.py:175-186).
+ *
+ *   nfst_abi_version, nfst_last_error_string, nfst_device_info, nfst_*_smem_bytes, nfst_*_workspace_bytes,
+ *   nfst_tile_debug_read    housekeeping of the boundary itself (version, error text -- the reference raises Python
+ *                           exceptions, e.g. scorers.py:719,878-879,1005,1030 --, device check, buffer sizes the
+ *                           caller must provide, range-check counters of a debug build); no reference counterpart.
  *
  * Every entry point returns 0 on success or a negative nfst_status; a human-readable
  * message for the last failure on the calling thread is at nfst_last_error_string().
